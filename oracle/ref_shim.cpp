@@ -1,0 +1,148 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, imported by, or executed from the product path.
+//
+// Thin extern "C" shim that instantiates the UNMODIFIED reference templates from
+// /root/reference/include (header-only; nothing is copied into this repo) so tests can
+// call the real RichDEM CPU implementation through ctypes.  Built by oracle/Makefile into
+// oracle/_ref/libref_richdem.so (git-ignored, travels to the GPU box with the snapshot).
+//
+// Every entry point takes plain row-major host buffers (i = y*W + x), wraps them unowned in
+// richdem::Array2D (reference: include/richdem/common/Array2D.hpp:344-352) and calls the
+// reference function named in the comment beside it.
+#include <richdem/common/Array2D.hpp>
+#include <richdem/common/Array3D.hpp>
+#include <richdem/depressions/depressions.hpp>
+#include <richdem/depressions/Zhou2016.hpp>
+#include <richdem/depressions/Barnes2014.hpp>
+#include <richdem/flats/flats.hpp>
+#include <richdem/flats/find_flats.hpp>
+#include <richdem/flowmet/d8_flowdirs.hpp>
+#include <richdem/methods/d8_methods.hpp>
+#include <richdem/methods/flow_accumulation.hpp>
+
+#include <cstdint>
+#include <cstring>
+
+using namespace richdem;
+
+extern "C" {
+
+// depressions/depressions.hpp:13-21 -> depressions/Zhou2016.hpp:125-191
+void ref_fill_depressions_d8_f32(float *dem, int w, int h) {
+  Array2D<float> a(dem, w, h);
+  FillDepressions<Topology::D8>(a);
+}
+
+// depressions/Zhou2016.hpp:125-191 (the function pyrichdem binds, pywrapper.hpp:32)
+void ref_priority_flood_zhou2016_f32(float *dem, int w, int h) {
+  Array2D<float> a(dem, w, h);
+  PriorityFlood_Zhou2016(a);
+}
+
+// depressions/Barnes2014.hpp:230-304 (independent second oracle)
+void ref_priority_flood_barnes2014_f32(float *dem, int w, int h) {
+  Array2D<float> a(dem, w, h);
+  PriorityFlood_Barnes2014<Topology::D8>(a);
+}
+
+// depressions/Barnes2014.hpp:136-198
+void ref_priority_flood_original_f32(float *dem, int w, int h) {
+  Array2D<float> a(dem, w, h);
+  PriorityFlood_Original<Topology::D8>(a);
+}
+
+// flats/find_flats.hpp:28-69
+void ref_find_flats_f32(const float *dem, int w, int h, float nodata, int8_t *flats) {
+  Array2D<float> a(const_cast<float *>(dem), w, h);
+  a.setNoData(nodata);
+  Array2D<int8_t> f;
+  FindFlats(a, f);
+  std::memcpy(flats, f.data(), (size_t)w * h);
+}
+
+// flats/Barnes2014.hpp:398-467 ; labels are order-dependent ids (only the partition matters)
+void ref_get_flat_mask_f32(const float *dem, int w, int h, float nodata, int32_t *mask,
+                           int32_t *labels) {
+  Array2D<float> a(const_cast<float *>(dem), w, h);
+  a.setNoData(nodata);
+  Array2D<int32_t> m, l;
+  GetFlatMask(a, m, l);
+  std::memcpy(mask, m.data(), sizeof(int32_t) * (size_t)w * h);
+  std::memcpy(labels, l.data(), sizeof(int32_t) * (size_t)w * h);
+}
+
+// flats/flats.hpp:21-28
+void ref_resolve_flats_epsilon_f32(float *dem, int w, int h, float nodata) {
+  Array2D<float> a(dem, w, h);
+  a.setNoData(nodata);
+  ResolveFlatsEpsilon(a);
+}
+
+// flowmet/d8_flowdirs.hpp:96-123
+void ref_d8_flow_directions_f32(const float *dem, int w, int h, float nodata, uint8_t *dirs) {
+  Array2D<float> a(const_cast<float *>(dem), w, h);
+  a.setNoData(nodata);
+  Array2D<uint8_t> d;
+  d8_flow_directions(a, d);
+  std::memcpy(dirs, d.data(), (size_t)w * h);
+}
+
+// methods/d8_methods.hpp:47-139  (direction grid NoData = 255, constants.hpp:76)
+void ref_d8_flow_accum_u8_i32(const uint8_t *dirs, int w, int h, int32_t *area) {
+  Array2D<uint8_t> d(const_cast<uint8_t *>(dirs), w, h);
+  d.setNoData(FLOWDIR_NO_DATA);
+  Array2D<int32_t> a;
+  d8_flow_accum(d, a);
+  std::memcpy(area, a.data(), sizeof(int32_t) * (size_t)w * h);
+}
+
+// same function on an int32 direction grid with an explicit NoData (the tests/flow_accum
+// fixtures are loaded as int32 with NODATA_value -1, tests/tests.cpp:135-146)
+void ref_d8_flow_accum_i32_i32(const int32_t *dirs, int w, int h, int32_t nodata, int32_t *area) {
+  Array2D<int32_t> d(const_cast<int32_t *>(dirs), w, h);
+  d.setNoData(nodata);
+  Array2D<int32_t> a;
+  d8_flow_accum(d, a);
+  std::memcpy(area, a.data(), sizeof(int32_t) * (size_t)w * h);
+}
+
+// flowmet/OCallaghan1984.hpp:81-84 ; props is [y][x][9] float (Array3D.hpp:203-206)
+void ref_fm_d8_f32(const float *dem, int w, int h, float nodata, float *props) {
+  Array2D<float> a(const_cast<float *>(dem), w, h);
+  a.setNoData(nodata);
+  Array3D<float> p(props, w, h);  // unowned wrap, Array3D.hpp:118
+  FM_D8(a, p);
+}
+
+// flowmet/Tarboton1997.hpp:14-144
+void ref_fm_tarboton_f32(const float *dem, int w, int h, float nodata, float *props) {
+  Array2D<float> a(const_cast<float *>(dem), w, h);
+  a.setNoData(nodata);
+  Array3D<float> p(props, w, h);
+  FM_Tarboton(a, p);
+}
+
+// methods/flow_accumulation_generic.hpp:33-100 ; props NoData = -2 (constants.hpp:85)
+void ref_flow_accumulation_props_f64(const float *props, int w, int h, double *accum) {
+  Array3D<float> p(const_cast<float *>(props), w, h);
+  p.setNoData(NO_DATA_GEN);
+  Array2D<double> a(accum, w, h);
+  FlowAccumulation(p, a);
+}
+
+// methods/flow_accumulation.hpp:27
+void ref_fa_d8_f32_f64(const float *dem, int w, int h, float nodata, double *accum) {
+  Array2D<float> a(const_cast<float *>(dem), w, h);
+  a.setNoData(nodata);
+  Array2D<double> acc(accum, w, h);
+  FA_D8(a, acc);
+}
+
+// methods/flow_accumulation.hpp:16
+void ref_fa_tarboton_f32_f64(const float *dem, int w, int h, float nodata, double *accum) {
+  Array2D<float> a(const_cast<float *>(dem), w, h);
+  a.setNoData(nodata);
+  Array2D<double> acc(accum, w, h);
+  FA_Tarboton(a, acc);
+}
+
+}  // extern "C"
