@@ -1,0 +1,183 @@
+/*
+ * richdem_b200.h -- C ABI of librichdem_b200.so (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for RichDEM's depression-filling / flat-resolution /
+ * flow-routing hot path.  Every entry point below replaces one reference function template
+ * (cited as file:line relative to the RichDEM source tree) for the dtypes the Python API
+ * uses on this path: elevations float32, accumulation float64, proportions float32 x 9,
+ * direction grids uint8.  Buffers are plain row-major rasters, i = y*width + x
+ * (reference include/richdem/common/Array2D.hpp:592-595) -- i.e. exactly what
+ * richdem::Array2D<T>::data() or a C-contiguous numpy array hands over.
+ *
+ * Conventions
+ *   - All functions return 0 on success, non-zero on failure; rdb200_last_error() then
+ *     returns a static, thread-local, human-readable message (CUDA errors included).
+ *     There is NO CPU fallback: without a usable sm_100 device every compute call fails.
+ *   - "Host" entry points take host pointers, copy to the device, compute, and copy the
+ *     result back before returning; nothing is retained after return (same ownership rules
+ *     as the reference: caller-owned, mutated in place).
+ *   - "dev" entry points take device pointers on the current device and run on the
+ *     library's stream; they let callers chain stages without leaving HBM.
+ *   - Calls are synchronous from the caller's point of view and must be made from one
+ *     thread at a time (the reference holds the GIL for the whole call as well).
+ *   - D8 neighbour numbering is the reference's (include/richdem/common/constants.hpp:44-45):
+ *         2 3 4
+ *         1 0 5
+ *         8 7 6
+ */
+#ifndef RICHDEM_B200_H_
+#define RICHDEM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDB200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define RDB200_API __attribute__((visibility("default")))
+#else
+#define RDB200_API
+#endif
+
+/* ---- library lifetime ------------------------------------------------------------- */
+
+/* Selects CUDA device `device` (>=0) for this process, creates the stream and workspace.
+ * Idempotent for the same device.  Compute calls lazily do rdb200_init(current device). */
+RDB200_API int rdb200_init(int device);
+/* Releases the workspace, stream and cached descriptors. */
+RDB200_API void rdb200_shutdown(void);
+RDB200_API const char *rdb200_last_error(void);
+RDB200_API int rdb200_version(void);
+
+/* Counters of the most recent call (for benchmarks / roofline accounting). */
+typedef struct rdb200_stats {
+  int64_t cells;             /* width*height of the raster processed                       */
+  int64_t kernel_launches;   /* CUDA kernels launched by the call                          */
+  int64_t fill_rounds;       /* fill: global sweep rounds (one persistent launch each)     */
+  int64_t fill_tile_visits;  /* fill: tiles loaded+relaxed, summed over rounds             */
+  int64_t fill_tile_cells;   /* fill: cells per tile (visits*tile_cells = cells swept)     */
+  int64_t fill_tile_iters;   /* fill: in-shared-memory relaxation passes, summed           */
+  int64_t accum_rounds;      /* accumulation: frontier rounds                              */
+  int64_t flat_bfs_levels;   /* flats: BFS levels (away + towards)                         */
+  int64_t flat_cells_raised; /* flats: cells whose elevation changed                       */
+  double ms_total;           /* device time of the whole call (CUDA events)                */
+  double ms_main_kernel;     /* device time summed over launches of the dominant kernel    */
+  double ms_h2d, ms_d2h;     /* host entry points only                                     */
+} rdb200_stats;
+RDB200_API int rdb200_get_stats(rdb200_stats *out);
+
+/* Tunables (0 keeps the default).  fill_max_iters caps in-tile relaxation passes per tile
+ * visit (default: relax each tile to its local fixed point). */
+RDB200_API int rdb200_set_param(const char *name, int64_t value);
+
+/* ---- host entry points: the reference functions they replace ----------------------- */
+
+/* richdem::FillDepressions<Topology::D8>(Array2D<float>&)
+ *   include/richdem/depressions/depressions.hpp:13-21 -> PriorityFlood_Zhou2016,
+ *   include/richdem/depressions/Zhou2016.hpp:125-191 (pyrichdem: rdFillDepressionsD8,
+ *   wrappers/pyrichdem/src/pywrapper.hpp:32).  In place.  NoData is not special (as in the
+ *   reference).  Result is bit-identical to the reference. */
+RDB200_API int rdb200_fill_depressions_d8_f32(float *dem, int32_t width, int32_t height);
+
+/* richdem::ResolveFlatsEpsilon(Array2D<float>&)
+ *   include/richdem/flats/flats.hpp:21-28 (GetFlatMask + ResolveFlatsEpsilon_Barnes2014,
+ *   include/richdem/flats/Barnes2014.hpp:398-467, 496-550); pyrichdem rdResolveFlatsEpsilon
+ *   (pywrapper.hpp:37).  In place; bit-identical. */
+RDB200_API int rdb200_resolve_flats_epsilon_f32(float *dem, int32_t width, int32_t height, float nodata);
+
+/* richdem::GetFlatMask (include/richdem/flats/Barnes2014.hpp:398-467): the int32 increment
+ * mask and a flat id per cell (0 = not in a drainable flat; ids are arbitrary but equal
+ * within one flat -- the reference's ids are traversal-order dependent too). */
+RDB200_API int rdb200_get_flat_mask_f32(const float *dem, int32_t *flat_mask, int32_t *labels, int32_t width,
+                             int32_t height, float nodata);
+
+/* richdem::d8_flow_directions(const Array2D<float>&, Array2D<uint8_t>&)
+ *   include/richdem/flowmet/d8_flowdirs.hpp:96-123 (+ d8_FlowDir :32-74).  Codes 0..8,
+ *   255 = NoData (include/richdem/common/constants.hpp:76).  Bit-identical. */
+RDB200_API int rdb200_d8_flow_directions_f32(const float *dem, uint8_t *flowdirs, int32_t width,
+                                  int32_t height, float nodata);
+
+/* richdem::d8_flow_accum(const Array2D<uint8_t>&, Array2D<int32_t>&)
+ *   include/richdem/methods/d8_methods.hpp:47-139.  NoData direction = 255 -> area -1. */
+RDB200_API int rdb200_d8_flow_accum_u8_i32(const uint8_t *flowdirs, int32_t *area, int32_t width,
+                                int32_t height);
+
+/* richdem::FM_D8 / FM_OCallaghan<D8>(const Array2D<float>&, Array3D<float>&)
+ *   include/richdem/flowmet/OCallaghan1984.hpp:13-77,81-84.  props9 is [y][x][9] float
+ *   (include/richdem/common/Array3D.hpp:203-206).  Bit-identical. */
+RDB200_API int rdb200_fm_d8_f32(const float *dem, float *props9, int32_t width, int32_t height, float nodata);
+
+/* richdem::FM_Tarboton / FM_Dinfinity  include/richdem/flowmet/Tarboton1997.hpp:14-149.
+ * Facet choice identical; proportions within 1 float ulp (device atan2 vs libm). */
+RDB200_API int rdb200_fm_tarboton_f32(const float *dem, float *props9, int32_t width, int32_t height,
+                           float nodata);
+
+/* richdem::FlowAccumulation(const Array3D<float>&, Array2D<double>&)
+ *   include/richdem/methods/flow_accumulation_generic.hpp:33-100 (pyrichdem
+ *   "FlowAccumulation", wrappers/pyrichdem/src/pywrapper.cpp:50).  accum arrives holding the
+ *   per-cell weights and leaves holding the accumulation; NoData cells (props slot 0 == -2)
+ *   become -1.  Flow out of raster-edge cells is ignored (the reference FM_* never emit it). */
+RDB200_API int rdb200_flow_accumulation_props_f64(const float *props9, double *accum_inout, int32_t width,
+                                       int32_t height);
+
+/* richdem::FA_D8 / FA_Tarboton(=FA_Dinfinity)(const Array2D<float>&, Array2D<double>&)
+ *   include/richdem/methods/flow_accumulation.hpp:27,16,17 (pywrapper.hpp:64,55,56).
+ *   Fused: the 36 B/cell proportions array is never materialised.  accum_inout as above;
+ *   pass accum_is_ones != 0 to promise that every weight is 1.0 (skips the upload). */
+RDB200_API int rdb200_fa_d8_f32_f64(const float *dem, double *accum_inout, int32_t width, int32_t height,
+                         float nodata, int32_t accum_is_ones);
+RDB200_API int rdb200_fa_tarboton_f32_f64(const float *dem, double *accum_inout, int32_t width,
+                               int32_t height, float nodata, int32_t accum_is_ones);
+
+/* ---- device entry points (pointers into HBM of the current device) ----------------- */
+
+RDB200_API int rdb200_dev_fill_depressions_d8_f32(float *d_dem, int32_t width, int32_t height);
+RDB200_API int rdb200_dev_resolve_flats_epsilon_f32(float *d_dem, int32_t width, int32_t height, float nodata);
+RDB200_API int rdb200_dev_d8_flow_directions_f32(const float *d_dem, uint8_t *d_flowdirs, int32_t width,
+                                      int32_t height, float nodata);
+RDB200_API int rdb200_dev_d8_flow_accum_u8_i32(const uint8_t *d_flowdirs, int32_t *d_area, int32_t width,
+                                    int32_t height);
+RDB200_API int rdb200_dev_fm_d8_f32(const float *d_dem, float *d_props9, int32_t width, int32_t height,
+                         float nodata);
+RDB200_API int rdb200_dev_fm_tarboton_f32(const float *d_dem, float *d_props9, int32_t width, int32_t height,
+                               float nodata);
+RDB200_API int rdb200_dev_flow_accumulation_props_f64(const float *d_props9, double *d_accum_inout,
+                                           int32_t width, int32_t height);
+RDB200_API int rdb200_dev_fa_d8_f32_f64(const float *d_dem, double *d_accum_inout, int32_t width,
+                             int32_t height, float nodata, int32_t accum_is_ones);
+RDB200_API int rdb200_dev_fa_tarboton_f32_f64(const float *d_dem, double *d_accum_inout, int32_t width,
+                                   int32_t height, float nodata, int32_t accum_is_ones);
+
+/* Seeded synthetic fractal DEM (value-noise fBm, float32, no NaN / NoData) generated in HBM;
+ * benchmark input only (the reference's generate_perlin_terrain is single-octave/double:
+ * src/terrain_generation/terrain_generation.cpp:11-24).  Cell (x,y) of the band is global
+ * cell (x, y0+y) of a raster `full_height` rows tall, so row bands of one raster agree. */
+RDB200_API int rdb200_dev_generate_fbm_f32(float *d_dem, int32_t width, int32_t height, int32_t y0,
+                                uint32_t seed, int32_t octaves, float quantum);
+
+/* ---- row-band (multi-GPU) fill: one band per GPU, halo rows exchanged by the caller -- */
+/* The band raster handed in is (band_rows + ghost rows) x width.  Its first and last rows are
+ * boundary conditions that the solver never changes: a real raster border row, or a ghost
+ * row holding the neighbouring band's current water level (+inf before the first exchange).
+ * Protocol per GPU: begin -> { run ; read own edge rows ; exchange ; update ghost rows } until
+ * no band changed anywhere -> finish.  See richdem_b200/sharded.py. */
+typedef struct rdb200_fill_state rdb200_fill_state;
+RDB200_API int rdb200_dev_fill_begin(rdb200_fill_state **state, const float *d_dem, int32_t width,
+                          int32_t height);
+/* Relax to the local fixed point.  *changed_rows: bit0 = row 1 changed, bit1 = row height-2
+ * changed since the previous run (the rows a neighbouring band holds as ghosts). */
+RDB200_API int rdb200_dev_fill_run(rdb200_fill_state *state, int32_t *changed_rows);
+/* Copy water-level row y (0..height-1) to d_row[width]. */
+RDB200_API int rdb200_dev_fill_read_row(rdb200_fill_state *state, int32_t y, float *d_row);
+/* Replace boundary row y (0 or height-1) by d_row (element-wise <= the old values). */
+RDB200_API int rdb200_dev_fill_update_row(rdb200_fill_state *state, int32_t y, const float *d_row);
+/* Write the filled band to d_out (height x width, boundary rows included) and free state. */
+RDB200_API int rdb200_dev_fill_finish(rdb200_fill_state *state, float *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RICHDEM_B200_H_ */

@@ -1,0 +1,277 @@
+"""richdem_b200 -- B200-native drop-in for RichDEM's fill -> flats -> flow-accumulation path.
+
+The public surface mirrors the part of the reference Python API that lies on that path
+(reference: wrappers/pyrichdem/richdem/__init__.py): ``rdarray`` / ``rd3array`` (:155, :226),
+``FillDepressions`` (:381), ``ResolveFlats`` (:461), ``FlowAccumulation`` (:490),
+``FlowAccumFromProps`` (:599) and ``FlowProportions`` (:650) -- same names, argument meaning,
+return conventions and error behaviour (bare ``Exception`` for argument validation,
+``RuntimeError`` for engine failures).  Everything is computed by hand-written CUDA kernels in
+``librichdem_b200.so`` reached through its C ABI (``include/richdem_b200.h``); there is no CPU
+fallback and methods outside the hot path raise.
+"""
+from __future__ import annotations
+
+import copy
+import datetime
+from typing import Any, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import RichdemB200Error, init, set_param, shutdown, stats  # noqa: F401
+
+__version__ = "0.1.0"
+
+_D8_METHODS = ("D8", "OCallaghanD8")
+_DINF_METHODS = ("Dinf", "Tarboton")
+_OUT_OF_SCOPE_METHODS = ("Quinn", "Holmgren", "Freeman", "FairfieldLeymarieD8", "FairfieldLeymarieD4",
+                         "Rho8", "Rho4", "OCallaghanD4", "D4")
+
+
+def _version_string() -> str:
+    return f"richdem_b200 {__version__} (librichdem_b200 {_lib.lib().rdb200_version()})"
+
+
+def _add_analysis(rda, analysis: str) -> None:
+    # PROCESSING_HISTORY provenance, as the reference's _AddAnalysis (:34-48)
+    if type(rda) not in (rdarray, rd3array):
+        raise Exception("An rdarray or rd3array is required!")
+    stamp = datetime.datetime.now(datetime.timezone.utc).strftime("%Y-%m-%d %H:%M:%S.%f UTC")
+    if rda.metadata is None:
+        rda.metadata = dict()
+    rda.metadata["PROCESSING_HISTORY"] = rda.metadata.get("PROCESSING_HISTORY", "") + \
+        f"\n{stamp} | {_version_string()} | {analysis}"
+
+
+class _MetaArray(np.ndarray):
+    def __array_finalize__(self, obj):
+        if obj is None:
+            return
+        self.metadata = copy.deepcopy(getattr(obj, "metadata", dict()))
+        self.no_data = copy.deepcopy(getattr(obj, "no_data", None))
+        self.projection = copy.deepcopy(getattr(obj, "projection", ""))
+        self.geotransform = copy.deepcopy(getattr(obj, "geotransform", None))
+
+    def _take_meta(self, meta_obj, no_data, geotransform=None):
+        if meta_obj is not None:
+            self.metadata = copy.deepcopy(getattr(meta_obj, "metadata", dict()))
+            self.no_data = copy.deepcopy(getattr(meta_obj, "no_data", None))
+            self.projection = copy.deepcopy(getattr(meta_obj, "projection", ""))
+            self.geotransform = copy.deepcopy(getattr(meta_obj, "geotransform", None))
+        elif geotransform is not None:
+            self.geotransform = geotransform
+        if no_data is not None:
+            self.no_data = no_data
+        if no_data is None:
+            raise Exception("A no_data value must be specified!")
+
+
+class rdarray(_MetaArray):
+    """2-D raster with ``no_data`` / ``geotransform`` / ``projection`` / ``metadata``
+    (reference rdarray, :155-223)."""
+
+    def __new__(cls, array, meta_obj=None, no_data=None, dtype=None, order=None, geotransform=None,
+                copy: bool = False, **kwargs: Any):
+        arr = np.array(array, dtype=dtype, order=order, copy=True) if copy else \
+            np.asarray(array, dtype=dtype, order=order)
+        obj = arr.view(cls)
+        obj.metadata = dict()
+        obj.projection = ""
+        obj.geotransform = None
+        obj.no_data = None
+        obj._take_meta(meta_obj, no_data, geotransform)
+        return obj
+
+
+class rd3array(_MetaArray):
+    """(H, W, 9) float32 flow-proportion array (reference rd3array, :226-279)."""
+
+    def __new__(cls, array, meta_obj=None, no_data=None, order=None, **kwargs: Any):
+        obj = np.asarray(array, dtype=np.float32, order=order).view(cls)
+        obj.metadata = dict()
+        obj.projection = ""
+        obj.geotransform = None
+        obj.no_data = None
+        obj._take_meta(meta_obj, no_data)
+        return obj
+
+
+# ---------------------------------------------------------------------------------------------
+def _dem_f32(dem: rdarray, what: str) -> np.ndarray:
+    if dem.ndim != 2:
+        raise RuntimeError("Array must have two dimensions!")  # pywrapper.hpp:118-119
+    if dem.dtype != np.float32:
+        raise Exception(
+            f"{what}: the B200 path is built for float32 elevations (got '{dem.dtype}'); "
+            "convert with dem.astype('float32') -- there is no CPU fallback for other dtypes.")
+    if not dem.flags["C_CONTIGUOUS"]:
+        raise Exception(f"{what}: the raster must be C-contiguous")
+    return dem
+
+
+def _nodata_f32(dem) -> float:
+    nd = dem.no_data
+    if nd is None:
+        print("Warning! no_data was None. Setting it to -9999!")  # reference :204-206
+        nd = -9999
+    return float(np.float32(nd))
+
+
+def FillDepressions(dem: rdarray, epsilon: bool = False, in_place: bool = False,
+                    topology: str = "D8") -> Optional[rdarray]:
+    """Fills all depressions in a DEM (reference FillDepressions, :381-422 ->
+    PriorityFlood_Zhou2016).  Returns the filled DEM unless ``in_place``."""
+    if type(dem) is not rdarray:
+        raise Exception("A richdem.rdarray or numpy.ndarray is required!")
+    if topology not in ["D8", "D4"]:
+        raise Exception("Unknown topology!")
+    if epsilon:
+        raise Exception("FillDepressions(epsilon=True) is outside the B200 hot path (SURVEY 8f-3)")
+    if topology != "D8":
+        raise Exception("FillDepressions(topology='D4') is outside the B200 hot path")
+    if not in_place:
+        dem = dem.copy()
+    _add_analysis(dem, f"FillDepressions(dem, epsilon={epsilon})")
+    d = _dem_f32(dem, "FillDepressions")
+    h, w = d.shape
+    _lib.check(_lib.lib().rdb200_fill_depressions_d8_f32(_lib.ptr(d), w, h))
+    if not in_place:
+        return dem
+    return None
+
+
+def ResolveFlats(dem: rdarray, in_place: bool = False) -> Optional[rdarray]:
+    """Imposes a local gradient on drainable flats (reference ResolveFlats, :461-487 ->
+    ResolveFlatsEpsilon)."""
+    if type(dem) is not rdarray:
+        raise Exception("A richdem.rdarray or numpy.ndarray is required!")
+    if not in_place:
+        dem = dem.copy()
+    _add_analysis(dem, f"ResolveFlats(dem, in_place={in_place})")
+    d = _dem_f32(dem, "ResolveFlats")
+    h, w = d.shape
+    _lib.check(_lib.lib().rdb200_resolve_flats_epsilon_f32(_lib.ptr(d), w, h, _nodata_f32(dem)))
+    if not in_place:
+        return dem
+    return None
+
+
+def _accum_array(like, weights, in_place, shape):
+    ones = False
+    if weights is not None and in_place:
+        accum = rdarray(weights, no_data=-1)
+    elif weights is not None and not in_place:
+        accum = rdarray(weights, copy=True, meta_obj=like, no_data=-1)
+    else:
+        accum = rdarray(np.empty(shape=shape, dtype="float64"), meta_obj=like, no_data=-1)
+        ones = True  # unit weights are generated on the device; nothing is uploaded
+    if accum.dtype != "float64":
+        raise Exception("Accumulation array must be of type 'float64'!")
+    if accum.shape != tuple(shape):
+        raise RuntimeError("Accumulation array must have same dimensions as proportions array!")
+    if not accum.flags["C_CONTIGUOUS"]:
+        raise Exception("Accumulation array must be C-contiguous")
+    return accum, ones
+
+
+def FlowAccumulation(dem: rdarray, method: Optional[str] = None, exponent: Optional[float] = None,
+                     weights: Optional[rdarray] = None, in_place: bool = False) -> rdarray:
+    """Flow accumulation (reference FlowAccumulation, :490-596).  Methods on the B200 path:
+    ``D8`` / ``OCallaghanD8`` (FA_D8) and ``Dinf`` / ``Tarboton`` (FA_Tarboton)."""
+    if type(dem) is not rdarray:
+        raise Exception("A richdem.rdarray or numpy.ndarray is required!")
+    accum, ones = _accum_array(dem, weights, in_place, dem.shape)
+    _add_analysis(accum, "FlowAccumulation(dem, method={0}, exponent={1}, weights={2}, in_place={3})".format(
+        method, exponent, "None" if weights is None else "weights", in_place))
+    d = _dem_f32(dem, "FlowAccumulation")
+    h, w = d.shape
+    L = _lib.lib()
+    if method in _D8_METHODS:
+        _lib.check(L.rdb200_fa_d8_f32_f64(_lib.ptr(d), _lib.ptr(accum), w, h, _nodata_f32(dem), int(ones)))
+    elif method in _DINF_METHODS:
+        _lib.check(L.rdb200_fa_tarboton_f32_f64(_lib.ptr(d), _lib.ptr(accum), w, h, _nodata_f32(dem), int(ones)))
+    elif method in _OUT_OF_SCOPE_METHODS:
+        raise Exception(f'FlowAccumulation method "{method}" is outside the B200 hot path '
+                        "(available: D8, OCallaghanD8, Dinf, Tarboton)")
+    else:
+        raise Exception("Invalid FlowAccumulation method. Valid methods are: " +
+                        ", ".join(_DINF_METHODS + _D8_METHODS + _OUT_OF_SCOPE_METHODS))
+    accum.no_data = -1
+    return accum
+
+
+def FlowAccumFromProps(props: rd3array, weights: Optional[rdarray] = None, in_place: bool = False) -> rdarray:
+    """Flow accumulation from (H, W, 9) proportions (reference FlowAccumFromProps, :599-647)."""
+    if type(props) is not rd3array:
+        raise Exception("A richdem.rd3array or numpy.ndarray is required!")
+    if props.ndim != 3 or props.shape[2] != 9:
+        raise RuntimeError("Array must have three dimensions with the last of size 9!")
+    accum, ones = _accum_array(props, weights, in_place, props.shape[0:2])
+    if ones:
+        accum[...] = 1.0
+    _add_analysis(accum, "FlowAccumFromProps(dem, weights={0}, in_place={1})".format(
+        "None" if weights is None else "weights", in_place))
+    p = np.ascontiguousarray(props, dtype=np.float32)
+    h, w = p.shape[0:2]
+    _lib.check(_lib.lib().rdb200_flow_accumulation_props_f64(_lib.ptr(p), _lib.ptr(accum), w, h))
+    accum.no_data = -1
+    return accum
+
+
+def FlowProportions(dem: rdarray, method: Optional[str] = None, exponent: Optional[float] = None) -> rd3array:
+    """Flow proportions (reference FlowProportions, :650-732): (H, W, 9) float32, slot 0 holds
+    -2 NoData / -1 no flow / 0 has flow, slots 1..8 the share sent to D8 neighbour n."""
+    if type(dem) is not rdarray:
+        raise Exception("A richdem.rdarray or numpy.ndarray is required!")
+    fprops = rd3array(np.empty(shape=dem.shape + (9,), dtype="float32"), meta_obj=dem, no_data=-2)
+    _add_analysis(fprops, f"FlowProportions(dem, method={method}, exponent={exponent})")
+    d = _dem_f32(dem, "FlowProportions")
+    h, w = d.shape
+    L = _lib.lib()
+    if method in _D8_METHODS:
+        _lib.check(L.rdb200_fm_d8_f32(_lib.ptr(d), _lib.ptr(fprops), w, h, _nodata_f32(dem)))
+    elif method in _DINF_METHODS:
+        _lib.check(L.rdb200_fm_tarboton_f32(_lib.ptr(d), _lib.ptr(fprops), w, h, _nodata_f32(dem)))
+    elif method in _OUT_OF_SCOPE_METHODS:
+        raise Exception(f'FlowProportions method "{method}" is outside the B200 hot path '
+                        "(available: D8, OCallaghanD8, Dinf, Tarboton)")
+    else:
+        raise Exception("Invalid FlowProportions method. Valid methods are: " +
+                        ", ".join(_DINF_METHODS + _D8_METHODS + _OUT_OF_SCOPE_METHODS))
+    fprops.no_data = -2
+    return fprops
+
+
+# ---- C++-only functions of the path, exposed for completeness ---------------------------------
+def FlowDirectionsD8(dem: rdarray) -> rdarray:
+    """richdem::d8_flow_directions (flowmet/d8_flowdirs.hpp:96-123): uint8 codes 0..8, 255 NoData."""
+    if type(dem) is not rdarray:
+        raise Exception("A richdem.rdarray or numpy.ndarray is required!")
+    d = _dem_f32(dem, "FlowDirectionsD8")
+    h, w = d.shape
+    out = rdarray(np.empty((h, w), np.uint8), meta_obj=dem, no_data=255)
+    _lib.check(_lib.lib().rdb200_d8_flow_directions_f32(_lib.ptr(d), _lib.ptr(out), w, h, _nodata_f32(dem)))
+    out.no_data = 255
+    return out
+
+
+def D8FlowAccum(flowdirs: np.ndarray) -> rdarray:
+    """richdem::d8_flow_accum (methods/d8_methods.hpp:47-139) on a uint8 direction grid."""
+    f = np.ascontiguousarray(flowdirs, dtype=np.uint8)
+    if f.ndim != 2:
+        raise RuntimeError("Array must have two dimensions!")
+    h, w = f.shape
+    out = rdarray(np.empty((h, w), np.int32), no_data=-1)
+    _lib.check(_lib.lib().rdb200_d8_flow_accum_u8_i32(_lib.ptr(f), _lib.ptr(out), w, h))
+    return out
+
+
+def FlatMask(dem: rdarray):
+    """richdem::GetFlatMask (flats/Barnes2014.hpp:398-467): (mask, labels) int32 arrays."""
+    d = _dem_f32(dem, "FlatMask")
+    h, w = d.shape
+    mask = np.empty((h, w), np.int32)
+    labels = np.empty((h, w), np.int32)
+    _lib.check(_lib.lib().rdb200_get_flat_mask_f32(_lib.ptr(d), _lib.ptr(mask), _lib.ptr(labels), w, h,
+                                                    _nodata_f32(dem)))
+    return mask, labels

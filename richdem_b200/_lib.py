@@ -1,0 +1,118 @@
+"""ctypes binding of librichdem_b200.so (the C ABI in include/richdem_b200.h).
+
+This is the only way the Python layer reaches the compute path.  There is no CPU fallback: if the
+shared library is missing, or no B200 is visible, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librichdem_b200.so")
+
+_lib = None
+
+
+class RichdemB200Error(RuntimeError):
+    """Raised for any non-zero status from the C ABI (mirrors the std::runtime_error ->
+    RuntimeError translation pybind11 does for the reference, pywrapper.hpp:109-123)."""
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("cells", C.c_int64), ("kernel_launches", C.c_int64), ("fill_rounds", C.c_int64),
+        ("fill_tile_visits", C.c_int64), ("fill_tile_cells", C.c_int64), ("fill_tile_iters", C.c_int64),
+        ("accum_rounds", C.c_int64), ("flat_bfs_levels", C.c_int64), ("flat_cells_raised", C.c_int64),
+        ("ms_total", C.c_double), ("ms_main_kernel", C.c_double), ("ms_h2d", C.c_double),
+        ("ms_d2h", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/richdem_b200.h declares: name -> argtypes (restype is int unless noted)
+_i32, _f32, _vp = C.c_int32, C.c_float, C.c_void_p
+SIGNATURES = {
+    "rdb200_init": [C.c_int],
+    "rdb200_get_stats": [C.POINTER(Stats)],
+    "rdb200_set_param": [C.c_char_p, C.c_int64],
+    "rdb200_fill_depressions_d8_f32": [_vp, _i32, _i32],
+    "rdb200_resolve_flats_epsilon_f32": [_vp, _i32, _i32, _f32],
+    "rdb200_get_flat_mask_f32": [_vp, _vp, _vp, _i32, _i32, _f32],
+    "rdb200_d8_flow_directions_f32": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_d8_flow_accum_u8_i32": [_vp, _vp, _i32, _i32],
+    "rdb200_fm_d8_f32": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_fm_tarboton_f32": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_flow_accumulation_props_f64": [_vp, _vp, _i32, _i32],
+    "rdb200_fa_d8_f32_f64": [_vp, _vp, _i32, _i32, _f32, _i32],
+    "rdb200_fa_tarboton_f32_f64": [_vp, _vp, _i32, _i32, _f32, _i32],
+    "rdb200_dev_fill_depressions_d8_f32": [_vp, _i32, _i32],
+    "rdb200_dev_resolve_flats_epsilon_f32": [_vp, _i32, _i32, _f32],
+    "rdb200_dev_d8_flow_directions_f32": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_dev_d8_flow_accum_u8_i32": [_vp, _vp, _i32, _i32],
+    "rdb200_dev_fm_d8_f32": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_dev_fm_tarboton_f32": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_dev_flow_accumulation_props_f64": [_vp, _vp, _i32, _i32],
+    "rdb200_dev_fa_d8_f32_f64": [_vp, _vp, _i32, _i32, _f32, _i32],
+    "rdb200_dev_fa_tarboton_f32_f64": [_vp, _vp, _i32, _i32, _f32, _i32],
+    "rdb200_dev_generate_fbm_f32": [_vp, _i32, _i32, _i32, C.c_uint32, _i32, _f32],
+    "rdb200_dev_fill_begin": [C.POINTER(_vp), _vp, _i32, _i32],
+    "rdb200_dev_fill_run": [_vp, C.POINTER(_i32)],
+    "rdb200_dev_fill_read_row": [_vp, _i32, _vp],
+    "rdb200_dev_fill_update_row": [_vp, _i32, _vp],
+    "rdb200_dev_fill_finish": [_vp, _vp],
+}
+OTHER_SYMBOLS = ["rdb200_shutdown", "rdb200_last_error", "rdb200_version"]
+
+
+def lib():
+    """Load (once) and return the shared library; raises loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RichdemB200Error(
+                f"{LIB_PATH} not found: build it with `python -m richdem_b200.build` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            f = getattr(L, name)
+            f.argtypes = argtypes
+            f.restype = C.c_int
+        L.rdb200_last_error.restype = C.c_char_p
+        L.rdb200_last_error.argtypes = []
+        L.rdb200_version.restype = C.c_int
+        L.rdb200_shutdown.restype = None
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().rdb200_last_error()
+        raise RichdemB200Error(msg.decode("utf-8", "replace") if msg else f"librichdem_b200 error {rc}")
+
+
+def ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+def stats() -> dict:
+    s = Stats()
+    check(lib().rdb200_get_stats(C.byref(s)))
+    return s.as_dict()
+
+
+def set_param(name: str, value: int) -> None:
+    check(lib().rdb200_set_param(name.encode(), int(value)))
+
+
+def init(device: int = 0) -> None:
+    check(lib().rdb200_init(int(device)))
+
+
+def shutdown() -> None:
+    lib().rdb200_shutdown()

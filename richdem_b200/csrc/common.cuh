@@ -1,0 +1,141 @@
+// Shared host/device plumbing for librichdem_b200 (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/richdem_b200.h"
+
+namespace rdb {
+
+// ---- errors -----------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+[[noreturn]] inline void fail(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw Error(buf);
+}
+
+#define RDB_CK(expr)                                                                        \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      ::rdb::fail("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---- D8 tables (reference include/richdem/common/constants.hpp:44-45,65) ----------------
+//   2 3 4
+//   1 0 5
+//   8 7 6
+__host__ __device__ __forceinline__ int d8dx(int n) {
+  // {0,-1,-1,0,1,1,1,0,-1} packed 2 bits each (+1 bias)
+  return (int)((0x6a41u >> (2 * n)) & 3u) - 1;  // n:0->0,1->-1,2->-1,3->0,4->1,5->1,6->1,7->0,8->-1
+}
+__host__ __device__ __forceinline__ int d8dy(int n) {
+  // {0,0,-1,-1,-1,0,1,1,1}
+  return (int)((0x2a405u >> (2 * n)) & 3u) - 1;
+}
+
+// ---- context ----------------------------------------------------------------------------
+struct Params {
+  int64_t fill_max_iters = 0;   // 0 = relax every tile visit to its local fixed point
+  int64_t fill_rounds_per_sync = 8;
+  int64_t fill_use_tma = 1;     // 0: plain ld.global staging (debug aid)
+  int64_t accum_threads = 256;
+};
+
+struct WsBlock {
+  void *ptr;
+  size_t bytes;
+  bool in_use;
+};
+
+struct Ctx {
+  bool inited = false;
+  int device = -1;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  std::vector<WsBlock> ws;
+  void *pinned = nullptr;  // small pinned scratch for read-backs
+  size_t pinned_bytes = 0;
+  rdb200_stats stats;
+  Params params;
+};
+
+Ctx &ctx();
+void ensure_init();
+void *ws_alloc(size_t bytes);
+void ws_free(void *p);
+void ws_release_all();
+
+// RAII device scratch buffer from the cached workspace
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t count) { alloc(count); }
+  void alloc(size_t count) {
+    reset();
+    n = count;
+    p = (T *)ws_alloc((count ? count : 1) * sizeof(T));
+  }
+  void reset() {
+    if (p) ws_free(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { reset(); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  operator T *() const { return p; }
+};
+
+inline void count_launch(int64_t k = 1) { ctx().stats.kernel_launches += k; }
+
+// kernel timing helper for the "dominant kernel" accounting (events on the launch stream)
+struct KernelTimer {
+  bool active;
+  explicit KernelTimer(bool on = true) : active(on) {
+    if (active) RDB_CK(cudaEventRecord(ctx().evk0, ctx().stream));
+  }
+  void stop_async() {
+    if (active) RDB_CK(cudaEventRecord(ctx().evk1, ctx().stream));
+  }
+  // call after a stream sync
+  double ms() {
+    float t = 0;
+    if (active) RDB_CK(cudaEventElapsedTime(&t, ctx().evk0, ctx().evk1));
+    return t;
+  }
+};
+
+// ---- stage entry points implemented in the .cu files (device pointers, ctx stream) -------
+void fill_depressions_dev(float *d_dem, int w, int h);
+void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask_out,
+                       int32_t *d_labels_out, bool apply);
+void d8_flow_directions_dev(const float *d_dem, uint8_t *d_dirs, int w, int h, float nodata);
+void d8_flow_accum_dev(const uint8_t *d_dirs, int32_t *d_area, int w, int h);
+void fm_d8_dev(const float *d_dem, float *d_props, int w, int h, float nodata);
+void fm_tarboton_dev(const float *d_dem, float *d_props, int w, int h, float nodata);
+void flow_accumulation_props_dev(const float *d_props, double *d_accum, int w, int h);
+void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodata, bool ones,
+                  bool dinf);
+void generate_fbm_dev(float *d_dem, int w, int h, int y0, uint32_t seed, int octaves, float quantum);
+
+}  // namespace rdb

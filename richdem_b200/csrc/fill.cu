@@ -1,0 +1,622 @@
+// Depression filling on B200: the Priority-Flood result computed as the greatest fixed point of
+//
+//     W(c) = max( Z(c), min over the 8 neighbours n of W(n) ),   W = Z on the raster border,
+//
+// reached from above (W0 = +inf on interior cells).  The fixed point is the unique
+// min-over-paths-of-max-elevation surface, i.e. exactly what the reference's serial
+// priority-queue flood produces (include/richdem/depressions/Zhou2016.hpp:125-191 via
+// depressions.hpp:13-21), and only comparisons/copies of input values are involved, so the
+// result is bit-identical.  See DESIGN.md section "fill" for the proof sketch and layout.
+//
+// Formulation ("spill-scan"): the raster is cut into 64x64 tiles.  One sweep round is ONE
+// persistent kernel launch that walks a compacted worklist of active tiles; for each tile it
+//   1. stages W (with a one-cell apron) and Z into shared memory with two TMA tile loads
+//      (cp.async.bulk.tensor.2d + mbarrier),
+//   2. relaxes the tile to its local fixed point entirely in shared memory / registers
+//      (each thread owns a 4x4 block in registers and runs forward+backward Gauss-Seidel
+//      passes over it, exchanging only block rims through shared memory),
+//   3. writes W back with coalesced float4 stores if anything changed, and
+//   4. appends the neighbouring tiles whose apron it changed to the next round's worklist.
+// Between tiles the iteration is chaotic (asynchronous Jacobi); every value ever stored is an
+// upper bound of the answer and updates are monotone, so any schedule converges to the same
+// fixed point.  The device-wide "anything changed" signal is the next worklist's length.
+#include "common.cuh"
+
+namespace rdb {
+
+namespace {
+
+constexpr int TX = 64;           // tile width  (cells)
+constexpr int TY = 64;           // tile height (cells)
+constexpr int PADL = 4;          // cell (x,y) lives at padded (x+PADL, y+1)
+constexpr int SP = TX + 2 * PADL;  // shared-memory row pitch of the W tile (floats): 72
+constexpr int SROWS = TY + 2;    // W tile rows incl. apron: 66
+constexpr int FILL_THREADS = 256;  // 16 x 16 threads, each owning a 4x4 block
+constexpr uint32_t W_TILE_BYTES = SP * SROWS * 4;
+constexpr uint32_t Z_TILE_BYTES = TX * TY * 4;
+
+struct RoundCtl {
+  int count;  // tiles in this round's worklist
+  int take;   // next worklist slot to hand out
+};
+
+struct FillDev {
+  RoundCtl ctl[3];  // rotating: cur = round%3, next = (round+1)%3, being-zeroed = (round+2)%3
+  unsigned long long visits;
+  unsigned long long iters;
+  int edge_changed;  // bit0: raster row 1 changed, bit1: raster row H-2 changed
+  int pad;
+};
+
+struct FillArgs {
+  const float *Zp;
+  float *Wp;
+  int pitch;  // floats
+  int W, H;
+  int tilesX, tilesY;
+  int *list0, *list1;
+  int *stamp;
+  FillDev *dev;
+  int round;
+  int max_iters;
+  int use_tma;
+};
+
+// ---- PTX helpers: mbarrier + TMA ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n"
+        "  .reg .pred p;\n"
+        "  mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "  selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1,
+                                            unsigned long long *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void enqueue_tile(const FillArgs &a, RoundCtl *next, int *list_next, int t,
+                                             int stampval) {
+  if (atomicExch(&a.stamp[t], stampval) != stampval) {
+    const int idx = atomicAdd(&next->count, 1);
+    list_next[idx] = t;
+  }
+}
+
+__device__ __forceinline__ float min8(float a, float b, float c, float d, float e, float f, float g,
+                                      float h) {
+  return fminf(fminf(fminf(a, b), fminf(c, d)), fminf(fminf(e, f), fminf(g, h)));
+}
+
+// ---- the sweep kernel --------------------------------------------------------------------
+__global__ void __launch_bounds__(FILL_THREADS, 3)
+    fill_sweep_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ,
+                      const FillArgs a) {
+  __shared__ __align__(128) float sW[SROWS * SP];
+  __shared__ __align__(128) float sZ[TY * TX];
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ int sTile;
+  __shared__ int sFlags;
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15;   // block column: cells 4tx..4tx+3
+  const int ty = tid >> 4;   // block row:    cells 4ty..4ty+3
+  const int r = a.round;
+  RoundCtl *cur = &a.dev->ctl[r % 3];
+  RoundCtl *next = &a.dev->ctl[(r + 1) % 3];
+  const int *list_cur = (r & 1) ? a.list1 : a.list0;
+  int *list_next = (r & 1) ? a.list0 : a.list1;
+  const int n = cur->count;
+
+  if (blockIdx.x == 0 && tid == 0) {
+    RoundCtl *z = &a.dev->ctl[(r + 2) % 3];
+    z->count = 0;
+    z->take = 0;
+    if (n > 0) atomicAdd(&a.dev->visits, (unsigned long long)n);
+  }
+  if (n == 0) return;
+
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t phase = 0;
+  const int max_iters = a.max_iters;
+
+  for (;;) {
+    if (tid == 0) sTile = atomicAdd(&cur->take, 1);
+    __syncthreads();  // publishes sTile (and the mbarrier init); all warps are done with smem
+    const int li = sTile;
+    if (li >= n) break;
+    const int t = list_cur[li];
+    const int tyT = t / a.tilesX, txT = t - tyT * a.tilesX;
+    const int x0 = txT * TX, y0 = tyT * TY;  // raster coords of the tile's first cell
+
+    // ---- stage W (+apron) and Z ----
+    if (a.use_tma) {
+      if (tid == 0) {
+        sFlags = 0;
+        fence_proxy_async();  // order earlier generic-proxy smem accesses before the async writes
+        mbar_arrive_expect_tx(&mbar, W_TILE_BYTES + Z_TILE_BYTES);
+        tma_load_2d(sW, &mapW, x0, y0, &mbar);               // padded cols x0..x0+71, rows y0..y0+65
+        tma_load_2d(sZ, &mapZ, x0 + PADL, y0 + 1, &mbar);    // the 64x64 interior
+      }
+      mbar_wait(&mbar, phase);
+      phase ^= 1;
+    } else {
+      if (tid == 0) sFlags = 0;
+      const float4 *gW = reinterpret_cast<const float4 *>(a.Wp + (size_t)y0 * a.pitch + x0);
+      for (int k = tid; k < SROWS * (SP / 4); k += FILL_THREADS) {
+        const int rr = k / (SP / 4), cc = k - rr * (SP / 4);
+        reinterpret_cast<float4 *>(sW)[k] =
+            __ldcg(reinterpret_cast<const float4 *>(a.Wp + (size_t)(y0 + rr) * a.pitch + x0) + cc);
+      }
+      (void)gW;
+      for (int k = tid; k < TY * (TX / 4); k += FILL_THREADS) {
+        const int rr = k / (TX / 4), cc = k - rr * (TX / 4);
+        reinterpret_cast<float4 *>(sZ)[k] = __ldg(
+            reinterpret_cast<const float4 *>(a.Zp + (size_t)(y0 + 1 + rr) * a.pitch + x0 + PADL) + cc);
+      }
+      __syncthreads();
+    }
+
+    // ---- registers: own 4x4 block of W (v[1..4][1..4]) and Z ----
+    float v[6][6];
+    float z[4][4];
+    const int srow = 4 * ty + 1;     // smem row of own row 0
+    const int scol = 4 * tx + PADL;  // smem col of own col 0
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float4 w4 = *reinterpret_cast<const float4 *>(&sW[(srow + j) * SP + scol]);
+      v[j + 1][1] = w4.x; v[j + 1][2] = w4.y; v[j + 1][3] = w4.z; v[j + 1][4] = w4.w;
+      const float4 z4 = *reinterpret_cast<const float4 *>(&sZ[(4 * ty + j) * TX + 4 * tx]);
+      z[j][0] = z4.x; z[j][1] = z4.y; z[j][2] = z4.z; z[j][3] = z4.w;
+    }
+
+    uint32_t chAll = 0;  // cells of my block that changed during this visit (bit 4*j+i)
+    int iters = 0;
+    bool again = false;
+    for (;;) {
+      // rim of the block (apron or neighbouring threads' cells; may be mid-update: harmless)
+      {
+        const float *top = &sW[(srow - 1) * SP + scol];
+        const float *bot = &sW[(srow + 4) * SP + scol];
+        const float4 t4 = *reinterpret_cast<const float4 *>(top);
+        const float4 b4 = *reinterpret_cast<const float4 *>(bot);
+        v[0][0] = top[-1]; v[0][1] = t4.x; v[0][2] = t4.y; v[0][3] = t4.z; v[0][4] = t4.w; v[0][5] = top[4];
+        v[5][0] = bot[-1]; v[5][1] = b4.x; v[5][2] = b4.y; v[5][3] = b4.z; v[5][4] = b4.w; v[5][5] = bot[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          v[j + 1][0] = sW[(srow + j) * SP + scol - 1];
+          v[j + 1][5] = sW[(srow + j) * SP + scol + 4];
+        }
+      }
+      uint32_t ch = 0;
+      // forward Gauss-Seidel pass
+#pragma unroll
+      for (int j = 1; j <= 4; j++) {
+#pragma unroll
+        for (int i = 1; i <= 4; i++) {
+          const float m = min8(v[j - 1][i - 1], v[j - 1][i], v[j - 1][i + 1], v[j][i - 1], v[j][i + 1],
+                               v[j + 1][i - 1], v[j + 1][i], v[j + 1][i + 1]);
+          const float nw = fmaxf(z[j - 1][i - 1], m);
+          if (nw < v[j][i]) {
+            v[j][i] = nw;
+            ch |= 1u << ((j - 1) * 4 + (i - 1));
+          }
+        }
+      }
+      // backward pass
+#pragma unroll
+      for (int j = 4; j >= 1; j--) {
+#pragma unroll
+        for (int i = 4; i >= 1; i--) {
+          const float m = min8(v[j - 1][i - 1], v[j - 1][i], v[j - 1][i + 1], v[j][i - 1], v[j][i + 1],
+                               v[j + 1][i - 1], v[j + 1][i], v[j + 1][i + 1]);
+          const float nw = fmaxf(z[j - 1][i - 1], m);
+          if (nw < v[j][i]) {
+            v[j][i] = nw;
+            ch |= 1u << ((j - 1) * 4 + (i - 1));
+          }
+        }
+      }
+      // publish changed rows
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (ch & (0xFu << (4 * j))) {
+          *reinterpret_cast<float4 *>(&sW[(srow + j) * SP + scol]) =
+              make_float4(v[j + 1][1], v[j + 1][2], v[j + 1][3], v[j + 1][4]);
+        }
+      }
+      chAll |= ch;
+      iters++;
+      const int any = __syncthreads_or(ch != 0);
+      if (!any) break;
+      if (max_iters > 0 && iters >= max_iters) {
+        again = true;  // not at the local fixed point yet: revisit next round
+        break;
+      }
+    }
+
+    // ---- write back + activate neighbours ----
+    const int tileChanged = __syncthreads_or(chAll != 0);
+    if (tileChanged) {
+      if (chAll) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (chAll & (0xFu << (4 * j))) {
+            float4 *dst = reinterpret_cast<float4 *>(a.Wp + (size_t)(y0 + 1 + 4 * ty + j) * a.pitch +
+                                                     (x0 + PADL + 4 * tx));
+            __stcg(dst, make_float4(v[j + 1][1], v[j + 1][2], v[j + 1][3], v[j + 1][4]));
+          }
+        }
+        int f = 0;
+        if (ty == 0 && (chAll & 0x000Fu)) f |= 1;    // N edge row changed
+        if (ty == 15 && (chAll & 0xF000u)) f |= 2;   // S
+        if (tx == 0 && (chAll & 0x1111u)) f |= 4;    // W
+        if (tx == 15 && (chAll & 0x8888u)) f |= 8;   // E
+        // rows a neighbouring band holds as ghost rows (row-band multi-GPU mode)
+        {
+          const int gy0 = y0 + 4 * ty;  // raster row of my block row 0
+          const int j1 = 1 - gy0, j2 = (a.H - 2) - gy0;
+          if (j1 >= 0 && j1 < 4 && (chAll & (0xFu << (4 * j1)))) f |= 16;
+          if (j2 >= 0 && j2 < 4 && (chAll & (0xFu << (4 * j2)))) f |= 32;
+        }
+        if (f) atomicOr(&sFlags, f);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        const int f = sFlags;
+        const int sv = r + 1;
+        const bool n_ok = tyT > 0, s_ok = tyT < a.tilesY - 1, w_ok = txT > 0, e_ok = txT < a.tilesX - 1;
+        if ((f & 1) && n_ok) enqueue_tile(a, next, list_next, t - a.tilesX, sv);
+        if ((f & 2) && s_ok) enqueue_tile(a, next, list_next, t + a.tilesX, sv);
+        if ((f & 4) && w_ok) enqueue_tile(a, next, list_next, t - 1, sv);
+        if ((f & 8) && e_ok) enqueue_tile(a, next, list_next, t + 1, sv);
+        if ((f & 5) == 5 && n_ok && w_ok) enqueue_tile(a, next, list_next, t - a.tilesX - 1, sv);
+        if ((f & 9) == 9 && n_ok && e_ok) enqueue_tile(a, next, list_next, t - a.tilesX + 1, sv);
+        if ((f & 6) == 6 && s_ok && w_ok) enqueue_tile(a, next, list_next, t + a.tilesX - 1, sv);
+        if ((f & 10) == 10 && s_ok && e_ok) enqueue_tile(a, next, list_next, t + a.tilesX + 1, sv);
+        if (again) enqueue_tile(a, next, list_next, t, sv);
+        if (f & 48) atomicOr(&a.dev->edge_changed, (f >> 4) & 3);
+        atomicAdd(&a.dev->iters, (unsigned long long)iters);
+      }
+    } else if (tid == 0) {
+      atomicAdd(&a.dev->iters, (unsigned long long)iters);
+    }
+  }
+}
+
+// ---- layout kernels ----------------------------------------------------------------------
+// compact dem (H x W) -> padded Z and W.  Border cells (all four sides of the raster handed in)
+// are boundary conditions: W = Z = dem there; interior W = +inf; padding Z = W = +inf.
+__global__ void fill_init_kernel(const float *__restrict__ dem, float *__restrict__ Zp,
+                                 float *__restrict__ Wp, int W, int H, int pitch, int rows) {
+  const int px4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // padded column (multiple of 4)
+  if (px4 >= pitch) return;
+  const float inf = __int_as_float(0x7f800000);
+  for (int py = blockIdx.y; py < rows; py += gridDim.y) {
+    float zv[4], wv[4];
+    const int y = py - 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int x = px4 + k - PADL;
+      float zz = inf, ww = inf;
+      if (x >= 0 && x < W && y >= 0 && y < H) {
+        zz = dem[(size_t)y * W + x];
+        const bool border = (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
+        ww = border ? zz : inf;
+      }
+      zv[k] = zz;
+      wv[k] = ww;
+    }
+    const size_t o = (size_t)py * pitch + px4;
+    *reinterpret_cast<float4 *>(Zp + o) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+    *reinterpret_cast<float4 *>(Wp + o) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+  }
+}
+
+__global__ void fill_finish_kernel(const float *__restrict__ Wp, float *__restrict__ out, int W, int H,
+                                   int pitch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  for (int y = blockIdx.y; y < H; y += gridDim.y) out[(size_t)y * W + x] = Wp[(size_t)(y + 1) * pitch + x + PADL];
+}
+
+// ---- host side ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    RDB_CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) fail("cuTensorMapEncodeTiled not available from the driver");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+CUtensorMap make_map(float *base, int pitch, int rows, int boxw, int boxh) {
+  CUtensorMap m;
+  const cuuint64_t gdim[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)pitch * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)boxw, (cuuint32_t)boxh};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult rc = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
+  return m;
+}
+
+}  // namespace
+
+struct FillState {
+  int W = 0, H = 0, pitch = 0, rows = 0, tilesX = 0, tilesY = 0;
+  DevBuf<float> Zp, Wp;
+  DevBuf<int> list0, list1, stamp;
+  DevBuf<FillDev> dev;
+  CUtensorMap mapW, mapZ;
+  int round = 0;
+  int grid = 0;
+  int64_t rounds_run = 0;
+  unsigned long long visits_seen = 0, iters_seen = 0;
+
+  void begin(const float *d_dem, int w, int h) {
+    Ctx &c = ctx();
+    W = w;
+    H = h;
+    tilesX = (w + TX - 1) / TX;
+    tilesY = (h + TY - 1) / TY;
+    pitch = tilesX * TX + 2 * PADL;
+    rows = tilesY * TY + 2;
+    const size_t np = (size_t)pitch * rows;
+    Zp.alloc(np);
+    Wp.alloc(np);
+    const size_t nt = (size_t)tilesX * tilesY;
+    list0.alloc(nt);
+    list1.alloc(nt);
+    stamp.alloc(nt);
+    dev.alloc(1);
+    RDB_CK(cudaMemsetAsync(stamp.p, 0, nt * sizeof(int), c.stream));
+    RDB_CK(cudaMemsetAsync(dev.p, 0, sizeof(FillDev), c.stream));
+    {
+      dim3 blk(128), grd((pitch / 4 + 127) / 128, rows < 32768 ? rows : 32768);
+      fill_init_kernel<<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows);
+      RDB_CK(cudaGetLastError());
+      count_launch();
+    }
+    mapW = make_map(Wp.p, pitch, rows, SP, SROWS);
+    mapZ = make_map(Zp.p, pitch, rows, TX, TY);
+    int per_sm = 0;
+    RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_sweep_kernel, FILL_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    grid = c.num_sms * per_sm;
+    round = 0;
+    // initial worklist: every tile on the perimeter of the tile grid (the only tiles whose
+    // cells can see a finite neighbour at the start)
+    std::vector<int> init;
+    for (int ty = 0; ty < tilesY; ty++)
+      for (int tx = 0; tx < tilesX; tx++)
+        if (ty == 0 || tx == 0 || ty == tilesY - 1 || tx == tilesX - 1) init.push_back(ty * tilesX + tx);
+    seed_worklist(init);
+  }
+
+  // place `tiles` (deduplicated) as the worklist of the next round to be launched
+  void seed_worklist(const std::vector<int> &tiles) {
+    Ctx &c = ctx();
+    int *lst = (round & 1) ? list1.p : list0.p;
+    RDB_CK(cudaMemcpyAsync(lst, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    RoundCtl ctl[3];
+    memset(ctl, 0, sizeof(ctl));
+    ctl[round % 3].count = (int)tiles.size();
+    RDB_CK(cudaMemcpyAsync(&dev.p->ctl[0], ctl, sizeof(ctl), cudaMemcpyHostToDevice, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));  // host vectors go out of scope
+  }
+
+  // run rounds until the worklist is empty; returns the edge_changed bits accumulated
+  int run() {
+    Ctx &c = ctx();
+    FillArgs a;
+    a.Zp = Zp.p;
+    a.Wp = Wp.p;
+    a.pitch = pitch;
+    a.W = W;
+    a.H = H;
+    a.tilesX = tilesX;
+    a.tilesY = tilesY;
+    a.list0 = list0.p;
+    a.list1 = list1.p;
+    a.stamp = stamp.p;
+    a.dev = dev.p;
+    a.max_iters = (int)c.params.fill_max_iters;
+    a.use_tma = (int)c.params.fill_use_tma;
+    const int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 8);
+    FillDev *hd = (FillDev *)c.pinned;
+    RDB_CK(cudaMemsetAsync(&dev.p->edge_changed, 0, sizeof(int), c.stream));
+    for (;;) {
+      KernelTimer kt;  // device time of the sweep launches only (read-back excluded)
+      for (int k = 0; k < per_sync; k++) {
+        a.round = round;
+        fill_sweep_kernel<<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
+        round++;
+      }
+      kt.stop_async();
+      RDB_CK(cudaGetLastError());
+      RDB_CK(cudaMemcpyAsync(hd, dev.p, sizeof(FillDev), cudaMemcpyDeviceToHost, c.stream));
+      RDB_CK(cudaStreamSynchronize(c.stream));
+      c.stats.ms_main_kernel += kt.ms();
+      // rounds that found an empty worklist are not counted as launches of interest
+      c.stats.kernel_launches += per_sync;
+      rounds_run += per_sync;
+      if (hd->ctl[round % 3].count == 0) break;
+      if (round > (1 << 30)) fail("fill: round counter overflow");
+    }
+    c.stats.fill_rounds = rounds_run;
+    c.stats.fill_tile_visits = (int64_t)hd->visits;
+    c.stats.fill_tile_iters = (int64_t)hd->iters;
+    c.stats.fill_tile_cells = TX * TY;
+    return hd->edge_changed;
+  }
+
+  void read_row(int y, float *d_row) {
+    if (y < 0 || y >= H) fail("fill_read_row: row %d out of range", y);
+    RDB_CK(cudaMemcpyAsync(d_row, Wp.p + (size_t)(y + 1) * pitch + PADL, (size_t)W * 4,
+                           cudaMemcpyDeviceToDevice, ctx().stream));
+  }
+
+  void update_row(int y, const float *d_row) {
+    if (y != 0 && y != H - 1) fail("fill_update_row: only boundary rows (0, height-1) can be replaced");
+    Ctx &c = ctx();
+    const size_t o = (size_t)(y + 1) * pitch + PADL;
+    RDB_CK(cudaMemcpyAsync(Wp.p + o, d_row, (size_t)W * 4, cudaMemcpyDeviceToDevice, c.stream));
+    RDB_CK(cudaMemcpyAsync(Zp.p + o, d_row, (size_t)W * 4, cudaMemcpyDeviceToDevice, c.stream));
+    pending_rows.push_back(y);
+  }
+  std::vector<int> pending_rows;
+
+  void activate_pending() {
+    if (pending_rows.empty()) return;
+    std::vector<char> mark((size_t)tilesX * tilesY, 0);
+    std::vector<int> tiles;
+    for (int y : pending_rows) {
+      const int tyT = y / TY;
+      for (int tx = 0; tx < tilesX; tx++) {
+        const int t = tyT * tilesX + tx;
+        if (!mark[t]) {
+          mark[t] = 1;
+          tiles.push_back(t);
+        }
+      }
+    }
+    pending_rows.clear();
+    seed_worklist(tiles);
+  }
+
+  void finish(float *d_out) {
+    Ctx &c = ctx();
+    dim3 blk(256), grd((W + 255) / 256, H < 32768 ? H : 32768);
+    fill_finish_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, d_out, W, H, pitch);
+    RDB_CK(cudaGetLastError());
+    count_launch();
+  }
+};
+
+void fill_depressions_dev(float *d_dem, int w, int h) {
+  Ctx &c = ctx();
+  c.stats.cells = (int64_t)w * h;
+  if (w <= 2 || h <= 2) return;  // every cell is a border cell: nothing can change
+  FillState st;
+  st.begin(d_dem, w, h);
+  st.run();
+  st.finish(d_dem);
+  RDB_CK(cudaStreamSynchronize(c.stream));
+}
+
+}  // namespace rdb
+
+// ---- C ABI: row-band protocol ------------------------------------------------------------
+struct rdb200_fill_state {
+  rdb::FillState st;
+};
+
+namespace rdb {
+int capi_guard_begin();
+void capi_set_error(const char *msg);
+}  // namespace rdb
+
+#define RDB_CAPI_TRY try {
+#define RDB_CAPI_END                 \
+  }                                  \
+  catch (const std::exception &e) {  \
+    rdb::capi_set_error(e.what());   \
+    return 1;                        \
+  }                                  \
+  return 0;
+
+extern "C" {
+
+int rdb200_dev_fill_begin(rdb200_fill_state **state, const float *d_dem, int32_t width, int32_t height) {
+  RDB_CAPI_TRY
+  rdb::ensure_init();
+  if (!state) rdb::fail("fill_begin: null state pointer");
+  if (width < 3 || height < 3) rdb::fail("fill_begin: band must be at least 3x3");
+  auto *s = new rdb200_fill_state();
+  try {
+    s->st.begin(d_dem, width, height);
+  } catch (...) {
+    delete s;
+    throw;
+  }
+  *state = s;
+  RDB_CAPI_END
+}
+
+int rdb200_dev_fill_run(rdb200_fill_state *state, int32_t *changed_rows) {
+  RDB_CAPI_TRY
+  if (!state) rdb::fail("fill_run: null state");
+  state->st.activate_pending();
+  const int ch = state->st.run();
+  if (changed_rows) *changed_rows = ch;
+  RDB_CAPI_END
+}
+
+int rdb200_dev_fill_read_row(rdb200_fill_state *state, int32_t y, float *d_row) {
+  RDB_CAPI_TRY
+  if (!state) rdb::fail("fill_read_row: null state");
+  state->st.read_row(y, d_row);
+  RDB_CK(cudaStreamSynchronize(rdb::ctx().stream));
+  RDB_CAPI_END
+}
+
+int rdb200_dev_fill_update_row(rdb200_fill_state *state, int32_t y, const float *d_row) {
+  RDB_CAPI_TRY
+  if (!state) rdb::fail("fill_update_row: null state");
+  state->st.update_row(y, d_row);
+  RDB_CK(cudaStreamSynchronize(rdb::ctx().stream));
+  RDB_CAPI_END
+}
+
+int rdb200_dev_fill_finish(rdb200_fill_state *state, float *d_out) {
+  RDB_CAPI_TRY
+  if (!state) rdb::fail("fill_finish: null state");
+  if (d_out) {
+    state->st.finish(d_out);
+    RDB_CK(cudaStreamSynchronize(rdb::ctx().stream));
+  }
+  delete state;
+  RDB_CAPI_END
+}
+
+}  // extern "C"

@@ -1,0 +1,352 @@
+// Barnes-2014 flat resolution on B200 (reference flats/flats.hpp:21-28, flats/Barnes2014.hpp).
+//
+// The reference builds the increment mask with serial FIFO floods; its outputs only depend on
+// order-independent quantities, which is what the kernels below compute:
+//   flats     (find_flats.hpp:28-69)     3x3 stencil classification
+//   edges     (Barnes2014.hpp:309-369)   low edge  = NOT_A_FLAT data cell with an equal-elevation
+//                                                     IS_A_FLAT neighbour;
+//                                        high edge = IS_A_FLAT cell with a higher neighbour
+//   labels    (:244-280, :437-441)       8-connected components of exactly-equal elevation that
+//                                        contain a low edge  -> lock-free union-find (atomicCAS hooks
+//                                        onto the smaller root) + path flattening
+//   away      (:62-110)                  1 + multi-source BFS distance from the high edges through
+//                                        same-label IS_A_FLAT cells;  H[label] = max away
+//   towards   (:152-211)                 1 + BFS distance from the low edges (same stepping rule)
+//   mask      (:191-194)                 2*towards + (away>0 ? H[label]-away : 0)
+//   apply     (:496-550)                 interior cells with label!=0: `mask` x nextafter(z,+inf),
+//                                        done as one integer add on the ordered float key
+// BFS levels are level-synchronous launches over compacted frontier arrays; a launch reads its
+// frontier length from device memory, so the host only synchronises every few levels.
+#include "common.cuh"
+
+namespace rdb {
+
+namespace {
+
+constexpr uint8_t FT_FLAT = 1, FT_LOW = 2, FT_HIGH = 4, FT_NODATA = 8;
+
+struct LevelCtl {
+  int count;
+  int pad;
+};
+struct FlatDev {
+  LevelCtl ctl[3];
+  int n_low, n_high, n_flat, n_raised;
+};
+
+// a3: FindFlats
+__global__ void __launch_bounds__(256) flats_classify_kernel(const float *__restrict__ dem, uint8_t *__restrict__ ft,
+                                                              int W, int H, float nodata, FlatDev *dev) {
+  const size_t n = (size_t)W * H;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int isflat = 0;
+  if (i < n) {
+    const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+    const float e = __ldg(dem + i);
+    uint8_t f = 0;
+    if (e == nodata) {
+      f = FT_NODATA;
+    } else if (!(x == 0 || y == 0 || x == W - 1 || y == H - 1)) {
+      f = FT_FLAT;
+#pragma unroll
+      for (int k = 1; k <= 8; k++) {
+        const float ne = __ldg(dem + (size_t)(y + d8dy(k)) * W + (x + d8dx(k)));
+        if (ne < e || ne == nodata) f = 0;  // find_flats.hpp:58-61
+      }
+    }
+    ft[i] = f;
+    isflat = f == FT_FLAT;
+  }
+  const int cnt = __syncthreads_count(isflat);
+  if (threadIdx.x == 0 && cnt) atomicAdd(&dev->n_flat, cnt);
+}
+
+// a4: FindFlatEdges
+__global__ void __launch_bounds__(256) flats_edges_kernel(const float *__restrict__ dem, uint8_t *ft, int W, int H,
+                                                           FlatDev *dev) {
+  const size_t n = (size_t)W * H;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int low = 0, high = 0;
+  if (i < n) {
+    const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+    const uint8_t f = ft[i] & (FT_FLAT | FT_NODATA);
+    if (!(f & FT_NODATA)) {
+      const float e = __ldg(dem + i);
+#pragma unroll
+      for (int k = 1; k <= 8; k++) {
+        const int nx = x + d8dx(k), ny = y + d8dy(k);
+        if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
+        const size_t ni = (size_t)ny * W + nx;
+        const float ne = __ldg(dem + ni);
+        if (f == 0) {
+          if ((ft[ni] & FT_FLAT) && ne == e) low = 1;  // Barnes2014.hpp:343-350
+        } else {
+          if (e < ne) high = 1;  // :354-360
+        }
+      }
+    }
+  }
+  // NOTE: neighbours' FT_FLAT/FT_NODATA bits are final (written by the previous kernel); this
+  // kernel only ORs the edge bits into its own cell, so concurrent reads of bit 0 are safe.
+  if (low | high) ft[i] = (uint8_t)(ft[i] | (low ? FT_LOW : 0) | (high ? FT_HIGH : 0));
+  const int nl = __syncthreads_count(low), nh = __syncthreads_count(high);
+  if (threadIdx.x == 0) {
+    if (nl) atomicAdd(&dev->n_low, nl);
+    if (nh) atomicAdd(&dev->n_high, nh);
+  }
+}
+
+// ---- union-find over exactly-equal elevations --------------------------------------------------
+__device__ __forceinline__ int uf_find(int *parent, int i) {
+  int p = parent[i];
+  while (p != i) {
+    const int gp = parent[p];
+    if (gp != p) parent[i] = gp;  // path halving (benign race: always points to an ancestor)
+    i = p;
+    p = gp;
+  }
+  return i;
+}
+
+__device__ __forceinline__ void uf_union(int *parent, int a, int b) {
+  for (;;) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a > b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    // hook the larger root under the smaller one
+    const int old = atomicCAS(&parent[b], b, a);
+    if (old == b) return;
+  }
+}
+
+__global__ void __launch_bounds__(256) uf_init_kernel(int *parent, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) parent[i] = (int)i;
+}
+
+__global__ void __launch_bounds__(256) uf_union_kernel(const float *__restrict__ dem, const uint8_t *__restrict__ ft,
+                                                        int *parent, int W, int H) {
+  const size_t n = (size_t)W * H;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (ft[i] & FT_NODATA) return;  // a flat's target elevation is a data value (Barnes2014.hpp:257)
+  const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+  const float e = __ldg(dem + i);
+  // forward half of the 8-neighbourhood: E(5), SE(6), S(7), SW(8)
+#pragma unroll
+  for (int k = 5; k <= 8; k++) {
+    const int nx = x + d8dx(k), ny = y + d8dy(k);
+    if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
+    const size_t ni = (size_t)ny * W + nx;
+    if (__ldg(dem + ni) == e && !(ft[ni] & FT_NODATA)) uf_union(parent, (int)i, (int)ni);
+  }
+}
+
+__global__ void __launch_bounds__(256) uf_flatten_mark_kernel(const uint8_t *__restrict__ ft, int *parent,
+                                                               uint8_t *rootflag, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = uf_find(parent, (int)i);
+  parent[i] = r;
+  if (ft[i] & FT_LOW) rootflag[r] = 1;  // this component has an outlet
+}
+
+// ---- BFS ---------------------------------------------------------------------------------------
+template <bool AWAY>
+__global__ void __launch_bounds__(256) bfs_seed_kernel(const uint8_t *__restrict__ ft, const int *__restrict__ labels,
+                                                        int *dist, int *H, int *queue, FlatDev *dev, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t f = ft[i];
+  const bool src = AWAY ? ((f & FT_HIGH) && labels[i] != 0)  // Barnes2014.hpp:445-454
+                        : ((f & FT_LOW) != 0);
+  if (!src) return;
+  dist[i] = 1;
+  if (AWAY) atomicMax(&H[labels[i] - 1], 1);
+  queue[atomicAdd(&dev->ctl[0].count, 1)] = (int)i;
+}
+
+template <bool AWAY>
+__global__ void __launch_bounds__(256) bfs_level_kernel(const uint8_t *__restrict__ ft, const int *__restrict__ labels,
+                                                         int *dist, int *H, int *q0, int *q1, FlatDev *dev, int round,
+                                                         int W, int Hh) {
+  LevelCtl *cur = &dev->ctl[round % 3];
+  LevelCtl *next = &dev->ctl[(round + 1) % 3];
+  const int n = cur->count;
+  if (blockIdx.x == 0 && threadIdx.x == 0) dev->ctl[(round + 2) % 3].count = 0;
+  if (n == 0) return;
+  const int *qc = (round & 1) ? q1 : q0;
+  int *qn = (round & 1) ? q0 : q1;
+  const int level = round + 1;  // distance value of the cells in the current frontier
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int c = qc[idx];
+    const int lab = labels[c];
+    const int y = c / W, x = c - y * W;
+#pragma unroll
+    for (int k = 1; k <= 8; k++) {
+      const int nx = x + d8dx(k), ny = y + d8dy(k);
+      if (nx < 0 || ny < 0 || nx >= W || ny >= Hh) continue;
+      const int ni = ny * W + nx;
+      if (!(ft[ni] & FT_FLAT)) continue;   // :98-104 / :196-206
+      if (labels[ni] != lab) continue;
+      if (dist[ni] != 0) continue;
+      if (atomicCAS(&dist[ni], 0, level + 1) == 0) {
+        qn[atomicAdd(&next->count, 1)] = ni;
+        if (AWAY && H[lab - 1] < level + 1) atomicMax(&H[lab - 1], level + 1);  // flat_height = deepest level, :94
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float advance_ulps(float z, int k) {
+  // k successive nextafterf(z, +inf) (Barnes2014.hpp:527-528) as integer arithmetic
+  if (k <= 0 || z != z) return z;
+  const uint32_t b = __float_as_uint(z);
+  const bool neg = (b >> 31) != 0;
+  const long long mag = (long long)(b & 0x7fffffffu);
+  long long key = neg ? -mag : mag;  // -0.0 and +0.0 share key 0
+  key += k;
+  if (key >= 0x7f800000ll) return __uint_as_float(0x7f800000u);  // saturate at +inf
+  if (key > 0) return __uint_as_float((uint32_t)key);
+  if (key == 0) return neg ? __uint_as_float(0x80000000u) : 0.0f;  // a negative value lands on -0.0
+  return __uint_as_float(0x80000000u | (uint32_t)(-key));
+}
+
+__global__ void __launch_bounds__(256) flats_apply_kernel(float *dem, const int *__restrict__ labels,
+                                                           const int *__restrict__ away, const int *__restrict__ tw,
+                                                           const int *__restrict__ Hh, int32_t *mask_out,
+                                                           int32_t *labels_out, int W, int H, int apply, FlatDev *dev) {
+  const size_t n = (size_t)W * H;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int raised = 0;
+  if (i < n) {
+    const int lab = labels[i];
+    int m = 0;
+    if (lab != 0) {
+      const int t = tw[i];
+      if (t > 0) {
+        const int a = away[i];
+        m = 2 * t + (a > 0 ? Hh[lab - 1] - a : 0);  // :191-194
+      }
+    }
+    if (mask_out) mask_out[i] = m;
+    if (labels_out) labels_out[i] = lab;
+    if (apply && lab != 0 && m > 0) {
+      const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+      if (x > 0 && y > 0 && x < W - 1 && y < H - 1) {  // :511-512 interior only
+        const float z = dem[i];
+        const float z2 = advance_ulps(z, m);
+        dem[i] = z2;
+        raised = 1;
+      }
+    }
+  }
+  const int cnt = __syncthreads_count(raised);
+  if (threadIdx.x == 0 && cnt) atomicAdd(&dev->n_raised, cnt);
+}
+
+__global__ void __launch_bounds__(256) make_labels_kernel(const int *__restrict__ parent, const uint8_t *__restrict__ rootflag,
+                                                           const uint8_t *__restrict__ ft, int *labels, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int lab = 0;
+  if (!(ft[i] & FT_NODATA)) {
+    const int r = parent[i];  // flattened: parent[i] is the root
+    if (rootflag[r]) lab = r + 1;
+  }
+  labels[i] = lab;
+}
+
+template <bool AWAY>
+int run_bfs(const uint8_t *ft, const int *labels, int *dist, int *H, int *q0, int *q1, FlatDev *dev, int w, int h) {
+  Ctx &c = ctx();
+  const size_t n = (size_t)w * h;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  RDB_CK(cudaMemsetAsync(dev->ctl, 0, sizeof(LevelCtl) * 3, c.stream));
+  RDB_CK(cudaMemsetAsync(dist, 0, n * sizeof(int), c.stream));
+  bfs_seed_kernel<AWAY><<<blocks, 256, 0, c.stream>>>(ft, labels, dist, H, q0, dev, n);
+  RDB_CK(cudaGetLastError());
+  count_launch();
+  FlatDev *hd = (FlatDev *)c.pinned;
+  const int grid = c.num_sms * 4;
+  int round = 0;
+  const int per_sync = 32;
+  for (;;) {
+    for (int k = 0; k < per_sync; k++) {
+      bfs_level_kernel<AWAY><<<grid, 256, 0, c.stream>>>(ft, labels, dist, H, q0, q1, dev, round, w, h);
+      round++;
+    }
+    RDB_CK(cudaGetLastError());
+    count_launch(per_sync);
+    RDB_CK(cudaMemcpyAsync(hd, dev, sizeof(FlatDev), cudaMemcpyDeviceToHost, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    if (hd->ctl[round % 3].count == 0) break;
+  }
+  return round;
+}
+
+}  // namespace
+
+// ResolveFlatsEpsilon (apply=true) / GetFlatMask (apply=false, outputs requested)
+void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask_out, int32_t *d_labels_out,
+                       bool apply) {
+  Ctx &c = ctx();
+  const size_t n = (size_t)w * h;
+  c.stats.cells = (int64_t)n;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  DevBuf<uint8_t> ft(n);
+  DevBuf<FlatDev> dev(1);
+  RDB_CK(cudaMemsetAsync(dev.p, 0, sizeof(FlatDev), c.stream));
+  flats_classify_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, w, h, nodata, dev.p);
+  flats_edges_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, w, h, dev.p);
+  RDB_CK(cudaGetLastError());
+  count_launch(2);
+  FlatDev *hd = (FlatDev *)c.pinned;
+  RDB_CK(cudaMemcpyAsync(hd, dev.p, sizeof(FlatDev), cudaMemcpyDeviceToHost, c.stream));
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  const int n_low = hd->n_low, n_flat = hd->n_flat;
+  if (n_low == 0) {  // Barnes2014.hpp:429-435: nothing to resolve
+    if (d_mask_out) RDB_CK(cudaMemsetAsync(d_mask_out, 0, n * sizeof(int32_t), c.stream));
+    if (d_labels_out) RDB_CK(cudaMemsetAsync(d_labels_out, 0, n * sizeof(int32_t), c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    return;
+  }
+
+  // labels
+  DevBuf<int> parent(n), labels(n);
+  DevBuf<uint8_t> rootflag(n);
+  RDB_CK(cudaMemsetAsync(rootflag.p, 0, n, c.stream));
+  uf_init_kernel<<<blocks, 256, 0, c.stream>>>(parent.p, n);
+  uf_union_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, parent.p, w, h);
+  // no unions run concurrently with this pass, so roots are stable and parent[i] ends up being
+  // the true root of every cell
+  uf_flatten_mark_kernel<<<blocks, 256, 0, c.stream>>>(ft.p, parent.p, rootflag.p, n);
+  make_labels_kernel<<<blocks, 256, 0, c.stream>>>(parent.p, rootflag.p, ft.p, labels.p, n);
+  RDB_CK(cudaGetLastError());
+  count_launch(4);
+
+  // gradients
+  DevBuf<int> away(n), tw(n), Hh(n);
+  const size_t qcap = (size_t)n_flat + (size_t)n_low + 16;
+  DevBuf<int> q0(qcap), q1(qcap);
+  RDB_CK(cudaMemsetAsync(Hh.p, 0, n * sizeof(int), c.stream));
+  int levels = 0;
+  levels += run_bfs<true>(ft.p, labels.p, away.p, Hh.p, q0.p, q1.p, dev.p, w, h);
+  levels += run_bfs<false>(ft.p, labels.p, tw.p, Hh.p, q0.p, q1.p, dev.p, w, h);
+  c.stats.flat_bfs_levels = levels;
+
+  flats_apply_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, labels.p, away.p, tw.p, Hh.p, d_mask_out, d_labels_out, w, h,
+                                                   apply ? 1 : 0, dev.p);
+  RDB_CK(cudaGetLastError());
+  count_launch();
+  RDB_CK(cudaMemcpyAsync(hd, dev.p, sizeof(FlatDev), cudaMemcpyDeviceToHost, c.stream));
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  c.stats.flat_cells_raised = hd->n_raised;
+}
+
+}  // namespace rdb

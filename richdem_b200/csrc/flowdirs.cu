@@ -1,0 +1,144 @@
+// Per-cell flow-direction / flow-proportion kernels (pure 3x3 stencils, HBM-bound):
+//   d8_flow_directions  (reference flowmet/d8_flowdirs.hpp:96-123)      4 B in, 1 B out per cell
+//   FM_D8               (reference flowmet/OCallaghan1984.hpp:13-84)    4 B in, 36 B out
+//   FM_Tarboton         (reference flowmet/Tarboton1997.hpp:14-149)     4 B in, 36 B out
+// Neighbour reads go through the read-only path; a warp covers 32 consecutive cells of a row so
+// the three row segments it touches are fetched once from HBM and re-used from L1/L2.
+#include "flowmet.cuh"
+
+namespace rdb {
+
+namespace {
+
+// d8_FlowDir, flowmet/d8_flowdirs.hpp:32-74
+__global__ void d8_flowdirs_kernel(const float *__restrict__ dem, uint8_t *__restrict__ dirs, int W, int H,
+                                   float nodata) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  for (int y = blockIdx.y; y < H; y += gridDim.y) {
+    const size_t i = (size_t)y * W + x;
+    const float e = __ldg(dem + i);
+    uint8_t d;
+    if (e == nodata) {  // :117-118
+      d = 255;
+    } else if (x == 0 || y == 0 || x == W - 1 || y == H - 1) {  // :36-54
+      if (x == 0 && y == 0) d = 2;
+      else if (x == 0 && y == H - 1) d = 8;
+      else if (x == W - 1 && y == 0) d = 4;
+      else if (x == W - 1 && y == H - 1) d = 6;
+      else if (x == 0) d = 1;
+      else if (x == W - 1) d = 5;
+      else if (y == 0) d = 3;
+      else d = 7;
+    } else {
+      float minimum = e;
+      int flowdir = 0;
+#pragma unroll
+      for (int n = 1; n <= 8; n++) {  // :63-71 (NoData neighbours are NOT skipped here)
+        const float ne = __ldg(dem + (size_t)(y + d8dy(n)) * W + (x + d8dx(n)));
+        if (ne < minimum || (ne == minimum && flowdir > 0 && (flowdir & 1) == 0 && (n & 1) == 1)) {
+          minimum = ne;
+          flowdir = n;
+        }
+      }
+      d = (uint8_t)flowdir;
+    }
+    dirs[i] = d;
+  }
+}
+
+// materialised proportions: 256 cells per block staged through shared memory so the 36 B/cell
+// AoS output leaves as coalesced float4 stores
+template <bool DINF>
+__global__ void __launch_bounds__(256) fm_props_kernel(const float *__restrict__ dem, float *__restrict__ props,
+                                                        int W, int H, float nodata) {
+  __shared__ __align__(16) float s[256 * 9];
+  const size_t n = (size_t)W * H;
+  const size_t base = (size_t)blockIdx.x * 256;
+  const size_t i = base + threadIdx.x;
+  float p[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) p[k] = kNoFlowGen;
+  if (i < n) {
+    const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+    if (DINF) {
+      float rmax = 0;
+      const int nm = fm_tarboton_cell(dem, x, y, W, H, nodata, &rmax);
+      if (nm == kCodeNoData) {
+        p[0] = kNoDataGen;
+      } else if (nm > 0) {
+        p[0] = kHasFlowGen;
+        const int nn = nwrap(nm + 1);
+        float p1 = 0, p2 = 0;
+        int n1 = 0, n2 = 0;  // slots to write
+        if (rmax == 0.0f) {
+          n1 = nm;
+          p1 = 1.0f;
+        } else if (rmax == kDang) {
+          n1 = nn;
+          p1 = 1.0f;
+        } else {
+          tarboton_props(rmax, &p1, &p2);
+          n1 = nm;
+          n2 = nn;
+        }
+#pragma unroll
+        for (int k = 1; k <= 8; k++) {
+          if (k == n1) p[k] = p1;
+          if (k == n2) p[k] = p2;
+        }
+      }
+    } else {
+      const int c = fm_d8_cell(dem, x, y, W, H, nodata);
+      if (c == kCodeNoData) {
+        p[0] = kNoDataGen;
+      } else if (c > 0) {
+        p[0] = kHasFlowGen;
+#pragma unroll
+        for (int k = 1; k <= 8; k++)
+          if (k == c) p[k] = 1.0f;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; k++) s[threadIdx.x * 9 + k] = p[k];
+  __syncthreads();
+  const size_t cells_here = (base + 256 <= n) ? 256 : (n > base ? n - base : 0);
+  const size_t floats_here = cells_here * 9;
+  float *out = props + base * 9;  // 256*36 B per block keeps float4 alignment
+  if (cells_here == 256) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(s);
+    float4 *o4 = reinterpret_cast<float4 *>(out);
+    for (int k = threadIdx.x; k < 256 * 9 / 4; k += 256) __stcs(o4 + k, s4[k]);
+  } else {
+    for (size_t k = threadIdx.x; k < floats_here; k += 256) out[k] = s[k];
+  }
+}
+
+}  // namespace
+
+void d8_flow_directions_dev(const float *d_dem, uint8_t *d_dirs, int w, int h, float nodata) {
+  Ctx &c = ctx();
+  dim3 blk(128), grd((w + 127) / 128, h < 16384 ? h : 16384);
+  d8_flowdirs_kernel<<<grd, blk, 0, c.stream>>>(d_dem, d_dirs, w, h, nodata);
+  RDB_CK(cudaGetLastError());
+  count_launch();
+}
+
+void fm_d8_dev(const float *d_dem, float *d_props, int w, int h, float nodata) {
+  Ctx &c = ctx();
+  const size_t n = (size_t)w * h;
+  fm_props_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d_dem, d_props, w, h, nodata);
+  RDB_CK(cudaGetLastError());
+  count_launch();
+}
+
+void fm_tarboton_dev(const float *d_dem, float *d_props, int w, int h, float nodata) {
+  Ctx &c = ctx();
+  const size_t n = (size_t)w * h;
+  fm_props_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d_dem, d_props, w, h, nodata);
+  RDB_CK(cudaGetLastError());
+  count_launch();
+}
+
+}  // namespace rdb
