@@ -52,6 +52,10 @@ RDB200_API void rdb200_shutdown(void);
 RDB200_API const char *rdb200_last_error(void);
 RDB200_API int rdb200_version(void);
 
+/* Run all subsequent work on the caller's CUDA stream (a cudaStream_t; NULL restores the
+ * library's own stream).  Lets a caller bracket calls with its own CUDA events. */
+RDB200_API int rdb200_set_stream(void *cuda_stream);
+
 /* Counters of the most recent call (for benchmarks / roofline accounting). */
 typedef struct rdb200_stats {
   int64_t cells;             /* width*height of the raster processed                       */

@@ -19,6 +19,8 @@
 #include <richdem/methods/d8_methods.hpp>
 #include <richdem/methods/flow_accumulation.hpp>
 
+#include <omp.h>
+
 #include <cstdint>
 #include <cstring>
 
@@ -91,7 +93,12 @@ void ref_d8_flow_accum_u8_i32(const uint8_t *dirs, int w, int h, int32_t *area) 
   Array2D<uint8_t> d(const_cast<uint8_t *>(dirs), w, h);
   d.setNoData(FLOWDIR_NO_DATA);
   Array2D<int32_t> a;
+  // the reference's dependency pass increments shared counters from an OpenMP loop without
+  // synchronisation (d8_methods.hpp:68-92); run it single-threaded so the oracle is deterministic
+  const int nt = omp_get_max_threads();
+  omp_set_num_threads(1);
   d8_flow_accum(d, a);
+  omp_set_num_threads(nt);
   std::memcpy(area, a.data(), sizeof(int32_t) * (size_t)w * h);
 }
 
@@ -101,7 +108,10 @@ void ref_d8_flow_accum_i32_i32(const int32_t *dirs, int w, int h, int32_t nodata
   Array2D<int32_t> d(const_cast<int32_t *>(dirs), w, h);
   d.setNoData(nodata);
   Array2D<int32_t> a;
+  const int nt = omp_get_max_threads();
+  omp_set_num_threads(1);
   d8_flow_accum(d, a);
+  omp_set_num_threads(nt);
   std::memcpy(area, a.data(), sizeof(int32_t) * (size_t)w * h);
 }
 

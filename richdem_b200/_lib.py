@@ -38,6 +38,7 @@ class Stats(C.Structure):
 _i32, _f32, _vp = C.c_int32, C.c_float, C.c_void_p
 SIGNATURES = {
     "rdb200_init": [C.c_int],
+    "rdb200_set_stream": [C.c_void_p],
     "rdb200_get_stats": [C.POINTER(Stats)],
     "rdb200_set_param": [C.c_char_p, C.c_int64],
     "rdb200_fill_depressions_d8_f32": [_vp, _i32, _i32],
@@ -112,6 +113,11 @@ def set_param(name: str, value: int) -> None:
 
 def init(device: int = 0) -> None:
     check(lib().rdb200_init(int(device)))
+
+
+def set_stream(cuda_stream) -> None:
+    """Run subsequent work on `cuda_stream` (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+    check(lib().rdb200_set_stream(C.c_void_p(int(cuda_stream) if cuda_stream else None)))
 
 
 def shutdown() -> None:

@@ -34,7 +34,8 @@ static void init_device(int device) {
          prop.minor);
   c.device = device;
   c.num_sms = prop.multiProcessorCount;
-  RDB_CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  RDB_CK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+  c.stream = c.own_stream;
   RDB_CK(cudaEventCreate(&c.ev0));
   RDB_CK(cudaEventCreate(&c.ev1));
   RDB_CK(cudaEventCreate(&c.evk0));
@@ -194,12 +195,21 @@ void rdb200_shutdown(void) {
   cudaEventDestroy(c.ev1);
   cudaEventDestroy(c.evk0);
   cudaEventDestroy(c.evk1);
-  cudaStreamDestroy(c.stream);
+  cudaStreamDestroy(c.own_stream);
   c = Ctx();
 }
 
 const char *rdb200_last_error(void) { return g_last_error.c_str(); }
 int rdb200_version(void) { return RDB200_VERSION; }
+
+int rdb200_set_stream(void *cuda_stream) {
+  CAPI_TRY
+  ensure_init();
+  Ctx &c = ctx();
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  c.stream = cuda_stream ? (cudaStream_t)cuda_stream : c.own_stream;
+  CAPI_END
+}
 
 int rdb200_get_stats(rdb200_stats *out) {
   CAPI_TRY

@@ -68,7 +68,8 @@ struct Ctx {
   bool inited = false;
   int device = -1;
   int num_sms = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // stream all work runs on
+  cudaStream_t own_stream = nullptr;  // the library's default stream
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   std::vector<WsBlock> ws;
   void *pinned = nullptr;  // small pinned scratch for read-backs

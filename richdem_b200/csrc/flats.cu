@@ -147,13 +147,17 @@ __global__ void __launch_bounds__(256) uf_union_kernel(const float *__restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) uf_flatten_mark_kernel(const uint8_t *__restrict__ ft, int *parent,
-                                                               uint8_t *rootflag, size_t n) {
+// Read-only root lookup (no path compression here: concurrent halving stores could overwrite a
+// neighbour's freshly flattened entry with a non-root ancestor).  Writes the root of every data
+// cell to `root_of` and flags roots whose component holds a low edge (an outlet).
+__global__ void __launch_bounds__(256) uf_roots_kernel(const uint8_t *__restrict__ ft, const int *__restrict__ parent,
+                                                        int *__restrict__ root_of, uint8_t *rootflag, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int r = uf_find(parent, (int)i);
-  parent[i] = r;
-  if (ft[i] & FT_LOW) rootflag[r] = 1;  // this component has an outlet
+  int r = (int)i;
+  for (int p = parent[r]; p != r; p = parent[r]) r = p;
+  root_of[i] = r;
+  if (ft[i] & FT_LOW) rootflag[r] = 1;
 }
 
 // ---- BFS ---------------------------------------------------------------------------------------
@@ -250,13 +254,14 @@ __global__ void __launch_bounds__(256) flats_apply_kernel(float *dem, const int 
   if (threadIdx.x == 0 && cnt) atomicAdd(&dev->n_raised, cnt);
 }
 
-__global__ void __launch_bounds__(256) make_labels_kernel(const int *__restrict__ parent, const uint8_t *__restrict__ rootflag,
+// label = root+1 for data cells of components holding a low edge, else 0 (Barnes2014.hpp:437-441)
+__global__ void __launch_bounds__(256) make_labels_kernel(const uint8_t *__restrict__ rootflag,
                                                            const uint8_t *__restrict__ ft, int *labels, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int lab = 0;
   if (!(ft[i] & FT_NODATA)) {
-    const int r = parent[i];  // flattened: parent[i] is the root
+    const int r = labels[i];  // root_of[i]
     if (rootflag[r]) lab = r + 1;
   }
   labels[i] = lab;
@@ -323,10 +328,8 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   RDB_CK(cudaMemsetAsync(rootflag.p, 0, n, c.stream));
   uf_init_kernel<<<blocks, 256, 0, c.stream>>>(parent.p, n);
   uf_union_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, parent.p, w, h);
-  // no unions run concurrently with this pass, so roots are stable and parent[i] ends up being
-  // the true root of every cell
-  uf_flatten_mark_kernel<<<blocks, 256, 0, c.stream>>>(ft.p, parent.p, rootflag.p, n);
-  make_labels_kernel<<<blocks, 256, 0, c.stream>>>(parent.p, rootflag.p, ft.p, labels.p, n);
+  uf_roots_kernel<<<blocks, 256, 0, c.stream>>>(ft.p, parent.p, labels.p, rootflag.p, n);
+  make_labels_kernel<<<blocks, 256, 0, c.stream>>>(rootflag.p, ft.p, labels.p, n);
   RDB_CK(cudaGetLastError());
   count_launch(4);
 

@@ -1,0 +1,158 @@
+"""Row-band sharding of the hot path across GPUs: one process per GPU, ``torch.distributed`` for
+the plumbing (NCCL over NVLink on the GPU box, gloo in the CPU unit tests).
+
+A raster of H rows is cut into G contiguous row bands (row-major memory => a band is one
+contiguous slab).  Rank g owns rows [r0, r1) and works on a *local raster* made of its rows plus
+one ghost row on every side that touches another band.  The reference's own answer to distribution
+is a two-round tile farm over MPI (programs/parallel_priority_flood/main.cpp:603-823); here the
+exchange is a one-row halo (W*4 bytes per neighbour) plus a one-int all-reduce per global round.
+
+Fill protocol (every value exchanged is a monotonically decreasing upper bound of the answer):
+
+    state = begin(local raster, ghost rows = +inf)
+    repeat:
+        run(state)                      # relax the band to its local fixed point (many sweeps)
+        send own edge rows to the neighbours, receive theirs
+        if no rank's edge rows changed: break
+        update ghost rows with what was received
+    finish(state)
+
+The band solver is pluggable so that the protocol can be unit-tested on CPU (gloo, world_size 2)
+with a stand-in solver supplied by the test; the product always uses :class:`CudaBandSolver`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+try:  # torch is only needed for the distributed entry points
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def band_bounds(height: int, world: int) -> List[Tuple[int, int]]:
+    """Row ranges [r0, r1) of the ``world`` bands (sizes differ by at most one row)."""
+    if world < 1:
+        raise ValueError("world size must be >= 1")
+    if height < world:
+        raise ValueError(f"cannot cut {height} rows into {world} bands")
+    base, extra = divmod(height, world)
+    out, r = [], 0
+    for g in range(world):
+        n = base + (1 if g < extra else 0)
+        out.append((r, r + n))
+        r += n
+    return out
+
+
+def local_rows(height: int, world: int, rank: int) -> Tuple[int, int, int, int]:
+    """(r0, r1, g_top, g_bot): owned rows and number of ghost rows above / below (0 or 1)."""
+    r0, r1 = band_bounds(height, world)[rank]
+    return r0, r1, (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
+
+
+class CudaBandSolver:
+    """The product band solver: librichdem_b200's row-band fill entry points on device memory."""
+
+    def __init__(self, local_dem: "torch.Tensor"):
+        from . import _lib
+        assert local_dem.is_cuda and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
+        self._lib = _lib
+        self.h, self.w = local_dem.shape
+        self.device = local_dem.device
+        self._state = C.c_void_p()
+        _lib.check(_lib.lib().rdb200_dev_fill_begin(C.byref(self._state), local_dem.data_ptr(), self.w, self.h))
+
+    def run(self) -> int:
+        ch = C.c_int32(0)
+        self._lib.check(self._lib.lib().rdb200_dev_fill_run(self._state, C.byref(ch)))
+        return int(ch.value)
+
+    def read_row(self, y: int) -> "torch.Tensor":
+        row = torch.empty(self.w, dtype=torch.float32, device=self.device)
+        self._lib.check(self._lib.lib().rdb200_dev_fill_read_row(self._state, y, row.data_ptr()))
+        return row
+
+    def update_row(self, y: int, row: "torch.Tensor") -> None:
+        assert row.is_cuda and row.dtype == torch.float32 and row.numel() == self.w
+        self._lib.check(self._lib.lib().rdb200_dev_fill_update_row(self._state, y, row.contiguous().data_ptr()))
+
+    def finish(self) -> "torch.Tensor":
+        out = torch.empty((self.h, self.w), dtype=torch.float32, device=self.device)
+        self._lib.check(self._lib.lib().rdb200_dev_fill_finish(self._state, out.data_ptr()))
+        self._state = None
+        return out
+
+
+def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None, group=None,
+              max_rounds: int = 100000):
+    """Fill this rank's band.  ``local_dem`` is (g_top + owned + g_bot) x W with the ghost rows'
+    contents ignored (they are initialised to +inf).  Returns (filled local raster incl. ghost rows,
+    number of exchange rounds).  Collective: every rank of ``group`` must call it."""
+    solver_cls = solver_cls or CudaBandSolver
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    h, w = local_dem.shape
+    if g_top:
+        local_dem[0].fill_(float("inf"))
+    if g_bot:
+        local_dem[h - 1].fill_(float("inf"))
+    solver = solver_cls(local_dem)
+    rounds = 0
+    while True:
+        changed = solver.run()
+        rounds += 1
+        if world == 1:
+            break
+        # rows my neighbours hold as ghosts: local row 1 (if there is a band above), row h-2 (below)
+        my_change = 0
+        if g_top and (changed & 1 or rounds == 1):
+            my_change = 1
+        if g_bot and (changed & 2 or rounds == 1):
+            my_change = 1
+        flag = torch.tensor([my_change], dtype=torch.int32, device=local_dem.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()) == 0:
+            break
+        ops, recv_up, recv_dn = [], None, None
+        if g_top:
+            send_up = solver.read_row(1)
+            recv_up = torch.empty_like(send_up)
+            ops += [dist.P2POp(dist.isend, send_up, rank - 1, group), dist.P2POp(dist.irecv, recv_up, rank - 1, group)]
+        if g_bot:
+            send_dn = solver.read_row(h - 2)
+            recv_dn = torch.empty_like(send_dn)
+            ops += [dist.P2POp(dist.isend, send_dn, rank + 1, group), dist.P2POp(dist.irecv, recv_dn, rank + 1, group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if recv_up is not None:
+            solver.update_row(0, recv_up)
+        if recv_dn is not None:
+            solver.update_row(h - 1, recv_dn)
+        if rounds >= max_rounds:
+            raise RuntimeError("fill_band: exchange rounds exceeded max_rounds")
+    return solver.finish(), rounds
+
+
+def scatter_rows(full: Optional[np.ndarray], height: int, width: int, dtype, device, group=None):
+    """Convenience for tests/bench: rank 0 holds ``full`` (H x W numpy); every rank receives its
+    local raster (owned rows + ghost rows, ghost contents = neighbour's rows) as a tensor."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    r0, r1, gt, gb = local_rows(height, world, rank)
+    if world == 1:
+        return torch.as_tensor(np.ascontiguousarray(full), device=device).to(dtype).contiguous(), (r0, r1, gt, gb)
+    local = torch.empty((r1 - r0 + gt + gb, width), dtype=dtype, device=device)
+    if rank == 0:
+        for g in range(1, world):
+            a0, a1, at, ab = local_rows(height, world, g)
+            dist.send(torch.as_tensor(np.ascontiguousarray(full[a0 - at:a1 + ab]), device=device).to(dtype), g, group)
+        local.copy_(torch.as_tensor(np.ascontiguousarray(full[r0 - gt:r1 + gb]), device=device).to(dtype))
+    else:
+        dist.recv(local, 0, group)
+    return local, (r0, r1, gt, gb)

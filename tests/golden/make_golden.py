@@ -1,0 +1,113 @@
+"""Regenerates the golden fixtures under tests/golden/ (run in the build container only).
+
+Sources, all under /root/reference (never copied as source; only test DATA is re-encoded):
+  * tests/depressions/testdem1.dem -> testdem1.all.out   known-answer fill (tests/tests.cpp:238-271)
+  * tests/flow_accum/*.d8 -> *.out                        known-answer d8_flow_accum (tests/tests.cpp:135-146)
+  * data/*.dem                                             hand-made flat-resolution / D-infinity inputs
+  * docs/imgs/beauford.npz                                 the Beauford DEM (crop with NoData)
+and outputs of the UNMODIFIED reference implementation (oracle/_ref, built by oracle/Makefile from
+/root/reference/include) on those inputs and on seeded synthetic DEMs.
+"""
+import glob
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def read_ascii_grid(path):
+    """ESRI ASCII grid: 6 header lines then rows."""
+    with open(path) as f:
+        toks = f.read().split()
+    hdr = {toks[2 * i].lower(): float(toks[2 * i + 1]) for i in range(6)}
+    ncols, nrows = int(hdr["ncols"]), int(hdr["nrows"])
+    vals = np.array(toks[12:12 + ncols * nrows], dtype=np.float64).reshape(nrows, ncols)
+    return vals, hdr["nodata_value"]
+
+
+def main():
+    R = oracle.ref()
+
+    # 1. fill known-answer
+    dem, nd = read_ascii_grid(f"{REF}/tests/depressions/testdem1.dem")
+    exp, _ = read_ascii_grid(f"{REF}/tests/depressions/testdem1.all.out")
+    np.savez_compressed(f"{OUT}/fill_testdem1.npz", dem=dem.astype(np.float32), expected=exp.astype(np.float32),
+                        nodata=np.float32(nd))
+
+    # 2. d8_flow_accum known-answers
+    names, d8s, outs, nds = [], [], [], []
+    for p in sorted(glob.glob(f"{REF}/tests/flow_accum/*.d8")):
+        o = p[:-3] + ".out"
+        if not os.path.exists(o):
+            continue
+        a, nda = read_ascii_grid(p)
+        b, _ = read_ascii_grid(o)
+        names.append(os.path.basename(p)[:-3])
+        d8s.append(a.astype(np.int32))
+        outs.append(b.astype(np.int32))
+        nds.append(int(nda))
+    fa = {"names": np.array(names), "d8_nodata": np.array(nds, np.int32)}
+    for nm, a, b in zip(names, d8s, outs):
+        fa[nm + "__d8"] = a
+        fa[nm + "__out"] = b
+    np.savez_compressed(f"{OUT}/flow_accum_fixtures.npz", **fa)
+
+    # 3. hand-made flats / dinf inputs with reference outputs
+    flat_cases = {}
+    for p in sorted(glob.glob(f"{REF}/data/*.dem")):
+        a, nda = read_ascii_grid(p)
+        a32 = a.astype(np.float32)
+        key = os.path.basename(p)[:-4]
+        flat_cases[key + "__dem"] = a32
+        flat_cases[key + "__nodata"] = np.float32(nda)
+        flat_cases[key + "__resolved"] = R.resolve_flats(a32, float(nda))
+        m, l = R.flat_mask(a32, float(nda))
+        flat_cases[key + "__mask"] = m
+        flat_cases[key + "__labeled"] = (l != 0)
+        flat_cases[key + "__filled"] = R.fill_depressions(a32)
+        flat_cases[key + "__dirs"] = R.d8_flow_directions(a32, float(nda))
+        flat_cases[key + "__fm_d8"] = R.fm_d8(a32, float(nda))
+        flat_cases[key + "__fm_dinf"] = R.fm_dinf(a32, float(nda))
+    np.savez_compressed(f"{OUT}/data_dems.npz", **flat_cases)
+
+    # 4. Beauford crop (has NoData = -9999) through the whole reference pipeline
+    b = np.load(f"{REF}/docs/imgs/beauford.npz")["beauford"]
+    crop = np.ascontiguousarray(b[300:620, 300:700])
+    nd = -9999.0
+    filled = R.fill_depressions(crop, "fill_zhou")
+    resolved = R.resolve_flats(filled, nd)
+    np.savez_compressed(
+        f"{OUT}/beauford_crop.npz", dem=crop, nodata=np.float32(nd), filled=filled, resolved=resolved,
+        dirs=R.d8_flow_directions(resolved, nd), fa_d8=R.fa_d8(resolved, nd), fa_dinf=R.fa_dinf(resolved, nd),
+        fm_dinf_nz=np.float32(R.fm_dinf(resolved, nd)).reshape(-1, 9)[::7],  # every 7th cell's 9 slots
+    )
+
+    # 5. seeded synthetic DEMs (inputs are regenerated at test time from the seed)
+    syn = {}
+    for seed, (h, w), q in [(101, (180, 260), None), (102, (200, 150), 0.5), (103, (256, 256), 2.0)]:
+        dem = oracle.fbm_terrain(h, w, seed=seed, quantum=q)
+        f = R.fill_depressions(dem)
+        r = R.resolve_flats(f, -9999.0)
+        k = f"s{seed}"
+        syn[k + "__shape"] = np.array([h, w])
+        syn[k + "__quantum"] = np.float64(q if q else 0)
+        syn[k + "__dem"] = dem
+        syn[k + "__filled"] = f
+        syn[k + "__resolved"] = r
+        syn[k + "__dirs"] = R.d8_flow_directions(r, -9999.0)
+        syn[k + "__fa_d8"] = R.fa_d8(r, -9999.0)
+        syn[k + "__fa_dinf"] = R.fa_dinf(r, -9999.0)
+    np.savez_compressed(f"{OUT}/synthetic_ref.npz", **syn)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

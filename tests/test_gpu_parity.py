@@ -1,0 +1,237 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Every call goes through the C ABI of
+librichdem_b200.so (via the Python mirror of the reference API) and is compared with the CPU
+checker on the same inputs: bit-exact for filled elevations, flat masks, resolved elevations,
+direction grids, FM_D8 proportions and unit-weight D8 accumulation; <= 1 float ulp for D-infinity
+proportions; 1e-9 relative (north_star allows 1e-5) for weighted / D-infinity accumulation."""
+import numpy as np
+import pytest
+
+import oracle
+import richdem_b200 as rd
+from richdem_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+ND = -9999.0
+ACC_RTOL = 1e-9  # north_star tolerance is 1e-5 relative; only atomic-add ordering differs
+
+
+def R(a, nd=ND):
+    return rd.rdarray(np.ascontiguousarray(a), no_data=nd)
+
+
+def ulp_diff(a, b):
+    return np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+
+
+def check_pipeline(dem, nd, O, accum_weights=None):
+    filled = np.asarray(rd.FillDepressions(R(dem, nd)))
+    f_ref = O.fill_depressions(dem)
+    assert np.array_equal(filled, f_ref), f"fill: {(filled != f_ref).sum()} cells differ"
+    m, l = rd.FlatMask(R(f_ref, nd))
+    m_ref, l_ref = O.flat_mask(f_ref, nd)
+    assert np.array_equal(l != 0, l_ref != 0), "flat labels (membership) differ"
+    assert np.array_equal(m, m_ref), f"flat mask: {(m != m_ref).sum()} cells differ"
+    # same partition: label pairs must be in bijection
+    pairs = np.unique(np.stack([l[l != 0], l_ref[l_ref != 0]]), axis=1)
+    assert len(np.unique(pairs[0])) == pairs.shape[1] == len(np.unique(pairs[1]))
+    res = np.asarray(rd.ResolveFlats(R(f_ref, nd)))
+    r_ref = O.resolve_flats(f_ref, nd)
+    assert np.array_equal(res.view(np.uint32), r_ref.view(np.uint32)), "resolve_flats bits differ"
+    assert np.array_equal(np.asarray(rd.FlowDirectionsD8(R(r_ref, nd))), O.d8_flow_directions(r_ref, nd))
+    dirs = O.d8_flow_directions(r_ref, nd)
+    assert np.array_equal(np.asarray(rd.D8FlowAccum(dirs)), O.d8_flow_accum(dirs))
+    assert np.array_equal(np.asarray(rd.FlowProportions(R(r_ref, nd), "D8")), O.fm_d8(r_ref, nd))
+    pg, pr = np.asarray(rd.FlowProportions(R(r_ref, nd), "Dinf")), O.fm_dinf(r_ref, nd)
+    assert np.array_equal(pg > 0, pr > 0), "D-infinity facet choice differs"
+    assert ulp_diff(pg, pr).max() <= 1
+    a = rd.FlowAccumulation(R(r_ref, nd), "D8")
+    assert a.no_data == -1 and a.dtype == np.float64
+    assert np.array_equal(np.asarray(a), O.fa_d8(r_ref, nd)), "unit-weight D8 accumulation must be exact"
+    np.testing.assert_allclose(np.asarray(rd.FlowAccumulation(R(r_ref, nd), "Dinf")), O.fa_dinf(r_ref, nd),
+                               rtol=ACC_RTOL, atol=0)
+    if accum_weights is not None:
+        w = R(accum_weights, -1)
+        np.testing.assert_allclose(np.asarray(rd.FlowAccumulation(R(r_ref, nd), "D8", weights=w)),
+                                   O.fa_d8(r_ref, nd, accum_weights), rtol=ACC_RTOL, atol=0)
+        np.testing.assert_allclose(np.asarray(rd.FlowAccumulation(R(r_ref, nd), "Tarboton", weights=w)),
+                                   O.fa_dinf(r_ref, nd, accum_weights), rtol=ACC_RTOL, atol=0)
+    np.testing.assert_allclose(np.asarray(rd.FlowAccumFromProps(rd.rd3array(pr, no_data=-2))),
+                               O.flow_accumulation(pr), rtol=ACC_RTOL, atol=0)
+    pd8 = O.fm_d8(r_ref, nd)
+    assert np.array_equal(np.asarray(rd.FlowAccumFromProps(rd.rd3array(pd8, no_data=-2))), O.flow_accumulation(pd8))
+
+
+# ---- golden fixtures -------------------------------------------------------------------------
+def test_fill_known_answer(golden):
+    g = golden["fill_testdem1"]
+    assert np.array_equal(np.asarray(rd.FillDepressions(R(g["dem"], float(g["nodata"])))), g["expected"])
+
+
+def test_d8_flow_accum_known_answers(golden):
+    g = golden["flow_accum_fixtures"]
+    for name, nd in zip(g["names"], g["d8_nodata"]):
+        d = g[f"{name}__d8"]
+        u8 = np.where(d == nd, 255, d).astype(np.uint8)
+        assert np.array_equal(np.asarray(rd.D8FlowAccum(u8)), g[f"{name}__out"]), name
+
+
+def test_data_dems(golden):
+    g = golden["data_dems"]
+    for k in sorted({k.split("__")[0] for k in g.files}):
+        dem, nd = g[f"{k}__dem"], float(g[f"{k}__nodata"])
+        assert np.array_equal(np.asarray(rd.FillDepressions(R(dem, nd))), g[f"{k}__filled"]), k
+        assert np.array_equal(np.asarray(rd.ResolveFlats(R(dem, nd))), g[f"{k}__resolved"]), k
+        m, l = rd.FlatMask(R(dem, nd))
+        assert np.array_equal(m, g[f"{k}__mask"]) and np.array_equal(l != 0, g[f"{k}__labeled"]), k
+        assert np.array_equal(np.asarray(rd.FlowDirectionsD8(R(dem, nd))), g[f"{k}__dirs"]), k
+        assert np.array_equal(np.asarray(rd.FlowProportions(R(dem, nd), "D8")), g[f"{k}__fm_d8"]), k
+        assert ulp_diff(np.asarray(rd.FlowProportions(R(dem, nd), "Dinf")), g[f"{k}__fm_dinf"]).max() <= 1, k
+
+
+def test_beauford_crop_golden(golden):
+    g = golden["beauford_crop"]
+    dem, nd = g["dem"], float(g["nodata"])
+    filled = rd.FillDepressions(R(dem, nd))
+    assert np.array_equal(np.asarray(filled), g["filled"])
+    resolved = rd.ResolveFlats(filled)
+    assert np.array_equal(np.asarray(resolved), g["resolved"])
+    assert np.array_equal(np.asarray(rd.FlowDirectionsD8(resolved)), g["dirs"])
+    assert np.array_equal(np.asarray(rd.FlowAccumulation(resolved, "D8")), g["fa_d8"])
+    np.testing.assert_allclose(np.asarray(rd.FlowAccumulation(resolved, "Dinf")), g["fa_dinf"], rtol=ACC_RTOL)
+
+
+def test_synthetic_golden(golden):
+    g = golden["synthetic_ref"]
+    for seed in (101, 102, 103):
+        k = f"s{seed}"
+        filled = rd.FillDepressions(R(g[f"{k}__dem"]))
+        assert np.array_equal(np.asarray(filled), g[f"{k}__filled"])
+        resolved = rd.ResolveFlats(filled)
+        assert np.array_equal(np.asarray(resolved), g[f"{k}__resolved"])
+        assert np.array_equal(np.asarray(rd.FlowAccumulation(resolved, "D8")), g[f"{k}__fa_d8"])
+
+
+# ---- oracle comparisons on seeded inputs -----------------------------------------------------
+@pytest.mark.parametrize("shape,seed,q,patch", [
+    ((150, 220), 1, None, False), ((257, 131), 2, 0.5, False), ((400, 500), 3, 2.0, True),
+    ((65, 129), 4, 1.0, False), ((64, 64), 5, 10.0, False), ((63, 200), 6, None, True),
+    ((1024, 1024), 7, None, False), ((777, 1025), 8, 1.0, True),
+])
+def test_pipeline_vs_oracle(checker, shape, seed, q, patch):
+    dem = oracle.fbm_terrain(*shape, seed=seed, quantum=q)
+    if patch:
+        h, w = shape
+        dem[h // 4: h // 4 + h // 8, w // 3: w // 3 + w // 6] = ND
+        dem[0: h // 10, 0: w // 10] = ND
+    wts = np.random.default_rng(seed).random(shape)
+    check_pipeline(dem, ND, checker, accum_weights=wts)
+
+
+def test_pipeline_vs_oracle_large(checker):
+    dem = oracle.fbm_terrain(2048, 3000, seed=21, quantum=0.5)
+    check_pipeline(dem, ND, checker)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 7), (2, 2), (3, 3), (3, 64), (5, 1), (4, 130)])
+def test_degenerate_shapes(checker, shape):
+    dem = (np.random.default_rng(3).random(shape) * 10).astype(np.float32)
+    check_pipeline(dem, ND, checker)
+
+
+def test_special_rasters(checker):
+    flat = np.full((70, 90), 5.0, np.float32)                 # one big undrainable flat
+    check_pipeline(flat, ND, checker)
+    allnd = np.full((40, 50), ND, np.float32)                 # everything NoData
+    check_pipeline(allnd, ND, checker)
+    bowl = np.fromfunction(lambda y, x: (y - 40) ** 2 + (x - 50) ** 2, (81, 101)).astype(np.float32)
+    check_pipeline(bowl, ND, checker)                         # one deep pit -> big drainable flat
+    neg = -oracle.fbm_terrain(100, 100, seed=9, quantum=1.0)  # negative elevations and zeros
+    check_pipeline(neg - neg.max() / 2, ND, checker)
+    tiny = (oracle.fbm_terrain(90, 90, seed=10, quantum=50.0) * 1e-42).astype(np.float32)  # denormals
+    check_pipeline(tiny, ND, checker)
+
+
+def test_non_tma_staging_gives_identical_fill(checker):
+    dem = oracle.fbm_terrain(500, 700, seed=12)
+    a = np.asarray(rd.FillDepressions(R(dem)))
+    _lib.set_param("fill_use_tma", 0)
+    try:
+        b = np.asarray(rd.FillDepressions(R(dem)))
+    finally:
+        _lib.set_param("fill_use_tma", 1)
+    assert np.array_equal(a, b) and np.array_equal(a, checker.fill_depressions(dem))
+
+
+def test_capped_in_tile_iterations_converge_to_same_answer(checker):
+    dem = oracle.fbm_terrain(600, 600, seed=13)
+    _lib.set_param("fill_max_iters", 2)
+    try:
+        a = np.asarray(rd.FillDepressions(R(dem)))
+    finally:
+        _lib.set_param("fill_max_iters", 0)
+    assert np.array_equal(a, checker.fill_depressions(dem))
+
+
+def test_in_place_and_copy_semantics():
+    dem = R(oracle.fbm_terrain(128, 128, seed=14))
+    orig = np.array(dem)
+    out = rd.FillDepressions(dem)
+    assert out is not dem and np.array_equal(np.asarray(dem), orig)
+    assert rd.FillDepressions(dem, in_place=True) is None
+    assert np.array_equal(np.asarray(dem), np.asarray(out))
+    assert "FillDepressions" in out.metadata["PROCESSING_HISTORY"]
+    w = R(np.full((128, 128), 2.0), -1)
+    acc = rd.FlowAccumulation(dem, "D8", weights=w, in_place=True)
+    assert np.shares_memory(acc, w)
+
+
+# ---- size-independent properties at a size the CPU oracle would need minutes for ----------------
+def test_properties_at_8192():
+    import torch
+    N = 8192
+    L = _lib.lib()
+    d = torch.empty((N, N), dtype=torch.float32, device="cuda")
+    _lib.check(L.rdb200_dev_generate_fbm_f32(d.data_ptr(), N, N, 0, 77, 12, 0.0))
+    z = d.clone()
+    _lib.check(L.rdb200_dev_fill_depressions_d8_f32(d.data_ptr(), N, N))
+    assert bool((d >= z).all()), "fill never lowers a cell"
+    assert bool(torch.isfinite(d).all())
+    for sl in (np.s_[0, :], np.s_[-1, :], np.s_[:, 0], np.s_[:, -1]):
+        assert torch.equal(d[sl], z[sl]), "border cells are pinned"
+    raised = float((d > z).float().mean())
+    assert 0.05 < raised < 0.6
+    again = d.clone()
+    _lib.check(L.rdb200_dev_fill_depressions_d8_f32(again.data_ptr(), N, N))
+    assert torch.equal(again, d), "fill is idempotent"
+    # every interior cell has a neighbour that is not higher (no pits left)
+    pad = torch.nn.functional.pad(d[None, None], (1, 1, 1, 1), value=float("inf"))
+    nmin = -torch.nn.functional.max_pool2d(-pad, 3, stride=1)[0, 0]
+    inner = torch.ones_like(d, dtype=torch.bool)
+    inner[0, :] = inner[-1, :] = False
+    inner[:, 0] = inner[:, -1] = False
+    # nmin includes the centre; a pit would have all 8 neighbours strictly higher -> check via
+    # second-smallest is overkill: use the definition W = max(Z, min8(W)) instead
+    p = torch.nn.functional.pad(d[None, None], (1, 1, 1, 1), value=float("inf"))[0, 0]
+    m8 = torch.full_like(d, float("inf"))
+    for dy in (0, 1, 2):
+        for dx in (0, 1, 2):
+            if dy == 1 and dx == 1:
+                continue
+            m8 = torch.minimum(m8, p[dy:dy + N, dx:dx + N])
+    assert torch.equal(d[inner], torch.maximum(z, m8)[inner]), "fixed-point equation holds everywhere"
+    del pad, nmin, p, m8, again
+    # D8 accumulation: flow is conserved -- the accumulation of all outlets sums to the cell count
+    acc = torch.empty((N, N), dtype=torch.float64, device="cuda")
+    _lib.check(L.rdb200_dev_fa_d8_f32_f64(d.data_ptr(), acc.data_ptr(), N, N, ND, 1))
+    props = torch.empty((N, N, 9), dtype=torch.float32, device="cuda")
+    _lib.check(L.rdb200_dev_fm_d8_f32(d.data_ptr(), props.data_ptr(), N, N, ND))
+    outlet = props[..., 0] == -1.0
+    assert float(acc[outlet].sum()) == float(N * N)
+    assert float(acc.min()) == 1.0
+    acc2 = torch.empty_like(acc)
+    _lib.check(L.rdb200_dev_fa_d8_f32_f64(d.data_ptr(), acc2.data_ptr(), N, N, ND, 1))
+    assert torch.equal(acc, acc2), "unit-weight D8 accumulation is deterministic"
+    # generic props path agrees with the fused path
+    acc3 = torch.ones_like(acc)
+    _lib.check(L.rdb200_dev_flow_accumulation_props_f64(props.data_ptr(), acc3.data_ptr(), N, N))
+    assert torch.equal(acc, acc3)

@@ -1,0 +1,98 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol the header declares,
+the Python mirror of the reference API validates arguments like the reference does, and compute
+calls fail loudly (no CPU fallback) when no B200 is visible."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import richdem_b200 as rd
+from richdem_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    assert os.path.exists(path)
+    header = open(os.path.join(ROOT, "include", "richdem_b200.h")).read()
+    declared = set(re.findall(r"RDB200_API[^;]*?\b(rdb200_\w+)\s*\(", header))
+    assert len(declared) >= 30
+    L = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/richdem_b200.h but not exported"
+    # and the ctypes table covers the whole header
+    assert declared == set(_lib.SIGNATURES) | set(_lib.OTHER_SYMBOLS)
+    assert _lib.lib().rdb200_version() == 100
+
+
+def test_sass_contains_tma_and_no_legacy_paths():
+    """The fill sweep stages tiles with TMA (UTMALDG in SASS, B200_PROFILING.md) and the library
+    is built for sm_100a only."""
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
+    assert "UTMALDG" in out
+    assert "SM100a" in out or "sm_100a" in out
+    archs = set(re.findall(r"arch = (sm_\w+)", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_rdarray_semantics():
+    a = rd.rdarray(np.zeros((4, 5), np.float32), no_data=-9999)
+    assert a.no_data == -9999 and a.shape == (4, 5)
+    b = a.copy()
+    assert b.no_data == -9999 and type(b) is rd.rdarray
+    with pytest.raises(Exception, match="no_data value must be specified"):
+        rd.rdarray(np.zeros((2, 2)))
+    c = rd.rdarray(np.ones((3, 3)), meta_obj=a, no_data=-1)
+    assert c.no_data == -1
+    p = rd.rd3array(np.zeros((3, 3, 9)), no_data=-2)
+    assert p.dtype == np.float32
+
+
+def test_argument_validation_matches_reference_behaviour():
+    raw = np.zeros((8, 8), np.float32)
+    dem = rd.rdarray(raw, no_data=-9999)
+    with pytest.raises(Exception, match="rdarray or numpy.ndarray is required"):
+        rd.FillDepressions(raw)
+    with pytest.raises(Exception, match="Unknown topology"):
+        rd.FillDepressions(dem, topology="D6")
+    with pytest.raises(Exception, match="rdarray or numpy.ndarray is required"):
+        rd.ResolveFlats(raw)
+    with pytest.raises(Exception, match="Invalid FlowAccumulation method"):
+        rd.FlowAccumulation(dem, method="nope")
+    with pytest.raises(Exception, match="outside the B200 hot path"):
+        rd.FlowAccumulation(dem, method="Quinn")
+    with pytest.raises(Exception, match="must be of type 'float64'"):
+        rd.FlowAccumulation(dem, method="D8", weights=rd.rdarray(np.ones((8, 8), np.float32), no_data=-1))
+    with pytest.raises(Exception, match="Invalid FlowProportions method"):
+        rd.FlowProportions(dem, method=None)
+    with pytest.raises(Exception, match="rd3array"):
+        rd.FlowAccumFromProps(dem)
+    with pytest.raises(Exception, match="float32"):
+        rd.FillDepressions(rd.rdarray(np.zeros((8, 8), np.float64), no_data=-1))
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_compute_fails_loudly():
+    dem = rd.rdarray(np.arange(64, dtype=np.float32).reshape(8, 8), no_data=-9999)
+    for call in (lambda: rd.FillDepressions(dem), lambda: rd.ResolveFlats(dem),
+                 lambda: rd.FlowAccumulation(dem, method="D8"), lambda: rd.FlowProportions(dem, method="Dinf")):
+        with pytest.raises(rd.RichdemB200Error, match="no CPU fallback|no CUDA"):
+            call()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "richdem_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f

@@ -1,0 +1,124 @@
+"""Pins the CPU oracle (oracle/oracle.c) before anything trusts it:
+  * against the reference's own known-answer fixtures (re-encoded in tests/golden/),
+  * against stored outputs of the unmodified reference on real + synthetic terrain,
+  * live against oracle/_ref (the compiled reference) when it is available.
+No GPU involved."""
+import numpy as np
+import pytest
+
+import oracle
+
+ND = -9999.0
+
+
+def test_fill_known_answer(port, golden):
+    g = golden["fill_testdem1"]  # reference tests/tests.cpp:238-271
+    assert np.array_equal(port.fill_depressions(g["dem"]), g["expected"])
+
+
+def test_d8_flow_accum_known_answers(port, golden):
+    g = golden["flow_accum_fixtures"]  # reference tests/tests.cpp:135-146
+    assert len(g["names"]) == 24
+    for name, nd in zip(g["names"], g["d8_nodata"]):
+        got = port.d8_flow_accum(g[f"{name}__d8"], nodata=int(nd))
+        assert np.array_equal(got, g[f"{name}__out"]), name
+
+
+def test_data_dems_against_reference_outputs(port, golden):
+    g = golden["data_dems"]
+    keys = sorted({k.split("__")[0] for k in g.files})
+    assert {"pit", "multi_flat", "garbrecht", "dinf_test"} <= set(keys)
+    for k in keys:
+        dem, nd = g[f"{k}__dem"], float(g[f"{k}__nodata"])
+        assert np.array_equal(port.fill_depressions(dem), g[f"{k}__filled"]), k
+        assert np.array_equal(port.resolve_flats(dem, nd), g[f"{k}__resolved"]), k
+        m, l = port.flat_mask(dem, nd)
+        assert np.array_equal(m, g[f"{k}__mask"]), k
+        assert np.array_equal(l != 0, g[f"{k}__labeled"]), k
+        assert np.array_equal(port.d8_flow_directions(dem, nd), g[f"{k}__dirs"]), k
+        assert np.array_equal(port.fm_d8(dem, nd), g[f"{k}__fm_d8"]), k
+        assert np.array_equal(port.fm_dinf(dem, nd), g[f"{k}__fm_dinf"]), k
+
+
+def test_beauford_crop_pipeline(port, golden):
+    g = golden["beauford_crop"]
+    dem, nd = g["dem"], float(g["nodata"])
+    assert (dem == nd).mean() > 0.05  # the crop exercises the NoData branches
+    filled = port.fill_depressions(dem)
+    assert np.array_equal(filled, g["filled"])
+    resolved = port.resolve_flats(filled, nd)
+    assert np.array_equal(resolved, g["resolved"])
+    assert np.array_equal(port.d8_flow_directions(resolved, nd), g["dirs"])
+    assert np.array_equal(port.fa_d8(resolved, nd), g["fa_d8"])
+    assert np.array_equal(port.fa_dinf(resolved, nd), g["fa_dinf"])
+    assert np.array_equal(port.fm_dinf(resolved, nd).reshape(-1, 9)[::7], g["fm_dinf_nz"])
+
+
+def test_synthetic_against_reference_outputs(port, golden):
+    g = golden["synthetic_ref"]
+    for seed in (101, 102, 103):
+        k = f"s{seed}"
+        h, w = (int(v) for v in g[f"{k}__shape"])
+        q = float(g[f"{k}__quantum"]) or None
+        dem = oracle.fbm_terrain(h, w, seed=seed, quantum=q)
+        assert np.array_equal(dem, g[f"{k}__dem"]), "terrain generator drifted"
+        f = port.fill_depressions(dem)
+        assert np.array_equal(f, g[f"{k}__filled"])
+        r = port.resolve_flats(f, ND)
+        assert np.array_equal(r, g[f"{k}__resolved"])
+        assert np.array_equal(port.d8_flow_directions(r, ND), g[f"{k}__dirs"])
+        assert np.array_equal(port.fa_d8(r, ND), g[f"{k}__fa_d8"])
+        assert np.array_equal(port.fa_dinf(r, ND), g[f"{k}__fa_dinf"])
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no reference tree)")
+@pytest.mark.parametrize("seed,shape,q,nodata_patch", [(7, (97, 133), None, False), (8, (160, 120), 0.5, True),
+                                                       (9, (300, 300), 4.0, False)])
+def test_port_matches_compiled_reference_live(port, seed, shape, q, nodata_patch):
+    R = oracle.ref()
+    dem = oracle.fbm_terrain(*shape, seed=seed, quantum=q)
+    if nodata_patch:
+        dem[20:50, 30:70] = ND
+        dem[:9, :13] = ND
+    f = port.fill_depressions(dem)
+    for variant in (None, "fill_zhou", "fill_barnes", "fill_original"):
+        assert np.array_equal(f, R.fill_depressions(dem, variant))
+    assert np.array_equal(port.find_flats(f, ND), R.find_flats(f, ND))
+    (m1, l1), (m2, l2) = port.flat_mask(f, ND), R.flat_mask(f, ND)
+    assert np.array_equal(m1, m2) and np.array_equal(l1 != 0, l2 != 0)
+    r = port.resolve_flats(f, ND)
+    assert np.array_equal(r, R.resolve_flats(f, ND))
+    d = port.d8_flow_directions(r, ND)
+    assert np.array_equal(d, R.d8_flow_directions(r, ND))
+    assert np.array_equal(port.d8_flow_accum(d), R.d8_flow_accum(d))
+    assert np.array_equal(port.fm_d8(r, ND), R.fm_d8(r, ND))
+    assert np.array_equal(port.fm_dinf(r, ND), R.fm_dinf(r, ND))
+    assert np.array_equal(port.fa_d8(r, ND), R.fa_d8(r, ND))
+    assert np.array_equal(port.fa_dinf(r, ND), R.fa_dinf(r, ND))
+    wts = np.random.default_rng(seed).random(shape)
+    assert np.array_equal(port.fa_dinf(r, ND, wts), R.fa_dinf(r, ND, wts))
+
+
+def test_fill_is_min_over_paths_of_max(port):
+    """Independent definition check on a tiny raster: brute-force Jacobi iteration of
+    W = max(Z, min_nbrs W) from +inf (SURVEY 8a'-1)."""
+    dem = oracle.fbm_terrain(23, 31, seed=5, quantum=5.0)
+    h, w = dem.shape
+    W = np.full((h + 2, w + 2), np.inf, np.float32)
+    Z = np.full((h + 2, w + 2), np.inf, np.float32)
+    Z[1:-1, 1:-1] = dem
+    border = np.zeros((h + 2, w + 2), bool)
+    border[1, 1:-1] = border[-2, 1:-1] = border[1:-1, 1] = border[1:-1, -2] = True
+    W[border] = Z[border]
+    for _ in range(10 * (h + w)):
+        m = np.full_like(W, np.inf)
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if dy or dx:
+                    m[1:-1, 1:-1] = np.minimum(m[1:-1, 1:-1], W[1 + dy:h + 1 + dy, 1 + dx:w + 1 + dx])
+        new = np.minimum(W, np.maximum(Z, m))
+        new[border] = Z[border]
+        if np.array_equal(new, W):
+            break
+        W = new
+    assert np.array_equal(W[1:-1, 1:-1], port.fill_depressions(dem))
