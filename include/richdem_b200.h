@@ -181,6 +181,35 @@ RDB200_API int rdb200_dev_fill_update_row(rdb200_fill_state *state, int32_t y, c
 /* Write the filled band to d_out (height x width, boundary rows included) and free state. */
 RDB200_API int rdb200_dev_fill_finish(rdb200_fill_state *state, float *d_out);
 
+/* ---- row-band (multi-GPU) flow accumulation ---------------------------------------------- */
+/* Same role as FA_D8 / FA_Tarboton (include/richdem/methods/flow_accumulation.hpp:27,16) for one
+ * row band.  The local raster (elevations and accumulation) is ghost_top + owned + ghost_bottom
+ * rows; ghost elevation rows must hold the neighbouring bands' rows.  The ghost rows of the
+ * accumulation array are scratch (parking slots for flow that leaves the band).
+ * Protocol per GPU: begin -> exchange edge codes (get_edge_codes / set_ghost_codes) ->
+ *   repeat { run ; take_outflow per side ; exchange ; apply_inflow per side } until no rank sent
+ *   anything -> finish.  See richdem_b200/sharded.py. */
+typedef struct rdb200_facc_state rdb200_facc_state;
+RDB200_API int rdb200_dev_facc_begin(rdb200_facc_state **state, const float *d_dem, double *d_accum_inout,
+                                     int32_t width, int32_t height, float nodata, int32_t ghost_top,
+                                     int32_t ghost_bottom, int32_t dinf, int32_t accum_is_ones);
+/* which: 0 = top side, 1 = bottom side.  Flow codes (1 byte/cell, + float rmax for D-infinity) of
+ * my first/last owned row, to be installed as the neighbour's ghost codes. */
+RDB200_API int rdb200_dev_facc_get_edge_codes(rdb200_facc_state *state, int32_t which, uint8_t *d_code_row,
+                                              float *d_rmax_row);
+RDB200_API int rdb200_dev_facc_set_ghost_codes(rdb200_facc_state *state, int32_t which,
+                                               const uint8_t *d_code_row, const float *d_rmax_row);
+/* Walk from the current frontier (first call: from all sources).  sent_*: number of flow parcels
+ * parked in the top / bottom ghost row by this run. */
+RDB200_API int rdb200_dev_facc_run(rdb200_facc_state *state, int32_t *sent_top, int32_t *sent_bottom);
+/* Move the parked flow of one ghost row out (sum per cell, number of parcels per cell) and clear it. */
+RDB200_API int rdb200_dev_facc_take_outflow(rdb200_facc_state *state, int32_t which, double *d_sum_row,
+                                            int32_t *d_cnt_row);
+/* Add a neighbour's outflow to my first/last owned row and release the cells it completes. */
+RDB200_API int rdb200_dev_facc_apply_inflow(rdb200_facc_state *state, int32_t which, const double *d_sum_row,
+                                            const int32_t *d_cnt_row);
+RDB200_API int rdb200_dev_facc_finish(rdb200_facc_state *state);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,13 @@ SIGNATURES = {
     "rdb200_dev_fill_read_row": [_vp, _i32, _vp],
     "rdb200_dev_fill_update_row": [_vp, _i32, _vp],
     "rdb200_dev_fill_finish": [_vp, _vp],
+    "rdb200_dev_facc_begin": [C.POINTER(_vp), _vp, _vp, _i32, _i32, _f32, _i32, _i32, _i32, _i32],
+    "rdb200_dev_facc_get_edge_codes": [_vp, _i32, _vp, _vp],
+    "rdb200_dev_facc_set_ghost_codes": [_vp, _i32, _vp, _vp],
+    "rdb200_dev_facc_run": [_vp, C.POINTER(_i32), C.POINTER(_i32)],
+    "rdb200_dev_facc_take_outflow": [_vp, _i32, _vp, _vp],
+    "rdb200_dev_facc_apply_inflow": [_vp, _i32, _vp, _vp],
+    "rdb200_dev_facc_finish": [_vp],
 }
 OTHER_SYMBOLS = ["rdb200_shutdown", "rdb200_last_error", "rdb200_version"]
 

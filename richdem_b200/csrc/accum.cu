@@ -53,12 +53,12 @@ __global__ void __launch_bounds__(256) flow_code_kernel(const float *__restrict_
 
 // ---- K2: dependency counters by gathering over the 8 neighbours' codes; marks sources ----------
 __global__ void __launch_bounds__(256) deps_gather_kernel(const uint8_t *__restrict__ code, uint32_t *__restrict__ st,
-                                                           int W, int H) {
+                                                           int W, int H, int y_lo, int y_hi) {
   const size_t n = (size_t)W * H;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
-  if (code[i] == kCodeNoData) {
+  if (code[i] == kCodeNoData || y < y_lo || y >= y_hi) {  // NoData, or a ghost row of a row band
     st[i] = 0;
     return;
   }
@@ -121,6 +121,10 @@ struct WalkArgs {
   int *next_frontier;
   int *next_count;
   int W, H;
+  // row-band mode: cells below ghost_lo_end / at or above ghost_hi_start belong to a neighbouring
+  // band; flow into them is parked in their accum slot and counted in ghostcnt[2*W]
+  int ghost_lo_end, ghost_hi_start;
+  int *ghostcnt;
 };
 
 template <class A>
@@ -128,7 +132,22 @@ __device__ __forceinline__ A ld_acc(const A *p) {
   return __ldcg(p);
 }
 
-template <int MODE, bool CHECK, class A>
+template <class A>
+__device__ __forceinline__ bool park_in_ghost(const WalkArgs<A> &a, int r, A val) {
+  if (r < a.ghost_lo_end) {
+    atomicAdd(a.accum + r, val);
+    atomicAdd(a.ghostcnt + r, 1);
+    return true;
+  }
+  if (r >= a.ghost_hi_start) {
+    atomicAdd(a.accum + r, val);
+    atomicAdd(a.ghostcnt + a.W + (r - a.ghost_hi_start), 1);
+    return true;
+  }
+  return false;
+}
+
+template <int MODE, bool CHECK, class A, bool BAND = false>
 __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= a.nfrontier) return;
@@ -154,6 +173,7 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
       }
       const int r = c + dy * W + dx;
       if (a.code[r] == kCodeNoData) break;  // flow into NoData is dropped
+      if (BAND && park_in_ghost(a, r, acc)) break;
       atomicAdd(a.accum + r, acc);
       __threadfence();
       const uint32_t old = atomicSub(a.st + r, 1u);
@@ -170,14 +190,20 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
         float p1, p2;
         tarboton_props(a.rmaxArr[c], &p1, &p2);
         // generic.hpp:87  accum(ni) += props(ci,n)*c_accum  (float * double)
-        if (p1 > 0) atomicAdd(a.accum + r1, (A)((double)p1 * (double)acc));
-        if (p2 > 0) atomicAdd(a.accum + r2, (A)((double)p2 * (double)acc));
+        const A v1 = (A)((double)p1 * (double)acc), v2 = (A)((double)p2 * (double)acc);
+        bool live1 = p1 > 0, live2 = p2 > 0;
+        if (BAND) {
+          if (live1 && park_in_ghost(a, r1, v1)) live1 = false;
+          if (live2 && park_in_ghost(a, r2, v2)) live2 = false;
+        }
+        if (live1) atomicAdd(a.accum + r1, v1);
+        if (live2) atomicAdd(a.accum + r2, v2);
         __threadfence();
-        if (p1 > 0) {
+        if (live1) {
           const uint32_t o1 = atomicSub(a.st + r1, 1u);
           if ((o1 & kDepsMask) == 1u) next = r1;
         }
-        if (p2 > 0) {
+        if (live2) {
           const uint32_t o2 = atomicSub(a.st + r2, 1u);
           if ((o2 & kDepsMask) == 1u) {
             if (next < 0) next = r2;
@@ -185,6 +211,7 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
           }
         }
       } else {
+        if (BAND && park_in_ghost(a, r1, acc)) break;
         atomicAdd(a.accum + r1, acc);
         __threadfence();
         const uint32_t o1 = atomicSub(a.st + r1, 1u);
@@ -294,7 +321,7 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
   else
     flow_code_kernel<false><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, nullptr, d_accum, w, h, nodata, ones ? 1 : 0);
   RDB_CK(cudaGetLastError());
-  deps_gather_kernel<<<blocks, 256, 0, c.stream>>>(code.p, st.p, w, h);
+  deps_gather_kernel<<<blocks, 256, 0, c.stream>>>(code.p, st.p, w, h, 0, h);
   RDB_CK(cudaGetLastError());
   count_launch(2);
   WalkArgs<double> a;
@@ -340,7 +367,7 @@ void d8_flow_accum_dev(const uint8_t *d_dirs, int32_t *d_area, int w, int h) {
   const unsigned blocks = (unsigned)((n + 255) / 256);
   sanitize_dirs_kernel<<<blocks, 256, 0, c.stream>>>(d_dirs, code.p, n);
   area_init_kernel<<<blocks, 256, 0, c.stream>>>(d_dirs, d_area, n);
-  deps_gather_kernel<<<blocks, 256, 0, c.stream>>>(code.p, st.p, w, h);
+  deps_gather_kernel<<<blocks, 256, 0, c.stream>>>(code.p, st.p, w, h, 0, h);
   RDB_CK(cudaGetLastError());
   count_launch(3);
   WalkArgs<int32_t> a;
@@ -354,3 +381,321 @@ void d8_flow_accum_dev(const uint8_t *d_dirs, int32_t *d_area, int w, int h) {
 }
 
 }  // namespace rdb
+
+// =================================================================================================
+// Row-band (multi-GPU) accumulation.  The local raster is (ghost_top + owned + ghost_bottom) rows;
+// the ghost rows carry the neighbouring bands' flow codes (so dependency counts are complete) and
+// act as parking slots for flow that leaves the band.  Per global round: walk -> take_outflow ->
+// (caller exchanges rows) -> apply_inflow -> walk from the cells that just became ready.
+// =================================================================================================
+namespace rdb {
+namespace {
+
+__global__ void __launch_bounds__(256) band_apply_inflow_kernel(double *accum_row, uint32_t *st_row,
+                                                                 const double *__restrict__ sum,
+                                                                 const int *__restrict__ cnt, int W, int base_index,
+                                                                 int *frontier, int *fcount) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const int k = cnt[x];
+  if (k <= 0) return;
+  accum_row[x] += sum[x];
+  const uint32_t old = st_row[x];
+  st_row[x] = old - (uint32_t)k;
+  if ((old & kDepsMask) == (uint32_t)k) frontier[atomicAdd(fcount, 1)] = base_index + x;
+}
+
+__global__ void __launch_bounds__(256) band_zero_ghost_kernel(double *row, int W) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < W) row[x] = 0.0;
+}
+
+}  // namespace
+
+struct FaccState {
+  int W = 0, H = 0, gt = 0, gb = 0;
+  bool dinf = false;
+  double *accum = nullptr;
+  DevBuf<uint8_t> code;
+  DevBuf<float> rmax;
+  DevBuf<uint32_t> st;
+  DevBuf<int> ghostcnt, fr0, fr1, cnt;
+  bool prepared = false;
+  int n_frontier = 0;     // cells waiting in fr0 (seeded by apply_inflow)
+  int rounds = 0;
+
+  size_t n() const { return (size_t)W * H; }
+
+  void begin(const float *d_dem, double *d_accum, int w, int h, float nodata, int ghost_top, int ghost_bottom,
+             bool dinf_, bool ones) {
+    Ctx &c = ctx();
+    W = w;
+    H = h;
+    gt = ghost_top ? 1 : 0;
+    gb = ghost_bottom ? 1 : 0;
+    dinf = dinf_;
+    accum = d_accum;
+    if (h - gt - gb < 1) fail("facc_begin: band has no owned rows");
+    code.alloc(n());
+    st.alloc(n());
+    if (dinf) rmax.alloc(n());
+    ghostcnt.alloc(2 * (size_t)W);
+    fr0.alloc(n());
+    fr1.alloc(n());
+    cnt.alloc(4);
+    RDB_CK(cudaMemsetAsync(ghostcnt.p, 0, 2 * (size_t)W * sizeof(int), c.stream));
+    RDB_CK(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(int), c.stream));
+    const unsigned blocks = (unsigned)((n() + 255) / 256);
+    // rows 0 / H-1 of the local raster are either true raster edges (no ghost) or ghost rows whose
+    // codes are replaced below, so the per-cell functions' own edge test is exactly right here
+    if (dinf)
+      flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, ones ? 1 : 0);
+    else
+      flow_code_kernel<false><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, nullptr, d_accum, w, h, nodata, ones ? 1 : 0);
+    RDB_CK(cudaGetLastError());
+    count_launch();
+    const unsigned rb = (unsigned)((W + 255) / 256);
+    if (gt) band_zero_ghost_kernel<<<rb, 256, 0, c.stream>>>(accum, W);
+    if (gb) band_zero_ghost_kernel<<<rb, 256, 0, c.stream>>>(accum + (size_t)(H - 1) * W, W);
+    RDB_CK(cudaGetLastError());
+  }
+
+  int edge_row(int which) const { return which == 0 ? gt : H - 1 - gb; }   // my first / last owned row
+  int ghost_row(int which) const { return which == 0 ? 0 : H - 1; }
+
+  void get_edge_codes(int which, uint8_t *d_code_row, float *d_rmax_row) {
+    Ctx &c = ctx();
+    const size_t o = (size_t)edge_row(which) * W;
+    RDB_CK(cudaMemcpyAsync(d_code_row, code.p + o, W, cudaMemcpyDeviceToDevice, c.stream));
+    if (dinf && d_rmax_row)
+      RDB_CK(cudaMemcpyAsync(d_rmax_row, rmax.p + o, (size_t)W * 4, cudaMemcpyDeviceToDevice, c.stream));
+  }
+  void set_ghost_codes(int which, const uint8_t *d_code_row, const float *d_rmax_row) {
+    Ctx &c = ctx();
+    if ((which == 0 && !gt) || (which == 1 && !gb)) fail("facc_set_ghost_codes: no ghost row on that side");
+    const size_t o = (size_t)ghost_row(which) * W;
+    RDB_CK(cudaMemcpyAsync(code.p + o, d_code_row, W, cudaMemcpyDeviceToDevice, c.stream));
+    if (dinf && d_rmax_row)
+      RDB_CK(cudaMemcpyAsync(rmax.p + o, d_rmax_row, (size_t)W * 4, cudaMemcpyDeviceToDevice, c.stream));
+  }
+
+  template <int MODE>
+  void walk(WalkArgs<double> a) {
+    Ctx &c = ctx();
+    int *hcnt = (int *)c.pinned;
+    for (;;) {
+      const unsigned blocks = (unsigned)(((size_t)a.nfrontier + 255) / 256);
+      if (blocks) {
+        accum_walk_kernel<MODE, false, double, true><<<blocks, 256, 0, c.stream>>>(a);
+        RDB_CK(cudaGetLastError());
+        count_launch();
+      }
+      if (MODE == 0) break;
+      RDB_CK(cudaMemcpyAsync(hcnt, a.next_count, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+      RDB_CK(cudaStreamSynchronize(c.stream));
+      const int nn = *hcnt;
+      if (nn == 0) break;
+      a.frontier = a.next_frontier;
+      a.nfrontier = nn;
+      a.next_frontier = (a.frontier == fr0.p) ? fr1.p : fr0.p;
+      RDB_CK(cudaMemsetAsync(a.next_count, 0, sizeof(int), c.stream));
+    }
+  }
+
+  // returns the number of flow parcels parked in the ghost rows by this run: [top, bottom]
+  void run(int *sent_top, int *sent_bottom) {
+    Ctx &c = ctx();
+    WalkArgs<double> a;
+    memset(&a, 0, sizeof(a));
+    a.code = code.p;
+    a.rmaxArr = rmax.p;
+    a.accum = accum;
+    a.st = st.p;
+    a.W = W;
+    a.H = H;
+    a.ghost_lo_end = gt ? W : 0;
+    a.ghost_hi_start = gb ? (H - 1) * W : H * W;
+    a.ghostcnt = ghostcnt.p;
+    a.next_count = cnt.p + 1;
+    if (!prepared) {
+      const unsigned blocks = (unsigned)((n() + 255) / 256);
+      deps_gather_kernel<<<blocks, 256, 0, c.stream>>>(code.p, st.p, W, H, gt, H - gb);
+      RDB_CK(cudaGetLastError());
+      count_launch();
+      prepared = true;
+      a.frontier = nullptr;
+      a.nfrontier = (int)n();
+      a.next_frontier = fr1.p;
+    } else {
+      a.frontier = fr0.p;
+      a.nfrontier = n_frontier;
+      a.next_frontier = fr1.p;
+    }
+    RDB_CK(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(int), c.stream));
+    if (dinf) walk<1>(a);
+    else walk<0>(a);
+    n_frontier = 0;
+    rounds++;
+    // how much left the band?
+    // (cheap: reduce the two count rows on the host side of a tiny kernel-free copy is overkill;
+    //  the caller exchanges the rows anyway, so only a boolean is needed -> thrust-free sum)
+    int *h = (int *)c.pinned;
+    DevBuf<int> sums(2);
+    RDB_CK(cudaMemsetAsync(sums.p, 0, 2 * sizeof(int), c.stream));
+    sum_rows(sums.p);
+    RDB_CK(cudaMemcpyAsync(h, sums.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    if (sent_top) *sent_top = h[0];
+    if (sent_bottom) *sent_bottom = h[1];
+    c.stats.accum_rounds = rounds;
+  }
+
+  void sum_rows(int *d_sums);
+
+  void take_outflow(int which, double *d_sum_row, int *d_cnt_row) {
+    Ctx &c = ctx();
+    if ((which == 0 && !gt) || (which == 1 && !gb)) fail("facc_take_outflow: no ghost row on that side");
+    double *grow = accum + (size_t)ghost_row(which) * W;
+    int *crow = ghostcnt.p + (which == 0 ? 0 : W);
+    RDB_CK(cudaMemcpyAsync(d_sum_row, grow, (size_t)W * 8, cudaMemcpyDeviceToDevice, c.stream));
+    RDB_CK(cudaMemcpyAsync(d_cnt_row, crow, (size_t)W * 4, cudaMemcpyDeviceToDevice, c.stream));
+    RDB_CK(cudaMemsetAsync(grow, 0, (size_t)W * 8, c.stream));
+    RDB_CK(cudaMemsetAsync(crow, 0, (size_t)W * 4, c.stream));
+  }
+
+  void apply_inflow(int which, const double *d_sum_row, const int *d_cnt_row) {
+    Ctx &c = ctx();
+    if ((which == 0 && !gt) || (which == 1 && !gb)) fail("facc_apply_inflow: no neighbour on that side");
+    const int row = edge_row(which);
+    const unsigned rb = (unsigned)((W + 255) / 256);
+    // frontier count lives in cnt[2]; cells are appended to fr0 after whatever is already waiting
+    band_apply_inflow_kernel<<<rb, 256, 0, c.stream>>>(accum + (size_t)row * W, st.p + (size_t)row * W, d_sum_row,
+                                                       d_cnt_row, W, row * W, fr0.p, cnt.p + 2);
+    RDB_CK(cudaGetLastError());
+    count_launch();
+    pending_apply = true;
+  }
+  bool pending_apply = false;
+
+  void collect_frontier() {
+    Ctx &c = ctx();
+    if (!pending_apply) return;
+    int *h = (int *)c.pinned;
+    RDB_CK(cudaMemcpyAsync(h, cnt.p + 2, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    n_frontier = h[0];
+    RDB_CK(cudaMemsetAsync(cnt.p + 2, 0, sizeof(int), c.stream));
+    pending_apply = false;
+  }
+};
+
+namespace {
+__global__ void __launch_bounds__(256) band_sum_counts_kernel(const int *__restrict__ ghostcnt, int W, int *sums) {
+  int s0 = 0, s1 = 0;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+    s0 += ghostcnt[x];
+    s1 += ghostcnt[W + x];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_down_sync(0xffffffffu, s0, o);
+    s1 += __shfl_down_sync(0xffffffffu, s1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (s0) atomicAdd(&sums[0], s0);
+    if (s1) atomicAdd(&sums[1], s1);
+  }
+}
+}  // namespace
+
+void FaccState::sum_rows(int *d_sums) {
+  Ctx &c = ctx();
+  band_sum_counts_kernel<<<64, 256, 0, c.stream>>>(ghostcnt.p, W, d_sums);
+  RDB_CK(cudaGetLastError());
+}
+
+void capi_set_error(const char *msg);
+
+}  // namespace rdb
+
+struct rdb200_facc_state {
+  rdb::FaccState st;
+};
+
+#define FACC_TRY try {
+#define FACC_END                        \
+  }                                     \
+  catch (const std::exception &e) {     \
+    rdb::capi_set_error(e.what());      \
+    return 1;                           \
+  }                                     \
+  return 0;
+
+extern "C" {
+
+int rdb200_dev_facc_begin(rdb200_facc_state **state, const float *d_dem, double *d_accum_inout, int32_t width,
+                          int32_t height, float nodata, int32_t ghost_top, int32_t ghost_bottom, int32_t dinf,
+                          int32_t accum_is_ones) {
+  FACC_TRY
+  rdb::ensure_init();
+  if (!state || !d_dem || !d_accum_inout) rdb::fail("facc_begin: null pointer");
+  auto *s = new rdb200_facc_state();
+  try {
+    s->st.begin(d_dem, d_accum_inout, width, height, nodata, ghost_top, ghost_bottom, dinf != 0, accum_is_ones != 0);
+  } catch (...) {
+    delete s;
+    throw;
+  }
+  *state = s;
+  FACC_END
+}
+
+int rdb200_dev_facc_get_edge_codes(rdb200_facc_state *state, int32_t which, uint8_t *d_code_row, float *d_rmax_row) {
+  FACC_TRY
+  state->st.get_edge_codes(which, d_code_row, d_rmax_row);
+  RDB_CK(cudaStreamSynchronize(rdb::ctx().stream));
+  FACC_END
+}
+
+int rdb200_dev_facc_set_ghost_codes(rdb200_facc_state *state, int32_t which, const uint8_t *d_code_row,
+                                    const float *d_rmax_row) {
+  FACC_TRY
+  state->st.set_ghost_codes(which, d_code_row, d_rmax_row);
+  RDB_CK(cudaStreamSynchronize(rdb::ctx().stream));
+  FACC_END
+}
+
+int rdb200_dev_facc_run(rdb200_facc_state *state, int32_t *sent_top, int32_t *sent_bottom) {
+  FACC_TRY
+  state->st.collect_frontier();
+  int a = 0, b = 0;
+  state->st.run(&a, &b);
+  if (sent_top) *sent_top = a;
+  if (sent_bottom) *sent_bottom = b;
+  FACC_END
+}
+
+int rdb200_dev_facc_take_outflow(rdb200_facc_state *state, int32_t which, double *d_sum_row, int32_t *d_cnt_row) {
+  FACC_TRY
+  state->st.take_outflow(which, d_sum_row, d_cnt_row);
+  RDB_CK(cudaStreamSynchronize(rdb::ctx().stream));
+  FACC_END
+}
+
+int rdb200_dev_facc_apply_inflow(rdb200_facc_state *state, int32_t which, const double *d_sum_row,
+                                 const int32_t *d_cnt_row) {
+  FACC_TRY
+  state->st.apply_inflow(which, d_sum_row, d_cnt_row);
+  RDB_CK(cudaStreamSynchronize(rdb::ctx().stream));
+  FACC_END
+}
+
+int rdb200_dev_facc_finish(rdb200_facc_state *state) {
+  FACC_TRY
+  if (state) {
+    RDB_CK(cudaStreamSynchronize(rdb::ctx().stream));
+    delete state;
+  }
+  FACC_END
+}
+
+}  // extern "C"

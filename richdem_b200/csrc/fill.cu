@@ -123,6 +123,9 @@ __global__ void __launch_bounds__(FILL_THREADS, 3)
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ int sTile;
   __shared__ int sFlags;
+  // per-thread-block "inputs changed" marks, double buffered by iteration parity; 18x18 so that
+  // marking the 8 neighbouring blocks needs no bounds checks (rim entries are never read)
+  __shared__ unsigned char sDirty[2][18 * 18];
 
   const int tid = threadIdx.x;
   const int tx = tid & 15;   // block column: cells 4tx..4tx+3
@@ -149,8 +152,11 @@ __global__ void __launch_bounds__(FILL_THREADS, 3)
   uint32_t phase = 0;
   const int max_iters = a.max_iters;
 
+  const int dme = (ty + 1) * 18 + (tx + 1);
   for (;;) {
     if (tid == 0) sTile = atomicAdd(&cur->take, 1);
+    sDirty[0][dme] = 0;
+    sDirty[1][dme] = 0;
     __syncthreads();  // publishes sTile (and the mbarrier init); all warps are done with smem
     const int li = sTile;
     if (li >= n) break;
@@ -203,58 +209,78 @@ __global__ void __launch_bounds__(FILL_THREADS, 3)
     int iters = 0;
     bool again = false;
     for (;;) {
-      // rim of the block (apron or neighbouring threads' cells; may be mid-update: harmless)
-      {
-        const float *top = &sW[(srow - 1) * SP + scol];
-        const float *bot = &sW[(srow + 4) * SP + scol];
-        const float4 t4 = *reinterpret_cast<const float4 *>(top);
-        const float4 b4 = *reinterpret_cast<const float4 *>(bot);
-        v[0][0] = top[-1]; v[0][1] = t4.x; v[0][2] = t4.y; v[0][3] = t4.z; v[0][4] = t4.w; v[0][5] = top[4];
-        v[5][0] = bot[-1]; v[5][1] = b4.x; v[5][2] = b4.y; v[5][3] = b4.z; v[5][4] = b4.w; v[5][5] = bot[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          v[j + 1][0] = sW[(srow + j) * SP + scol - 1];
-          v[j + 1][5] = sW[(srow + j) * SP + scol + 4];
-        }
-      }
+      // A block has to be relaxed again only if one of its inputs changed since it last ran: its
+      // own cells (only it writes them) or the rim owned by the 8 neighbouring blocks.  Blocks
+      // that changed in the previous pass marked themselves and their neighbours.
+      const int par = iters & 1;
+      const bool need = (iters == 0) || (sDirty[par][dme] != 0);
       uint32_t ch = 0;
-      // forward Gauss-Seidel pass
+      if (need) {
+        sDirty[par][dme] = 0;  // this buffer is marked again two passes from now
+        // rim of the block (apron or neighbouring threads' cells; may be mid-update: harmless)
+        {
+          const float *top = &sW[(srow - 1) * SP + scol];
+          const float *bot = &sW[(srow + 4) * SP + scol];
+          const float4 t4 = *reinterpret_cast<const float4 *>(top);
+          const float4 b4 = *reinterpret_cast<const float4 *>(bot);
+          v[0][0] = top[-1]; v[0][1] = t4.x; v[0][2] = t4.y; v[0][3] = t4.z; v[0][4] = t4.w; v[0][5] = top[4];
+          v[5][0] = bot[-1]; v[5][1] = b4.x; v[5][2] = b4.y; v[5][3] = b4.z; v[5][4] = b4.w; v[5][5] = bot[4];
 #pragma unroll
-      for (int j = 1; j <= 4; j++) {
-#pragma unroll
-        for (int i = 1; i <= 4; i++) {
-          const float m = min8(v[j - 1][i - 1], v[j - 1][i], v[j - 1][i + 1], v[j][i - 1], v[j][i + 1],
-                               v[j + 1][i - 1], v[j + 1][i], v[j + 1][i + 1]);
-          const float nw = fmaxf(z[j - 1][i - 1], m);
-          if (nw < v[j][i]) {
-            v[j][i] = nw;
-            ch |= 1u << ((j - 1) * 4 + (i - 1));
+          for (int j = 0; j < 4; j++) {
+            v[j + 1][0] = sW[(srow + j) * SP + scol - 1];
+            v[j + 1][5] = sW[(srow + j) * SP + scol + 4];
           }
         }
-      }
-      // backward pass
+        // forward Gauss-Seidel pass
 #pragma unroll
-      for (int j = 4; j >= 1; j--) {
+        for (int j = 1; j <= 4; j++) {
 #pragma unroll
-        for (int i = 4; i >= 1; i--) {
-          const float m = min8(v[j - 1][i - 1], v[j - 1][i], v[j - 1][i + 1], v[j][i - 1], v[j][i + 1],
-                               v[j + 1][i - 1], v[j + 1][i], v[j + 1][i + 1]);
-          const float nw = fmaxf(z[j - 1][i - 1], m);
-          if (nw < v[j][i]) {
-            v[j][i] = nw;
-            ch |= 1u << ((j - 1) * 4 + (i - 1));
+          for (int i = 1; i <= 4; i++) {
+            const float m = min8(v[j - 1][i - 1], v[j - 1][i], v[j - 1][i + 1], v[j][i - 1], v[j][i + 1],
+                                 v[j + 1][i - 1], v[j + 1][i], v[j + 1][i + 1]);
+            const float nw = fmaxf(z[j - 1][i - 1], m);
+            if (nw < v[j][i]) {
+              v[j][i] = nw;
+              ch |= 1u << ((j - 1) * 4 + (i - 1));
+            }
           }
         }
-      }
-      // publish changed rows
+        // backward pass
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        if (ch & (0xFu << (4 * j))) {
-          *reinterpret_cast<float4 *>(&sW[(srow + j) * SP + scol]) =
-              make_float4(v[j + 1][1], v[j + 1][2], v[j + 1][3], v[j + 1][4]);
+        for (int j = 4; j >= 1; j--) {
+#pragma unroll
+          for (int i = 4; i >= 1; i--) {
+            const float m = min8(v[j - 1][i - 1], v[j - 1][i], v[j - 1][i + 1], v[j][i - 1], v[j][i + 1],
+                                 v[j + 1][i - 1], v[j + 1][i], v[j + 1][i + 1]);
+            const float nw = fmaxf(z[j - 1][i - 1], m);
+            if (nw < v[j][i]) {
+              v[j][i] = nw;
+              ch |= 1u << ((j - 1) * 4 + (i - 1));
+            }
+          }
+        }
+        if (ch) {
+          // publish changed rows and wake the blocks that read them
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (ch & (0xFu << (4 * j))) {
+              *reinterpret_cast<float4 *>(&sW[(srow + j) * SP + scol]) =
+                  make_float4(v[j + 1][1], v[j + 1][2], v[j + 1][3], v[j + 1][4]);
+            }
+          }
+          unsigned char *dn = &sDirty[par ^ 1][dme];
+          dn[0] = 1;  // a changed block re-checks itself (its two passes are not a local fixed point)
+          if (ch & 0x000Fu) { dn[-18] = 1; }
+          if (ch & 0xF000u) { dn[18] = 1; }
+          if (ch & 0x1111u) { dn[-1] = 1; }
+          if (ch & 0x8888u) { dn[1] = 1; }
+          if (ch & 0x0001u) { dn[-19] = 1; }
+          if (ch & 0x0008u) { dn[-17] = 1; }
+          if (ch & 0x1000u) { dn[17] = 1; }
+          if (ch & 0x8000u) { dn[19] = 1; }
+          chAll |= ch;
         }
       }
-      chAll |= ch;
       iters++;
       const int any = __syncthreads_or(ch != 0);
       if (!any) break;

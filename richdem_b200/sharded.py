@@ -89,8 +89,45 @@ class CudaBandSolver:
         return out
 
 
+def _neighbour_exchange(send_up, send_dn, g_top, g_bot, rank, group):
+    """Send a row to each existing neighbour and receive theirs (batched P2P).  Each of
+    send_up / send_dn may be a tensor or a list of tensors; returns matching receive buffers."""
+    def as_list(x):
+        return list(x) if isinstance(x, (list, tuple)) else [x]
+    ops, recv_up, recv_dn = [], None, None
+    if g_top:
+        su = as_list(send_up)
+        recv_up = [torch.empty_like(t) for t in su]
+        for t, r in zip(su, recv_up):
+            ops += [dist.P2POp(dist.isend, t, rank - 1, group), dist.P2POp(dist.irecv, r, rank - 1, group)]
+    if g_bot:
+        sd = as_list(send_dn)
+        recv_dn = [torch.empty_like(t) for t in sd]
+        for t, r in zip(sd, recv_dn):
+            ops += [dist.P2POp(dist.isend, t, rank + 1, group), dist.P2POp(dist.irecv, r, rank + 1, group)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return recv_up, recv_dn
+
+
+def exchange_rows(local: "torch.Tensor", g_top: int, g_bot: int, group=None) -> None:
+    """Fill the ghost rows of ``local`` with the neighbouring bands' edge rows (in place)."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return
+    rank = dist.get_rank(group)
+    h = local.shape[0]
+    up = local[1].contiguous() if g_top else None
+    dn = local[h - 2].contiguous() if g_bot else None
+    ru, rd = _neighbour_exchange(up, dn, g_top, g_bot, rank, group)
+    if ru is not None:
+        local[0].copy_(ru[0])
+    if rd is not None:
+        local[h - 1].copy_(rd[0])
+
+
 def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None, group=None,
-              max_rounds: int = 100000):
+              max_rounds: int = 100000, return_stats: bool = False):
     """Fill this rank's band.  ``local_dem`` is (g_top + owned + g_bot) x W with the ghost rows'
     contents ignored (they are initialised to +inf).  Returns (filled local raster incl. ghost rows,
     number of exchange rounds).  Collective: every rank of ``group`` must call it."""
@@ -119,24 +156,112 @@ def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None
         dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
         if int(flag.item()) == 0:
             break
-        ops, recv_up, recv_dn = [], None, None
-        if g_top:
-            send_up = solver.read_row(1)
-            recv_up = torch.empty_like(send_up)
-            ops += [dist.P2POp(dist.isend, send_up, rank - 1, group), dist.P2POp(dist.irecv, recv_up, rank - 1, group)]
-        if g_bot:
-            send_dn = solver.read_row(h - 2)
-            recv_dn = torch.empty_like(send_dn)
-            ops += [dist.P2POp(dist.isend, send_dn, rank + 1, group), dist.P2POp(dist.irecv, recv_dn, rank + 1, group)]
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+        send_up = solver.read_row(1) if g_top else None
+        send_dn = solver.read_row(h - 2) if g_bot else None
+        recv_up, recv_dn = _neighbour_exchange(send_up, send_dn, g_top, g_bot, rank, group)
         if recv_up is not None:
-            solver.update_row(0, recv_up)
+            solver.update_row(0, recv_up[0])
         if recv_dn is not None:
-            solver.update_row(h - 1, recv_dn)
+            solver.update_row(h - 1, recv_dn[0])
         if rounds >= max_rounds:
             raise RuntimeError("fill_band: exchange rounds exceeded max_rounds")
-    return solver.finish(), rounds
+    out = solver.finish()
+    if return_stats:
+        from . import _lib
+        return out, rounds, _lib.stats()
+    return out, rounds
+
+
+class CudaBandAccumulator:
+    """librichdem_b200's row-band accumulation entry points (rdb200_dev_facc_*)."""
+
+    def __init__(self, local_dem, local_accum, nodata: float, g_top: int, g_bot: int, dinf: bool, ones: bool):
+        from . import _lib
+        assert local_dem.is_cuda and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
+        assert local_accum.is_cuda and local_accum.dtype == torch.float64 and local_accum.is_contiguous()
+        self._lib = _lib
+        self.L = _lib.lib()
+        self.h, self.w = local_dem.shape
+        self.dev = local_dem.device
+        self.dinf = dinf
+        self._state = C.c_void_p()
+        _lib.check(self.L.rdb200_dev_facc_begin(C.byref(self._state), local_dem.data_ptr(), local_accum.data_ptr(),
+                                                self.w, self.h, float(nodata), int(g_top), int(g_bot), int(dinf),
+                                                int(ones)))
+
+    def edge_codes(self, which: int):
+        code = torch.empty(self.w, dtype=torch.uint8, device=self.dev)
+        rmax = torch.zeros(self.w, dtype=torch.float32, device=self.dev)
+        self._lib.check(self.L.rdb200_dev_facc_get_edge_codes(self._state, which, code.data_ptr(), rmax.data_ptr()))
+        return [code, rmax]
+
+    def set_ghost_codes(self, which: int, code, rmax):
+        self._lib.check(self.L.rdb200_dev_facc_set_ghost_codes(self._state, which, code.data_ptr(), rmax.data_ptr()))
+
+    def run(self):
+        a, b = C.c_int32(0), C.c_int32(0)
+        self._lib.check(self.L.rdb200_dev_facc_run(self._state, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def take_outflow(self, which: int):
+        s = torch.empty(self.w, dtype=torch.float64, device=self.dev)
+        c = torch.empty(self.w, dtype=torch.int32, device=self.dev)
+        self._lib.check(self.L.rdb200_dev_facc_take_outflow(self._state, which, s.data_ptr(), c.data_ptr()))
+        return [s, c]
+
+    def apply_inflow(self, which: int, s, c):
+        self._lib.check(self.L.rdb200_dev_facc_apply_inflow(self._state, which, s.data_ptr(), c.data_ptr()))
+
+    def finish(self):
+        self._lib.check(self.L.rdb200_dev_facc_finish(self._state))
+        self._state = None
+
+
+def fa_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, nodata: float, dinf: bool = False,
+            weights: Optional["torch.Tensor"] = None, rank_rows=None, group=None, max_rounds: int = 1000000,
+            return_stats: bool = False, accumulator_cls=None):
+    """FA_D8 / FA_Tarboton over this rank's band.  ``local_dem`` is (g_top + owned + g_bot) x W and
+    its ghost rows must already hold the neighbouring bands' elevations (``fill_band`` leaves them so;
+    otherwise call :func:`exchange_rows`).  ``weights`` (float64, same local shape) defaults to ones.
+    Returns (local accumulation incl. scratch ghost rows, exchange rounds[, stats])."""
+    accumulator_cls = accumulator_cls or CudaBandAccumulator
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    ones = weights is None
+    acc = torch.empty(local_dem.shape, dtype=torch.float64, device=local_dem.device) if ones else weights
+    A = accumulator_cls(local_dem, acc, nodata, g_top, g_bot, dinf, ones)
+    if world > 1:
+        up = A.edge_codes(0) if g_top else None
+        dn = A.edge_codes(1) if g_bot else None
+        ru, rd = _neighbour_exchange(up, dn, g_top, g_bot, rank, group)
+        if ru is not None:
+            A.set_ghost_codes(0, ru[0], ru[1])
+        if rd is not None:
+            A.set_ghost_codes(1, rd[0], rd[1])
+    rounds = 0
+    while True:
+        sent_t, sent_b = A.run()
+        rounds += 1
+        if world == 1:
+            break
+        flag = torch.tensor([1 if (sent_t + sent_b) > 0 else 0], dtype=torch.int32, device=local_dem.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()) == 0:
+            break
+        up = A.take_outflow(0) if g_top else None
+        dn = A.take_outflow(1) if g_bot else None
+        ru, rd = _neighbour_exchange(up, dn, g_top, g_bot, rank, group)
+        if ru is not None:
+            A.apply_inflow(0, ru[0], ru[1])
+        if rd is not None:
+            A.apply_inflow(1, rd[0], rd[1])
+        if rounds >= max_rounds:
+            raise RuntimeError("fa_band: exchange rounds exceeded max_rounds")
+    A.finish()
+    if return_stats:
+        from . import _lib
+        return acc, rounds, _lib.stats()
+    return acc, rounds
 
 
 def scatter_rows(full: Optional[np.ndarray], height: int, width: int, dtype, device, group=None):

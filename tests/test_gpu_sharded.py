@@ -57,3 +57,71 @@ def test_band_fill_equals_single_fill(checker, G):
     expected = checker.fill_depressions(dem)
     got, rounds = emulate_bands(dem, G)
     assert np.array_equal(got, expected), f"G={G}: {(got != expected).sum()} cells differ after {rounds} rounds"
+
+
+def emulate_fa_bands(dem: np.ndarray, G: int, nodata: float, dinf: bool, weights=None):
+    """Drive G CudaBandAccumulators on one device through the fa_band protocol."""
+    import torch
+    h, w = dem.shape
+    accs, metas, outs = [], [], []
+    for g in range(G):
+        r0, r1, gt, gb = sharded.local_rows(h, G, g)
+        local = torch.from_numpy(np.ascontiguousarray(dem[r0 - gt:r1 + gb])).cuda().contiguous()
+        if weights is None:
+            acc = torch.empty(local.shape, dtype=torch.float64, device="cuda")
+        else:
+            acc = torch.from_numpy(np.ascontiguousarray(weights[r0 - gt:r1 + gb])).cuda().contiguous()
+        A = sharded.CudaBandAccumulator(local, acc, nodata, gt, gb, dinf, weights is None)
+        accs.append(A)
+        outs.append(acc)
+        metas.append((r0, r1, gt, gb))
+    for g, (r0, r1, gt, gb) in enumerate(metas):  # exchange edge codes
+        if gt:
+            c = accs[g - 1].edge_codes(1)
+            accs[g].set_ghost_codes(0, c[0], c[1])
+        if gb:
+            c = accs[g + 1].edge_codes(0)
+            accs[g].set_ghost_codes(1, c[0], c[1])
+    rounds = 0
+    while True:
+        sent = [A.run() for A in accs]
+        rounds += 1
+        if not any(a + b for a, b in sent):
+            break
+        ups = {g: accs[g].take_outflow(0) for g, m in enumerate(metas) if m[2]}
+        dns = {g: accs[g].take_outflow(1) for g, m in enumerate(metas) if m[3]}
+        for g, (r0, r1, gt, gb) in enumerate(metas):
+            if gt:
+                accs[g].apply_inflow(0, *dns[g - 1])
+            if gb:
+                accs[g].apply_inflow(1, *ups[g + 1])
+        assert rounds < 10000
+    out = np.empty((h, w), np.float64)
+    for g, (r0, r1, gt, gb) in enumerate(metas):
+        accs[g].finish()
+        out[r0:r1] = outs[g][gt:gt + (r1 - r0)].cpu().numpy()
+    return out, rounds
+
+
+@pytest.mark.parametrize("G", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("dinf", [False, True])
+def test_band_accumulation_equals_single(checker, G, dinf):
+    nd = -9999.0
+    dem = oracle.fbm_terrain(640, 500, seed=41, quantum=0.25)
+    dem[100:140, 200:260] = nd
+    filled = checker.fill_depressions(dem)
+    resolved = checker.resolve_flats(filled, nd)
+    expected = checker.fa_dinf(resolved, nd) if dinf else checker.fa_d8(resolved, nd)
+    got, rounds = emulate_fa_bands(resolved, G, nd, dinf)
+    if dinf:
+        np.testing.assert_allclose(got, expected, rtol=1e-9, atol=0)
+    else:
+        assert np.array_equal(got, expected), f"G={G}: {(got != expected).sum()} cells differ ({rounds} rounds)"
+
+
+def test_band_accumulation_with_weights(checker):
+    nd = -9999.0
+    dem = checker.resolve_flats(checker.fill_depressions(oracle.fbm_terrain(300, 280, seed=43)), nd)
+    wts = np.random.default_rng(1).random(dem.shape)
+    got, _ = emulate_fa_bands(dem, 4, nd, False, weights=wts)
+    np.testing.assert_allclose(got, checker.fa_d8(dem, nd, wts), rtol=1e-9, atol=0)
