@@ -15,6 +15,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
     "--expt-relaxed-constexpr",
 ]
+# compile-time tuning knobs of the fill sweep (tile shape, CTA size), e.g. RDB_DEFS="-DRDB_TY=32"
+NVCC_FLAGS += os.environ.get("RDB_DEFS", "").split()
 
 
 def _nvcc() -> str:

@@ -226,6 +226,7 @@ int rdb200_set_param(const char *name, int64_t value) {
   if (n == "fill_max_iters") p.fill_max_iters = value;
   else if (n == "fill_rounds_per_sync") p.fill_rounds_per_sync = value > 0 ? value : 8;
   else if (n == "fill_use_tma") p.fill_use_tma = value;
+  else if (n == "fill_profile") p.fill_profile = value;
   else if (n == "accum_threads") p.accum_threads = value > 0 ? value : 256;
   else fail("rdb200_set_param: unknown parameter '%s'", name);
   CAPI_END

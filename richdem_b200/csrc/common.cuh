@@ -55,6 +55,7 @@ struct Params {
   int64_t fill_max_iters = 0;   // 0 = relax every tile visit to its local fixed point
   int64_t fill_rounds_per_sync = 8;
   int64_t fill_use_tma = 1;     // 0: plain ld.global staging (debug aid)
+  int64_t fill_profile = 0;     // 1: collect + print in-tile work counters (slower)
   int64_t accum_threads = 256;
 };
 

@@ -26,12 +26,28 @@ namespace rdb {
 
 namespace {
 
-constexpr int TX = 64;           // tile width  (cells)
-constexpr int TY = 64;           // tile height (cells)
+#ifndef RDB_TX
+#define RDB_TX 64
+#endif
+#ifndef RDB_TY
+#define RDB_TY 64
+#endif
+#ifndef RDB_FILL_THREADS
+#define RDB_FILL_THREADS 128
+#endif
+#ifndef RDB_FILL_MIN_CTAS
+#define RDB_FILL_MIN_CTAS 6
+#endif
+constexpr int TX = RDB_TX;       // tile width  (cells), multiple of 4, <= 248
+constexpr int TY = RDB_TY;       // tile height (cells), multiple of 4
+constexpr int BXN = TX / 4;      // 4x4 blocks per tile row
+constexpr int BYN = TY / 4;      // block rows per tile (<= 16: they are tracked in a 16-bit mask)
 constexpr int PADL = 4;          // cell (x,y) lives at padded (x+PADL, y+1)
 constexpr int SP = TX + 2 * PADL;  // shared-memory row pitch of the W tile (floats): 72
 constexpr int SROWS = TY + 2;    // W tile rows incl. apron: 66
-constexpr int FILL_THREADS = 256;  // 16 x 16 threads, each owning a 4x4 block
+constexpr int FILL_THREADS = RDB_FILL_THREADS;  // threads per CTA; each pass hands one dirty 4x4 block to a thread
+constexpr int FILL_MIN_CTAS = RDB_FILL_MIN_CTAS;
+static_assert(BYN <= 16 && BXN * BYN <= 256 && TX % 4 == 0 && TY % 4 == 0, "tile shape");
 constexpr uint32_t W_TILE_BYTES = SP * SROWS * 4;
 constexpr uint32_t Z_TILE_BYTES = TX * TY * 4;
 
@@ -44,6 +60,10 @@ struct FillDev {
   RoundCtl ctl[3];  // rotating: cur = round%3, next = (round+1)%3, being-zeroed = (round+2)%3
   unsigned long long visits;
   unsigned long long iters;
+  unsigned long long block_updates;  // 4x4 blocks relaxed (threads that did not skip a pass)
+  unsigned long long warp_updates;   // warps with at least one such thread
+  unsigned long long idle_visits;    // tile visits that changed nothing
+  unsigned long long iter_hist[8];   // visits by pass count: 1,2,3-4,5-8,9-16,17-32,33-64,65+
   int edge_changed;  // bit0: raster row 1 changed, bit1: raster row H-2 changed
   int pad;
 };
@@ -56,10 +76,12 @@ struct FillArgs {
   int tilesX, tilesY;
   int *list0, *list1;
   int *stamp;
+  int *sides;  // [2][tiles]: apron sides that changed, by round parity
   FillDev *dev;
   int round;
   int max_iters;
   int use_tma;
+  int profile;
 };
 
 // ---- PTX helpers: mbarrier + TMA ----------------------------------------------------------
@@ -101,41 +123,52 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- the sweep kernel --------------------------------------------------------------------
+// A tile is 16x16 "blocks" of 4x4 cells.  Relaxation is driven by a compacted list of dirty
+// blocks kept in shared memory: a pass hands one dirty block to each thread (so warps stay full
+// however sparse the activity is), the thread pulls the block and its rim into registers, runs a
+// forward and a backward Gauss-Seidel pass over the 16 cells, writes back the rows that changed
+// and marks the blocks that read the cells it changed.  Marks are compacted (ballot + popc) into
+// the next pass's list.  A visit starts from the blocks along the apron sides that changed since
+// the tile was last relaxed (the interior is still at its local fixed point).
+constexpr int NBLK = BXN * BYN;  // blocks per tile
+constexpr int MKP = BXN + 2;       // pitch of the mark array (one spare entry all round)
+// apron sides (and corners) of a tile that changed; SIDE_FULL = relax every block
+enum : int { SIDE_N = 1, SIDE_S = 2, SIDE_W = 4, SIDE_E = 8, SIDE_NW = 16, SIDE_NE = 32, SIDE_SW = 64,
+             SIDE_SE = 128, SIDE_FULL = 256 };
+
 __device__ __forceinline__ void enqueue_tile(const FillArgs &a, RoundCtl *next, int *list_next, int t,
-                                             int stampval) {
+                                             int stampval, int side_bits) {
+  atomicOr(&a.sides[(stampval & 1) * a.tilesX * a.tilesY + t], side_bits);
   if (atomicExch(&a.stamp[t], stampval) != stampval) {
     const int idx = atomicAdd(&next->count, 1);
     list_next[idx] = t;
   }
 }
 
-__device__ __forceinline__ float min8(float a, float b, float c, float d, float e, float f, float g,
-                                      float h) {
-  return fminf(fminf(fminf(a, b), fminf(c, d)), fminf(fminf(e, f), fminf(g, h)));
-}
+__device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
 
-// ---- the sweep kernel --------------------------------------------------------------------
-__global__ void __launch_bounds__(FILL_THREADS, 3)
+__global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     fill_sweep_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ,
                       const FillArgs a) {
   __shared__ __align__(128) float sW[SROWS * SP];
   __shared__ __align__(128) float sZ[TY * TX];
   __shared__ __align__(8) unsigned long long mbar;
+  __shared__ unsigned char sMark[MKP * (BYN + 2)];  // next-pass marks; spare rim so neighbour marks need no bounds checks
+  __shared__ unsigned char sList[2][NBLK];    // compacted dirty-block lists, double buffered
+  __shared__ int sCount[2];
   __shared__ int sTile;
   __shared__ int sFlags;
-  // per-thread-block "inputs changed" marks, double buffered by iteration parity; 18x18 so that
-  // marking the 8 neighbouring blocks needs no bounds checks (rim entries are never read)
-  __shared__ unsigned char sDirty[2][18 * 18];
+  __shared__ int sProf[2];
 
   const int tid = threadIdx.x;
-  const int tx = tid & 15;   // block column: cells 4tx..4tx+3
-  const int ty = tid >> 4;   // block row:    cells 4ty..4ty+3
   const int r = a.round;
   RoundCtl *cur = &a.dev->ctl[r % 3];
   RoundCtl *next = &a.dev->ctl[(r + 1) % 3];
   const int *list_cur = (r & 1) ? a.list1 : a.list0;
   int *list_next = (r & 1) ? a.list0 : a.list1;
   const int n = cur->count;
+  const int ntiles = a.tilesX * a.tilesY;
 
   if (blockIdx.x == 0 && tid == 0) {
     RoundCtl *z = &a.dev->ctl[(r + 2) % 3];
@@ -152,11 +185,9 @@ __global__ void __launch_bounds__(FILL_THREADS, 3)
   uint32_t phase = 0;
   const int max_iters = a.max_iters;
 
-  const int dme = (ty + 1) * 18 + (tx + 1);
   for (;;) {
     if (tid == 0) sTile = atomicAdd(&cur->take, 1);
-    sDirty[0][dme] = 0;
-    sDirty[1][dme] = 0;
+    for (int k = tid; k < MKP * (BYN + 2); k += FILL_THREADS) sMark[k] = 0;
     __syncthreads();  // publishes sTile (and the mbarrier init); all warps are done with smem
     const int li = sTile;
     if (li >= n) break;
@@ -165,83 +196,102 @@ __global__ void __launch_bounds__(FILL_THREADS, 3)
     const int x0 = txT * TX, y0 = tyT * TY;  // raster coords of the tile's first cell
 
     // ---- stage W (+apron) and Z ----
+    if (tid == 0) {
+      sFlags = 0;
+      sCount[0] = 0;
+      sCount[1] = 0;
+      sProf[0] = sProf[1] = 0;
+    }
     if (a.use_tma) {
       if (tid == 0) {
-        sFlags = 0;
         fence_proxy_async();  // order earlier generic-proxy smem accesses before the async writes
         mbar_arrive_expect_tx(&mbar, W_TILE_BYTES + Z_TILE_BYTES);
         tma_load_2d(sW, &mapW, x0, y0, &mbar);               // padded cols x0..x0+71, rows y0..y0+65
         tma_load_2d(sZ, &mapZ, x0 + PADL, y0 + 1, &mbar);    // the 64x64 interior
       }
-      mbar_wait(&mbar, phase);
-      phase ^= 1;
     } else {
-      if (tid == 0) sFlags = 0;
-      const float4 *gW = reinterpret_cast<const float4 *>(a.Wp + (size_t)y0 * a.pitch + x0);
       for (int k = tid; k < SROWS * (SP / 4); k += FILL_THREADS) {
         const int rr = k / (SP / 4), cc = k - rr * (SP / 4);
         reinterpret_cast<float4 *>(sW)[k] =
             __ldcg(reinterpret_cast<const float4 *>(a.Wp + (size_t)(y0 + rr) * a.pitch + x0) + cc);
       }
-      (void)gW;
       for (int k = tid; k < TY * (TX / 4); k += FILL_THREADS) {
         const int rr = k / (TX / 4), cc = k - rr * (TX / 4);
         reinterpret_cast<float4 *>(sZ)[k] = __ldg(
             reinterpret_cast<const float4 *>(a.Zp + (size_t)(y0 + 1 + rr) * a.pitch + x0 + PADL) + cc);
       }
-      __syncthreads();
     }
-
-    // ---- registers: own 4x4 block of W (v[1..4][1..4]) and Z ----
-    float v[6][6];
-    float z[4][4];
-    const int srow = 4 * ty + 1;     // smem row of own row 0
-    const int scol = 4 * tx + PADL;  // smem col of own col 0
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const float4 w4 = *reinterpret_cast<const float4 *>(&sW[(srow + j) * SP + scol]);
-      v[j + 1][1] = w4.x; v[j + 1][2] = w4.y; v[j + 1][3] = w4.z; v[j + 1][4] = w4.w;
-      const float4 z4 = *reinterpret_cast<const float4 *>(&sZ[(4 * ty + j) * TX + 4 * tx]);
-      z[j][0] = z4.x; z[j][1] = z4.y; z[j][2] = z4.z; z[j][3] = z4.w;
+    // ---- initial dirty list from the apron sides that changed (overlaps the TMA flight) ----
+    int sides = a.sides[(r & 1) * ntiles + t];
+    __syncthreads();  // everyone has read `sides` (and sCount is zero) before it is cleared
+    if (tid == 0) a.sides[(r & 1) * ntiles + t] = 0;
+    // seeded tile (start of a fill, or a ghost row was replaced): boundary cells may lie inside the
+    // tile when the raster edge is not tile-aligned, so relax every block once
+    if (sides == 0) sides = SIDE_FULL;
+    for (int b0 = 0; b0 < NBLK; b0 += FILL_THREADS) {
+      const int b = b0 + tid;
+      const int bx = b % BXN, by = b / BXN;
+      bool on = (sides & SIDE_FULL) != 0;
+      on |= (sides & SIDE_N) && by == 0;
+      on |= (sides & SIDE_S) && by == BYN - 1;
+      on |= (sides & SIDE_W) && bx == 0;
+      on |= (sides & SIDE_E) && bx == BXN - 1;
+      on |= (sides & SIDE_NW) && b == 0;
+      on |= (sides & SIDE_NE) && b == BXN - 1;
+      on |= (sides & SIDE_SW) && b == NBLK - BXN;
+      on |= (sides & SIDE_SE) && b == NBLK - 1;
+      on &= b < NBLK;
+      const unsigned bal = __ballot_sync(0xffffffffu, on);
+      if (bal) {
+        int base = 0;
+        if ((tid & 31) == 0) base = atomicAdd(&sCount[0], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (on) sList[0][base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (unsigned char)b;
+      }
     }
+    if (a.use_tma) {
+      mbar_wait(&mbar, phase);
+      phase ^= 1;
+    }
+    __syncthreads();  // list 0 complete; (non-TMA path) tile staged
 
-    uint32_t chAll = 0;  // cells of my block that changed during this visit (bit 4*j+i)
+    int f = 0;        // edge/corner-changed flags gathered by this thread
     int iters = 0;
+    int cl = 0;       // current list
     bool again = false;
-    for (;;) {
-      // A block has to be relaxed again only if one of its inputs changed since it last ran: its
-      // own cells (only it writes them) or the rim owned by the 8 neighbouring blocks.  Blocks
-      // that changed in the previous pass marked themselves and their neighbours.
-      const int par = iters & 1;
-      const bool need = (iters == 0) || (sDirty[par][dme] != 0);
-      uint32_t ch = 0;
-      if (need) {
-        sDirty[par][dme] = 0;  // this buffer is marked again two passes from now
-        // rim of the block (apron or neighbouring threads' cells; may be mid-update: harmless)
-        {
-          const float *top = &sW[(srow - 1) * SP + scol];
-          const float *bot = &sW[(srow + 4) * SP + scol];
-          const float4 t4 = *reinterpret_cast<const float4 *>(top);
-          const float4 b4 = *reinterpret_cast<const float4 *>(bot);
-          v[0][0] = top[-1]; v[0][1] = t4.x; v[0][2] = t4.y; v[0][3] = t4.z; v[0][4] = t4.w; v[0][5] = top[4];
-          v[5][0] = bot[-1]; v[5][1] = b4.x; v[5][2] = b4.y; v[5][3] = b4.z; v[5][4] = b4.w; v[5][5] = bot[4];
+    int nlist = sCount[0];
+    while (nlist > 0) {
+      if (tid == 0) sCount[cl ^ 1] = 0;
+      for (int i = tid; i < nlist; i += FILL_THREADS) {
+        const int b = sList[cl][i];
+        const int bx = b % BXN, by = b / BXN;
+        const int srow = 4 * by + 1, scol = 4 * bx + PADL;
+        float v[6][6];
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            v[j + 1][0] = sW[(srow + j) * SP + scol - 1];
-            v[j + 1][5] = sW[(srow + j) * SP + scol + 4];
-          }
+        for (int j = 0; j < 6; j++) {
+          const float *row = &sW[(srow - 1 + j) * SP + scol];
+          const float4 m4 = *reinterpret_cast<const float4 *>(row);
+          v[j][0] = row[-1]; v[j][1] = m4.x; v[j][2] = m4.y; v[j][3] = m4.z; v[j][4] = m4.w; v[j][5] = row[4];
         }
+        float z[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float4 z4 = *reinterpret_cast<const float4 *>(&sZ[(4 * by + j) * TX + 4 * bx]);
+          z[j][0] = z4.x; z[j][1] = z4.y; z[j][2] = z4.z; z[j][3] = z4.w;
+        }
+        uint32_t ch = 0;
         // forward Gauss-Seidel pass
 #pragma unroll
         for (int j = 1; j <= 4; j++) {
 #pragma unroll
-          for (int i = 1; i <= 4; i++) {
-            const float m = min8(v[j - 1][i - 1], v[j - 1][i], v[j - 1][i + 1], v[j][i - 1], v[j][i + 1],
-                                 v[j + 1][i - 1], v[j + 1][i], v[j + 1][i + 1]);
-            const float nw = fmaxf(z[j - 1][i - 1], m);
-            if (nw < v[j][i]) {
-              v[j][i] = nw;
-              ch |= 1u << ((j - 1) * 4 + (i - 1));
+          for (int i2 = 1; i2 <= 4; i2++) {
+            const float m = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
+                                  min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]),
+                                  fminf(v[j][i2 - 1], v[j][i2 + 1]));
+            const float nw = fmaxf(z[j - 1][i2 - 1], m);
+            if (nw < v[j][i2]) {
+              v[j][i2] = nw;
+              ch |= 1u << ((j - 1) * 4 + (i2 - 1));
             }
           }
         }
@@ -249,18 +299,18 @@ __global__ void __launch_bounds__(FILL_THREADS, 3)
 #pragma unroll
         for (int j = 4; j >= 1; j--) {
 #pragma unroll
-          for (int i = 4; i >= 1; i--) {
-            const float m = min8(v[j - 1][i - 1], v[j - 1][i], v[j - 1][i + 1], v[j][i - 1], v[j][i + 1],
-                                 v[j + 1][i - 1], v[j + 1][i], v[j + 1][i + 1]);
-            const float nw = fmaxf(z[j - 1][i - 1], m);
-            if (nw < v[j][i]) {
-              v[j][i] = nw;
-              ch |= 1u << ((j - 1) * 4 + (i - 1));
+          for (int i2 = 4; i2 >= 1; i2--) {
+            const float m = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
+                                  min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]),
+                                  fminf(v[j][i2 - 1], v[j][i2 + 1]));
+            const float nw = fmaxf(z[j - 1][i2 - 1], m);
+            if (nw < v[j][i2]) {
+              v[j][i2] = nw;
+              ch |= 1u << ((j - 1) * 4 + (i2 - 1));
             }
           }
         }
         if (ch) {
-          // publish changed rows and wake the blocks that read them
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             if (ch & (0xFu << (4 * j))) {
@@ -268,73 +318,107 @@ __global__ void __launch_bounds__(FILL_THREADS, 3)
                   make_float4(v[j + 1][1], v[j + 1][2], v[j + 1][3], v[j + 1][4]);
             }
           }
-          unsigned char *dn = &sDirty[par ^ 1][dme];
-          dn[0] = 1;  // a changed block re-checks itself (its two passes are not a local fixed point)
-          if (ch & 0x000Fu) { dn[-18] = 1; }
-          if (ch & 0xF000u) { dn[18] = 1; }
-          if (ch & 0x1111u) { dn[-1] = 1; }
-          if (ch & 0x8888u) { dn[1] = 1; }
-          if (ch & 0x0001u) { dn[-19] = 1; }
-          if (ch & 0x0008u) { dn[-17] = 1; }
-          if (ch & 0x1000u) { dn[17] = 1; }
-          if (ch & 0x8000u) { dn[19] = 1; }
-          chAll |= ch;
+          unsigned char *mk = &sMark[(by + 1) * MKP + (bx + 1)];
+          mk[0] = 1;  // two passes are not a local fixed point: look at this block again
+          if (ch & 0x000Fu) mk[-MKP] = 1;
+          if (ch & 0xF000u) mk[MKP] = 1;
+          if (ch & 0x1111u) mk[-1] = 1;
+          if (ch & 0x8888u) mk[1] = 1;
+          if (ch & 0x0001u) mk[-MKP - 1] = 1;
+          if (ch & 0x0008u) mk[-MKP + 1] = 1;
+          if (ch & 0x1000u) mk[MKP - 1] = 1;
+          if (ch & 0x8000u) mk[MKP + 1] = 1;
+          // which tile edges / corners / watched raster rows did this block touch?
+          if (by == 0 && (ch & 0x000Fu)) f |= SIDE_N;
+          if (by == BYN - 1 && (ch & 0xF000u)) f |= SIDE_S;
+          if (bx == 0 && (ch & 0x1111u)) f |= SIDE_W;
+          if (bx == BXN - 1 && (ch & 0x8888u)) f |= SIDE_E;
+          if (b == 0 && (ch & 0x0001u)) f |= SIDE_NW;
+          if (b == BXN - 1 && (ch & 0x0008u)) f |= SIDE_NE;
+          if (b == NBLK - BXN && (ch & 0x1000u)) f |= SIDE_SW;
+          if (b == NBLK - 1 && (ch & 0x8000u)) f |= SIDE_SE;
+          {
+            const int gy0 = y0 + 4 * by;  // raster row of this block's row 0
+            const int j1 = 1 - gy0, j2 = (a.H - 2) - gy0;
+            if (j1 >= 0 && j1 < 4 && (ch & (0xFu << (4 * j1)))) f |= 1 << 9;
+            if (j2 >= 0 && j2 < 4 && (ch & (0xFu << (4 * j2)))) f |= 1 << 10;
+          }
+          f |= 1 << (12 + by);  // block row `by` holds a changed cell (bits 12..27)
         }
       }
+      if (a.profile && tid == 0) {
+        sProf[0] += nlist;
+        sProf[1] += (nlist + 31) / 32;
+      }
       iters++;
-      const int any = __syncthreads_or(ch != 0);
-      if (!any) break;
-      if (max_iters > 0 && iters >= max_iters) {
-        again = true;  // not at the local fixed point yet: revisit next round
+      __syncthreads();  // marks and W rows of this pass are visible; list `cl` is consumed
+      // compact the marks into the other list
+      for (int b0 = 0; b0 < NBLK; b0 += FILL_THREADS) {
+        const int b = b0 + tid;
+        const int mi = (b / BXN + 1) * MKP + (b % BXN) + 1;
+        const bool on = (b < NBLK) && sMark[mi] != 0;
+        if (on) sMark[mi] = 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (bal) {
+          int base = 0;
+          if ((tid & 31) == 0) base = atomicAdd(&sCount[cl ^ 1], __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (on) sList[cl ^ 1][base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (unsigned char)b;
+        }
+      }
+      __syncthreads();
+      cl ^= 1;
+      nlist = sCount[cl];
+      if (nlist > 0 && max_iters > 0 && iters >= max_iters) {
+        again = true;  // not at the local fixed point yet: revisit (fully) next round
         break;
       }
     }
 
     // ---- write back + activate neighbours ----
-    const int tileChanged = __syncthreads_or(chAll != 0);
-    if (tileChanged) {
-      if (chAll) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          if (chAll & (0xFu << (4 * j))) {
-            float4 *dst = reinterpret_cast<float4 *>(a.Wp + (size_t)(y0 + 1 + 4 * ty + j) * a.pitch +
-                                                     (x0 + PADL + 4 * tx));
-            __stcg(dst, make_float4(v[j + 1][1], v[j + 1][2], v[j + 1][3], v[j + 1][4]));
-          }
+    if (f) atomicOr(&sFlags, f);
+    __syncthreads();
+    const int fl = sFlags;
+    const int rowch = (fl >> 12) & 0xFFFF;
+    if (rowch) {
+      // coalesced float4 write-back of the block rows (4 cell rows x 64) that hold a change
+      for (int k = tid; k < TY * (TX / 4); k += FILL_THREADS) {
+        const int rr = k / (TX / 4), cc = k % (TX / 4);
+        if (rowch & (1 << (rr >> 2))) {
+          const float4 val = *reinterpret_cast<const float4 *>(&sW[(rr + 1) * SP + PADL + 4 * cc]);
+          __stcg(reinterpret_cast<float4 *>(a.Wp + (size_t)(y0 + 1 + rr) * a.pitch + (x0 + PADL)) + cc, val);
         }
-        int f = 0;
-        if (ty == 0 && (chAll & 0x000Fu)) f |= 1;    // N edge row changed
-        if (ty == 15 && (chAll & 0xF000u)) f |= 2;   // S
-        if (tx == 0 && (chAll & 0x1111u)) f |= 4;    // W
-        if (tx == 15 && (chAll & 0x8888u)) f |= 8;   // E
-        // rows a neighbouring band holds as ghost rows (row-band multi-GPU mode)
-        {
-          const int gy0 = y0 + 4 * ty;  // raster row of my block row 0
-          const int j1 = 1 - gy0, j2 = (a.H - 2) - gy0;
-          if (j1 >= 0 && j1 < 4 && (chAll & (0xFu << (4 * j1)))) f |= 16;
-          if (j2 >= 0 && j2 < 4 && (chAll & (0xFu << (4 * j2)))) f |= 32;
-        }
-        if (f) atomicOr(&sFlags, f);
       }
-      __syncthreads();
-      if (tid == 0) {
-        const int f = sFlags;
+      if (tid < 8) {
+        // one thread per neighbour: the enqueue atomics (or + exch + add) overlap instead of
+        // queueing behind each other on a single thread
         const int sv = r + 1;
         const bool n_ok = tyT > 0, s_ok = tyT < a.tilesY - 1, w_ok = txT > 0, e_ok = txT < a.tilesX - 1;
-        if ((f & 1) && n_ok) enqueue_tile(a, next, list_next, t - a.tilesX, sv);
-        if ((f & 2) && s_ok) enqueue_tile(a, next, list_next, t + a.tilesX, sv);
-        if ((f & 4) && w_ok) enqueue_tile(a, next, list_next, t - 1, sv);
-        if ((f & 8) && e_ok) enqueue_tile(a, next, list_next, t + 1, sv);
-        if ((f & 5) == 5 && n_ok && w_ok) enqueue_tile(a, next, list_next, t - a.tilesX - 1, sv);
-        if ((f & 9) == 9 && n_ok && e_ok) enqueue_tile(a, next, list_next, t - a.tilesX + 1, sv);
-        if ((f & 6) == 6 && s_ok && w_ok) enqueue_tile(a, next, list_next, t + a.tilesX - 1, sv);
-        if ((f & 10) == 10 && s_ok && e_ok) enqueue_tile(a, next, list_next, t + a.tilesX + 1, sv);
-        if (again) enqueue_tile(a, next, list_next, t, sv);
-        if (f & 48) atomicOr(&a.dev->edge_changed, (f >> 4) & 3);
-        atomicAdd(&a.dev->iters, (unsigned long long)iters);
+        int nb = -1, bits = 0;
+        switch (tid) {
+          case 0: if ((fl & SIDE_N) && n_ok) { nb = t - a.tilesX; bits = SIDE_S; } break;
+          case 1: if ((fl & SIDE_S) && s_ok) { nb = t + a.tilesX; bits = SIDE_N; } break;
+          case 2: if ((fl & SIDE_W) && w_ok) { nb = t - 1; bits = SIDE_E; } break;
+          case 3: if ((fl & SIDE_E) && e_ok) { nb = t + 1; bits = SIDE_W; } break;
+          case 4: if ((fl & SIDE_NW) && n_ok && w_ok) { nb = t - a.tilesX - 1; bits = SIDE_SE; } break;
+          case 5: if ((fl & SIDE_NE) && n_ok && e_ok) { nb = t - a.tilesX + 1; bits = SIDE_SW; } break;
+          case 6: if ((fl & SIDE_SW) && s_ok && w_ok) { nb = t + a.tilesX - 1; bits = SIDE_NE; } break;
+          default: if ((fl & SIDE_SE) && s_ok && e_ok) { nb = t + a.tilesX + 1; bits = SIDE_NW; } break;
+        }
+        if (nb >= 0) enqueue_tile(a, next, list_next, nb, sv, bits);
+        if (tid == 0 && (fl & (3 << 9))) atomicOr(&a.dev->edge_changed, (fl >> 9) & 3);
       }
-    } else if (tid == 0) {
+    }
+    if (tid == 0) {
+      if (again) enqueue_tile(a, next, list_next, t, r + 1, SIDE_FULL);
       atomicAdd(&a.dev->iters, (unsigned long long)iters);
+      if (a.profile) {
+        if (!rowch) atomicAdd(&a.dev->idle_visits, 1ull);
+        atomicAdd(&a.dev->block_updates, (unsigned long long)sProf[0]);
+        atomicAdd(&a.dev->warp_updates, (unsigned long long)sProf[1]);
+        const int hb = iters <= 1 ? 0 : iters <= 2 ? 1 : iters <= 4 ? 2 : iters <= 8 ? 3 : iters <= 16 ? 4 : iters <= 32 ? 5 : iters <= 64 ? 6 : 7;
+        atomicAdd(&a.dev->iter_hist[hb], 1ull);
+      }
     }
   }
 }
@@ -411,7 +495,7 @@ CUtensorMap make_map(float *base, int pitch, int rows, int boxw, int boxh) {
 struct FillState {
   int W = 0, H = 0, pitch = 0, rows = 0, tilesX = 0, tilesY = 0;
   DevBuf<float> Zp, Wp;
-  DevBuf<int> list0, list1, stamp;
+  DevBuf<int> list0, list1, stamp, sides;
   DevBuf<FillDev> dev;
   CUtensorMap mapW, mapZ;
   int round = 0;
@@ -434,8 +518,10 @@ struct FillState {
     list0.alloc(nt);
     list1.alloc(nt);
     stamp.alloc(nt);
+    sides.alloc(2 * nt);
     dev.alloc(1);
     RDB_CK(cudaMemsetAsync(stamp.p, 0, nt * sizeof(int), c.stream));
+    RDB_CK(cudaMemsetAsync(sides.p, 0, 2 * nt * sizeof(int), c.stream));
     RDB_CK(cudaMemsetAsync(dev.p, 0, sizeof(FillDev), c.stream));
     {
       dim3 blk(128), grd((pitch / 4 + 127) / 128, rows < 32768 ? rows : 32768);
@@ -485,9 +571,11 @@ struct FillState {
     a.list0 = list0.p;
     a.list1 = list1.p;
     a.stamp = stamp.p;
+    a.sides = sides.p;
     a.dev = dev.p;
     a.max_iters = (int)c.params.fill_max_iters;
     a.use_tma = (int)c.params.fill_use_tma;
+    a.profile = (int)c.params.fill_profile;
     const int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 8);
     FillDev *hd = (FillDev *)c.pinned;
     RDB_CK(cudaMemsetAsync(&dev.p->edge_changed, 0, sizeof(int), c.stream));
@@ -513,6 +601,13 @@ struct FillState {
     c.stats.fill_tile_visits = (int64_t)hd->visits;
     c.stats.fill_tile_iters = (int64_t)hd->iters;
     c.stats.fill_tile_cells = TX * TY;
+    if (c.params.fill_profile) {
+      fprintf(stderr, "[fill profile] visits=%llu iters=%llu block_updates=%llu (%.1f%% of 256/iter) warp_updates=%llu (%.1f%% of 8/iter) idle_visits=%llu hist(1,2,3-4,5-8,9-16,17-32,33-64,65+)=",
+              hd->visits, hd->iters, hd->block_updates, 100.0 * hd->block_updates / (256.0 * hd->iters + 1),
+              hd->warp_updates, 100.0 * hd->warp_updates / (8.0 * hd->iters + 1), hd->idle_visits);
+      for (int k = 0; k < 8; k++) fprintf(stderr, "%llu ", hd->iter_hist[k]);
+      fprintf(stderr, "\n");
+    }
     return hd->edge_changed;
   }
 
