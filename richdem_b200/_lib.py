@@ -123,8 +123,20 @@ def init(device: int = 0) -> None:
 
 
 def set_stream(cuda_stream) -> None:
-    """Run subsequent work on `cuda_stream` (int handle, e.g. torch.cuda.current_stream().cuda_stream)."""
-    check(lib().rdb200_set_stream(C.c_void_p(int(cuda_stream) if cuda_stream else None)))
+    """Run subsequent work on `cuda_stream` (int handle, e.g. torch.cuda.current_stream().cuda_stream).
+    None restores the library's own stream; 0 (torch's default stream) selects CUDA's legacy default
+    stream explicitly (cudaStreamLegacy)."""
+    if cuda_stream is None:
+        check(lib().rdb200_set_stream(C.c_void_p(None)))
+    else:
+        h = int(cuda_stream)
+        check(lib().rdb200_set_stream(C.c_void_p(h if h != 0 else 1)))
+
+
+def use_torch_stream() -> None:
+    """Order the library's work with torch's: run on torch's current CUDA stream."""
+    import torch
+    set_stream(torch.cuda.current_stream().cuda_stream)
 
 
 def shutdown() -> None:

@@ -632,12 +632,17 @@ struct FillState {
     std::vector<char> mark((size_t)tilesX * tilesY, 0);
     std::vector<int> tiles;
     for (int y : pending_rows) {
-      const int tyT = y / TY;
-      for (int tx = 0; tx < tilesX; tx++) {
-        const int t = tyT * tilesX + tx;
-        if (!mark[t]) {
-          mark[t] = 1;
-          tiles.push_back(t);
+      // the replaced row sits in tile row y/TY, but it is also the apron of the tile row next to it
+      // when it is the first/last row of its tile: wake every tile row that can read it
+      for (int yy = y - 1; yy <= y + 1; yy++) {
+        if (yy < 0 || yy >= H) continue;
+        const int tyT = yy / TY;
+        for (int tx = 0; tx < tilesX; tx++) {
+          const int t = tyT * tilesX + tx;
+          if (!mark[t]) {
+            mark[t] = 1;
+            tiles.push_back(t);
+          }
         }
       }
     }

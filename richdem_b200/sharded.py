@@ -63,6 +63,7 @@ class CudaBandSolver:
         from . import _lib
         assert local_dem.is_cuda and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
         self._lib = _lib
+        _lib.use_torch_stream()  # torch ops (halo copies, NCCL) and our kernels share one stream
         self.h, self.w = local_dem.shape
         self.device = local_dem.device
         self._state = C.c_void_p()
@@ -180,6 +181,7 @@ class CudaBandAccumulator:
         assert local_dem.is_cuda and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
         assert local_accum.is_cuda and local_accum.dtype == torch.float64 and local_accum.is_contiguous()
         self._lib = _lib
+        _lib.use_torch_stream()
         self.L = _lib.lib()
         self.h, self.w = local_dem.shape
         self.dev = local_dem.device

@@ -235,3 +235,16 @@ def test_properties_at_8192():
     acc3 = torch.ones_like(acc)
     _lib.check(L.rdb200_dev_flow_accumulation_props_f64(props.data_ptr(), acc3.data_ptr(), N, N))
     assert torch.equal(acc, acc3)
+
+
+def test_cxx_dropin_matches_reference_cpu_templates():
+    """The C++ drop-in header: RichDEM call sites on Array2D<float> run on the GPU and agree with
+    the reference's own CPU templates instantiated for double (in-process oracle inside the binary)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "_bin", "cxx_dropin_check")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_bin/cxx_dropin_check not built (reference headers absent at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert "thrown=0 mismatches=0 dim_mismatch_throws=1" in out.stdout, out.stdout[-3000:]

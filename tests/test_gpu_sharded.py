@@ -51,6 +51,16 @@ def emulate_bands(dem: np.ndarray, G: int):
     return out, rounds
 
 
+def test_band_fill_ghost_row_on_tile_boundary(checker):
+    """Band heights chosen so a ghost row is the first row of a 64-row tile (its only real row):
+    replacing it must wake the tile row above, whose apron it is."""
+    dem = oracle.fbm_terrain(256, 320, seed=33, quantum=0.5)   # 2 bands of 128 rows -> ghost at local row 128
+    expected = checker.fill_depressions(dem)
+    for G in (2, 4):
+        got, _ = emulate_bands(dem, G)
+        assert np.array_equal(got, expected), f"G={G}"
+
+
 @pytest.mark.parametrize("G", [1, 2, 3, 4, 8])
 def test_band_fill_equals_single_fill(checker, G):
     dem = oracle.fbm_terrain(700, 900, seed=31, quantum=0.5)

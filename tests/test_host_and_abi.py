@@ -96,3 +96,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_cxx_dropin_header_links_and_fails_loudly_without_gpu():
+    """include/richdem_b200.hpp specialises the reference templates; the prebuilt check binary
+    (built by __graft_entry__.build() against /root/reference/include) must route every call into
+    librichdem_b200 -- on a box without a GPU that means 9 std::runtime_errors, no CPU fallback."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "_bin", "cxx_dropin_check")
+    if not os.path.exists(exe):
+        pytest.skip("tests/_bin/cxx_dropin_check not built (reference headers absent)")
+    if _has_gpu():
+        pytest.skip("GPU present: covered by the gpu-marked test")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert "calls=9 thrown=9" in out.stdout

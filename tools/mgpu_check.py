@@ -11,6 +11,7 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 _lib.init(lr)
+_lib.use_torch_stream()
 L = _lib.lib()
 ND = -9999.0
 res = {"world": world, "cases": []}
