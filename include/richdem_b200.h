@@ -171,8 +171,9 @@ RDB200_API int rdb200_dev_generate_fbm_f32(float *d_dem, int32_t width, int32_t 
 typedef struct rdb200_fill_state rdb200_fill_state;
 RDB200_API int rdb200_dev_fill_begin(rdb200_fill_state **state, const float *d_dem, int32_t width,
                           int32_t height);
-/* Relax to the local fixed point.  *changed_rows: bit0 = row 1 changed, bit1 = row height-2
- * changed since the previous run (the rows a neighbouring band holds as ghosts). */
+/* Relax to the local fixed point (or for about `fill_band_rounds` sweep rounds when that parameter
+ * is set).  *changed_rows: bit0 = row 1 changed, bit1 = row height-2 changed during this call (the
+ * rows a neighbouring band holds as ghosts); bit2 = tiles are still active (call again). */
 RDB200_API int rdb200_dev_fill_run(rdb200_fill_state *state, int32_t *changed_rows);
 /* Copy water-level row y (0..height-1) to d_row[width]. */
 RDB200_API int rdb200_dev_fill_read_row(rdb200_fill_state *state, int32_t y, float *d_row);

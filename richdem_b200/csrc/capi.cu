@@ -227,6 +227,9 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "fill_rounds_per_sync") p.fill_rounds_per_sync = value > 0 ? value : 8;
   else if (n == "fill_use_tma") p.fill_use_tma = value;
   else if (n == "fill_profile") p.fill_profile = value;
+  else if (n == "fill_ordered") p.fill_ordered = value;
+  else if (n == "fill_order_rounds") p.fill_order_rounds = value;
+  else if (n == "fill_band_rounds") p.fill_band_rounds = value;
   else if (n == "accum_threads") p.accum_threads = value > 0 ? value : 256;
   else fail("rdb200_set_param: unknown parameter '%s'", name);
   CAPI_END

@@ -55,6 +55,9 @@ struct Params {
   int64_t fill_max_iters = 0;   // 0 = relax every tile visit to its local fixed point
   int64_t fill_rounds_per_sync = 8;
   int64_t fill_use_tma = 1;     // 0: plain ld.global staging (debug aid)
+  int64_t fill_ordered = 1;       // admit tiles by rising water level (device-side feedback on the level)
+  int64_t fill_order_rounds = 0;  // rounds the level schedule spans (0: 0.8 x tiles across the raster)
+  int64_t fill_band_rounds = 0;   // row-band mode: rounds per rdb200_dev_fill_run call (0: to convergence)
   int64_t fill_profile = 0;     // 1: collect + print in-tile work counters (slower)
   int64_t accum_threads = 256;
 };

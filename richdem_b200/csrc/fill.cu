@@ -58,6 +58,7 @@ struct RoundCtl {
 
 struct FillDev {
   RoundCtl ctl[3];  // rotating: cur = round%3, next = (round+1)%3, being-zeroed = (round+2)%3
+  RoundCtl proc[3]; // level-ordered mode: tiles of the current worklist admitted this round
   unsigned long long visits;
   unsigned long long iters;
   unsigned long long block_updates;  // 4x4 blocks relaxed (threads that did not skip a pass)
@@ -65,7 +66,12 @@ struct FillDev {
   unsigned long long idle_visits;    // tile visits that changed nothing
   unsigned long long iter_hist[8];   // visits by pass count: 1,2,3-4,5-8,9-16,17-32,33-64,65+
   int edge_changed;  // bit0: raster row 1 changed, bit1: raster row H-2 changed
-  int pad;
+  int zmin_ord, zmax_ord;  // ordered-int min / max of the finite input elevations
+  unsigned long long deferred;  // tile visits postponed by the level schedule
+  // level-ordered admission (device-side feedback loop, see fill_admit_kernel)
+  float level, step, step_min, level_max;
+  int target, ordered;
+  int ndefer[3];  // tiles postponed by the admit kernel, by round%3
 };
 
 struct FillArgs {
@@ -77,6 +83,10 @@ struct FillArgs {
   int *list0, *list1;
   int *stamp;
   int *sides;  // [2][tiles]: apron sides that changed, by round parity
+  int *keys;   // [2][tiles]: ordered-int min of the water levels that arrived at the tile's apron
+  float level; // tiles whose key is above this level are postponed to a later round (+inf: none)
+  int *plist;  // level-ordered mode: admitted tiles of this round (filled by fill_admit_kernel)
+  int use_proc;
   FillDev *dev;
   int round;
   int max_iters;
@@ -137,9 +147,24 @@ constexpr int MKP = BXN + 2;       // pitch of the mark array (one spare entry a
 enum : int { SIDE_N = 1, SIDE_S = 2, SIDE_W = 4, SIDE_E = 8, SIDE_NW = 16, SIDE_NE = 32, SIDE_SW = 64,
              SIDE_SE = 128, SIDE_FULL = 256 };
 
+// order-preserving float <-> int map (so atomicMin/Max on ints orders floats, negatives included)
+__host__ __device__ __forceinline__ int f2ord(float f) {
+  int b;
+  memcpy(&b, &f, 4);
+  return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+__host__ __device__ __forceinline__ float ord2f(int o) {
+  const int b = o >= 0 ? o : (o ^ 0x7fffffff);
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+}
+constexpr int ORD_POS_INF = 0x7f800000;
+
 __device__ __forceinline__ void enqueue_tile(const FillArgs &a, RoundCtl *next, int *list_next, int t,
-                                             int stampval, int side_bits) {
+                                             int stampval, int side_bits, int key_ord) {
   atomicOr(&a.sides[(stampval & 1) * a.tilesX * a.tilesY + t], side_bits);
+  atomicMin(&a.keys[(stampval & 1) * a.tilesX * a.tilesY + t], key_ord);
   if (atomicExch(&a.stamp[t], stampval) != stampval) {
     const int idx = atomicAdd(&next->count, 1);
     list_next[idx] = t;
@@ -159,6 +184,7 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
   __shared__ int sCount[2];
   __shared__ int sTile;
   __shared__ int sFlags;
+  __shared__ int sKey;
   __shared__ int sProf[2];
 
   const int tid = threadIdx.x;
@@ -167,13 +193,20 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
   RoundCtl *next = &a.dev->ctl[(r + 1) % 3];
   const int *list_cur = (r & 1) ? a.list1 : a.list0;
   int *list_next = (r & 1) ? a.list0 : a.list1;
-  const int n = cur->count;
   const int ntiles = a.tilesX * a.tilesY;
+  if (a.use_proc) {  // the admit kernel already split this round's worklist
+    cur = &a.dev->proc[r % 3];
+    list_cur = a.plist;
+  }
+  const int n = cur->count;
 
   if (blockIdx.x == 0 && tid == 0) {
     RoundCtl *z = &a.dev->ctl[(r + 2) % 3];
     z->count = 0;
     z->take = 0;
+    RoundCtl *zp = &a.dev->proc[(r + 1) % 3];
+    zp->count = 0;
+    zp->take = 0;
     if (n > 0) atomicAdd(&a.dev->visits, (unsigned long long)n);
   }
   if (n == 0) return;
@@ -198,6 +231,7 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     // ---- stage W (+apron) and Z ----
     if (tid == 0) {
       sFlags = 0;
+      sKey = ORD_POS_INF;
       sCount[0] = 0;
       sCount[1] = 0;
       sProf[0] = sProf[1] = 0;
@@ -224,7 +258,10 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     // ---- initial dirty list from the apron sides that changed (overlaps the TMA flight) ----
     int sides = a.sides[(r & 1) * ntiles + t];
     __syncthreads();  // everyone has read `sides` (and sCount is zero) before it is cleared
-    if (tid == 0) a.sides[(r & 1) * ntiles + t] = 0;
+    if (tid == 0) {
+      a.sides[(r & 1) * ntiles + t] = 0;
+      a.keys[(r & 1) * ntiles + t] = ORD_POS_INF;
+    }
     // seeded tile (start of a fill, or a ghost row was replaced): boundary cells may lie inside the
     // tile when the raster edge is not tile-aligned, so relax every block once
     if (sides == 0) sides = SIDE_FULL;
@@ -256,6 +293,7 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     __syncthreads();  // list 0 complete; (non-TMA path) tile staged
 
     int f = 0;        // edge/corner-changed flags gathered by this thread
+    float kmin = __int_as_float(0x7f800000);  // lowest new water level this thread put on a tile edge
     int iters = 0;
     int cl = 0;       // current list
     bool again = false;
@@ -280,34 +318,34 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
           z[j][0] = z4.x; z[j][1] = z4.y; z[j][2] = z4.z; z[j][3] = z4.w;
         }
         uint32_t ch = 0;
-        // forward Gauss-Seidel pass
+        // Forward then backward Gauss-Seidel pass.  new = min(v, max(z, min8)) is evaluated as
+        //   min( min(v, max(z, min(7 other neighbours))),  max(z, just-updated neighbour) )
+        // (min/max distribute; no NaNs here), so the serial dependence between consecutive cells of a
+        // row is two FMNMX long instead of the whole stencil.
 #pragma unroll
         for (int j = 1; j <= 4; j++) {
 #pragma unroll
           for (int i2 = 1; i2 <= 4; i2++) {
-            const float m = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
-                                  min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]),
-                                  fminf(v[j][i2 - 1], v[j][i2 + 1]));
-            const float nw = fmaxf(z[j - 1][i2 - 1], m);
-            if (nw < v[j][i2]) {
-              v[j][i2] = nw;
-              ch |= 1u << ((j - 1) * 4 + (i2 - 1));
-            }
+            const float zz = z[j - 1][i2 - 1];
+            const float others = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
+                                       min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]), v[j][i2 + 1]);
+            const float b0 = fminf(v[j][i2], fmaxf(zz, others));
+            const float nw = fminf(b0, fmaxf(zz, v[j][i2 - 1]));  // v[j][i2-1] was updated one step ago
+            if (nw < v[j][i2]) ch |= 1u << ((j - 1) * 4 + (i2 - 1));
+            v[j][i2] = nw;
           }
         }
-        // backward pass
 #pragma unroll
         for (int j = 4; j >= 1; j--) {
 #pragma unroll
           for (int i2 = 4; i2 >= 1; i2--) {
-            const float m = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
-                                  min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]),
-                                  fminf(v[j][i2 - 1], v[j][i2 + 1]));
-            const float nw = fmaxf(z[j - 1][i2 - 1], m);
-            if (nw < v[j][i2]) {
-              v[j][i2] = nw;
-              ch |= 1u << ((j - 1) * 4 + (i2 - 1));
-            }
+            const float zz = z[j - 1][i2 - 1];
+            const float others = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
+                                       min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]), v[j][i2 - 1]);
+            const float b0 = fminf(v[j][i2], fmaxf(zz, others));
+            const float nw = fminf(b0, fmaxf(zz, v[j][i2 + 1]));  // v[j][i2+1] was updated one step ago
+            if (nw < v[j][i2]) ch |= 1u << ((j - 1) * 4 + (i2 - 1));
+            v[j][i2] = nw;
           }
         }
         if (ch) {
@@ -344,6 +382,13 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
             if (j2 >= 0 && j2 < 4 && (ch & (0xFu << (4 * j2)))) f |= 1 << 10;
           }
           f |= 1 << (12 + by);  // block row `by` holds a changed cell (bits 12..27)
+          if (bx == 0 || by == 0 || bx == BXN - 1 || by == BYN - 1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+              for (int i2 = 0; i2 < 4; i2++)
+                if (ch & (1u << (4 * j + i2))) kmin = fminf(kmin, v[j + 1][i2 + 1]);
+          }
         }
       }
       if (a.profile && tid == 0) {
@@ -376,7 +421,10 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     }
 
     // ---- write back + activate neighbours ----
-    if (f) atomicOr(&sFlags, f);
+    if (f) {
+      atomicOr(&sFlags, f);
+      if (f & 0xFF) atomicMin(&sKey, f2ord(kmin));
+    }
     __syncthreads();
     const int fl = sFlags;
     const int rowch = (fl >> 12) & 0xFFFF;
@@ -405,12 +453,12 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
           case 6: if ((fl & SIDE_SW) && s_ok && w_ok) { nb = t + a.tilesX - 1; bits = SIDE_NE; } break;
           default: if ((fl & SIDE_SE) && s_ok && e_ok) { nb = t + a.tilesX + 1; bits = SIDE_NW; } break;
         }
-        if (nb >= 0) enqueue_tile(a, next, list_next, nb, sv, bits);
+        if (nb >= 0) enqueue_tile(a, next, list_next, nb, sv, bits, sKey);
         if (tid == 0 && (fl & (3 << 9))) atomicOr(&a.dev->edge_changed, (fl >> 9) & 3);
       }
     }
     if (tid == 0) {
-      if (again) enqueue_tile(a, next, list_next, t, r + 1, SIDE_FULL);
+      if (again) enqueue_tile(a, next, list_next, t, r + 1, SIDE_FULL, f2ord(-__int_as_float(0x7f800000)));
       atomicAdd(&a.dev->iters, (unsigned long long)iters);
       if (a.profile) {
         if (!rowch) atomicAdd(&a.dev->idle_visits, 1ull);
@@ -423,15 +471,60 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
   }
 }
 
+// ---- level-ordered mode: split the round's worklist into admitted / postponed tiles ----------
+// Tiles whose lowest incoming water level is above the round's level are carried over to the next
+// round untouched (their side masks and keys move to the other parity); flooding then proceeds
+// roughly in order of rising water level, as the serial priority flood does, which avoids
+// flooding a tile with a high level that a lower one will overwrite later.
+__global__ void __launch_bounds__(256) fill_admit_kernel(const FillArgs a) {
+  const int r = a.round;
+  const RoundCtl *cur = &a.dev->ctl[r % 3];
+  RoundCtl *next = &a.dev->ctl[(r + 1) % 3];
+  RoundCtl *proc = &a.dev->proc[r % 3];
+  const int *list_cur = (r & 1) ? a.list1 : a.list0;
+  int *list_next = (r & 1) ? a.list0 : a.list1;
+  const int n = cur->count;
+  const int ntiles = a.tilesX * a.tilesY;
+  const float level = a.level;
+  int nd = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int t = list_cur[i];
+    const int kord = a.keys[(r & 1) * ntiles + t];
+    if (ord2f(kord) <= level) {
+      a.plist[atomicAdd(&proc->count, 1)] = t;
+    } else {
+      int bits = a.sides[(r & 1) * ntiles + t];
+      if (bits == 0) bits = SIDE_FULL;
+      a.sides[(r & 1) * ntiles + t] = 0;
+      a.keys[(r & 1) * ntiles + t] = ORD_POS_INF;
+      enqueue_tile(a, next, list_next, t, r + 1, bits, kord);
+      nd++;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, o);
+  if ((threadIdx.x & 31) == 0 && nd) atomicAdd(&a.dev->ndefer[r % 3], nd);
+}
+
+// host-chosen seeds (perimeter tiles at the start, tiles next to a replaced ghost row later)
+__global__ void __launch_bounds__(256) fill_seed_kernel(const FillArgs a, const int *__restrict__ tiles, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int r = a.round;
+  // enqueue_tile() targets round `stampval`: here the round about to be launched
+  RoundCtl *cur = &a.dev->ctl[r % 3];
+  int *list_cur = (r & 1) ? a.list1 : a.list0;
+  enqueue_tile(a, cur, list_cur, tiles[i], r, SIDE_FULL, f2ord(-__int_as_float(0x7f800000)));
+}
+
 // ---- layout kernels ----------------------------------------------------------------------
 // compact dem (H x W) -> padded Z and W.  Border cells (all four sides of the raster handed in)
 // are boundary conditions: W = Z = dem there; interior W = +inf; padding Z = W = +inf.
 __global__ void fill_init_kernel(const float *__restrict__ dem, float *__restrict__ Zp,
-                                 float *__restrict__ Wp, int W, int H, int pitch, int rows) {
+                                 float *__restrict__ Wp, int W, int H, int pitch, int rows, FillDev *dev) {
   const int px4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // padded column (multiple of 4)
-  if (px4 >= pitch) return;
   const float inf = __int_as_float(0x7f800000);
-  for (int py = blockIdx.y; py < rows; py += gridDim.y) {
+  float lo = inf, hi = -inf;
+  for (int py = blockIdx.y; py < rows && px4 < pitch; py += gridDim.y) {
     float zv[4], wv[4];
     const int y = py - 1;
 #pragma unroll
@@ -442,6 +535,10 @@ __global__ void fill_init_kernel(const float *__restrict__ dem, float *__restric
         zz = dem[(size_t)y * W + x];
         const bool border = (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
         ww = border ? zz : inf;
+        if (zz < inf && zz > -inf) {
+          lo = fminf(lo, zz);
+          hi = fmaxf(hi, zz);
+        }
       }
       zv[k] = zz;
       wv[k] = ww;
@@ -450,6 +547,52 @@ __global__ void fill_init_kernel(const float *__restrict__ dem, float *__restric
     *reinterpret_cast<float4 *>(Zp + o) = make_float4(zv[0], zv[1], zv[2], zv[3]);
     *reinterpret_cast<float4 *>(Wp + o) = make_float4(wv[0], wv[1], wv[2], wv[3]);
   }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float slo[4], shi[4];  // blockDim.x == 128
+  if ((threadIdx.x & 31) == 0) {
+    slo[threadIdx.x >> 5] = lo;
+    shi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    lo = fminf(fminf(slo[0], slo[1]), fminf(slo[2], slo[3]));
+    hi = fmaxf(fmaxf(shi[0], shi[1]), fmaxf(shi[2], shi[3]));
+    if (lo <= hi) {
+      atomicMin(&dev->zmin_ord, f2ord(lo));
+      atomicMax(&dev->zmax_ord, f2ord(hi));
+    }
+  }
+}
+
+// sampled histogram of the input elevations (every `row_stride`-th padded row) for the level schedule
+constexpr int HIST_BINS = 1024;
+__global__ void __launch_bounds__(256) fill_hist_kernel(const float *__restrict__ Zp, int pitch, int rows, int row_stride,
+                                                         float zmin, float inv_range, unsigned int *hist) {
+  __shared__ unsigned int sh[HIST_BINS];
+  for (int k = threadIdx.x; k < HIST_BINS; k += blockDim.x) sh[k] = 0;
+  __syncthreads();
+  const int row = blockIdx.x * row_stride + 1;
+  if (row < rows) {
+    for (int x = threadIdx.x; x < pitch; x += blockDim.x) {
+      const float zv = Zp[(size_t)row * pitch + x];
+      if (zv < __int_as_float(0x7f800000) && zv > -__int_as_float(0x7f800000)) {
+        int b = (int)((zv - zmin) * inv_range * HIST_BINS);
+        b = b < 0 ? 0 : (b >= HIST_BINS ? HIST_BINS - 1 : b);
+        atomicAdd(&sh[b], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < HIST_BINS; k += blockDim.x)
+    if (sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+
+__global__ void fill_i32_kernel(int *p, int v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 __global__ void fill_finish_kernel(const float *__restrict__ Wp, float *__restrict__ out, int W, int H,
@@ -495,12 +638,18 @@ CUtensorMap make_map(float *base, int pitch, int rows, int boxw, int boxh) {
 struct FillState {
   int W = 0, H = 0, pitch = 0, rows = 0, tilesX = 0, tilesY = 0;
   DevBuf<float> Zp, Wp;
-  DevBuf<int> list0, list1, stamp, sides;
+  DevBuf<int> list0, list1, plist, stamp, sides, keys;
+  float zmin = 0.f, zmax = 0.f;
+  bool first_run = true;
+  bool ordered = false;
+  std::vector<float> levels;
   DevBuf<FillDev> dev;
   CUtensorMap mapW, mapZ;
   int round = 0;
   int grid = 0;
   int64_t rounds_run = 0;
+  bool still_active = false;
+  int64_t sched_round = 0;
   unsigned long long visits_seen = 0, iters_seen = 0;
 
   void begin(const float *d_dem, int w, int h) {
@@ -517,17 +666,68 @@ struct FillState {
     const size_t nt = (size_t)tilesX * tilesY;
     list0.alloc(nt);
     list1.alloc(nt);
+    plist.alloc(nt);
     stamp.alloc(nt);
     sides.alloc(2 * nt);
+    keys.alloc(2 * nt);
     dev.alloc(1);
     RDB_CK(cudaMemsetAsync(stamp.p, 0, nt * sizeof(int), c.stream));
     RDB_CK(cudaMemsetAsync(sides.p, 0, 2 * nt * sizeof(int), c.stream));
-    RDB_CK(cudaMemsetAsync(dev.p, 0, sizeof(FillDev), c.stream));
     {
-      dim3 blk(128), grd((pitch / 4 + 127) / 128, rows < 32768 ? rows : 32768);
-      fill_init_kernel<<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows);
+      FillDev h0;
+      memset(&h0, 0, sizeof(h0));
+      h0.zmin_ord = ORD_POS_INF;
+      h0.zmax_ord = f2ord(-__builtin_inff());
+      memcpy(c.pinned, &h0, sizeof(h0));
+      RDB_CK(cudaMemcpyAsync(dev.p, c.pinned, sizeof(FillDev), cudaMemcpyHostToDevice, c.stream));
+      // keys start at +inf (0x7f800000 repeated is not a byte pattern: fill with a tiny kernel-free trick:
+      // ORD_POS_INF = 0x7f800000 -> use cudaMemsetD32-equivalent via cuMemset is driver API; a 1-line kernel is simpler)
+    }
+    {
+      const int n2 = (int)(2 * nt);
+      fill_i32_kernel<<<(n2 + 255) / 256, 256, 0, c.stream>>>(keys.p, ORD_POS_INF, n2);
+      dim3 blk(128), grd((pitch / 4 + 127) / 128, rows < 2048 ? rows : 2048);
+      fill_init_kernel<<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows, dev.p);
       RDB_CK(cudaGetLastError());
-      count_launch();
+      count_launch(2);
+      FillDev *hd = (FillDev *)c.pinned;
+      RDB_CK(cudaMemcpyAsync(hd, dev.p, sizeof(FillDev), cudaMemcpyDeviceToHost, c.stream));
+      RDB_CK(cudaStreamSynchronize(c.stream));
+      zmin = ord2f(hd->zmin_ord);
+      zmax = ord2f(hd->zmax_ord);
+      if (!(zmin <= zmax)) zmin = zmax = 0.f;
+      ordered = c.params.fill_ordered != 0 && zmax > zmin;
+      levels.clear();
+      if (ordered) {
+        // Level schedule: round k admits tiles whose incoming water level is below the k/R quantile of
+        // the input elevations, so about the same number of cells becomes floodable every round.
+        int64_t R = c.params.fill_order_rounds;
+        if (R <= 0) R = (int64_t)(0.8 * (tilesX > tilesY ? tilesX : tilesY));
+        if (R < 8) {
+          ordered = false;
+        } else {
+          DevBuf<unsigned int> hist(HIST_BINS);
+          RDB_CK(cudaMemsetAsync(hist.p, 0, HIST_BINS * sizeof(unsigned int), c.stream));
+          const int stride = rows > 4096 ? 16 : (rows > 512 ? 4 : 1);
+          const int nb = (rows - 2 + stride - 1) / stride;
+          fill_hist_kernel<<<nb, 256, 0, c.stream>>>(Zp.p, pitch, rows, stride, zmin, 1.0f / (zmax - zmin), hist.p);
+          RDB_CK(cudaGetLastError());
+          count_launch();
+          unsigned int *hh = (unsigned int *)c.pinned;
+          RDB_CK(cudaMemcpyAsync(hh, hist.p, HIST_BINS * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+          RDB_CK(cudaStreamSynchronize(c.stream));
+          double total = 0;
+          for (int k = 0; k < HIST_BINS; k++) total += hh[k];
+          levels.resize((size_t)R);
+          double cum = 0;
+          int bin = 0;
+          for (int64_t k = 0; k < R; k++) {
+            const double want = total * (double)(k + 1) / (double)R;
+            while (bin < HIST_BINS - 1 && cum + hh[bin] < want) cum += hh[bin++];
+            levels[(size_t)k] = zmin + (zmax - zmin) * (float)(bin + 1) / (float)HIST_BINS;
+          }
+        }
+      }
     }
     mapW = make_map(Wp.p, pitch, rows, SP, SROWS);
     mapZ = make_map(Zp.p, pitch, rows, TX, TY);
@@ -535,7 +735,7 @@ struct FillState {
     RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_sweep_kernel, FILL_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     grid = c.num_sms * per_sm;
-    round = 0;
+    round = 1;  // stamps start at 0, so round numbers (used as stamp values) start at 1
     // initial worklist: every tile on the perimeter of the tile grid (the only tiles whose
     // cells can see a finite neighbour at the start)
     std::vector<int> init;
@@ -545,22 +745,25 @@ struct FillState {
     seed_worklist(init);
   }
 
-  // place `tiles` (deduplicated) as the worklist of the next round to be launched
+  // add `tiles` to the worklist of the next round to be launched (always eligible: key = -inf,
+  // relax every block).  Tiles already waiting in that list are not duplicated (round stamp).
   void seed_worklist(const std::vector<int> &tiles) {
     Ctx &c = ctx();
-    int *lst = (round & 1) ? list1.p : list0.p;
-    RDB_CK(cudaMemcpyAsync(lst, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-    RoundCtl ctl[3];
-    memset(ctl, 0, sizeof(ctl));
-    ctl[round % 3].count = (int)tiles.size();
-    RDB_CK(cudaMemcpyAsync(&dev.p->ctl[0], ctl, sizeof(ctl), cudaMemcpyHostToDevice, c.stream));
-    RDB_CK(cudaStreamSynchronize(c.stream));  // host vectors go out of scope
+    if (tiles.empty()) return;
+    DevBuf<int> d(tiles.size());
+    RDB_CK(cudaMemcpyAsync(d.p, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    FillArgs a = make_args();
+    a.round = round;
+    fill_seed_kernel<<<(unsigned)((tiles.size() + 255) / 256), 256, 0, c.stream>>>(a, d.p, (int)tiles.size());
+    RDB_CK(cudaGetLastError());
+    count_launch();
+    RDB_CK(cudaStreamSynchronize(c.stream));  // host vector / scratch go out of scope
   }
 
-  // run rounds until the worklist is empty; returns the edge_changed bits accumulated
-  int run() {
+  FillArgs make_args() {
     Ctx &c = ctx();
     FillArgs a;
+    memset(&a, 0, sizeof(a));
     a.Zp = Zp.p;
     a.Wp = Wp.p;
     a.pitch = pitch;
@@ -572,10 +775,22 @@ struct FillState {
     a.list1 = list1.p;
     a.stamp = stamp.p;
     a.sides = sides.p;
+    a.keys = keys.p;
+    a.plist = plist.p;
     a.dev = dev.p;
     a.max_iters = (int)c.params.fill_max_iters;
     a.use_tma = (int)c.params.fill_use_tma;
     a.profile = (int)c.params.fill_profile;
+    a.level = __builtin_inff();
+    return a;
+  }
+
+  // max_rounds > 0: stop after about that many rounds even if tiles are still active (bit 2 of the
+  // result then says so); the caller exchanges halos and calls run again
+  int run(int64_t max_rounds = 0) {
+    Ctx &c = ctx();
+    int64_t rounds_this_call = 0;
+    FillArgs a = make_args();
     const int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 8);
     FillDev *hd = (FillDev *)c.pinned;
     RDB_CK(cudaMemsetAsync(&dev.p->edge_changed, 0, sizeof(int), c.stream));
@@ -583,6 +798,17 @@ struct FillState {
       KernelTimer kt;  // device time of the sweep launches only (read-back excluded)
       for (int k = 0; k < per_sync; k++) {
         a.round = round;
+        // level-ordered admission while the schedule lasts; afterwards every active tile is processed
+        if (ordered && sched_round < (int64_t)levels.size()) {
+          a.level = levels[(size_t)sched_round];
+          a.use_proc = 1;
+          fill_admit_kernel<<<c.num_sms * 2, 256, 0, c.stream>>>(a);
+          c.stats.kernel_launches++;
+        } else {
+          a.level = __builtin_inff();
+          a.use_proc = 0;
+        }
+        sched_round++;
         fill_sweep_kernel<<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
         round++;
       }
@@ -594,21 +820,25 @@ struct FillState {
       // rounds that found an empty worklist are not counted as launches of interest
       c.stats.kernel_launches += per_sync;
       rounds_run += per_sync;
-      if (hd->ctl[round % 3].count == 0) break;
+      rounds_this_call += per_sync;
+      still_active = hd->ctl[round % 3].count != 0;
+      if (!still_active) break;
+      if (max_rounds > 0 && rounds_this_call >= max_rounds) break;
       if (round > (1 << 30)) fail("fill: round counter overflow");
     }
+    if (!still_active) first_run = false;
     c.stats.fill_rounds = rounds_run;
     c.stats.fill_tile_visits = (int64_t)hd->visits;
     c.stats.fill_tile_iters = (int64_t)hd->iters;
     c.stats.fill_tile_cells = TX * TY;
     if (c.params.fill_profile) {
-      fprintf(stderr, "[fill profile] visits=%llu iters=%llu block_updates=%llu (%.1f%% of 256/iter) warp_updates=%llu (%.1f%% of 8/iter) idle_visits=%llu hist(1,2,3-4,5-8,9-16,17-32,33-64,65+)=",
-              hd->visits, hd->iters, hd->block_updates, 100.0 * hd->block_updates / (256.0 * hd->iters + 1),
+      fprintf(stderr, "[fill profile] deferred=%llu visits=%llu iters=%llu block_updates=%llu (%.1f%% of 256/iter) warp_updates=%llu (%.1f%% of 8/iter) idle_visits=%llu hist(1,2,3-4,5-8,9-16,17-32,33-64,65+)=",
+              hd->deferred, hd->visits, hd->iters, hd->block_updates, 100.0 * hd->block_updates / (256.0 * hd->iters + 1),
               hd->warp_updates, 100.0 * hd->warp_updates / (8.0 * hd->iters + 1), hd->idle_visits);
       for (int k = 0; k < 8; k++) fprintf(stderr, "%llu ", hd->iter_hist[k]);
       fprintf(stderr, "\n");
     }
-    return hd->edge_changed;
+    return hd->edge_changed | (still_active ? 4 : 0);
   }
 
   void read_row(int y, float *d_row) {
@@ -713,7 +943,7 @@ int rdb200_dev_fill_run(rdb200_fill_state *state, int32_t *changed_rows) {
   RDB_CAPI_TRY
   if (!state) rdb::fail("fill_run: null state");
   state->st.activate_pending();
-  const int ch = state->st.run();
+  const int ch = state->st.run(rdb::ctx().params.fill_band_rounds);
   if (changed_rows) *changed_rows = ch;
   RDB_CAPI_END
 }

@@ -143,9 +143,11 @@ def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None
     solver = solver_cls(local_dem)
     rounds = 0
     while True:
-        changed = solver.run()
+        changed = solver.run()   # bits 0/1: my edge rows changed; bit 2: tiles still active (bounded run)
         rounds += 1
         if world == 1:
+            if changed & 4:
+                continue
             break
         # rows my neighbours hold as ghosts: local row 1 (if there is a band above), row h-2 (below)
         my_change = 0
@@ -153,10 +155,15 @@ def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None
             my_change = 1
         if g_bot and (changed & 2 or rounds == 1):
             my_change = 1
+        if changed & 4:
+            my_change |= 2
         flag = torch.tensor([my_change], dtype=torch.int32, device=local_dem.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
-        if int(flag.item()) == 0:
+        dist.all_reduce(flag, op=dist.ReduceOp.BOR, group=group)
+        gflag = int(flag.item())
+        if gflag == 0:
             break
+        if not (gflag & 1):
+            continue  # someone is still relaxing but no edge row moved: nothing to exchange
         send_up = solver.read_row(1) if g_top else None
         send_dn = solver.read_row(h - 2) if g_bot else None
         recv_up, recv_dn = _neighbour_exchange(send_up, send_dn, g_top, g_bot, rank, group)
