@@ -19,6 +19,7 @@ namespace {
 
 constexpr uint32_t kDepsMask = 0xFFu;
 constexpr uint32_t kSrcFlag = 0x80000000u;
+constexpr int kCodeSole = 32;  // bit 5 of a code byte: this cell is the only donor of its receiver
 
 // ---- K1: dem -> compact flow code (+ rmax for D-infinity), weights/NoData initialisation ------
 template <bool DINF>
@@ -51,9 +52,75 @@ __global__ void __launch_bounds__(256) flow_code_kernel(const float *__restrict_
   else if (ones) accum[i] = 1.0;
 }
 
+// D8 fast path: 4 consecutive cells of one row per thread (float4 row loads, uchar4 / double2 stores).
+// Requires W % 4 == 0.  Same per-cell rule as fm_d8_cell (reference flowmet/OCallaghan1984.hpp:37-75).
+__global__ void __launch_bounds__(256) flow_code_d8_x4_kernel(const float *__restrict__ dem, uint8_t *__restrict__ code,
+                                                               double *__restrict__ accum, int W, int H, float nodata,
+                                                               int ones) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x4 >= W) return;
+  for (int y = blockIdx.y; y < H; y += gridDim.y) {
+    const size_t i0 = (size_t)y * W + x4;
+    float r[3][6];  // rows y-1, y, y+1 ; columns x4-1 .. x4+4
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int yy = y + j - 1;
+      if (yy < 0 || yy >= H) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) r[j][k] = 0.f;
+      } else {
+        const float *row = dem + (size_t)yy * W + x4;
+        const float4 m = __ldg(reinterpret_cast<const float4 *>(row));
+        r[j][1] = m.x; r[j][2] = m.y; r[j][3] = m.z; r[j][4] = m.w;
+        r[j][0] = x4 > 0 ? __ldg(row - 1) : 0.f;
+        r[j][5] = x4 + 4 < W ? __ldg(row + 4) : 0.f;
+      }
+    }
+    uint8_t cd[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int x = x4 + k;
+      const float e = r[1][k + 1];
+      int c;
+      if (e == nodata) {
+        c = kCodeNoData;
+      } else if (x == 0 || y == 0 || x == W - 1 || y == H - 1) {
+        c = 0;
+      } else {
+        // neighbours n = 1..8 : W, NW, N, NE, E, SE, S, SW
+        const float ne[9] = {0.f, r[1][k], r[0][k], r[0][k + 1], r[0][k + 2], r[1][k + 2], r[2][k + 2], r[2][k + 1], r[2][k]};
+        int lowest_n = 0;
+        float lowest = 3.402823466e+38f;
+#pragma unroll
+        for (int n = 1; n <= 8; n++) {
+          const float v = ne[n];
+          if (v == nodata) continue;
+          if (v >= e) continue;
+          if (v < lowest) {
+            lowest = v;
+            lowest_n = n;
+          }
+        }
+        c = lowest_n;
+      }
+      cd[k] = (uint8_t)c;
+    }
+    *reinterpret_cast<uchar4 *>(code + i0) = make_uchar4(cd[0], cd[1], cd[2], cd[3]);
+    double *ap = accum + i0;
+    if (ones) {
+      reinterpret_cast<double2 *>(ap)[0] = make_double2(cd[0] == kCodeNoData ? -1.0 : 1.0, cd[1] == kCodeNoData ? -1.0 : 1.0);
+      reinterpret_cast<double2 *>(ap)[1] = make_double2(cd[2] == kCodeNoData ? -1.0 : 1.0, cd[3] == kCodeNoData ? -1.0 : 1.0);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (cd[k] == kCodeNoData) ap[k] = -1.0;
+    }
+  }
+}
+
 // ---- K2: dependency counters by gathering over the 8 neighbours' codes; marks sources ----------
-__global__ void __launch_bounds__(256) deps_gather_kernel(const uint8_t *__restrict__ code, uint32_t *__restrict__ st,
-                                                           int W, int H, int y_lo, int y_hi) {
+__global__ void __launch_bounds__(256) deps_gather_kernel(uint8_t *code, uint32_t *__restrict__ st, int W, int H,
+                                                           int y_lo, int y_hi, int mark_sole) {
   const size_t n = (size_t)W * H;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -63,18 +130,87 @@ __global__ void __launch_bounds__(256) deps_gather_kernel(const uint8_t *__restr
     return;
   }
   uint32_t deps = 0;
+  size_t donor = 0;
+  int donor_code = 0;
 #pragma unroll
   for (int k = 1; k <= 8; k++) {
     const int nx = x + d8dx(k), ny = y + d8dy(k);
     if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
     const int cn = code[(size_t)ny * W + nx];
-    if (cn == 0 || cn == kCodeNoData) continue;
+    if ((cn & 15) == 0 || cn == kCodeNoData) continue;
     const int inv = d8_inverse(k);  // direction from that neighbour to me
     const int first = cn & 15;
-    if (first == inv) deps++;
-    else if ((cn & kCodeTwo) && nwrap(first + 1) == inv) deps++;
+    bool hit = first == inv;
+    if (!hit && (cn & kCodeTwo) && nwrap(first + 1) == inv) hit = true;
+    if (hit) {
+      deps++;
+      donor = (size_t)ny * W + nx;
+      donor_code = cn;
+    }
   }
   st[i] = deps | (deps == 0 ? kSrcFlag : 0u);
+  // A single-receiver donor that is my only donor may add to me without atomics (nobody else
+  // touches my accumulator before I am processed): tell it so.  Only this thread writes that bit
+  // of that byte; concurrent readers mask it off.
+  if (mark_sole && deps == 1 && !(donor_code & kCodeTwo)) code[donor] = (uint8_t)(donor_code | kCodeSole);
+}
+
+// 4 cells per thread version of deps_gather_kernel for W % 4 == 0: the three code rows are read as
+// 32-bit words (+ one byte on each side) and the four state words leave as one uint4 store.
+__global__ void __launch_bounds__(256) deps_gather_x4_kernel(uint8_t *code, uint32_t *__restrict__ st, int W, int H,
+                                                              int y_lo, int y_hi, int mark_sole) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x4 >= W) return;
+  for (int y = blockIdx.y; y < H; y += gridDim.y) {
+    const size_t i0 = (size_t)y * W + x4;
+    uint8_t r[3][6];  // rows y-1..y+1, columns x4-1..x4+4 ; 0 = "no flow" for anything off the raster
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int yy = y + j - 1;
+      if (yy < 0 || yy >= H) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) r[j][k] = 0;
+      } else {
+        const uint8_t *row = code + (size_t)yy * W + x4;
+        const uchar4 m = *reinterpret_cast<const uchar4 *>(row);
+        r[j][1] = m.x; r[j][2] = m.y; r[j][3] = m.z; r[j][4] = m.w;
+        r[j][0] = x4 > 0 ? row[-1] : (uint8_t)0;
+        r[j][5] = x4 + 4 < W ? row[4] : (uint8_t)0;
+      }
+    }
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int cc = r[1][k + 1];
+      if (cc == kCodeNoData || y < y_lo || y >= y_hi) {
+        out[k] = 0;
+        continue;
+      }
+      // neighbour n = 1..8 : W, NW, N, NE, E, SE, S, SW  -> (row, col) in r
+      const int nr[9] = {0, 1, 0, 0, 0, 1, 2, 2, 2};
+      const int nc[9] = {0, k, k, k + 1, k + 2, k + 2, k + 2, k + 1, k};
+      uint32_t deps = 0;
+      int dn = 0, dcode = 0;
+#pragma unroll
+      for (int n = 1; n <= 8; n++) {
+        const int cn = r[nr[n]][nc[n]];
+        if ((cn & 15) == 0 || cn == kCodeNoData) continue;
+        const int inv = d8_inverse(n);
+        const int first = cn & 15;
+        bool hit = first == inv;
+        if (!hit && (cn & kCodeTwo) && nwrap(first + 1) == inv) hit = true;
+        if (hit) {
+          deps++;
+          dn = n;
+          dcode = cn;
+        }
+      }
+      out[k] = deps | (deps == 0 ? kSrcFlag : 0u);
+      if (mark_sole && deps == 1 && !(dcode & kCodeTwo))
+        code[(size_t)(y + d8dy(dn)) * W + (x4 + k + d8dx(dn))] = (uint8_t)(dcode | kCodeSole);
+    }
+    *reinterpret_cast<uint4 *>(st + i0) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
 }
 
 // ---- proportions path: scatter dependency counts, then mark sources ----------------------------
@@ -163,8 +299,10 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
   for (;;) {
     int next = -1;
     if (MODE == 0) {
-      const int cd = a.code[c];
-      if (cd == 0 || cd == kCodeNoData) break;
+      const int cdraw = a.code[c];
+      if (cdraw == kCodeNoData) break;
+      const int cd = cdraw & 15;
+      if (cd == 0) break;
       const int dx = d8dx(cd), dy = d8dy(cd);
       if (CHECK) {  // direction grids may point off the raster (d8_methods.hpp:121-122)
         const int y = c / W, x = c - y * W;
@@ -172,6 +310,14 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
         if (nx < 0 || ny < 0 || nx >= W || ny >= a.H) break;
       }
       const int r = c + dy * W + dx;
+      if (cdraw & kCodeSole) {
+        // I am the receiver's only donor: no other thread touches accum[r] before I hand it on
+        const A sum = ld_acc(a.accum + r) + acc;
+        a.accum[r] = sum;
+        acc = sum;
+        c = r;
+        continue;
+      }
       if (a.code[r] == kCodeNoData) break;  // flow into NoData is dropped
       if (BAND && park_in_ghost(a, r, acc)) break;
       atomicAdd(a.accum + r, acc);
@@ -180,7 +326,7 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
       if ((old & kDepsMask) == 1u) next = r;
     } else if (MODE == 1) {
       const int cd = a.code[c];
-      if (cd == 0 || cd == kCodeNoData) break;
+      if (cd == kCodeNoData || (cd & 15) == 0) break;
       const int n1 = cd & 15;
       const int r1 = c + d8dy(n1) * W + d8dx(n1);
       int r2 = -1;
@@ -245,7 +391,8 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
       }
     }
     if (next < 0) break;
-    __threadfence();
+    // the atomicSub that returned 1 was performed after every other donor's (fenced) add, and this
+    // L2 load is issued after it returned: it observes the complete sum
     c = next;
     acc = ld_acc(a.accum + c);
   }
@@ -318,10 +465,18 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
   const unsigned blocks = (unsigned)((n + 255) / 256);
   if (dinf)
     flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, ones ? 1 : 0);
-  else
+  else if ((w & 3) == 0 && ((uintptr_t)d_dem & 15) == 0 && ((uintptr_t)d_accum & 15) == 0) {
+    dim3 blk(256), grd((w / 4 + 255) / 256, h < 8192 ? h : 8192);
+    flow_code_d8_x4_kernel<<<grd, blk, 0, c.stream>>>(d_dem, code.p, d_accum, w, h, nodata, ones ? 1 : 0);
+  } else
     flow_code_kernel<false><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, nullptr, d_accum, w, h, nodata, ones ? 1 : 0);
   RDB_CK(cudaGetLastError());
-  deps_gather_kernel<<<blocks, 256, 0, c.stream>>>(code.p, st.p, w, h, 0, h);
+  if ((w & 3) == 0) {
+    dim3 blk(256), grd((w / 4 + 255) / 256, h < 8192 ? h : 8192);
+    deps_gather_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, st.p, w, h, 0, h, dinf ? 0 : 1);
+  } else {
+    deps_gather_kernel<<<blocks, 256, 0, c.stream>>>(code.p, st.p, w, h, 0, h, dinf ? 0 : 1);
+  }
   RDB_CK(cudaGetLastError());
   count_launch(2);
   WalkArgs<double> a;
@@ -367,7 +522,7 @@ void d8_flow_accum_dev(const uint8_t *d_dirs, int32_t *d_area, int w, int h) {
   const unsigned blocks = (unsigned)((n + 255) / 256);
   sanitize_dirs_kernel<<<blocks, 256, 0, c.stream>>>(d_dirs, code.p, n);
   area_init_kernel<<<blocks, 256, 0, c.stream>>>(d_dirs, d_area, n);
-  deps_gather_kernel<<<blocks, 256, 0, c.stream>>>(code.p, st.p, w, h, 0, h);
+  deps_gather_kernel<<<blocks, 256, 0, c.stream>>>(code.p, st.p, w, h, 0, h, 1);
   RDB_CK(cudaGetLastError());
   count_launch(3);
   WalkArgs<int32_t> a;
@@ -519,7 +674,7 @@ struct FaccState {
     a.next_count = cnt.p + 1;
     if (!prepared) {
       const unsigned blocks = (unsigned)((n() + 255) / 256);
-      deps_gather_kernel<<<blocks, 256, 0, c.stream>>>(code.p, st.p, W, H, gt, H - gb);
+      deps_gather_kernel<<<blocks, 256, 0, c.stream>>>(code.p, st.p, W, H, gt, H - gb, dinf ? 0 : 1);
       RDB_CK(cudaGetLastError());
       count_launch();
       prepared = true;

@@ -595,6 +595,17 @@ __global__ void fill_i32_kernel(int *p, int v, int n) {
   if (i < n) p[i] = v;
 }
 
+// W % 4 == 0 version: 16-byte loads and stores (padded rows start 16-byte aligned at column PADL)
+__global__ void __launch_bounds__(256) fill_finish_x4_kernel(const float *__restrict__ Wp, float *__restrict__ out, int W,
+                                                              int H, int pitch) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x4 >= W) return;
+  for (int y = blockIdx.y; y < H; y += gridDim.y) {
+    const float4 v = __ldcs(reinterpret_cast<const float4 *>(Wp + (size_t)(y + 1) * pitch + x4 + PADL));
+    __stcs(reinterpret_cast<float4 *>(out + (size_t)y * W + x4), v);
+  }
+}
+
 __global__ void fill_finish_kernel(const float *__restrict__ Wp, float *__restrict__ out, int W, int H,
                                    int pitch) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -882,8 +893,13 @@ struct FillState {
 
   void finish(float *d_out) {
     Ctx &c = ctx();
-    dim3 blk(256), grd((W + 255) / 256, H < 32768 ? H : 32768);
-    fill_finish_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, d_out, W, H, pitch);
+    if ((W & 3) == 0 && ((uintptr_t)d_out & 15) == 0) {
+      dim3 blk(256), grd((W / 4 + 255) / 256, H < 4096 ? H : 4096);
+      fill_finish_x4_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, d_out, W, H, pitch);
+    } else {
+      dim3 blk(256), grd((W + 255) / 256, H < 32768 ? H : 32768);
+      fill_finish_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, d_out, W, H, pitch);
+    }
     RDB_CK(cudaGetLastError());
     count_launch();
   }

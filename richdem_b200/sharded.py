@@ -128,13 +128,22 @@ def exchange_rows(local: "torch.Tensor", g_top: int, g_bot: int, group=None) -> 
 
 
 def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None, group=None,
-              max_rounds: int = 100000, return_stats: bool = False):
+              max_rounds: int = 100000, return_stats: bool = False, band_rounds: Optional[int] = None):
     """Fill this rank's band.  ``local_dem`` is (g_top + owned + g_bot) x W with the ghost rows'
     contents ignored (they are initialised to +inf).  Returns (filled local raster incl. ghost rows,
     number of exchange rounds).  Collective: every rank of ``group`` must call it."""
-    solver_cls = solver_cls or CudaBandSolver
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if solver_cls is None:
+        solver_cls = CudaBandSolver
+        # halos are exchanged every `band_rounds` sweep rounds instead of after full local convergence,
+        # so the flood enters a band from its neighbours when it arrives there rather than after the
+        # band has been flooded once from its own raster edges
+        import os
+        from . import _lib
+        if band_rounds is None:
+            band_rounds = int(os.environ.get("RDB_BAND_ROUNDS", "32")) if world > 1 else 0
+        _lib.set_param("fill_band_rounds", band_rounds)
     h, w = local_dem.shape
     if g_top:
         local_dem[0].fill_(float("inf"))
