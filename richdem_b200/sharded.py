@@ -164,14 +164,12 @@ def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None
             my_change = 1
         if g_bot and (changed & 2 or rounds == 1):
             my_change = 1
-        if changed & 4:
-            my_change |= 2
-        flag = torch.tensor([my_change], dtype=torch.int32, device=local_dem.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.BOR, group=group)
-        gflag = int(flag.item())
-        if gflag == 0:
+        flag = torch.tensor([my_change, 1 if (changed & 4) else 0], dtype=torch.int32, device=local_dem.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)  # (NCCL has no bitwise-or reduction)
+        any_edge, any_active = (int(v) for v in flag.tolist())
+        if not any_edge and not any_active:
             break
-        if not (gflag & 1):
+        if not any_edge:
             continue  # someone is still relaxing but no edge row moved: nothing to exchange
         send_up = solver.read_row(1) if g_top else None
         send_dn = solver.read_row(h - 2) if g_bot else None
