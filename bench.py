@@ -285,6 +285,28 @@ def run_b200(args):
                    "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                    "note": "per-rank pinned host band -> sharded fill + FA_D8 -> pinned host band"}
 
+    # ---- the other stages of the path, timed once outside the headline region (N=1) ----
+    other = None
+    if world == 1 and not args.no_other_stages:
+        other = {}
+        work.copy_(dem0)
+        _lib.check(L.rdb200_dev_fill_depressions_d8_f32(work.data_ptr(), W, hloc))
+        _lib.check(L.rdb200_dev_resolve_flats_epsilon_f32(work.data_ptr(), W, hloc, ND))
+        s = _lib.stats()
+        other["resolve_flats_ms"] = s["ms_total"]
+        other["resolve_flats_bfs_levels"] = s["flat_bfs_levels"]
+        other["resolve_flats_cells_raised"] = s["flat_cells_raised"]
+        _lib.check(L.rdb200_dev_fa_d8_f32_f64(work.data_ptr(), acc.data_ptr(), W, hloc, ND, 1))
+        other["fa_d8_after_flats_ms"] = _lib.stats()["ms_total"]
+        _lib.check(L.rdb200_dev_fa_tarboton_f32_f64(work.data_ptr(), acc.data_ptr(), W, hloc, ND, 1))
+        s = _lib.stats()
+        other["fa_dinf_after_flats_ms"] = s["ms_total"]
+        other["fa_dinf_frontier_rounds"] = s["accum_rounds"]
+        dirs = torch.empty((hloc, W), dtype=torch.uint8, device="cuda")
+        _lib.check(L.rdb200_dev_d8_flow_directions_f32(work.data_ptr(), dirs.data_ptr(), W, hloc, ND))
+        other["d8_flow_directions_ms"] = _lib.stats()["ms_total"]
+        del dirs
+
     if world > 1:
         tot = torch.tensor([agg["launches"], agg["visits"], agg["sweep_ms"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -336,6 +358,7 @@ def run_b200(args):
         if world == 1 else {"fill_rank0_wall": agg["fill_ms"] / args.steps, "fa_d8_rank0_wall": agg["acc_ms"] / args.steps,
                             "fill_exchange_rounds": agg.get("fill_xr", 0) / args.steps,
                             "fa_exchange_rounds": agg.get("acc_xr", 0) / args.steps},
+        "other_stages_once": other,
         "roofline": roofline,
         "cpu_baseline": cb,
         "e2e": e2e,
@@ -358,6 +381,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-stages", action="store_true")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per sweep launch from the committed ncu capture (profiles/)")
     args = ap.parse_args()

@@ -13,6 +13,9 @@
 // independent of the order in which atomics land (bit-identical to the serial reference).
 #include "flowmet.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace rdb {
 
 namespace {
@@ -296,6 +299,11 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
   }
   const int W = a.W;
   A acc = ld_acc(a.accum + c);
+  // receivers that become ready while this walker already has a successor wait on a small private
+  // stack (depth-first, same launch); only what does not fit goes to the global frontier array
+  constexpr int STK = 1;  // (kept for the row-band path; the single-GPU multi-receiver path uses accum_levels_kernel)
+  int stk[STK];
+  int sp = 0;
   for (;;) {
     int next = -1;
     if (MODE == 0) {
@@ -326,7 +334,7 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
       if ((old & kDepsMask) == 1u) next = r;
     } else if (MODE == 1) {
       const int cd = a.code[c];
-      if (cd == kCodeNoData || (cd & 15) == 0) break;
+      if (cd == kCodeNoData || (cd & 15) == 0) goto no_receiver;
       const int n1 = cd & 15;
       const int r1 = c + d8dy(n1) * W + d8dx(n1);
       int r2 = -1;
@@ -353,11 +361,12 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
           const uint32_t o2 = atomicSub(a.st + r2, 1u);
           if ((o2 & kDepsMask) == 1u) {
             if (next < 0) next = r2;
+            else if (sp < STK) stk[sp++] = r2;
             else a.next_frontier[atomicAdd(a.next_count, 1)] = r2;
           }
         }
       } else {
-        if (BAND && park_in_ghost(a, r1, acc)) break;
+        if (BAND && park_in_ghost(a, r1, acc)) goto no_receiver;
         atomicAdd(a.accum + r1, acc);
         __threadfence();
         const uint32_t o1 = atomicSub(a.st + r1, 1u);
@@ -365,7 +374,7 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
       }
     } else {
       const int y = c / W, x = c - y * W;
-      if (x == 0 || y == 0 || x == W - 1 || y == a.H - 1) break;  // edge cells carry no flow
+      if (x == 0 || y == 0 || x == W - 1 || y == a.H - 1) goto no_receiver;  // edge cells carry no flow
       const float *p = a.props + (size_t)9 * c;
       uint32_t sent = 0;
 #pragma unroll
@@ -377,7 +386,7 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
         atomicAdd(a.accum + r, (A)((double)pk * (double)acc));
         sent |= 1u << k;
       }
-      if (!sent) break;
+      if (!sent) goto no_receiver;
       __threadfence();
 #pragma unroll
       for (int k = 1; k <= 8; k++) {
@@ -386,16 +395,149 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
         const uint32_t o = atomicSub(a.st + r, 1u);
         if ((o & kDepsMask) == 1u) {
           if (next < 0) next = r;
+          else if (sp < STK) stk[sp++] = r;
           else a.next_frontier[atomicAdd(a.next_count, 1)] = r;
         }
       }
     }
-    if (next < 0) break;
+  no_receiver:
+    if (next < 0) {
+      if (MODE != 0 && sp > 0) next = stk[--sp];
+      else break;
+    }
     // the atomicSub that returned 1 was performed after every other donor's (fenced) add, and this
     // L2 load is issued after it returned: it observes the complete sum
     c = next;
     acc = ld_acc(a.accum + c);
   }
+}
+
+// Multi-receiver graphs (D-infinity: <= 2 receivers, proportions: <= 8): ONE cooperative launch.
+// Level L drains the frontier written by level L-1 (level 0: every source); a thread processes a
+// ready cell and keeps following the receiver it completed for at most `budget` steps, so long
+// single-file reaches cost no extra levels, while every other cell it completes -- and its own
+// continuation when the budget runs out -- is appended (coalesced-group atomics) to the next
+// frontier, where other threads pick it up in parallel.  Levels meet at grid.sync().
+template <int MODE>
+__global__ void __launch_bounds__(256) accum_levels_kernel(const WalkArgs<double> a, int *q0, int *q1, int *counts,
+                                                            int ncells, int budget, int *levels_out) {
+  cg::grid_group grid = cg::this_grid();
+  const int W = a.W;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  int level = 0;
+  for (;; level++) {
+    const int n = level == 0 ? ncells : *reinterpret_cast<volatile int *>(&counts[level % 3]);
+    if (n == 0) break;
+    if (gtid == 0) counts[(level + 2) % 3] = 0;
+    const int *qc = (level & 1) ? q1 : q0;
+    int *qn = (level & 1) ? q0 : q1;
+    int *cntn = &counts[(level + 1) % 3];
+    auto push = [&](int r) {
+      cg::coalesced_group g = cg::coalesced_threads();
+      int base = 0;
+      if (g.thread_rank() == 0) base = atomicAdd(cntn, (int)g.size());
+      base = g.shfl(base, 0);
+      qn[base + g.thread_rank()] = r;
+    };
+    for (int idx = gtid; idx < n; idx += gsize) {
+      int c;
+      if (level == 0) {
+        c = idx;
+        if (!(a.st[c] & kSrcFlag)) continue;
+      } else {
+        c = __ldcg(qc + idx);
+      }
+      double acc = __ldcg(a.accum + c);
+      for (int step = 0;; step++) {
+        int next = -1;
+        if (MODE == 1) {
+          const int cd = a.code[c];
+          if (cd != kCodeNoData && (cd & 15) != 0) {
+            const int n1 = cd & 15;
+            const int r1 = c + d8dy(n1) * W + d8dx(n1);
+            if (cd & kCodeTwo) {
+              const int n2 = nwrap(n1 + 1);
+              const int r2 = c + d8dy(n2) * W + d8dx(n2);
+              float p1, p2;
+              tarboton_props(a.rmaxArr[c], &p1, &p2);
+              // generic.hpp:87  accum(ni) += props(ci,n)*c_accum  (float * double)
+              if (p1 > 0) atomicAdd(a.accum + r1, (double)p1 * acc);
+              if (p2 > 0) atomicAdd(a.accum + r2, (double)p2 * acc);
+              __threadfence();
+              if (p1 > 0 && (atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
+              if (p2 > 0 && (atomicSub(a.st + r2, 1u) & kDepsMask) == 1u) {
+                if (next < 0) next = r2;
+                else push(r2);
+              }
+            } else {
+              atomicAdd(a.accum + r1, acc);
+              __threadfence();
+              if ((atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
+            }
+          }
+        } else {
+          const int y = c / W, x = c - y * W;
+          if (!(x == 0 || y == 0 || x == W - 1 || y == a.H - 1)) {  // edge cells carry no flow
+            const float *p = a.props + (size_t)9 * c;
+            uint32_t sent = 0;
+#pragma unroll
+            for (int k = 1; k <= 8; k++) {
+              const float pk = p[k];
+              if (pk <= 0) continue;  // generic.hpp:82-83
+              const int r = c + d8dy(k) * W + d8dx(k);
+              if (a.props[(size_t)9 * r] == kNoDataGen) continue;  // :85-86
+              atomicAdd(a.accum + r, (double)pk * acc);
+              sent |= 1u << k;
+            }
+            if (sent) {
+              __threadfence();
+#pragma unroll
+              for (int k = 1; k <= 8; k++) {
+                if (!(sent & (1u << k))) continue;
+                const int r = c + d8dy(k) * W + d8dx(k);
+                if ((atomicSub(a.st + r, 1u) & kDepsMask) == 1u) {
+                  if (next < 0) next = r;
+                  else push(r);
+                }
+              }
+            }
+          }
+        }
+        if (next < 0) break;
+        if (step + 1 >= budget) {  // hand the continuation to the next level
+          push(next);
+          break;
+        }
+        c = next;
+        acc = __ldcg(a.accum + c);
+      }
+    }
+    grid.sync();
+  }
+  if (gtid == 0) *levels_out = level;
+}
+
+template <int MODE>
+void run_levels(WalkArgs<double> a, size_t ncells) {
+  Ctx &c = ctx();
+  DevBuf<int> fr0(ncells), fr1(ncells), cnt(4);
+  RDB_CK(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(int), c.stream));
+  int per_sm = 0;
+  RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_levels_kernel<MODE>, 256, 0));
+  if (per_sm < 1) per_sm = 1;
+  const int grid = c.num_sms * per_sm;
+  int *q0 = fr0.p, *q1 = fr1.p, *counts = cnt.p, *lv = cnt.p + 3;
+  int nc = (int)ncells, budget = (int)(c.params.accum_budget > 0 ? c.params.accum_budget : 128);
+  void *args[] = {(void *)&a, (void *)&q0, (void *)&q1, (void *)&counts, (void *)&nc, (void *)&budget, (void *)&lv};
+  KernelTimer kt;
+  RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_levels_kernel<MODE>, dim3(grid), dim3(256), args, 0, c.stream));
+  count_launch();
+  kt.stop_async();
+  int *h = (int *)c.pinned;
+  RDB_CK(cudaMemcpyAsync(h, lv, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  c.stats.ms_main_kernel += kt.ms();
+  c.stats.accum_rounds = *h;
 }
 
 template <int MODE, bool CHECK, class A>
@@ -487,7 +629,7 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
   a.st = st.p;
   a.W = w;
   a.H = h;
-  if (dinf) run_walk<1, false, double>(a, n);
+  if (dinf) run_levels<1>(a, n);
   else run_walk<0, false, double>(a, n);
 }
 
@@ -510,7 +652,7 @@ void flow_accumulation_props_dev(const float *d_props, double *d_accum, int w, i
   a.st = st.p;
   a.W = w;
   a.H = h;
-  run_walk<2, false, double>(a, n);
+  run_levels<2>(a, n);
 }
 
 // d8_flow_accum(dirs, area) (reference methods/d8_methods.hpp:47-139)

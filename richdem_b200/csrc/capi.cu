@@ -34,7 +34,9 @@ static void init_device(int device) {
          prop.minor);
   c.device = device;
   c.num_sms = prop.multiProcessorCount;
-  RDB_CK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+  // a *blocking* stream: it orders itself with the legacy default stream, so callers that prepare
+  // device buffers there (cudaMemcpy, PyTorch's default stream, ...) need no explicit events
+  RDB_CK(cudaStreamCreate(&c.own_stream));
   c.stream = c.own_stream;
   RDB_CK(cudaEventCreate(&c.ev0));
   RDB_CK(cudaEventCreate(&c.ev1));
@@ -231,6 +233,7 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "fill_order_rounds") p.fill_order_rounds = value;
   else if (n == "fill_band_rounds") p.fill_band_rounds = value;
   else if (n == "accum_threads") p.accum_threads = value > 0 ? value : 256;
+  else if (n == "accum_budget") p.accum_budget = value;
   else fail("rdb200_set_param: unknown parameter '%s'", name);
   CAPI_END
 }

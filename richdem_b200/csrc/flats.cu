@@ -19,6 +19,12 @@
 // frontier length from device memory, so the host only synchronises every few levels.
 #include "common.cuh"
 
+#include <chrono>
+#include <cstdlib>
+
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace rdb {
 
 namespace {
@@ -32,6 +38,7 @@ struct LevelCtl {
 struct FlatDev {
   LevelCtl ctl[3];
   int n_low, n_high, n_flat, n_raised;
+  int rounds_done;
 };
 
 // a3: FindFlats
@@ -160,19 +167,33 @@ __global__ void __launch_bounds__(256) uf_roots_kernel(const uint8_t *__restrict
   if (ft[i] & FT_LOW) rootflag[r] = 1;
 }
 
+// append `item` for the lanes where `pred` holds: one atomicAdd per warp instead of one per lane
+__device__ __forceinline__ void warp_append(bool pred, int item, int *queue, int *count) {
+  const unsigned bal = __ballot_sync(0xffffffffu, pred);
+  if (!bal) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == (__ffs(bal) - 1)) base = atomicAdd(count, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+  if (pred) queue[base + __popc(bal & ((1u << lane) - 1u))] = item;
+}
+
 // ---- BFS ---------------------------------------------------------------------------------------
 template <bool AWAY>
 __global__ void __launch_bounds__(256) bfs_seed_kernel(const uint8_t *__restrict__ ft, const int *__restrict__ labels,
                                                         int *dist, int *H, int *queue, FlatDev *dev, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint8_t f = ft[i];
-  const bool src = AWAY ? ((f & FT_HIGH) && labels[i] != 0)  // Barnes2014.hpp:445-454
-                        : ((f & FT_LOW) != 0);
-  if (!src) return;
-  dist[i] = 1;
-  if (AWAY) atomicMax(&H[labels[i] - 1], 1);
-  queue[atomicAdd(&dev->ctl[0].count, 1)] = (int)i;
+  bool src = false;
+  if (i < n) {
+    const uint8_t f = ft[i];
+    src = AWAY ? ((f & FT_HIGH) && labels[i] != 0)  // Barnes2014.hpp:445-454
+               : ((f & FT_LOW) != 0);
+    if (src) {
+      dist[i] = 1;
+      if (AWAY && H[labels[i] - 1] < 1) atomicMax(&H[labels[i] - 1], 1);
+    }
+  }
+  warp_append(src, (int)i, queue, &dev->ctl[0].count);
 }
 
 template <bool AWAY>
@@ -205,6 +226,54 @@ __global__ void __launch_bounds__(256) bfs_level_kernel(const uint8_t *__restric
       }
     }
   }
+}
+
+// All BFS levels in ONE cooperative launch: the grid walks the frontier of a level, appends the
+// next one (warp-aggregated), and meets at a grid-wide barrier; no host round trip per level.
+template <bool AWAY>
+__global__ void __launch_bounds__(256) bfs_persistent_kernel(const uint8_t *__restrict__ ft,
+                                                              const int *__restrict__ labels, int *dist, int *H, int *q0,
+                                                              int *q1, FlatDev *dev, int W, int Hh) {
+  cg::grid_group grid = cg::this_grid();
+  int round = 0;
+  for (;; round++) {
+    LevelCtl *cur = &dev->ctl[round % 3];
+    LevelCtl *next = &dev->ctl[(round + 1) % 3];
+    const int n = *reinterpret_cast<volatile int *>(&cur->count);
+    if (n == 0) break;  // every block reads the same, final value (written before the last grid.sync)
+    if (blockIdx.x == 0 && threadIdx.x == 0) dev->ctl[(round + 2) % 3].count = 0;
+    const int *qc = (round & 1) ? q1 : q0;
+    int *qn = (round & 1) ? q0 : q1;
+    const int level = round + 1;  // distance value of the cells in the current frontier
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+      const int idx = base + threadIdx.x;
+      const bool valid = idx < n;
+      int c = 0, lab = 0, x = 0, y = 0;
+      if (valid) {
+        c = __ldcg(qc + idx);  // written by other SMs in the previous level: bypass L1
+        lab = labels[c];
+        y = c / W;
+        x = c - y * W;
+      }
+      int hmax = 0;
+#pragma unroll
+      for (int k = 1; k <= 8; k++) {
+        const int nx = x + d8dx(k), ny = y + d8dy(k);
+        bool won = false;
+        int ni = 0;
+        if (valid && nx >= 0 && ny >= 0 && nx < W && ny < Hh) {
+          ni = ny * W + nx;
+          if ((ft[ni] & FT_FLAT) && labels[ni] == lab && __ldcg(dist + ni) == 0)  // :98-104 / :196-206
+            won = atomicCAS(&dist[ni], 0, level + 1) == 0;
+        }
+        if (won) hmax = level + 1;
+        warp_append(won, ni, qn, &next->count);
+      }
+      if (AWAY && hmax && H[lab - 1] < hmax) atomicMax(&H[lab - 1], hmax);  // flat_height = deepest level, :94
+    }
+    grid.sync();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) dev->rounds_done = round;
 }
 
 __device__ __forceinline__ float advance_ulps(float z, int k) {
@@ -278,20 +347,19 @@ int run_bfs(const uint8_t *ft, const int *labels, int *dist, int *H, int *q0, in
   RDB_CK(cudaGetLastError());
   count_launch();
   FlatDev *hd = (FlatDev *)c.pinned;
-  const int grid = c.num_sms * 4;
-  int round = 0;
-  const int per_sync = 32;
-  for (;;) {
-    for (int k = 0; k < per_sync; k++) {
-      bfs_level_kernel<AWAY><<<grid, 256, 0, c.stream>>>(ft, labels, dist, H, q0, q1, dev, round, w, h);
-      round++;
-    }
-    RDB_CK(cudaGetLastError());
-    count_launch(per_sync);
-    RDB_CK(cudaMemcpyAsync(hd, dev, sizeof(FlatDev), cudaMemcpyDeviceToHost, c.stream));
-    RDB_CK(cudaStreamSynchronize(c.stream));
-    if (hd->ctl[round % 3].count == 0) break;
-  }
+  int per_sm = 0;
+  RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bfs_persistent_kernel<AWAY>, 256, 0));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  const int grid = c.num_sms * per_sm;
+  int wi = w, hi = h;
+  void *args[] = {(void *)&ft, (void *)&labels, (void *)&dist, (void *)&H, (void *)&q0, (void *)&q1, (void *)&dev,
+                  (void *)&wi, (void *)&hi};
+  RDB_CK(cudaLaunchCooperativeKernel((const void *)bfs_persistent_kernel<AWAY>, dim3(grid), dim3(256), args, 0, c.stream));
+  count_launch();
+  RDB_CK(cudaMemcpyAsync(hd, dev, sizeof(FlatDev), cudaMemcpyDeviceToHost, c.stream));
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  const int round = hd->rounds_done;
   return round;
 }
 
@@ -304,6 +372,15 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   const size_t n = (size_t)w * h;
   c.stats.cells = (int64_t)n;
   const unsigned blocks = (unsigned)((n + 255) / 256);
+  const bool prof = getenv("RDB200_PROFILE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!prof) return;
+    cudaStreamSynchronize(c.stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[flats profile] %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   DevBuf<uint8_t> ft(n);
   DevBuf<FlatDev> dev(1);
   RDB_CK(cudaMemsetAsync(dev.p, 0, sizeof(FlatDev), c.stream));
@@ -315,6 +392,7 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   RDB_CK(cudaMemcpyAsync(hd, dev.p, sizeof(FlatDev), cudaMemcpyDeviceToHost, c.stream));
   RDB_CK(cudaStreamSynchronize(c.stream));
   const int n_low = hd->n_low, n_flat = hd->n_flat;
+  lap("classify+edges");
   if (n_low == 0) {  // Barnes2014.hpp:429-435: nothing to resolve
     if (d_mask_out) RDB_CK(cudaMemsetAsync(d_mask_out, 0, n * sizeof(int32_t), c.stream));
     if (d_labels_out) RDB_CK(cudaMemsetAsync(d_labels_out, 0, n * sizeof(int32_t), c.stream));
@@ -327,12 +405,15 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   DevBuf<uint8_t> rootflag(n);
   RDB_CK(cudaMemsetAsync(rootflag.p, 0, n, c.stream));
   uf_init_kernel<<<blocks, 256, 0, c.stream>>>(parent.p, n);
+  lap("uf init");
   uf_union_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, parent.p, w, h);
+  lap("uf union");
   uf_roots_kernel<<<blocks, 256, 0, c.stream>>>(ft.p, parent.p, labels.p, rootflag.p, n);
   make_labels_kernel<<<blocks, 256, 0, c.stream>>>(rootflag.p, ft.p, labels.p, n);
   RDB_CK(cudaGetLastError());
   count_launch(4);
 
+  lap("roots+labels");
   // gradients
   DevBuf<int> away(n), tw(n), Hh(n);
   const size_t qcap = (size_t)n_flat + (size_t)n_low + 16;
@@ -340,7 +421,9 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   RDB_CK(cudaMemsetAsync(Hh.p, 0, n * sizeof(int), c.stream));
   int levels = 0;
   levels += run_bfs<true>(ft.p, labels.p, away.p, Hh.p, q0.p, q1.p, dev.p, w, h);
+  lap("bfs away");
   levels += run_bfs<false>(ft.p, labels.p, tw.p, Hh.p, q0.p, q1.p, dev.p, w, h);
+  lap("bfs towards");
   c.stats.flat_bfs_levels = levels;
 
   flats_apply_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, labels.p, away.p, tw.p, Hh.p, d_mask_out, d_labels_out, w, h,
@@ -350,6 +433,7 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   RDB_CK(cudaMemcpyAsync(hd, dev.p, sizeof(FlatDev), cudaMemcpyDeviceToHost, c.stream));
   RDB_CK(cudaStreamSynchronize(c.stream));
   c.stats.flat_cells_raised = hd->n_raised;
+  lap("apply");
 }
 
 }  // namespace rdb

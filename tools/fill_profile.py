@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from richdem_b200 import _lib
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-L = _lib.lib(); _lib.init(0)
+L = _lib.lib(); _lib.init(0); _lib.use_torch_stream()
 d = torch.empty((N, N), dtype=torch.float32, device="cuda")
 _lib.check(L.rdb200_dev_generate_fbm_f32(d.data_ptr(), N, N, 0, 42, 12, 0.0))
 ref = d.clone()
