@@ -527,7 +527,7 @@ void run_levels(WalkArgs<double> a, size_t ncells) {
   if (per_sm < 1) per_sm = 1;
   const int grid = c.num_sms * per_sm;
   int *q0 = fr0.p, *q1 = fr1.p, *counts = cnt.p, *lv = cnt.p + 3;
-  int nc = (int)ncells, budget = (int)(c.params.accum_budget > 0 ? c.params.accum_budget : 128);
+  int nc = (int)ncells, budget = (int)(c.params.accum_budget > 0 ? c.params.accum_budget : 4);
   void *args[] = {(void *)&a, (void *)&q0, (void *)&q1, (void *)&counts, (void *)&nc, (void *)&budget, (void *)&lv};
   KernelTimer kt;
   RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_levels_kernel<MODE>, dim3(grid), dim3(256), args, 0, c.stream));
