@@ -178,6 +178,15 @@ __device__ __forceinline__ void warp_append(bool pred, int item, int *queue, int
   if (pred) queue[base + __popc(bal & ((1u << lane) - 1u))] = item;
 }
 
+// distance array of one BFS: 0 = flat cell not reached yet, -1 = not a flat cell (never entered),
+// > 0 = level.  Two adjacent IS_A_FLAT cells always have equal elevation (neither has a lower
+// neighbour), i.e. the same label, so inside the flood the label test of the reference
+// (Barnes2014.hpp:98-104) is implied by "is a flat cell" and one 4-byte load per neighbour suffices.
+__global__ void __launch_bounds__(256) bfs_init_kernel(const uint8_t *__restrict__ ft, int *__restrict__ dist, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dist[i] = (ft[i] & FT_FLAT) ? 0 : -1;
+}
+
 // ---- BFS ---------------------------------------------------------------------------------------
 template <bool AWAY>
 __global__ void __launch_bounds__(256) bfs_seed_kernel(const uint8_t *__restrict__ ft, const int *__restrict__ labels,
@@ -194,38 +203,6 @@ __global__ void __launch_bounds__(256) bfs_seed_kernel(const uint8_t *__restrict
     }
   }
   warp_append(src, (int)i, queue, &dev->ctl[0].count);
-}
-
-template <bool AWAY>
-__global__ void __launch_bounds__(256) bfs_level_kernel(const uint8_t *__restrict__ ft, const int *__restrict__ labels,
-                                                         int *dist, int *H, int *q0, int *q1, FlatDev *dev, int round,
-                                                         int W, int Hh) {
-  LevelCtl *cur = &dev->ctl[round % 3];
-  LevelCtl *next = &dev->ctl[(round + 1) % 3];
-  const int n = cur->count;
-  if (blockIdx.x == 0 && threadIdx.x == 0) dev->ctl[(round + 2) % 3].count = 0;
-  if (n == 0) return;
-  const int *qc = (round & 1) ? q1 : q0;
-  int *qn = (round & 1) ? q0 : q1;
-  const int level = round + 1;  // distance value of the cells in the current frontier
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-    const int c = qc[idx];
-    const int lab = labels[c];
-    const int y = c / W, x = c - y * W;
-#pragma unroll
-    for (int k = 1; k <= 8; k++) {
-      const int nx = x + d8dx(k), ny = y + d8dy(k);
-      if (nx < 0 || ny < 0 || nx >= W || ny >= Hh) continue;
-      const int ni = ny * W + nx;
-      if (!(ft[ni] & FT_FLAT)) continue;   // :98-104 / :196-206
-      if (labels[ni] != lab) continue;
-      if (dist[ni] != 0) continue;
-      if (atomicCAS(&dist[ni], 0, level + 1) == 0) {
-        qn[atomicAdd(&next->count, 1)] = ni;
-        if (AWAY && H[lab - 1] < level + 1) atomicMax(&H[lab - 1], level + 1);  // flat_height = deepest level, :94
-      }
-    }
-  }
 }
 
 // All BFS levels in ONE cooperative launch: the grid walks the frontier of a level, appends the
@@ -263,7 +240,9 @@ __global__ void __launch_bounds__(256) bfs_persistent_kernel(const uint8_t *__re
         int ni = 0;
         if (valid && nx >= 0 && ny >= 0 && nx < W && ny < Hh) {
           ni = ny * W + nx;
-          if ((ft[ni] & FT_FLAT) && labels[ni] == lab && __ldcg(dist + ni) == 0)  // :98-104 / :196-206
+          // low-edge sources (first level of the towards-flood) are not flat cells themselves and may
+          // touch a lower, different flat: only they need the explicit label test (:196-206)
+          if (__ldcg(dist + ni) == 0 && (AWAY || round > 0 || labels[ni] == lab))
             won = atomicCAS(&dist[ni], 0, level + 1) == 0;
         }
         if (won) hmax = level + 1;
@@ -342,7 +321,7 @@ int run_bfs(const uint8_t *ft, const int *labels, int *dist, int *H, int *q0, in
   const size_t n = (size_t)w * h;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   RDB_CK(cudaMemsetAsync(dev->ctl, 0, sizeof(LevelCtl) * 3, c.stream));
-  RDB_CK(cudaMemsetAsync(dist, 0, n * sizeof(int), c.stream));
+  bfs_init_kernel<<<blocks, 256, 0, c.stream>>>(ft, dist, n);
   bfs_seed_kernel<AWAY><<<blocks, 256, 0, c.stream>>>(ft, labels, dist, H, q0, dev, n);
   RDB_CK(cudaGetLastError());
   count_launch();
