@@ -59,6 +59,7 @@ struct Params {
   int64_t fill_order_rounds = 0;  // rounds the level schedule spans (0: 0.8 x tiles across the raster)
   int64_t fill_band_rounds = 0;   // row-band mode: rounds per rdb200_dev_fill_run call (0: to convergence)
   int64_t fill_profile = 0;     // 1: collect + print in-tile work counters (slower)
+  int64_t flats_tiled = 1;   // flat-resolution gradients by the tile engine (0: one cooperative BFS launch each)
   int64_t accum_threads = 256;
   int64_t accum_budget = 0;  // cells one thread follows per level in the multi-receiver accumulation (0: 4)
 };
@@ -133,6 +134,7 @@ struct KernelTimer {
 
 // ---- stage entry points implemented in the .cu files (device pointers, ctx stream) -------
 void fill_depressions_dev(float *d_dem, int w, int h);
+void geodesic_distance_dev(const uint8_t *d_open, int open_bit, float *d_w_inout, int w, int h);
 void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask_out,
                        int32_t *d_labels_out, bool apply);
 void d8_flow_directions_dev(const float *d_dem, uint8_t *d_dirs, int w, int h, float nodata);

@@ -173,6 +173,10 @@ __device__ __forceinline__ void enqueue_tile(const FillArgs &a, RoundCtl *next, 
 
 __device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
 
+// STEP = 0: depression filling,     new = min(W, max(Z, min8 W))
+// STEP = 1: geodesic distance,      new = min(W, max(Z, 1 + min8 W))   with Z = 0 on cells the flood
+//           may enter and +inf elsewhere (used for the flat-resolution gradients, csrc/flats.cu)
+template <int STEP>
 __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     fill_sweep_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ,
                       const FillArgs a) {
@@ -329,8 +333,8 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
             const float zz = z[j - 1][i2 - 1];
             const float others = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
                                        min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]), v[j][i2 + 1]);
-            const float b0 = fminf(v[j][i2], fmaxf(zz, others));
-            const float nw = fminf(b0, fmaxf(zz, v[j][i2 - 1]));  // v[j][i2-1] was updated one step ago
+            const float b0 = fminf(v[j][i2], fmaxf(zz, STEP ? others + 1.0f : others));
+            const float nw = fminf(b0, fmaxf(zz, STEP ? v[j][i2 - 1] + 1.0f : v[j][i2 - 1]));  // updated one step ago
             if (nw < v[j][i2]) ch |= 1u << ((j - 1) * 4 + (i2 - 1));
             v[j][i2] = nw;
           }
@@ -342,8 +346,8 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
             const float zz = z[j - 1][i2 - 1];
             const float others = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
                                        min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]), v[j][i2 - 1]);
-            const float b0 = fminf(v[j][i2], fmaxf(zz, others));
-            const float nw = fminf(b0, fmaxf(zz, v[j][i2 + 1]));  // v[j][i2+1] was updated one step ago
+            const float b0 = fminf(v[j][i2], fmaxf(zz, STEP ? others + 1.0f : others));
+            const float nw = fminf(b0, fmaxf(zz, STEP ? v[j][i2 + 1] + 1.0f : v[j][i2 + 1]));  // updated one step ago
             if (nw < v[j][i2]) ch |= 1u << ((j - 1) * 4 + (i2 - 1));
             v[j][i2] = nw;
           }
@@ -590,6 +594,27 @@ __global__ void __launch_bounds__(256) fill_hist_kernel(const float *__restrict_
     if (sh[k]) atomicAdd(&hist[k], sh[k]);
 }
 
+// distance mode: padded Z = 0 where `open[i]` has bit `open_bit` (cells the flood may enter), +inf
+// elsewhere; padded W = winit (compact float array: +inf, or the seed distance)
+__global__ void __launch_bounds__(128) dist_pad_init_kernel(const uint8_t *__restrict__ open, int open_bit,
+                                                             const float *__restrict__ winit, float *__restrict__ Zp,
+                                                             float *__restrict__ Wp, int W, int H, int pitch, int rows) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= pitch) return;
+  const float inf = __int_as_float(0x7f800000);
+  for (int py = blockIdx.y; py < rows; py += gridDim.y) {
+    const int x = px - PADL, y = py - 1;
+    float zz = inf, ww = inf;
+    if (x >= 0 && x < W && y >= 0 && y < H) {
+      const size_t i = (size_t)y * W + x;
+      if (open[i] & open_bit) zz = 0.0f;
+      ww = winit[i];
+    }
+    Zp[(size_t)py * pitch + px] = zz;
+    Wp[(size_t)py * pitch + px] = ww;
+  }
+}
+
 __global__ void fill_i32_kernel(int *p, int v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -653,6 +678,7 @@ struct FillState {
   float zmin = 0.f, zmax = 0.f;
   bool first_run = true;
   bool ordered = false;
+  int step_mode = 0;  // 0: fill, 1: geodesic distance
   std::vector<float> levels;
   DevBuf<FillDev> dev;
   CUtensorMap mapW, mapZ;
@@ -743,7 +769,7 @@ struct FillState {
     mapW = make_map(Wp.p, pitch, rows, SP, SROWS);
     mapZ = make_map(Zp.p, pitch, rows, TX, TY);
     int per_sm = 0;
-    RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_sweep_kernel, FILL_THREADS, 0));
+    RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_sweep_kernel<0>, FILL_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     grid = c.num_sms * per_sm;
     round = 1;  // stamps start at 0, so round numbers (used as stamp values) start at 1
@@ -753,6 +779,50 @@ struct FillState {
     for (int ty = 0; ty < tilesY; ty++)
       for (int tx = 0; tx < tilesX; tx++)
         if (ty == 0 || tx == 0 || ty == tilesY - 1 || tx == tilesX - 1) init.push_back(ty * tilesX + tx);
+    seed_worklist(init);
+  }
+
+  // Geodesic-distance mode: `open` marks the cells the flood may enter (bit `open_bit`), `winit`
+  // holds +inf or the seed distance of every cell.  Every tile is seeded once.
+  void begin_dist(const uint8_t *d_open, int open_bit, const float *d_winit, int w, int h) {
+    Ctx &c = ctx();
+    step_mode = 1;
+    W = w;
+    H = h;
+    tilesX = (w + TX - 1) / TX;
+    tilesY = (h + TY - 1) / TY;
+    pitch = tilesX * TX + 2 * PADL;
+    rows = tilesY * TY + 2;
+    const size_t np = (size_t)pitch * rows;
+    Zp.alloc(np);
+    Wp.alloc(np);
+    const size_t nt = (size_t)tilesX * tilesY;
+    list0.alloc(nt);
+    list1.alloc(nt);
+    plist.alloc(nt);
+    stamp.alloc(nt);
+    sides.alloc(2 * nt);
+    keys.alloc(2 * nt);
+    dev.alloc(1);
+    RDB_CK(cudaMemsetAsync(stamp.p, 0, nt * sizeof(int), c.stream));
+    RDB_CK(cudaMemsetAsync(sides.p, 0, 2 * nt * sizeof(int), c.stream));
+    RDB_CK(cudaMemsetAsync(dev.p, 0, sizeof(FillDev), c.stream));
+    const int n2 = (int)(2 * nt);
+    fill_i32_kernel<<<(n2 + 255) / 256, 256, 0, c.stream>>>(keys.p, ORD_POS_INF, n2);
+    dim3 blk(128), grd((pitch + 127) / 128, rows < 2048 ? rows : 2048);
+    dist_pad_init_kernel<<<grd, blk, 0, c.stream>>>(d_open, open_bit, d_winit, Zp.p, Wp.p, W, H, pitch, rows);
+    RDB_CK(cudaGetLastError());
+    count_launch(2);
+    ordered = false;
+    mapW = make_map(Wp.p, pitch, rows, SP, SROWS);
+    mapZ = make_map(Zp.p, pitch, rows, TX, TY);
+    int per_sm = 0;
+    RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_sweep_kernel<1>, FILL_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    grid = c.num_sms * per_sm;
+    round = 1;
+    std::vector<int> init((size_t)nt);
+    for (size_t t = 0; t < nt; t++) init[t] = (int)t;
     seed_worklist(init);
   }
 
@@ -820,7 +890,8 @@ struct FillState {
           a.use_proc = 0;
         }
         sched_round++;
-        fill_sweep_kernel<<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
+        if (step_mode) fill_sweep_kernel<1><<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
+        else fill_sweep_kernel<0><<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
         round++;
       }
       kt.stop_async();
@@ -904,6 +975,26 @@ struct FillState {
     count_launch();
   }
 };
+
+// Geodesic (8-connected, unit step) distance from the seeds in `d_w_inout` (+inf = not a seed)
+// through the cells whose `d_open` byte has `open_bit` set; other cells keep +inf unless seeded.
+// Same tile machinery as the fill (the operator only differs by the "+1"); exact for distances
+// below 2^24.  Result overwrites d_w_inout.
+void geodesic_distance_dev(const uint8_t *d_open, int open_bit, float *d_w_inout, int w, int h) {
+  Ctx &c = ctx();
+  FillState st;
+  const rdb200_stats saved = c.stats;
+  st.begin_dist(d_open, open_bit, d_w_inout, w, h);
+  st.run();
+  st.finish(d_w_inout);
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  // keep the caller's accounting: only add what this solve cost
+  const int64_t launches = c.stats.kernel_launches;
+  const int64_t rounds = c.stats.fill_rounds;
+  c.stats = saved;
+  c.stats.kernel_launches = launches;
+  c.stats.flat_bfs_levels += rounds;
+}
 
 void fill_depressions_dev(float *d_dem, int w, int h) {
   Ctx &c = ctx();

@@ -315,6 +315,48 @@ __global__ void __launch_bounds__(256) make_labels_kernel(const uint8_t *__restr
   labels[i] = lab;
 }
 
+// ---- tiled formulation: the two gradients as geodesic distances solved by the fill's tile engine ----
+// away:    seeds = high-edge cells of drainable flats, distance 1            (Barnes2014.hpp:62-110)
+// towards: low-edge cells get 1 (set at conversion); the IS_A_FLAT cells next to a low edge of the
+//          same elevation (= same flat) are the seeds, distance 2           (Barnes2014.hpp:152-211)
+__global__ void __launch_bounds__(256) gradient_seed_kernel(const float *__restrict__ dem, const uint8_t *__restrict__ ft,
+                                                             const int *__restrict__ labels, float *__restrict__ winit,
+                                                             int W, int H, int away) {
+  const size_t n = (size_t)W * H;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float inf = __int_as_float(0x7f800000);
+  const uint8_t f = ft[i];
+  float w0 = inf;
+  if (away) {
+    if ((f & FT_HIGH) && labels[i] != 0) w0 = 1.0f;
+  } else if (f & FT_FLAT) {
+    const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+    const float e = __ldg(dem + i);
+#pragma unroll
+    for (int k = 1; k <= 8; k++) {  // flat cells are interior cells: all 8 neighbours exist
+      const size_t ni = (size_t)(y + d8dy(k)) * W + (x + d8dx(k));
+      if ((ft[ni] & FT_LOW) && __ldg(dem + ni) == e) w0 = 2.0f;
+    }
+  }
+  winit[i] = w0;
+}
+
+// float distances -> int levels in place (0 = not reached); away also folds the per-flat maximum
+__global__ void __launch_bounds__(256) gradient_convert_kernel(const uint8_t *__restrict__ ft, const int *__restrict__ labels,
+                                                                int *dist_inout, int *Hh, size_t n, int away) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = __int_as_float(dist_inout[i]);
+  int d = (v < __int_as_float(0x7f800000)) ? (int)v : 0;
+  if (!away && (ft[i] & FT_LOW)) d = 1;
+  dist_inout[i] = d;
+  if (away && d > 0) {
+    const int lab = labels[i];
+    if (lab != 0 && Hh[lab - 1] < d) atomicMax(&Hh[lab - 1], d);  // flat_height, Barnes2014.hpp:93-94
+  }
+}
+
 template <bool AWAY>
 int run_bfs(const uint8_t *ft, const int *labels, int *dist, int *H, int *q0, int *q1, FlatDev *dev, int w, int h) {
   Ctx &c = ctx();
@@ -399,10 +441,28 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   DevBuf<int> q0(qcap), q1(qcap);
   RDB_CK(cudaMemsetAsync(Hh.p, 0, n * sizeof(int), c.stream));
   int levels = 0;
-  levels += run_bfs<true>(ft.p, labels.p, away.p, Hh.p, q0.p, q1.p, dev.p, w, h);
-  lap("bfs away");
-  levels += run_bfs<false>(ft.p, labels.p, tw.p, Hh.p, q0.p, q1.p, dev.p, w, h);
-  lap("bfs towards");
+  if (c.params.flats_tiled) {
+    q0.reset();
+    q1.reset();
+    for (int pass = 0; pass < 2; pass++) {
+      const int is_away = pass == 0;
+      int *dist = is_away ? away.p : tw.p;
+      gradient_seed_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, labels.p, reinterpret_cast<float *>(dist), w, h, is_away);
+      RDB_CK(cudaGetLastError());
+      count_launch();
+      geodesic_distance_dev(ft.p, FT_FLAT, reinterpret_cast<float *>(dist), w, h);
+      gradient_convert_kernel<<<blocks, 256, 0, c.stream>>>(ft.p, labels.p, dist, Hh.p, n, is_away);
+      RDB_CK(cudaGetLastError());
+      count_launch();
+      lap(is_away ? "gradient away (tiled)" : "gradient towards (tiled)");
+    }
+    levels = (int)c.stats.flat_bfs_levels;
+  } else {
+    levels += run_bfs<true>(ft.p, labels.p, away.p, Hh.p, q0.p, q1.p, dev.p, w, h);
+    lap("bfs away");
+    levels += run_bfs<false>(ft.p, labels.p, tw.p, Hh.p, q0.p, q1.p, dev.p, w, h);
+    lap("bfs towards");
+  }
   c.stats.flat_bfs_levels = levels;
 
   flats_apply_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, labels.p, away.p, tw.p, Hh.p, d_mask_out, d_labels_out, w, h,
