@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(256) flow_code_d8_x4_kernel(const float *__res
     }
     *reinterpret_cast<uchar4 *>(code + i0) = make_uchar4(cd[0], cd[1], cd[2], cd[3]);
     double *ap = accum + i0;
-    if (ones) {
+    if (ones == 2) {
+      // packed unit-weight path: deps_gather_packed_x4_kernel initialises the accumulator words
+    } else if (ones) {
       reinterpret_cast<double2 *>(ap)[0] = make_double2(cd[0] == kCodeNoData ? -1.0 : 1.0, cd[1] == kCodeNoData ? -1.0 : 1.0);
       reinterpret_cast<double2 *>(ap)[1] = make_double2(cd[2] == kCodeNoData ? -1.0 : 1.0, cd[3] == kCodeNoData ? -1.0 : 1.0);
     } else {
@@ -596,10 +598,125 @@ __global__ void sanitize_dirs_kernel(const uint8_t *__restrict__ dirs, uint8_t *
 
 }  // namespace
 
+// =================================================================================================
+// Unit-weight D8 (the Python default, richdem.FlowAccumulation(dem, 'D8')): every partial sum is an
+// integer < 2^31, so a cell's accumulator and its remaining-donor count share ONE 64-bit word
+//     [ 8 bits donors left | 56 bits integer sum ]
+// living in the caller's accumulation array.  A donor adds (value - 1<<56) with a single atomicAdd:
+// the returned old word tells it whether it was the last donor, and if so the complete sum -- no
+// second atomic, no fence, no separate load.  The last donor then overwrites the word with the final
+// double (nobody else touches it any more) and walks on.  Results are the same integers the
+// reference computes in double arithmetic, bit for bit.
+// =================================================================================================
+namespace {
+constexpr unsigned long long kPkOne = 1ull << 56;
+constexpr unsigned long long kPkVal = kPkOne - 1;
+constexpr unsigned long long kPkSource = (1ull << 63) | 1ull;  // no donors, own unit of flow, not started yet
+
+__global__ void __launch_bounds__(256) deps_gather_packed_x4_kernel(uint8_t *code, unsigned long long *__restrict__ word,
+                                                                     int W, int H) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x4 >= W) return;
+  for (int y = blockIdx.y; y < H; y += gridDim.y) {
+    const size_t i0 = (size_t)y * W + x4;
+    uint8_t r[3][6];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int yy = y + j - 1;
+      if (yy < 0 || yy >= H) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) r[j][k] = 0;
+      } else {
+        const uint8_t *row = code + (size_t)yy * W + x4;
+        const uchar4 m = *reinterpret_cast<const uchar4 *>(row);
+        r[j][1] = m.x; r[j][2] = m.y; r[j][3] = m.z; r[j][4] = m.w;
+        r[j][0] = x4 > 0 ? row[-1] : (uint8_t)0;
+        r[j][5] = x4 + 4 < W ? row[4] : (uint8_t)0;
+      }
+    }
+    unsigned long long out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int cc = r[1][k + 1];
+      if (cc == kCodeNoData) {
+        out[k] = 0xBFF0000000000000ull;  // -1.0 (flow_accumulation_generic.hpp:95-97)
+        continue;
+      }
+      const int nr[9] = {0, 1, 0, 0, 0, 1, 2, 2, 2};
+      const int nc[9] = {0, k, k, k + 1, k + 2, k + 2, k + 2, k + 1, k};
+      unsigned deps = 0;
+      int dn = 0, dcode = 0;
+#pragma unroll
+      for (int n = 1; n <= 8; n++) {
+        const int cn = r[nr[n]][nc[n]];
+        if ((cn & 15) == 0 || cn == kCodeNoData) continue;
+        if ((cn & 15) == d8_inverse(n)) {
+          deps++;
+          dn = n;
+          dcode = cn;
+        }
+      }
+      out[k] = deps == 0 ? kPkSource : (((unsigned long long)deps << 56) | 1ull);
+      if (deps == 1) code[(size_t)(y + d8dy(dn)) * W + (x4 + k + d8dx(dn))] = (uint8_t)(dcode | kCodeSole);
+    }
+    reinterpret_cast<ulonglong2 *>(word + i0)[0] = make_ulonglong2(out[0], out[1]);
+    reinterpret_cast<ulonglong2 *>(word + i0)[1] = make_ulonglong2(out[2], out[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) accum_walk_packed_kernel(const uint8_t *__restrict__ code, unsigned long long *word,
+                                                                 int W, int ncells) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ncells) return;
+  int c = t;
+  if (word[c] != kPkSource) return;
+  unsigned long long acc = 1;
+  word[c] = (unsigned long long)__double_as_longlong(1.0);
+  for (;;) {
+    const int cdraw = code[c];
+    const int cd = cdraw & 15;
+    if (cdraw == kCodeNoData || cd == 0) break;
+    const int r = c + d8dy(cd) * W + d8dx(cd);
+    unsigned long long total;
+    if (cdraw & kCodeSole) {
+      total = acc + 1;  // the receiver holds its own unit and waits for me alone
+    } else {
+      if (code[r] == kCodeNoData) break;  // flow into NoData is dropped (FM_D8 never produces it)
+      const unsigned long long old = atomicAdd(word + r, acc - kPkOne);
+      if ((old >> 56) != 1ull) break;     // other donors are still to come: the last one carries on
+      total = (old & kPkVal) + acc;
+    }
+    word[r] = (unsigned long long)__double_as_longlong((double)total);
+    acc = total;
+    c = r;
+  }
+}
+}  // namespace
+
 // FA_D8 / FA_Tarboton fused (reference methods/flow_accumulation.hpp:27,16): no 36 B/cell props
 void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodata, bool ones, bool dinf) {
   Ctx &c = ctx();
   const size_t n = (size_t)w * h;
+  if (!dinf && ones && (w & 3) == 0 && ((uintptr_t)d_dem & 15) == 0 && ((uintptr_t)d_accum & 15) == 0 &&
+      c.params.accum_packed) {
+    // unit-weight D8: packed integer accumulation (see above)
+    DevBuf<uint8_t> code(n);
+    dim3 blk(256), grd((w / 4 + 255) / 256, h < 8192 ? h : 8192);
+    flow_code_d8_x4_kernel<<<grd, blk, 0, c.stream>>>(d_dem, code.p, d_accum, w, h, nodata, 2);
+    deps_gather_packed_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, reinterpret_cast<unsigned long long *>(d_accum), w, h);
+    RDB_CK(cudaGetLastError());
+    count_launch(2);
+    KernelTimer kt;
+    accum_walk_packed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(
+        code.p, reinterpret_cast<unsigned long long *>(d_accum), w, (int)n);
+    RDB_CK(cudaGetLastError());
+    count_launch();
+    kt.stop_async();
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    c.stats.ms_main_kernel += kt.ms();
+    c.stats.accum_rounds = 1;
+    return;
+  }
   DevBuf<uint8_t> code(n);
   DevBuf<uint32_t> st(n);
   DevBuf<float> rmax;

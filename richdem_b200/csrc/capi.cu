@@ -235,6 +235,7 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "accum_threads") p.accum_threads = value > 0 ? value : 256;
   else if (n == "accum_budget") p.accum_budget = value;
   else if (n == "flats_tiled") p.flats_tiled = value;
+  else if (n == "accum_packed") p.accum_packed = value;
   else fail("rdb200_set_param: unknown parameter '%s'", name);
   CAPI_END
 }

@@ -143,6 +143,8 @@ __device__ __forceinline__ void fence_proxy_async() {
 // the tile was last relaxed (the interior is still at its local fixed point).
 constexpr int NBLK = BXN * BYN;  // blocks per tile
 constexpr int MKP = BXN + 2;       // pitch of the mark array (one spare entry all round)
+constexpr int NWARP = FILL_THREADS / 32;
+constexpr int SEG = ((NBLK + NWARP - 1) / NWARP + 31) / 32 * 32;  // blocks scanned / listed per warp
 // apron sides (and corners) of a tile that changed; SIDE_FULL = relax every block
 enum : int { SIDE_N = 1, SIDE_S = 2, SIDE_W = 4, SIDE_E = 8, SIDE_NW = 16, SIDE_NE = 32, SIDE_SW = 64,
              SIDE_SE = 128, SIDE_FULL = 256 };
@@ -184,8 +186,10 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
   __shared__ __align__(128) float sZ[TY * TX];
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ unsigned char sMark[MKP * (BYN + 2)];  // next-pass marks; spare rim so neighbour marks need no bounds checks
-  __shared__ unsigned char sList[2][NBLK];    // compacted dirty-block lists, double buffered
-  __shared__ int sCount[2];
+  // compacted dirty-block lists, double buffered.  Every warp compacts a fixed share of the blocks
+  // into its own segment (ballot + popc, no atomics); a pass walks the concatenation of the segments.
+  __shared__ unsigned char sList[2][NWARP][SEG];
+  __shared__ __align__(16) int sCnt[2][NWARP];
   __shared__ int sTile;
   __shared__ int sFlags;
   __shared__ int sKey;
@@ -236,8 +240,6 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     if (tid == 0) {
       sFlags = 0;
       sKey = ORD_POS_INF;
-      sCount[0] = 0;
-      sCount[1] = 0;
       sProf[0] = sProf[1] = 0;
     }
     if (a.use_tma) {
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     }
     // ---- initial dirty list from the apron sides that changed (overlaps the TMA flight) ----
     int sides = a.sides[(r & 1) * ntiles + t];
-    __syncthreads();  // everyone has read `sides` (and sCount is zero) before it is cleared
+    __syncthreads();  // everyone has read `sides` before it is cleared
     if (tid == 0) {
       a.sides[(r & 1) * ntiles + t] = 0;
       a.keys[(r & 1) * ntiles + t] = ORD_POS_INF;
@@ -269,26 +271,28 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     // seeded tile (start of a fill, or a ghost row was replaced): boundary cells may lie inside the
     // tile when the raster edge is not tile-aligned, so relax every block once
     if (sides == 0) sides = SIDE_FULL;
-    for (int b0 = 0; b0 < NBLK; b0 += FILL_THREADS) {
-      const int b = b0 + tid;
-      const int bx = b % BXN, by = b / BXN;
-      bool on = (sides & SIDE_FULL) != 0;
-      on |= (sides & SIDE_N) && by == 0;
-      on |= (sides & SIDE_S) && by == BYN - 1;
-      on |= (sides & SIDE_W) && bx == 0;
-      on |= (sides & SIDE_E) && bx == BXN - 1;
-      on |= (sides & SIDE_NW) && b == 0;
-      on |= (sides & SIDE_NE) && b == BXN - 1;
-      on |= (sides & SIDE_SW) && b == NBLK - BXN;
-      on |= (sides & SIDE_SE) && b == NBLK - 1;
-      on &= b < NBLK;
-      const unsigned bal = __ballot_sync(0xffffffffu, on);
-      if (bal) {
-        int base = 0;
-        if ((tid & 31) == 0) base = atomicAdd(&sCount[0], __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (on) sList[0][base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (unsigned char)b;
+    const int lane = tid & 31, wrp = tid >> 5;
+    {
+      int cntw = 0;
+#pragma unroll
+      for (int q = 0; q < SEG / 32; q++) {
+        const int b = wrp * SEG + 32 * q + lane;  // this warp's share of the blocks
+        const int bx = b % BXN, by = b / BXN;
+        bool on = (sides & SIDE_FULL) != 0;
+        on |= (sides & SIDE_N) && by == 0;
+        on |= (sides & SIDE_S) && by == BYN - 1;
+        on |= (sides & SIDE_W) && bx == 0;
+        on |= (sides & SIDE_E) && bx == BXN - 1;
+        on |= (sides & SIDE_NW) && b == 0;
+        on |= (sides & SIDE_NE) && b == BXN - 1;
+        on |= (sides & SIDE_SW) && b == NBLK - BXN;
+        on |= (sides & SIDE_SE) && b == NBLK - 1;
+        on &= b < NBLK;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (on) sList[0][wrp][cntw + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)b;
+        cntw += __popc(bal);
       }
+      if (lane == 0) sCnt[0][wrp] = cntw;
     }
     if (a.use_tma) {
       mbar_wait(&mbar, phase);
@@ -301,11 +305,25 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     int iters = 0;
     int cl = 0;       // current list
     bool again = false;
-    int nlist = sCount[0];
+    int segn[NWARP];
+    int nlist = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < NWARP; w2++) {
+      segn[w2] = sCnt[0][w2];
+      nlist += segn[w2];
+    }
     while (nlist > 0) {
-      if (tid == 0) sCount[cl ^ 1] = 0;
       for (int i = tid; i < nlist; i += FILL_THREADS) {
-        const int b = sList[cl][i];
+        // i-th entry of the concatenated per-warp segments
+        int seg = 0, off = i;
+#pragma unroll
+        for (int w2 = 0; w2 < NWARP - 1; w2++) {
+          if (seg == w2 && off >= segn[w2]) {
+            off -= segn[w2];
+            seg = w2 + 1;
+          }
+        }
+        const int b = sList[cl][seg][off];
         const int bx = b % BXN, by = b / BXN;
         const int srow = 4 * by + 1, scol = 4 * bx + PADL;
         float v[6][6];
@@ -401,23 +419,29 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
       }
       iters++;
       __syncthreads();  // marks and W rows of this pass are visible; list `cl` is consumed
-      // compact the marks into the other list
-      for (int b0 = 0; b0 < NBLK; b0 += FILL_THREADS) {
-        const int b = b0 + tid;
-        const int mi = (b / BXN + 1) * MKP + (b % BXN) + 1;
-        const bool on = (b < NBLK) && sMark[mi] != 0;
-        if (on) sMark[mi] = 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, on);
-        if (bal) {
-          int base = 0;
-          if ((tid & 31) == 0) base = atomicAdd(&sCount[cl ^ 1], __popc(bal));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (on) sList[cl ^ 1][base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (unsigned char)b;
+      // compact the marks into the other list: each warp scans its share and fills its own segment
+      {
+        int cntw = 0;
+#pragma unroll
+        for (int q = 0; q < SEG / 32; q++) {
+          const int b = wrp * SEG + 32 * q + lane;
+          const int mi = (b / BXN + 1) * MKP + (b % BXN) + 1;
+          const bool on = (b < NBLK) && sMark[mi] != 0;
+          if (on) sMark[mi] = 0;
+          const unsigned bal = __ballot_sync(0xffffffffu, on);
+          if (on) sList[cl ^ 1][wrp][cntw + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)b;
+          cntw += __popc(bal);
         }
+        if (lane == 0) sCnt[cl ^ 1][wrp] = cntw;
       }
       __syncthreads();
       cl ^= 1;
-      nlist = sCount[cl];
+      nlist = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < NWARP; w2++) {
+        segn[w2] = sCnt[cl][w2];
+        nlist += segn[w2];
+      }
       if (nlist > 0 && max_iters > 0 && iters >= max_iters) {
         again = true;  // not at the local fixed point yet: revisit (fully) next round
         break;
