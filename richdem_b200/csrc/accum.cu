@@ -614,7 +614,7 @@ constexpr unsigned long long kPkVal = kPkOne - 1;
 constexpr unsigned long long kPkSource = (1ull << 63) | 1ull;  // no donors, own unit of flow, not started yet
 
 __global__ void __launch_bounds__(256) deps_gather_packed_x4_kernel(uint8_t *code, unsigned long long *__restrict__ word,
-                                                                     int W, int H) {
+                                                                     int W, int H, int y_lo, int y_hi) {
   const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (x4 >= W) return;
   for (int y = blockIdx.y; y < H; y += gridDim.y) {
@@ -638,6 +638,10 @@ __global__ void __launch_bounds__(256) deps_gather_packed_x4_kernel(uint8_t *cod
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int cc = r[1][k + 1];
+      if (y < y_lo || y >= y_hi) {  // ghost row of a row band: an empty parking slot
+        out[k] = 0;
+        continue;
+      }
       if (cc == kCodeNoData) {
         out[k] = 0xBFF0000000000000ull;  // -1.0 (flow_accumulation_generic.hpp:95-97)
         continue;
@@ -664,14 +668,26 @@ __global__ void __launch_bounds__(256) deps_gather_packed_x4_kernel(uint8_t *cod
   }
 }
 
+// BAND: cells below ghost_lo_end / from ghost_hi_start on belong to a neighbouring row band; flow
+// into them is parked in their word as [parcel count | sum] for the caller to ship.  `frontier`
+// (optional) lists cells completed by a neighbour's flow; their word already holds the final double.
+template <bool BAND>
 __global__ void __launch_bounds__(256) accum_walk_packed_kernel(const uint8_t *__restrict__ code, unsigned long long *word,
-                                                                 int W, int ncells) {
+                                                                 int W, int ncells, const int *__restrict__ frontier,
+                                                                 int ghost_lo_end, int ghost_hi_start) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ncells) return;
-  int c = t;
-  if (word[c] != kPkSource) return;
-  unsigned long long acc = 1;
-  word[c] = (unsigned long long)__double_as_longlong(1.0);
+  int c;
+  unsigned long long acc;
+  if (BAND && frontier) {
+    c = frontier[t];
+    acc = (unsigned long long)__longlong_as_double((long long)word[c]);
+  } else {
+    c = t;
+    if (word[c] != kPkSource) return;
+    acc = 1;
+    word[c] = (unsigned long long)__double_as_longlong(1.0);
+  }
   for (;;) {
     const int cdraw = code[c];
     const int cd = cdraw & 15;
@@ -682,6 +698,10 @@ __global__ void __launch_bounds__(256) accum_walk_packed_kernel(const uint8_t *_
       total = acc + 1;  // the receiver holds its own unit and waits for me alone
     } else {
       if (code[r] == kCodeNoData) break;  // flow into NoData is dropped (FM_D8 never produces it)
+      if (BAND && (r < ghost_lo_end || r >= ghost_hi_start)) {
+        atomicAdd(word + r, acc + kPkOne);  // one more parcel, `acc` more flow
+        break;
+      }
       const unsigned long long old = atomicAdd(word + r, acc - kPkOne);
       if ((old >> 56) != 1ull) break;     // other donors are still to come: the last one carries on
       total = (old & kPkVal) + acc;
@@ -689,6 +709,58 @@ __global__ void __launch_bounds__(256) accum_walk_packed_kernel(const uint8_t *_
     word[r] = (unsigned long long)__double_as_longlong((double)total);
     acc = total;
     c = r;
+  }
+}
+// packed ghost row -> (sum, parcels) rows for shipping; clears the slots; counts the parcels
+__global__ void __launch_bounds__(256) band_take_packed_kernel(unsigned long long *ghost, double *sum, int *cnt, int W,
+                                                                int *total) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  int k = 0;
+  if (x < W) {
+    const unsigned long long wv = ghost[x];
+    k = (int)(wv >> 56);
+    sum[x] = (double)(wv & kPkVal);
+    cnt[x] = k;
+    ghost[x] = 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) k += __shfl_down_sync(0xffffffffu, k, o);
+  if ((threadIdx.x & 31) == 0 && k) atomicAdd(total, k);
+}
+
+__global__ void __launch_bounds__(256) band_count_packed_kernel(const unsigned long long *__restrict__ gtop,
+                                                                 const unsigned long long *__restrict__ gbot, int W,
+                                                                 int *sums) {
+  int s0 = 0, s1 = 0;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+    if (gtop) s0 += (int)(gtop[x] >> 56);
+    if (gbot) s1 += (int)(gbot[x] >> 56);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_down_sync(0xffffffffu, s0, o);
+    s1 += __shfl_down_sync(0xffffffffu, s1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (s0) atomicAdd(&sums[0], s0);
+    if (s1) atomicAdd(&sums[1], s1);
+  }
+}
+
+// neighbour's flow arrives at my edge row: fold it into the packed words, release completed cells
+__global__ void __launch_bounds__(256) band_apply_packed_kernel(unsigned long long *row, const double *__restrict__ sum,
+                                                                 const int *__restrict__ cnt, int W, int base_index,
+                                                                 int *frontier, int *fcount) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const int k = cnt[x];
+  if (k <= 0) return;
+  const unsigned long long wv = row[x];
+  const unsigned long long val = (wv & kPkVal) + (unsigned long long)sum[x];
+  const unsigned long long left = (wv >> 56) - (unsigned long long)k;
+  if (left == 0) {
+    row[x] = (unsigned long long)__double_as_longlong((double)val);
+    frontier[atomicAdd(fcount, 1)] = base_index + x;
+  } else {
+    row[x] = (left << 56) | val;
   }
 }
 }  // namespace
@@ -703,12 +775,12 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     DevBuf<uint8_t> code(n);
     dim3 blk(256), grd((w / 4 + 255) / 256, h < 8192 ? h : 8192);
     flow_code_d8_x4_kernel<<<grd, blk, 0, c.stream>>>(d_dem, code.p, d_accum, w, h, nodata, 2);
-    deps_gather_packed_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, reinterpret_cast<unsigned long long *>(d_accum), w, h);
+    deps_gather_packed_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, reinterpret_cast<unsigned long long *>(d_accum), w, h, 0, h);
     RDB_CK(cudaGetLastError());
     count_launch(2);
     KernelTimer kt;
-    accum_walk_packed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(
-        code.p, reinterpret_cast<unsigned long long *>(d_accum), w, (int)n);
+    accum_walk_packed_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(
+        code.p, reinterpret_cast<unsigned long long *>(d_accum), w, (int)n, nullptr, 0, 0);
     RDB_CK(cudaGetLastError());
     count_launch();
     kt.stop_async();
@@ -835,6 +907,7 @@ struct FaccState {
   DevBuf<uint32_t> st;
   DevBuf<int> ghostcnt, fr0, fr1, cnt;
   bool prepared = false;
+  bool packed = false;    // unit-weight D8: accumulator words are [donors left | integer sum] until final
   int n_frontier = 0;     // cells waiting in fr0 (seeded by apply_inflow)
   int rounds = 0;
 
@@ -850,8 +923,9 @@ struct FaccState {
     dinf = dinf_;
     accum = d_accum;
     if (h - gt - gb < 1) fail("facc_begin: band has no owned rows");
+    packed = !dinf && ones && (w & 3) == 0 && ((uintptr_t)d_accum & 15) == 0 && c.params.accum_packed != 0;
     code.alloc(n());
-    st.alloc(n());
+    if (!packed) st.alloc(n());
     if (dinf) rmax.alloc(n());
     ghostcnt.alloc(2 * (size_t)W);
     fr0.alloc(n());
@@ -868,6 +942,7 @@ struct FaccState {
       flow_code_kernel<false><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, nullptr, d_accum, w, h, nodata, ones ? 1 : 0);
     RDB_CK(cudaGetLastError());
     count_launch();
+    if (packed) return;  // the packed gather (first run) initialises every accumulator word
     const unsigned rb = (unsigned)((W + 255) / 256);
     if (gt) band_zero_ghost_kernel<<<rb, 256, 0, c.stream>>>(accum, W);
     if (gb) band_zero_ghost_kernel<<<rb, 256, 0, c.stream>>>(accum + (size_t)(H - 1) * W, W);
@@ -916,8 +991,40 @@ struct FaccState {
     }
   }
 
+  void run_packed(int *sent_top, int *sent_bottom) {
+    Ctx &c = ctx();
+    unsigned long long *word = reinterpret_cast<unsigned long long *>(accum);
+    const int lo_end = gt ? W : 0, hi_start = gb ? (H - 1) * W : H * W;
+    if (!prepared) {
+      dim3 blk(256), grd((W / 4 + 255) / 256, H < 8192 ? H : 8192);
+      deps_gather_packed_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, W, H, gt, H - gb);
+      accum_walk_packed_kernel<true><<<(unsigned)((n() + 255) / 256), 256, 0, c.stream>>>(code.p, word, W, (int)n(),
+                                                                                         nullptr, lo_end, hi_start);
+      count_launch(2);
+      prepared = true;
+    } else if (n_frontier > 0) {
+      accum_walk_packed_kernel<true><<<(unsigned)((n_frontier + 255) / 256), 256, 0, c.stream>>>(
+          code.p, word, W, n_frontier, fr0.p, lo_end, hi_start);
+      count_launch();
+    }
+    RDB_CK(cudaGetLastError());
+    n_frontier = 0;
+    rounds++;
+    int *h = (int *)c.pinned;
+    DevBuf<int> sums(2);
+    RDB_CK(cudaMemsetAsync(sums.p, 0, 2 * sizeof(int), c.stream));
+    band_count_packed_kernel<<<64, 256, 0, c.stream>>>(gt ? word : nullptr, gb ? word + (size_t)(H - 1) * W : nullptr, W,
+                                                       sums.p);
+    RDB_CK(cudaMemcpyAsync(h, sums.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    if (sent_top) *sent_top = h[0];
+    if (sent_bottom) *sent_bottom = h[1];
+    c.stats.accum_rounds = rounds;
+  }
+
   // returns the number of flow parcels parked in the ghost rows by this run: [top, bottom]
   void run(int *sent_top, int *sent_bottom) {
+    if (packed) return run_packed(sent_top, sent_bottom);
     Ctx &c = ctx();
     WalkArgs<double> a;
     memset(&a, 0, sizeof(a));
@@ -969,6 +1076,13 @@ struct FaccState {
   void take_outflow(int which, double *d_sum_row, int *d_cnt_row) {
     Ctx &c = ctx();
     if ((which == 0 && !gt) || (which == 1 && !gb)) fail("facc_take_outflow: no ghost row on that side");
+    if (packed) {
+      unsigned long long *g = reinterpret_cast<unsigned long long *>(accum) + (size_t)ghost_row(which) * W;
+      band_take_packed_kernel<<<(unsigned)((W + 255) / 256), 256, 0, c.stream>>>(g, d_sum_row, d_cnt_row, W, cnt.p + 3);
+      RDB_CK(cudaGetLastError());
+      count_launch();
+      return;
+    }
     double *grow = accum + (size_t)ghost_row(which) * W;
     int *crow = ghostcnt.p + (which == 0 ? 0 : W);
     RDB_CK(cudaMemcpyAsync(d_sum_row, grow, (size_t)W * 8, cudaMemcpyDeviceToDevice, c.stream));
@@ -982,6 +1096,14 @@ struct FaccState {
     if ((which == 0 && !gt) || (which == 1 && !gb)) fail("facc_apply_inflow: no neighbour on that side");
     const int row = edge_row(which);
     const unsigned rb = (unsigned)((W + 255) / 256);
+    if (packed) {
+      band_apply_packed_kernel<<<rb, 256, 0, c.stream>>>(reinterpret_cast<unsigned long long *>(accum) + (size_t)row * W,
+                                                         d_sum_row, d_cnt_row, W, row * W, fr0.p, cnt.p + 2);
+      RDB_CK(cudaGetLastError());
+      count_launch();
+      pending_apply = true;
+      return;
+    }
     // frontier count lives in cnt[2]; cells are appended to fr0 after whatever is already waiting
     band_apply_inflow_kernel<<<rb, 256, 0, c.stream>>>(accum + (size_t)row * W, st.p + (size_t)row * W, d_sum_row,
                                                        d_cnt_row, W, row * W, fr0.p, cnt.p + 2);
