@@ -383,8 +383,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-stages", action="store_true")
     ap.add_argument("--traffic", type=float, default=None,
-                    help="dram bytes per sweep launch from the committed ncu capture (profiles/)")
+                    help="dram bytes per sweep launch from the committed ncu capture (default: profiles/traffic.json)")
     args = ap.parse_args()
+    if args.traffic is None:
+        try:
+            args.traffic = float(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["dram_bytes_per_launch"])
+        except Exception:
+            args.traffic = None
     if args.impl == "reference":
         run_reference(args)
     else:

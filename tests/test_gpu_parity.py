@@ -248,3 +248,35 @@ def test_cxx_dropin_matches_reference_cpu_templates():
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout[-3000:]
     assert "thrown=0 mismatches=0 dim_mismatch_throws=1" in out.stdout, out.stdout[-3000:]
+
+
+# ---- alternative code paths must give identical results ------------------------------------------
+def test_algorithm_variants_agree(checker):
+    """Level-ordered vs plain tile admission (fill), tiled vs level-synchronous gradients (flats),
+    packed vs double accumulators (unit-weight D8): same bits, and equal to the checker."""
+    dem = oracle.fbm_terrain(768, 1024, seed=17, quantum=0.25)
+    f_ref = checker.fill_depressions(dem)
+    r_ref = checker.resolve_flats(f_ref, ND)
+    a_ref = checker.fa_d8(r_ref, ND)
+    for name, value in (("fill_ordered", 0), ("flats_tiled", 0), ("accum_packed", 0)):
+        default = 1
+        _lib.set_param(name, value)
+        try:
+            f = np.asarray(rd.FillDepressions(R(dem)))
+            r = np.asarray(rd.ResolveFlats(R(f_ref)))
+            a = np.asarray(rd.FlowAccumulation(R(r_ref), "D8"))
+        finally:
+            _lib.set_param(name, default)
+        assert np.array_equal(f, f_ref), name
+        assert np.array_equal(r.view(np.uint32), r_ref.view(np.uint32)), name
+        assert np.array_equal(a, a_ref), name
+    # and the defaults
+    assert np.array_equal(np.asarray(rd.FillDepressions(R(dem))), f_ref)
+    assert np.array_equal(np.asarray(rd.ResolveFlats(R(f_ref))).view(np.uint32), r_ref.view(np.uint32))
+    assert np.array_equal(np.asarray(rd.FlowAccumulation(R(r_ref), "D8")), a_ref)
+
+
+def test_unit_weight_d8_on_width_not_multiple_of_4(checker):
+    """W % 4 != 0 takes the scalar (non-vectorised, non-packed) kernels."""
+    dem = checker.fill_depressions(oracle.fbm_terrain(301, 403, seed=19, quantum=0.5))
+    assert np.array_equal(np.asarray(rd.FlowAccumulation(R(dem), "D8")), checker.fa_d8(dem, ND))
