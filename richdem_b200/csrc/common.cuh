@@ -53,7 +53,7 @@ __host__ __device__ __forceinline__ int d8dy(int n) {
 // ---- context ----------------------------------------------------------------------------
 struct Params {
   int64_t fill_max_iters = 0;   // 0 = relax every tile visit to its local fixed point
-  int64_t fill_rounds_per_sync = 8;
+  int64_t fill_rounds_per_sync = 16;
   int64_t fill_use_tma = 1;     // 0: plain ld.global staging (debug aid)
   int64_t fill_ordered = 1;       // admit tiles by rising water level (device-side feedback on the level)
   int64_t fill_order_rounds = 0;  // rounds the level schedule spans (0: 0.8 x tiles across the raster)

@@ -896,7 +896,7 @@ struct FillState {
     Ctx &c = ctx();
     int64_t rounds_this_call = 0;
     FillArgs a = make_args();
-    const int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 8);
+    const int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 16);
     FillDev *hd = (FillDev *)c.pinned;
     RDB_CK(cudaMemsetAsync(&dev.p->edge_changed, 0, sizeof(int), c.stream));
     for (;;) {

@@ -142,8 +142,12 @@ def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None
         import os
         from . import _lib
         if band_rounds is None:
-            band_rounds = int(os.environ.get("RDB_BAND_ROUNDS", "32")) if world > 1 else 0
+            band_rounds = int(os.environ.get("RDB_BAND_ROUNDS", "64")) if world > 1 else 0
         _lib.set_param("fill_band_rounds", band_rounds)
+        for knob in ("fill_ordered", "fill_rounds_per_sync"):  # experiment hooks
+            v = os.environ.get("RDB_" + knob.upper())
+            if v is not None:
+                _lib.set_param(knob, int(v))
     h, w = local_dem.shape
     if g_top:
         local_dem[0].fill_(float("inf"))
