@@ -301,11 +301,8 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
   }
   const int W = a.W;
   A acc = ld_acc(a.accum + c);
-  // receivers that become ready while this walker already has a successor wait on a small private
-  // stack (depth-first, same launch); only what does not fit goes to the global frontier array
-  constexpr int STK = 1;  // (kept for the row-band path; the single-GPU multi-receiver path uses accum_levels_kernel)
-  int stk[STK];
-  int sp = 0;
+  // receivers that become ready while this walker already has a successor go to the frontier array
+  // of the next launch (row-band D-infinity path; single-GPU multi-receiver graphs use accum_levels_kernel)
   for (;;) {
     int next = -1;
     if (MODE == 0) {
@@ -363,7 +360,6 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
           const uint32_t o2 = atomicSub(a.st + r2, 1u);
           if ((o2 & kDepsMask) == 1u) {
             if (next < 0) next = r2;
-            else if (sp < STK) stk[sp++] = r2;
             else a.next_frontier[atomicAdd(a.next_count, 1)] = r2;
           }
         }
@@ -397,16 +393,12 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
         const uint32_t o = atomicSub(a.st + r, 1u);
         if ((o & kDepsMask) == 1u) {
           if (next < 0) next = r;
-          else if (sp < STK) stk[sp++] = r;
           else a.next_frontier[atomicAdd(a.next_count, 1)] = r;
         }
       }
     }
   no_receiver:
-    if (next < 0) {
-      if (MODE != 0 && sp > 0) next = stk[--sp];
-      else break;
-    }
+    if (next < 0) break;
     // the atomicSub that returned 1 was performed after every other donor's (fenced) add, and this
     // L2 load is issued after it returned: it observes the complete sum
     c = next;

@@ -155,12 +155,6 @@ static void d2h(T *dst, const T *src, size_t n) {
   c.stats.ms_d2h += ms;
 }
 
-__global__ void fill_ones_kernel(double *p, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) p[i] = 1.0;
-}
-
 }  // namespace rdb
 
 using namespace rdb;

@@ -711,7 +711,6 @@ struct FillState {
   int64_t rounds_run = 0;
   bool still_active = false;
   int64_t sched_round = 0;
-  unsigned long long visits_seen = 0, iters_seen = 0;
 
   void begin(const float *d_dem, int w, int h) {
     Ctx &c = ctx();
@@ -1039,7 +1038,6 @@ struct rdb200_fill_state {
 };
 
 namespace rdb {
-int capi_guard_begin();
 void capi_set_error(const char *msg);
 }  // namespace rdb
 
