@@ -211,6 +211,28 @@ RDB200_API int rdb200_dev_facc_apply_inflow(rdb200_facc_state *state, int32_t wh
                                             const int32_t *d_cnt_row);
 RDB200_API int rdb200_dev_facc_finish(rdb200_facc_state *state);
 
+/* ---- row-band (multi-GPU) flat resolution -------------------------------------------------- */
+/* Same role as ResolveFlatsEpsilon (include/richdem/flats/flats.hpp:21-28) for one row band; the
+ * local elevation raster (ghost_top + owned + ghost_bottom rows, ghost rows = the neighbours' rows)
+ * is modified in place on the owned rows.  The steps run the single-GPU kernels on the local
+ * raster; between them the caller moves the seam rows (see the protocol in csrc/flats.cu and
+ * richdem_b200/sharded.py: resolve_flats_band). */
+typedef struct rdb200_flats_state rdb200_flats_state;
+RDB200_API int rdb200_dev_flats_begin(rdb200_flats_state **state, float *d_dem, int32_t width, int32_t height,
+                                      float nodata, int32_t ghost_top, int32_t ghost_bottom);
+RDB200_API int rdb200_dev_flats_arrays(rdb200_flats_state *state, uint64_t *out6);
+RDB200_API int rdb200_dev_flats_edges(rdb200_flats_state *state);
+RDB200_API int rdb200_dev_flats_components(rdb200_flats_state *state);
+RDB200_API int rdb200_dev_flats_labels(rdb200_flats_state *state);
+/* The distance state returned here speaks the row-band fill protocol: rdb200_dev_fill_run /
+ * _read_row / _update_row; hand it back to gradient_end (do not call rdb200_dev_fill_finish). */
+RDB200_API int rdb200_dev_flats_gradient_begin(rdb200_flats_state *state, int32_t away,
+                                               rdb200_fill_state **dist_state);
+RDB200_API int rdb200_dev_flats_gradient_end(rdb200_flats_state *state, int32_t away,
+                                             rdb200_fill_state *dist_state);
+RDB200_API int rdb200_dev_flats_apply(rdb200_flats_state *state);
+RDB200_API int rdb200_dev_flats_finish(rdb200_flats_state *state);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,15 @@ SIGNATURES = {
     "rdb200_dev_facc_take_outflow": [_vp, _i32, _vp, _vp],
     "rdb200_dev_facc_apply_inflow": [_vp, _i32, _vp, _vp],
     "rdb200_dev_facc_finish": [_vp],
+    "rdb200_dev_flats_begin": [C.POINTER(_vp), _vp, _i32, _i32, _f32, _i32, _i32],
+    "rdb200_dev_flats_arrays": [_vp, C.POINTER(C.c_uint64)],
+    "rdb200_dev_flats_edges": [_vp],
+    "rdb200_dev_flats_components": [_vp],
+    "rdb200_dev_flats_labels": [_vp],
+    "rdb200_dev_flats_gradient_begin": [_vp, _i32, C.POINTER(_vp)],
+    "rdb200_dev_flats_gradient_end": [_vp, _i32, _vp],
+    "rdb200_dev_flats_apply": [_vp],
+    "rdb200_dev_flats_finish": [_vp],
 }
 OTHER_SYMBOLS = ["rdb200_shutdown", "rdb200_last_error", "rdb200_version"]
 

@@ -14,6 +14,8 @@
 
 #include "../../include/richdem_b200.h"
 
+struct rdb200_fill_state;
+
 namespace rdb {
 
 // ---- errors -----------------------------------------------------------------------------
@@ -136,6 +138,9 @@ struct KernelTimer {
 // ---- stage entry points implemented in the .cu files (device pointers, ctx stream) -------
 void fill_depressions_dev(float *d_dem, int w, int h);
 void geodesic_distance_dev(const uint8_t *d_open, int open_bit, float *d_w_inout, int w, int h);
+rdb200_fill_state *new_band_distance_state(const uint8_t *d_open, int open_bit, const float *d_winit, int w, int h,
+                                           int ghost_top, int ghost_bottom);
+void finish_band_distance_state(rdb200_fill_state *s, float *d_out);
 void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask_out,
                        int32_t *d_labels_out, bool apply);
 void d8_flow_directions_dev(const float *d_dem, uint8_t *d_dirs, int w, int h, float nodata);

@@ -622,7 +622,8 @@ __global__ void __launch_bounds__(256) fill_hist_kernel(const float *__restrict_
 // elsewhere; padded W = winit (compact float array: +inf, or the seed distance)
 __global__ void __launch_bounds__(128) dist_pad_init_kernel(const uint8_t *__restrict__ open, int open_bit,
                                                              const float *__restrict__ winit, float *__restrict__ Zp,
-                                                             float *__restrict__ Wp, int W, int H, int pitch, int rows) {
+                                                             float *__restrict__ Wp, int W, int H, int pitch, int rows,
+                                                             int ghost_top, int ghost_bottom) {
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
   if (px >= pitch) return;
   const float inf = __int_as_float(0x7f800000);
@@ -631,8 +632,11 @@ __global__ void __launch_bounds__(128) dist_pad_init_kernel(const uint8_t *__res
     float zz = inf, ww = inf;
     if (x >= 0 && x < W && y >= 0 && y < H) {
       const size_t i = (size_t)y * W + x;
-      if (open[i] & open_bit) zz = 0.0f;
-      ww = winit[i];
+      // ghost rows of a row band start closed (+inf): they only ever hold what the neighbour sends
+      if (!((ghost_top && y == 0) || (ghost_bottom && y == H - 1))) {
+        if (open[i] & open_bit) zz = 0.0f;
+        ww = winit[i];
+      }
     }
     Zp[(size_t)py * pitch + px] = zz;
     Wp[(size_t)py * pitch + px] = ww;
@@ -807,7 +811,8 @@ struct FillState {
 
   // Geodesic-distance mode: `open` marks the cells the flood may enter (bit `open_bit`), `winit`
   // holds +inf or the seed distance of every cell.  Every tile is seeded once.
-  void begin_dist(const uint8_t *d_open, int open_bit, const float *d_winit, int w, int h) {
+  void begin_dist(const uint8_t *d_open, int open_bit, const float *d_winit, int w, int h, int ghost_top = 0,
+                  int ghost_bottom = 0) {
     Ctx &c = ctx();
     step_mode = 1;
     W = w;
@@ -833,7 +838,8 @@ struct FillState {
     const int n2 = (int)(2 * nt);
     fill_i32_kernel<<<(n2 + 255) / 256, 256, 0, c.stream>>>(keys.p, ORD_POS_INF, n2);
     dim3 blk(128), grd((pitch + 127) / 128, rows < 2048 ? rows : 2048);
-    dist_pad_init_kernel<<<grd, blk, 0, c.stream>>>(d_open, open_bit, d_winit, Zp.p, Wp.p, W, H, pitch, rows);
+    dist_pad_init_kernel<<<grd, blk, 0, c.stream>>>(d_open, open_bit, d_winit, Zp.p, Wp.p, W, H, pitch, rows, ghost_top,
+                                                    ghost_bottom);
     RDB_CK(cudaGetLastError());
     count_launch(2);
     ordered = false;
@@ -1036,6 +1042,26 @@ void fill_depressions_dev(float *d_dem, int w, int h) {
 struct rdb200_fill_state {
   rdb::FillState st;
 };
+
+namespace rdb {
+// row-band geodesic distance: same protocol object as the band fill (run / read_row / update_row / finish)
+rdb200_fill_state *new_band_distance_state(const uint8_t *d_open, int open_bit, const float *d_winit, int w, int h,
+                                           int ghost_top, int ghost_bottom) {
+  auto *s = new rdb200_fill_state();
+  try {
+    s->st.begin_dist(d_open, open_bit, d_winit, w, h, ghost_top, ghost_bottom);
+  } catch (...) {
+    delete s;
+    throw;
+  }
+  return s;
+}
+void finish_band_distance_state(rdb200_fill_state *s, float *d_out) {
+  s->st.finish(d_out);
+  RDB_CK(cudaStreamSynchronize(ctx().stream));
+  delete s;
+}
+}  // namespace rdb
 
 namespace rdb {
 void capi_set_error(const char *msg);

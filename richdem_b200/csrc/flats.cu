@@ -476,3 +476,180 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
 }
 
 }  // namespace rdb
+
+// =================================================================================================
+// Row-band (multi-GPU) flat resolution.  The stencil / union-find / seeding / conversion / apply
+// kernels above run unchanged on the local raster (ghost_top + owned + ghost_bottom rows); what
+// crosses a seam is moved by the caller (richdem_b200/sharded.py) between the steps below:
+//   begin (classify)            -> exchange flag rows (IS_A_FLAT / NoData of the ghost rows)
+//   edges                       -> exchange flag rows again (low / high edge bits)
+//   components (local union-find over owned + ghost rows, outlet flag per local root)
+//                               -> OR the outlet flags of roots that meet at a seam until stable
+//   labels
+//   gradient_begin(away)        -> band distance protocol (rdb200_dev_fill_run / read_row / update_row)
+//   gradient_end(away)          -> MAX the flat heights of roots that meet at a seam until stable
+//   gradient_begin/end(towards) -> band distance protocol
+//   apply, finish
+// =================================================================================================
+struct rdb200_flats_state {
+  int W = 0, H = 0, gt = 0, gb = 0;
+  float nodata = 0.f;
+  float *dem = nullptr;
+  rdb::DevBuf<uint8_t> ft, rootflag;
+  rdb::DevBuf<int> parent, labels, away, tw, Hh;
+  rdb::DevBuf<rdb::FlatDev> dev;
+  size_t n() const { return (size_t)W * H; }
+  unsigned blocks() const { return (unsigned)((n() + 255) / 256); }
+};
+
+namespace rdb {
+void capi_set_error(const char *msg);
+}
+
+#define FLATS_TRY try {
+#define FLATS_END                      \
+  }                                    \
+  catch (const std::exception &e) {    \
+    rdb::capi_set_error(e.what());     \
+    return 1;                          \
+  }                                    \
+  return 0;
+
+extern "C" {
+
+int rdb200_dev_flats_begin(rdb200_flats_state **state, float *d_dem, int32_t width, int32_t height, float nodata,
+                           int32_t ghost_top, int32_t ghost_bottom) {
+  FLATS_TRY
+  using namespace rdb;
+  ensure_init();
+  if (!state || !d_dem) fail("flats_begin: null pointer");
+  if (height - (ghost_top ? 1 : 0) - (ghost_bottom ? 1 : 0) < 1) fail("flats_begin: band has no owned rows");
+  Ctx &c = ctx();
+  auto *s = new rdb200_flats_state();
+  try {
+    s->W = width;
+    s->H = height;
+    s->gt = ghost_top ? 1 : 0;
+    s->gb = ghost_bottom ? 1 : 0;
+    s->nodata = nodata;
+    s->dem = d_dem;
+    const size_t n = s->n();
+    s->ft.alloc(n);
+    s->rootflag.alloc(n);
+    s->parent.alloc(n);
+    s->labels.alloc(n);
+    s->away.alloc(n);
+    s->tw.alloc(n);
+    s->Hh.alloc(n);
+    s->dev.alloc(1);
+    RDB_CK(cudaMemsetAsync(s->dev.p, 0, sizeof(FlatDev), c.stream));
+    RDB_CK(cudaMemsetAsync(s->rootflag.p, 0, n, c.stream));
+    RDB_CK(cudaMemsetAsync(s->Hh.p, 0, n * sizeof(int), c.stream));
+    // rows 0 / H-1 are classified as raster-edge cells; for ghost rows the caller overwrites them
+    flats_classify_kernel<<<s->blocks(), 256, 0, c.stream>>>(d_dem, s->ft.p, width, height, nodata, s->dev.p);
+    RDB_CK(cudaGetLastError());
+    RDB_CK(cudaStreamSynchronize(c.stream));
+  } catch (...) {
+    delete s;
+    throw;
+  }
+  *state = s;
+  FLATS_END
+}
+
+// device addresses of the state arrays the caller moves across seams:
+//   out[0] flags (uint8 H x W: bit0 flat, bit1 low edge, bit2 high edge, bit3 NoData)
+//   out[1] root of every cell's equal-elevation component, later its label (int32 H x W)
+//   out[2] outlet flag per root (uint8, indexed by cell index of the root)
+//   out[3] away levels, out[4] towards levels (int32 H x W), out[5] flat height per root (int32)
+int rdb200_dev_flats_arrays(rdb200_flats_state *s, uint64_t *out6) {
+  FLATS_TRY
+  if (!s || !out6) rdb::fail("flats_arrays: null pointer");
+  out6[0] = (uint64_t)s->ft.p;
+  out6[1] = (uint64_t)s->labels.p;
+  out6[2] = (uint64_t)s->rootflag.p;
+  out6[3] = (uint64_t)s->away.p;
+  out6[4] = (uint64_t)s->tw.p;
+  out6[5] = (uint64_t)s->Hh.p;
+  FLATS_END
+}
+
+int rdb200_dev_flats_edges(rdb200_flats_state *s) {
+  FLATS_TRY
+  using namespace rdb;
+  Ctx &c = ctx();
+  flats_edges_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->dem, s->ft.p, s->W, s->H, s->dev.p);
+  RDB_CK(cudaGetLastError());
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  FLATS_END
+}
+
+int rdb200_dev_flats_components(rdb200_flats_state *s) {
+  FLATS_TRY
+  using namespace rdb;
+  Ctx &c = ctx();
+  const size_t n = s->n();
+  uf_init_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->parent.p, n);
+  uf_union_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->dem, s->ft.p, s->parent.p, s->W, s->H);
+  uf_roots_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->ft.p, s->parent.p, s->labels.p, s->rootflag.p, n);
+  RDB_CK(cudaGetLastError());
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  FLATS_END
+}
+
+int rdb200_dev_flats_labels(rdb200_flats_state *s) {
+  FLATS_TRY
+  using namespace rdb;
+  Ctx &c = ctx();
+  make_labels_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->rootflag.p, s->ft.p, s->labels.p, s->n());
+  RDB_CK(cudaGetLastError());
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  FLATS_END
+}
+
+int rdb200_dev_flats_gradient_begin(rdb200_flats_state *s, int32_t away, rdb200_fill_state **dist_state) {
+  FLATS_TRY
+  using namespace rdb;
+  Ctx &c = ctx();
+  if (!dist_state) fail("flats_gradient_begin: null pointer");
+  int *dist = away ? s->away.p : s->tw.p;
+  gradient_seed_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->dem, s->ft.p, s->labels.p, reinterpret_cast<float *>(dist),
+                                                          s->W, s->H, away ? 1 : 0);
+  RDB_CK(cudaGetLastError());
+  *dist_state = new_band_distance_state(s->ft.p, FT_FLAT, reinterpret_cast<const float *>(dist), s->W, s->H, s->gt, s->gb);
+  FLATS_END
+}
+
+int rdb200_dev_flats_gradient_end(rdb200_flats_state *s, int32_t away, rdb200_fill_state *dist_state) {
+  FLATS_TRY
+  using namespace rdb;
+  Ctx &c = ctx();
+  int *dist = away ? s->away.p : s->tw.p;
+  finish_band_distance_state(dist_state, reinterpret_cast<float *>(dist));
+  gradient_convert_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->ft.p, s->labels.p, dist, s->Hh.p, s->n(), away ? 1 : 0);
+  RDB_CK(cudaGetLastError());
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  FLATS_END
+}
+
+int rdb200_dev_flats_apply(rdb200_flats_state *s) {
+  FLATS_TRY
+  using namespace rdb;
+  Ctx &c = ctx();
+  flats_apply_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->dem, s->labels.p, s->away.p, s->tw.p, s->Hh.p, nullptr, nullptr,
+                                                        s->W, s->H, 1, s->dev.p);
+  RDB_CK(cudaGetLastError());
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  FLATS_END
+}
+
+int rdb200_dev_flats_finish(rdb200_flats_state *s) {
+  FLATS_TRY
+  if (s) {
+    RDB_CK(cudaStreamSynchronize(rdb::ctx().stream));
+    delete s;
+  }
+  FLATS_END
+}
+
+}  // extern "C"

@@ -154,36 +154,7 @@ def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None
     if g_bot:
         local_dem[h - 1].fill_(float("inf"))
     solver = solver_cls(local_dem)
-    rounds = 0
-    while True:
-        changed = solver.run()   # bits 0/1: my edge rows changed; bit 2: tiles still active (bounded run)
-        rounds += 1
-        if world == 1:
-            if changed & 4:
-                continue
-            break
-        # rows my neighbours hold as ghosts: local row 1 (if there is a band above), row h-2 (below)
-        my_change = 0
-        if g_top and (changed & 1 or rounds == 1):
-            my_change = 1
-        if g_bot and (changed & 2 or rounds == 1):
-            my_change = 1
-        flag = torch.tensor([my_change, 1 if (changed & 4) else 0], dtype=torch.int32, device=local_dem.device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)  # (NCCL has no bitwise-or reduction)
-        any_edge, any_active = (int(v) for v in flag.tolist())
-        if not any_edge and not any_active:
-            break
-        if not any_edge:
-            continue  # someone is still relaxing but no edge row moved: nothing to exchange
-        send_up = solver.read_row(1) if g_top else None
-        send_dn = solver.read_row(h - 2) if g_bot else None
-        recv_up, recv_dn = _neighbour_exchange(send_up, send_dn, g_top, g_bot, rank, group)
-        if recv_up is not None:
-            solver.update_row(0, recv_up[0])
-        if recv_dn is not None:
-            solver.update_row(h - 1, recv_dn[0])
-        if rounds >= max_rounds:
-            raise RuntimeError("fill_band: exchange rounds exceeded max_rounds")
+    rounds = _relax_band(solver, g_top, g_bot, rank, world, group, max_rounds)
     out = solver.finish()
     if return_stats:
         from . import _lib
@@ -301,3 +272,227 @@ def scatter_rows(full: Optional[np.ndarray], height: int, width: int, dtype, dev
     else:
         dist.recv(local, 0, group)
     return local, (r0, r1, gt, gb)
+
+
+# =================================================================================================
+# Row-band flat resolution (ResolveFlatsEpsilon over bands)
+# =================================================================================================
+class _DevArray:
+    """Zero-copy torch view of a device array owned by librichdem_b200 (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def _view(ptr, shape, typestr, device):
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device=device)
+
+
+class CudaFlatsBand:
+    """Stepwise row-band flat resolution on one GPU (rdb200_dev_flats_*).  `local_dem` is the
+    (g_top + owned + g_bot) x W float32 raster with the neighbours' rows in the ghost rows; the owned
+    rows are modified in place by :meth:`apply`."""
+
+    FT_FLAT, FT_LOW, FT_HIGH, FT_NODATA = 1, 2, 4, 8
+
+    def __init__(self, local_dem, nodata: float, g_top: int, g_bot: int):
+        from . import _lib
+        assert local_dem.is_cuda and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
+        self._lib, self.L = _lib, _lib.lib()
+        _lib.use_torch_stream()
+        self.h, self.w = local_dem.shape
+        self.gt, self.gb = int(g_top), int(g_bot)
+        self.dev = local_dem.device
+        self._dem = local_dem
+        self._state = C.c_void_p()
+        _lib.check(self.L.rdb200_dev_flats_begin(C.byref(self._state), local_dem.data_ptr(), self.w, self.h,
+                                                 float(nodata), self.gt, self.gb))
+        ptrs = (C.c_uint64 * 6)()
+        _lib.check(self.L.rdb200_dev_flats_arrays(self._state, ptrs))
+        n = self.h * self.w
+        self.ft = _view(ptrs[0], (self.h, self.w), "|u1", self.dev)
+        self.root = _view(ptrs[1], (self.h, self.w), "<i4", self.dev)    # later: labels
+        self.rootflag = _view(ptrs[2], (n,), "|u1", self.dev)
+        self.height = _view(ptrs[5], (n,), "<i4", self.dev)
+
+    # rows that face a neighbour: (my edge row, my ghost row) per side
+    def rows(self, which: int):
+        return (self.gt, 0) if which == 0 else (self.h - 1 - self.gb, self.h - 1)
+
+    def step(self, name: str):
+        self._lib.check(getattr(self.L, "rdb200_dev_flats_" + name)(self._state))
+
+    def gradient_begin(self, away: bool):
+        st = C.c_void_p()
+        self._lib.check(self.L.rdb200_dev_flats_gradient_begin(self._state, int(away), C.byref(st)))
+        return _BandStateSolver(st, self.h, self.w, self.dev)
+
+    def gradient_end(self, away: bool, solver: "_BandStateSolver"):
+        self._lib.check(self.L.rdb200_dev_flats_gradient_end(self._state, int(away), solver._state))
+        solver._state = None
+
+    def finish(self):
+        self._lib.check(self.L.rdb200_dev_flats_finish(self._state))
+        self._state = None
+
+    # ---- seam payloads (comm-agnostic; used by the NCCL driver and by the single-GPU emulation) ----
+    def flag_payload(self, which: int):
+        """uint8 rows [edge, ghost]: outlet flag of the component of every seam cell."""
+        e, g = self.rows(which)
+        f32 = self.rootflag
+        return torch.stack([f32[self.root[e].long()], f32[self.root[g].long()]])
+
+    def merge_flags(self, which: int, theirs) -> bool:
+        """theirs = neighbour's flag_payload for the shared seam: their edge row is my ghost row and
+        their ghost row is my edge row.  ORs their flags into my roots; True if anything changed."""
+        e, g = self.rows(which)
+        changed = False
+        for my_row, their in ((g, theirs[0]), (e, theirs[1])):
+            ok = (self.ft[my_row] & self.FT_NODATA) == 0
+            idx = self.root[my_row].long()[ok]
+            val = their[ok]
+            before = self.rootflag[idx]
+            need = (val != 0) & (before == 0)
+            if bool(need.any()):
+                self.rootflag[idx[need]] = 1
+                changed = True
+        return changed
+
+    def height_payload(self, which: int):
+        """int32 rows [edge, ghost]: flat height (max away level) of the flat of every seam cell (0: none)."""
+        e, g = self.rows(which)
+        out = []
+        for r in (e, g):
+            lab = self.root[r].long()      # holds labels now (root + 1, 0 = none)
+            hv = self.height[(lab - 1).clamp(min=0)]
+            out.append(torch.where(lab > 0, hv, torch.zeros_like(hv)))
+        return torch.stack(out)
+
+    def merge_heights(self, which: int, theirs) -> bool:
+        e, g = self.rows(which)
+        changed = False
+        for my_row, their in ((g, theirs[0]), (e, theirs[1])):
+            lab = self.root[my_row].long()
+            ok = lab > 0
+            if not bool(ok.any()):
+                continue
+            idx = (lab[ok] - 1)
+            val = their[ok].to(torch.int32)
+            before = self.height[idx]
+            if bool((val > before).any()):
+                self.height.scatter_reduce_(0, idx, val, reduce="amax", include_self=True)
+                changed = True
+        return changed
+
+
+class _BandStateSolver:
+    """An existing rdb200_fill_state (here: a band distance state) behind the band-solver interface."""
+
+    def __init__(self, state, h, w, device):
+        from . import _lib
+        self._lib, self._state, self.h, self.w, self.device = _lib, state, h, w, device
+
+    def run(self) -> int:
+        ch = C.c_int32(0)
+        self._lib.check(self._lib.lib().rdb200_dev_fill_run(self._state, C.byref(ch)))
+        return int(ch.value)
+
+    def read_row(self, y: int):
+        row = torch.empty(self.w, dtype=torch.float32, device=self.device)
+        self._lib.check(self._lib.lib().rdb200_dev_fill_read_row(self._state, y, row.data_ptr()))
+        return row
+
+    def update_row(self, y: int, row):
+        self._lib.check(self._lib.lib().rdb200_dev_fill_update_row(self._state, y, row.contiguous().data_ptr()))
+
+
+def _relax_band(solver, g_top, g_bot, rank, world, group, max_rounds=100000):
+    """The row-band relaxation protocol shared by the fill and the flat-resolution gradients."""
+    h = solver.h
+    rounds = 0
+    while True:
+        changed = solver.run()
+        rounds += 1
+        if world == 1:
+            if changed & 4:
+                continue
+            return rounds
+        my_change = 0
+        if g_top and (changed & 1 or rounds == 1):
+            my_change = 1
+        if g_bot and (changed & 2 or rounds == 1):
+            my_change = 1
+        dev = getattr(solver, "device", "cpu")
+        flag = torch.tensor([my_change, 1 if (changed & 4) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        any_edge, any_active = (int(v) for v in flag.tolist())
+        if not any_edge and not any_active:
+            return rounds
+        if not any_edge:
+            continue
+        send_up = solver.read_row(1) if g_top else None
+        send_dn = solver.read_row(h - 2) if g_bot else None
+        recv_up, recv_dn = _neighbour_exchange(send_up, send_dn, g_top, g_bot, rank, group)
+        if recv_up is not None:
+            solver.update_row(0, recv_up[0])
+        if recv_dn is not None:
+            solver.update_row(h - 1, recv_dn[0])
+        if rounds >= max_rounds:
+            raise RuntimeError("band relaxation: exchange rounds exceeded max_rounds")
+
+
+def resolve_flats_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, nodata: float, group=None):
+    """ResolveFlatsEpsilon over this rank's band, in place on the owned rows of ``local_dem`` (whose
+    ghost rows must hold the neighbours' elevation rows).  Collective.  Returns the number of seam
+    iterations (flags + heights)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    F = CudaFlatsBand(local_dem, nodata, g_top, g_bot)
+
+    def exchange_ft():
+        if world == 1:
+            return
+        up = F.ft[F.rows(0)[0]].contiguous() if g_top else None
+        dn = F.ft[F.rows(1)[0]].contiguous() if g_bot else None
+        ru, rd = _neighbour_exchange(up, dn, g_top, g_bot, rank, group)
+        if ru is not None:
+            F.ft[0].copy_(ru[0])
+        if rd is not None:
+            F.ft[F.h - 1].copy_(rd[0])
+
+    def merge_until_stable(payload, merge):
+        it = 0
+        while world > 1:
+            it += 1
+            up = payload(0) if g_top else None
+            dn = payload(1) if g_bot else None
+            ru, rd = _neighbour_exchange(up, dn, g_top, g_bot, rank, group)
+            ch = False
+            if ru is not None:
+                ch |= merge(0, ru[0])
+            if rd is not None:
+                ch |= merge(1, rd[0])
+            flag = torch.tensor([1 if ch else 0], dtype=torch.int32, device=local_dem.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if int(flag.item()) == 0:
+                break
+        return it
+
+    exchange_ft()               # IS_A_FLAT / NoData of the ghost rows
+    F.step("edges")
+    exchange_ft()               # low / high edge bits of the ghost rows
+    F.step("components")
+    iters = merge_until_stable(F.flag_payload, F.merge_flags)
+    F.step("labels")
+    for away in (True, False):
+        solver = F.gradient_begin(away)
+        from . import _lib
+        _lib.set_param("fill_band_rounds", 64 if world > 1 else 0)
+        _relax_band(solver, g_top, g_bot, rank, world, group)
+        F.gradient_end(away, solver)
+        if away:
+            iters += merge_until_stable(F.height_payload, F.merge_heights)
+    F.step("apply")
+    F.finish()
+    return iters

@@ -135,3 +135,119 @@ def test_band_accumulation_with_weights(checker):
     wts = np.random.default_rng(1).random(dem.shape)
     got, _ = emulate_fa_bands(dem, 4, nd, False, weights=wts)
     np.testing.assert_allclose(got, checker.fa_d8(dem, nd, wts), rtol=1e-9, atol=0)
+
+
+# ---- row-band flat resolution: G bands on one device, same seam protocol as sharded.resolve_flats_band ----
+def _relax_emulated(solvers, metas):
+    rounds = 0
+    while True:
+        changed = [s.run() for s in solvers]
+        rounds += 1
+        any_edge = any((m[2] and ((c & 1) or rounds == 1)) or (m[3] and ((c & 2) or rounds == 1))
+                       for c, m in zip(changed, metas))
+        any_active = any(c & 4 for c in changed)
+        if not any_edge and not any_active:
+            return rounds
+        if not any_edge:
+            continue
+        ups = {g: solvers[g].read_row(1) for g, m in enumerate(metas) if m[2]}
+        dns = {g: solvers[g].read_row(m[4] - 2) for g, m in enumerate(metas) if m[3]}
+        for g, m in enumerate(metas):
+            if m[2]:
+                solvers[g].update_row(0, dns[g - 1])
+            if m[3]:
+                solvers[g].update_row(m[4] - 1, ups[g + 1])
+        assert rounds < 10000
+
+
+def emulate_flats_bands(dem: np.ndarray, G: int, nodata: float):
+    import torch
+    h, w = dem.shape
+    F, metas, locals_ = [], [], []
+    for g in range(G):
+        r0, r1, gt, gb = sharded.local_rows(h, G, g)
+        local = torch.from_numpy(np.ascontiguousarray(dem[r0 - gt:r1 + gb])).cuda().contiguous()
+        locals_.append(local)
+        F.append(sharded.CudaFlatsBand(local, nodata, gt, gb))
+        metas.append((r0, r1, gt, gb, local.shape[0]))
+
+    def exchange_ft():
+        rows = [(f.ft[f.rows(0)[0]].clone(), f.ft[f.rows(1)[0]].clone()) for f in F]
+        for g, m in enumerate(metas):
+            if m[2]:
+                F[g].ft[0].copy_(rows[g - 1][1])
+            if m[3]:
+                F[g].ft[m[4] - 1].copy_(rows[g + 1][0])
+
+    def merge(payload, apply):
+        iters = 0
+        while G > 1:
+            iters += 1
+            pay = [(getattr(f, payload)(0) if m[2] else None, getattr(f, payload)(1) if m[3] else None)
+                   for f, m in zip(F, metas)]
+            ch = False
+            for g, m in enumerate(metas):
+                if m[2]:
+                    ch |= getattr(F[g], apply)(0, pay[g - 1][1])
+                if m[3]:
+                    ch |= getattr(F[g], apply)(1, pay[g + 1][0])
+            if not ch:
+                break
+            assert iters < 100
+        return iters
+
+    exchange_ft()
+    for f in F:
+        f.step("edges")
+    exchange_ft()
+    for f in F:
+        f.step("components")
+    it1 = merge("flag_payload", "merge_flags")
+    for f in F:
+        f.step("labels")
+    it2 = 0
+    for away in (True, False):
+        solvers = [f.gradient_begin(away) for f in F]
+        _relax_emulated(solvers, metas)
+        for f, s in zip(F, solvers):
+            f.gradient_end(away, s)
+        if away:
+            it2 = merge("height_payload", "merge_heights")
+    out = np.empty_like(dem)
+    for g, (r0, r1, gt, gb, lh) in enumerate(metas):
+        F[g].step("apply")
+        F[g].finish()
+        out[r0:r1] = locals_[g][gt:gt + (r1 - r0)].cpu().numpy()
+    return out, it1, it2
+
+
+@pytest.mark.parametrize("G", [1, 2, 3, 5, 8])
+def test_band_flat_resolution_equals_single(checker, G):
+    nd = -9999.0
+    dem = oracle.fbm_terrain(640, 520, seed=51, quantum=0.5)
+    dem[300:330, 100:180] = nd
+    filled = checker.fill_depressions(dem)
+    expected = checker.resolve_flats(filled, nd)
+    assert (expected != filled).mean() > 0.05
+    got, it1, it2 = emulate_flats_bands(filled, G, nd)
+    bad = (got.view(np.uint32) != expected.view(np.uint32)).sum()
+    assert bad == 0, f"G={G}: {bad} cells differ (flag iterations {it1}, height iterations {it2})"
+
+
+def test_band_flat_resolution_snaking_flat(checker):
+    """One flat that crosses every seam several times (a comb), so outlet flags and flat heights have
+    to travel through several seam iterations."""
+    nd = -9999.0
+    dem = np.full((96, 64), 10.0, np.float32)
+    dem[:, ::4] = 5.0                      # vertical channels at elevation 5 ...
+    dem[2, :] = 5.0                        # ... joined at the top
+    dem[93, 1::8] = 5.0
+    dem[0, :] = dem[-1, :] = 20.0
+    dem[:, 0] = dem[:, -1] = 20.0
+    dem[94, 4] = 1.0                       # a single outlet near the bottom
+    dem[95, 4] = 0.0
+    filled = checker.fill_depressions(dem)
+    expected = checker.resolve_flats(filled, nd)
+    for G in (2, 4, 6):
+        got, it1, it2 = emulate_flats_bands(filled, G, nd)
+        assert np.array_equal(got.view(np.uint32), expected.view(np.uint32)), (G, it1, it2)

@@ -23,25 +23,34 @@ for (H, W, q) in [(3000, 2000, 0.5), (8192, 8192, 0.0)]:
     torch.cuda.synchronize(); dist.barrier(); t = time.time()
     filled, frounds = sharded.fill_band(loc.clone(), gt, gb)
     torch.cuda.synchronize(); dist.barrier(); tf = time.time() - t; t = time.time()
+    own_f = filled[gt:gt + (r1 - r0)].clone()
+    # flat resolution over bands (in place), then refresh the ghost rows with the neighbours' resolved rows
+    seam_iters = sharded.resolve_flats_band(filled, gt, gb, ND)
+    sharded.exchange_rows(filled, gt, gb)
+    torch.cuda.synchronize(); dist.barrier(); tz = time.time() - t; t = time.time()
+    own_r = filled[gt:gt + (r1 - r0)].clone()
     acc, arounds = sharded.fa_band(filled, gt, gb, ND, dinf=False)
     torch.cuda.synchronize(); dist.barrier(); ta = time.time() - t; t = time.time()
     accinf, irounds = sharded.fa_band(filled, gt, gb, ND, dinf=True)
     torch.cuda.synchronize(); dist.barrier(); ti = time.time() - t
     # single-GPU truth on rank 0
-    own_f = filled[gt:gt + (r1 - r0)].contiguous(); own_a = acc[gt:gt + (r1 - r0)].contiguous()
+    own_a = acc[gt:gt + (r1 - r0)].contiguous()
     own_i = accinf[gt:gt + (r1 - r0)].contiguous()
     if rank == 0:
         full = torch.empty((H, W), dtype=torch.float32, device="cuda")
         _lib.check(L.rdb200_dev_generate_fbm_f32(full.data_ptr(), W, H, 0, 7, 12, q))
         _lib.check(L.rdb200_dev_fill_depressions_d8_f32(full.data_ptr(), W, H))
+        full_filled = full.clone()
+        _lib.check(L.rdb200_dev_resolve_flats_epsilon_f32(full.data_ptr(), W, H, ND))
         a1 = torch.empty((H, W), dtype=torch.float64, device="cuda")
         _lib.check(L.rdb200_dev_fa_d8_f32_f64(full.data_ptr(), a1.data_ptr(), W, H, ND, 1))
         a2 = torch.empty((H, W), dtype=torch.float64, device="cuda")
         _lib.check(L.rdb200_dev_fa_tarboton_f32_f64(full.data_ptr(), a2.data_ptr(), W, H, ND, 1))
     ok = {}
-    for name, own, dtype in (("fill", own_f, torch.float32), ("fa_d8", own_a, torch.float64), ("fa_dinf", own_i, torch.float64)):
+    for name, own, dtype in (("fill", own_f, torch.float32), ("flats", own_r, torch.float32), ("fa_d8", own_a, torch.float64),
+                             ("fa_dinf", own_i, torch.float64)):
         if rank == 0:
-            ref = {"fill": full, "fa_d8": a1, "fa_dinf": a2}[name]
+            ref = {"fill": full_filled, "flats": full, "fa_d8": a1, "fa_dinf": a2}[name]
             good = True
             for g in range(world):
                 b0, b1, _, _ = sharded.local_rows(H, world, g)
@@ -58,7 +67,7 @@ for (H, W, q) in [(3000, 2000, 0.5), (8192, 8192, 0.0)]:
         else:
             dist.send(own, 0)
     if rank == 0:
-        case = {"H": H, "W": W, "q": q, "ok": ok, "fill_s": tf, "fa_d8_s": ta, "fa_dinf_s": ti,
+        case = {"H": H, "W": W, "q": q, "ok": ok, "fill_s": tf, "flats_s": tz, "flats_seam_iters": seam_iters, "fa_d8_s": ta, "fa_dinf_s": ti,
                 "fill_exchange_rounds": frounds, "fa_d8_rounds": arounds, "fa_dinf_rounds": irounds}
         print(json.dumps(case), flush=True)
         res["cases"].append(case)
