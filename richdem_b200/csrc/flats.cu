@@ -334,8 +334,11 @@ __global__ void __launch_bounds__(256) gradient_seed_kernel(const float *__restr
     const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
     const float e = __ldg(dem + i);
 #pragma unroll
-    for (int k = 1; k <= 8; k++) {  // flat cells are interior cells: all 8 neighbours exist
-      const size_t ni = (size_t)(y + d8dy(k)) * W + (x + d8dx(k));
+    for (int k = 1; k <= 8; k++) {
+      // (flat cells are interior cells of the raster, but in a row band a ghost row can hold them)
+      const int nx = x + d8dx(k), ny = y + d8dy(k);
+      if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
+      const size_t ni = (size_t)ny * W + nx;
       if ((ft[ni] & FT_LOW) && __ldg(dem + ni) == e) w0 = 2.0f;
     }
   }
