@@ -12,14 +12,19 @@
 // persistent kernel launch that walks a compacted worklist of active tiles; for each tile it
 //   1. stages W (with a one-cell apron) and Z into shared memory with two TMA tile loads
 //      (cp.async.bulk.tensor.2d + mbarrier),
-//   2. relaxes the tile to its local fixed point entirely in shared memory / registers
-//      (each thread owns a 4x4 block in registers and runs forward+backward Gauss-Seidel
-//      passes over it, exchanging only block rims through shared memory),
-//   3. writes W back with coalesced float4 stores if anything changed, and
-//   4. appends the neighbouring tiles whose apron it changed to the next round's worklist.
+//   2. relaxes the tile to its local fixed point entirely in shared memory / registers: a
+//      compacted list of dirty 4x4 blocks is kept in shared memory; every pass hands one dirty
+//      block to a thread, which runs a forward+backward Gauss-Seidel pass over its 16 cells in
+//      registers and marks the blocks that read what it changed,
+//   3. writes the changed block rows back with coalesced float4 stores, and
+//   4. appends the neighbouring tiles whose apron it changed to the next round's worklist,
+//      together with the apron side(s) that changed and the lowest water level that arrived.
 // Between tiles the iteration is chaotic (asynchronous Jacobi); every value ever stored is an
 // upper bound of the answer and updates are monotone, so any schedule converges to the same
 // fixed point.  The device-wide "anything changed" signal is the next worklist's length.
+// fill_admit_kernel orders the flood by rising water level; the same engine
+// with the "+1" operator (fill_sweep_kernel<1>) computes the geodesic distances of the flat
+// resolution (csrc/flats.cu), and FillState doubles as the row-band (multi-GPU) solver.
 #include "common.cuh"
 
 namespace rdb {
