@@ -412,9 +412,11 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
 // single-file reaches cost no extra levels, while every other cell it completes -- and its own
 // continuation when the budget runs out -- is appended (coalesced-group atomics) to the next
 // frontier, where other threads pick it up in parallel.  Levels meet at grid.sync().
-template <int MODE>
+// BAND (row bands, D-infinity): level 0 can be seeded with the cells completed by a neighbour's flow
+// (q0[0..ncells), seeded != 0) and flow into a ghost row is parked there instead of followed.
+template <int MODE, bool BAND = false>
 __global__ void __launch_bounds__(256) accum_levels_kernel(const WalkArgs<double> a, int *q0, int *q1, int *counts,
-                                                            int ncells, int budget, int *levels_out) {
+                                                            int ncells, int budget, int *levels_out, int seeded) {
   cg::grid_group grid = cg::this_grid();
   const int W = a.W;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(256) accum_levels_kernel(const WalkArgs<double
     };
     for (int idx = gtid; idx < n; idx += gsize) {
       int c;
-      if (level == 0) {
+      if (level == 0 && !(BAND && seeded)) {
         c = idx;
         if (!(a.st[c] & kSrcFlag)) continue;
       } else {
@@ -455,15 +457,20 @@ __global__ void __launch_bounds__(256) accum_levels_kernel(const WalkArgs<double
               float p1, p2;
               tarboton_props(a.rmaxArr[c], &p1, &p2);
               // generic.hpp:87  accum(ni) += props(ci,n)*c_accum  (float * double)
-              if (p1 > 0) atomicAdd(a.accum + r1, (double)p1 * acc);
-              if (p2 > 0) atomicAdd(a.accum + r2, (double)p2 * acc);
+              bool live1 = p1 > 0, live2 = p2 > 0;
+              if (BAND) {
+                if (live1 && park_in_ghost(a, r1, (double)p1 * acc)) live1 = false;
+                if (live2 && park_in_ghost(a, r2, (double)p2 * acc)) live2 = false;
+              }
+              if (live1) atomicAdd(a.accum + r1, (double)p1 * acc);
+              if (live2) atomicAdd(a.accum + r2, (double)p2 * acc);
               __threadfence();
-              if (p1 > 0 && (atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
-              if (p2 > 0 && (atomicSub(a.st + r2, 1u) & kDepsMask) == 1u) {
+              if (live1 && (atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
+              if (live2 && (atomicSub(a.st + r2, 1u) & kDepsMask) == 1u) {
                 if (next < 0) next = r2;
                 else push(r2);
               }
-            } else {
+            } else if (!(BAND && park_in_ghost(a, r1, acc))) {
               atomicAdd(a.accum + r1, acc);
               __threadfence();
               if ((atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
@@ -522,7 +529,9 @@ void run_levels(WalkArgs<double> a, size_t ncells) {
   const int grid = c.num_sms * per_sm;
   int *q0 = fr0.p, *q1 = fr1.p, *counts = cnt.p, *lv = cnt.p + 3;
   int nc = (int)ncells, budget = (int)(c.params.accum_budget > 0 ? c.params.accum_budget : 4);
-  void *args[] = {(void *)&a, (void *)&q0, (void *)&q1, (void *)&counts, (void *)&nc, (void *)&budget, (void *)&lv};
+  int seeded = 0;
+  void *args[] = {(void *)&a,      (void *)&q0, (void *)&q1,    (void *)&counts,
+                  (void *)&nc,     (void *)&budget, (void *)&lv, (void *)&seeded};
   KernelTimer kt;
   RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_levels_kernel<MODE>, dim3(grid), dim3(256), args, 0, c.stream));
   count_launch();
@@ -1045,8 +1054,27 @@ struct FaccState {
       a.next_frontier = fr1.p;
     }
     RDB_CK(cudaMemsetAsync(cnt.p, 0, 2 * sizeof(int), c.stream));
-    if (dinf) walk<1>(a);
-    else walk<0>(a);
+    if (dinf) {
+      // one cooperative launch: levels of the frontier inside the band (accum_levels_kernel)
+      DevBuf<int> lc(4);
+      RDB_CK(cudaMemsetAsync(lc.p, 0, 4 * sizeof(int), c.stream));
+      int per_sm = 0;
+      RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_levels_kernel<1, true>, 256, 0));
+      if (per_sm < 1) per_sm = 1;
+      const int grid = c.num_sms * per_sm;
+      int *q0 = fr0.p, *q1 = fr1.p, *counts = lc.p, *lv = lc.p + 3;
+      int seeded = a.frontier ? 1 : 0;
+      int nc = a.nfrontier, budget = (int)(c.params.accum_budget > 0 ? c.params.accum_budget : 4);
+      if (nc > 0) {
+        void *args[] = {(void *)&a,  (void *)&q0,     (void *)&q1, (void *)&counts,
+                        (void *)&nc, (void *)&budget, (void *)&lv, (void *)&seeded};
+        RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_levels_kernel<1, true>, dim3(grid), dim3(256), args, 0,
+                                           c.stream));
+        count_launch();
+      }
+    } else {
+      walk<0>(a);
+    }
     n_frontier = 0;
     rounds++;
     // how much left the band?
