@@ -111,3 +111,34 @@ def test_cxx_dropin_header_links_and_fails_loudly_without_gpu():
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout[-2000:]
     assert "calls=9 thrown=9" in out.stdout
+
+
+def test_header_and_ctypes_table_agree_on_arity():
+    """Every prototype in include/richdem_b200.h has as many parameters as its ctypes signature."""
+    header = open(os.path.join(ROOT, "include", "richdem_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"RDB200_API\s+[\w\s\*]+?\b(rdb200_\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 40
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        if name in _lib.SIGNATURES:
+            assert n == len(_lib.SIGNATURES[name]), (name, n, len(_lib.SIGNATURES[name]))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs on CPU only and prints one JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "384",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "Mcells/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
