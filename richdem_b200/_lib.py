@@ -95,6 +95,12 @@ def lib():
                 f"{LIB_PATH} not found: build it with `python -m richdem_b200.build` "
                 "(there is no CPU fallback)")
         L = C.CDLL(LIB_PATH)
+        if hasattr(L, "rdb200_emulated"):
+            # tests/emu builds the kernel sources for a CPU fiber model to check their logic; it is
+            # test infrastructure, never a compute path
+            raise RichdemB200Error(
+                f"{LIB_PATH} is the CPU kernel-emulation test build, not librichdem_b200 "
+                "(there is no CPU fallback)")
         for name, argtypes in SIGNATURES.items():
             f = getattr(L, name)
             f.argtypes = argtypes

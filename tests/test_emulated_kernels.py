@@ -1,0 +1,127 @@
+"""Kernel-logic parity WITHOUT a GPU: the shipped CUDA sources (richdem_b200/csrc/*.cu, unmodified) are
+rewritten against a single-threaded fiber model of CUDA (tests/emu/) and compiled with g++ into
+tests/_bin/librdb200_emu_test.so; the GPU parity tests' own checks are then run against that library.
+
+This is test infrastructure, not a backend: the product loader (richdem_b200/_lib.py) refuses to load
+the emulation build, and only this module -- by swapping the already-loaded library handle inside a
+fixture -- ever points the Python layer at it.  It checks the kernels' logic (worklists, dirty-block
+lists, union-find, dependency counters, level schedules, band protocols); it cannot say anything about
+TMA staging, memory ordering, races or speed -- the `-m gpu` suite on the B200 remains the parity gate.
+"""
+import ctypes as C
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from richdem_b200 import _lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load_module(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    if sys.platform != "linux" or os.uname().machine != "x86_64":
+        pytest.skip("the fiber switch of tests/emu is x86-64 SysV only")
+    build_emu = _load_module("build_emu", os.path.join(HERE, "emu", "build_emu.py"))
+    path = build_emu.build()
+    L = C.CDLL(str(path))
+    assert L.rdb200_emulated() == 1
+    for name, argtypes in _lib.SIGNATURES.items():
+        f = getattr(L, name)
+        f.argtypes = argtypes
+        f.restype = C.c_int
+    L.rdb200_last_error.restype = C.c_char_p
+    L.rdb200_last_error.argtypes = []
+    L.rdb200_version.restype = C.c_int
+    L.rdb200_shutdown.restype = None
+    return L
+
+
+@pytest.fixture()
+def emulated(emu_lib, monkeypatch):
+    """Point the Python layer at the emulation for ONE test, then restore the real (absent) handle."""
+    monkeypatch.setattr(_lib, "_lib", emu_lib)
+    _lib.init(0)
+    _lib.set_param("fill_use_tma", 0)  # TMA / mbarrier PTX is not emulated
+    yield emu_lib
+    for name, value in (("fill_ordered", 1), ("fill_max_iters", 0), ("fill_rounds_per_sync", 16), ("flats_tiled", 1),
+                        ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0)):
+        _lib.set_param(name, value)
+
+
+@pytest.fixture(scope="module")
+def gp():
+    return _load_module("gpu_parity_checks", os.path.join(HERE, "test_gpu_parity.py"))
+
+
+def test_loader_refuses_the_emulation_build(emu_lib, monkeypatch):
+    build_emu = sys.modules.get("build_emu") or _load_module("build_emu", os.path.join(HERE, "emu", "build_emu.py"))
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(build_emu.LIB))
+    with pytest.raises(_lib.RichdemB200Error, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_golden_fixtures(emulated, gp, golden):
+    gp.test_fill_known_answer(golden)
+    gp.test_d8_flow_accum_known_answers(golden)
+    gp.test_data_dems(golden)
+    gp.test_synthetic_golden(golden)
+
+
+def test_beauford_crop(emulated, gp, golden):
+    gp.test_beauford_crop_golden(golden)
+
+
+@pytest.mark.parametrize("shape,seed,q,patch", [
+    ((150, 220), 1, None, False), ((257, 131), 2, 0.5, False), ((400, 500), 3, 2.0, True),
+    ((65, 129), 4, 1.0, False), ((64, 64), 5, 10.0, False), ((63, 200), 6, None, True),
+])
+def test_pipeline_vs_oracle(emulated, gp, checker, shape, seed, q, patch):
+    gp.test_pipeline_vs_oracle(checker, shape, seed, q, patch)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 7), (2, 2), (3, 3), (3, 64), (5, 1), (4, 130)])
+def test_degenerate_shapes(emulated, gp, checker, shape):
+    gp.test_degenerate_shapes(checker, shape)
+
+
+def test_special_rasters(emulated, gp, checker):
+    gp.test_special_rasters(checker)
+
+
+def test_in_place_and_copy_semantics(emulated, gp):
+    gp.test_in_place_and_copy_semantics()
+
+
+@pytest.mark.parametrize("param,value", [
+    ("fill_ordered", 0), ("fill_max_iters", 1), ("fill_max_iters", 2), ("fill_rounds_per_sync", 1), ("fill_order_rounds", 40),
+    ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
+])
+def test_algorithm_variants_agree(emulated, gp, checker, param, value):
+    """Every tunable is a schedule / layout choice; none may change a result."""
+    _lib.set_param(param, value)
+    dem = oracle.fbm_terrain(300, 420, seed=17, quantum=0.5)
+    dem[40:70, 100:180] = gp.ND
+    gp.check_pipeline(dem, gp.ND, checker)
+
+
+def test_level_schedule_engages_and_matches(emulated, gp, checker):
+    """A raster wide enough (>= 10 tiles across) for the level-ordered admission to be active."""
+    import richdem_b200 as rd
+    dem = oracle.fbm_terrain(200, 900, seed=23)
+    got = np.asarray(rd.FillDepressions(gp.R(dem)))
+    assert np.array_equal(got, checker.fill_depressions(dem))
+    s = _lib.stats()
+    assert s["fill_tile_visits"] > 0 and s["fill_rounds"] > 0
