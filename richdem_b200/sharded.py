@@ -56,12 +56,17 @@ def local_rows(height: int, world: int, rank: int) -> Tuple[int, int, int, int]:
     return r0, r1, (1 if rank > 0 else 0), (1 if rank < world - 1 else 0)
 
 
+def _on_device(t) -> bool:
+    """Band state lives in HBM: every tensor handed to the rdb200_dev_* entry points must be a CUDA tensor."""
+    return bool(t.is_cuda)
+
+
 class CudaBandSolver:
     """The product band solver: librichdem_b200's row-band fill entry points on device memory."""
 
     def __init__(self, local_dem: "torch.Tensor"):
         from . import _lib
-        assert local_dem.is_cuda and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
+        assert _on_device(local_dem) and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
         self._lib = _lib
         _lib.use_torch_stream()  # torch ops (halo copies, NCCL) and our kernels share one stream
         self.h, self.w = local_dem.shape
@@ -80,7 +85,7 @@ class CudaBandSolver:
         return row
 
     def update_row(self, y: int, row: "torch.Tensor") -> None:
-        assert row.is_cuda and row.dtype == torch.float32 and row.numel() == self.w
+        assert _on_device(row) and row.dtype == torch.float32 and row.numel() == self.w
         self._lib.check(self._lib.lib().rdb200_dev_fill_update_row(self._state, y, row.contiguous().data_ptr()))
 
     def finish(self) -> "torch.Tensor":
@@ -167,8 +172,8 @@ class CudaBandAccumulator:
 
     def __init__(self, local_dem, local_accum, nodata: float, g_top: int, g_bot: int, dinf: bool, ones: bool):
         from . import _lib
-        assert local_dem.is_cuda and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
-        assert local_accum.is_cuda and local_accum.dtype == torch.float64 and local_accum.is_contiguous()
+        assert _on_device(local_dem) and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
+        assert _on_device(local_accum) and local_accum.dtype == torch.float64 and local_accum.is_contiguous()
         self._lib = _lib
         _lib.use_torch_stream()
         self.L = _lib.lib()
@@ -298,7 +303,7 @@ class CudaFlatsBand:
 
     def __init__(self, local_dem, nodata: float, g_top: int, g_bot: int):
         from . import _lib
-        assert local_dem.is_cuda and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
+        assert _on_device(local_dem) and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
         self._lib, self.L = _lib, _lib.lib()
         _lib.use_torch_stream()
         self.h, self.w = local_dem.shape

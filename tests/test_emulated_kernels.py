@@ -125,3 +125,67 @@ def test_level_schedule_engages_and_matches(emulated, gp, checker):
     assert np.array_equal(got, checker.fill_depressions(dem))
     s = _lib.stats()
     assert s["fill_tile_visits"] > 0 and s["fill_rounds"] > 0
+
+
+# ---- row-band (multi-GPU) protocols: the G-bands-on-one-device drivers of test_gpu_sharded.py, on host memory ----
+@pytest.fixture()
+def band_drivers(emulated, monkeypatch):
+    import torch
+    from richdem_b200 import sharded
+
+    def host_view(ptr, shape, typestr, device):
+        dt = np.dtype(typestr)
+        n = int(np.prod(shape))
+        buf = (C.c_char * (n * dt.itemsize)).from_address(int(ptr))
+        return torch.from_numpy(np.frombuffer(buf, dtype=dt, count=n).reshape(shape))
+
+    monkeypatch.setattr(sharded, "_on_device", lambda t: True)       # "device" memory is host memory here
+    monkeypatch.setattr(sharded, "_view", host_view)
+    monkeypatch.setattr(_lib, "use_torch_stream", lambda: None)
+    gs = _load_module("gpu_sharded_drivers", os.path.join(HERE, "test_gpu_sharded.py"))
+    gs.DEV = "cpu"
+    return gs
+
+
+@pytest.mark.parametrize("G", [1, 2, 3, 5])
+def test_band_fill(band_drivers, checker, G):
+    dem = oracle.fbm_terrain(330, 300, seed=31, quantum=0.5)
+    got, rounds = band_drivers.emulate_bands(dem, G)
+    assert np.array_equal(got, checker.fill_depressions(dem)), f"G={G} after {rounds} exchanges"
+
+
+def test_band_fill_ghost_row_on_tile_boundary(band_drivers, checker):
+    band_drivers.test_band_fill_ghost_row_on_tile_boundary(checker)
+
+
+@pytest.mark.parametrize("G", [2, 3, 5])
+@pytest.mark.parametrize("dinf", [False, True])
+def test_band_accumulation(band_drivers, checker, G, dinf):
+    nd = -9999.0
+    dem = oracle.fbm_terrain(260, 210, seed=41, quantum=0.25)
+    dem[100:140, 60:120] = nd
+    resolved = checker.resolve_flats(checker.fill_depressions(dem), nd)
+    got, _ = band_drivers.emulate_fa_bands(resolved, G, nd, dinf)
+    if dinf:
+        np.testing.assert_allclose(got, checker.fa_dinf(resolved, nd), rtol=1e-9, atol=0)
+    else:
+        assert np.array_equal(got, checker.fa_d8(resolved, nd))
+
+
+def test_band_accumulation_with_weights(band_drivers, checker):
+    band_drivers.test_band_accumulation_with_weights(checker)
+
+
+@pytest.mark.parametrize("G", [2, 3, 5])
+def test_band_flat_resolution(band_drivers, checker, G):
+    nd = -9999.0
+    dem = oracle.fbm_terrain(300, 260, seed=51, quantum=0.5)
+    dem[150:170, 60:120] = nd
+    filled = checker.fill_depressions(dem)
+    expected = checker.resolve_flats(filled, nd)
+    got, it1, it2 = band_drivers.emulate_flats_bands(filled, G, nd)
+    assert np.array_equal(got.view(np.uint32), expected.view(np.uint32)), (G, it1, it2)
+
+
+def test_band_flat_resolution_snaking_flat(band_drivers, checker):
+    band_drivers.test_band_flat_resolution_snaking_flat(checker)

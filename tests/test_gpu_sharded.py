@@ -9,6 +9,7 @@ import oracle
 from richdem_b200 import sharded
 
 pytestmark = pytest.mark.gpu
+DEV = "cuda"  # tests/test_emulated_kernels.py re-runs these drivers on host memory against the kernel emulation
 
 
 def emulate_bands(dem: np.ndarray, G: int):
@@ -17,7 +18,7 @@ def emulate_bands(dem: np.ndarray, G: int):
     solvers, metas = [], []
     for g in range(G):
         r0, r1, gt, gb = sharded.local_rows(h, G, g)
-        local = torch.from_numpy(np.ascontiguousarray(dem[r0 - gt:r1 + gb])).cuda()
+        local = torch.from_numpy(np.ascontiguousarray(dem[r0 - gt:r1 + gb])).to(DEV, copy=True)
         if gt:
             local[0].fill_(float("inf"))
         if gb:
@@ -76,11 +77,11 @@ def emulate_fa_bands(dem: np.ndarray, G: int, nodata: float, dinf: bool, weights
     accs, metas, outs = [], [], []
     for g in range(G):
         r0, r1, gt, gb = sharded.local_rows(h, G, g)
-        local = torch.from_numpy(np.ascontiguousarray(dem[r0 - gt:r1 + gb])).cuda().contiguous()
+        local = torch.from_numpy(np.ascontiguousarray(dem[r0 - gt:r1 + gb])).to(DEV, copy=True).contiguous()
         if weights is None:
-            acc = torch.empty(local.shape, dtype=torch.float64, device="cuda")
+            acc = torch.empty(local.shape, dtype=torch.float64, device=DEV)
         else:
-            acc = torch.from_numpy(np.ascontiguousarray(weights[r0 - gt:r1 + gb])).cuda().contiguous()
+            acc = torch.from_numpy(np.ascontiguousarray(weights[r0 - gt:r1 + gb])).to(DEV, copy=True).contiguous()
         A = sharded.CudaBandAccumulator(local, acc, nodata, gt, gb, dinf, weights is None)
         accs.append(A)
         outs.append(acc)
@@ -166,7 +167,7 @@ def emulate_flats_bands(dem: np.ndarray, G: int, nodata: float):
     F, metas, locals_ = [], [], []
     for g in range(G):
         r0, r1, gt, gb = sharded.local_rows(h, G, g)
-        local = torch.from_numpy(np.ascontiguousarray(dem[r0 - gt:r1 + gb])).cuda().contiguous()
+        local = torch.from_numpy(np.ascontiguousarray(dem[r0 - gt:r1 + gb])).to(DEV, copy=True).contiguous()
         locals_.append(local)
         F.append(sharded.CudaFlatsBand(local, nodata, gt, gb))
         metas.append((r0, r1, gt, gb, local.shape[0]))
