@@ -406,111 +406,180 @@ __global__ void __launch_bounds__(256) accum_walk_kernel(const WalkArgs<A> a) {
   }
 }
 
+// one ready cell: push its flow downstream and keep following the receiver it completes for at most
+// `budget` steps; every other receiver it completes (and its own continuation when the budget runs
+// out) goes to `push`
+template <int MODE, bool BAND, class Push>
+__device__ __forceinline__ void levels_follow(const WalkArgs<double> &a, int c, int budget, Push &&push) {
+  const int W = a.W;
+  double acc = __ldcg(a.accum + c);
+  for (int step = 0;; step++) {
+    int next = -1;
+    if (MODE == 1) {
+      const int cd = a.code[c];
+      if (cd != kCodeNoData && (cd & 15) != 0) {
+        const int n1 = cd & 15;
+        const int r1 = c + d8dy(n1) * W + d8dx(n1);
+        if (cd & kCodeTwo) {
+          const int n2 = nwrap(n1 + 1);
+          const int r2 = c + d8dy(n2) * W + d8dx(n2);
+          float p1, p2;
+          tarboton_props(a.rmaxArr[c], &p1, &p2);
+          // generic.hpp:87  accum(ni) += props(ci,n)*c_accum  (float * double)
+          bool live1 = p1 > 0, live2 = p2 > 0;
+          if (BAND) {
+            if (live1 && park_in_ghost(a, r1, (double)p1 * acc)) live1 = false;
+            if (live2 && park_in_ghost(a, r2, (double)p2 * acc)) live2 = false;
+          }
+          if (live1) atomicAdd(a.accum + r1, (double)p1 * acc);
+          if (live2) atomicAdd(a.accum + r2, (double)p2 * acc);
+          __threadfence();
+          if (live1 && (atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
+          if (live2 && (atomicSub(a.st + r2, 1u) & kDepsMask) == 1u) {
+            if (next < 0) next = r2;
+            else push(r2);
+          }
+        } else if (!(BAND && park_in_ghost(a, r1, acc))) {
+          atomicAdd(a.accum + r1, acc);
+          __threadfence();
+          if ((atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
+        }
+      }
+    } else {
+      const int y = c / W, x = c - y * W;
+      if (!(x == 0 || y == 0 || x == W - 1 || y == a.H - 1)) {  // edge cells carry no flow
+        const float *p = a.props + (size_t)9 * c;
+        uint32_t sent = 0;
+#pragma unroll
+        for (int k = 1; k <= 8; k++) {
+          const float pk = p[k];
+          if (pk <= 0) continue;  // generic.hpp:82-83
+          const int r = c + d8dy(k) * W + d8dx(k);
+          if (a.props[(size_t)9 * r] == kNoDataGen) continue;  // :85-86
+          atomicAdd(a.accum + r, (double)pk * acc);
+          sent |= 1u << k;
+        }
+        if (sent) {
+          __threadfence();
+#pragma unroll
+          for (int k = 1; k <= 8; k++) {
+            if (!(sent & (1u << k))) continue;
+            const int r = c + d8dy(k) * W + d8dx(k);
+            if ((atomicSub(a.st + r, 1u) & kDepsMask) == 1u) {
+              if (next < 0) next = r;
+              else push(r);
+            }
+          }
+        }
+      }
+    }
+    if (next < 0) break;
+    if (step + 1 >= budget) {  // hand the continuation to the next level
+      push(next);
+      break;
+    }
+    c = next;
+    acc = __ldcg(a.accum + c);
+  }
+}
+
 // Multi-receiver graphs (D-infinity: <= 2 receivers, proportions: <= 8): ONE cooperative launch.
 // Level L drains the frontier written by level L-1 (level 0: every source); a thread processes a
 // ready cell and keeps following the receiver it completed for at most `budget` steps, so long
 // single-file reaches cost no extra levels, while every other cell it completes -- and its own
 // continuation when the budget runs out -- is appended (coalesced-group atomics) to the next
 // frontier, where other threads pick it up in parallel.  Levels meet at grid.sync().
+// Tail mode (tail_n > 0): once a frontier has at most tail_n cells there is nothing for a whole
+// grid to do, and a grid-wide barrier per level costs far more than the level; block 0 then drains
+// the following levels alone with block barriers (and a larger walking budget) until the frontier
+// is empty or has grown past 4 * tail_n again, while the other blocks wait at the next grid.sync().
 // BAND (row bands, D-infinity): level 0 can be seeded with the cells completed by a neighbour's flow
 // (q0[0..ncells), seeded != 0) and flow into a ghost row is parked there instead of followed.
 template <int MODE, bool BAND = false>
 __global__ void __launch_bounds__(256) accum_levels_kernel(const WalkArgs<double> a, int *q0, int *q1, int *counts,
-                                                            int ncells, int budget, int *levels_out, int seeded) {
+                                                            int ncells, int budget, int *levels_out, int seeded,
+                                                            int tail_n, int tail_budget, int agg) {
+  constexpr int kLvCap = 4096;
+  __shared__ int sBuf[kLvCap];
+  __shared__ int sCount, sBase;
   cg::grid_group grid = cg::this_grid();
-  const int W = a.W;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   int level = 0;
   for (;; level++) {
     const int n = level == 0 ? ncells : *reinterpret_cast<volatile int *>(&counts[level % 3]);
     if (n == 0) break;
+    if (tail_n > 0 && level > 0 && n <= tail_n) {
+      grid.sync();  // every block has read `n` and taken this branch before block 0 starts recycling the counters
+      if (blockIdx.x == 0) {
+        int lv = level;
+        for (;;) {
+          const int m = *reinterpret_cast<volatile int *>(&counts[lv % 3]);
+          if (m == 0 || m > 4 * tail_n) break;
+          if (threadIdx.x == 0) counts[(lv + 2) % 3] = 0;
+          const int *qc = (lv & 1) ? q1 : q0;
+          int *qn = (lv & 1) ? q0 : q1;
+          int *cntn = &counts[(lv + 1) % 3];
+          auto push = [&](int r) { qn[atomicAdd(cntn, 1)] = r; };
+          for (int idx = threadIdx.x; idx < m; idx += blockDim.x)
+            levels_follow<MODE, BAND>(a, __ldcg(qc + idx), tail_budget, push);
+          __threadfence();
+          __syncthreads();  // the next frontier and its count are complete and visible to the block
+          lv++;
+        }
+        if (threadIdx.x == 0) *levels_out = lv;  // level to resume at (its frontier is in counts[lv % 3])
+        __threadfence();
+      }
+      grid.sync();
+      level = *reinterpret_cast<volatile int *>(levels_out) - 1;
+      continue;
+    }
     if (gtid == 0) counts[(level + 2) % 3] = 0;
     const int *qc = (level & 1) ? q1 : q0;
     int *qn = (level & 1) ? q0 : q1;
     int *cntn = &counts[(level + 1) % 3];
-    auto push = [&](int r) {
-      cg::coalesced_group g = cg::coalesced_threads();
-      int base = 0;
-      if (g.thread_rank() == 0) base = atomicAdd(cntn, (int)g.size());
-      base = g.shfl(base, 0);
-      qn[base + g.thread_rank()] = r;
-    };
-    for (int idx = gtid; idx < n; idx += gsize) {
-      int c;
-      if (level == 0 && !(BAND && seeded)) {
-        c = idx;
-        if (!(a.st[c] & kSrcFlag)) continue;
-      } else {
-        c = __ldcg(qc + idx);
-      }
-      double acc = __ldcg(a.accum + c);
-      for (int step = 0;; step++) {
-        int next = -1;
-        if (MODE == 1) {
-          const int cd = a.code[c];
-          if (cd != kCodeNoData && (cd & 15) != 0) {
-            const int n1 = cd & 15;
-            const int r1 = c + d8dy(n1) * W + d8dx(n1);
-            if (cd & kCodeTwo) {
-              const int n2 = nwrap(n1 + 1);
-              const int r2 = c + d8dy(n2) * W + d8dx(n2);
-              float p1, p2;
-              tarboton_props(a.rmaxArr[c], &p1, &p2);
-              // generic.hpp:87  accum(ni) += props(ci,n)*c_accum  (float * double)
-              bool live1 = p1 > 0, live2 = p2 > 0;
-              if (BAND) {
-                if (live1 && park_in_ghost(a, r1, (double)p1 * acc)) live1 = false;
-                if (live2 && park_in_ghost(a, r2, (double)p2 * acc)) live2 = false;
-              }
-              if (live1) atomicAdd(a.accum + r1, (double)p1 * acc);
-              if (live2) atomicAdd(a.accum + r2, (double)p2 * acc);
-              __threadfence();
-              if (live1 && (atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
-              if (live2 && (atomicSub(a.st + r2, 1u) & kDepsMask) == 1u) {
-                if (next < 0) next = r2;
-                else push(r2);
-              }
-            } else if (!(BAND && park_in_ghost(a, r1, acc))) {
-              atomicAdd(a.accum + r1, acc);
-              __threadfence();
-              if ((atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
-            }
-          }
+    if (agg) {
+      // block-aggregated frontier: cells are collected in shared memory and appended to the global
+      // frontier with ONE atomic per block and level instead of one per converged group of lanes
+      // (the frontier counter is a single address; with ~10^5 pushes per level it serialises at L2)
+      if (threadIdx.x == 0) sCount = 0;
+      __syncthreads();
+      auto push = [&](int r) {
+        const int pos = atomicAdd(&sCount, 1);
+        if (pos < kLvCap) sBuf[pos] = r;
+        else qn[atomicAdd(cntn, 1)] = r;  // buffer full: straight to the global frontier
+      };
+      for (int idx = gtid; idx < n; idx += gsize) {
+        int c;
+        if (level == 0 && !(BAND && seeded)) {
+          c = idx;
+          if (!(a.st[c] & kSrcFlag)) continue;
         } else {
-          const int y = c / W, x = c - y * W;
-          if (!(x == 0 || y == 0 || x == W - 1 || y == a.H - 1)) {  // edge cells carry no flow
-            const float *p = a.props + (size_t)9 * c;
-            uint32_t sent = 0;
-#pragma unroll
-            for (int k = 1; k <= 8; k++) {
-              const float pk = p[k];
-              if (pk <= 0) continue;  // generic.hpp:82-83
-              const int r = c + d8dy(k) * W + d8dx(k);
-              if (a.props[(size_t)9 * r] == kNoDataGen) continue;  // :85-86
-              atomicAdd(a.accum + r, (double)pk * acc);
-              sent |= 1u << k;
-            }
-            if (sent) {
-              __threadfence();
-#pragma unroll
-              for (int k = 1; k <= 8; k++) {
-                if (!(sent & (1u << k))) continue;
-                const int r = c + d8dy(k) * W + d8dx(k);
-                if ((atomicSub(a.st + r, 1u) & kDepsMask) == 1u) {
-                  if (next < 0) next = r;
-                  else push(r);
-                }
-              }
-            }
-          }
+          c = __ldcg(qc + idx);
         }
-        if (next < 0) break;
-        if (step + 1 >= budget) {  // hand the continuation to the next level
-          push(next);
-          break;
+        levels_follow<MODE, BAND>(a, c, budget, push);
+      }
+      __syncthreads();
+      const int m = sCount < kLvCap ? sCount : kLvCap;
+      if (threadIdx.x == 0) sBase = m ? atomicAdd(cntn, m) : 0;
+      __syncthreads();
+      for (int i = threadIdx.x; i < m; i += blockDim.x) qn[sBase + i] = sBuf[i];
+    } else {
+      auto push = [&](int r) {
+        cg::coalesced_group g = cg::coalesced_threads();
+        int base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(cntn, (int)g.size());
+        base = g.shfl(base, 0);
+        qn[base + g.thread_rank()] = r;
+      };
+      for (int idx = gtid; idx < n; idx += gsize) {
+        int c;
+        if (level == 0 && !(BAND && seeded)) {
+          c = idx;
+          if (!(a.st[c] & kSrcFlag)) continue;
+        } else {
+          c = __ldcg(qc + idx);
         }
-        c = next;
-        acc = __ldcg(a.accum + c);
+        levels_follow<MODE, BAND>(a, c, budget, push);
       }
     }
     grid.sync();
@@ -530,8 +599,10 @@ void run_levels(WalkArgs<double> a, size_t ncells) {
   int *q0 = fr0.p, *q1 = fr1.p, *counts = cnt.p, *lv = cnt.p + 3;
   int nc = (int)ncells, budget = (int)(c.params.accum_budget > 0 ? c.params.accum_budget : 4);
   int seeded = 0;
-  void *args[] = {(void *)&a,      (void *)&q0, (void *)&q1,    (void *)&counts,
-                  (void *)&nc,     (void *)&budget, (void *)&lv, (void *)&seeded};
+  int tail_n = (int)c.params.accum_tail, tail_budget = (int)(c.params.accum_tail_budget > 0 ? c.params.accum_tail_budget : 32);
+  int agg = (int)c.params.accum_agg;
+  void *args[] = {(void *)&a,      (void *)&q0, (void *)&q1,     (void *)&counts, (void *)&nc,          (void *)&budget,
+                  (void *)&lv,     (void *)&seeded, (void *)&tail_n, (void *)&tail_budget, (void *)&agg};
   KernelTimer kt;
   RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_levels_kernel<MODE>, dim3(grid), dim3(256), args, 0, c.stream));
   count_launch();
@@ -1065,9 +1136,11 @@ struct FaccState {
       int *q0 = fr0.p, *q1 = fr1.p, *counts = lc.p, *lv = lc.p + 3;
       int seeded = a.frontier ? 1 : 0;
       int nc = a.nfrontier, budget = (int)(c.params.accum_budget > 0 ? c.params.accum_budget : 4);
+      int tail_n = (int)c.params.accum_tail, tail_budget = (int)(c.params.accum_tail_budget > 0 ? c.params.accum_tail_budget : 32);
       if (nc > 0) {
-        void *args[] = {(void *)&a,  (void *)&q0,     (void *)&q1, (void *)&counts,
-                        (void *)&nc, (void *)&budget, (void *)&lv, (void *)&seeded};
+        int agg = (int)c.params.accum_agg;
+        void *args[] = {(void *)&a,  (void *)&q0,     (void *)&q1,     (void *)&counts,      (void *)&nc, (void *)&budget,
+                        (void *)&lv, (void *)&seeded, (void *)&tail_n, (void *)&tail_budget, (void *)&agg};
         RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_levels_kernel<1, true>, dim3(grid), dim3(256), args, 0,
                                            c.stream));
         count_launch();

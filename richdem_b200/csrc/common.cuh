@@ -65,6 +65,9 @@ struct Params {
   int64_t accum_packed = 1;  // unit-weight D8: accumulator and donor count share one 64-bit word
   int64_t accum_threads = 256;
   int64_t accum_budget = 0;  // cells one thread follows per level in the multi-receiver accumulation (0: 4)
+  int64_t accum_tail = 0;         // multi-receiver accumulation: frontiers up to this size are drained by one block (0: off)
+  int64_t accum_agg = 0;          // multi-receiver accumulation: block-aggregated frontier appends (0: per converged group)
+  int64_t accum_tail_budget = 0;  // walking budget per level in that tail mode (0: 32)
 };
 
 struct WsBlock {

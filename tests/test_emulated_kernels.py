@@ -56,7 +56,8 @@ def emulated(emu_lib, monkeypatch):
     _lib.set_param("fill_use_tma", 0)  # TMA / mbarrier PTX is not emulated
     yield emu_lib
     for name, value in (("fill_ordered", 1), ("fill_max_iters", 0), ("fill_rounds_per_sync", 16), ("flats_tiled", 1),
-                        ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0)):
+                        ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0), ("accum_agg", 0), ("accum_tail", 0),
+                        ("accum_tail_budget", 0)):
         _lib.set_param(name, value)
 
 
@@ -108,6 +109,7 @@ def test_in_place_and_copy_semantics(emulated, gp):
 @pytest.mark.parametrize("param,value", [
     ("fill_ordered", 0), ("fill_max_iters", 1), ("fill_max_iters", 2), ("fill_rounds_per_sync", 1), ("fill_order_rounds", 40),
     ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
+    ("accum_agg", 1), ("accum_tail", 5), ("accum_tail", 1 << 20),
 ])
 def test_algorithm_variants_agree(emulated, gp, checker, param, value):
     """Every tunable is a schedule / layout choice; none may change a result."""
@@ -159,9 +161,14 @@ def test_band_fill_ghost_row_on_tile_boundary(band_drivers, checker):
 
 
 @pytest.mark.parametrize("G", [2, 3, 5])
-@pytest.mark.parametrize("dinf", [False, True])
+@pytest.mark.parametrize("dinf", [False, True, "tail"])
 def test_band_accumulation(band_drivers, checker, G, dinf):
     nd = -9999.0
+    if dinf == "tail":  # D-infinity with the small-frontier tail mode and block-aggregated appends
+        _lib.set_param("accum_tail", 64)
+        _lib.set_param("accum_tail_budget", 3)
+        _lib.set_param("accum_agg", 1)
+        dinf = True
     dem = oracle.fbm_terrain(260, 210, seed=41, quantum=0.25)
     dem[100:140, 60:120] = nd
     resolved = checker.resolve_flats(checker.fill_depressions(dem), nd)

@@ -7,7 +7,7 @@
 // concurrent CTAs).  Every variant must end at the same surface; the tool checks that.
 //
 //   gcc -O2 -fopenmp -o fillsim fillsim.c -lm
-//   ./fillsim N [seed_mode] [ordered] [Rfactor]
+//   ./fillsim N [seed_mode] [ordered] [Rfactor] [echo_filter]
 //     seed_mode 0: border cells only (what fill.cu does)
 //               1: + cells with a strictly descending steepest-descent path to the border (W = Z is exact there)
 //     ordered   0/1: level-ordered admission (quantile schedule with R = Rfactor * tiles across)
@@ -98,6 +98,9 @@ typedef struct { float w[TS * TS]; int tile; int sides; float key; } TileOut;
 enum { S_N = 1, S_S = 2, S_W = 4, S_E = 8, S_NW = 16, S_NE = 32, S_SW = 64, S_SE = 128 };
 
 static long long g_passes = 0;
+static int g_echo_filter = 0;
+static long long g_chist[8];  // visits by changed cells: 0, 1-16, 17-64, 65-256, 257-1024, 1025-2048, 2049-4095, 4096
+static long long g_changed_cells = 0;
 
 // relax tile t to its local fixed point; returns 1 if anything changed
 static int relax_tile(int t, TileOut *out) {
@@ -133,7 +136,11 @@ static int relax_tile(int t, TileOut *out) {
   }
 #pragma omp atomic
   g_passes += passes;
-  if (!any) return 0;
+  if (!any) {
+#pragma omp atomic
+    g_chist[0]++;
+    return 0;
+  }
   out->tile = t;
   out->sides = 0;
   out->key = INFINITY;
@@ -143,17 +150,53 @@ static int relax_tile(int t, TileOut *out) {
       out->w[j * TS + i] = nv;
       const float ov = Wg[(size_t)(y0 + j) * N + x0 + i];
       if (nv < ov) {
-        if (j == 0) out->sides |= S_N;
-        if (j == TS - 1) out->sides |= S_S;
-        if (i == 0) out->sides |= S_W;
-        if (i == TS - 1) out->sides |= S_E;
-        if (j == 0 && i == 0) out->sides |= S_NW;
-        if (j == 0 && i == TS - 1) out->sides |= S_NE;
-        if (j == TS - 1 && i == 0) out->sides |= S_SW;
-        if (j == TS - 1 && i == TS - 1) out->sides |= S_SE;
+        if (!g_echo_filter) {
+          if (j == 0) out->sides |= S_N;
+          if (j == TS - 1) out->sides |= S_S;
+          if (i == 0) out->sides |= S_W;
+          if (i == TS - 1) out->sides |= S_E;
+          if (j == 0 && i == 0) out->sides |= S_NW;
+          if (j == 0 && i == TS - 1) out->sides |= S_NE;
+          if (j == TS - 1 && i == 0) out->sides |= S_SW;
+          if (j == TS - 1 && i == TS - 1) out->sides |= S_SE;
+        } else if (j == 0 || i == 0 || j == TS - 1 || i == TS - 1) {
+          // activate a neighbour only if the new value is below one of ITS cells next to this one
+          // (apron copy; the live value can only be lower, so this never misses a needed visit)
+          for (int dj = -1; dj <= 1; dj++)
+            for (int di = -1; di <= 1; di++) {
+              const int aj = j + dj, ai = i + di;
+              if (aj >= 0 && aj < TS && ai >= 0 && ai < TS) continue;  // inside this tile
+              if (!(nv < w[(aj + 1) * P + ai + 1])) continue;
+              if (g_echo_filter >= 2) {  // exact: the neighbour's cell must be able to go down (needs its Z)
+                const int gx = x0 + ai, gy = y0 + aj;
+                if (gx < 0 || gy < 0 || gx >= N || gy >= N) continue;
+                if (!(fmaxf(Z[(size_t)gy * N + gx], nv) < w[(aj + 1) * P + ai + 1])) continue;
+              }
+              const int sy = aj < 0 ? -1 : (aj >= TS ? 1 : 0), sx = ai < 0 ? -1 : (ai >= TS ? 1 : 0);
+              if (sy == -1 && sx == 0) out->sides |= S_N;
+              if (sy == 1 && sx == 0) out->sides |= S_S;
+              if (sy == 0 && sx == -1) out->sides |= S_W;
+              if (sy == 0 && sx == 1) out->sides |= S_E;
+              if (sy == -1 && sx == -1) out->sides |= S_NW;
+              if (sy == -1 && sx == 1) out->sides |= S_NE;
+              if (sy == 1 && sx == -1) out->sides |= S_SW;
+              if (sy == 1 && sx == 1) out->sides |= S_SE;
+            }
+        }
         if (j < 4 || i < 4 || j >= TS - 4 || i >= TS - 4) out->key = fminf(out->key, nv);
       }
     }
+  {
+    int nc = 0;
+    for (int j = 0; j < TS; j++)
+      for (int i = 0; i < TS; i++)
+        if (out->w[j * TS + i] < Wg[(size_t)(y0 + j) * N + x0 + i]) nc++;
+    const int b = nc <= 16 ? 1 : nc <= 64 ? 2 : nc <= 256 ? 3 : nc <= 1024 ? 4 : nc <= 2048 ? 5 : nc < 4096 ? 6 : 7;
+#pragma omp atomic
+    g_chist[b]++;
+#pragma omp atomic
+    g_changed_cells += nc;
+  }
   return 1;
 }
 
@@ -162,7 +205,8 @@ int main(int argc, char **argv) {
   const int seed_mode = argc > 2 ? atoi(argv[2]) : 0;
   const int ordered = argc > 3 ? atoi(argv[3]) : 1;
   const double rfac = argc > 4 ? atof(argv[4]) : 0.8;
-  const char *dump = argc > 5 ? argv[5] : NULL;
+  g_echo_filter = argc > 5 ? atoi(argv[5]) : 0;
+  const char *dump = argc > 6 ? argv[6] : NULL;
   TN = N / TS;
   if (N % TS) { fprintf(stderr, "N must be a multiple of %d\n", TS); return 1; }
   Z = malloc((size_t)N * N * 4);
@@ -282,6 +326,9 @@ int main(int argc, char **argv) {
   }
   printf("rounds=%d visits=%lld (%.2f raster-equivalents) deferred=%lld passes/visit=%.2f small_rounds=%lld model_ms=%.1f\n", round - 1, visits,
          (double)visits / NT, deferred, (double)g_passes / visits, hist_small, model_us / 1000.0);
+  printf("visits by changed cells [0 | 1-16 | 17-64 | 65-256 | 257-1024 | 1025-2048 | 2049-4095 | 4096]:");
+  for (int k = 0; k < 8; k++) printf(" %lld", g_chist[k]);
+  printf("  cell updates=%.2f per cell\n", (double)g_changed_cells / ((double)N * N));
   // fixed-point check + checksum
   size_t bad = 0; double sum = 0; size_t nfilled = 0;
   for (int y = 1; y < N - 1; y++)
