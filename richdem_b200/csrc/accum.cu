@@ -783,6 +783,140 @@ __global__ void __launch_bounds__(256) accum_walk_packed_kernel(const uint8_t *_
     c = r;
   }
 }
+// Same walk with persistent, always-busy lanes (accum_walk_lanes = 1).  In the kernel above a thread
+// that is not a source exits at once and a walk ends as soon as its thread is not the last donor, so
+// most resident warps hold one or two live lanes and the walk is bound by how few dependent atomics
+// are in flight.  Here a warp pulls chunks of cells from a global cursor, compacts their sources
+// (ballot + popc) into a small queue in shared memory, and every lane whose walk has ended takes
+// the next source from that queue; the loop body is one converged walk step for all 32 lanes.
+constexpr int kLaneChunk = 1024;  // cells fetched per cursor atomic
+constexpr int kLaneQueue = 128;   // per-warp source queue (power of two, >= 64)
+
+template <bool BAND>
+__global__ void __launch_bounds__(256) accum_walk_packed_lanes_kernel(const uint8_t *__restrict__ code,
+                                                                       unsigned long long *word, int W, int ncells,
+                                                                       const int *__restrict__ frontier, int ghost_lo_end,
+                                                                       int ghost_hi_start, int *cursor) {
+  __shared__ int sQ[8][kLaneQueue];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int *q = sQ[threadIdx.x >> 5];
+  const unsigned lt = (1u << lane) - 1u;
+  int head = 0, count = 0;           // warp-uniform queue state
+  int pos = 0, end = 0;              // warp-uniform: next candidate, end of the current chunk
+  bool more = true;                  // the cursor may still hold chunks
+  bool walking = false;
+  int c = 0;
+  unsigned long long acc = 0;
+  for (;;) {
+    // ---- refill: keep at least a warp's worth of sources queued while candidates last ----
+    while (count <= kLaneQueue - 32) {
+      if (pos >= end) {
+        if (!more) break;
+        int b = 0;
+        if (lane == 0) b = atomicAdd(cursor, kLaneChunk);
+        b = __shfl_sync(full, b, 0);
+        if (b >= ncells) {
+          more = false;
+          break;
+        }
+        pos = b;
+        end = b + kLaneChunk < ncells ? b + kLaneChunk : ncells;
+      }
+      const int i = pos + lane;
+      bool src = false;
+      int cell = 0;
+      if (i < end) {
+        if (BAND && frontier) {
+          cell = frontier[i];
+          src = true;
+        } else {
+          cell = i;
+          src = word[i] == kPkSource;
+        }
+      }
+      const unsigned bal = __ballot_sync(full, src);
+      if (src) q[(head + count + __popc(bal & lt)) & (kLaneQueue - 1)] = cell;
+      count += __popc(bal);
+      pos += 32;
+    }
+    __syncwarp();  // queue entries written above are read by other lanes below
+    // ---- hand queued sources to the lanes that are not walking ----
+    const unsigned idle = __ballot_sync(full, !walking);
+    if (idle == full && count == 0 && !more && pos >= end) break;
+    const int rank = __popc(idle & lt);
+    if (!walking && rank < count) {
+      c = q[(head + rank) & (kLaneQueue - 1)];
+      if (BAND && frontier) {
+        acc = (unsigned long long)__longlong_as_double((long long)word[c]);  // completed by a neighbour's flow
+      } else {
+        acc = 1;
+        word[c] = (unsigned long long)__double_as_longlong(1.0);
+      }
+      walking = true;
+    }
+    {
+      const int nidle = __popc(idle);
+      const int taken = nidle < count ? nidle : count;
+      head = (head + taken) & (kLaneQueue - 1);
+      count -= taken;
+    }
+    __syncwarp();  // everyone has read its queue slot before the next refill overwrites the ring
+    // ---- one walk step ----
+    if (walking) {
+      const int cdraw = code[c];
+      const int cd = cdraw & 15;
+      if (cdraw == kCodeNoData || cd == 0) {
+        walking = false;
+      } else {
+        const int r = c + d8dy(cd) * W + d8dx(cd);
+        unsigned long long total = 0;
+        if (cdraw & kCodeSole) {
+          total = acc + 1;  // the receiver holds its own unit and waits for me alone
+        } else if (code[r] == kCodeNoData) {
+          walking = false;  // flow into NoData is dropped
+        } else if (BAND && (r < ghost_lo_end || r >= ghost_hi_start)) {
+          atomicAdd(word + r, acc + kPkOne);  // park in the ghost row: one more parcel, `acc` more flow
+          walking = false;
+        } else {
+          const unsigned long long old = atomicAdd(word + r, acc - kPkOne);
+          if ((old >> 56) != 1ull) walking = false;  // other donors are still to come
+          else total = (old & kPkVal) + acc;
+        }
+        if (walking) {
+          word[r] = (unsigned long long)__double_as_longlong((double)total);
+          acc = total;
+          c = r;
+        }
+      }
+    }
+  }
+}
+
+template <bool BAND>
+void launch_walk_packed(const uint8_t *code, unsigned long long *word, int W, int ncells, const int *frontier,
+                        int ghost_lo_end, int ghost_hi_start) {
+  Ctx &c = ctx();
+  if (ncells <= 0) return;
+  if (c.params.accum_walk_lanes) {
+    DevBuf<int> cursor(1);
+    RDB_CK(cudaMemsetAsync(cursor.p, 0, sizeof(int), c.stream));
+    int per_sm = 0;
+    RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_packed_lanes_kernel<BAND>, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (long long)c.num_sms * per_sm;
+    const long long need = ((long long)ncells + kLaneChunk - 1) / kLaneChunk;  // no more warps than chunks
+    if (blocks * 8 > need) blocks = (need + 7) / 8;
+    accum_walk_packed_lanes_kernel<BAND><<<(unsigned)blocks, 256, 0, c.stream>>>(code, word, W, ncells, frontier, ghost_lo_end,
+                                                                               ghost_hi_start, cursor.p);
+    RDB_CK(cudaGetLastError());
+    RDB_CK(cudaStreamSynchronize(c.stream));  // `cursor` goes out of scope
+  } else {
+    accum_walk_packed_kernel<BAND><<<(unsigned)((ncells + 255) / 256), 256, 0, c.stream>>>(code, word, W, ncells, frontier,
+                                                                                        ghost_lo_end, ghost_hi_start);
+  }
+}
+
 // packed ghost row -> (sum, parcels) rows for shipping; clears the slots; counts the parcels
 __global__ void __launch_bounds__(256) band_take_packed_kernel(unsigned long long *ghost, double *sum, int *cnt, int W,
                                                                 int *total) {
@@ -851,8 +985,7 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     RDB_CK(cudaGetLastError());
     count_launch(2);
     KernelTimer kt;
-    accum_walk_packed_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(
-        code.p, reinterpret_cast<unsigned long long *>(d_accum), w, (int)n, nullptr, 0, 0);
+    launch_walk_packed<false>(code.p, reinterpret_cast<unsigned long long *>(d_accum), w, (int)n, nullptr, 0, 0);
     RDB_CK(cudaGetLastError());
     count_launch();
     kt.stop_async();
@@ -1070,13 +1203,11 @@ struct FaccState {
     if (!prepared) {
       dim3 blk(256), grd((W / 4 + 255) / 256, H < 8192 ? H : 8192);
       deps_gather_packed_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, W, H, gt, H - gb);
-      accum_walk_packed_kernel<true><<<(unsigned)((n() + 255) / 256), 256, 0, c.stream>>>(code.p, word, W, (int)n(),
-                                                                                         nullptr, lo_end, hi_start);
+      launch_walk_packed<true>(code.p, word, W, (int)n(), nullptr, lo_end, hi_start);
       count_launch(2);
       prepared = true;
     } else if (n_frontier > 0) {
-      accum_walk_packed_kernel<true><<<(unsigned)((n_frontier + 255) / 256), 256, 0, c.stream>>>(
-          code.p, word, W, n_frontier, fr0.p, lo_end, hi_start);
+      launch_walk_packed<true>(code.p, word, W, n_frontier, fr0.p, lo_end, hi_start);
       count_launch();
     }
     RDB_CK(cudaGetLastError());

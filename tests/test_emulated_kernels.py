@@ -57,7 +57,7 @@ def emulated(emu_lib, monkeypatch):
     yield emu_lib
     for name, value in (("fill_ordered", 1), ("fill_max_iters", 0), ("fill_rounds_per_sync", 16), ("flats_tiled", 1),
                         ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0), ("accum_agg", 0), ("accum_tail", 0),
-                        ("accum_tail_budget", 0)):
+                        ("accum_tail_budget", 0), ("accum_walk_lanes", 0)):
         _lib.set_param(name, value)
 
 
@@ -109,7 +109,7 @@ def test_in_place_and_copy_semantics(emulated, gp):
 @pytest.mark.parametrize("param,value", [
     ("fill_ordered", 0), ("fill_max_iters", 1), ("fill_max_iters", 2), ("fill_rounds_per_sync", 1), ("fill_order_rounds", 40),
     ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
-    ("accum_agg", 1), ("accum_tail", 5), ("accum_tail", 1 << 20),
+    ("accum_agg", 1), ("accum_tail", 5), ("accum_tail", 1 << 20), ("accum_walk_lanes", 1),
 ])
 def test_algorithm_variants_agree(emulated, gp, checker, param, value):
     """Every tunable is a schedule / layout choice; none may change a result."""
@@ -161,9 +161,12 @@ def test_band_fill_ghost_row_on_tile_boundary(band_drivers, checker):
 
 
 @pytest.mark.parametrize("G", [2, 3, 5])
-@pytest.mark.parametrize("dinf", [False, True, "tail"])
+@pytest.mark.parametrize("dinf", [False, True, "tail", "lanes"])
 def test_band_accumulation(band_drivers, checker, G, dinf):
     nd = -9999.0
+    if dinf == "lanes":  # unit-weight D8 with the persistent-lane walk
+        _lib.set_param("accum_walk_lanes", 1)
+        dinf = False
     if dinf == "tail":  # D-infinity with the small-frontier tail mode and block-aggregated appends
         _lib.set_param("accum_tail", 64)
         _lib.set_param("accum_tail_budget", 3)
