@@ -740,6 +740,143 @@ __global__ void __launch_bounds__(256) deps_gather_packed_x4_kernel(uint8_t *cod
   }
 }
 
+// Fused replacement of flow_code_d8_x4_kernel + deps_gather_packed_x4_kernel (accum_fused_prep = 1):
+// ONE pass over the DEM with a rolling row window.  A block owns 1024 columns (4 per thread, the
+// outer 4 on each side are halo: blocks overlap by 8 columns) and walks down a chunk of rows.  Per
+// row step g it (A) loads DEM row g+1 (one float4 per thread, neighbours by shuffle) and computes
+// the flow codes of row g into a 5-row ring in shared memory, (B) counts the donors of row g-1 from
+// the code rows g-2..g into a 4-row ring, and (C) writes row g-2: the packed word from its donor
+// count, and its code byte with the sole-donor bit looked up at the receiver (rows g-3..g-1 of the
+// rings).  Every DEM row is fetched once per block, all stores are coalesced, and the scattered
+// one-byte sole-donor marks of the two-pass version disappear: 4 B read + 9 B written per cell.
+constexpr int kPrepCols = 1024;
+constexpr int kPrepOut = kPrepCols - 8;
+constexpr int kPrepRows = 64;
+
+__global__ void __launch_bounds__(256) fa_d8_prep_rolling_kernel(const float *__restrict__ dem, uint8_t *__restrict__ code,
+                                                                  unsigned long long *__restrict__ word, int W, int H,
+                                                                  float nodata) {
+  // ring rows carry 4 guard bytes on each side (column c of the block lives at byte c + 4)
+  __shared__ __align__(16) uint8_t sCode[5][kPrepCols + 8];
+  __shared__ __align__(16) uint8_t sDeps[4][kPrepCols + 8];
+  const unsigned full = 0xffffffffu;
+  const int t = threadIdx.x, lane = t & 31;
+  const int xc = (int)blockIdx.x * kPrepOut - 4 + 4 * t;  // first of this thread's 4 columns
+  const int y0 = (int)blockIdx.y * kPrepRows;
+  const bool col_in = xc >= 0 && xc < W;  // W % 4 == 0: the 4 columns are inside or outside together
+  const bool writer = t >= 1 && t <= 254 && col_in;
+  if (t < 4) {
+#pragma unroll
+    for (int r = 0; r < 5; r++) sCode[r][t] = sCode[r][kPrepCols + 4 + t] = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) sDeps[r][t] = sDeps[r][kPrepCols + 4 + t] = 0;
+  }
+  float d[3][6];  // DEM rows g-1, g, g+1 ; columns xc-1 .. xc+4
+  auto load_row = [&](int gy, float(&o)[6]) {
+    const bool rin = gy >= 0 && gy < H;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rin && col_in) m = __ldg(reinterpret_cast<const float4 *>(dem + (size_t)gy * W + xc));
+    float left = __shfl_up_sync(full, m.w, 1), right = __shfl_down_sync(full, m.x, 1);
+    if (lane == 0) left = (rin && xc - 1 >= 0 && xc - 1 < W) ? __ldg(dem + (size_t)gy * W + xc - 1) : 0.f;
+    if (lane == 31) right = (rin && xc + 4 >= 0 && xc + 4 < W) ? __ldg(dem + (size_t)gy * W + xc + 4) : 0.f;
+    o[0] = left; o[1] = m.x; o[2] = m.y; o[3] = m.z; o[4] = m.w; o[5] = right;
+  };
+  load_row(y0 - 3, d[0]);
+  load_row(y0 - 2, d[1]);
+  for (int g = y0 - 2; g <= y0 + kPrepRows + 1; g++) {
+    if (g - 2 >= H) break;  // no row left to write (uniform across the block)
+    load_row(g + 1, d[2]);
+    // ---- A: flow codes of row g (same per-cell rule as flow_code_d8_x4_kernel) ----
+    {
+      uint8_t cd[4];
+      const bool row_in = g >= 0 && g < H;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int x = xc + k;
+        const float e = d[1][k + 1];
+        int c = 0;
+        if (row_in && col_in) {
+          if (e == nodata) {
+            c = kCodeNoData;
+          } else if (!(x == 0 || g == 0 || x == W - 1 || g == H - 1)) {
+            // neighbours n = 1..8 : W, NW, N, NE, E, SE, S, SW
+            const float ne[9] = {0.f, d[1][k], d[0][k], d[0][k + 1], d[0][k + 2], d[1][k + 2], d[2][k + 2], d[2][k + 1], d[2][k]};
+            float lowest = 3.402823466e+38f;
+#pragma unroll
+            for (int n = 1; n <= 8; n++) {
+              const float v = ne[n];
+              if (v == nodata) continue;
+              if (v >= e) continue;
+              if (v < lowest) {
+                lowest = v;
+                c = n;
+              }
+            }
+          }
+        }
+        cd[k] = (uint8_t)c;
+      }
+      *reinterpret_cast<uchar4 *>(&sCode[(g + 10) % 5][4 + 4 * t]) = make_uchar4(cd[0], cd[1], cd[2], cd[3]);
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        d[0][k] = d[1][k];
+        d[1][k] = d[2][k];
+      }
+    }
+    __syncthreads();
+    // ---- B: donors of row g-1 from code rows g-2, g-1, g ----
+    if (g >= y0) {
+      uint8_t r[3][6];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const uint8_t *row = &sCode[(g - 2 + j + 10) % 5][4 + 4 * t];
+        const uchar4 m = *reinterpret_cast<const uchar4 *>(row);
+        r[j][0] = row[-1]; r[j][1] = m.x; r[j][2] = m.y; r[j][3] = m.z; r[j][4] = m.w; r[j][5] = row[4];
+      }
+      uint8_t dp[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int nr[9] = {0, 1, 0, 0, 0, 1, 2, 2, 2};
+        const int nc[9] = {0, k, k, k + 1, k + 2, k + 2, k + 2, k + 1, k};
+        int deps = 0;
+#pragma unroll
+        for (int n = 1; n <= 8; n++)  // NoData (255 -> 15) and "no flow" (0) never equal an inverse direction
+          deps += ((r[nr[n]][nc[n]] & 15) == d8_inverse(n)) ? 1 : 0;
+        dp[k] = (uint8_t)deps;
+      }
+      *reinterpret_cast<uchar4 *>(&sDeps[(g - 1 + 8) % 4][4 + 4 * t]) = make_uchar4(dp[0], dp[1], dp[2], dp[3]);
+    }
+    __syncthreads();
+    // ---- C: write row g-2 ----
+    if (g >= y0 + 2 && writer) {
+      const int yy = g - 2;
+      const uchar4 c4 = *reinterpret_cast<const uchar4 *>(&sCode[(yy + 10) % 5][4 + 4 * t]);
+      const uchar4 d4 = *reinterpret_cast<const uchar4 *>(&sDeps[(yy + 8) % 4][4 + 4 * t]);
+      int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+      const int dd[4] = {d4.x, d4.y, d4.z, d4.w};
+      unsigned long long out[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (cc[k] == kCodeNoData) {
+          out[k] = 0xBFF0000000000000ull;  // -1.0 (flow_accumulation_generic.hpp:95-97)
+          continue;
+        }
+        out[k] = dd[k] == 0 ? kPkSource : (((unsigned long long)dd[k] << 56) | 1ull);
+        const int dir = cc[k] & 15;
+        if (dir != 0) {
+          const int ry = yy + d8dy(dir), ro = 4 + 4 * t + k + d8dx(dir);
+          const int rc = sCode[(ry + 10) % 5][ro];
+          if (rc != kCodeNoData && sDeps[(ry + 8) % 4][ro] == 1) cc[k] |= kCodeSole;  // I am my receiver's only donor
+        }
+      }
+      const size_t i0 = (size_t)yy * W + xc;
+      *reinterpret_cast<uchar4 *>(code + i0) = make_uchar4((uint8_t)cc[0], (uint8_t)cc[1], (uint8_t)cc[2], (uint8_t)cc[3]);
+      reinterpret_cast<ulonglong2 *>(word + i0)[0] = make_ulonglong2(out[0], out[1]);
+      reinterpret_cast<ulonglong2 *>(word + i0)[1] = make_ulonglong2(out[2], out[3]);
+    }
+  }
+}
+
 // BAND: cells below ghost_lo_end / from ghost_hi_start on belong to a neighbouring row band; flow
 // into them is parked in their word as [parcel count | sum] for the caller to ship.  `frontier`
 // (optional) lists cells completed by a neighbour's flow; their word already holds the final double.
@@ -980,10 +1117,17 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     // unit-weight D8: packed integer accumulation (see above)
     DevBuf<uint8_t> code(n);
     dim3 blk(256), grd((w / 4 + 255) / 256, h < 8192 ? h : 8192);
-    flow_code_d8_x4_kernel<<<grd, blk, 0, c.stream>>>(d_dem, code.p, d_accum, w, h, nodata, 2);
-    deps_gather_packed_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, reinterpret_cast<unsigned long long *>(d_accum), w, h, 0, h);
+    if (c.params.accum_fused_prep) {
+      dim3 pgrd((unsigned)((w + kPrepOut - 1) / kPrepOut), (unsigned)((h + kPrepRows - 1) / kPrepRows));
+      fa_d8_prep_rolling_kernel<<<pgrd, blk, 0, c.stream>>>(d_dem, code.p, reinterpret_cast<unsigned long long *>(d_accum), w, h,
+                                                            nodata);
+      count_launch();
+    } else {
+      flow_code_d8_x4_kernel<<<grd, blk, 0, c.stream>>>(d_dem, code.p, d_accum, w, h, nodata, 2);
+      deps_gather_packed_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, reinterpret_cast<unsigned long long *>(d_accum), w, h, 0, h);
+      count_launch(2);
+    }
     RDB_CK(cudaGetLastError());
-    count_launch(2);
     KernelTimer kt;
     launch_walk_packed<false>(code.p, reinterpret_cast<unsigned long long *>(d_accum), w, (int)n, nullptr, 0, 0);
     RDB_CK(cudaGetLastError());

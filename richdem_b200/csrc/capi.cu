@@ -232,6 +232,7 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "accum_tail_budget") p.accum_tail_budget = value;
   else if (n == "accum_agg") p.accum_agg = value;
   else if (n == "accum_walk_lanes") p.accum_walk_lanes = value;
+  else if (n == "accum_fused_prep") p.accum_fused_prep = value;
   else if (n == "flats_tiled") p.flats_tiled = value;
   else if (n == "accum_packed") p.accum_packed = value;
   else fail("rdb200_set_param: unknown parameter '%s'", name);

@@ -63,6 +63,7 @@ struct Params {
   int64_t fill_profile = 0;     // 1: collect + print in-tile work counters (slower)
   int64_t flats_tiled = 1;   // flat-resolution gradients by the tile engine (0: one cooperative BFS launch each)
   int64_t accum_packed = 1;  // unit-weight D8: accumulator and donor count share one 64-bit word
+  int64_t accum_fused_prep = 0;   // unit-weight D8: flow codes + donor counts + sole-donor bits in one rolling-window pass
   int64_t accum_walk_lanes = 0;   // unit-weight D8 walk: persistent always-busy lanes fed from per-warp source queues
   int64_t accum_threads = 256;
   int64_t accum_budget = 0;  // cells one thread follows per level in the multi-receiver accumulation (0: 4)

@@ -57,7 +57,7 @@ def emulated(emu_lib, monkeypatch):
     yield emu_lib
     for name, value in (("fill_ordered", 1), ("fill_max_iters", 0), ("fill_rounds_per_sync", 16), ("flats_tiled", 1),
                         ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0), ("accum_agg", 0), ("accum_tail", 0),
-                        ("accum_tail_budget", 0), ("accum_walk_lanes", 0)):
+                        ("accum_tail_budget", 0), ("accum_walk_lanes", 0), ("accum_fused_prep", 0)):
         _lib.set_param(name, value)
 
 
@@ -110,6 +110,7 @@ def test_in_place_and_copy_semantics(emulated, gp):
     ("fill_ordered", 0), ("fill_max_iters", 1), ("fill_max_iters", 2), ("fill_rounds_per_sync", 1), ("fill_order_rounds", 40),
     ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
     ("accum_agg", 1), ("accum_tail", 5), ("accum_tail", 1 << 20), ("accum_walk_lanes", 1),
+    ("accum_fused_prep", 1),
 ])
 def test_algorithm_variants_agree(emulated, gp, checker, param, value):
     """Every tunable is a schedule / layout choice; none may change a result."""
@@ -199,3 +200,18 @@ def test_band_flat_resolution(band_drivers, checker, G):
 
 def test_band_flat_resolution_snaking_flat(band_drivers, checker):
     band_drivers.test_band_flat_resolution_snaking_flat(checker)
+
+
+@pytest.mark.parametrize("shape", [(70, 2040), (130, 1016), (67, 1020), (3, 1024), (200, 4), (129, 8), (66, 1012)])
+def test_fused_d8_preparation_block_seams(emulated, gp, checker, shape):
+    """accum_fused_prep: blocks own 1016 output columns / 64 rows and overlap by a halo; widths and heights around
+    those seams, with and without the persistent-lane walk."""
+    import richdem_b200 as rd
+    dem = oracle.fbm_terrain(*shape, seed=sum(shape), quantum=0.5)
+    dem[shape[0] // 3: shape[0] // 3 + 5, shape[1] // 2: shape[1] // 2 + 9] = gp.ND
+    expected = checker.fa_d8(dem, gp.ND)
+    for lanes in (0, 1):
+        _lib.set_param("accum_fused_prep", 1)
+        _lib.set_param("accum_walk_lanes", lanes)
+        got = np.asarray(rd.FlowAccumulation(gp.R(dem), "D8"))
+        assert np.array_equal(got, expected), (shape, lanes)
