@@ -4,6 +4,7 @@
 The rewrite is purely syntactic:
   * `kernel<<<grid, block, smem, stream>>>(args)`        -> `rdb_emu::launch(grid, block, [&]() { kernel(args); })`
   * `cudaLaunchCooperativeKernel((const void *)k, ...)`  -> `rdb_emu::launch_coop(k, ...)`
+  * `__shared__ T x[N];`                                 -> a block-local object from `rdb_emu::shared_mem`
   * `asm volatile("...")` statements                    -> `rdb_emu::asm_stub("...")` (TMA PTX aborts if reached)
   * `#include <cuda*.h>` / `<cooperative_groups.h>`      -> `#include "cuda_emu.h"`
 Nothing in the package, bench.py or __graft_entry__.smoke() uses the result; richdem_b200/_lib.py refuses
@@ -71,8 +72,40 @@ def _split_top(s: str) -> list[str]:
 _LAUNCH = re.compile(r"([A-Za-z_][A-Za-z0-9_:]*(?:\s*<[^<>;(){}]*>)?)\s*<<<")
 
 
+_SHARED = re.compile(r"^([ \t]*)__shared__\s+(?:__align__\((\d+)\)\s+)?([^;]+);", re.M)
+
+
+def _rewrite_shared(text: str) -> str:
+    """`__shared__ T a[N], b;` -> one block-local object per declarator (rdb_emu::shared_mem), so that
+    cooperative launches can run several blocks at once with their own shared memory."""
+    def repl(m):
+        indent, align, decl = m.group(1), m.group(2) or "16", m.group(3).strip()
+        # the first declarator starts at the last identifier before the first '[' or ','
+        cut = len(decl)
+        for ch in "[,":
+            k = decl.find(ch)
+            if k >= 0:
+                cut = min(cut, k)
+        head = decl[:cut].rstrip()
+        k = len(head)
+        while k > 0 and (head[k - 1].isalnum() or head[k - 1] == "_"):
+            k -= 1
+        ctype, rest = decl[:k].strip(), decl[k:]
+        out = []
+        for d in _split_top(rest):
+            mm = re.match(r"^(\w+)\s*((?:\[[^\]]*\])*)$", d.strip())
+            if not mm:
+                raise ValueError(f"cannot parse __shared__ declarator {d!r} in {m.group(0)!r}")
+            nm, dims = mm.group(1), mm.group(2)
+            out.append(f"{indent}typedef {ctype} {nm}__t{dims}; static rdb_emu::SharedSlot {nm}__slot; "
+                       f"{nm}__t &{nm} = *reinterpret_cast<{nm}__t *>(rdb_emu::shared_mem(&{nm}__slot, sizeof({nm}__t), {align}));")
+        return "\n".join(out)
+    return _SHARED.sub(repl, text)
+
+
 def rewrite(text: str, name: str) -> str:
     text = re.sub(r'#include\s*<(cuda|cuda_runtime|cooperative_groups)\.h>', '#include "cuda_emu.h"', text)
+    text = _rewrite_shared(text)
     # kernel launches
     out, pos = [], 0
     while True:

@@ -59,6 +59,7 @@ struct Block {
 };
 
 struct Fiber {
+  int slot = 0;    // index of its block among the blocks running concurrently
   void *sp = nullptr;
   bool done = false;
   uint3 tid{0, 0, 0}, bid{0, 0, 0};
@@ -186,6 +187,9 @@ void launch(dim3 grid, dim3 block, const std::function<void()> &body, bool coope
     fprintf(stderr, "rdb_emu: %zu threads per block\n", nthreads);
     abort();
   }
+  static const bool trace = getenv("RDB_EMU_TRACE") != nullptr;
+  if (trace) fprintf(stderr, "rdb_emu: launch grid=(%u,%u,%u) block=(%u,%u,%u)%s\n", grid.x, grid.y, grid.z, block.x, block.y,
+                     block.z, cooperative ? " cooperative" : "");
   Launch l;
   l.body = &body;
   l.cooperative = cooperative;
@@ -219,6 +223,7 @@ void launch(dim3 grid, dim3 block, const std::function<void()> &body, bool coope
         f.tid.y = (unsigned)((t / block.x) % block.y);
         f.tid.z = (unsigned)(t / ((size_t)block.x * block.y));
         f.lin = (int)t;
+        f.slot = (int)k;
         f.blk = &bs;
         prepare(&f, g_stacks + (k * nthreads + t + 1) * kStack);
       }
@@ -277,6 +282,22 @@ uint64_t warp_exchange(uint64_t val, int src, unsigned *ballot_out, int pred) {
   return w->vals[slot][src];
 }
 
+void *shared_mem(SharedSlot *slot, size_t size, size_t align) {
+  const size_t k = (size_t)g_cur->slot;
+  if (slot->size != size) {  // first use (or a different template instantiation sharing the slot: never happens)
+    for (void *p : slot->per_block) free(p);
+    slot->per_block.clear();
+    slot->size = size;
+  }
+  if (slot->per_block.size() <= k) slot->per_block.resize(k + 1, nullptr);
+  if (!slot->per_block[k]) {
+    if (align < 16) align = 16;
+    slot->per_block[k] = aligned_alloc(align, (size + align - 1) / align * align);
+    memset(slot->per_block[k], 0xA5, size);  // shared memory starts as garbage
+  }
+  return slot->per_block[k];
+}
+
 void asm_stub(const char *text) {
   if (strstr(text, "cp.async.bulk") || strstr(text, "try_wait") || strstr(text, "expect_tx")) {
     fprintf(stderr, "rdb_emu: TMA / mbarrier PTX is not emulated (run with fill_use_tma = 0): %s\n", text);
@@ -323,7 +344,8 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
   snprintf(p->name, sizeof(p->name), "rdb_emu (CPU fibers, test only)");
   p->major = 10;
   p->minor = 0;
-  p->multiProcessorCount = 1;
+  const char *sms = getenv("RDB_EMU_SMS");  // > 1: cooperative kernels run several blocks side by side
+  p->multiProcessorCount = sms && atoi(sms) > 0 ? atoi(sms) : 1;
   p->cooperativeLaunch = 1;
   p->totalGlobalMem = (size_t)8 << 30;
   return cudaSuccess;

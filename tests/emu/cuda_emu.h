@@ -14,7 +14,7 @@
 // round-robin.  __syncthreads / __syncthreads_count wait for all live threads of the block, warp
 // collectives (full masks only) for all live lanes of the warp, cooperative grid.sync() for all
 // live threads of the launch (cooperative launches run all their blocks concurrently and must use
-// one block when the kernel has __shared__ state; the emulated device reports 1 SM so they do).
+// their own shared memory; the emulated device reports RDB_EMU_SMS SMs, default 1).
 // TMA / mbarrier inline PTX is not emulated: the sources run with fill_use_tma = 0.
 #pragma once
 #include <algorithm>
@@ -39,7 +39,6 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __grid_constant__
-#define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 
 // ---- vector types ----
@@ -130,6 +129,12 @@ void sync_grid();
 uint64_t warp_exchange(uint64_t val, int src_lane_or_neg, unsigned *ballot_out, int pred);
 int lane_id();
 void asm_stub(const char *text);
+// block-local "shared memory": one object per __shared__ declaration and concurrently running block
+struct SharedSlot {
+  std::vector<void *> per_block;
+  size_t size = 0;
+};
+void *shared_mem(SharedSlot *slot, size_t size, size_t align);
 
 template <class... A, size_t... I>
 void call_unpacked(void (*f)(A...), void **args, std::index_sequence<I...>) {

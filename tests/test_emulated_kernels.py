@@ -215,3 +215,17 @@ def test_fused_d8_preparation_block_seams(emulated, gp, checker, shape):
         _lib.set_param("accum_walk_lanes", lanes)
         got = np.asarray(rd.FlowAccumulation(gp.R(dem), "D8"))
         assert np.array_equal(got, expected), (shape, lanes)
+
+
+def test_cooperative_kernels_with_several_blocks():
+    """The cooperative kernels (multi-receiver level kernel with its tail mode and block-aggregated appends, the
+    persistent BFS) size their grid from the SM count; re-run their cases with 3 emulated SMs so that they execute as
+    3 blocks side by side, each with its own shared memory and a real grid barrier."""
+    import subprocess
+    if os.environ.get("RDB_EMU_SMS"):
+        pytest.skip("already inside the multi-block run")
+    env = dict(os.environ, RDB_EMU_SMS="3")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.abspath(__file__), "-k",
+                        "variants or band_accumulation or special_rasters or degenerate"],
+                       env=env, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
