@@ -61,6 +61,7 @@ struct Params {
   int64_t fill_order_rounds = 0;  // rounds the level schedule spans (0: 0.8 x tiles across the raster)
   int64_t fill_band_rounds = 0;   // row-band mode: rounds per rdb200_dev_fill_run call (0: to convergence)
   int64_t fill_profile = 0;     // 1: collect + print in-tile work counters (slower)
+  int64_t flats_uf_tiled = 0;  // union-find: unite inside 64x16 tiles in shared memory first, then across tile seams
   int64_t flats_tiled = 1;   // flat-resolution gradients by the tile engine (0: one cooperative BFS launch each)
   int64_t accum_packed = 1;  // unit-weight D8: accumulator and donor count share one 64-bit word
   int64_t accum_fused_prep = 0;   // unit-weight D8: flow codes + donor counts + sole-donor bits in one rolling-window pass

@@ -154,6 +154,107 @@ __global__ void __launch_bounds__(256) uf_union_kernel(const float *__restrict__
   }
 }
 
+// Two-level variant (flats_uf_tiled = 1): a block first unites the equal-elevation neighbours INSIDE its
+// 64x16 tile with the same lock-free union-find running on shared memory (no global atomics), then
+// writes every cell's parent as the global index of its in-tile root (the smallest index of its in-tile
+// component, so "smaller index wins" still holds); a second kernel unites across tile seams only, on
+// those roots.  Replaces uf_init_kernel + uf_union_kernel; the partition is identical.
+constexpr int UT_W = 64, UT_H = 16, UT_N = UT_W * UT_H;
+
+__global__ void __launch_bounds__(256) uf_tile_kernel(const float *__restrict__ dem, const uint8_t *__restrict__ ft,
+                                                       int *__restrict__ parent, int W, int H) {
+  __shared__ float sE[UT_N];
+  __shared__ int sP[UT_N];
+  __shared__ uint8_t sOk[UT_N];
+  const int x0 = blockIdx.x * UT_W, y0 = blockIdx.y * UT_H;
+  for (int k = threadIdx.x; k < UT_N; k += blockDim.x) {
+    const int lx = k % UT_W, ly = k / UT_W, gx = x0 + lx, gy = y0 + ly;
+    float e = 0.f;
+    uint8_t ok = 0;
+    if (gx < W && gy < H) {
+      const size_t i = (size_t)gy * W + gx;
+      ok = (ft[i] & FT_NODATA) ? 0 : 1;
+      e = __ldg(dem + i);
+    }
+    sE[k] = e;
+    sOk[k] = ok;
+    sP[k] = k;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < UT_N; k += blockDim.x) {
+    if (!sOk[k]) continue;
+    const int lx = k % UT_W, ly = k / UT_W;
+    const float e = sE[k];
+#pragma unroll
+    for (int d = 5; d <= 8; d++) {  // forward half of the 8-neighbourhood: E, SE, S, SW
+      const int nx = lx + d8dx(d), ny = ly + d8dy(d);
+      if (nx < 0 || nx >= UT_W || ny >= UT_H) continue;
+      const int nk = ny * UT_W + nx;
+      if (sOk[nk] && sE[nk] == e) uf_union(sP, k, nk);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < UT_N; k += blockDim.x) {
+    const int lx = k % UT_W, ly = k / UT_W, gx = x0 + lx, gy = y0 + ly;
+    if (gx >= W || gy >= H) continue;
+    int r = k;
+    for (int p = sP[r]; p != r; p = sP[r]) r = p;  // read-only: the unions are complete
+    parent[(size_t)gy * W + gx] = (y0 + r / UT_W) * W + x0 + r % UT_W;
+  }
+}
+
+// the cells of a tile whose forward neighbours can lie in another tile: left / right column, bottom row
+__global__ void __launch_bounds__(128) uf_seams_kernel(const float *__restrict__ dem, const uint8_t *__restrict__ ft, int *parent,
+                                                        int W, int H) {
+  const int x0 = blockIdx.x * UT_W, y0 = blockIdx.y * UT_H;
+  const int t = threadIdx.x;
+  int lx, ly;
+  if (t < UT_W) {
+    lx = t;
+    ly = UT_H - 1;
+  } else if (t < UT_W + UT_H - 1) {
+    lx = 0;
+    ly = t - UT_W;
+  } else if (t < UT_W + 2 * (UT_H - 1)) {
+    lx = UT_W - 1;
+    ly = t - (UT_W + UT_H - 1);
+  } else {
+    return;
+  }
+  int gx = x0 + lx, gy = y0 + ly;
+  // partial tiles at the raster edge: their last real row / column plays the seam role of nothing (no
+  // neighbour beyond the raster), so cells outside the raster simply drop out
+  if (gx >= W || gy >= H) return;
+  const size_t i = (size_t)gy * W + gx;
+  if (ft[i] & FT_NODATA) return;
+  const float e = __ldg(dem + i);
+#pragma unroll
+  for (int d = 5; d <= 8; d++) {
+    const int nlx = lx + d8dx(d), nly = ly + d8dy(d);
+    if (nlx >= 0 && nlx < UT_W && nly < UT_H) continue;  // same tile: done in shared memory
+    const int nx = gx + d8dx(d), ny = gy + d8dy(d);
+    if (nx < 0 || nx >= W || ny >= H) continue;
+    const size_t ni = (size_t)ny * W + nx;
+    if (__ldg(dem + ni) == e && !(ft[ni] & FT_NODATA)) uf_union(parent, (int)i, (int)ni);
+  }
+}
+
+// parent[] for the union-find over exactly-equal elevations, by either variant
+void uf_build(const float *d_dem, const uint8_t *ft, int *parent, int w, int h) {
+  Ctx &c = ctx();
+  const size_t n = (size_t)w * h;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (c.params.flats_uf_tiled) {
+    dim3 grd((unsigned)((w + UT_W - 1) / UT_W), (unsigned)((h + UT_H - 1) / UT_H));
+    uf_tile_kernel<<<grd, 256, 0, c.stream>>>(d_dem, ft, parent, w, h);
+    uf_seams_kernel<<<grd, 128, 0, c.stream>>>(d_dem, ft, parent, w, h);
+  } else {
+    uf_init_kernel<<<blocks, 256, 0, c.stream>>>(parent, n);
+    uf_union_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft, parent, w, h);
+  }
+  RDB_CK(cudaGetLastError());
+}
+
 // Read-only root lookup (no path compression here: concurrent halving stores could overwrite a
 // neighbour's freshly flattened entry with a non-root ancestor).  Writes the root of every data
 // cell to `root_of` and flags roots whose component holds a low edge (an outlet).
@@ -428,10 +529,8 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   DevBuf<int> parent(n), labels(n);
   DevBuf<uint8_t> rootflag(n);
   RDB_CK(cudaMemsetAsync(rootflag.p, 0, n, c.stream));
-  uf_init_kernel<<<blocks, 256, 0, c.stream>>>(parent.p, n);
-  lap("uf init");
-  uf_union_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, parent.p, w, h);
-  lap("uf union");
+  uf_build(d_dem, ft.p, parent.p, w, h);
+  lap("uf init + union");
   uf_roots_kernel<<<blocks, 256, 0, c.stream>>>(ft.p, parent.p, labels.p, rootflag.p, n);
   make_labels_kernel<<<blocks, 256, 0, c.stream>>>(rootflag.p, ft.p, labels.p, n);
   RDB_CK(cudaGetLastError());
@@ -592,8 +691,7 @@ int rdb200_dev_flats_components(rdb200_flats_state *s) {
   using namespace rdb;
   Ctx &c = ctx();
   const size_t n = s->n();
-  uf_init_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->parent.p, n);
-  uf_union_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->dem, s->ft.p, s->parent.p, s->W, s->H);
+  uf_build(s->dem, s->ft.p, s->parent.p, s->W, s->H);
   uf_roots_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->ft.p, s->parent.p, s->labels.p, s->rootflag.p, n);
   RDB_CK(cudaGetLastError());
   RDB_CK(cudaStreamSynchronize(c.stream));

@@ -57,7 +57,8 @@ def emulated(emu_lib, monkeypatch):
     yield emu_lib
     for name, value in (("fill_ordered", 1), ("fill_max_iters", 0), ("fill_rounds_per_sync", 16), ("flats_tiled", 1),
                         ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0), ("accum_agg", 0), ("accum_tail", 0),
-                        ("accum_tail_budget", 0), ("accum_walk_lanes", 0), ("accum_fused_prep", 0)):
+                        ("accum_tail_budget", 0), ("accum_walk_lanes", 0), ("accum_fused_prep", 0),
+                        ("flats_uf_tiled", 0)):
         _lib.set_param(name, value)
 
 
@@ -110,7 +111,7 @@ def test_in_place_and_copy_semantics(emulated, gp):
     ("fill_ordered", 0), ("fill_max_iters", 1), ("fill_max_iters", 2), ("fill_rounds_per_sync", 1), ("fill_order_rounds", 40),
     ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
     ("accum_agg", 1), ("accum_tail", 5), ("accum_tail", 1 << 20), ("accum_walk_lanes", 1),
-    ("accum_fused_prep", 1),
+    ("accum_fused_prep", 1), ("flats_uf_tiled", 1),
 ])
 def test_algorithm_variants_agree(emulated, gp, checker, param, value):
     """Every tunable is a schedule / layout choice; none may change a result."""
@@ -187,9 +188,12 @@ def test_band_accumulation_with_weights(band_drivers, checker):
     band_drivers.test_band_accumulation_with_weights(checker)
 
 
-@pytest.mark.parametrize("G", [2, 3, 5])
+@pytest.mark.parametrize("G", [2, 3, 5, "uf_tiled"])
 def test_band_flat_resolution(band_drivers, checker, G):
     nd = -9999.0
+    if G == "uf_tiled":
+        _lib.set_param("flats_uf_tiled", 1)
+        G = 3
     dem = oracle.fbm_terrain(300, 260, seed=51, quantum=0.5)
     dem[150:170, 60:120] = nd
     filled = checker.fill_depressions(dem)
@@ -229,3 +233,20 @@ def test_cooperative_kernels_with_several_blocks():
                         "variants or band_accumulation or special_rasters or degenerate"],
                        env=env, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("shape,q", [((40, 200), 2.0), ((16, 64), 5.0), ((17, 65), 5.0), ((100, 130), 20.0), ((33, 129), 1000.0)])
+def test_tiled_union_find_seams(emulated, gp, checker, shape, q):
+    """flats_uf_tiled: flats that cross the 64x16 union-find tiles in every direction (coarse quantisation makes
+    large plateaus; the last case is one flat covering the raster)."""
+    import richdem_b200 as rd
+    _lib.set_param("flats_uf_tiled", 1)
+    dem = checker.fill_depressions(oracle.fbm_terrain(*shape, seed=shape[1], quantum=q))
+    dem[shape[0] // 2, shape[1] // 3: shape[1] // 3 + 4] = gp.ND
+    m, l = rd.FlatMask(gp.R(dem))
+    m_ref, l_ref = checker.flat_mask(dem, gp.ND)
+    assert np.array_equal(m, m_ref)
+    pairs = np.unique(np.stack([l[l != 0], l_ref[l_ref != 0]]), axis=1)
+    assert len(np.unique(pairs[0])) == pairs.shape[1] == len(np.unique(pairs[1]))
+    got = np.asarray(rd.ResolveFlats(gp.R(dem)))
+    assert np.array_equal(got.view(np.uint32), checker.resolve_flats(dem, gp.ND).view(np.uint32))

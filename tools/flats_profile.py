@@ -3,7 +3,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from richdem_b200 import _lib
 L = _lib.lib(); _lib.init(0); _lib.use_torch_stream()
-for N in [int(a) for a in sys.argv[1:]] or [4096, 16384]:
+# k=v arguments are rdb200_set_param switches (e.g. flats_uf_tiled=1); RDB200_PROFILE=1 prints the phase laps
+for kv in [a for a in sys.argv[1:] if "=" in a]:
+    _lib.set_param(kv.split("=")[0], int(kv.split("=")[1]))
+for N in [int(a) for a in sys.argv[1:] if "=" not in a] or [4096, 16384]:
     d = torch.empty((N, N), dtype=torch.float32, device="cuda")
     _lib.check(L.rdb200_dev_generate_fbm_f32(d.data_ptr(), N, N, 0, 42, 12, 0.0))
     _lib.check(L.rdb200_dev_fill_depressions_d8_f32(d.data_ptr(), N, N)); s0 = _lib.stats()
