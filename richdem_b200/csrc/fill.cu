@@ -504,6 +504,445 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
   }
 }
 
+// =================================================================================================
+// Asynchronous variant of the sweep (fill_async = 1; prepared for round 2, off by default).
+//
+// The round engine above is as slow as the slowest tile of every round, pays two launches per round
+// and leaves the last wave of CTAs partly idle.  Here ONE cooperative launch of persistent CTAs
+// drains per-level tile queues with no round barrier:
+//   * every tile has a state IDLE / QUEUED / BUSY / BUSY_DIRTY.  Activating a neighbour ORs the
+//     changed apron sides into its mask, then moves IDLE -> QUEUED (and pushes it) or BUSY ->
+//     BUSY_DIRTY; a CTA that finishes a BUSY_DIRTY tile queues it again, so a tile is never relaxed
+//     by two CTAs at once and no activation is lost (the data written before an activation is
+//     fenced before the state change; the relaxing CTA takes the side mask after it set BUSY);
+//   * AQ_BUCKETS ring queues, one per quantile band of the incoming water level (the same sampled
+//     histogram as the level schedule); a CTA always takes from the lowest non-empty bucket, so the
+//     flood still rises roughly in level order but no CTA ever waits for a round to end;
+//   * `pending` counts tiles that are QUEUED or BUSY; CTAs leave when it reaches zero.  A spin
+//     budget turns a protocol bug into an error instead of a hang.
+// The in-tile relaxation is the same code as in fill_sweep_kernel<0>.
+// =================================================================================================
+constexpr int AQ_BUCKETS = 32;
+enum : int { TS_IDLE = 0, TS_QUEUED = 1, TS_BUSY = 2, TS_BUSY_DIRTY = 3 };
+
+struct AsyncDev {
+  unsigned int head[AQ_BUCKETS];
+  unsigned int tail[AQ_BUCKETS];
+  float thr[AQ_BUCKETS];  // bucket b takes levels <= thr[b]; the last one is +inf
+  int pending;            // tiles QUEUED or BUSY
+  int abort_flag;         // set by the spin watchdog
+  unsigned long long visits, iters, requeues, pop_retries;
+};
+
+struct AsyncArgs {
+  const float *Zp;
+  float *Wp;
+  int pitch;
+  int W, H;
+  int tilesX, tilesY;
+  int *state;
+  int *sides;
+  int *keys;
+  int *queue;  // [AQ_BUCKETS][cap]; a slot holds tile + 1, or 0 while empty
+  int cap;     // power of two > number of tiles
+  AsyncDev *dev;
+  int max_iters;
+  int use_tma;
+  int profile;
+  long long spin_limit;
+};
+
+__device__ __forceinline__ void aq_sleep(unsigned ns = 100) { __nanosleep(ns); }
+// order generic-proxy accesses (other CTAs' stores, made visible by their fences) before this thread's
+// async-proxy (TMA) reads of global memory
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ int aq_bucket(const AsyncDev *dev, int key_ord) {
+  const float k = ord2f(key_ord);
+  int b = 0;
+  while (b < AQ_BUCKETS - 1 && k > dev->thr[b]) b++;
+  return b;
+}
+
+__device__ __forceinline__ void aq_push(const AsyncArgs &a, int t, int b) {
+  const unsigned int p = atomicAdd(&a.dev->tail[b], 1u);
+  __threadfence();
+  *reinterpret_cast<volatile int *>(&a.queue[(size_t)b * a.cap + (p & (unsigned)(a.cap - 1))]) = t + 1;
+}
+
+// tell tile `nb` that the apron sides `bits` changed (lowest new level `key_ord`)
+__device__ __forceinline__ void aq_activate(const AsyncArgs &a, int nb, int bits, int key_ord) {
+  atomicOr(&a.sides[nb], bits);
+  atomicMin(&a.keys[nb], key_ord);
+  __threadfence();
+  for (;;) {
+    const int s = atomicCAS(&a.state[nb], TS_IDLE, TS_QUEUED);
+    if (s == TS_IDLE) {
+      atomicAdd(&a.dev->pending, 1);
+      aq_push(a, nb, aq_bucket(a.dev, key_ord));
+      return;
+    }
+    if (s == TS_QUEUED || s == TS_BUSY_DIRTY) return;  // it will (re)read its apron anyway
+    if (atomicCAS(&a.state[nb], TS_BUSY, TS_BUSY_DIRTY) == TS_BUSY) return;
+    // the state moved between the two CAS: look again
+  }
+}
+
+__global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
+    fill_async_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ,
+                      const AsyncArgs a) {
+  constexpr int STEP = 0;
+  __shared__ __align__(128) float sW[SROWS * SP];
+  __shared__ __align__(128) float sZ[TY * TX];
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ unsigned char sMark[MKP * (BYN + 2)];
+  __shared__ unsigned char sList[2][NWARP][SEG];
+  __shared__ __align__(16) int sCnt[2][NWARP];
+  __shared__ int sTile;
+  __shared__ int sSides;
+  __shared__ int sFlags;
+  __shared__ int sKey;
+  __shared__ int sProf[2];
+
+  const int tid = threadIdx.x;
+  const unsigned full = 0xffffffffu;
+  AsyncDev *dev = a.dev;
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t phase = 0;
+  const int max_iters = a.max_iters;
+
+  for (;;) {
+    // ---- take a tile from the lowest non-empty bucket (warp 0; lane b watches bucket b) ----
+    if (tid < 32) {
+      int t = -1;
+      long long spins = 0;
+      for (;;) {
+        unsigned int h = 0, tl = 0;
+        if (tid < AQ_BUCKETS) {
+          h = *reinterpret_cast<volatile unsigned int *>(&dev->head[tid]);
+          tl = *reinterpret_cast<volatile unsigned int *>(&dev->tail[tid]);
+        }
+        const unsigned ne = __ballot_sync(full, (int)(tl - h) > 0);
+        if (ne) {
+          const int b = __ffs((int)ne) - 1;
+          const unsigned int hb = __shfl_sync(full, h, b);
+          int got = 0;
+          if (tid == 0) got = atomicCAS(&dev->head[b], hb, hb + 1u) == hb ? 1 : 0;
+          got = __shfl_sync(full, got, 0);
+          if (got) {
+            if (tid == 0) {
+              volatile int *slot = &a.queue[(size_t)b * a.cap + (hb & (unsigned)(a.cap - 1))];
+              int v;
+              while ((v = *slot) == 0) aq_sleep();  // the pusher has its ticket but has not written yet
+              *slot = 0;
+              t = v - 1;
+              // QUEUED -> BUSY, then take what arrived for this tile (activations after this point find
+              // BUSY and mark the tile dirty)
+              atomicExch(&a.state[t], TS_BUSY);
+              __threadfence();
+              sSides = atomicExch(&a.sides[t], 0);
+              atomicExch(&a.keys[t], ORD_POS_INF);
+            }
+            break;
+          }
+          if (tid == 0 && a.profile) atomicAdd(&dev->pop_retries, 1ull);
+          continue;
+        }
+        int stop = 0;  // read once per warp so that all lanes take the same branch
+        if (tid == 0)
+          stop = *reinterpret_cast<volatile int *>(&dev->pending) <= 0 || *reinterpret_cast<volatile int *>(&dev->abort_flag);
+        if (__shfl_sync(full, stop, 0)) break;
+        aq_sleep(spins < 4 ? 100u << spins : 2000u);  // back off: idle CTAs must not hammer the queue counters
+        if (++spins > a.spin_limit) {
+          if (tid == 0) atomicExch(&dev->abort_flag, 1);
+          break;
+        }
+      }
+      if (tid == 0) sTile = t;
+    }
+    for (int k = tid; k < MKP * (BYN + 2); k += FILL_THREADS) sMark[k] = 0;
+    __syncthreads();  // publishes sTile / sSides; all warps are done with smem of the previous tile
+    const int t = sTile;
+    if (t < 0) break;
+    const int tyT = t / a.tilesX, txT = t - tyT * a.tilesX;
+    const int x0 = txT * TX, y0 = tyT * TY;
+
+    // ---- stage W (+apron) and Z ----
+    if (tid == 0) {
+      sFlags = 0;
+      sKey = ORD_POS_INF;
+      sProf[0] = sProf[1] = 0;
+    }
+    if (a.use_tma) {
+      if (tid == 0) {
+        fence_proxy_async_all();
+        mbar_arrive_expect_tx(&mbar, W_TILE_BYTES + Z_TILE_BYTES);
+        tma_load_2d(sW, &mapW, x0, y0, &mbar);
+        tma_load_2d(sZ, &mapZ, x0 + PADL, y0 + 1, &mbar);
+      }
+    } else {
+      for (int k = tid; k < SROWS * (SP / 4); k += FILL_THREADS) {
+        const int rr = k / (SP / 4), cc = k - rr * (SP / 4);
+        reinterpret_cast<float4 *>(sW)[k] =
+            __ldcg(reinterpret_cast<const float4 *>(a.Wp + (size_t)(y0 + rr) * a.pitch + x0) + cc);
+      }
+      for (int k = tid; k < TY * (TX / 4); k += FILL_THREADS) {
+        const int rr = k / (TX / 4), cc = k - rr * (TX / 4);
+        reinterpret_cast<float4 *>(sZ)[k] = __ldg(
+            reinterpret_cast<const float4 *>(a.Zp + (size_t)(y0 + 1 + rr) * a.pitch + x0 + PADL) + cc);
+      }
+    }
+    int sides = sSides;
+    // seeded tile (start of a fill, or a ghost row was replaced): boundary cells may lie inside the
+    // tile when the raster edge is not tile-aligned, so relax every block once
+    if (sides == 0) sides = SIDE_FULL;
+    const int lane = tid & 31, wrp = tid >> 5;
+    {
+      int cntw = 0;
+#pragma unroll
+      for (int q = 0; q < SEG / 32; q++) {
+        const int b = wrp * SEG + 32 * q + lane;  // this warp's share of the blocks
+        const int bx = b % BXN, by = b / BXN;
+        bool on = (sides & SIDE_FULL) != 0;
+        on |= (sides & SIDE_N) && by == 0;
+        on |= (sides & SIDE_S) && by == BYN - 1;
+        on |= (sides & SIDE_W) && bx == 0;
+        on |= (sides & SIDE_E) && bx == BXN - 1;
+        on |= (sides & SIDE_NW) && b == 0;
+        on |= (sides & SIDE_NE) && b == BXN - 1;
+        on |= (sides & SIDE_SW) && b == NBLK - BXN;
+        on |= (sides & SIDE_SE) && b == NBLK - 1;
+        on &= b < NBLK;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (on) sList[0][wrp][cntw + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)b;
+        cntw += __popc(bal);
+      }
+      if (lane == 0) sCnt[0][wrp] = cntw;
+    }
+    if (a.use_tma) {
+      mbar_wait(&mbar, phase);
+      phase ^= 1;
+    }
+    __syncthreads();  // list 0 complete; (non-TMA path) tile staged
+
+    int f = 0;        // edge/corner-changed flags gathered by this thread
+    float kmin = __int_as_float(0x7f800000);  // lowest new water level this thread put on a tile edge
+    int iters = 0;
+    int cl = 0;       // current list
+    bool again = false;
+    int segn[NWARP];
+    int nlist = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < NWARP; w2++) {
+      segn[w2] = sCnt[0][w2];
+      nlist += segn[w2];
+    }
+    while (nlist > 0) {
+      for (int i = tid; i < nlist; i += FILL_THREADS) {
+        // i-th entry of the concatenated per-warp segments
+        int seg = 0, off = i;
+#pragma unroll
+        for (int w2 = 0; w2 < NWARP - 1; w2++) {
+          if (seg == w2 && off >= segn[w2]) {
+            off -= segn[w2];
+            seg = w2 + 1;
+          }
+        }
+        const int b = sList[cl][seg][off];
+        const int bx = b % BXN, by = b / BXN;
+        const int srow = 4 * by + 1, scol = 4 * bx + PADL;
+        float v[6][6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          const float *row = &sW[(srow - 1 + j) * SP + scol];
+          const float4 m4 = *reinterpret_cast<const float4 *>(row);
+          v[j][0] = row[-1]; v[j][1] = m4.x; v[j][2] = m4.y; v[j][3] = m4.z; v[j][4] = m4.w; v[j][5] = row[4];
+        }
+        float z[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float4 z4 = *reinterpret_cast<const float4 *>(&sZ[(4 * by + j) * TX + 4 * bx]);
+          z[j][0] = z4.x; z[j][1] = z4.y; z[j][2] = z4.z; z[j][3] = z4.w;
+        }
+        uint32_t ch = 0;
+        // Forward then backward Gauss-Seidel pass.  new = min(v, max(z, min8)) is evaluated as
+        //   min( min(v, max(z, min(7 other neighbours))),  max(z, just-updated neighbour) )
+        // (min/max distribute; no NaNs here), so the serial dependence between consecutive cells of a
+        // row is two FMNMX long instead of the whole stencil.
+#pragma unroll
+        for (int j = 1; j <= 4; j++) {
+#pragma unroll
+          for (int i2 = 1; i2 <= 4; i2++) {
+            const float zz = z[j - 1][i2 - 1];
+            const float others = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
+                                       min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]), v[j][i2 + 1]);
+            const float b0 = fminf(v[j][i2], fmaxf(zz, STEP ? others + 1.0f : others));
+            const float nw = fminf(b0, fmaxf(zz, STEP ? v[j][i2 - 1] + 1.0f : v[j][i2 - 1]));  // updated one step ago
+            if (nw < v[j][i2]) ch |= 1u << ((j - 1) * 4 + (i2 - 1));
+            v[j][i2] = nw;
+          }
+        }
+#pragma unroll
+        for (int j = 4; j >= 1; j--) {
+#pragma unroll
+          for (int i2 = 4; i2 >= 1; i2--) {
+            const float zz = z[j - 1][i2 - 1];
+            const float others = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
+                                       min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]), v[j][i2 - 1]);
+            const float b0 = fminf(v[j][i2], fmaxf(zz, STEP ? others + 1.0f : others));
+            const float nw = fminf(b0, fmaxf(zz, STEP ? v[j][i2 + 1] + 1.0f : v[j][i2 + 1]));  // updated one step ago
+            if (nw < v[j][i2]) ch |= 1u << ((j - 1) * 4 + (i2 - 1));
+            v[j][i2] = nw;
+          }
+        }
+        if (ch) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (ch & (0xFu << (4 * j))) {
+              *reinterpret_cast<float4 *>(&sW[(srow + j) * SP + scol]) =
+                  make_float4(v[j + 1][1], v[j + 1][2], v[j + 1][3], v[j + 1][4]);
+            }
+          }
+          unsigned char *mk = &sMark[(by + 1) * MKP + (bx + 1)];
+          mk[0] = 1;  // two passes are not a local fixed point: look at this block again
+          if (ch & 0x000Fu) mk[-MKP] = 1;
+          if (ch & 0xF000u) mk[MKP] = 1;
+          if (ch & 0x1111u) mk[-1] = 1;
+          if (ch & 0x8888u) mk[1] = 1;
+          if (ch & 0x0001u) mk[-MKP - 1] = 1;
+          if (ch & 0x0008u) mk[-MKP + 1] = 1;
+          if (ch & 0x1000u) mk[MKP - 1] = 1;
+          if (ch & 0x8000u) mk[MKP + 1] = 1;
+          // which tile edges / corners / watched raster rows did this block touch?
+          if (by == 0 && (ch & 0x000Fu)) f |= SIDE_N;
+          if (by == BYN - 1 && (ch & 0xF000u)) f |= SIDE_S;
+          if (bx == 0 && (ch & 0x1111u)) f |= SIDE_W;
+          if (bx == BXN - 1 && (ch & 0x8888u)) f |= SIDE_E;
+          if (b == 0 && (ch & 0x0001u)) f |= SIDE_NW;
+          if (b == BXN - 1 && (ch & 0x0008u)) f |= SIDE_NE;
+          if (b == NBLK - BXN && (ch & 0x1000u)) f |= SIDE_SW;
+          if (b == NBLK - 1 && (ch & 0x8000u)) f |= SIDE_SE;
+          {
+            const int gy0 = y0 + 4 * by;  // raster row of this block's row 0
+            const int j1 = 1 - gy0, j2 = (a.H - 2) - gy0;
+            if (j1 >= 0 && j1 < 4 && (ch & (0xFu << (4 * j1)))) f |= 1 << 9;
+            if (j2 >= 0 && j2 < 4 && (ch & (0xFu << (4 * j2)))) f |= 1 << 10;
+          }
+          f |= 1 << (12 + by);  // block row `by` holds a changed cell (bits 12..27)
+          if (bx == 0 || by == 0 || bx == BXN - 1 || by == BYN - 1) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+              for (int i2 = 0; i2 < 4; i2++)
+                if (ch & (1u << (4 * j + i2))) kmin = fminf(kmin, v[j + 1][i2 + 1]);
+          }
+        }
+      }
+      if (a.profile && tid == 0) {
+        sProf[0] += nlist;
+        sProf[1] += (nlist + 31) / 32;
+      }
+      iters++;
+      __syncthreads();  // marks and W rows of this pass are visible; list `cl` is consumed
+      // compact the marks into the other list: each warp scans its share and fills its own segment
+      {
+        int cntw = 0;
+#pragma unroll
+        for (int q = 0; q < SEG / 32; q++) {
+          const int b = wrp * SEG + 32 * q + lane;
+          const int mi = (b / BXN + 1) * MKP + (b % BXN) + 1;
+          const bool on = (b < NBLK) && sMark[mi] != 0;
+          if (on) sMark[mi] = 0;
+          const unsigned bal = __ballot_sync(0xffffffffu, on);
+          if (on) sList[cl ^ 1][wrp][cntw + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)b;
+          cntw += __popc(bal);
+        }
+        if (lane == 0) sCnt[cl ^ 1][wrp] = cntw;
+      }
+      __syncthreads();
+      cl ^= 1;
+      nlist = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < NWARP; w2++) {
+        segn[w2] = sCnt[cl][w2];
+        nlist += segn[w2];
+      }
+      if (nlist > 0 && max_iters > 0 && iters >= max_iters) {
+        again = true;  // not at the local fixed point yet: revisit (fully) next round
+        break;
+      }
+    }
+    // ---- write back, then activate neighbours ----
+    if (f) {
+      atomicOr(&sFlags, f);
+      if (f & 0xFF) atomicMin(&sKey, f2ord(kmin));
+    }
+    __syncthreads();
+    const int fl = sFlags;
+    const int rowch = (fl >> 12) & 0xFFFF;
+    if (rowch) {
+      for (int k = tid; k < TY * (TX / 4); k += FILL_THREADS) {
+        const int rr = k / (TX / 4), cc = k % (TX / 4);
+        if (rowch & (1 << (rr >> 2))) {
+          const float4 val = *reinterpret_cast<const float4 *>(&sW[(rr + 1) * SP + PADL + 4 * cc]);
+          __stcg(reinterpret_cast<float4 *>(a.Wp + (size_t)(y0 + 1 + rr) * a.pitch + (x0 + PADL)) + cc, val);
+        }
+      }
+      __threadfence();  // my rows are visible device-wide before any neighbour is told about them
+    }
+    __syncthreads();    // ... and every thread's rows are
+    if (rowch && tid < 8) {
+      const bool n_ok = tyT > 0, s_ok = tyT < a.tilesY - 1, w_ok = txT > 0, e_ok = txT < a.tilesX - 1;
+      int nb = -1, bits = 0;
+      switch (tid) {
+        case 0: if ((fl & SIDE_N) && n_ok) { nb = t - a.tilesX; bits = SIDE_S; } break;
+        case 1: if ((fl & SIDE_S) && s_ok) { nb = t + a.tilesX; bits = SIDE_N; } break;
+        case 2: if ((fl & SIDE_W) && w_ok) { nb = t - 1; bits = SIDE_E; } break;
+        case 3: if ((fl & SIDE_E) && e_ok) { nb = t + 1; bits = SIDE_W; } break;
+        case 4: if ((fl & SIDE_NW) && n_ok && w_ok) { nb = t - a.tilesX - 1; bits = SIDE_SE; } break;
+        case 5: if ((fl & SIDE_NE) && n_ok && e_ok) { nb = t - a.tilesX + 1; bits = SIDE_SW; } break;
+        case 6: if ((fl & SIDE_SW) && s_ok && w_ok) { nb = t + a.tilesX - 1; bits = SIDE_NE; } break;
+        default: if ((fl & SIDE_SE) && s_ok && e_ok) { nb = t + a.tilesX + 1; bits = SIDE_NW; } break;
+      }
+      if (nb >= 0) aq_activate(a, nb, bits, sKey);
+    }
+    __syncthreads();  // all activations of this visit are out before the tile is released
+    if (tid == 0) {
+      atomicAdd(&dev->visits, 1ull);
+      atomicAdd(&dev->iters, (unsigned long long)iters);
+      if (again) {  // iteration cap: not at the local fixed point, relax every block again
+        atomicOr(&a.sides[t], SIDE_FULL);
+        atomicCAS(&a.state[t], TS_BUSY, TS_BUSY_DIRTY);
+      }
+      __threadfence();
+      if (atomicCAS(&a.state[t], TS_BUSY, TS_IDLE) == TS_BUSY) {
+        atomicSub(&dev->pending, 1);
+      } else {
+        // activated while it was being relaxed: straight back into a queue (still counted in `pending`)
+        const int k = *reinterpret_cast<volatile int *>(&a.keys[t]);
+        atomicExch(&a.state[t], TS_QUEUED);
+        aq_push(a, t, aq_bucket(dev, k));
+        if (a.profile) atomicAdd(&dev->requeues, 1ull);
+      }
+    }
+  }
+}
+
+// perimeter tiles of the tile grid start QUEUED in bucket 0 with every block dirty
+__global__ void __launch_bounds__(256) fill_async_seed_kernel(const AsyncArgs a, const int *__restrict__ tiles, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = tiles[i];
+  a.sides[t] = SIDE_FULL;
+  a.keys[t] = f2ord(-__int_as_float(0x7f800000));
+  a.state[t] = TS_QUEUED;
+  atomicAdd(&a.dev->pending, 1);
+  aq_push(a, t, 0);
+}
+
 // ---- level-ordered mode: split the round's worklist into admitted / postponed tiles ----------
 // Tiles whose lowest incoming water level is above the round's level are carried over to the next
 // round untouched (their side masks and keys move to the other parity); flooding then proceeds
@@ -957,6 +1396,85 @@ struct FillState {
     return hd->edge_changed | (still_active ? 4 : 0);
   }
 
+  // fill_async = 1: one cooperative launch of persistent CTAs draining per-level tile queues (see
+  // fill_async_kernel).  Whole-raster fills only; the row-band protocol keeps the round engine.
+  void run_async() {
+    Ctx &c = ctx();
+    const size_t nt = (size_t)tilesX * tilesY;
+    int cap = 1024;  // ring size per bucket: a power of two above the tile count (a tile is queued at most once)
+    while ((size_t)cap <= nt) cap <<= 1;
+    DevBuf<int> state(nt), queue((size_t)AQ_BUCKETS * cap);
+    DevBuf<AsyncDev> adev(1);
+    RDB_CK(cudaMemsetAsync(state.p, 0, nt * sizeof(int), c.stream));
+    RDB_CK(cudaMemsetAsync(queue.p, 0, (size_t)AQ_BUCKETS * cap * sizeof(int), c.stream));
+    RDB_CK(cudaMemsetAsync(sides.p, 0, nt * sizeof(int), c.stream));  // begin() seeded the round engine's lists
+    fill_i32_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, c.stream>>>(keys.p, ORD_POS_INF, (int)nt);
+    AsyncDev *h0 = (AsyncDev *)c.pinned;
+    memset(h0, 0, sizeof(AsyncDev));
+    for (int b = 0; b < AQ_BUCKETS; b++) {
+      float thr = __builtin_inff();
+      if (!levels.empty() && b < AQ_BUCKETS - 1) {
+        const size_t k = (size_t)((double)(b + 1) / AQ_BUCKETS * (double)levels.size());
+        thr = levels[k < levels.size() ? k : levels.size() - 1];
+      }
+      h0->thr[b] = thr;
+    }
+    RDB_CK(cudaMemcpyAsync(adev.p, h0, sizeof(AsyncDev), cudaMemcpyHostToDevice, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    AsyncArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Zp = Zp.p;
+    a.Wp = Wp.p;
+    a.pitch = pitch;
+    a.W = W;
+    a.H = H;
+    a.tilesX = tilesX;
+    a.tilesY = tilesY;
+    a.state = state.p;
+    a.sides = sides.p;
+    a.keys = keys.p;
+    a.queue = queue.p;
+    a.cap = cap;
+    a.dev = adev.p;
+    a.max_iters = (int)c.params.fill_max_iters;
+    a.use_tma = (int)c.params.fill_use_tma;
+    a.profile = (int)c.params.fill_profile;
+    a.spin_limit = c.params.fill_async_spin > 0 ? c.params.fill_async_spin : 4000000;
+    std::vector<int> init;
+    for (int ty = 0; ty < tilesY; ty++)
+      for (int tx = 0; tx < tilesX; tx++)
+        if (ty == 0 || tx == 0 || ty == tilesY - 1 || tx == tilesX - 1) init.push_back(ty * tilesX + tx);
+    DevBuf<int> dinit(init.size());
+    RDB_CK(cudaMemcpyAsync(dinit.p, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    fill_async_seed_kernel<<<(unsigned)((init.size() + 255) / 256), 256, 0, c.stream>>>(a, dinit.p, (int)init.size());
+    RDB_CK(cudaGetLastError());
+    int per_sm = 0;
+    RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_async_kernel, FILL_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    long long blocks = (long long)c.num_sms * per_sm;
+    if (blocks > (long long)nt) blocks = (long long)nt;
+    void *args[] = {(void *)&mapW, (void *)&mapZ, (void *)&a};
+    KernelTimer kt;
+    RDB_CK(cudaLaunchCooperativeKernel((const void *)fill_async_kernel, dim3((unsigned)blocks), dim3(FILL_THREADS), args, 0, c.stream));
+    kt.stop_async();
+    count_launch(3);
+    AsyncDev *hd = (AsyncDev *)c.pinned;
+    RDB_CK(cudaMemcpyAsync(hd, adev.p, sizeof(AsyncDev), cudaMemcpyDeviceToHost, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    c.stats.ms_main_kernel += kt.ms();
+    if (hd->abort_flag || hd->pending != 0)
+      fail("fill (async engine): the tile queues did not drain (pending=%d, watchdog=%d)", hd->pending, hd->abort_flag);
+    still_active = false;
+    first_run = false;
+    c.stats.fill_rounds = 1;
+    c.stats.fill_tile_visits = (int64_t)hd->visits;
+    c.stats.fill_tile_iters = (int64_t)hd->iters;
+    c.stats.fill_tile_cells = TX * TY;
+    if (c.params.fill_profile)
+      fprintf(stderr, "[fill async] visits=%llu iters=%llu requeues=%llu pop_retries=%llu\n", hd->visits, hd->iters, hd->requeues,
+              hd->pop_retries);
+  }
+
   void read_row(int y, float *d_row) {
     if (y < 0 || y >= H) fail("fill_read_row: row %d out of range", y);
     RDB_CK(cudaMemcpyAsync(d_row, Wp.p + (size_t)(y + 1) * pitch + PADL, (size_t)W * 4,
@@ -1036,7 +1554,8 @@ void fill_depressions_dev(float *d_dem, int w, int h) {
   if (w <= 2 || h <= 2) return;  // every cell is a border cell: nothing can change
   FillState st;
   st.begin(d_dem, w, h);
-  st.run();
+  if (c.params.fill_async) st.run_async();
+  else st.run();
   st.finish(d_dem);
   RDB_CK(cudaStreamSynchronize(c.stream));
 }

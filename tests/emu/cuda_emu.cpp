@@ -85,6 +85,10 @@ size_t g_nstacks = 0;
 unsigned long long g_progress = 0;  // barrier releases + fiber exits (deadlock detection)
 
 void yield() { rdb_emu_switch(&g_cur->sp, g_sched_sp); }
+}  // namespace
+bool in_kernel() { return g_cur != nullptr; }
+void yield_now() { yield(); }
+namespace {
 
 void release_block_if_complete(Block *b) {
   if (b->live > 0 && b->arrived == b->live) {
@@ -153,6 +157,7 @@ void ensure_stacks(size_t n) {
 
 void run_fibers(Launch &l, size_t first, size_t count) {
   size_t remaining = count;
+  size_t idle_passes = 0;
   while (remaining) {
     const unsigned long long before = g_progress;
     for (size_t i = first; i < first + count; i++) {
@@ -166,8 +171,10 @@ void run_fibers(Launch &l, size_t first, size_t count) {
     }
     // every live fiber was resumed once; if none finished and no barrier completed, they are all
     // parked at barriers that can never complete
-    if (remaining && g_progress == before) {
-      fprintf(stderr, "rdb_emu: deadlock -- %zu threads are waiting at barriers that cannot complete\n", remaining);
+    // (spin-waits with __nanosleep may legitimately take a few passes without a barrier completing)
+    idle_passes = (remaining && g_progress == before) ? idle_passes + 1 : 0;
+    if (idle_passes > 20000) {
+      fprintf(stderr, "rdb_emu: deadlock -- %zu threads made no progress for 20000 scheduler passes\n", remaining);
       abort();
     }
   }
@@ -232,6 +239,21 @@ void launch(dim3 grid, dim3 block, const std::function<void()> &body, bool coope
   }
   g_launch = nullptr;
   g_cur = nullptr;
+}
+
+static uint64_t g_chaos = 0;
+static bool g_chaos_init = false;
+void maybe_yield() {
+  if (!g_chaos_init) {
+    g_chaos_init = true;
+    const char *s = getenv("RDB_EMU_CHAOS");
+    g_chaos = s ? (uint64_t)strtoull(s, nullptr, 10) * 0x9E3779B97F4A7C15ull + 1 : 0;
+  }
+  if (!g_chaos || !g_cur) return;
+  g_chaos ^= g_chaos << 13;
+  g_chaos ^= g_chaos >> 7;
+  g_chaos ^= g_chaos << 17;
+  if ((g_chaos & 7) == 0) yield();
 }
 
 void sync_block() {
@@ -306,6 +328,10 @@ void asm_stub(const char *text) {
 }
 
 }  // namespace rdb_emu
+
+void rdb_emu_nanosleep() {
+  if (rdb_emu::in_kernel()) rdb_emu::yield_now();
+}
 
 // ---- runtime stand-ins ----
 struct rdb_emu_stream { int dummy; };

@@ -128,6 +128,9 @@ void sync_grid();
 // warp collectives over the live lanes of the calling thread's warp; `val` travels as 64 bits
 uint64_t warp_exchange(uint64_t val, int src_lane_or_neg, unsigned *ballot_out, int pred);
 int lane_id();
+bool in_kernel();
+void yield_now();
+void maybe_yield();  // RDB_EMU_CHAOS=<seed>: atomics yield at random so that blocks interleave differently
 void asm_stub(const char *text);
 // block-local "shared memory": one object per __shared__ declaration and concurrently running block
 struct SharedSlot {
@@ -149,6 +152,8 @@ cudaError_t launch_coop(void (*f)(A...), dim3 grid, dim3 block, void **args, siz
 
 static inline void __syncthreads() { rdb_emu::sync_block(); }
 static inline int __syncthreads_count(int pred) { return rdb_emu::sync_block_count(pred); }
+void rdb_emu_nanosleep();
+static inline void __nanosleep(unsigned) { rdb_emu_nanosleep(); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline void __syncwarp(unsigned = 0xffffffffu) {
@@ -220,14 +225,14 @@ static inline float __fmul_rn(float a, float b) { return a * b; }
 // ---- atomics (single OS thread: plain read-modify-write) ----
 template <class T> struct rdb_emu_id { typedef T type; };
 #define RDB_EMU_ARG(T) typename rdb_emu_id<T>::type
-template <class T> static inline T atomicAdd(T *p, RDB_EMU_ARG(T) v) { const T o = *p; *p = o + v; return o; }
-template <class T> static inline T atomicSub(T *p, RDB_EMU_ARG(T) v) { const T o = *p; *p = o - v; return o; }
-template <class T> static inline T atomicMin(T *p, RDB_EMU_ARG(T) v) { const T o = *p; if (v < o) *p = v; return o; }
-template <class T> static inline T atomicMax(T *p, RDB_EMU_ARG(T) v) { const T o = *p; if (v > o) *p = v; return o; }
-template <class T> static inline T atomicOr(T *p, RDB_EMU_ARG(T) v) { const T o = *p; *p = o | v; return o; }
-template <class T> static inline T atomicAnd(T *p, RDB_EMU_ARG(T) v) { const T o = *p; *p = o & v; return o; }
-template <class T> static inline T atomicExch(T *p, RDB_EMU_ARG(T) v) { const T o = *p; *p = v; return o; }
-template <class T> static inline T atomicCAS(T *p, RDB_EMU_ARG(T) cmp, RDB_EMU_ARG(T) v) { const T o = *p; if (o == cmp) *p = v; return o; }
+template <class T> static inline T atomicAdd(T *p, RDB_EMU_ARG(T) v) { rdb_emu::maybe_yield(); const T o = *p; *p = o + v; return o; }
+template <class T> static inline T atomicSub(T *p, RDB_EMU_ARG(T) v) { rdb_emu::maybe_yield(); const T o = *p; *p = o - v; return o; }
+template <class T> static inline T atomicMin(T *p, RDB_EMU_ARG(T) v) { rdb_emu::maybe_yield(); const T o = *p; if (v < o) *p = v; return o; }
+template <class T> static inline T atomicMax(T *p, RDB_EMU_ARG(T) v) { rdb_emu::maybe_yield(); const T o = *p; if (v > o) *p = v; return o; }
+template <class T> static inline T atomicOr(T *p, RDB_EMU_ARG(T) v) { rdb_emu::maybe_yield(); const T o = *p; *p = o | v; return o; }
+template <class T> static inline T atomicAnd(T *p, RDB_EMU_ARG(T) v) { rdb_emu::maybe_yield(); const T o = *p; *p = o & v; return o; }
+template <class T> static inline T atomicExch(T *p, RDB_EMU_ARG(T) v) { rdb_emu::maybe_yield(); const T o = *p; *p = v; return o; }
+template <class T> static inline T atomicCAS(T *p, RDB_EMU_ARG(T) cmp, RDB_EMU_ARG(T) v) { rdb_emu::maybe_yield(); const T o = *p; if (o == cmp) *p = v; return o; }
 
 // ---- cooperative groups (the subset the sources use) ----
 namespace cooperative_groups {

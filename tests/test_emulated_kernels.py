@@ -58,7 +58,7 @@ def emulated(emu_lib, monkeypatch):
     for name, value in (("fill_ordered", 1), ("fill_max_iters", 0), ("fill_rounds_per_sync", 16), ("flats_tiled", 1),
                         ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0), ("accum_agg", 0), ("accum_tail", 0),
                         ("accum_tail_budget", 0), ("accum_walk_lanes", 0), ("accum_fused_prep", 0),
-                        ("flats_uf_tiled", 0)):
+                        ("flats_uf_tiled", 0), ("fill_async", 0)):
         _lib.set_param(name, value)
 
 
@@ -111,7 +111,7 @@ def test_in_place_and_copy_semantics(emulated, gp):
     ("fill_ordered", 0), ("fill_max_iters", 1), ("fill_max_iters", 2), ("fill_rounds_per_sync", 1), ("fill_order_rounds", 40),
     ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
     ("accum_agg", 1), ("accum_tail", 5), ("accum_tail", 1 << 20), ("accum_walk_lanes", 1),
-    ("accum_fused_prep", 1), ("flats_uf_tiled", 1),
+    ("accum_fused_prep", 1), ("flats_uf_tiled", 1), ("fill_async", 1),
 ])
 def test_algorithm_variants_agree(emulated, gp, checker, param, value):
     """Every tunable is a schedule / layout choice; none may change a result."""
@@ -221,6 +221,22 @@ def test_fused_d8_preparation_block_seams(emulated, gp, checker, shape):
         assert np.array_equal(got, expected), (shape, lanes)
 
 
+@pytest.mark.parametrize("shape,q", [((150, 200), None), ((300, 420), 0.5), ((64, 64), None), ((65, 129), 1.0), ((3, 3), None),
+                                     ((200, 1500), None), ((640, 700), 2.0)])
+def test_async_fill_engine(emulated, gp, checker, shape, q):
+    """fill_async: persistent CTAs draining per-level tile queues (tile states IDLE / QUEUED / BUSY / BUSY_DIRTY).
+    Also with the in-tile iteration cap, which exercises the re-queue of a tile by the CTA that holds it."""
+    import richdem_b200 as rd
+    dem = oracle.fbm_terrain(*shape, seed=shape[0] + shape[1], quantum=q)
+    expected = checker.fill_depressions(dem)
+    _lib.set_param("fill_async", 1)
+    for cap in (0, 2):
+        _lib.set_param("fill_max_iters", cap)
+        got = np.asarray(rd.FillDepressions(gp.R(dem)))
+        assert np.array_equal(got, expected), (shape, cap)
+        assert _lib.stats()["fill_tile_visits"] > 0
+
+
 def test_cooperative_kernels_with_several_blocks():
     """The cooperative kernels (multi-receiver level kernel with its tail mode and block-aggregated appends, the
     persistent BFS) size their grid from the SM count; re-run their cases with 3 emulated SMs so that they execute as
@@ -228,9 +244,9 @@ def test_cooperative_kernels_with_several_blocks():
     import subprocess
     if os.environ.get("RDB_EMU_SMS"):
         pytest.skip("already inside the multi-block run")
-    env = dict(os.environ, RDB_EMU_SMS="3")
+    env = dict(os.environ, RDB_EMU_SMS="3", RDB_EMU_CHAOS="7")  # CHAOS: atomics yield at random -> other interleavings
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.abspath(__file__), "-k",
-                        "variants or band_accumulation or special_rasters or degenerate"],
+                        "variants or band_accumulation or special_rasters or degenerate or async"],
                        env=env, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 

@@ -13,6 +13,7 @@ ref.copy_(d)
 _lib.check(L.rdb200_dev_fill_depressions_d8_f32(ref.data_ptr(), N, N))
 st = _lib.stats()
 print(f"N={N} baseline ms_total={st['ms_total']:.2f} sweep_ms={st['ms_main_kernel']:.2f} rounds={st['fill_rounds']} visits={st['fill_tile_visits']} iters={st['fill_tile_iters']}", flush=True)
+# e.g.  python tools/fill_profile.py 32768 "" fill_async=1 fill_async=1,fill_ordered=0   (wrap in `timeout`)
 configs = sys.argv[2:] or [""]
 for cfg in configs:
     kv = [a.split("=") for a in cfg.split(",") if a]
