@@ -522,7 +522,10 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
 //     budget turns a protocol bug into an error instead of a hang.
 // The in-tile relaxation is the same code as in fill_sweep_kernel<0>.
 // =================================================================================================
-constexpr int AQ_BUCKETS = 32;
+#ifndef RDB_AQ_BUCKETS
+#define RDB_AQ_BUCKETS 32
+#endif
+constexpr int AQ_BUCKETS = RDB_AQ_BUCKETS;  // <= 32: lane b of the popping warp watches bucket b
 enum : int { TS_IDLE = 0, TS_QUEUED = 1, TS_BUSY = 2, TS_BUSY_DIRTY = 3 };
 
 struct AsyncDev {
@@ -531,6 +534,7 @@ struct AsyncDev {
   float thr[AQ_BUCKETS];  // bucket b takes levels <= thr[b]; the last one is +inf
   int pending;            // tiles QUEUED or BUSY
   int abort_flag;         // set by the spin watchdog
+  int edge_changed;       // bit0: raster row 1 changed, bit1: raster row H-2 changed (row-band protocol)
   unsigned long long visits, iters, requeues, pop_retries;
 };
 
@@ -588,10 +592,10 @@ __device__ __forceinline__ void aq_activate(const AsyncArgs &a, int nb, int bits
   }
 }
 
+template <int STEP>
 __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     fill_async_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ,
                       const AsyncArgs a) {
-  constexpr int STEP = 0;
   __shared__ __align__(128) float sW[SROWS * SP];
   __shared__ __align__(128) float sZ[TY * TX];
   __shared__ __align__(8) unsigned long long mbar;
@@ -908,6 +912,7 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
         default: if ((fl & SIDE_SE) && s_ok && e_ok) { nb = t + a.tilesX + 1; bits = SIDE_NW; } break;
       }
       if (nb >= 0) aq_activate(a, nb, bits, sKey);
+      if (tid == 0 && (fl & (3 << 9))) atomicOr(&dev->edge_changed, (fl >> 9) & 3);
     }
     __syncthreads();  // all activations of this visit are out before the tile is released
     if (tid == 0) {
@@ -931,16 +936,12 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
   }
 }
 
-// perimeter tiles of the tile grid start QUEUED in bucket 0 with every block dirty
+// host-chosen seeds (perimeter tiles at the start, every tile in distance mode, tiles next to a replaced
+// ghost row later): every block dirty, always eligible
 __global__ void __launch_bounds__(256) fill_async_seed_kernel(const AsyncArgs a, const int *__restrict__ tiles, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int t = tiles[i];
-  a.sides[t] = SIDE_FULL;
-  a.keys[t] = f2ord(-__int_as_float(0x7f800000));
-  a.state[t] = TS_QUEUED;
-  atomicAdd(&a.dev->pending, 1);
-  aq_push(a, t, 0);
+  aq_activate(a, tiles[i], SIDE_FULL, f2ord(-__int_as_float(0x7f800000)));
 }
 
 // ---- level-ordered mode: split the round's worklist into admitted / postponed tiles ----------
@@ -1244,6 +1245,7 @@ struct FillState {
     if (per_sm < 1) per_sm = 1;
     grid = c.num_sms * per_sm;
     round = 1;  // stamps start at 0, so round numbers (used as stamp values) start at 1
+    use_async = c.params.fill_async != 0;
     // initial worklist: every tile on the perimeter of the tile grid (the only tiles whose
     // cells can see a finite neighbour at the start)
     std::vector<int> init;
@@ -1294,6 +1296,7 @@ struct FillState {
     if (per_sm < 1) per_sm = 1;
     grid = c.num_sms * per_sm;
     round = 1;
+    use_async = c.params.fill_async != 0;
     std::vector<int> init((size_t)nt);
     for (size_t t = 0; t < nt; t++) init[t] = (int)t;
     seed_worklist(init);
@@ -1304,6 +1307,10 @@ struct FillState {
   void seed_worklist(const std::vector<int> &tiles) {
     Ctx &c = ctx();
     if (tiles.empty()) return;
+    if (use_async) {  // queued by the next run_async()
+      a_seeds.insert(a_seeds.end(), tiles.begin(), tiles.end());
+      return;
+    }
     DevBuf<int> d(tiles.size());
     RDB_CK(cudaMemcpyAsync(d.p, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
     FillArgs a = make_args();
@@ -1343,6 +1350,7 @@ struct FillState {
   // result then says so); the caller exchanges halos and calls run again
   int run(int64_t max_rounds = 0) {
     Ctx &c = ctx();
+    if (use_async) return run_async();
     int64_t rounds_this_call = 0;
     FillArgs a = make_args();
     const int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 16);
@@ -1397,30 +1405,39 @@ struct FillState {
   }
 
   // fill_async = 1: one cooperative launch of persistent CTAs draining per-level tile queues (see
-  // fill_async_kernel).  Whole-raster fills only; the row-band protocol keeps the round engine.
-  void run_async() {
+  // fill_async_kernel) instead of rounds.  Runs to quiescence; in the row-band protocol every call
+  // between two halo exchanges is one such launch.
+  bool use_async = false;
+  DevBuf<int> a_state, a_queue;
+  DevBuf<AsyncDev> a_dev;
+  int a_cap = 0;
+  std::vector<int> a_seeds;
+
+  int run_async() {
     Ctx &c = ctx();
     const size_t nt = (size_t)tilesX * tilesY;
-    int cap = 1024;  // ring size per bucket: a power of two above the tile count (a tile is queued at most once)
-    while ((size_t)cap <= nt) cap <<= 1;
-    DevBuf<int> state(nt), queue((size_t)AQ_BUCKETS * cap);
-    DevBuf<AsyncDev> adev(1);
-    RDB_CK(cudaMemsetAsync(state.p, 0, nt * sizeof(int), c.stream));
-    RDB_CK(cudaMemsetAsync(queue.p, 0, (size_t)AQ_BUCKETS * cap * sizeof(int), c.stream));
-    RDB_CK(cudaMemsetAsync(sides.p, 0, nt * sizeof(int), c.stream));  // begin() seeded the round engine's lists
-    fill_i32_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, c.stream>>>(keys.p, ORD_POS_INF, (int)nt);
-    AsyncDev *h0 = (AsyncDev *)c.pinned;
-    memset(h0, 0, sizeof(AsyncDev));
-    for (int b = 0; b < AQ_BUCKETS; b++) {
-      float thr = __builtin_inff();
-      if (!levels.empty() && b < AQ_BUCKETS - 1) {
-        const size_t k = (size_t)((double)(b + 1) / AQ_BUCKETS * (double)levels.size());
-        thr = levels[k < levels.size() ? k : levels.size() - 1];
+    AsyncDev *hd = (AsyncDev *)c.pinned;
+    if (a_cap == 0) {
+      a_cap = 1024;  // ring size per bucket: a power of two above the tile count (a tile is queued at most once)
+      while ((size_t)a_cap <= nt) a_cap <<= 1;
+      a_state.alloc(nt);
+      a_queue.alloc((size_t)AQ_BUCKETS * a_cap);
+      a_dev.alloc(1);
+      RDB_CK(cudaMemsetAsync(a_state.p, 0, nt * sizeof(int), c.stream));
+      RDB_CK(cudaMemsetAsync(a_queue.p, 0, (size_t)AQ_BUCKETS * a_cap * sizeof(int), c.stream));
+      memset(hd, 0, sizeof(AsyncDev));
+      for (int b = 0; b < AQ_BUCKETS; b++) {
+        float thr = __builtin_inff();
+        if (!levels.empty() && b < AQ_BUCKETS - 1) {
+          const size_t k = (size_t)((double)(b + 1) / AQ_BUCKETS * (double)levels.size());
+          thr = levels[k < levels.size() ? k : levels.size() - 1];
+        }
+        hd->thr[b] = thr;
       }
-      h0->thr[b] = thr;
+      RDB_CK(cudaMemcpyAsync(a_dev.p, hd, sizeof(AsyncDev), cudaMemcpyHostToDevice, c.stream));
+      RDB_CK(cudaStreamSynchronize(c.stream));
     }
-    RDB_CK(cudaMemcpyAsync(adev.p, h0, sizeof(AsyncDev), cudaMemcpyHostToDevice, c.stream));
-    RDB_CK(cudaStreamSynchronize(c.stream));
+    RDB_CK(cudaMemsetAsync(&a_dev.p->edge_changed, 0, sizeof(int), c.stream));
     AsyncArgs a;
     memset(&a, 0, sizeof(a));
     a.Zp = Zp.p;
@@ -1430,49 +1447,56 @@ struct FillState {
     a.H = H;
     a.tilesX = tilesX;
     a.tilesY = tilesY;
-    a.state = state.p;
+    a.state = a_state.p;
     a.sides = sides.p;
     a.keys = keys.p;
-    a.queue = queue.p;
-    a.cap = cap;
-    a.dev = adev.p;
+    a.queue = a_queue.p;
+    a.cap = a_cap;
+    a.dev = a_dev.p;
     a.max_iters = (int)c.params.fill_max_iters;
     a.use_tma = (int)c.params.fill_use_tma;
     a.profile = (int)c.params.fill_profile;
     a.spin_limit = c.params.fill_async_spin > 0 ? c.params.fill_async_spin : 4000000;
-    std::vector<int> init;
-    for (int ty = 0; ty < tilesY; ty++)
-      for (int tx = 0; tx < tilesX; tx++)
-        if (ty == 0 || tx == 0 || ty == tilesY - 1 || tx == tilesX - 1) init.push_back(ty * tilesX + tx);
-    DevBuf<int> dinit(init.size());
-    RDB_CK(cudaMemcpyAsync(dinit.p, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-    fill_async_seed_kernel<<<(unsigned)((init.size() + 255) / 256), 256, 0, c.stream>>>(a, dinit.p, (int)init.size());
-    RDB_CK(cudaGetLastError());
+    int launches = 0;
+    if (!a_seeds.empty()) {
+      DevBuf<int> dseeds(a_seeds.size());
+      RDB_CK(cudaMemcpyAsync(dseeds.p, a_seeds.data(), a_seeds.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+      fill_async_seed_kernel<<<(unsigned)((a_seeds.size() + 255) / 256), 256, 0, c.stream>>>(a, dseeds.p, (int)a_seeds.size());
+      RDB_CK(cudaGetLastError());
+      RDB_CK(cudaStreamSynchronize(c.stream));  // host vector / scratch go out of scope
+      a_seeds.clear();
+      launches++;
+    }
     int per_sm = 0;
-    RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_async_kernel, FILL_THREADS, 0));
+    if (step_mode) RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_async_kernel<1>, FILL_THREADS, 0));
+    else RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_async_kernel<0>, FILL_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     long long blocks = (long long)c.num_sms * per_sm;
     if (blocks > (long long)nt) blocks = (long long)nt;
     void *args[] = {(void *)&mapW, (void *)&mapZ, (void *)&a};
     KernelTimer kt;
-    RDB_CK(cudaLaunchCooperativeKernel((const void *)fill_async_kernel, dim3((unsigned)blocks), dim3(FILL_THREADS), args, 0, c.stream));
+    if (step_mode)
+      RDB_CK(cudaLaunchCooperativeKernel((const void *)fill_async_kernel<1>, dim3((unsigned)blocks), dim3(FILL_THREADS), args, 0, c.stream));
+    else
+      RDB_CK(cudaLaunchCooperativeKernel((const void *)fill_async_kernel<0>, dim3((unsigned)blocks), dim3(FILL_THREADS), args, 0, c.stream));
     kt.stop_async();
-    count_launch(3);
-    AsyncDev *hd = (AsyncDev *)c.pinned;
-    RDB_CK(cudaMemcpyAsync(hd, adev.p, sizeof(AsyncDev), cudaMemcpyDeviceToHost, c.stream));
+    count_launch(launches + 1);
+    RDB_CK(cudaMemcpyAsync(hd, a_dev.p, sizeof(AsyncDev), cudaMemcpyDeviceToHost, c.stream));
     RDB_CK(cudaStreamSynchronize(c.stream));
     c.stats.ms_main_kernel += kt.ms();
     if (hd->abort_flag || hd->pending != 0)
       fail("fill (async engine): the tile queues did not drain (pending=%d, watchdog=%d)", hd->pending, hd->abort_flag);
     still_active = false;
     first_run = false;
-    c.stats.fill_rounds = 1;
+    rounds_run++;
+    c.stats.fill_rounds = rounds_run;
     c.stats.fill_tile_visits = (int64_t)hd->visits;
     c.stats.fill_tile_iters = (int64_t)hd->iters;
     c.stats.fill_tile_cells = TX * TY;
     if (c.params.fill_profile)
       fprintf(stderr, "[fill async] visits=%llu iters=%llu requeues=%llu pop_retries=%llu\n", hd->visits, hd->iters, hd->requeues,
               hd->pop_retries);
+    return hd->edge_changed;
   }
 
   void read_row(int y, float *d_row) {
@@ -1554,8 +1578,7 @@ void fill_depressions_dev(float *d_dem, int w, int h) {
   if (w <= 2 || h <= 2) return;  // every cell is a border cell: nothing can change
   FillState st;
   st.begin(d_dem, w, h);
-  if (c.params.fill_async) st.run_async();
-  else st.run();
+  st.run();
   st.finish(d_dem);
   RDB_CK(cudaStreamSynchronize(c.stream));
 }

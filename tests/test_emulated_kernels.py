@@ -151,8 +151,11 @@ def band_drivers(emulated, monkeypatch):
     return gs
 
 
-@pytest.mark.parametrize("G", [1, 2, 3, 5])
+@pytest.mark.parametrize("G", [1, 2, 3, 5, "async"])
 def test_band_fill(band_drivers, checker, G):
+    if G == "async":  # the asynchronous engine under the row-band protocol (one launch per halo exchange)
+        _lib.set_param("fill_async", 1)
+        G = 3
     dem = oracle.fbm_terrain(330, 300, seed=31, quantum=0.5)
     got, rounds = band_drivers.emulate_bands(dem, G)
     assert np.array_equal(got, checker.fill_depressions(dem)), f"G={G} after {rounds} exchanges"
@@ -188,11 +191,14 @@ def test_band_accumulation_with_weights(band_drivers, checker):
     band_drivers.test_band_accumulation_with_weights(checker)
 
 
-@pytest.mark.parametrize("G", [2, 3, 5, "uf_tiled"])
+@pytest.mark.parametrize("G", [2, 3, 5, "uf_tiled", "async"])
 def test_band_flat_resolution(band_drivers, checker, G):
     nd = -9999.0
     if G == "uf_tiled":
         _lib.set_param("flats_uf_tiled", 1)
+        G = 3
+    if G == "async":  # geodesic distances of the flat gradients on the asynchronous engine
+        _lib.set_param("fill_async", 1)
         G = 3
     dem = oracle.fbm_terrain(300, 260, seed=51, quantum=0.5)
     dem[150:170, 60:120] = nd
