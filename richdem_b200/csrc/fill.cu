@@ -640,15 +640,23 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
             if (tid == 0) {
               volatile int *slot = &a.queue[(size_t)b * a.cap + (hb & (unsigned)(a.cap - 1))];
               int v;
-              while ((v = *slot) == 0) aq_sleep();  // the pusher has its ticket but has not written yet
-              *slot = 0;
-              t = v - 1;
-              // QUEUED -> BUSY, then take what arrived for this tile (activations after this point find
-              // BUSY and mark the tile dirty)
-              atomicExch(&a.state[t], TS_BUSY);
-              __threadfence();
-              sSides = atomicExch(&a.sides[t], 0);
-              atomicExch(&a.keys[t], ORD_POS_INF);
+              long long w = 0;
+              while ((v = *slot) == 0) {  // the pusher has its ticket but has not written yet
+                aq_sleep();
+                if (++w > a.spin_limit) break;
+              }
+              if (v == 0) {
+                atomicExch(&dev->abort_flag, 1);  // a ticket without an entry: protocol error, stop everyone
+              } else {
+                *slot = 0;
+                t = v - 1;
+                // QUEUED -> BUSY, then take what arrived for this tile (activations after this point find
+                // BUSY and mark the tile dirty)
+                atomicExch(&a.state[t], TS_BUSY);
+                __threadfence();
+                sSides = atomicExch(&a.sides[t], 0);
+                atomicExch(&a.keys[t], ORD_POS_INF);
+              }
             }
             break;
           }
