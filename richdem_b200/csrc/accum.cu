@@ -23,6 +23,7 @@ namespace {
 constexpr uint32_t kDepsMask = 0xFFu;
 constexpr uint32_t kSrcFlag = 0x80000000u;
 constexpr int kCodeSole = 32;  // bit 5 of a code byte: this cell is the only donor of its receiver
+constexpr int kLaneChunk = 1024;  // cells a persistent warp fetches per cursor atomic (source scans)
 
 // ---- K1: dem -> compact flow code (+ rmax for D-infinity), weights/NoData initialisation ------
 template <bool DINF>
@@ -587,9 +588,296 @@ __global__ void __launch_bounds__(256) accum_levels_kernel(const WalkArgs<double
   if (gtid == 0) *levels_out = level;
 }
 
+// =================================================================================================
+// Asynchronous multi-receiver accumulation (accum_async = 1; prepared for round 2, off by default).
+// No levels and no grid barriers: persistent warps keep all 32 lanes on a ready cell.  A lane pushes
+// its cell's flow downstream, keeps the first receiver it completes and puts the others on its
+// warp's stack in shared memory; lanes without a cell take from that stack, then from the scan of
+// source cells (1024-cell chunks off a global cursor), then from a global ring that warps spill to
+// when their stack runs full or when the ring is empty and they hold more than a warp's worth.
+// Termination: a warp that finds no work anywhere counts itself idle; work is only ever created by
+// busy warps, so "every warp idle" is final.  (Cells on a cycle of a user-supplied proportions grid
+// are never ready, exactly as in the level kernel and in the reference's queue.)
+// =================================================================================================
+#ifndef RDB_AS_STACK
+#define RDB_AS_STACK 192
+#endif
+constexpr int kAsStack = RDB_AS_STACK;  // per-warp stack of ready cells (shared memory); >= 80
+static_assert(kAsStack >= 80, "the spill rule needs more than 32 entries above the high-water mark");
+struct AccAsyncDev {
+  unsigned int qhead, qtail;  // global ring of spilled ready cells (never wraps: a cell is ready once)
+  int cursor;                 // next chunk of the source scan
+  int idle;                   // warps that found no work anywhere
+  int abort_flag;
+  unsigned long long spilled, steps;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) accum_async_kernel(const WalkArgs<double> a, int ncells, int *gq, AccAsyncDev *dev,
+                                                           long long spin_limit) {
+  __shared__ int sStack[8][kAsStack];
+  __shared__ int sTop[8];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  int *stk = sStack[wrp];
+  int *topp = &sTop[wrp];
+  const int nwarps = (int)gridDim.x * 8;
+  const int W = a.W;
+  if (lane == 0) *topp = 0;
+  __syncwarp();
+  bool have = false;
+  int c = -1;
+  int pos = 0, end = 0;  // warp-uniform: source-scan window
+  bool more = true;      // the cursor may still hold chunks
+  bool counted_idle = false;
+  long long spins = 0;
+  unsigned long long steps = 0;
+  int iter = 0;
+
+  auto global_push = [&](int r) {
+    const unsigned int p = atomicAdd(&dev->qtail, 1u);
+    __threadfence();
+    *reinterpret_cast<volatile int *>(&gq[p]) = r + 1;
+  };
+  auto push = [&](int r) {  // a receiver this lane completed but does not follow itself
+    const int p = atomicAdd(topp, 1);
+    if (p < kAsStack) {
+      stk[p] = r;
+    } else {
+      atomicSub(topp, 1);
+      global_push(r);
+    }
+  };
+
+  for (;; iter++) {
+    // ---- (1) lanes without a cell take from the warp's stack ----
+    unsigned idle = __ballot_sync(full, !have);
+    int top = *reinterpret_cast<volatile int *>(topp);
+    if (idle && top > 0) {
+      const int nidle = __popc(idle);
+      const int take = nidle < top ? nidle : top;
+      const int rank = __popc(idle & lt);
+      if (!have && rank < take) {
+        c = stk[top - 1 - rank];
+        have = true;
+      }
+      __syncwarp();
+      if (lane == 0) *topp = top - take;
+      __syncwarp();
+      top -= take;
+      idle = __ballot_sync(full, !have);
+    }
+    // ---- (2) idle lanes left: scan for sources, else pull from the global ring, else rest ----
+    if (idle) {
+      if (top <= kAsStack - 32 && (pos < end || more)) {
+        if (pos >= end) {
+          int b = 0;
+          if (lane == 0) b = atomicAdd(&dev->cursor, kLaneChunk);
+          b = __shfl_sync(full, b, 0);
+          if (b >= ncells) {
+            more = false;
+          } else {
+            pos = b;
+            end = b + kLaneChunk < ncells ? b + kLaneChunk : ncells;
+          }
+        }
+        if (pos < end) {
+          const int i = pos + lane;
+          const bool src = i < end && (a.st[i] & kSrcFlag) != 0;
+          const unsigned bal = __ballot_sync(full, src);
+          if (src) stk[top + __popc(bal & lt)] = i;
+          __syncwarp();
+          if (lane == 0) *topp = top + __popc(bal);
+          __syncwarp();
+          pos += 32;
+        }
+        continue;  // hand the new entries out in (1)
+      }
+      if (!more && pos >= end) {
+        unsigned int h = 0, t = 0;
+        if (lane == 0) {
+          h = *reinterpret_cast<volatile unsigned int *>(&dev->qhead);
+          t = *reinterpret_cast<volatile unsigned int *>(&dev->qtail);
+        }
+        h = __shfl_sync(full, h, 0);
+        t = __shfl_sync(full, t, 0);
+        const int avail = (int)(t - h);
+        if (avail > 0) {
+          if (counted_idle) {  // about to take work: no longer idle
+            if (lane == 0) atomicSub(&dev->idle, 1);
+            counted_idle = false;
+          }
+          const int nidle = __popc(idle);
+          const int want = avail < nidle ? avail : nidle;
+          int got = 0;
+          if (lane == 0) got = atomicCAS(&dev->qhead, h, h + (unsigned)want) == h ? 1 : 0;
+          got = __shfl_sync(full, got, 0);
+          if (got) {
+            const int rank = __popc(idle & lt);
+            if (!have && rank < want) {
+              volatile int *slot = &gq[h + (unsigned)rank];
+              int v;
+              long long w = 0;
+              while ((v = *slot) == 0) {  // the pusher has its ticket but has not written yet
+                __nanosleep(100);
+                if (++w > spin_limit) break;
+              }
+              if (v == 0) {
+                atomicExch(&dev->abort_flag, 1);
+              } else {
+                c = v - 1;
+                have = true;
+              }
+            }
+          }
+          continue;
+        }
+        if (idle == full && top == 0) {  // nothing anywhere for this warp
+          int fin = 0;
+          if (lane == 0) {
+            if (!counted_idle) atomicAdd(&dev->idle, 1);
+            fin = *reinterpret_cast<volatile int *>(&dev->idle) >= nwarps || *reinterpret_cast<volatile int *>(&dev->abort_flag);
+          }
+          counted_idle = true;
+          if (__shfl_sync(full, fin, 0)) break;
+          __nanosleep(spins < 4 ? 200u << spins : 3000u);
+          if (++spins > spin_limit) {
+            if (lane == 0) atomicExch(&dev->abort_flag, 1);
+            break;
+          }
+          continue;
+        }
+      }
+    }
+    spins = 0;
+    // ---- (3) one step for every lane that holds a ready cell ----
+    if (have) {
+      const double acc = __ldcg(a.accum + c);
+      int next = -1;
+      if (MODE == 1) {
+        const int cd = a.code[c];
+        if (cd != kCodeNoData && (cd & 15) != 0) {
+          const int n1 = cd & 15;
+          const int r1 = c + d8dy(n1) * W + d8dx(n1);
+          if (cd & kCodeTwo) {
+            const int n2 = nwrap(n1 + 1);
+            const int r2 = c + d8dy(n2) * W + d8dx(n2);
+            float p1, p2;
+            tarboton_props(a.rmaxArr[c], &p1, &p2);
+            const bool live1 = p1 > 0, live2 = p2 > 0;
+            if (live1) atomicAdd(a.accum + r1, (double)p1 * acc);
+            if (live2) atomicAdd(a.accum + r2, (double)p2 * acc);
+            __threadfence();
+            if (live1 && (atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
+            if (live2 && (atomicSub(a.st + r2, 1u) & kDepsMask) == 1u) {
+              if (next < 0) next = r2;
+              else push(r2);
+            }
+          } else {
+            atomicAdd(a.accum + r1, acc);
+            __threadfence();
+            if ((atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
+          }
+        }
+      } else {
+        const int y = c / W, x = c - y * W;
+        if (!(x == 0 || y == 0 || x == W - 1 || y == a.H - 1)) {  // edge cells carry no flow
+          const float *p = a.props + (size_t)9 * c;
+          uint32_t sent = 0;
+#pragma unroll
+          for (int k = 1; k <= 8; k++) {
+            const float pk = p[k];
+            if (pk <= 0) continue;
+            const int r = c + d8dy(k) * W + d8dx(k);
+            if (a.props[(size_t)9 * r] == kNoDataGen) continue;
+            atomicAdd(a.accum + r, (double)pk * acc);
+            sent |= 1u << k;
+          }
+          if (sent) {
+            __threadfence();
+#pragma unroll
+            for (int k = 1; k <= 8; k++) {
+              if (!(sent & (1u << k))) continue;
+              const int r = c + d8dy(k) * W + d8dx(k);
+              if ((atomicSub(a.st + r, 1u) & kDepsMask) == 1u) {
+                if (next < 0) next = r;
+                else push(r);
+              }
+            }
+          }
+        }
+      }
+      steps++;
+      if (next >= 0) c = next;
+      else have = false;
+    }
+    __syncwarp();
+    // ---- (4) share: a stack close to full always spills a warp's worth; every 16 steps also when the
+    //      global ring is empty and this warp holds more than it can use itself ----
+    {
+      const int top2 = *reinterpret_cast<volatile int *>(topp);
+      int spill = top2 > kAsStack - 40 ? 1 : 0;
+      if (!spill && (iter & 15) == 15 && top2 > 64) {
+        int empty = 0;
+        if (lane == 0)
+          empty = *reinterpret_cast<volatile unsigned int *>(&dev->qhead) == *reinterpret_cast<volatile unsigned int *>(&dev->qtail);
+        spill = __shfl_sync(full, empty, 0);
+      }
+      if (spill) {
+        const int r = stk[top2 - 1 - lane];  // top2 > 32 in both cases
+        __syncwarp();
+        if (lane == 0) *topp = top2 - 32;
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(&dev->qtail, 32u);
+        base = __shfl_sync(full, base, 0);
+        __threadfence();
+        *reinterpret_cast<volatile int *>(&gq[base + (unsigned)lane]) = r + 1;
+        if (lane == 0) atomicAdd(&dev->spilled, 32ull);
+        __syncwarp();
+      }
+    }
+  }
+  if (lane == 0 && steps) atomicAdd(&dev->steps, steps);
+}
+
+template <int MODE>
+void run_accum_async(WalkArgs<double> a, size_t ncells) {
+  Ctx &c = ctx();
+  DevBuf<int> gq(ncells);
+  DevBuf<AccAsyncDev> dev(1);
+  RDB_CK(cudaMemsetAsync(gq.p, 0, ncells * sizeof(int), c.stream));
+  RDB_CK(cudaMemsetAsync(dev.p, 0, sizeof(AccAsyncDev), c.stream));
+  int per_sm = 0;
+  RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_async_kernel<MODE>, 256, 0));
+  if (per_sm < 1) per_sm = 1;
+  long long blocks = (long long)c.num_sms * per_sm;
+  const long long need = ((long long)ncells + kLaneChunk - 1) / kLaneChunk;
+  if (blocks * 8 > need) blocks = (need + 7) / 8;
+  int nc = (int)ncells;
+  int *q = gq.p;
+  AccAsyncDev *d = dev.p;
+  long long spin = 2000000;
+  void *args[] = {(void *)&a, (void *)&nc, (void *)&q, (void *)&d, (void *)&spin};
+  KernelTimer kt;
+  RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_async_kernel<MODE>, dim3((unsigned)blocks), dim3(256), args, 0, c.stream));
+  count_launch();
+  kt.stop_async();
+  AccAsyncDev *h = (AccAsyncDev *)c.pinned;
+  RDB_CK(cudaMemcpyAsync(h, dev.p, sizeof(AccAsyncDev), cudaMemcpyDeviceToHost, c.stream));
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  c.stats.ms_main_kernel += kt.ms();
+  if (h->abort_flag) fail("accumulation (async engine): watchdog expired (qhead=%u qtail=%u idle=%d)", h->qhead, h->qtail, h->idle);
+  c.stats.accum_rounds = 1;
+}
+
 template <int MODE>
 void run_levels(WalkArgs<double> a, size_t ncells) {
   Ctx &c = ctx();
+  if (c.params.accum_async) {
+    run_accum_async<MODE>(a, ncells);
+    return;
+  }
   DevBuf<int> fr0(ncells), fr1(ncells), cnt(4);
   RDB_CK(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(int), c.stream));
   int per_sm = 0;
@@ -926,7 +1214,6 @@ __global__ void __launch_bounds__(256) accum_walk_packed_kernel(const uint8_t *_
 // are in flight.  Here a warp pulls chunks of cells from a global cursor, compacts their sources
 // (ballot + popc) into a small queue in shared memory, and every lane whose walk has ended takes
 // the next source from that queue; the loop body is one converged walk step for all 32 lanes.
-constexpr int kLaneChunk = 1024;  // cells fetched per cursor atomic
 constexpr int kLaneQueue = 128;   // per-warp source queue (power of two, >= 64)
 
 template <bool BAND>

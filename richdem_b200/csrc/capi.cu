@@ -233,6 +233,7 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "accum_agg") p.accum_agg = value;
   else if (n == "accum_walk_lanes") p.accum_walk_lanes = value;
   else if (n == "accum_fused_prep") p.accum_fused_prep = value;
+  else if (n == "accum_async") p.accum_async = value;
   else if (n == "flats_tiled") p.flats_tiled = value;
   else if (n == "fill_async") p.fill_async = value;
   else if (n == "fill_async_spin") p.fill_async_spin = value;

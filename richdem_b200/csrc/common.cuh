@@ -66,6 +66,7 @@ struct Params {
   int64_t flats_uf_tiled = 0;  // union-find: unite inside 64x16 tiles in shared memory first, then across tile seams
   int64_t flats_tiled = 1;   // flat-resolution gradients by the tile engine (0: one cooperative BFS launch each)
   int64_t accum_packed = 1;  // unit-weight D8: accumulator and donor count share one 64-bit word
+  int64_t accum_async = 0;        // multi-receiver accumulation without levels: persistent warps, per-warp stacks, a spill ring
   int64_t accum_fused_prep = 0;   // unit-weight D8: flow codes + donor counts + sole-donor bits in one rolling-window pass
   int64_t accum_walk_lanes = 0;   // unit-weight D8 walk: persistent always-busy lanes fed from per-warp source queues
   int64_t accum_threads = 256;

@@ -58,7 +58,7 @@ def emulated(emu_lib, monkeypatch):
     for name, value in (("fill_ordered", 1), ("fill_max_iters", 0), ("fill_rounds_per_sync", 16), ("flats_tiled", 1),
                         ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0), ("accum_agg", 0), ("accum_tail", 0),
                         ("accum_tail_budget", 0), ("accum_walk_lanes", 0), ("accum_fused_prep", 0),
-                        ("flats_uf_tiled", 0), ("fill_async", 0)):
+                        ("flats_uf_tiled", 0), ("fill_async", 0), ("accum_async", 0)):
         _lib.set_param(name, value)
 
 
@@ -111,7 +111,7 @@ def test_in_place_and_copy_semantics(emulated, gp):
     ("fill_ordered", 0), ("fill_max_iters", 1), ("fill_max_iters", 2), ("fill_rounds_per_sync", 1), ("fill_order_rounds", 40),
     ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
     ("accum_agg", 1), ("accum_tail", 5), ("accum_tail", 1 << 20), ("accum_walk_lanes", 1),
-    ("accum_fused_prep", 1), ("flats_uf_tiled", 1), ("fill_async", 1),
+    ("accum_fused_prep", 1), ("flats_uf_tiled", 1), ("fill_async", 1), ("accum_async", 1),
 ])
 def test_algorithm_variants_agree(emulated, gp, checker, param, value):
     """Every tunable is a schedule / layout choice; none may change a result."""
@@ -243,6 +243,44 @@ def test_async_fill_engine(emulated, gp, checker, shape, q):
         assert _lib.stats()["fill_tile_visits"] > 0
 
 
+def _spread_to_all_lower_neighbours(dem):
+    """An 8-receiver proportions grid (equal shares to every lower neighbour); edge cells carry no flow, as in every
+    FM_* output (the reference's accumulation never bounds-checks receivers, flow_accumulation_generic.hpp:84-87)."""
+    h, w = dem.shape
+    p = np.zeros((h, w, 9), np.float32)
+    d8x = [0, -1, -1, 0, 1, 1, 1, 0, -1]
+    d8y = [0, 0, -1, -1, -1, 0, 1, 1, 1]
+    for n in range(1, 9):
+        sh = np.full_like(dem, np.inf)
+        ys = slice(max(0, -d8y[n]), h - max(0, d8y[n]))
+        xs = slice(max(0, -d8x[n]), w - max(0, d8x[n]))
+        sh[ys, xs] = dem[ys.start + d8y[n]:ys.stop + d8y[n], xs.start + d8x[n]:xs.stop + d8x[n]]
+        p[:, :, n] = sh < dem
+    p[0, :, :] = p[-1, :, :] = 0
+    p[:, 0, :] = p[:, -1, :] = 0
+    s_ = p[:, :, 1:].sum(axis=2, keepdims=True)
+    p[:, :, 1:] = np.where(s_ > 0, p[:, :, 1:] / np.maximum(s_, 1), 0)
+    return p
+
+
+@pytest.mark.parametrize("mode", ["levels", "agg_tail", "async"])
+def test_eight_receiver_proportions(emulated, gp, checker, mode):
+    """FlowAccumulation(props) on graphs with up to 8 receivers per cell (a cone with huge fan-in, and fBm), on the
+    level kernel, its tail / aggregated variants and the asynchronous engine."""
+    import richdem_b200 as rd
+    if mode == "agg_tail":
+        _lib.set_param("accum_agg", 1)
+        _lib.set_param("accum_tail", 100)
+    if mode == "async":
+        _lib.set_param("accum_async", 1)
+    yy, xx = np.mgrid[0:201, 0:231]
+    cone = np.hypot(yy - 100, xx - 115).astype(np.float32)
+    for dem in (cone, checker.resolve_flats(checker.fill_depressions(oracle.fbm_terrain(260, 300, seed=5)), gp.ND)):
+        props = _spread_to_all_lower_neighbours(dem)
+        got = np.asarray(rd.FlowAccumFromProps(rd.rd3array(props, no_data=-2)))
+        np.testing.assert_allclose(got, checker.flow_accumulation(props), rtol=1e-9, atol=0)
+
+
 def test_cooperative_kernels_with_several_blocks():
     """The cooperative kernels (multi-receiver level kernel with its tail mode and block-aggregated appends, the
     persistent BFS) size their grid from the SM count; re-run their cases with 3 emulated SMs so that they execute as
@@ -252,7 +290,7 @@ def test_cooperative_kernels_with_several_blocks():
         pytest.skip("already inside the multi-block run")
     env = dict(os.environ, RDB_EMU_SMS="3", RDB_EMU_CHAOS="7")  # CHAOS: atomics yield at random -> other interleavings
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.abspath(__file__), "-k",
-                        "variants or band_accumulation or special_rasters or degenerate or async"],
+                        "variants or band_accumulation or special_rasters or degenerate or async or eight_receiver"],
                        env=env, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 

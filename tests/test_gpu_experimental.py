@@ -19,7 +19,7 @@ from richdem_b200 import _lib
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not os.environ.get("RDB_TEST_EXPERIMENTAL"), reason="opt-in: RDB_TEST_EXPERIMENTAL=1")]
 ND = -9999.0
-SWITCHES = ("fill_async", "accum_fused_prep", "accum_walk_lanes", "accum_agg", "accum_tail", "accum_tail_budget",
+SWITCHES = ("fill_async", "accum_async", "accum_fused_prep", "accum_walk_lanes", "accum_agg", "accum_tail", "accum_tail_budget",
             "flats_uf_tiled")
 
 
@@ -36,7 +36,7 @@ def switches():
 
 CONFIGS = [{"accum_fused_prep": 1}, {"accum_walk_lanes": 1}, {"accum_fused_prep": 1, "accum_walk_lanes": 1},
            {"accum_agg": 1}, {"accum_tail": 2048}, {"accum_agg": 1, "accum_tail": 64, "accum_tail_budget": 3},
-           {"flats_uf_tiled": 1}, {"fill_async": 1}]
+           {"flats_uf_tiled": 1}, {"fill_async": 1}, {"accum_async": 1}]
 
 
 @pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()))
@@ -78,3 +78,27 @@ def test_switch_at_8192_matches_default(switches, cfg):
     acc = torch.empty((N, N), dtype=torch.float64, device="cuda")
     _lib.check(L.rdb200_dev_fa_d8_f32_f64(w.data_ptr(), acc.data_ptr(), N, N, ND, 1))
     assert torch.equal(acc, acc0)
+
+
+@pytest.mark.parametrize("cfg", [{}, {"accum_agg": 1, "accum_tail": 2048}, {"accum_async": 1}], ids=lambda c: ",".join(c) or "default")
+def test_eight_receiver_proportions(checker, switches, cfg):
+    """FlowAccumulation(props) with up to 8 receivers per cell (equal shares to every lower neighbour)."""
+    for k, v in cfg.items():
+        _lib.set_param(k, v)
+    dem = checker.resolve_flats(checker.fill_depressions(oracle.fbm_terrain(900, 1100, seed=5)), ND)
+    h, w = dem.shape
+    p = np.zeros((h, w, 9), np.float32)
+    d8x = [0, -1, -1, 0, 1, 1, 1, 0, -1]
+    d8y = [0, 0, -1, -1, -1, 0, 1, 1, 1]
+    for n in range(1, 9):
+        sh = np.full_like(dem, np.inf)
+        ys = slice(max(0, -d8y[n]), h - max(0, d8y[n]))
+        xs = slice(max(0, -d8x[n]), w - max(0, d8x[n]))
+        sh[ys, xs] = dem[ys.start + d8y[n]:ys.stop + d8y[n], xs.start + d8x[n]:xs.stop + d8x[n]]
+        p[:, :, n] = sh < dem
+    p[0, :, :] = p[-1, :, :] = 0
+    p[:, 0, :] = p[:, -1, :] = 0
+    s_ = p[:, :, 1:].sum(axis=2, keepdims=True)
+    p[:, :, 1:] = np.where(s_ > 0, p[:, :, 1:] / np.maximum(s_, 1), 0)
+    got = np.asarray(rd.FlowAccumFromProps(rd.rd3array(p, no_data=-2)))
+    np.testing.assert_allclose(got, checker.flow_accumulation(p), rtol=1e-9, atol=0)

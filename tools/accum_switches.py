@@ -30,10 +30,11 @@ if DINF:
     _lib.check(L.rdb200_dev_resolve_flats_epsilon_f32(dem.data_ptr(), N, N, ND))
 acc = torch.empty((N, N), dtype=torch.float64, device="cuda")
 
-ALL = ("accum_fused_prep", "accum_walk_lanes", "accum_agg", "accum_tail", "accum_tail_budget")
+ALL = ("accum_fused_prep", "accum_walk_lanes", "accum_agg", "accum_tail", "accum_tail_budget", "accum_async")
 if DINF:
     configs = [{}, {"accum_agg": 1}, {"accum_tail": 1024}, {"accum_tail": 4096}, {"accum_tail": 4096, "accum_tail_budget": 128},
-               {"accum_agg": 1, "accum_tail": 4096}, {"accum_agg": 1, "accum_tail": 16384, "accum_tail_budget": 64}]
+               {"accum_agg": 1, "accum_tail": 4096}, {"accum_agg": 1, "accum_tail": 16384, "accum_tail_budget": 64},
+               {"accum_async": 1}]
 else:
     configs = [{}, {"accum_fused_prep": 1}, {"accum_walk_lanes": 1}, {"accum_fused_prep": 1, "accum_walk_lanes": 1}]
 
