@@ -8,6 +8,10 @@ uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
 
 extern "C" int rdb200_emulated(void) { return 1; }  // marker: the product loader rejects this library
+// scheduler passes over all launches so far: every pass advances each live thread to its next barrier, so
+// the count is a crude, hardware-free proxy for the critical path of a schedule (tools only)
+static unsigned long long g_total_passes = 0;
+extern "C" unsigned long long rdb_emu_passes(void) { return g_total_passes; }
 
 // ---- context switch: callee-saved registers + stack pointer ----
 extern "C" void rdb_emu_switch(void **save_sp, void *load_sp);
@@ -159,6 +163,7 @@ void run_fibers(Launch &l, size_t first, size_t count) {
   size_t remaining = count;
   size_t idle_passes = 0;
   while (remaining) {
+    g_total_passes++;
     const unsigned long long before = g_progress;
     for (size_t i = first; i < first + count; i++) {
       Fiber *f = &l.fibers[i];
@@ -203,7 +208,10 @@ void launch(dim3 grid, dim3 block, const std::function<void()> &body, bool coope
   g_launch = &l;
   blockDim = block;
   gridDim = grid;
-  const size_t concurrent_blocks = cooperative ? nblocks : 1;
+  // RDB_EMU_CONCURRENT=1: also ordinary launches of up to 2048 blocks run their blocks side by side (for the
+  // pass-count comparison of schedules; the default runs them one after another, which is faster)
+  static const bool all_concurrent = getenv("RDB_EMU_CONCURRENT") != nullptr;
+  const size_t concurrent_blocks = (cooperative || (all_concurrent && nblocks <= 2048)) ? nblocks : 1;
   ensure_stacks(concurrent_blocks * nthreads);
   l.fibers.resize(concurrent_blocks * nthreads);
   l.blocks.resize(concurrent_blocks);
