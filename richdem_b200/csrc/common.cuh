@@ -62,6 +62,7 @@ struct Params {
   int64_t fill_band_rounds = 0;   // row-band mode: rounds per rdb200_dev_fill_run call (0: to convergence)
   int64_t fill_profile = 0;     // 1: collect + print in-tile work counters (slower)
   int64_t fill_async = 0;        // whole-raster fill by one cooperative launch draining per-level tile queues (no rounds)
+  int64_t fill_async_thick = 0;  // queue entries from which a bucket is claimed by fetch-add tickets instead of CAS (0: 256)
   int64_t fill_async_spin = 0;   // spin budget of an idle CTA before the watchdog aborts the launch (0: 4e6)
   int64_t flats_uf_tiled = 0;  // union-find: unite inside 64x16 tiles in shared memory first, then across tile seams
   int64_t flats_tiled = 1;   // flat-resolution gradients by the tile engine (0: one cooperative BFS launch each)

@@ -554,6 +554,7 @@ struct AsyncArgs {
   int use_tma;
   int profile;
   long long spin_limit;
+  int thick;  // entries from which a bucket is claimed by fetch-add tickets
 };
 
 __device__ __forceinline__ void aq_sleep(unsigned ns = 100) { __nanosleep(ns); }
@@ -568,10 +569,22 @@ __device__ __forceinline__ int aq_bucket(const AsyncDev *dev, int key_ord) {
   return b;
 }
 
+// Queue protocol.  A ring slot holds 0 (empty), tile + 1, or -1 (a consumer gave its ticket back).
+// Consumers claim from a well-filled bucket with an unconditional fetch-add on `head` -- a
+// compare-and-swap there succeeds about once per memory round trip however many CTAs try, far
+// below the ~30 pops/us a B200 needs -- so `head` can briefly run ahead of `tail`; a consumer whose
+// slot stays empty for long hands the ticket back by writing -1, and the pusher that later lands
+// on such a slot clears it and draws the next ticket.  Thin buckets are claimed by compare-and-swap.
 __device__ __forceinline__ void aq_push(const AsyncArgs &a, int t, int b) {
-  const unsigned int p = atomicAdd(&a.dev->tail[b], 1u);
-  __threadfence();
-  *reinterpret_cast<volatile int *>(&a.queue[(size_t)b * a.cap + (p & (unsigned)(a.cap - 1))]) = t + 1;
+  __threadfence();  // state / sides / keys / tile data are visible before the entry is
+  for (;;) {
+    const unsigned int p = atomicAdd(&a.dev->tail[b], 1u);
+    int *slot = &a.queue[(size_t)b * a.cap + (p & (unsigned)(a.cap - 1))];
+    const int old = atomicCAS(slot, 0, t + 1);
+    if (old == 0) return;
+    // old == -1: that ticket was handed back; recycle the slot and take the next one
+    atomicExch(slot, 0);
+  }
 }
 
 // tell tile `nb` that the apron sides `bits` changed (lowest new level `key_ord`)
@@ -631,36 +644,59 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
         }
         const unsigned ne = __ballot_sync(full, (int)(tl - h) > 0);
         if (ne) {
-          const int b = __ffs((int)ne) - 1;
-          const unsigned int hb = __shfl_sync(full, h, b);
-          int got = 0;
-          if (tid == 0) got = atomicCAS(&dev->head[b], hb, hb + 1u) == hb ? 1 : 0;
-          got = __shfl_sync(full, got, 0);
-          if (got) {
+          // Lowest level first.  A bucket holding plenty (>= a.thick entries: more than the CTAs that can
+          // race for them in one memory round trip) is claimed with an unconditional fetch-add ticket;
+          // a thin one with a single compare-and-swap, and whoever loses that moves on to the next bucket
+          // instead of retrying, so a crowd of idle CTAs neither serialises on one counter nor draws
+          // tickets for entries that do not exist.
+          int res = -1;
+          unsigned todo = ne;
+          while (todo && res < 0) {
+            const int b = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const unsigned int hb = __shfl_sync(full, h, b);
+            const unsigned int tb = __shfl_sync(full, tl, b);
             if (tid == 0) {
-              volatile int *slot = &a.queue[(size_t)b * a.cap + (hb & (unsigned)(a.cap - 1))];
-              int v;
-              long long w = 0;
-              while ((v = *slot) == 0) {  // the pusher has its ticket but has not written yet
-                aq_sleep();
-                if (++w > a.spin_limit) break;
+              int *slot = nullptr;
+              if ((int)(tb - hb) >= a.thick) {
+                const unsigned int tk = atomicAdd(&dev->head[b], 1u);
+                slot = &a.queue[(size_t)b * a.cap + (tk & (unsigned)(a.cap - 1))];
+              } else if (atomicCAS(&dev->head[b], hb, hb + 1u) == hb) {
+                slot = &a.queue[(size_t)b * a.cap + (hb & (unsigned)(a.cap - 1))];
+              } else if (a.profile) {
+                atomicAdd(&dev->pop_retries, 1ull);
               }
-              if (v == 0) {
-                atomicExch(&dev->abort_flag, 1);  // a ticket without an entry: protocol error, stop everyone
-              } else {
-                *slot = 0;
-                t = v - 1;
-                // QUEUED -> BUSY, then take what arrived for this tile (activations after this point find
-                // BUSY and mark the tile dirty)
-                atomicExch(&a.state[t], TS_BUSY);
-                __threadfence();
-                sSides = atomicExch(&a.sides[t], 0);
-                atomicExch(&a.keys[t], ORD_POS_INF);
+              if (slot) {
+                int v = 0;
+                for (long long w = 0; w < a.spin_limit; w++) {  // the pusher has its ticket but may not have written yet
+                  v = *reinterpret_cast<volatile int *>(slot);
+                  if (v > 0) break;
+                  aq_sleep();
+                  if (w >= 512 && (w & 63) == 0) {  // a ticket beyond the tail (over-claimed): hand it back
+                    const int old = atomicCAS(slot, 0, -1);
+                    if (old == 0) break;
+                    v = old;
+                    break;
+                  }
+                }
+                if (v > 0) {
+                  atomicExch(slot, 0);
+                  res = v - 1;
+                  // QUEUED -> BUSY, then take what arrived for this tile (activations after this point find
+                  // BUSY and mark the tile dirty)
+                  atomicExch(&a.state[res], TS_BUSY);
+                  __threadfence();
+                  sSides = atomicExch(&a.sides[res], 0);
+                  atomicExch(&a.keys[res], ORD_POS_INF);
+                }
               }
             }
+            res = __shfl_sync(full, res, 0);
+          }
+          if (res >= 0) {
+            t = res;
             break;
           }
-          if (tid == 0 && a.profile) atomicAdd(&dev->pop_retries, 1ull);
           continue;
         }
         int stop = 0;  // read once per warp so that all lanes take the same branch
@@ -1426,8 +1462,10 @@ struct FillState {
     const size_t nt = (size_t)tilesX * tilesY;
     AsyncDev *hd = (AsyncDev *)c.pinned;
     if (a_cap == 0) {
-      a_cap = 1024;  // ring size per bucket: a power of two above the tile count (a tile is queued at most once)
-      while ((size_t)a_cap <= nt) a_cap <<= 1;
+      // ring size per bucket: a power of two above the tile count (a tile is queued at most once) plus
+      // the tickets idle CTAs may hold beyond the tail
+      a_cap = 4096;
+      while ((size_t)a_cap <= nt + 4096) a_cap <<= 1;
       a_state.alloc(nt);
       a_queue.alloc((size_t)AQ_BUCKETS * a_cap);
       a_dev.alloc(1);
@@ -1465,6 +1503,7 @@ struct FillState {
     a.use_tma = (int)c.params.fill_use_tma;
     a.profile = (int)c.params.fill_profile;
     a.spin_limit = c.params.fill_async_spin > 0 ? c.params.fill_async_spin : 4000000;
+    a.thick = (int)(c.params.fill_async_thick > 0 ? c.params.fill_async_thick : 256);
     int launches = 0;
     if (!a_seeds.empty()) {
       DevBuf<int> dseeds(a_seeds.size());

@@ -245,6 +245,7 @@ void launch(dim3 grid, dim3 block, const std::function<void()> &body, bool coope
     }
     run_fibers(l, 0, concurrent_blocks * nthreads);
   }
+  if (trace) fprintf(stderr, "rdb_emu:   ... %llu scheduler passes so far\n", g_total_passes);
   g_launch = nullptr;
   g_cur = nullptr;
 }

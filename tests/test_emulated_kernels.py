@@ -58,7 +58,8 @@ def emulated(emu_lib, monkeypatch):
     for name, value in (("fill_ordered", 1), ("fill_max_iters", 0), ("fill_rounds_per_sync", 16), ("flats_tiled", 1),
                         ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0), ("accum_agg", 0), ("accum_tail", 0),
                         ("accum_tail_budget", 0), ("accum_walk_lanes", 0), ("accum_fused_prep", 0),
-                        ("flats_uf_tiled", 0), ("fill_async", 0), ("accum_async", 0)):
+                        ("flats_uf_tiled", 0), ("fill_async", 0), ("accum_async", 0),
+                        ("fill_async_thick", 0)):
         _lib.set_param(name, value)
 
 
@@ -236,10 +237,11 @@ def test_async_fill_engine(emulated, gp, checker, shape, q):
     dem = oracle.fbm_terrain(*shape, seed=shape[0] + shape[1], quantum=q)
     expected = checker.fill_depressions(dem)
     _lib.set_param("fill_async", 1)
-    for cap in (0, 2):
+    for cap, thick in ((0, 0), (2, 0), (0, 1), (2, 4)):  # thick: queue length from which tickets replace CAS claims
         _lib.set_param("fill_max_iters", cap)
+        _lib.set_param("fill_async_thick", thick)
         got = np.asarray(rd.FillDepressions(gp.R(dem)))
-        assert np.array_equal(got, expected), (shape, cap)
+        assert np.array_equal(got, expected), (shape, cap, thick)
         assert _lib.stats()["fill_tile_visits"] > 0
 
 
