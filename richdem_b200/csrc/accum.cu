@@ -591,19 +591,19 @@ __global__ void __launch_bounds__(256) accum_levels_kernel(const WalkArgs<double
 // =================================================================================================
 // Asynchronous multi-receiver accumulation (accum_async = 1; prepared for round 2, off by default).
 // No levels and no grid barriers: persistent warps keep all 32 lanes on a ready cell.  A lane pushes
-// its cell's flow downstream, keeps the first receiver it completes and puts the others on its
-// warp's stack in shared memory; lanes without a cell take from that stack, then from the scan of
+// its cell's flow downstream, keeps the first receiver it completes and appends the others to its
+// warp's FIFO in shared memory; lanes without a cell take from that FIFO, then from the scan of
 // source cells (1024-cell chunks off a global cursor), then from a global ring that warps spill to
-// when their stack runs full or when the ring is empty and they hold more than a warp's worth.
+// when their FIFO runs full or when the ring is empty and they hold more than a warp's worth.
 // Termination: a warp that finds no work anywhere counts itself idle; work is only ever created by
 // busy warps, so "every warp idle" is final.  (Cells on a cycle of a user-supplied proportions grid
 // are never ready, exactly as in the level kernel and in the reference's queue.)
 // =================================================================================================
-#ifndef RDB_AS_STACK
-#define RDB_AS_STACK 192
+#ifndef RDB_AS_RING
+#define RDB_AS_RING 256
 #endif
-constexpr int kAsStack = RDB_AS_STACK;  // per-warp stack of ready cells (shared memory); >= 80
-static_assert(kAsStack >= 80, "the spill rule needs more than 32 entries above the high-water mark");
+constexpr int kAsRing = RDB_AS_RING;  // per-warp FIFO of ready cells (shared memory); a power of two >= 128
+static_assert(kAsRing >= 128 && (kAsRing & (kAsRing - 1)) == 0, "ring size");
 struct AccAsyncDev {
   unsigned int qhead, qtail;  // global ring of spilled ready cells (never wraps: a cell is ready once)
   int cursor;                 // next chunk of the source scan
@@ -615,16 +615,21 @@ struct AccAsyncDev {
 template <int MODE>
 __global__ void __launch_bounds__(256) accum_async_kernel(const WalkArgs<double> a, int ncells, int *gq, AccAsyncDev *dev,
                                                            long long spin_limit) {
-  __shared__ int sStack[8][kAsStack];
-  __shared__ int sTop[8];
+  // Ready cells wait in FIFO order: a cell on the critical path of the flow graph must not sit under
+  // newer ones (a stack here tripled the number of steps the longest chain took on the CPU model).
+  __shared__ int sRing[8][kAsRing];
+  __shared__ int sHead[8], sTail[8];  // monotonic; count = tail - head
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  int *stk = sStack[wrp];
-  int *topp = &sTop[wrp];
+  int *ring = sRing[wrp];
+  int *headp = &sHead[wrp], *tailp = &sTail[wrp];
   const int nwarps = (int)gridDim.x * 8;
   const int W = a.W;
-  if (lane == 0) *topp = 0;
+  if (lane == 0) {
+    *headp = 0;
+    *tailp = 0;
+  }
   __syncwarp();
   bool have = false;
   int c = -1;
@@ -641,36 +646,38 @@ __global__ void __launch_bounds__(256) accum_async_kernel(const WalkArgs<double>
     *reinterpret_cast<volatile int *>(&gq[p]) = r + 1;
   };
   auto push = [&](int r) {  // a receiver this lane completed but does not follow itself
-    const int p = atomicAdd(topp, 1);
-    if (p < kAsStack) {
-      stk[p] = r;
+    const int p = atomicAdd(tailp, 1);
+    if (p - *reinterpret_cast<volatile int *>(headp) < kAsRing) {
+      ring[p & (kAsRing - 1)] = r;
     } else {
-      atomicSub(topp, 1);
+      atomicSub(tailp, 1);  // full (any later ticket fails as well, so the surviving ones stay contiguous)
       global_push(r);
     }
   };
 
   for (;; iter++) {
-    // ---- (1) lanes without a cell take from the warp's stack ----
+    // ---- (1) lanes without a cell take the oldest entries of the warp's FIFO ----
     unsigned idle = __ballot_sync(full, !have);
-    int top = *reinterpret_cast<volatile int *>(topp);
-    if (idle && top > 0) {
+    int head = *reinterpret_cast<volatile int *>(headp);
+    int cnt = *reinterpret_cast<volatile int *>(tailp) - head;
+    if (idle && cnt > 0) {
       const int nidle = __popc(idle);
-      const int take = nidle < top ? nidle : top;
+      const int take = nidle < cnt ? nidle : cnt;
       const int rank = __popc(idle & lt);
       if (!have && rank < take) {
-        c = stk[top - 1 - rank];
+        c = ring[(head + rank) & (kAsRing - 1)];
         have = true;
       }
       __syncwarp();
-      if (lane == 0) *topp = top - take;
+      if (lane == 0) *headp = head + take;
       __syncwarp();
-      top -= take;
+      head += take;
+      cnt -= take;
       idle = __ballot_sync(full, !have);
     }
     // ---- (2) idle lanes left: scan for sources, else pull from the global ring, else rest ----
     if (idle) {
-      if (top <= kAsStack - 32 && (pos < end || more)) {
+      if (cnt <= kAsRing - 32 && (pos < end || more)) {
         if (pos >= end) {
           int b = 0;
           if (lane == 0) b = atomicAdd(&dev->cursor, kLaneChunk);
@@ -686,9 +693,9 @@ __global__ void __launch_bounds__(256) accum_async_kernel(const WalkArgs<double>
           const int i = pos + lane;
           const bool src = i < end && (a.st[i] & kSrcFlag) != 0;
           const unsigned bal = __ballot_sync(full, src);
-          if (src) stk[top + __popc(bal & lt)] = i;
+          if (src) ring[(head + cnt + __popc(bal & lt)) & (kAsRing - 1)] = i;
           __syncwarp();
-          if (lane == 0) *topp = top + __popc(bal);
+          if (lane == 0) *tailp = head + cnt + __popc(bal);
           __syncwarp();
           pos += 32;
         }
@@ -733,7 +740,7 @@ __global__ void __launch_bounds__(256) accum_async_kernel(const WalkArgs<double>
           }
           continue;
         }
-        if (idle == full && top == 0) {  // nothing anywhere for this warp
+        if (idle == full && cnt == 0) {  // nothing anywhere for this warp
           int fin = 0;
           if (lane == 0) {
             if (!counted_idle) atomicAdd(&dev->idle, 1);
@@ -813,21 +820,22 @@ __global__ void __launch_bounds__(256) accum_async_kernel(const WalkArgs<double>
       else have = false;
     }
     __syncwarp();
-    // ---- (4) share: a stack close to full always spills a warp's worth; every 16 steps also when the
-    //      global ring is empty and this warp holds more than it can use itself ----
+    // ---- (4) share: a FIFO close to full always hands a warp's worth (its oldest entries) to the global
+    //      ring; every 16 steps also when that ring is empty and this warp holds more than it can use ----
     {
-      const int top2 = *reinterpret_cast<volatile int *>(topp);
-      int spill = top2 > kAsStack - 40 ? 1 : 0;
-      if (!spill && (iter & 15) == 15 && top2 > 64) {
+      const int head2 = *reinterpret_cast<volatile int *>(headp);
+      const int cnt2 = *reinterpret_cast<volatile int *>(tailp) - head2;
+      int spill = cnt2 > kAsRing - 72 ? 1 : 0;  // a step can add up to 32 * 7 entries; the overflow path covers the rest
+      if (!spill && (iter & 15) == 15 && cnt2 > 64) {
         int empty = 0;
         if (lane == 0)
           empty = *reinterpret_cast<volatile unsigned int *>(&dev->qhead) == *reinterpret_cast<volatile unsigned int *>(&dev->qtail);
         spill = __shfl_sync(full, empty, 0);
       }
       if (spill) {
-        const int r = stk[top2 - 1 - lane];  // top2 > 32 in both cases
+        const int r = ring[(head2 + lane) & (kAsRing - 1)];  // cnt2 > 32 in both cases
         __syncwarp();
-        if (lane == 0) *topp = top2 - 32;
+        if (lane == 0) *headp = head2 + 32;
         unsigned int base = 0;
         if (lane == 0) base = atomicAdd(&dev->qtail, 32u);
         base = __shfl_sync(full, base, 0);
