@@ -239,6 +239,7 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "fill_async_spin") p.fill_async_spin = value;
   else if (n == "fill_async_thick") p.fill_async_thick = value;
   else if (n == "flats_uf_tiled") p.flats_uf_tiled = value;
+  else if (n == "flowdirs_rolling") p.flowdirs_rolling = value;
   else if (n == "accum_packed") p.accum_packed = value;
   else fail("rdb200_set_param: unknown parameter '%s'", name);
   CAPI_END

@@ -64,6 +64,7 @@ struct Params {
   int64_t fill_async = 0;        // whole-raster fill by one cooperative launch draining per-level tile queues (no rounds)
   int64_t fill_async_thick = 0;  // queue entries from which a bucket is claimed by fetch-add tickets instead of CAS (0: 256)
   int64_t fill_async_spin = 0;   // spin budget of an idle CTA before the watchdog aborts the launch (0: 4e6)
+  int64_t flowdirs_rolling = 0;  // d8_flow_directions with a rolling three-row register window (W % 4 == 0)
   int64_t flats_uf_tiled = 0;  // union-find: unite inside 64x16 tiles in shared memory first, then across tile seams
   int64_t flats_tiled = 1;   // flat-resolution gradients by the tile engine (0: one cooperative BFS launch each)
   int64_t accum_packed = 1;  // unit-weight D8: accumulator and donor count share one 64-bit word

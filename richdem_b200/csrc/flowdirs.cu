@@ -47,6 +47,77 @@ __global__ void d8_flowdirs_kernel(const float *__restrict__ dem, uint8_t *__res
   }
 }
 
+// Rolling-window variant (flowdirs_rolling = 1, W % 4 == 0): a thread owns 4 columns and walks down a
+// chunk of rows keeping three DEM rows in registers, so every row is fetched once per block (one
+// float4 per thread, the two halo columns by shuffle) instead of nine scalar loads per cell; the
+// direction bytes leave as uchar4.  Same per-cell rule as above.
+constexpr int kDirRows = 64;
+
+__global__ void __launch_bounds__(256) d8_flowdirs_rolling_kernel(const float *__restrict__ dem, uint8_t *__restrict__ dirs,
+                                                                   int W, int H, float nodata) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int xc = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const bool col_in = xc < W;
+  const int y0 = blockIdx.y * kDirRows;
+  float d[3][6];  // rows y-1, y, y+1 ; columns xc-1 .. xc+4
+  auto load_row = [&](int gy, float(&o)[6]) {
+    const bool rin = gy >= 0 && gy < H;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rin && col_in) m = __ldg(reinterpret_cast<const float4 *>(dem + (size_t)gy * W + xc));
+    float left = __shfl_up_sync(full, m.w, 1), right = __shfl_down_sync(full, m.x, 1);
+    if (lane == 0) left = (rin && col_in && xc > 0) ? __ldg(dem + (size_t)gy * W + xc - 1) : 0.f;
+    if (lane == 31) right = (rin && xc + 4 < W) ? __ldg(dem + (size_t)gy * W + xc + 4) : 0.f;
+    o[0] = left; o[1] = m.x; o[2] = m.y; o[3] = m.z; o[4] = m.w; o[5] = right;
+  };
+  load_row(y0 - 1, d[0]);
+  load_row(y0, d[1]);
+  for (int y = y0; y < y0 + kDirRows && y < H; y++) {  // uniform across the block
+    load_row(y + 1, d[2]);
+    if (col_in) {
+      uint8_t out[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int x = xc + k;
+        const float e = d[1][k + 1];
+        int dd;
+        if (e == nodata) {
+          dd = 255;
+        } else if (x == 0 || y == 0 || x == W - 1 || y == H - 1) {
+          if (x == 0 && y == 0) dd = 2;
+          else if (x == 0 && y == H - 1) dd = 8;
+          else if (x == W - 1 && y == 0) dd = 4;
+          else if (x == W - 1 && y == H - 1) dd = 6;
+          else if (x == 0) dd = 1;
+          else if (x == W - 1) dd = 5;
+          else if (y == 0) dd = 3;
+          else dd = 7;
+        } else {
+          // neighbours n = 1..8 : W, NW, N, NE, E, SE, S, SW
+          const float ne[9] = {0.f, d[1][k], d[0][k], d[0][k + 1], d[0][k + 2], d[1][k + 2], d[2][k + 2], d[2][k + 1], d[2][k]};
+          float minimum = e;
+          int flowdir = 0;
+#pragma unroll
+          for (int n = 1; n <= 8; n++) {
+            if (ne[n] < minimum || (ne[n] == minimum && flowdir > 0 && (flowdir & 1) == 0 && (n & 1) == 1)) {
+              minimum = ne[n];
+              flowdir = n;
+            }
+          }
+          dd = flowdir;
+        }
+        out[k] = (uint8_t)dd;
+      }
+      *reinterpret_cast<uchar4 *>(dirs + (size_t)y * W + xc) = make_uchar4(out[0], out[1], out[2], out[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      d[0][k] = d[1][k];
+      d[1][k] = d[2][k];
+    }
+  }
+}
+
 // materialised proportions: 256 cells per block staged through shared memory so the 36 B/cell
 // AoS output leaves as coalesced float4 stores
 template <bool DINF>
@@ -119,8 +190,13 @@ __global__ void __launch_bounds__(256) fm_props_kernel(const float *__restrict__
 
 void d8_flow_directions_dev(const float *d_dem, uint8_t *d_dirs, int w, int h, float nodata) {
   Ctx &c = ctx();
-  dim3 blk(128), grd((w + 127) / 128, h < 16384 ? h : 16384);
-  d8_flowdirs_kernel<<<grd, blk, 0, c.stream>>>(d_dem, d_dirs, w, h, nodata);
+  if (c.params.flowdirs_rolling && (w & 3) == 0 && ((uintptr_t)d_dem & 15) == 0 && ((uintptr_t)d_dirs & 3) == 0) {
+    dim3 blk(256), grd((unsigned)((w / 4 + 255) / 256), (unsigned)((h + kDirRows - 1) / kDirRows));
+    d8_flowdirs_rolling_kernel<<<grd, blk, 0, c.stream>>>(d_dem, d_dirs, w, h, nodata);
+  } else {
+    dim3 blk(128), grd((w + 127) / 128, h < 16384 ? h : 16384);
+    d8_flowdirs_kernel<<<grd, blk, 0, c.stream>>>(d_dem, d_dirs, w, h, nodata);
+  }
   RDB_CK(cudaGetLastError());
   count_launch();
 }

@@ -59,7 +59,7 @@ def emulated(emu_lib, monkeypatch):
                         ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0), ("accum_agg", 0), ("accum_tail", 0),
                         ("accum_tail_budget", 0), ("accum_walk_lanes", 0), ("accum_fused_prep", 0),
                         ("flats_uf_tiled", 0), ("fill_async", 0), ("accum_async", 0),
-                        ("fill_async_thick", 0)):
+                        ("fill_async_thick", 0), ("flowdirs_rolling", 0)):
         _lib.set_param(name, value)
 
 
@@ -112,7 +112,7 @@ def test_in_place_and_copy_semantics(emulated, gp):
     ("fill_ordered", 0), ("fill_max_iters", 1), ("fill_max_iters", 2), ("fill_rounds_per_sync", 1), ("fill_order_rounds", 40),
     ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
     ("accum_agg", 1), ("accum_tail", 5), ("accum_tail", 1 << 20), ("accum_walk_lanes", 1),
-    ("accum_fused_prep", 1), ("flats_uf_tiled", 1), ("fill_async", 1), ("accum_async", 1),
+    ("accum_fused_prep", 1), ("flats_uf_tiled", 1), ("fill_async", 1), ("accum_async", 1), ("flowdirs_rolling", 1),
 ])
 def test_algorithm_variants_agree(emulated, gp, checker, param, value):
     """Every tunable is a schedule / layout choice; none may change a result."""
@@ -312,3 +312,13 @@ def test_tiled_union_find_seams(emulated, gp, checker, shape, q):
     assert len(np.unique(pairs[0])) == pairs.shape[1] == len(np.unique(pairs[1]))
     got = np.asarray(rd.ResolveFlats(gp.R(dem)))
     assert np.array_equal(got.view(np.uint32), checker.resolve_flats(dem, gp.ND).view(np.uint32))
+
+
+@pytest.mark.parametrize("shape", [(70, 2052), (130, 1024), (65, 1028), (3, 8), (200, 4), (64, 64), (1, 12)])
+def test_rolling_flow_directions(emulated, gp, checker, shape):
+    """flowdirs_rolling: 4 columns per thread, 64-row chunks, halo columns by shuffle; widths around the block seams."""
+    import richdem_b200 as rd
+    _lib.set_param("flowdirs_rolling", 1)
+    dem = checker.resolve_flats(checker.fill_depressions(oracle.fbm_terrain(*shape, seed=shape[1], quantum=0.5)), gp.ND)
+    dem[shape[0] // 2:, shape[1] // 2: shape[1] // 2 + 3] = gp.ND
+    assert np.array_equal(np.asarray(rd.FlowDirectionsD8(gp.R(dem))), checker.d8_flow_directions(dem, gp.ND))

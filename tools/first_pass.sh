@@ -24,7 +24,7 @@ step() {  # name, seconds, command...
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv >"$OUT/gpu.txt" 2>&1
 
 # 1. parity of each switch against the reference on small rasters (opt-in test file)
-for k in accum_fused_prep accum_walk_lanes accum_agg accum_tail accum_async flats_uf_tiled fill_async eight_receiver; do
+for k in accum_fused_prep accum_walk_lanes accum_agg accum_tail accum_async flats_uf_tiled flowdirs_rolling fill_async eight_receiver; do
   RDB_TEST_EXPERIMENTAL=1 step "parity_$k" 240 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q -k "$k"
 done
 
