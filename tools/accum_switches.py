@@ -68,3 +68,16 @@ for cfg in configs:
           f"levels={st['accum_rounds']} same={same}", flush=True)
 for k in ALL:
     _lib.set_param(k, 0)
+if not DINF:  # d8_flow_directions: default kernel vs the rolling-window one
+    dirs = torch.empty((N, N), dtype=torch.uint8, device="cuda")
+    base_dirs = None
+    for roll in (0, 1):
+        _lib.set_param("flowdirs_rolling", roll)
+        best = 1e30
+        for _ in range(3):
+            _lib.check(L.rdb200_dev_d8_flow_directions_f32(dem.data_ptr(), dirs.data_ptr(), N, N, ND))
+            best = min(best, _lib.stats()["ms_total"])
+        if base_dirs is None:
+            base_dirs = dirs.clone()
+        print(f"N={N} d8_flow_directions flowdirs_rolling={roll}: ms_total={best:.2f} same={bool(torch.equal(dirs, base_dirs))}", flush=True)
+    _lib.set_param("flowdirs_rolling", 0)
