@@ -273,185 +273,7 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
       a.sides[(r & 1) * ntiles + t] = 0;
       a.keys[(r & 1) * ntiles + t] = ORD_POS_INF;
     }
-    // seeded tile (start of a fill, or a ghost row was replaced): boundary cells may lie inside the
-    // tile when the raster edge is not tile-aligned, so relax every block once
-    if (sides == 0) sides = SIDE_FULL;
-    const int lane = tid & 31, wrp = tid >> 5;
-    {
-      int cntw = 0;
-#pragma unroll
-      for (int q = 0; q < SEG / 32; q++) {
-        const int b = wrp * SEG + 32 * q + lane;  // this warp's share of the blocks
-        const int bx = b % BXN, by = b / BXN;
-        bool on = (sides & SIDE_FULL) != 0;
-        on |= (sides & SIDE_N) && by == 0;
-        on |= (sides & SIDE_S) && by == BYN - 1;
-        on |= (sides & SIDE_W) && bx == 0;
-        on |= (sides & SIDE_E) && bx == BXN - 1;
-        on |= (sides & SIDE_NW) && b == 0;
-        on |= (sides & SIDE_NE) && b == BXN - 1;
-        on |= (sides & SIDE_SW) && b == NBLK - BXN;
-        on |= (sides & SIDE_SE) && b == NBLK - 1;
-        on &= b < NBLK;
-        const unsigned bal = __ballot_sync(0xffffffffu, on);
-        if (on) sList[0][wrp][cntw + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)b;
-        cntw += __popc(bal);
-      }
-      if (lane == 0) sCnt[0][wrp] = cntw;
-    }
-    if (a.use_tma) {
-      mbar_wait(&mbar, phase);
-      phase ^= 1;
-    }
-    __syncthreads();  // list 0 complete; (non-TMA path) tile staged
-
-    int f = 0;        // edge/corner-changed flags gathered by this thread
-    float kmin = __int_as_float(0x7f800000);  // lowest new water level this thread put on a tile edge
-    int iters = 0;
-    int cl = 0;       // current list
-    bool again = false;
-    int segn[NWARP];
-    int nlist = 0;
-#pragma unroll
-    for (int w2 = 0; w2 < NWARP; w2++) {
-      segn[w2] = sCnt[0][w2];
-      nlist += segn[w2];
-    }
-    while (nlist > 0) {
-      for (int i = tid; i < nlist; i += FILL_THREADS) {
-        // i-th entry of the concatenated per-warp segments
-        int seg = 0, off = i;
-#pragma unroll
-        for (int w2 = 0; w2 < NWARP - 1; w2++) {
-          if (seg == w2 && off >= segn[w2]) {
-            off -= segn[w2];
-            seg = w2 + 1;
-          }
-        }
-        const int b = sList[cl][seg][off];
-        const int bx = b % BXN, by = b / BXN;
-        const int srow = 4 * by + 1, scol = 4 * bx + PADL;
-        float v[6][6];
-#pragma unroll
-        for (int j = 0; j < 6; j++) {
-          const float *row = &sW[(srow - 1 + j) * SP + scol];
-          const float4 m4 = *reinterpret_cast<const float4 *>(row);
-          v[j][0] = row[-1]; v[j][1] = m4.x; v[j][2] = m4.y; v[j][3] = m4.z; v[j][4] = m4.w; v[j][5] = row[4];
-        }
-        float z[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float4 z4 = *reinterpret_cast<const float4 *>(&sZ[(4 * by + j) * TX + 4 * bx]);
-          z[j][0] = z4.x; z[j][1] = z4.y; z[j][2] = z4.z; z[j][3] = z4.w;
-        }
-        uint32_t ch = 0;
-        // Forward then backward Gauss-Seidel pass.  new = min(v, max(z, min8)) is evaluated as
-        //   min( min(v, max(z, min(7 other neighbours))),  max(z, just-updated neighbour) )
-        // (min/max distribute; no NaNs here), so the serial dependence between consecutive cells of a
-        // row is two FMNMX long instead of the whole stencil.
-#pragma unroll
-        for (int j = 1; j <= 4; j++) {
-#pragma unroll
-          for (int i2 = 1; i2 <= 4; i2++) {
-            const float zz = z[j - 1][i2 - 1];
-            const float others = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
-                                       min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]), v[j][i2 + 1]);
-            const float b0 = fminf(v[j][i2], fmaxf(zz, STEP ? others + 1.0f : others));
-            const float nw = fminf(b0, fmaxf(zz, STEP ? v[j][i2 - 1] + 1.0f : v[j][i2 - 1]));  // updated one step ago
-            if (nw < v[j][i2]) ch |= 1u << ((j - 1) * 4 + (i2 - 1));
-            v[j][i2] = nw;
-          }
-        }
-#pragma unroll
-        for (int j = 4; j >= 1; j--) {
-#pragma unroll
-          for (int i2 = 4; i2 >= 1; i2--) {
-            const float zz = z[j - 1][i2 - 1];
-            const float others = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
-                                       min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]), v[j][i2 - 1]);
-            const float b0 = fminf(v[j][i2], fmaxf(zz, STEP ? others + 1.0f : others));
-            const float nw = fminf(b0, fmaxf(zz, STEP ? v[j][i2 + 1] + 1.0f : v[j][i2 + 1]));  // updated one step ago
-            if (nw < v[j][i2]) ch |= 1u << ((j - 1) * 4 + (i2 - 1));
-            v[j][i2] = nw;
-          }
-        }
-        if (ch) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            if (ch & (0xFu << (4 * j))) {
-              *reinterpret_cast<float4 *>(&sW[(srow + j) * SP + scol]) =
-                  make_float4(v[j + 1][1], v[j + 1][2], v[j + 1][3], v[j + 1][4]);
-            }
-          }
-          unsigned char *mk = &sMark[(by + 1) * MKP + (bx + 1)];
-          mk[0] = 1;  // two passes are not a local fixed point: look at this block again
-          if (ch & 0x000Fu) mk[-MKP] = 1;
-          if (ch & 0xF000u) mk[MKP] = 1;
-          if (ch & 0x1111u) mk[-1] = 1;
-          if (ch & 0x8888u) mk[1] = 1;
-          if (ch & 0x0001u) mk[-MKP - 1] = 1;
-          if (ch & 0x0008u) mk[-MKP + 1] = 1;
-          if (ch & 0x1000u) mk[MKP - 1] = 1;
-          if (ch & 0x8000u) mk[MKP + 1] = 1;
-          // which tile edges / corners / watched raster rows did this block touch?
-          if (by == 0 && (ch & 0x000Fu)) f |= SIDE_N;
-          if (by == BYN - 1 && (ch & 0xF000u)) f |= SIDE_S;
-          if (bx == 0 && (ch & 0x1111u)) f |= SIDE_W;
-          if (bx == BXN - 1 && (ch & 0x8888u)) f |= SIDE_E;
-          if (b == 0 && (ch & 0x0001u)) f |= SIDE_NW;
-          if (b == BXN - 1 && (ch & 0x0008u)) f |= SIDE_NE;
-          if (b == NBLK - BXN && (ch & 0x1000u)) f |= SIDE_SW;
-          if (b == NBLK - 1 && (ch & 0x8000u)) f |= SIDE_SE;
-          {
-            const int gy0 = y0 + 4 * by;  // raster row of this block's row 0
-            const int j1 = 1 - gy0, j2 = (a.H - 2) - gy0;
-            if (j1 >= 0 && j1 < 4 && (ch & (0xFu << (4 * j1)))) f |= 1 << 9;
-            if (j2 >= 0 && j2 < 4 && (ch & (0xFu << (4 * j2)))) f |= 1 << 10;
-          }
-          f |= 1 << (12 + by);  // block row `by` holds a changed cell (bits 12..27)
-          if (bx == 0 || by == 0 || bx == BXN - 1 || by == BYN - 1) {
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-#pragma unroll
-              for (int i2 = 0; i2 < 4; i2++)
-                if (ch & (1u << (4 * j + i2))) kmin = fminf(kmin, v[j + 1][i2 + 1]);
-          }
-        }
-      }
-      if (a.profile && tid == 0) {
-        sProf[0] += nlist;
-        sProf[1] += (nlist + 31) / 32;
-      }
-      iters++;
-      __syncthreads();  // marks and W rows of this pass are visible; list `cl` is consumed
-      // compact the marks into the other list: each warp scans its share and fills its own segment
-      {
-        int cntw = 0;
-#pragma unroll
-        for (int q = 0; q < SEG / 32; q++) {
-          const int b = wrp * SEG + 32 * q + lane;
-          const int mi = (b / BXN + 1) * MKP + (b % BXN) + 1;
-          const bool on = (b < NBLK) && sMark[mi] != 0;
-          if (on) sMark[mi] = 0;
-          const unsigned bal = __ballot_sync(0xffffffffu, on);
-          if (on) sList[cl ^ 1][wrp][cntw + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)b;
-          cntw += __popc(bal);
-        }
-        if (lane == 0) sCnt[cl ^ 1][wrp] = cntw;
-      }
-      __syncthreads();
-      cl ^= 1;
-      nlist = 0;
-#pragma unroll
-      for (int w2 = 0; w2 < NWARP; w2++) {
-        segn[w2] = sCnt[cl][w2];
-        nlist += segn[w2];
-      }
-      if (nlist > 0 && max_iters > 0 && iters >= max_iters) {
-        again = true;  // not at the local fixed point yet: revisit (fully) next round
-        break;
-      }
-    }
+#include "fill_relax_body.inc"
 
     // ---- write back + activate neighbours ----
     if (f) {
@@ -744,185 +566,8 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
       }
     }
     int sides = sSides;
-    // seeded tile (start of a fill, or a ghost row was replaced): boundary cells may lie inside the
-    // tile when the raster edge is not tile-aligned, so relax every block once
-    if (sides == 0) sides = SIDE_FULL;
-    const int lane = tid & 31, wrp = tid >> 5;
-    {
-      int cntw = 0;
-#pragma unroll
-      for (int q = 0; q < SEG / 32; q++) {
-        const int b = wrp * SEG + 32 * q + lane;  // this warp's share of the blocks
-        const int bx = b % BXN, by = b / BXN;
-        bool on = (sides & SIDE_FULL) != 0;
-        on |= (sides & SIDE_N) && by == 0;
-        on |= (sides & SIDE_S) && by == BYN - 1;
-        on |= (sides & SIDE_W) && bx == 0;
-        on |= (sides & SIDE_E) && bx == BXN - 1;
-        on |= (sides & SIDE_NW) && b == 0;
-        on |= (sides & SIDE_NE) && b == BXN - 1;
-        on |= (sides & SIDE_SW) && b == NBLK - BXN;
-        on |= (sides & SIDE_SE) && b == NBLK - 1;
-        on &= b < NBLK;
-        const unsigned bal = __ballot_sync(0xffffffffu, on);
-        if (on) sList[0][wrp][cntw + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)b;
-        cntw += __popc(bal);
-      }
-      if (lane == 0) sCnt[0][wrp] = cntw;
-    }
-    if (a.use_tma) {
-      mbar_wait(&mbar, phase);
-      phase ^= 1;
-    }
-    __syncthreads();  // list 0 complete; (non-TMA path) tile staged
+#include "fill_relax_body.inc"
 
-    int f = 0;        // edge/corner-changed flags gathered by this thread
-    float kmin = __int_as_float(0x7f800000);  // lowest new water level this thread put on a tile edge
-    int iters = 0;
-    int cl = 0;       // current list
-    bool again = false;
-    int segn[NWARP];
-    int nlist = 0;
-#pragma unroll
-    for (int w2 = 0; w2 < NWARP; w2++) {
-      segn[w2] = sCnt[0][w2];
-      nlist += segn[w2];
-    }
-    while (nlist > 0) {
-      for (int i = tid; i < nlist; i += FILL_THREADS) {
-        // i-th entry of the concatenated per-warp segments
-        int seg = 0, off = i;
-#pragma unroll
-        for (int w2 = 0; w2 < NWARP - 1; w2++) {
-          if (seg == w2 && off >= segn[w2]) {
-            off -= segn[w2];
-            seg = w2 + 1;
-          }
-        }
-        const int b = sList[cl][seg][off];
-        const int bx = b % BXN, by = b / BXN;
-        const int srow = 4 * by + 1, scol = 4 * bx + PADL;
-        float v[6][6];
-#pragma unroll
-        for (int j = 0; j < 6; j++) {
-          const float *row = &sW[(srow - 1 + j) * SP + scol];
-          const float4 m4 = *reinterpret_cast<const float4 *>(row);
-          v[j][0] = row[-1]; v[j][1] = m4.x; v[j][2] = m4.y; v[j][3] = m4.z; v[j][4] = m4.w; v[j][5] = row[4];
-        }
-        float z[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const float4 z4 = *reinterpret_cast<const float4 *>(&sZ[(4 * by + j) * TX + 4 * bx]);
-          z[j][0] = z4.x; z[j][1] = z4.y; z[j][2] = z4.z; z[j][3] = z4.w;
-        }
-        uint32_t ch = 0;
-        // Forward then backward Gauss-Seidel pass.  new = min(v, max(z, min8)) is evaluated as
-        //   min( min(v, max(z, min(7 other neighbours))),  max(z, just-updated neighbour) )
-        // (min/max distribute; no NaNs here), so the serial dependence between consecutive cells of a
-        // row is two FMNMX long instead of the whole stencil.
-#pragma unroll
-        for (int j = 1; j <= 4; j++) {
-#pragma unroll
-          for (int i2 = 1; i2 <= 4; i2++) {
-            const float zz = z[j - 1][i2 - 1];
-            const float others = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
-                                       min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]), v[j][i2 + 1]);
-            const float b0 = fminf(v[j][i2], fmaxf(zz, STEP ? others + 1.0f : others));
-            const float nw = fminf(b0, fmaxf(zz, STEP ? v[j][i2 - 1] + 1.0f : v[j][i2 - 1]));  // updated one step ago
-            if (nw < v[j][i2]) ch |= 1u << ((j - 1) * 4 + (i2 - 1));
-            v[j][i2] = nw;
-          }
-        }
-#pragma unroll
-        for (int j = 4; j >= 1; j--) {
-#pragma unroll
-          for (int i2 = 4; i2 >= 1; i2--) {
-            const float zz = z[j - 1][i2 - 1];
-            const float others = min3f(min3f(v[j - 1][i2 - 1], v[j - 1][i2], v[j - 1][i2 + 1]),
-                                       min3f(v[j + 1][i2 - 1], v[j + 1][i2], v[j + 1][i2 + 1]), v[j][i2 - 1]);
-            const float b0 = fminf(v[j][i2], fmaxf(zz, STEP ? others + 1.0f : others));
-            const float nw = fminf(b0, fmaxf(zz, STEP ? v[j][i2 + 1] + 1.0f : v[j][i2 + 1]));  // updated one step ago
-            if (nw < v[j][i2]) ch |= 1u << ((j - 1) * 4 + (i2 - 1));
-            v[j][i2] = nw;
-          }
-        }
-        if (ch) {
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            if (ch & (0xFu << (4 * j))) {
-              *reinterpret_cast<float4 *>(&sW[(srow + j) * SP + scol]) =
-                  make_float4(v[j + 1][1], v[j + 1][2], v[j + 1][3], v[j + 1][4]);
-            }
-          }
-          unsigned char *mk = &sMark[(by + 1) * MKP + (bx + 1)];
-          mk[0] = 1;  // two passes are not a local fixed point: look at this block again
-          if (ch & 0x000Fu) mk[-MKP] = 1;
-          if (ch & 0xF000u) mk[MKP] = 1;
-          if (ch & 0x1111u) mk[-1] = 1;
-          if (ch & 0x8888u) mk[1] = 1;
-          if (ch & 0x0001u) mk[-MKP - 1] = 1;
-          if (ch & 0x0008u) mk[-MKP + 1] = 1;
-          if (ch & 0x1000u) mk[MKP - 1] = 1;
-          if (ch & 0x8000u) mk[MKP + 1] = 1;
-          // which tile edges / corners / watched raster rows did this block touch?
-          if (by == 0 && (ch & 0x000Fu)) f |= SIDE_N;
-          if (by == BYN - 1 && (ch & 0xF000u)) f |= SIDE_S;
-          if (bx == 0 && (ch & 0x1111u)) f |= SIDE_W;
-          if (bx == BXN - 1 && (ch & 0x8888u)) f |= SIDE_E;
-          if (b == 0 && (ch & 0x0001u)) f |= SIDE_NW;
-          if (b == BXN - 1 && (ch & 0x0008u)) f |= SIDE_NE;
-          if (b == NBLK - BXN && (ch & 0x1000u)) f |= SIDE_SW;
-          if (b == NBLK - 1 && (ch & 0x8000u)) f |= SIDE_SE;
-          {
-            const int gy0 = y0 + 4 * by;  // raster row of this block's row 0
-            const int j1 = 1 - gy0, j2 = (a.H - 2) - gy0;
-            if (j1 >= 0 && j1 < 4 && (ch & (0xFu << (4 * j1)))) f |= 1 << 9;
-            if (j2 >= 0 && j2 < 4 && (ch & (0xFu << (4 * j2)))) f |= 1 << 10;
-          }
-          f |= 1 << (12 + by);  // block row `by` holds a changed cell (bits 12..27)
-          if (bx == 0 || by == 0 || bx == BXN - 1 || by == BYN - 1) {
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-#pragma unroll
-              for (int i2 = 0; i2 < 4; i2++)
-                if (ch & (1u << (4 * j + i2))) kmin = fminf(kmin, v[j + 1][i2 + 1]);
-          }
-        }
-      }
-      if (a.profile && tid == 0) {
-        sProf[0] += nlist;
-        sProf[1] += (nlist + 31) / 32;
-      }
-      iters++;
-      __syncthreads();  // marks and W rows of this pass are visible; list `cl` is consumed
-      // compact the marks into the other list: each warp scans its share and fills its own segment
-      {
-        int cntw = 0;
-#pragma unroll
-        for (int q = 0; q < SEG / 32; q++) {
-          const int b = wrp * SEG + 32 * q + lane;
-          const int mi = (b / BXN + 1) * MKP + (b % BXN) + 1;
-          const bool on = (b < NBLK) && sMark[mi] != 0;
-          if (on) sMark[mi] = 0;
-          const unsigned bal = __ballot_sync(0xffffffffu, on);
-          if (on) sList[cl ^ 1][wrp][cntw + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)b;
-          cntw += __popc(bal);
-        }
-        if (lane == 0) sCnt[cl ^ 1][wrp] = cntw;
-      }
-      __syncthreads();
-      cl ^= 1;
-      nlist = 0;
-#pragma unroll
-      for (int w2 = 0; w2 < NWARP; w2++) {
-        segn[w2] = sCnt[cl][w2];
-        nlist += segn[w2];
-      }
-      if (nlist > 0 && max_iters > 0 && iters >= max_iters) {
-        again = true;  // not at the local fixed point yet: revisit (fully) next round
-        break;
-      }
-    }
     // ---- write back, then activate neighbours ----
     if (f) {
       atomicOr(&sFlags, f);

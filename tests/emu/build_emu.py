@@ -149,7 +149,7 @@ def rewrite(text: str, name: str) -> str:
 def build(verbose: bool = False) -> Path:
     GEN_DIR.mkdir(parents=True, exist_ok=True)
     here = Path(__file__).resolve().parent
-    srcs = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh"))
+    srcs = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inc"))
     deps = srcs + [here / "cuda_emu.h", here / "cuda_emu.cpp", Path(__file__), ROOT / "include" / "richdem_b200.h"]
     if LIB.exists() and all(LIB.stat().st_mtime > d.stat().st_mtime for d in deps):
         return LIB
@@ -158,7 +158,7 @@ def build(verbose: bool = False) -> Path:
         text = rewrite(src.read_text(), src.name)
         # the sources include "../../include/richdem_b200.h" relative to csrc/
         text = text.replace('"../../include/richdem_b200.h"', f'"{ROOT / "include" / "richdem_b200.h"}"')
-        dst = GEN_DIR / (src.stem + (".cpp" if src.suffix == ".cu" else ".cuh"))
+        dst = GEN_DIR / (src.stem + (".cpp" if src.suffix == ".cu" else src.suffix))
         dst.write_text(text)
         if src.suffix == ".cu":
             cpps.append(dst)
