@@ -591,8 +591,8 @@ __global__ void __launch_bounds__(256) accum_levels_kernel(const WalkArgs<double
 // =================================================================================================
 // Asynchronous multi-receiver accumulation (accum_async = 1; prepared for round 2, off by default).
 // No levels and no grid barriers: persistent warps keep all 32 lanes on a ready cell.  A lane pushes
-// its cell's flow downstream, keeps the first receiver it completes and appends the others to its
-// warp's FIFO in shared memory; lanes without a cell take from that FIFO, then from the scan of
+// its cell's flow downstream and appends the receivers it completes to its warp's FIFO in shared
+// memory; lanes without a cell take from that FIFO, then from the scan of
 // source cells (1024-cell chunks off a global cursor), then from a global ring that warps spill to
 // when their FIFO runs full or when the ring is empty and they hold more than a warp's worth.
 // Termination: a warp that finds no work anywhere counts itself idle; work is only ever created by
@@ -625,7 +625,6 @@ __global__ void __launch_bounds__(256) accum_async_kernel(const WalkArgs<double>
   int *ring = sRing[wrp];
   int *headp = &sHead[wrp], *tailp = &sTail[wrp];
   const int nwarps = (int)gridDim.x * 8;
-  const int W = a.W;
   if (lane == 0) {
     *headp = 0;
     *tailp = 0;
@@ -645,7 +644,7 @@ __global__ void __launch_bounds__(256) accum_async_kernel(const WalkArgs<double>
     __threadfence();
     *reinterpret_cast<volatile int *>(&gq[p]) = r + 1;
   };
-  auto push = [&](int r) {  // a receiver this lane completed but does not follow itself
+  auto push = [&](int r) {  // a receiver this lane completed
     const int p = atomicAdd(tailp, 1);
     if (p - *reinterpret_cast<volatile int *>(headp) < kAsRing) {
       ring[p & (kAsRing - 1)] = r;
@@ -758,66 +757,12 @@ __global__ void __launch_bounds__(256) accum_async_kernel(const WalkArgs<double>
       }
     }
     spins = 0;
-    // ---- (3) one step for every lane that holds a ready cell ----
+    // ---- (3) one step for every lane that holds a ready cell: its flow goes downstream and every receiver
+    //      it completes joins the FIFO (the same per-cell code as the level kernel, with a budget of one) ----
     if (have) {
-      const double acc = __ldcg(a.accum + c);
-      int next = -1;
-      if (MODE == 1) {
-        const int cd = a.code[c];
-        if (cd != kCodeNoData && (cd & 15) != 0) {
-          const int n1 = cd & 15;
-          const int r1 = c + d8dy(n1) * W + d8dx(n1);
-          if (cd & kCodeTwo) {
-            const int n2 = nwrap(n1 + 1);
-            const int r2 = c + d8dy(n2) * W + d8dx(n2);
-            float p1, p2;
-            tarboton_props(a.rmaxArr[c], &p1, &p2);
-            const bool live1 = p1 > 0, live2 = p2 > 0;
-            if (live1) atomicAdd(a.accum + r1, (double)p1 * acc);
-            if (live2) atomicAdd(a.accum + r2, (double)p2 * acc);
-            __threadfence();
-            if (live1 && (atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
-            if (live2 && (atomicSub(a.st + r2, 1u) & kDepsMask) == 1u) {
-              if (next < 0) next = r2;
-              else push(r2);
-            }
-          } else {
-            atomicAdd(a.accum + r1, acc);
-            __threadfence();
-            if ((atomicSub(a.st + r1, 1u) & kDepsMask) == 1u) next = r1;
-          }
-        }
-      } else {
-        const int y = c / W, x = c - y * W;
-        if (!(x == 0 || y == 0 || x == W - 1 || y == a.H - 1)) {  // edge cells carry no flow
-          const float *p = a.props + (size_t)9 * c;
-          uint32_t sent = 0;
-#pragma unroll
-          for (int k = 1; k <= 8; k++) {
-            const float pk = p[k];
-            if (pk <= 0) continue;
-            const int r = c + d8dy(k) * W + d8dx(k);
-            if (a.props[(size_t)9 * r] == kNoDataGen) continue;
-            atomicAdd(a.accum + r, (double)pk * acc);
-            sent |= 1u << k;
-          }
-          if (sent) {
-            __threadfence();
-#pragma unroll
-            for (int k = 1; k <= 8; k++) {
-              if (!(sent & (1u << k))) continue;
-              const int r = c + d8dy(k) * W + d8dx(k);
-              if ((atomicSub(a.st + r, 1u) & kDepsMask) == 1u) {
-                if (next < 0) next = r;
-                else push(r);
-              }
-            }
-          }
-        }
-      }
+      levels_follow<MODE, false>(a, c, 1, push);
       steps++;
-      if (next >= 0) c = next;
-      else have = false;
+      have = false;
     }
     __syncwarp();
     // ---- (4) share: a FIFO close to full always hands a warp's worth (its oldest entries) to the global
