@@ -7,10 +7,12 @@
 // concurrent CTAs).  Every variant must end at the same surface; the tool checks that.
 //
 //   gcc -O2 -fopenmp -o fillsim fillsim.c -lm
-//   ./fillsim N [seed_mode] [ordered] [Rfactor] [echo_filter]
+//   ./fillsim N [seed_mode] [ordered] [Rfactor] [echo_filter] [bands]
 //     seed_mode 0: border cells only (what fill.cu does)
 //               1: + cells with a strictly descending steepest-descent path to the border (W = Z is exact there)
 //     ordered   0/1: level-ordered admission (quantile schedule with R = Rfactor * tiles across)
+//     echo_filter 0/1/2: activate a neighbour always / only if the new edge value is below its adjacent cell / and that cell can go down
+//     bands     G > 1: afterwards, flood again with the rows at every band seam preset to their exact values
 #include <math.h>
 #include <omp.h>
 #include <stdint.h>
@@ -206,7 +208,8 @@ int main(int argc, char **argv) {
   const int ordered = argc > 3 ? atoi(argv[3]) : 1;
   const double rfac = argc > 4 ? atof(argv[4]) : 0.8;
   g_echo_filter = argc > 5 ? atoi(argv[5]) : 0;
-  const char *dump = argc > 6 ? argv[6] : NULL;
+  const int bandsG = argc > 6 ? atoi(argv[6]) : 0;  // > 1: also measure a flood whose band seam rows start at their exact values
+  const char *dump = NULL;
   TN = N / TS;
   if (N % TS) { fprintf(stderr, "N must be a multiple of %d\n", TS); return 1; }
   Z = malloc((size_t)N * N * 4);
@@ -329,6 +332,67 @@ int main(int argc, char **argv) {
   printf("visits by changed cells [0 | 1-16 | 17-64 | 65-256 | 257-1024 | 1025-2048 | 2049-4095 | 4096]:");
   for (int k = 0; k < 8; k++) printf(" %lld", g_chist[k]);
   printf("  cell updates=%.2f per cell\n", (double)g_changed_cells / ((double)N * N));
+  if (bandsG > 1) {
+    // Seam experiment: how many rounds / visits does the flood need when the rows on both sides of every band seam
+    // already hold their exact values (what a seam spill-graph solve would provide)?  Every band then floods on its own.
+    float *exact = malloc((size_t)N * N * 4);
+    memcpy(exact, Wg, (size_t)N * N * 4);
+    const int bh = N / bandsG;
+    for (int y = 0; y < N; y++)
+      for (int x = 0; x < N; x++) {
+        const size_t i = (size_t)y * N + x;
+        const int border = x == 0 || y == 0 || x == N - 1 || y == N - 1;
+        const int seam = (y % bh == 0 || y % bh == bh - 1) && y > 0 && y < N - 1;
+        Wg[i] = (border || seam) ? exact[i] : INFINITY;
+      }
+    for (int t = 0; t < NT; t++) { key[0][t] = key[1][t] = INFINITY; stamp[t] = 0; }
+    n = 0;
+    for (int t = 0; t < NT; t++) {
+      const int ty = t / TN, tx = t % TN;
+      const int tb = bh / TS;  // tile rows per band
+      if (tx == 0 || tx == TN - 1 || ty % tb == 0 || ty % tb == tb - 1) { list[n++] = t; key[1][t] = -INFINITY; stamp[t] = 1; }
+    }
+    long long v2 = 0; int r2 = 1;
+    while (n > 0) {
+      const float level = (r2 - 1 < R) ? levels[r2 - 1] : INFINITY;
+      int nn = 0, np = 0;
+      float *kc = key[r2 & 1], *kn = key[(r2 + 1) & 1];
+      for (int i = 0; i < n; i++) {
+        const int t = list[i];
+        if (kc[t] <= level) { proc[np++] = t; kc[t] = INFINITY; }
+        else { if (stamp[t] != r2 + 1) { stamp[t] = r2 + 1; next[nn++] = t; } kn[t] = fminf(kn[t], kc[t]); kc[t] = INFINITY; }
+      }
+      int nout = 0;
+#pragma omp parallel for schedule(dynamic, 8)
+      for (int i = 0; i < np; i++) {
+        TileOut o;
+        if (relax_tile(proc[i], &o)) { int k;
+#pragma omp atomic capture
+          k = nout++;
+          outs[k] = o; }
+      }
+      v2 += np;
+      for (int k = 0; k < nout; k++) {
+        const TileOut *o = &outs[k];
+        const int t = o->tile, ty = t / TN, tx = t % TN;
+        for (int j = 0; j < TS; j++) memcpy(&Wg[(size_t)(ty * TS + j) * N + tx * TS], &o->w[j * TS], TS * 4);
+        const int nb[8][3] = {{S_N, 0, -1}, {S_S, 0, 1}, {S_W, -1, 0}, {S_E, 1, 0}, {S_NW, -1, -1}, {S_NE, 1, -1}, {S_SW, -1, 1}, {S_SE, 1, 1}};
+        for (int q = 0; q < 8; q++)
+          if (o->sides & nb[q][0]) {
+            const int ux = tx + nb[q][1], uy = ty + nb[q][2];
+            if (ux < 0 || uy < 0 || ux >= TN || uy >= TN) continue;
+            const int u = uy * TN + ux;
+            kn[u] = fminf(kn[u], o->key);
+            if (stamp[u] != r2 + 1) { stamp[u] = r2 + 1; next[nn++] = u; }
+          }
+      }
+      int *tmp = list; list = next; next = tmp; n = nn; r2++;
+    }
+    size_t bad2 = 0;
+    for (size_t i = 0; i < (size_t)N * N; i++) if (Wg[i] != exact[i]) bad2++;
+    printf("bands=%d with exact seam rows: rounds=%d visits=%lld (%.2f raster-equivalents) mismatches=%zu\n", bandsG, r2 - 1, v2, (double)v2 / NT, bad2);
+    free(exact);
+  }
   // fixed-point check + checksum
   size_t bad = 0; double sum = 0; size_t nfilled = 0;
   for (int y = 1; y < N - 1; y++)
