@@ -10,6 +10,7 @@
 //   ./fillsim N [seed_mode] [ordered] [Rfactor] [echo_filter] [bands]
 //     seed_mode 0: border cells only (what fill.cu does)
 //               1: + cells with a strictly descending steepest-descent path to the border (W = Z is exact there)
+//               2 / 3: interior starts at the lifted fill of the 8x8 / 16x16 max-pooled raster (an upper bound)
 //     ordered   0/1: level-ordered admission (quantile schedule with R = Rfactor * tiles across)
 //     echo_filter 0/1/2: activate a neighbour always / only if the new edge value is below its adjacent cell / and that cell can go down
 //     bands     G > 1: afterwards, flood again with the rows at every band seam preset to their exact values
@@ -220,10 +221,51 @@ int main(int argc, char **argv) {
 
   // init
   size_t nseed = 0;
-  if (seed_mode >= 1) {
+  if (seed_mode == 1) {
     t0 = omp_get_wtime();
     compute_drained();
     fprintf(stderr, "drained %.1fs\n", omp_get_wtime() - t0);
+  }
+  float *W0 = NULL;
+  if (seed_mode >= 2 && seed_mode <= 4) {
+    // coarse upper bound: max-pool Z over k x k blocks, fill the coarse raster exactly, lift (every fine cell of a
+    // block can reach the border below the block's coarse level: blocks are internally connected and 8-adjacent
+    // blocks share a fine 8-adjacency)
+    const int k = seed_mode == 2 ? 8 : (seed_mode == 3 ? 16 : 4), M = N / k;
+    float *Zc = malloc((size_t)M * M * 4), *Wc = malloc((size_t)M * M * 4);
+    for (int by = 0; by < M; by++)
+      for (int bx = 0; bx < M; bx++) {
+        float m = -INFINITY;
+        for (int j = 0; j < k; j++)
+          for (int i = 0; i < k; i++) m = fmaxf(m, Z[(size_t)(by * k + j) * N + bx * k + i]);
+        Zc[(size_t)by * M + bx] = m;
+      }
+    for (int i = 0; i < M * M; i++) Wc[i] = INFINITY;
+    for (int y = 0; y < M; y++)
+      for (int x = 0; x < M; x++)
+        if (!x || !y || x == M - 1 || y == M - 1) Wc[(size_t)y * M + x] = Zc[(size_t)y * M + x];
+    for (;;) {
+      int ch = 0;
+      for (int y = 1; y < M - 1; y++)
+        for (int x = 1; x < M - 1; x++) {
+          float *c = &Wc[(size_t)y * M + x];
+          float m = fminf(fminf(fminf(c[-M - 1], c[-M]), fminf(c[-M + 1], c[-1])), fminf(fminf(c[1], c[M - 1]), fminf(c[M], c[M + 1])));
+          const float nw = fmaxf(Zc[(size_t)y * M + x], m);
+          if (nw < *c) { *c = nw; ch = 1; }
+        }
+      for (int y = M - 2; y >= 1; y--)
+        for (int x = M - 2; x >= 1; x--) {
+          float *c = &Wc[(size_t)y * M + x];
+          float m = fminf(fminf(fminf(c[-M - 1], c[-M]), fminf(c[-M + 1], c[-1])), fminf(fminf(c[1], c[M - 1]), fminf(c[M], c[M + 1])));
+          const float nw = fmaxf(Zc[(size_t)y * M + x], m);
+          if (nw < *c) { *c = nw; ch = 1; }
+        }
+      if (!ch) break;
+    }
+    W0 = malloc((size_t)N * N * 4);
+    for (int y = 0; y < N; y++)
+      for (int x = 0; x < N; x++) W0[(size_t)y * N + x] = Wc[(size_t)(y / k) * M + x / k];
+    free(Zc); free(Wc);
   }
   size_t npit = 0;
   for (int y = 0; y < N; y++)
@@ -231,9 +273,9 @@ int main(int argc, char **argv) {
       const size_t i = (size_t)y * N + x;
       const int border = x == 0 || y == 0 || x == N - 1 || y == N - 1;
       int s = border;
-      if (seed_mode >= 1 && status[i] == ST_DRAINED) s = 1;
-      if (seed_mode >= 1 && !border && receiver(x, y) < 0) npit++;
-      Wg[i] = s ? Z[i] : INFINITY;
+      if (seed_mode == 1 && status[i] == ST_DRAINED) s = 1;
+      if (seed_mode == 1 && !border && receiver(x, y) < 0) npit++;
+      Wg[i] = s ? Z[i] : (W0 ? W0[i] : INFINITY);
       nseed += s;
     }
   printf("N=%d tiles=%d seed_mode=%d ordered=%d seeded_cells=%zu (%.2f%%) pits=%zu (%.3f%%)\n", N, TN * TN, seed_mode, ordered, nseed,
