@@ -681,8 +681,12 @@ __global__ void __launch_bounds__(256) fill_seed_kernel(const FillArgs a, const 
 // ---- layout kernels ----------------------------------------------------------------------
 // compact dem (H x W) -> padded Z and W.  Border cells (all four sides of the raster handed in)
 // are boundary conditions: W = Z = dem there; interior W = +inf; padding Z = W = +inf.
+// LIFT (fill_multigrid): interior cells start at the water level of their pool x pool block in the filled max-pooled
+// raster `coarse` (an upper bound of the answer, see fill_depressions_dev) instead of +inf.
+template <bool LIFT>
 __global__ void fill_init_kernel(const float *__restrict__ dem, float *__restrict__ Zp,
-                                 float *__restrict__ Wp, int W, int H, int pitch, int rows, FillDev *dev) {
+                                 float *__restrict__ Wp, int W, int H, int pitch, int rows, FillDev *dev,
+                                 const float *__restrict__ coarse, int Wc, int pool) {
   const int px4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // padded column (multiple of 4)
   const float inf = __int_as_float(0x7f800000);
   float lo = inf, hi = -inf;
@@ -696,7 +700,7 @@ __global__ void fill_init_kernel(const float *__restrict__ dem, float *__restric
       if (x >= 0 && x < W && y >= 0 && y < H) {
         zz = dem[(size_t)y * W + x];
         const bool border = (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
-        ww = border ? zz : inf;
+        ww = border ? zz : (LIFT ? __ldg(coarse + (size_t)(y / pool) * Wc + x / pool) : inf);
         if (zz < inf && zz > -inf) {
           lo = fminf(lo, zz);
           hi = fmaxf(hi, zz);
@@ -782,6 +786,25 @@ __global__ void fill_i32_kernel(int *p, int v, int n) {
   if (i < n) p[i] = v;
 }
 
+// k x k max-pooling of a raster (ragged last row / column of blocks included)
+__global__ void __launch_bounds__(256) fill_maxpool_kernel(const float *__restrict__ src, int W, int H, float *__restrict__ dst,
+                                                            int Wc, int Hc, int k) {
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bx >= Wc) return;
+  for (int by = blockIdx.y; by < Hc; by += gridDim.y) {
+    float m = -__int_as_float(0x7f800000);
+    for (int j = 0; j < k; j++) {
+      const int y = by * k + j;
+      if (y >= H) break;
+      for (int i = 0; i < k; i++) {
+        const int x = bx * k + i;
+        if (x < W) m = fmaxf(m, __ldg(src + (size_t)y * W + x));
+      }
+    }
+    dst[(size_t)by * Wc + bx] = m;
+  }
+}
+
 // W % 4 == 0 version: 16-byte loads and stores (padded rows start 16-byte aligned at column PADL)
 __global__ void __launch_bounds__(256) fill_finish_x4_kernel(const float *__restrict__ Wp, float *__restrict__ out, int W,
                                                               int H, int pitch) {
@@ -850,7 +873,7 @@ struct FillState {
   bool still_active = false;
   int64_t sched_round = 0;
 
-  void begin(const float *d_dem, int w, int h) {
+  void begin(const float *d_dem, int w, int h, const float *d_coarse = nullptr, int coarse_w = 0, int coarse_k = 0) {
     Ctx &c = ctx();
     W = w;
     H = h;
@@ -885,7 +908,10 @@ struct FillState {
       const int n2 = (int)(2 * nt);
       fill_i32_kernel<<<(n2 + 255) / 256, 256, 0, c.stream>>>(keys.p, ORD_POS_INF, n2);
       dim3 blk(128), grd((pitch / 4 + 127) / 128, rows < 2048 ? rows : 2048);
-      fill_init_kernel<<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows, dev.p);
+      if (d_coarse)
+        fill_init_kernel<true><<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows, dev.p, d_coarse, coarse_w, coarse_k);
+      else
+        fill_init_kernel<false><<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows, dev.p, nullptr, 0, 1);
       RDB_CK(cudaGetLastError());
       count_launch(2);
       FillDev *hd = (FillDev *)c.pinned;
@@ -894,7 +920,8 @@ struct FillState {
       zmin = ord2f(hd->zmin_ord);
       zmax = ord2f(hd->zmax_ord);
       if (!(zmin <= zmax)) zmin = zmax = 0.f;
-      ordered = c.params.fill_ordered != 0 && zmax > zmin;
+      // a lifted start (fill_multigrid) is already close to the answer everywhere: no level schedule
+      ordered = c.params.fill_ordered != 0 && zmax > zmin && !d_coarse;
       levels.clear();
       if (ordered) {
         // Level schedule: round k admits tiles whose incoming water level is below the k/R quantile of
@@ -940,7 +967,7 @@ struct FillState {
     std::vector<int> init;
     for (int ty = 0; ty < tilesY; ty++)
       for (int tx = 0; tx < tilesX; tx++)
-        if (ty == 0 || tx == 0 || ty == tilesY - 1 || tx == tilesX - 1) init.push_back(ty * tilesX + tx);
+        if (d_coarse || ty == 0 || tx == 0 || ty == tilesY - 1 || tx == tilesX - 1) init.push_back(ty * tilesX + tx);
     seed_worklist(init);
   }
 
@@ -1264,15 +1291,49 @@ void geodesic_distance_dev(const uint8_t *d_open, int open_bit, float *d_w_inout
   c.stats.flat_bfs_levels += rounds;
 }
 
-void fill_depressions_dev(float *d_dem, int w, int h) {
+// fill_multigrid = k (off by default; prepared for round 2): the flood does not have to start from +inf.  ANY
+// surface W0 >= W* with W0 = Z on the border relaxes to exactly W* (DESIGN.md 3.1), and a good one is cheap: max-pool
+// the raster over k x k blocks, fill THAT (recursively), and give every cell its block's coarse water level.  It is an
+// upper bound because the cells of a block are connected below the block's maximum and 8-adjacent blocks contain
+// 8-adjacent cells, so every coarse path lifts to a fine path that is nowhere higher; border blocks contain a border
+// cell.  On the CPU model of the schedule this cuts the dependent rounds 3.5x and the tile visits by 20-40 %.
+static void fill_depressions_level(float *d_dem, int w, int h, int depth) {
   Ctx &c = ctx();
-  c.stats.cells = (int64_t)w * h;
-  if (w <= 2 || h <= 2) return;  // every cell is a border cell: nothing can change
+  const int k = (int)c.params.fill_multigrid;
+  const int min_side = (int)(c.params.fill_multigrid_min > 0 ? c.params.fill_multigrid_min : 1024);
   FillState st;
+  if (k >= 2 && depth < 8 && w >= min_side && h >= min_side && w / k >= 3 && h / k >= 3) {
+    const int wc = (w + k - 1) / k, hc = (h + k - 1) / k;
+    DevBuf<float> coarse((size_t)wc * hc);
+    dim3 blk(256), grd((unsigned)((wc + 255) / 256), (unsigned)(hc < 4096 ? hc : 4096));
+    fill_maxpool_kernel<<<grd, blk, 0, c.stream>>>(d_dem, w, h, coarse.p, wc, hc, k);
+    RDB_CK(cudaGetLastError());
+    count_launch();
+    const rdb200_stats before = c.stats;
+    fill_depressions_level(coarse.p, wc, hc, depth + 1);
+    const rdb200_stats coarse_stats = c.stats;
+    st.begin(d_dem, w, h, coarse.p, wc, k);
+    st.run();
+    st.finish(d_dem);
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    // account the coarse levels' work on top of this level's
+    c.stats.fill_rounds += coarse_stats.fill_rounds - before.fill_rounds;
+    c.stats.fill_tile_visits += coarse_stats.fill_tile_visits - before.fill_tile_visits;
+    c.stats.fill_tile_iters += coarse_stats.fill_tile_iters - before.fill_tile_iters;
+    return;
+  }
+  if (w <= 2 || h <= 2) return;  // every cell is a border cell: nothing can change
   st.begin(d_dem, w, h);
   st.run();
   st.finish(d_dem);
   RDB_CK(cudaStreamSynchronize(c.stream));
+}
+
+void fill_depressions_dev(float *d_dem, int w, int h) {
+  Ctx &c = ctx();
+  c.stats.cells = (int64_t)w * h;
+  if (w <= 2 || h <= 2) return;  // every cell is a border cell: nothing can change
+  fill_depressions_level(d_dem, w, h, 0);
 }
 
 }  // namespace rdb

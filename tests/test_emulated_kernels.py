@@ -59,7 +59,7 @@ def emulated(emu_lib, monkeypatch):
                         ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0), ("accum_agg", 0), ("accum_tail", 0),
                         ("accum_tail_budget", 0), ("accum_walk_lanes", 0), ("accum_fused_prep", 0),
                         ("flats_uf_tiled", 0), ("fill_async", 0), ("accum_async", 0),
-                        ("fill_async_thick", 0), ("flowdirs_rolling", 0)):
+                        ("fill_async_thick", 0), ("flowdirs_rolling", 0), ("fill_multigrid", 0), ("fill_multigrid_min", 0)):
         _lib.set_param(name, value)
 
 
@@ -113,10 +113,13 @@ def test_in_place_and_copy_semantics(emulated, gp):
     ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
     ("accum_agg", 1), ("accum_tail", 5), ("accum_tail", 1 << 20), ("accum_walk_lanes", 1),
     ("accum_fused_prep", 1), ("flats_uf_tiled", 1), ("fill_async", 1), ("accum_async", 1), ("flowdirs_rolling", 1),
+    ("fill_multigrid", 4),
 ])
 def test_algorithm_variants_agree(emulated, gp, checker, param, value):
     """Every tunable is a schedule / layout choice; none may change a result."""
     _lib.set_param(param, value)
+    if param == "fill_multigrid":
+        _lib.set_param("fill_multigrid_min", 32)  # so that a 300 x 420 raster gets two coarse levels
     dem = oracle.fbm_terrain(300, 420, seed=17, quantum=0.5)
     dem[40:70, 100:180] = gp.ND
     gp.check_pipeline(dem, gp.ND, checker)
@@ -243,6 +246,22 @@ def test_async_fill_engine(emulated, gp, checker, shape, q):
         got = np.asarray(rd.FillDepressions(gp.R(dem)))
         assert np.array_equal(got, expected), (shape, cap, thick)
         assert _lib.stats()["fill_tile_visits"] > 0
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 8])
+@pytest.mark.parametrize("engine", ["rounds", "async"])
+def test_multigrid_seeded_fill(emulated, gp, checker, k, engine):
+    """fill_multigrid: the flood starts from the lifted fill of the k x k max-pooled raster (recursively) instead of
+    +inf; ragged block edges, NoData, plateaus, both engines.  Any upper bound must relax to the exact surface."""
+    import richdem_b200 as rd
+    _lib.set_param("fill_multigrid", k)
+    _lib.set_param("fill_multigrid_min", 32)
+    _lib.set_param("fill_async", 1 if engine == "async" else 0)
+    for shape, q in (((301, 423), 0.5), ((130, 70), None), ((65, 129), 5.0), ((33, 35), None), ((500, 640), None)):
+        dem = oracle.fbm_terrain(*shape, seed=k + shape[0], quantum=q)
+        dem[shape[0] // 3: shape[0] // 3 + 7, shape[1] // 2: shape[1] // 2 + 9] = gp.ND
+        got = np.asarray(rd.FillDepressions(gp.R(dem)))
+        assert np.array_equal(got, checker.fill_depressions(dem)), (k, engine, shape)
 
 
 def _spread_to_all_lower_neighbours(dem):

@@ -18,11 +18,11 @@ for name, argtypes in _lib.SIGNATURES.items():
     f = getattr(L, name); f.argtypes = argtypes; f.restype = C.c_int
 L.rdb200_last_error.restype = C.c_char_p; L.rdb200_last_error.argtypes=[]; L.rdb200_version.restype=C.c_int; L.rdb200_shutdown.restype=None
 _lib._lib = L
-_lib.init(0); _lib.set_param("fill_use_tma", 0)
+_lib.init(0); _lib.set_param("fill_use_tma", 0); _lib.set_param("fill_multigrid_min", 24)
 spec = importlib.util.spec_from_file_location("gp", os.path.join(ROOT, "tests", "test_gpu_parity.py")); gp = importlib.util.module_from_spec(spec); spec.loader.exec_module(gp)
 O = oracle.best()
 seed0=int(sys.argv[1]); T=float(sys.argv[2])
-ALLSW=["fill_async","accum_async","accum_fused_prep","accum_walk_lanes","accum_agg","accum_tail","flats_uf_tiled","flowdirs_rolling"]
+ALLSW=["fill_multigrid","fill_async","accum_async","accum_fused_prep","accum_walk_lanes","accum_agg","accum_tail","flats_uf_tiled","flowdirs_rolling"]
 rng=np.random.default_rng(seed0); t0=time.time(); n=0; fails=0
 while time.time()-t0 < T:
     h=int(rng.integers(1,420)); w=int(rng.integers(1,520))
@@ -39,7 +39,7 @@ while time.time()-t0 < T:
     sw={k:0 for k in ALLSW}
     if rng.random()<0.6:
         for k in ALLSW:
-            if rng.random()<0.4: sw[k]= int(rng.integers(1,300)) if k=="accum_tail" else 1
+            if rng.random()<0.4: sw[k]= int(rng.integers(1,300)) if k=="accum_tail" else (int(rng.integers(2,9)) if k=="fill_multigrid" else 1)
     for k,v in sw.items(): _lib.set_param(k,v)
     try:
         wts=rng.random((h,w)) if rng.random()<0.3 else None

@@ -24,7 +24,7 @@ step() {  # name, seconds, command...
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv >"$OUT/gpu.txt" 2>&1
 
 # 1. parity of each switch against the reference on small rasters (opt-in test file)
-for k in accum_fused_prep accum_walk_lanes accum_agg accum_tail accum_async flats_uf_tiled flowdirs_rolling fill_async eight_receiver; do
+for k in fill_multigrid accum_fused_prep accum_walk_lanes accum_agg accum_tail accum_async flats_uf_tiled flowdirs_rolling fill_async eight_receiver; do
   RDB_TEST_EXPERIMENTAL=1 step "parity_$k" 240 python -m pytest tests/test_gpu_experimental.py -m gpu -x -q -k "$k"
 done
 
@@ -33,7 +33,7 @@ step time_fa_d8 240 python tools/accum_switches.py "$N"
 step time_fa_dinf 400 python tools/accum_switches.py "$N" --dinf
 step time_flats_base 240 env RDB200_PROFILE=1 python tools/flats_profile.py "$N"
 step time_flats_uf_tiled 240 env RDB200_PROFILE=1 python tools/flats_profile.py "$N" flats_uf_tiled=1
-step time_fill 300 python tools/fill_profile.py "$N" "" "fill_ordered=0" "fill_async=1"
+step time_fill 400 python tools/fill_profile.py "$N" "" "fill_ordered=0" "fill_multigrid=8" "fill_multigrid=4" "fill_multigrid=8,fill_async=1" "fill_async=1"
 step time_fill_async_unordered 200 python tools/fill_profile.py "$N" "fill_async=1,fill_ordered=0"
 
 echo "done" | tee -a "$OUT/summary.txt"
