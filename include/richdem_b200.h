@@ -171,6 +171,17 @@ RDB200_API int rdb200_dev_generate_fbm_f32(float *d_dem, int32_t width, int32_t 
 typedef struct rdb200_fill_state rdb200_fill_state;
 RDB200_API int rdb200_dev_fill_begin(rdb200_fill_state **state, const float *d_dem, int32_t width,
                           int32_t height);
+/* Multigrid start for a band (parameter fill_multigrid): `d_coarse` is the FILLED k x k max-pooled raster of the
+ * WHOLE raster (coarse_width columns; every GPU solves that small raster itself), `row_offset` the global row of the
+ * band's row 0.  Interior cells start at their block's coarse water level (an upper bound of the answer) instead of
+ * +inf; the caller presets ghost rows the same way.  Everything else as rdb200_dev_fill_begin. */
+RDB200_API int rdb200_dev_fill_begin_lifted(rdb200_fill_state **state, const float *d_dem, int32_t width, int32_t height,
+                                 const float *d_coarse, int32_t coarse_width, int32_t pool, int32_t row_offset);
+/* k x k max-pooling of rows [row_offset, row_offset + height) of a raster into the rows of the full coarse raster
+ * (coarse_width x coarse_height, pre-filled by the caller, e.g. with -inf) that they touch; entries are combined
+ * with max, so bands that share a coarse row can be merged with a MAX all-reduce. */
+RDB200_API int rdb200_dev_maxpool_rows_f32(const float *d_src, int32_t width, int32_t height, int32_t row_offset, int32_t pool,
+                                float *d_coarse, int32_t coarse_width, int32_t coarse_height);
 /* Relax to the local fixed point (or for about `fill_band_rounds` sweep rounds when that parameter
  * is set).  *changed_rows: bit0 = row 1 changed, bit1 = row height-2 changed during this call (the
  * rows a neighbouring band holds as ghosts); bit2 = tiles are still active (call again). */

@@ -62,6 +62,8 @@ SIGNATURES = {
     "rdb200_dev_fa_tarboton_f32_f64": [_vp, _vp, _i32, _i32, _f32, _i32],
     "rdb200_dev_generate_fbm_f32": [_vp, _i32, _i32, _i32, C.c_uint32, _i32, _f32],
     "rdb200_dev_fill_begin": [C.POINTER(_vp), _vp, _i32, _i32],
+    "rdb200_dev_fill_begin_lifted": [C.POINTER(_vp), _vp, _i32, _i32, _vp, _i32, _i32, _i32],
+    "rdb200_dev_maxpool_rows_f32": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32],
     "rdb200_dev_fill_run": [_vp, C.POINTER(_i32)],
     "rdb200_dev_fill_read_row": [_vp, _i32, _vp],
     "rdb200_dev_fill_update_row": [_vp, _i32, _vp],

@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(256) fill_seed_kernel(const FillArgs a, const 
 template <bool LIFT>
 __global__ void fill_init_kernel(const float *__restrict__ dem, float *__restrict__ Zp,
                                  float *__restrict__ Wp, int W, int H, int pitch, int rows, FillDev *dev,
-                                 const float *__restrict__ coarse, int Wc, int pool) {
+                                 const float *__restrict__ coarse, int Wc, int pool, int yoff) {
   const int px4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;  // padded column (multiple of 4)
   const float inf = __int_as_float(0x7f800000);
   float lo = inf, hi = -inf;
@@ -700,7 +700,7 @@ __global__ void fill_init_kernel(const float *__restrict__ dem, float *__restric
       if (x >= 0 && x < W && y >= 0 && y < H) {
         zz = dem[(size_t)y * W + x];
         const bool border = (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
-        ww = border ? zz : (LIFT ? __ldg(coarse + (size_t)(y / pool) * Wc + x / pool) : inf);
+        ww = border ? zz : (LIFT ? __ldg(coarse + (size_t)((y + yoff) / pool) * Wc + x / pool) : inf);
         if (zz < inf && zz > -inf) {
           lo = fminf(lo, zz);
           hi = fmaxf(hi, zz);
@@ -786,22 +786,26 @@ __global__ void fill_i32_kernel(int *p, int v, int n) {
   if (i < n) p[i] = v;
 }
 
-// k x k max-pooling of a raster (ragged last row / column of blocks included)
-__global__ void __launch_bounds__(256) fill_maxpool_kernel(const float *__restrict__ src, int W, int H, float *__restrict__ dst,
-                                                            int Wc, int Hc, int k) {
+// k x k max-pooling of rows [yoff, yoff + H) of a raster into the coarse rows they touch (ragged last row / column
+// of blocks included).  `combine`: max with what `dst` already holds (a band covers part of a block row).
+__global__ void __launch_bounds__(256) fill_maxpool_kernel(const float *__restrict__ src, int W, int H, int yoff, float *dst, int Wc,
+                                                            int Hc, int k, int combine) {
   const int bx = blockIdx.x * blockDim.x + threadIdx.x;
   if (bx >= Wc) return;
-  for (int by = blockIdx.y; by < Hc; by += gridDim.y) {
+  const int by_lo = yoff / k, by_hi = (yoff + H - 1) / k;
+  for (int by = by_lo + blockIdx.y; by <= by_hi && by < Hc; by += gridDim.y) {
     float m = -__int_as_float(0x7f800000);
     for (int j = 0; j < k; j++) {
-      const int y = by * k + j;
+      const int y = by * k + j - yoff;  // local row
+      if (y < 0) continue;
       if (y >= H) break;
       for (int i = 0; i < k; i++) {
         const int x = bx * k + i;
         if (x < W) m = fmaxf(m, __ldg(src + (size_t)y * W + x));
       }
     }
-    dst[(size_t)by * Wc + bx] = m;
+    float *o = dst + (size_t)by * Wc + bx;
+    *o = combine ? fmaxf(*o, m) : m;
   }
 }
 
@@ -873,7 +877,8 @@ struct FillState {
   bool still_active = false;
   int64_t sched_round = 0;
 
-  void begin(const float *d_dem, int w, int h, const float *d_coarse = nullptr, int coarse_w = 0, int coarse_k = 0) {
+  void begin(const float *d_dem, int w, int h, const float *d_coarse = nullptr, int coarse_w = 0, int coarse_k = 0,
+             int coarse_yoff = 0) {
     Ctx &c = ctx();
     W = w;
     H = h;
@@ -909,9 +914,10 @@ struct FillState {
       fill_i32_kernel<<<(n2 + 255) / 256, 256, 0, c.stream>>>(keys.p, ORD_POS_INF, n2);
       dim3 blk(128), grd((pitch / 4 + 127) / 128, rows < 2048 ? rows : 2048);
       if (d_coarse)
-        fill_init_kernel<true><<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows, dev.p, d_coarse, coarse_w, coarse_k);
+        fill_init_kernel<true><<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows, dev.p, d_coarse, coarse_w, coarse_k,
+                                                         coarse_yoff);
       else
-        fill_init_kernel<false><<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows, dev.p, nullptr, 0, 1);
+        fill_init_kernel<false><<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows, dev.p, nullptr, 0, 1, 0);
       RDB_CK(cudaGetLastError());
       count_launch(2);
       FillDev *hd = (FillDev *)c.pinned;
@@ -1306,7 +1312,7 @@ static void fill_depressions_level(float *d_dem, int w, int h, int depth) {
     const int wc = (w + k - 1) / k, hc = (h + k - 1) / k;
     DevBuf<float> coarse((size_t)wc * hc);
     dim3 blk(256), grd((unsigned)((wc + 255) / 256), (unsigned)(hc < 4096 ? hc : 4096));
-    fill_maxpool_kernel<<<grd, blk, 0, c.stream>>>(d_dem, w, h, coarse.p, wc, hc, k);
+    fill_maxpool_kernel<<<grd, blk, 0, c.stream>>>(d_dem, w, h, 0, coarse.p, wc, hc, k, 0);
     RDB_CK(cudaGetLastError());
     count_launch();
     const rdb200_stats before = c.stats;
@@ -1327,6 +1333,12 @@ static void fill_depressions_level(float *d_dem, int w, int h, int depth) {
   st.run();
   st.finish(d_dem);
   RDB_CK(cudaStreamSynchronize(c.stream));
+}
+
+void fill_maxpool_rows(const float *d_src, int w, int h, int yoff, float *d_coarse, int wc, int hc, int k, dim3 grd, dim3 blk) {
+  fill_maxpool_kernel<<<grd, blk, 0, ctx().stream>>>(d_src, w, h, yoff, d_coarse, wc, hc, k, 1);
+  RDB_CK(cudaGetLastError());
+  count_launch();
 }
 
 void fill_depressions_dev(float *d_dem, int w, int h) {
@@ -1391,6 +1403,39 @@ int rdb200_dev_fill_begin(rdb200_fill_state **state, const float *d_dem, int32_t
     throw;
   }
   *state = s;
+  RDB_CAPI_END
+}
+
+int rdb200_dev_fill_begin_lifted(rdb200_fill_state **state, const float *d_dem, int32_t width, int32_t height,
+                                 const float *d_coarse, int32_t coarse_width, int32_t pool, int32_t row_offset) {
+  RDB_CAPI_TRY
+  rdb::ensure_init();
+  if (!state) rdb::fail("fill_begin_lifted: null state pointer");
+  if (width < 3 || height < 3) rdb::fail("fill_begin_lifted: band must be at least 3x3");
+  if (!d_coarse || pool < 2 || coarse_width < (width + pool - 1) / pool || row_offset < 0)
+    rdb::fail("fill_begin_lifted: bad coarse raster (pool %d, coarse_width %d, row_offset %d)", pool, coarse_width, row_offset);
+  auto *s = new rdb200_fill_state();
+  try {
+    s->st.begin(d_dem, width, height, d_coarse, coarse_width, pool, row_offset);
+  } catch (...) {
+    delete s;
+    throw;
+  }
+  *state = s;
+  RDB_CAPI_END
+}
+
+int rdb200_dev_maxpool_rows_f32(const float *d_src, int32_t width, int32_t height, int32_t row_offset, int32_t pool,
+                                float *d_coarse, int32_t coarse_width, int32_t coarse_height) {
+  RDB_CAPI_TRY
+  rdb::ensure_init();
+  if (width < 1 || height < 1 || pool < 2 || row_offset < 0 || coarse_width < (width + pool - 1) / pool ||
+      coarse_height < (row_offset + height + pool - 1) / pool)
+    rdb::fail("maxpool_rows: bad geometry");
+  rdb::Ctx &c = rdb::ctx();
+  dim3 blk(256), grd((unsigned)((coarse_width + 255) / 256), (unsigned)(height / pool + 2 < 4096 ? height / pool + 2 : 4096));
+  rdb::fill_maxpool_rows(d_src, width, height, row_offset, d_coarse, coarse_width, coarse_height, pool, grd, blk);
+  RDB_CK(cudaStreamSynchronize(c.stream));
   RDB_CAPI_END
 }
 

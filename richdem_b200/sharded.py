@@ -64,7 +64,9 @@ def _on_device(t) -> bool:
 class CudaBandSolver:
     """The product band solver: librichdem_b200's row-band fill entry points on device memory."""
 
-    def __init__(self, local_dem: "torch.Tensor"):
+    def __init__(self, local_dem: "torch.Tensor", coarse: Optional["torch.Tensor"] = None, pool: int = 0, row_offset: int = 0):
+        """``coarse`` (optional): the filled ``pool`` x ``pool`` max-pooled raster of the WHOLE raster; the band then
+        starts from its lifted water levels instead of +inf (``row_offset`` = global row of local row 0)."""
         from . import _lib
         assert _on_device(local_dem) and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
         self._lib = _lib
@@ -72,7 +74,13 @@ class CudaBandSolver:
         self.h, self.w = local_dem.shape
         self.device = local_dem.device
         self._state = C.c_void_p()
-        _lib.check(_lib.lib().rdb200_dev_fill_begin(C.byref(self._state), local_dem.data_ptr(), self.w, self.h))
+        if coarse is None:
+            _lib.check(_lib.lib().rdb200_dev_fill_begin(C.byref(self._state), local_dem.data_ptr(), self.w, self.h))
+        else:
+            assert _on_device(coarse) and coarse.dtype == torch.float32 and coarse.is_contiguous() and pool >= 2
+            self._coarse = coarse  # keep it alive until begin has consumed it
+            _lib.check(_lib.lib().rdb200_dev_fill_begin_lifted(C.byref(self._state), local_dem.data_ptr(), self.w, self.h,
+                                                               coarse.data_ptr(), coarse.shape[1], int(pool), int(row_offset)))
 
     def run(self) -> int:
         ch = C.c_int32(0)
@@ -132,11 +140,35 @@ def exchange_rows(local: "torch.Tensor", g_top: int, g_bot: int, group=None) -> 
         local[h - 1].copy_(rd[0])
 
 
+def coarse_fill(local_dem: "torch.Tensor", g_top: int, g_bot: int, row0: int, height: int, pool: int, group=None):
+    """The filled ``pool`` x ``pool`` max-pooled raster of the whole (``height`` rows) raster, on every rank: each rank
+    pools its owned rows into the coarse rows they touch, a MAX all-reduce merges the bands (a coarse row can straddle a
+    seam), and every rank fills the small raster itself -- redundant, but it is 1/pool^2 of the work and saves a
+    broadcast.  ``row0`` is the global row of ``local_dem``'s row 0 (the top ghost row if there is one)."""
+    from . import _lib
+    h, w = local_dem.shape
+    wc, hc = (w + pool - 1) // pool, (height + pool - 1) // pool
+    coarse = torch.full((hc, wc), float("-inf"), dtype=torch.float32, device=local_dem.device)
+    owned = local_dem[g_top:h - g_bot]
+    _lib.use_torch_stream()
+    _lib.check(_lib.lib().rdb200_dev_maxpool_rows_f32(owned.data_ptr(), w, owned.shape[0], row0 + g_top, pool,
+                                                      coarse.data_ptr(), wc, hc))
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(coarse, op=dist.ReduceOp.MAX, group=group)
+    _lib.check(_lib.lib().rdb200_dev_fill_depressions_d8_f32(coarse.data_ptr(), wc, hc))
+    return coarse
+
+
 def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None, group=None,
-              max_rounds: int = 100000, return_stats: bool = False, band_rounds: Optional[int] = None):
+              max_rounds: int = 100000, return_stats: bool = False, band_rounds: Optional[int] = None,
+              multigrid: int = 0, row0: int = 0, height: int = 0):
     """Fill this rank's band.  ``local_dem`` is (g_top + owned + g_bot) x W with the ghost rows'
     contents ignored (they are initialised to +inf).  Returns (filled local raster incl. ghost rows,
-    number of exchange rounds).  Collective: every rank of ``group`` must call it."""
+    number of exchange rounds).  Collective: every rank of ``group`` must call it.
+
+    ``multigrid`` = k >= 2 (with ``row0`` = global row of local row 0 and ``height`` = rows of the whole raster): start
+    from the lifted fill of the k x k max-pooled raster (see :func:`coarse_fill`) instead of +inf -- an upper bound of
+    the answer, so the result is the same, after far fewer dependent rounds and halo exchanges."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if solver_cls is None:
@@ -154,11 +186,19 @@ def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None
             if v is not None:
                 _lib.set_param(knob, int(v))
     h, w = local_dem.shape
-    if g_top:
-        local_dem[0].fill_(float("inf"))
-    if g_bot:
-        local_dem[h - 1].fill_(float("inf"))
-    solver = solver_cls(local_dem)
+    if multigrid >= 2:
+        assert height > 0, "multigrid start needs the global geometry (row0, height)"
+        coarse = coarse_fill(local_dem, g_top, g_bot, row0, height, multigrid, group)
+        for on, y in ((g_top, 0), (g_bot, h - 1)):  # ghost rows start at their lifted levels too
+            if on:
+                local_dem[y].copy_(coarse[(row0 + y) // multigrid].repeat_interleave(multigrid)[:w])
+        solver = solver_cls(local_dem, coarse, multigrid, row0)
+    else:
+        if g_top:
+            local_dem[0].fill_(float("inf"))
+        if g_bot:
+            local_dem[h - 1].fill_(float("inf"))
+        solver = solver_cls(local_dem)
     rounds = _relax_band(solver, g_top, g_bot, rank, world, group, max_rounds)
     out = solver.finish()
     if return_stats:

@@ -62,6 +62,7 @@ def _worker(rank, world, port, lib_path, dem, expected, params, out_q):
         sharded._view = host_view
         _lib.init(0)
         _lib.set_param("fill_use_tma", 0)
+        band_multigrid = params.pop("_band_multigrid", 0)  # fill_band's own argument, not a library switch
         for k, v in params.items():
             _lib.set_param(k, v)
 
@@ -70,7 +71,7 @@ def _worker(rank, world, port, lib_path, dem, expected, params, out_q):
         local, (r0, r1, gt, gb) = sharded.scatter_rows(dem if rank == 0 else None, h, w, torch.float32, "cpu")
         own = slice(gt, gt + (r1 - r0))
         res = {}
-        filled, _ = sharded.fill_band(local, gt, gb)
+        filled, _ = sharded.fill_band(local, gt, gb, multigrid=band_multigrid, row0=r0 - gt, height=h)
         res["fill"] = np.array_equal(filled[own].numpy(), expected["fill"][r0:r1])
         filled = filled.contiguous()
         sharded.resolve_flats_band(filled, gt, gb, ND)
@@ -90,8 +91,11 @@ def _worker(rank, world, port, lib_path, dem, expected, params, out_q):
             dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,params", [(2, {}), (3, {}), (3, {"fill_async": 1, "accum_walk_lanes": 1, "flats_uf_tiled": 1})],
-                         ids=["2-ranks", "3-ranks", "3-ranks-prepared-switches"])
+@pytest.mark.parametrize("world,params", [(2, {}), (3, {}), (3, {"fill_async": 1, "accum_walk_lanes": 1, "flats_uf_tiled": 1}),
+                                          (3, {"_band_multigrid": 4}), (2, {"_band_multigrid": 8, "fill_async": 1}),
+                                          (4, {"_band_multigrid": 3, "fill_multigrid": 2, "fill_multigrid_min": 16})],
+                         ids=["2-ranks", "3-ranks", "3-ranks-prepared-switches", "3-ranks-multigrid", "2-ranks-multigrid-async",
+                              "4-ranks-multigrid-recursive"])
 def test_sharded_pipeline_on_emulated_kernels(world, params):
     if sys.platform != "linux" or os.uname().machine != "x86_64":
         pytest.skip("the fiber switch of tests/emu is x86-64 SysV only")
@@ -107,7 +111,7 @@ def test_sharded_pipeline_on_emulated_kernels(world, params):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, lib_path, dem, expected, params, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, lib_path, dem, expected, dict(params), q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in range(world)]
