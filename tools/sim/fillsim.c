@@ -10,7 +10,7 @@
 //   ./fillsim N [seed_mode] [ordered] [Rfactor] [echo_filter] [bands]
 //     seed_mode 0: border cells only (what fill.cu does)
 //               1: + cells with a strictly descending steepest-descent path to the border (W = Z is exact there)
-//               2 / 3: interior starts at the lifted fill of the 8x8 / 16x16 max-pooled raster (an upper bound)
+//               2 / 3 / 4 / 5: interior starts at the lifted fill of the 8x8 / 16x16 / 4x4 / 2x2 max-pooled raster (an upper bound)
 //     ordered   0/1: level-ordered admission (quantile schedule with R = Rfactor * tiles across)
 //     echo_filter 0/1/2: activate a neighbour always / only if the new edge value is below its adjacent cell / and that cell can go down
 //     bands     G > 1: afterwards, flood again with the rows at every band seam preset to their exact values
@@ -101,6 +101,8 @@ typedef struct { float w[TS * TS]; int tile; int sides; float key; } TileOut;
 enum { S_N = 1, S_S = 2, S_W = 4, S_E = 8, S_NW = 16, S_NE = 32, S_SW = 64, S_SE = 128 };
 
 static long long g_passes = 0;
+static int g_vk = 0, g_vM = 0, g_vevery = 0;  // V-cycle: pool size, coarse side, fine rounds between coarse corrections
+static float *g_Zc = NULL, *g_Wc = NULL;
 static int g_echo_filter = 0;
 static long long g_chist[8];  // visits by changed cells: 0, 1-16, 17-64, 65-256, 257-1024, 1025-2048, 2049-4095, 4096
 static long long g_changed_cells = 0;
@@ -209,7 +211,8 @@ int main(int argc, char **argv) {
   const int ordered = argc > 3 ? atoi(argv[3]) : 1;
   const double rfac = argc > 4 ? atof(argv[4]) : 0.8;
   g_echo_filter = argc > 5 ? atoi(argv[5]) : 0;
-  const int bandsG = argc > 6 ? atoi(argv[6]) : 0;  // > 1: also measure a flood whose band seam rows start at their exact values
+  const int bandsG = argc > 6 ? atoi(argv[6]) : 0;
+  g_vevery = argc > 7 ? atoi(argv[7]) : 0;  // > 0 (with seed_mode 2..5): coarse-grid correction every that many fine rounds  // > 1: also measure a flood whose band seam rows start at their exact values
   const char *dump = NULL;
   TN = N / TS;
   if (N % TS) { fprintf(stderr, "N must be a multiple of %d\n", TS); return 1; }
@@ -227,11 +230,11 @@ int main(int argc, char **argv) {
     fprintf(stderr, "drained %.1fs\n", omp_get_wtime() - t0);
   }
   float *W0 = NULL;
-  if (seed_mode >= 2 && seed_mode <= 4) {
+  if (seed_mode >= 2 && seed_mode <= 5) {
     // coarse upper bound: max-pool Z over k x k blocks, fill the coarse raster exactly, lift (every fine cell of a
     // block can reach the border below the block's coarse level: blocks are internally connected and 8-adjacent
     // blocks share a fine 8-adjacency)
-    const int k = seed_mode == 2 ? 8 : (seed_mode == 3 ? 16 : 4), M = N / k;
+    const int k = seed_mode == 2 ? 8 : (seed_mode == 3 ? 16 : (seed_mode == 4 ? 4 : 2)), M = N / k;
     float *Zc = malloc((size_t)M * M * 4), *Wc = malloc((size_t)M * M * 4);
     for (int by = 0; by < M; by++)
       for (int bx = 0; bx < M; bx++) {
@@ -265,7 +268,7 @@ int main(int argc, char **argv) {
     W0 = malloc((size_t)N * N * 4);
     for (int y = 0; y < N; y++)
       for (int x = 0; x < N; x++) W0[(size_t)y * N + x] = Wc[(size_t)(y / k) * M + x / k];
-    free(Zc); free(Wc);
+    g_vk = k; g_vM = M; g_Zc = Zc; g_Wc = Wc;  // kept for the optional V-cycles
   }
   size_t npit = 0;
   for (int y = 0; y < N; y++)
@@ -318,7 +321,7 @@ int main(int argc, char **argv) {
   }
   TileOut *outs = malloc(sizeof(TileOut) * (size_t)NT);
   int *proc = malloc(sizeof(int) * NT);
-  long long visits = 0, deferred = 0;
+  long long visits = 0, deferred = 0, vcycles = 0, vlowered = 0;
   int round = 1;
   long long hist_small = 0;  // rounds with fewer tiles than 888 CTAs
   double model_us = 0;
@@ -367,8 +370,57 @@ int main(int argc, char **argv) {
     int *tmp = list; list = next; next = tmp;
     n = nn;
     round++;
+    if (g_vevery > 0 && g_Wc && n > 0 && (round - 1) % g_vevery == 0) {
+      // coarse-grid correction: restrict (block maximum of the current fine upper bound), relax the coarse raster,
+      // prolong (fine = min(fine, lifted)); both steps keep every value an upper bound of the answer
+      const int k = g_vk, M = g_vM;
+#pragma omp parallel for schedule(static)
+      for (int by = 0; by < M; by++)
+        for (int bx = 0; bx < M; bx++) {
+          float m = -INFINITY;
+          for (int j = 0; j < k; j++)
+            for (int i = 0; i < k; i++) m = fmaxf(m, Wg[(size_t)(by * k + j) * N + bx * k + i]);
+          float *wc = &g_Wc[(size_t)by * M + bx];
+          if (m < *wc) *wc = m;
+        }
+      for (;;) {
+        int ch = 0;
+        for (int y = 1; y < M - 1; y++)
+          for (int x = 1; x < M - 1; x++) {
+            float *c = &g_Wc[(size_t)y * M + x];
+            float m = fminf(fminf(fminf(c[-M - 1], c[-M]), fminf(c[-M + 1], c[-1])), fminf(fminf(c[1], c[M - 1]), fminf(c[M], c[M + 1])));
+            const float nw = fmaxf(g_Zc[(size_t)y * M + x], m);
+            if (nw < *c) { *c = nw; ch = 1; }
+          }
+        for (int y = M - 2; y >= 1; y--)
+          for (int x = M - 2; x >= 1; x--) {
+            float *c = &g_Wc[(size_t)y * M + x];
+            float m = fminf(fminf(fminf(c[-M - 1], c[-M]), fminf(c[-M + 1], c[-1])), fminf(fminf(c[1], c[M - 1]), fminf(c[M], c[M + 1])));
+            const float nw = fmaxf(g_Zc[(size_t)y * M + x], m);
+            if (nw < *c) { *c = nw; ch = 1; }
+          }
+        if (!ch) break;
+      }
+      long long lowered = 0;
+      float *kc2 = key[round & 1];
+      for (int y = 1; y < N - 1; y++)
+        for (int x = 1; x < N - 1; x++) {
+          const float l = g_Wc[(size_t)(y / k) * M + x / k];
+          float *w = &Wg[(size_t)y * N + x];
+          if (l < *w) {
+            *w = l;
+            lowered++;
+            const int t = (y / TS) * TN + x / TS;
+            if (stamp[t] != round) { stamp[t] = round; list[n++] = t; }
+            kc2[t] = -INFINITY;
+          }
+        }
+      vcycles++;
+      vlowered += lowered;
+    }
     if (round % 50 == 0) fprintf(stderr, "round %d active %d visits %lld (%.1fs)\n", round, n, visits, omp_get_wtime() - t0);
   }
+  if (g_vevery) printf("coarse corrections=%lld, cells lowered by prolongation=%lld\n", vcycles, vlowered);
   printf("rounds=%d visits=%lld (%.2f raster-equivalents) deferred=%lld passes/visit=%.2f small_rounds=%lld model_ms=%.1f\n", round - 1, visits,
          (double)visits / NT, deferred, (double)g_passes / visits, hist_small, model_us / 1000.0);
   printf("visits by changed cells [0 | 1-16 | 17-64 | 65-256 | 257-1024 | 1025-2048 | 2049-4095 | 4096]:");
