@@ -238,6 +238,7 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "fill_async") p.fill_async = value;
   else if (n == "fill_multigrid") p.fill_multigrid = value;
   else if (n == "fill_multigrid_min") p.fill_multigrid_min = value;
+  else if (n == "fill_vcycle") p.fill_vcycle = value;
   else if (n == "fill_async_spin") p.fill_async_spin = value;
   else if (n == "fill_async_thick") p.fill_async_thick = value;
   else if (n == "flats_uf_tiled") p.flats_uf_tiled = value;

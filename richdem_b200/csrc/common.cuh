@@ -62,6 +62,7 @@ struct Params {
   int64_t fill_band_rounds = 0;   // row-band mode: rounds per rdb200_dev_fill_run call (0: to convergence)
   int64_t fill_profile = 0;     // 1: collect + print in-tile work counters (slower)
   int64_t fill_multigrid = 0;      // k >= 2: start the flood from the lifted fill of the k x k max-pooled raster (recursive)
+  int64_t fill_vcycle = 0;         // with fill_multigrid: coarse-grid correction after every that many fine rounds (0: none)
   int64_t fill_multigrid_min = 0;  // smallest raster side that still gets a coarse level (0: 1024)
   int64_t fill_async = 0;        // whole-raster fill by one cooperative launch draining per-level tile queues (no rounds)
   int64_t fill_async_thick = 0;  // queue entries from which a bucket is claimed by fetch-add tickets instead of CAS (0: 256)

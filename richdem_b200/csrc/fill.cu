@@ -809,6 +809,43 @@ __global__ void __launch_bounds__(256) fill_maxpool_kernel(const float *__restri
   }
 }
 
+// V-cycle (fill_vcycle): restriction -- the coarse surface drops to the block maximum of the current fine surface
+// wherever that is lower (both are upper bounds of the answer for every cell of the block) ...
+__global__ void __launch_bounds__(256) fill_restrict_kernel(const float *__restrict__ Wp, int pitch, int W, int H,
+                                                             float *Wc, int Wcw, int Hc, int k) {
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bx >= Wcw) return;
+  for (int by = blockIdx.y; by < Hc; by += gridDim.y) {
+    float m = -__int_as_float(0x7f800000);
+    for (int j = 0; j < k; j++) {
+      const int y = by * k + j;
+      if (y >= H) break;
+      for (int i = 0; i < k; i++) {
+        const int x = bx * k + i;
+        if (x < W) m = fmaxf(m, __ldcg(Wp + (size_t)(y + 1) * pitch + x + PADL));
+      }
+    }
+    float *o = Wc + (size_t)by * Wcw + bx;
+    if (m < *o) *o = m;
+  }
+}
+
+// ... and prolongation: every interior fine cell drops to its block's (re-relaxed) coarse level where that is lower;
+// the tiles that hold such a cell are flagged so that the sweep can be told to look at them again.
+__global__ void __launch_bounds__(256) fill_prolong_kernel(float *Wp, int pitch, int W, int H, const float *__restrict__ Wc,
+                                                            int Wcw, int k, int *tile_flag, int tilesX) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < 1 || x >= W - 1) return;
+  for (int y = 1 + blockIdx.y; y < H - 1; y += gridDim.y) {
+    const float l = __ldg(Wc + (size_t)(y / k) * Wcw + x / k);
+    float *w = Wp + (size_t)(y + 1) * pitch + x + PADL;
+    if (l < *w) {
+      *w = l;
+      tile_flag[(y / TY) * tilesX + x / TX] = 1;
+    }
+  }
+}
+
 // W % 4 == 0 version: 16-byte loads and stores (padded rows start 16-byte aligned at column PADL)
 __global__ void __launch_bounds__(256) fill_finish_x4_kernel(const float *__restrict__ Wp, float *__restrict__ out, int W,
                                                               int H, int pitch) {
@@ -1075,7 +1112,8 @@ struct FillState {
     if (use_async) return run_async();
     int64_t rounds_this_call = 0;
     FillArgs a = make_args();
-    const int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 16);
+    int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 16);
+    if (max_rounds > 0 && max_rounds < per_sync) per_sync = (int)max_rounds;  // a short leash (V-cycles) is honoured exactly
     FillDev *hd = (FillDev *)c.pinned;
     RDB_CK(cudaMemsetAsync(&dev.p->edge_changed, 0, sizeof(int), c.stream));
     for (;;) {
@@ -1224,6 +1262,34 @@ struct FillState {
     return hd->edge_changed;
   }
 
+  // V-cycle plumbing (fill_vcycle): see fill_depressions_level
+  void restrict_to(float *d_wc, int wc, int hc, int k) {
+    Ctx &c = ctx();
+    dim3 blk(256), grd((unsigned)((wc + 255) / 256), (unsigned)(hc < 4096 ? hc : 4096));
+    fill_restrict_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, pitch, W, H, d_wc, wc, hc, k);
+    RDB_CK(cudaGetLastError());
+    count_launch();
+  }
+  // returns the number of tiles that were lowered (they are queued for the next run)
+  size_t prolong_from(const float *d_wc, int wc, int k) {
+    Ctx &c = ctx();
+    const size_t nt = (size_t)tilesX * tilesY;
+    DevBuf<int> flag(nt);
+    RDB_CK(cudaMemsetAsync(flag.p, 0, nt * sizeof(int), c.stream));
+    dim3 blk(256), grd((unsigned)((W + 255) / 256), (unsigned)(H < 4096 ? H : 4096));
+    fill_prolong_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, pitch, W, H, d_wc, wc, k, flag.p, tilesX);
+    RDB_CK(cudaGetLastError());
+    count_launch();
+    std::vector<int> hf(nt);
+    RDB_CK(cudaMemcpyAsync(hf.data(), flag.p, nt * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    std::vector<int> tiles;
+    for (size_t t = 0; t < nt; t++)
+      if (hf[t]) tiles.push_back((int)t);
+    seed_worklist(tiles);
+    return tiles.size();
+  }
+
   void read_row(int y, float *d_row) {
     if (y < 0 || y >= H) fail("fill_read_row: row %d out of range", y);
     RDB_CK(cudaMemcpyAsync(d_row, Wp.p + (size_t)(y + 1) * pitch + PADL, (size_t)W * 4,
@@ -1315,17 +1381,53 @@ static void fill_depressions_level(float *d_dem, int w, int h, int depth) {
     fill_maxpool_kernel<<<grd, blk, 0, c.stream>>>(d_dem, w, h, 0, coarse.p, wc, hc, k, 0);
     RDB_CK(cudaGetLastError());
     count_launch();
+    const int every = (int)c.params.fill_vcycle;  // > 0: coarse-grid correction after that many fine rounds
+    DevBuf<float> zc;
+    if (every > 0) {  // the coarse elevations are needed again for the corrections
+      zc.alloc((size_t)wc * hc);
+      RDB_CK(cudaMemcpyAsync(zc.p, coarse.p, (size_t)wc * hc * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+    }
     const rdb200_stats before = c.stats;
     fill_depressions_level(coarse.p, wc, hc, depth + 1);
-    const rdb200_stats coarse_stats = c.stats;
+    rdb200_stats extra = c.stats;  // work done on the coarse levels, accounted on top of this level's
+    extra.fill_rounds -= before.fill_rounds;
+    extra.fill_tile_visits -= before.fill_tile_visits;
+    extra.fill_tile_iters -= before.fill_tile_iters;
     st.begin(d_dem, w, h, coarse.p, wc, k);
-    st.run();
+    if (every <= 0) {
+      st.run();
+    } else {
+      // V-cycles.  The lifted start leaves every lake a little too high (max-pooling raises its pass), and lowering a
+      // lake is a sweep across it, one tile per round.  So after `every` fine rounds the coarse surface is lowered to
+      // the block maxima of the fine one (restriction), relaxed again -- the same sweep, k times fewer tiles across --
+      // and handed back (prolongation: fine = min(fine, lifted)).  Restriction and coarse relaxation keep every coarse
+      // value an upper bound of the answer for all cells of its block, so the fine surface stays an upper bound and
+      // still relaxes to exactly W*.
+      for (int cycle = 0;; cycle++) {
+        if (!(st.run(every) & 4)) break;  // converged
+        if (cycle >= 1000) {              // safety net: plain relaxation to the end
+          st.run();
+          break;
+        }
+        st.restrict_to(coarse.p, wc, hc, k);
+        {
+          FillState cst;  // coarse relaxation from the restricted surface (pool = 1 "lift": start from that array)
+          cst.begin(zc.p, wc, hc, coarse.p, wc, 1);
+          cst.run();
+          cst.finish(coarse.p);
+          RDB_CK(cudaStreamSynchronize(c.stream));
+          extra.fill_rounds += c.stats.fill_rounds;  // cst's own counters (FillState::run reports absolute values)
+          extra.fill_tile_visits += c.stats.fill_tile_visits;
+          extra.fill_tile_iters += c.stats.fill_tile_iters;
+        }
+        st.prolong_from(coarse.p, wc, k);
+      }
+    }
     st.finish(d_dem);
     RDB_CK(cudaStreamSynchronize(c.stream));
-    // account the coarse levels' work on top of this level's
-    c.stats.fill_rounds += coarse_stats.fill_rounds - before.fill_rounds;
-    c.stats.fill_tile_visits += coarse_stats.fill_tile_visits - before.fill_tile_visits;
-    c.stats.fill_tile_iters += coarse_stats.fill_tile_iters - before.fill_tile_iters;
+    c.stats.fill_rounds = st.rounds_run + extra.fill_rounds;
+    c.stats.fill_tile_visits += extra.fill_tile_visits;
+    c.stats.fill_tile_iters += extra.fill_tile_iters;
     return;
   }
   if (w <= 2 || h <= 2) return;  // every cell is a border cell: nothing can change

@@ -59,7 +59,7 @@ def emulated(emu_lib, monkeypatch):
                         ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0), ("accum_agg", 0), ("accum_tail", 0),
                         ("accum_tail_budget", 0), ("accum_walk_lanes", 0), ("accum_fused_prep", 0),
                         ("flats_uf_tiled", 0), ("fill_async", 0), ("accum_async", 0),
-                        ("fill_async_thick", 0), ("flowdirs_rolling", 0), ("fill_multigrid", 0), ("fill_multigrid_min", 0)):
+                        ("fill_async_thick", 0), ("flowdirs_rolling", 0), ("fill_multigrid", 0), ("fill_multigrid_min", 0), ("fill_vcycle", 0)):
         _lib.set_param(name, value)
 
 
@@ -249,7 +249,7 @@ def test_async_fill_engine(emulated, gp, checker, shape, q):
 
 
 @pytest.mark.parametrize("k", [2, 3, 4, 8])
-@pytest.mark.parametrize("engine", ["rounds", "async"])
+@pytest.mark.parametrize("engine", ["rounds", "async", "vcycle1", "vcycle3"])
 def test_multigrid_seeded_fill(emulated, gp, checker, k, engine):
     """fill_multigrid: the flood starts from the lifted fill of the k x k max-pooled raster (recursively) instead of
     +inf; ragged block edges, NoData, plateaus, both engines.  Any upper bound must relax to the exact surface."""
@@ -257,6 +257,9 @@ def test_multigrid_seeded_fill(emulated, gp, checker, k, engine):
     _lib.set_param("fill_multigrid", k)
     _lib.set_param("fill_multigrid_min", 32)
     _lib.set_param("fill_async", 1 if engine == "async" else 0)
+    if engine.startswith("vcycle"):  # coarse-grid corrections (restrict / coarse relax / prolong) every 1 or 3 fine rounds
+        _lib.set_param("fill_vcycle", int(engine[-1]))
+        _lib.set_param("fill_rounds_per_sync", 2)
     for shape, q in (((301, 423), 0.5), ((130, 70), None), ((65, 129), 5.0), ((33, 35), None), ((500, 640), None)):
         dem = oracle.fbm_terrain(*shape, seed=k + shape[0], quantum=q)
         dem[shape[0] // 3: shape[0] // 3 + 7, shape[1] // 2: shape[1] // 2 + 9] = gp.ND

@@ -19,7 +19,7 @@ from richdem_b200 import _lib
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not os.environ.get("RDB_TEST_EXPERIMENTAL"), reason="opt-in: RDB_TEST_EXPERIMENTAL=1")]
 ND = -9999.0
-SWITCHES = ("fill_multigrid", "fill_multigrid_min", "fill_async", "flowdirs_rolling", "accum_async", "accum_fused_prep", "accum_walk_lanes", "accum_agg", "accum_tail", "accum_tail_budget",
+SWITCHES = ("fill_multigrid", "fill_multigrid_min", "fill_vcycle", "fill_async", "flowdirs_rolling", "accum_async", "accum_fused_prep", "accum_walk_lanes", "accum_agg", "accum_tail", "accum_tail_budget",
             "flats_uf_tiled")
 
 
@@ -37,7 +37,8 @@ def switches():
 CONFIGS = [{"accum_fused_prep": 1}, {"accum_walk_lanes": 1}, {"accum_fused_prep": 1, "accum_walk_lanes": 1},
            {"accum_agg": 1}, {"accum_tail": 2048}, {"accum_agg": 1, "accum_tail": 64, "accum_tail_budget": 3},
            {"flats_uf_tiled": 1}, {"fill_async": 1}, {"accum_async": 1}, {"flowdirs_rolling": 1},
-           {"fill_multigrid": 8, "fill_multigrid_min": 256}, {"fill_multigrid": 4, "fill_multigrid_min": 256, "fill_async": 1}]
+           {"fill_multigrid": 8, "fill_multigrid_min": 256}, {"fill_multigrid": 4, "fill_multigrid_min": 256, "fill_async": 1},
+           {"fill_multigrid": 8, "fill_multigrid_min": 256, "fill_vcycle": 4}]
 
 
 @pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()))
@@ -60,7 +61,7 @@ def test_switch_matches_reference(checker, switches, cfg, shape, q):
 
 
 @pytest.mark.parametrize("cfg", [{"fill_async": 1}, {"accum_fused_prep": 1, "accum_walk_lanes": 1}, {"fill_multigrid": 8},
-                                 {"fill_multigrid": 4, "fill_async": 1}],
+                                 {"fill_multigrid": 4, "fill_async": 1}, {"fill_multigrid": 8, "fill_vcycle": 4}],
                          ids=lambda c: ",".join(c))
 def test_switch_at_8192_matches_default(switches, cfg):
     import torch

@@ -41,6 +41,7 @@ while time.time()-t0 < T:
         for k in ALLSW:
             if rng.random()<0.4: sw[k]= int(rng.integers(1,300)) if k=="accum_tail" else (int(rng.integers(2,9)) if k=="fill_multigrid" else 1)
     for k,v in sw.items(): _lib.set_param(k,v)
+    _lib.set_param("fill_vcycle", int(rng.integers(0,4)) if sw.get("fill_multigrid") else 0)
     try:
         wts=rng.random((h,w)) if rng.random()<0.3 else None
         gp.check_pipeline(dem, gp.ND, O, accum_weights=wts)

@@ -15,7 +15,7 @@ import torch  # noqa: E402
 from richdem_b200 import _lib  # noqa: E402
 
 DEFAULTS = {"fill_ordered": 1, "fill_order_rounds": 0, "fill_max_iters": 0, "fill_use_tma": 1, "fill_rounds_per_sync": 16,
-            "fill_async": 0, "fill_async_spin": 0, "fill_async_thick": 0, "fill_multigrid": 0, "fill_multigrid_min": 0, "fill_profile": 0}
+            "fill_async": 0, "fill_async_spin": 0, "fill_async_thick": 0, "fill_multigrid": 0, "fill_multigrid_min": 0, "fill_vcycle": 0, "fill_profile": 0}
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 L = _lib.lib()
 _lib.init(0)
