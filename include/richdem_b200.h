@@ -180,6 +180,17 @@ RDB200_API int rdb200_dev_fill_begin_lifted(rdb200_fill_state **state, const flo
 /* k x k max-pooling of rows [row_offset, row_offset + height) of a raster into the rows of the full coarse raster
  * (coarse_width x coarse_height, pre-filled by the caller, e.g. with -inf) that they touch; entries are combined
  * with max, so bands that share a coarse row can be merged with a MAX all-reduce. */
+/* Multigrid V-cycle pieces for bands (parameter fill_vcycle):
+ *   blockmax : k x k block maxima of the band's current water surface over its rows [skip_top, height - skip_bottom)
+ *              (the owned rows), max-combined into the full coarse array (pre-filled with -inf; bands merge by MAX);
+ *   relax_from: depression filling of `d_dem` started from the upper bound in `d_w_inout` (receives the result);
+ *   prolong  : every interior cell of the band drops to its block's coarse level where that is lower; the tiles
+ *              touched are queued for the next run; *tiles_lowered = how many. */
+RDB200_API int rdb200_dev_fill_blockmax(rdb200_fill_state *state, float *d_blockmax, int32_t coarse_width, int32_t coarse_height,
+                             int32_t pool, int32_t row_offset, int32_t skip_top, int32_t skip_bottom);
+RDB200_API int rdb200_dev_fill_relax_from_f32(const float *d_dem, float *d_w_inout, int32_t width, int32_t height);
+RDB200_API int rdb200_dev_fill_prolong(rdb200_fill_state *state, const float *d_coarse, int32_t coarse_width, int32_t pool,
+                            int32_t row_offset, int32_t *tiles_lowered);
 RDB200_API int rdb200_dev_maxpool_rows_f32(const float *d_src, int32_t width, int32_t height, int32_t row_offset, int32_t pool,
                                 float *d_coarse, int32_t coarse_width, int32_t coarse_height);
 /* Relax to the local fixed point (or for about `fill_band_rounds` sweep rounds when that parameter

@@ -64,6 +64,9 @@ SIGNATURES = {
     "rdb200_dev_fill_begin": [C.POINTER(_vp), _vp, _i32, _i32],
     "rdb200_dev_fill_begin_lifted": [C.POINTER(_vp), _vp, _i32, _i32, _vp, _i32, _i32, _i32],
     "rdb200_dev_maxpool_rows_f32": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32],
+    "rdb200_dev_fill_blockmax": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32],
+    "rdb200_dev_fill_relax_from_f32": [_vp, _vp, _i32, _i32],
+    "rdb200_dev_fill_prolong": [_vp, _vp, _i32, _i32, _i32, C.POINTER(C.c_int32)],
     "rdb200_dev_fill_run": [_vp, C.POINTER(_i32)],
     "rdb200_dev_fill_read_row": [_vp, _i32, _vp],
     "rdb200_dev_fill_update_row": [_vp, _i32, _vp],

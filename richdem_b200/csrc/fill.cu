@@ -830,14 +830,37 @@ __global__ void __launch_bounds__(256) fill_restrict_kernel(const float *__restr
   }
 }
 
+// band variant of the restriction: block maxima of rows [y_lo, y_hi) of a band whose row 0 is global row `yoff`,
+// max-combined into the full coarse array `out` (pre-filled with -inf; merged across bands by a MAX all-reduce)
+__global__ void __launch_bounds__(256) fill_blockmax_kernel(const float *__restrict__ Wp, int pitch, int W, int y_lo, int y_hi,
+                                                             int yoff, float *out, int Wcw, int Hc, int k) {
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bx >= Wcw) return;
+  const int by_lo = (yoff + y_lo) / k, by_hi = (yoff + y_hi - 1) / k;
+  for (int by = by_lo + blockIdx.y; by <= by_hi && by < Hc; by += gridDim.y) {
+    float m = -__int_as_float(0x7f800000);
+    for (int j = 0; j < k; j++) {
+      const int y = by * k + j - yoff;  // local row
+      if (y < y_lo) continue;
+      if (y >= y_hi) break;
+      for (int i = 0; i < k; i++) {
+        const int x = bx * k + i;
+        if (x < W) m = fmaxf(m, __ldcg(Wp + (size_t)(y + 1) * pitch + x + PADL));
+      }
+    }
+    float *o = out + (size_t)by * Wcw + bx;
+    *o = fmaxf(*o, m);
+  }
+}
+
 // ... and prolongation: every interior fine cell drops to its block's (re-relaxed) coarse level where that is lower;
 // the tiles that hold such a cell are flagged so that the sweep can be told to look at them again.
 __global__ void __launch_bounds__(256) fill_prolong_kernel(float *Wp, int pitch, int W, int H, const float *__restrict__ Wc,
-                                                            int Wcw, int k, int *tile_flag, int tilesX) {
+                                                            int Wcw, int k, int *tile_flag, int tilesX, int yoff) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x < 1 || x >= W - 1) return;
   for (int y = 1 + blockIdx.y; y < H - 1; y += gridDim.y) {
-    const float l = __ldg(Wc + (size_t)(y / k) * Wcw + x / k);
+    const float l = __ldg(Wc + (size_t)((y + yoff) / k) * Wcw + x / k);
     float *w = Wp + (size_t)(y + 1) * pitch + x + PADL;
     if (l < *w) {
       *w = l;
@@ -1271,13 +1294,20 @@ struct FillState {
     count_launch();
   }
   // returns the number of tiles that were lowered (they are queued for the next run)
-  size_t prolong_from(const float *d_wc, int wc, int k) {
+  void blockmax_into(float *d_out, int wc, int hc, int k, int yoff, int y_lo, int y_hi) {
+    Ctx &c = ctx();
+    dim3 blk(256), grd((unsigned)((wc + 255) / 256), (unsigned)((y_hi - y_lo) / k + 2 < 4096 ? (y_hi - y_lo) / k + 2 : 4096));
+    fill_blockmax_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, pitch, W, y_lo, y_hi, yoff, d_out, wc, hc, k);
+    RDB_CK(cudaGetLastError());
+    count_launch();
+  }
+  size_t prolong_from(const float *d_wc, int wc, int k, int yoff = 0) {
     Ctx &c = ctx();
     const size_t nt = (size_t)tilesX * tilesY;
     DevBuf<int> flag(nt);
     RDB_CK(cudaMemsetAsync(flag.p, 0, nt * sizeof(int), c.stream));
     dim3 blk(256), grd((unsigned)((W + 255) / 256), (unsigned)(H < 4096 ? H : 4096));
-    fill_prolong_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, pitch, W, H, d_wc, wc, k, flag.p, tilesX);
+    fill_prolong_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, pitch, W, H, d_wc, wc, k, flag.p, tilesX, yoff);
     RDB_CK(cudaGetLastError());
     count_launch();
     std::vector<int> hf(nt);
@@ -1437,6 +1467,22 @@ static void fill_depressions_level(float *d_dem, int w, int h, int depth) {
   RDB_CK(cudaStreamSynchronize(c.stream));
 }
 
+// fill with a given start: `d_w` holds an upper bound of the answer (e.g. a restricted coarse surface) and receives it
+void fill_relax_from_dev(const float *d_dem, float *d_w, int w, int h) {
+  Ctx &c = ctx();
+  c.stats.cells = (int64_t)w * h;
+  if (w <= 2 || h <= 2) {
+    RDB_CK(cudaMemcpyAsync(d_w, d_dem, (size_t)w * h * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    return;
+  }
+  FillState st;
+  st.begin(d_dem, w, h, d_w, w, 1);
+  st.run();
+  st.finish(d_w);
+  RDB_CK(cudaStreamSynchronize(c.stream));
+}
+
 void fill_maxpool_rows(const float *d_src, int w, int h, int yoff, float *d_coarse, int wc, int hc, int k, dim3 grd, dim3 blk) {
   fill_maxpool_kernel<<<grd, blk, 0, ctx().stream>>>(d_src, w, h, yoff, d_coarse, wc, hc, k, 1);
   RDB_CK(cudaGetLastError());
@@ -1538,6 +1584,37 @@ int rdb200_dev_maxpool_rows_f32(const float *d_src, int32_t width, int32_t heigh
   dim3 blk(256), grd((unsigned)((coarse_width + 255) / 256), (unsigned)(height / pool + 2 < 4096 ? height / pool + 2 : 4096));
   rdb::fill_maxpool_rows(d_src, width, height, row_offset, d_coarse, coarse_width, coarse_height, pool, grd, blk);
   RDB_CK(cudaStreamSynchronize(c.stream));
+  RDB_CAPI_END
+}
+
+int rdb200_dev_fill_relax_from_f32(const float *d_dem, float *d_w_inout, int32_t width, int32_t height) {
+  RDB_CAPI_TRY
+  rdb::ensure_init();
+  if (width < 1 || height < 1) rdb::fail("fill_relax_from: raster dimensions must be positive");
+  rdb::fill_relax_from_dev(d_dem, d_w_inout, width, height);
+  RDB_CAPI_END
+}
+
+int rdb200_dev_fill_blockmax(rdb200_fill_state *state, float *d_blockmax, int32_t coarse_width, int32_t coarse_height, int32_t pool,
+                             int32_t row_offset, int32_t skip_top, int32_t skip_bottom) {
+  RDB_CAPI_TRY
+  if (!state) rdb::fail("fill_blockmax: null state");
+  rdb::FillState &st = state->st;
+  if (pool < 2 || row_offset < 0 || skip_top < 0 || skip_bottom < 0 || skip_top + skip_bottom >= st.H ||
+      coarse_width < (st.W + pool - 1) / pool || coarse_height < (row_offset + st.H - skip_bottom + pool - 1) / pool)
+    rdb::fail("fill_blockmax: bad geometry");
+  st.blockmax_into(d_blockmax, coarse_width, coarse_height, pool, row_offset, skip_top, st.H - skip_bottom);
+  RDB_CK(cudaStreamSynchronize(rdb::ctx().stream));
+  RDB_CAPI_END
+}
+
+int rdb200_dev_fill_prolong(rdb200_fill_state *state, const float *d_coarse, int32_t coarse_width, int32_t pool, int32_t row_offset,
+                            int32_t *tiles_lowered) {
+  RDB_CAPI_TRY
+  if (!state) rdb::fail("fill_prolong: null state");
+  if (!d_coarse || pool < 2 || row_offset < 0) rdb::fail("fill_prolong: bad arguments");
+  const size_t n = state->st.prolong_from(d_coarse, coarse_width, pool, row_offset);
+  if (tiles_lowered) *tiles_lowered = (int32_t)n;
   RDB_CAPI_END
 }
 

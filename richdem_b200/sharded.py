@@ -96,6 +96,18 @@ class CudaBandSolver:
         assert _on_device(row) and row.dtype == torch.float32 and row.numel() == self.w
         self._lib.check(self._lib.lib().rdb200_dev_fill_update_row(self._state, y, row.contiguous().data_ptr()))
 
+    def blockmax(self, out: "torch.Tensor", pool: int, row_offset: int, skip_top: int, skip_bottom: int) -> None:
+        """V-cycle restriction: max-combine the pool x pool block maxima of the owned rows' water surface into ``out``."""
+        self._lib.check(self._lib.lib().rdb200_dev_fill_blockmax(self._state, out.data_ptr(), out.shape[1], out.shape[0], int(pool),
+                                                             int(row_offset), int(skip_top), int(skip_bottom)))
+
+    def prolong(self, coarse: "torch.Tensor", pool: int, row_offset: int) -> int:
+        """V-cycle prolongation: interior cells drop to their block's coarse level where lower; returns tiles touched."""
+        n = C.c_int32(0)
+        self._lib.check(self._lib.lib().rdb200_dev_fill_prolong(self._state, coarse.data_ptr(), coarse.shape[1], int(pool),
+                                                            int(row_offset), C.byref(n)))
+        return int(n.value)
+
     def finish(self) -> "torch.Tensor":
         out = torch.empty((self.h, self.w), dtype=torch.float32, device=self.device)
         self._lib.check(self._lib.lib().rdb200_dev_fill_finish(self._state, out.data_ptr()))
@@ -140,7 +152,8 @@ def exchange_rows(local: "torch.Tensor", g_top: int, g_bot: int, group=None) -> 
         local[h - 1].copy_(rd[0])
 
 
-def coarse_fill(local_dem: "torch.Tensor", g_top: int, g_bot: int, row0: int, height: int, pool: int, group=None):
+def coarse_fill(local_dem: "torch.Tensor", g_top: int, g_bot: int, row0: int, height: int, pool: int, group=None,
+                keep_elevations: bool = False):
     """The filled ``pool`` x ``pool`` max-pooled raster of the whole (``height`` rows) raster, on every rank: each rank
     pools its owned rows into the coarse rows they touch, a MAX all-reduce merges the bands (a coarse row can straddle a
     seam), and every rank fills the small raster itself -- redundant, but it is 1/pool^2 of the work and saves a
@@ -155,20 +168,25 @@ def coarse_fill(local_dem: "torch.Tensor", g_top: int, g_bot: int, row0: int, he
                                                       coarse.data_ptr(), wc, hc))
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(coarse, op=dist.ReduceOp.MAX, group=group)
+    elevations = coarse.clone() if keep_elevations else None
     _lib.check(_lib.lib().rdb200_dev_fill_depressions_d8_f32(coarse.data_ptr(), wc, hc))
-    return coarse
+    return (coarse, elevations) if keep_elevations else coarse
 
 
 def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None, group=None,
               max_rounds: int = 100000, return_stats: bool = False, band_rounds: Optional[int] = None,
-              multigrid: int = 0, row0: int = 0, height: int = 0):
+              multigrid: int = 0, row0: int = 0, height: int = 0, vcycle: int = 0):
     """Fill this rank's band.  ``local_dem`` is (g_top + owned + g_bot) x W with the ghost rows'
     contents ignored (they are initialised to +inf).  Returns (filled local raster incl. ghost rows,
     number of exchange rounds).  Collective: every rank of ``group`` must call it.
 
     ``multigrid`` = k >= 2 (with ``row0`` = global row of local row 0 and ``height`` = rows of the whole raster): start
     from the lifted fill of the k x k max-pooled raster (see :func:`coarse_fill`) instead of +inf -- an upper bound of
-    the answer, so the result is the same, after far fewer dependent rounds and halo exchanges."""
+    the answer, so the result is the same, after far fewer dependent rounds and halo exchanges.  ``vcycle`` = n > 0
+    adds coarse-grid corrections: after every n halo exchanges that did not end the relaxation, the coarse surface is
+    lowered to the block maxima of the bands' surfaces (restriction; MAX all-reduce), relaxed again on every rank and
+    handed back (prolongation: fine = min(fine, lifted)) -- a lake that is a little too high is lowered by a sweep
+    across the COARSE raster instead of one tile row / halo exchange at a time."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if solver_cls is None:
@@ -188,11 +206,33 @@ def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None
     h, w = local_dem.shape
     if multigrid >= 2:
         assert height > 0, "multigrid start needs the global geometry (row0, height)"
-        coarse = coarse_fill(local_dem, g_top, g_bot, row0, height, multigrid, group)
+        coarse, coarse_z = coarse_fill(local_dem, g_top, g_bot, row0, height, multigrid, group, keep_elevations=True)
         for on, y in ((g_top, 0), (g_bot, h - 1)):  # ghost rows start at their lifted levels too
             if on:
                 local_dem[y].copy_(coarse[(row0 + y) // multigrid].repeat_interleave(multigrid)[:w])
         solver = solver_cls(local_dem, coarse, multigrid, row0)
+        if vcycle > 0:
+            from . import _lib
+            rounds = 0
+            while True:
+                # at least two runs per burst: the first one always exchanges halos (prolongation may have lowered edge
+                # rows without the sweep noticing), only a later one can find that nothing moves any more
+                r, done = _relax_band(solver, g_top, g_bot, rank, world, group, max_rounds, stop_after=max(2, vcycle))
+                rounds += r
+                if done:
+                    break
+                bm = torch.full_like(coarse, float("-inf"))
+                solver.blockmax(bm, multigrid, row0, g_top, g_bot)
+                if world > 1:
+                    dist.all_reduce(bm, op=dist.ReduceOp.MAX, group=group)
+                torch.minimum(coarse, bm, out=coarse)
+                _lib.check(_lib.lib().rdb200_dev_fill_relax_from_f32(coarse_z.data_ptr(), coarse.data_ptr(), coarse.shape[1],
+                                                                     coarse.shape[0]))
+                solver.prolong(coarse, multigrid, row0)
+            out = solver.finish()
+            if return_stats:
+                return out, rounds, _lib.stats()
+            return out, rounds
     else:
         if g_top:
             local_dem[0].fill_(float("inf"))
@@ -452,8 +492,10 @@ class _BandStateSolver:
         self._lib.check(self._lib.lib().rdb200_dev_fill_update_row(self._state, y, row.contiguous().data_ptr()))
 
 
-def _relax_band(solver, g_top, g_bot, rank, world, group, max_rounds=100000):
-    """The row-band relaxation protocol shared by the fill and the flat-resolution gradients."""
+def _relax_band(solver, g_top, g_bot, rank, world, group, max_rounds=100000, stop_after=0):
+    """The row-band relaxation protocol shared by the fill and the flat-resolution gradients.  ``stop_after`` = n > 0:
+    return ``(rounds, done)`` after at most n solver runs (the caller does something -- a coarse-grid correction -- and
+    calls again); otherwise run to the end and return the number of rounds."""
     h = solver.h
     rounds = 0
     while True:
@@ -461,8 +503,10 @@ def _relax_band(solver, g_top, g_bot, rank, world, group, max_rounds=100000):
         rounds += 1
         if world == 1:
             if changed & 4:
+                if stop_after and rounds >= stop_after:
+                    return rounds, False
                 continue
-            return rounds
+            return (rounds, True) if stop_after else rounds
         my_change = 0
         if g_top and (changed & 1 or rounds == 1):
             my_change = 1
@@ -473,8 +517,10 @@ def _relax_band(solver, g_top, g_bot, rank, world, group, max_rounds=100000):
         dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
         any_edge, any_active = (int(v) for v in flag.tolist())
         if not any_edge and not any_active:
-            return rounds
+            return (rounds, True) if stop_after else rounds
         if not any_edge:
+            if stop_after and rounds >= stop_after:
+                return rounds, False
             continue
         send_up = solver.read_row(1) if g_top else None
         send_dn = solver.read_row(h - 2) if g_bot else None
@@ -485,6 +531,8 @@ def _relax_band(solver, g_top, g_bot, rank, world, group, max_rounds=100000):
             solver.update_row(h - 1, recv_dn[0])
         if rounds >= max_rounds:
             raise RuntimeError("band relaxation: exchange rounds exceeded max_rounds")
+        if stop_after and rounds >= stop_after:
+            return rounds, False
 
 
 def resolve_flats_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, nodata: float, group=None):

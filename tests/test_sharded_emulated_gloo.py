@@ -62,7 +62,8 @@ def _worker(rank, world, port, lib_path, dem, expected, params, out_q):
         sharded._view = host_view
         _lib.init(0)
         _lib.set_param("fill_use_tma", 0)
-        band_multigrid = params.pop("_band_multigrid", 0)  # fill_band's own argument, not a library switch
+        band_multigrid = params.pop("_band_multigrid", 0)  # fill_band's own arguments, not library switches
+        band_vcycle = params.pop("_band_vcycle", 0)
         for k, v in params.items():
             _lib.set_param(k, v)
 
@@ -71,7 +72,7 @@ def _worker(rank, world, port, lib_path, dem, expected, params, out_q):
         local, (r0, r1, gt, gb) = sharded.scatter_rows(dem if rank == 0 else None, h, w, torch.float32, "cpu")
         own = slice(gt, gt + (r1 - r0))
         res = {}
-        filled, _ = sharded.fill_band(local, gt, gb, multigrid=band_multigrid, row0=r0 - gt, height=h)
+        filled, _ = sharded.fill_band(local, gt, gb, multigrid=band_multigrid, row0=r0 - gt, height=h, vcycle=band_vcycle)
         res["fill"] = np.array_equal(filled[own].numpy(), expected["fill"][r0:r1])
         filled = filled.contiguous()
         sharded.resolve_flats_band(filled, gt, gb, ND)
@@ -93,9 +94,11 @@ def _worker(rank, world, port, lib_path, dem, expected, params, out_q):
 
 @pytest.mark.parametrize("world,params", [(2, {}), (3, {}), (3, {"fill_async": 1, "accum_walk_lanes": 1, "flats_uf_tiled": 1}),
                                           (3, {"_band_multigrid": 4}), (2, {"_band_multigrid": 8, "fill_async": 1}),
-                                          (4, {"_band_multigrid": 3, "fill_multigrid": 2, "fill_multigrid_min": 16})],
+                                          (4, {"_band_multigrid": 3, "fill_multigrid": 2, "fill_multigrid_min": 16}),
+                                          (3, {"_band_multigrid": 4, "_band_vcycle": 1, "fill_band_rounds": 2, "fill_rounds_per_sync": 2}),
+                                          (2, {"_band_multigrid": 8, "_band_vcycle": 2, "fill_band_rounds": 1, "fill_rounds_per_sync": 1})],
                          ids=["2-ranks", "3-ranks", "3-ranks-prepared-switches", "3-ranks-multigrid", "2-ranks-multigrid-async",
-                              "4-ranks-multigrid-recursive"])
+                              "4-ranks-multigrid-recursive", "3-ranks-vcycle", "2-ranks-vcycle"])
 def test_sharded_pipeline_on_emulated_kernels(world, params):
     if sys.platform != "linux" or os.uname().machine != "x86_64":
         pytest.skip("the fiber switch of tests/emu is x86-64 SysV only")

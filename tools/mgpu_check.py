@@ -8,6 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from richdem_b200 import _lib, sharded
 
 MG = int(os.environ.get("RDB_BAND_MULTIGRID", "0"))  # k >= 2: multigrid start of the band fill (fill_band(..., multigrid=k))
+VC = int(os.environ.get("RDB_BAND_VCYCLE", "0"))     # n > 0: coarse-grid correction after every n halo exchanges
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
@@ -23,7 +24,7 @@ for (H, W, q) in [(3000, 2000, 0.5), (8192, 8192, 0.0)]:
     loc = torch.empty((hloc, W), dtype=torch.float32, device="cuda")
     _lib.check(L.rdb200_dev_generate_fbm_f32(loc.data_ptr(), W, hloc, r0 - gt, 7, 12, q))
     torch.cuda.synchronize(); dist.barrier(); t = time.time()
-    filled, frounds = sharded.fill_band(loc.clone(), gt, gb, multigrid=MG, row0=r0 - gt, height=H)
+    filled, frounds = sharded.fill_band(loc.clone(), gt, gb, multigrid=MG, row0=r0 - gt, height=H, vcycle=VC)
     torch.cuda.synchronize(); dist.barrier(); tf = time.time() - t; t = time.time()
     own_f = filled[gt:gt + (r1 - r0)].clone()
     # flat resolution over bands (in place), then refresh the ghost rows with the neighbours' resolved rows

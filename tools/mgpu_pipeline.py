@@ -7,6 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from richdem_b200 import _lib, sharded
 
 MG = int(os.environ.get("RDB_BAND_MULTIGRID", "0"))  # k >= 2: multigrid start of the band fill (fill_band(..., multigrid=k))
+VC = int(os.environ.get("RDB_BAND_VCYCLE", "0"))     # n > 0: coarse-grid correction after every n halo exchanges
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
@@ -29,7 +30,7 @@ def timed(fn):
 res = {}
 for rep in range(2):   # second repetition is the reported one (workspace warm)
     work = dem0.clone()
-    (filled, fr), res["fill_ms"] = timed(lambda: sharded.fill_band(work, gt, gb, multigrid=MG, row0=r0 - gt, height=N))
+    (filled, fr), res["fill_ms"] = timed(lambda: sharded.fill_band(work, gt, gb, multigrid=MG, row0=r0 - gt, height=N, vcycle=VC))
     it, res["resolve_flats_ms"] = timed(lambda: sharded.resolve_flats_band(filled, gt, gb, ND))
     _, res["halo_refresh_ms"] = timed(lambda: sharded.exchange_rows(filled, gt, gb))
     (a8, r8), res["fa_d8_ms"] = timed(lambda: sharded.fa_band(filled, gt, gb, ND, dinf=False))
