@@ -34,6 +34,15 @@ ND = -9999.0
 SEED = 42
 
 
+def BAND_FILL_KW(row0, height):
+    """Experiment hook for the row-band fill (default: none): RDB_BAND_MULTIGRID=k starts every band from the lifted
+    fill of the k x k max-pooled raster, RDB_BAND_VCYCLE=n adds coarse-grid corrections."""
+    k = int(os.environ.get("RDB_BAND_MULTIGRID", "0"))
+    if k < 2:
+        return {}
+    return {"multigrid": k, "row0": row0, "height": height, "vcycle": int(os.environ.get("RDB_BAND_VCYCLE", "0"))}
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -186,7 +195,7 @@ def run_b200(args):
                 agg["acc_ms"] += s2["ms_total"]
         else:
             ta = time.perf_counter()
-            filled, rounds, st = sharded.fill_band(work, gt, gb, return_stats=True)
+            filled, rounds, st = sharded.fill_band(work, gt, gb, return_stats=True, **BAND_FILL_KW(r0 - gt, N))
             torch.cuda.synchronize()
             tb = time.perf_counter()
             res, rounds2, st2 = sharded.fa_band(filled, gt, gb, ND, dinf=False, rank_rows=(r0, r1, N), return_stats=True)
@@ -269,7 +278,7 @@ def run_b200(args):
                     loc[gt:gt + (r1 - r0)].copy_(h_src, non_blocking=True)
                     # ghost rows of elevation come from the neighbours
                     sharded.exchange_rows(loc, gt, gb)
-                    filled, _ = sharded.fill_band(loc, gt, gb)
+                    filled, _ = sharded.fill_band(loc, gt, gb, **BAND_FILL_KW(r0 - gt, N))
                     res, _ = sharded.fa_band(filled, gt, gb, ND, dinf=False, rank_rows=(r0, r1, N))
                     h_dem.copy_(filled[gt:gt + (r1 - r0)], non_blocking=True)
                     h_acc.copy_(res[gt:gt + (r1 - r0)], non_blocking=True)
