@@ -377,6 +377,7 @@ struct AsyncArgs {
   int profile;
   long long spin_limit;
   int thick;  // entries from which a bucket is claimed by fetch-add tickets
+  unsigned long long visit_stop;  // CTAs stop taking tiles once dev->visits reaches this (leaving the queues as they are)
 };
 
 __device__ __forceinline__ void aq_sleep(unsigned ns = 100) { __nanosleep(ns); }
@@ -459,6 +460,11 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
       int t = -1;
       long long spins = 0;
       for (;;) {
+        {  // a bounded burst (V-cycles): stop taking tiles once the visit budget is spent; queued tiles stay queued
+          int over = 0;
+          if (tid == 0) over = *reinterpret_cast<volatile unsigned long long *>(&dev->visits) >= a.visit_stop;
+          if (__shfl_sync(full, over, 0)) break;
+        }
         unsigned int h = 0, tl = 0;
         if (tid < AQ_BUCKETS) {
           h = *reinterpret_cast<volatile unsigned int *>(&dev->head[tid]);
@@ -1132,7 +1138,7 @@ struct FillState {
   // result then says so); the caller exchanges halos and calls run again
   int run(int64_t max_rounds = 0) {
     Ctx &c = ctx();
-    if (use_async) return run_async();
+    if (use_async) return run_async(max_rounds);
     int64_t rounds_this_call = 0;
     FillArgs a = make_args();
     int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 16);
@@ -1195,8 +1201,11 @@ struct FillState {
   DevBuf<AsyncDev> a_dev;
   int a_cap = 0;
   std::vector<int> a_seeds;
+  unsigned long long a_visits_done = 0;
 
-  int run_async() {
+  // max_rounds > 0: a bounded burst of about max_rounds / 4 raster-equivalents of tile visits (bit 2 of the result
+  // says whether tiles are still queued)
+  int run_async(int64_t max_rounds = 0) {
     Ctx &c = ctx();
     const size_t nt = (size_t)tilesX * tilesY;
     AsyncDev *hd = (AsyncDev *)c.pinned;
@@ -1243,6 +1252,8 @@ struct FillState {
     a.profile = (int)c.params.fill_profile;
     a.spin_limit = c.params.fill_async_spin > 0 ? c.params.fill_async_spin : 4000000;
     a.thick = (int)(c.params.fill_async_thick > 0 ? c.params.fill_async_thick : 256);
+    a.visit_stop = ~0ull;
+    if (max_rounds > 0) a.visit_stop = a_visits_done + (unsigned long long)((double)max_rounds / 4.0 * (double)nt) + 1;
     int launches = 0;
     if (!a_seeds.empty()) {
       DevBuf<int> dseeds(a_seeds.size());
@@ -1270,10 +1281,12 @@ struct FillState {
     RDB_CK(cudaMemcpyAsync(hd, a_dev.p, sizeof(AsyncDev), cudaMemcpyDeviceToHost, c.stream));
     RDB_CK(cudaStreamSynchronize(c.stream));
     c.stats.ms_main_kernel += kt.ms();
-    if (hd->abort_flag || hd->pending != 0)
+    a_visits_done = hd->visits;
+    const bool budget_stop = max_rounds > 0 && hd->visits >= a.visit_stop && hd->pending > 0 && !hd->abort_flag;
+    if (!budget_stop && (hd->abort_flag || hd->pending != 0))
       fail("fill (async engine): the tile queues did not drain (pending=%d, watchdog=%d)", hd->pending, hd->abort_flag);
-    still_active = false;
-    first_run = false;
+    still_active = budget_stop;
+    if (!still_active) first_run = false;
     rounds_run++;
     c.stats.fill_rounds = rounds_run;
     c.stats.fill_tile_visits = (int64_t)hd->visits;
@@ -1282,7 +1295,7 @@ struct FillState {
     if (c.params.fill_profile)
       fprintf(stderr, "[fill async] visits=%llu iters=%llu requeues=%llu pop_retries=%llu\n", hd->visits, hd->iters, hd->requeues,
               hd->pop_retries);
-    return hd->edge_changed;
+    return hd->edge_changed | (still_active ? 4 : 0);
   }
 
   // V-cycle plumbing (fill_vcycle): see fill_depressions_level

@@ -249,14 +249,16 @@ def test_async_fill_engine(emulated, gp, checker, shape, q):
 
 
 @pytest.mark.parametrize("k", [2, 3, 4, 8])
-@pytest.mark.parametrize("engine", ["rounds", "async", "vcycle1", "vcycle3"])
+@pytest.mark.parametrize("engine", ["rounds", "async", "vcycle1", "vcycle3", "async_vcycle2"])
 def test_multigrid_seeded_fill(emulated, gp, checker, k, engine):
     """fill_multigrid: the flood starts from the lifted fill of the k x k max-pooled raster (recursively) instead of
     +inf; ragged block edges, NoData, plateaus, both engines.  Any upper bound must relax to the exact surface."""
     import richdem_b200 as rd
     _lib.set_param("fill_multigrid", k)
     _lib.set_param("fill_multigrid_min", 32)
-    _lib.set_param("fill_async", 1 if engine == "async" else 0)
+    _lib.set_param("fill_async", 1 if engine.startswith("async") else 0)
+    if engine == "async_vcycle2":  # the queue engine in bounded bursts (about half a raster-equivalent of visits each)
+        _lib.set_param("fill_vcycle", 2)
     if engine.startswith("vcycle"):  # coarse-grid corrections (restrict / coarse relax / prolong) every 1 or 3 fine rounds
         _lib.set_param("fill_vcycle", int(engine[-1]))
         _lib.set_param("fill_rounds_per_sync", 2)

@@ -33,7 +33,7 @@ step time_fa_d8 240 python tools/accum_switches.py "$N"
 step time_fa_dinf 400 python tools/accum_switches.py "$N" --dinf
 step time_flats_base 240 env RDB200_PROFILE=1 python tools/flats_profile.py "$N"
 step time_flats_uf_tiled 240 env RDB200_PROFILE=1 python tools/flats_profile.py "$N" flats_uf_tiled=1
-step time_fill 400 python tools/fill_profile.py "$N" "" "fill_ordered=0" "fill_multigrid=8" "fill_multigrid=4" "fill_multigrid=8,fill_vcycle=4" "fill_multigrid=8,fill_vcycle=8" "fill_multigrid=4,fill_vcycle=4" "fill_multigrid=8,fill_async=1" "fill_async=1"
+step time_fill 400 python tools/fill_profile.py "$N" "" "fill_ordered=0" "fill_multigrid=8" "fill_multigrid=4" "fill_multigrid=8,fill_vcycle=4" "fill_multigrid=8,fill_vcycle=8" "fill_multigrid=4,fill_vcycle=4" "fill_multigrid=8,fill_async=1" "fill_multigrid=8,fill_vcycle=4,fill_async=1" "fill_async=1"
 step time_fill_async_unordered 200 python tools/fill_profile.py "$N" "fill_async=1,fill_ordered=0"
 
 echo "done" | tee -a "$OUT/summary.txt"
