@@ -98,6 +98,25 @@ def test_product_never_imports_the_oracle():
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
 
 
+def test_product_never_reaches_the_kernel_emulation():
+    """tests/emu (the CPU model of the kernels) is test infrastructure like the oracle: nothing shipped, benchmarked or
+    smoke-tested may name it, and the loader's only mention of it is the refusal to load such a build."""
+    names = ("librdb200_emu_test", "tests/emu", "cuda_emu", "build_emu")
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    for dirpath, _, fs in os.walk(os.path.join(ROOT, "richdem_b200")):
+        files += [os.path.join(dirpath, f) for f in fs if f.endswith((".py", ".cu", ".cuh", ".inc", ".h", ".hpp"))]
+    for dirpath, _, fs in os.walk(os.path.join(ROOT, "include")):
+        files += [os.path.join(dirpath, f) for f in fs]
+    for f in files:
+        src = open(f).read()
+        for n in names:
+            if f.endswith("_lib.py") and n == "tests/emu":
+                continue  # the comment next to the loader's refusal
+            assert n not in src, (f, n)
+    lib_src = open(os.path.join(ROOT, "richdem_b200", "_lib.py")).read()
+    assert lib_src.count("rdb200_emulated") == 1 and "no CPU fallback" in lib_src
+
+
 def test_cxx_dropin_header_links_and_fails_loudly_without_gpu():
     """include/richdem_b200.hpp specialises the reference templates; the prebuilt check binary
     (built by __graft_entry__.build() against /root/reference/include) must route every call into

@@ -6,7 +6,7 @@ coarsely quantised / negative terrain, random NoData patches, random weights and
     RDB_EMU_SMS=3 RDB_EMU_CHAOS=5 python tools/emu_fuzz.py <seed> <seconds>
 
 (RDB_EMU_SMS: cooperative kernels as that many concurrent blocks; RDB_EMU_CHAOS: atomics yield at random.)
-Failing inputs are saved as /tmp/fuzz_fail_<seed>_<case>.npy.  Round 1: 3 647 cases, 0 failures.
+Failing inputs are saved as /tmp/fuzz_fail_<seed>_<case>.npy.  Round 1: about 8 500 cases in all (pipeline and row-band protocols), 0 failures.
 """
 import sys, os, ctypes as C, importlib.util, time, traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
