@@ -115,6 +115,13 @@ def lib():
         L.rdb200_version.restype = C.c_int
         L.rdb200_shutdown.restype = None
         _lib = L
+        # experiment hook: RDB200_PARAMS="fill_multigrid=8,accum_fused_prep=1" presets rdb200_set_param switches for
+        # this process (tools, bench.py and the GPU tests can then run unchanged under candidate defaults)
+        for kv in filter(None, os.environ.get("RDB200_PARAMS", "").split(",")):
+            k, _, v = kv.partition("=")
+            if L.rdb200_set_param(k.strip().encode(), int(v)):
+                msg = L.rdb200_last_error()
+                raise RichdemB200Error(f"RDB200_PARAMS: {msg.decode('utf-8', 'replace') if msg else kv}")
     return _lib
 
 

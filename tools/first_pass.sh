@@ -36,4 +36,9 @@ step time_flats_uf_tiled 240 env RDB200_PROFILE=1 python tools/flats_profile.py 
 step time_fill 400 python tools/fill_profile.py "$N" "" "fill_ordered=0" "fill_multigrid=8" "fill_multigrid=4" "fill_multigrid=8,fill_vcycle=4" "fill_multigrid=8,fill_vcycle=8" "fill_multigrid=4,fill_vcycle=4" "fill_multigrid=8,fill_async=1" "fill_multigrid=8,fill_vcycle=4,fill_async=1" "fill_async=1"
 step time_fill_async_unordered 200 python tools/fill_profile.py "$N" "fill_async=1,fill_ordered=0"
 
+# 3. the whole GPU suite and the bench under the most promising combination
+CAND="fill_multigrid=8,accum_fused_prep=1,accum_walk_lanes=1"
+step suite_under_candidates 400 env RDB200_PARAMS="$CAND" python -m pytest tests -m gpu -x -q
+step bench_under_candidates 300 env RDB200_PARAMS="$CAND" python bench.py --steps 3 --warmup 3
+
 echo "done" | tee -a "$OUT/summary.txt"
