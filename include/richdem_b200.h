@@ -73,8 +73,9 @@ typedef struct rdb200_stats {
 } rdb200_stats;
 RDB200_API int rdb200_get_stats(rdb200_stats *out);
 
-/* Tunables (0 keeps the default).  fill_max_iters caps in-tile relaxation passes per tile
- * visit (default: relax each tile to its local fixed point). */
+/* Tunables (algorithm switches and debug aids; see struct Params in csrc/common.cuh for the list and the
+ * defaults).  "reset_defaults" restores every one of them.  They are process-wide and survive
+ * rdb200_shutdown / re-init.  The library is single-threaded by contract (see above). */
 RDB200_API int rdb200_set_param(const char *name, int64_t value);
 
 /* ---- host entry points: the reference functions they replace ----------------------- */
@@ -119,6 +120,33 @@ RDB200_API int rdb200_fm_d8_f32(const float *dem, float *props9, int32_t width, 
 RDB200_API int rdb200_fm_tarboton_f32(const float *dem, float *props9, int32_t width, int32_t height,
                            float nodata);
 
+/* richdem::FM_D4 = FM_OCallaghan<Topology::D4>  include/richdem/flowmet/OCallaghan1984.hpp:13-77,89-91.
+ * As in the reference, the single receiver's proportion 1 is stored in slot n of the D4 numbering
+ * (1 = W, 2 = N, 3 = E, 4 = S; common/constants.hpp:53-54).  Bit-identical. */
+RDB200_API int rdb200_fm_d4_f32(const float *dem, float *props9, int32_t width, int32_t height, float nodata);
+/* richdem::FM_Quinn  include/richdem/flowmet/Quinn1991.hpp:12-16 (= FM_Holmgren with exponent 1); bit-identical.
+ * richdem::FM_Holmgren(elevations, props, xparam)  include/richdem/flowmet/Holmgren1994.hpp:13-83.
+ * richdem::FM_Freeman(elevations, props, xparam)   include/richdem/flowmet/Freeman1991.hpp:13-80.
+ * Same mixed float/double arithmetic as the reference; with an exponent other than 1 the device pow differs from
+ * libm by <= 2 ulp (double), i.e. proportions within 1 float ulp. */
+RDB200_API int rdb200_fm_quinn_f32(const float *dem, float *props9, int32_t width, int32_t height, float nodata);
+RDB200_API int rdb200_fm_holmgren_f32(const float *dem, float *props9, int32_t width, int32_t height, float nodata,
+                                      double xparam);
+RDB200_API int rdb200_fm_freeman_f32(const float *dem, float *props9, int32_t width, int32_t height, float nodata,
+                                     double xparam);
+
+/* richdem::FA_D4 / FA_Quinn / FA_Holmgren / FA_Freeman(const Array2D<float>&, Array2D<double>&[, xparam])
+ *   include/richdem/methods/flow_accumulation.hpp:28,19,18,20 (pyrichdem: pywrapper.hpp:65,58,57,59).
+ *   FM_x into a device-resident proportions array (36 B/cell, never leaves HBM) + the generic accumulation below.
+ *   accum_inout arrives holding the weights. */
+RDB200_API int rdb200_fa_d4_f32_f64(const float *dem, double *accum_inout, int32_t width, int32_t height, float nodata);
+RDB200_API int rdb200_fa_quinn_f32_f64(const float *dem, double *accum_inout, int32_t width, int32_t height,
+                                       float nodata);
+RDB200_API int rdb200_fa_holmgren_f32_f64(const float *dem, double *accum_inout, int32_t width, int32_t height,
+                                          float nodata, double xparam);
+RDB200_API int rdb200_fa_freeman_f32_f64(const float *dem, double *accum_inout, int32_t width, int32_t height,
+                                         float nodata, double xparam);
+
 /* richdem::FlowAccumulation(const Array3D<float>&, Array2D<double>&)
  *   include/richdem/methods/flow_accumulation_generic.hpp:33-100 (pyrichdem
  *   "FlowAccumulation", wrappers/pyrichdem/src/pywrapper.cpp:50).  accum arrives holding the
@@ -148,6 +176,11 @@ RDB200_API int rdb200_dev_fm_d8_f32(const float *d_dem, float *d_props9, int32_t
                          float nodata);
 RDB200_API int rdb200_dev_fm_tarboton_f32(const float *d_dem, float *d_props9, int32_t width, int32_t height,
                                float nodata);
+/* method: 0 FM_D8, 1 FM_Tarboton, 2 FM_D4, 3 FM_Holmgren (xparam; FM_Quinn = 1.0), 4 FM_Freeman (xparam) */
+RDB200_API int rdb200_dev_fm_method_f32(int32_t method, const float *d_dem, float *d_props9, int32_t width,
+                                        int32_t height, float nodata, double xparam);
+RDB200_API int rdb200_dev_fa_method_f32_f64(int32_t method, const float *d_dem, double *d_accum_inout, int32_t width,
+                                            int32_t height, float nodata, double xparam);
 RDB200_API int rdb200_dev_flow_accumulation_props_f64(const float *d_props9, double *d_accum_inout,
                                            int32_t width, int32_t height);
 RDB200_API int rdb200_dev_fa_d8_f32_f64(const float *d_dem, double *d_accum_inout, int32_t width,

@@ -61,6 +61,22 @@ template <class A2, class P3>
 void fm_tarboton(const A2 &dem, P3 &props) {
   check(rdb200_fm_tarboton_f32(dem.data(), props.getData(), dem.width(), dem.height(), (float)dem.noData()));
 }
+template <class A2, class P3>
+void fm_d4(const A2 &dem, P3 &props) {
+  check(rdb200_fm_d4_f32(dem.data(), props.getData(), dem.width(), dem.height(), (float)dem.noData()));
+}
+template <class A2, class P3>
+void fm_quinn(const A2 &dem, P3 &props) {
+  check(rdb200_fm_quinn_f32(dem.data(), props.getData(), dem.width(), dem.height(), (float)dem.noData()));
+}
+template <class A2, class P3>
+void fm_holmgren(const A2 &dem, P3 &props, double xparam) {
+  check(rdb200_fm_holmgren_f32(dem.data(), props.getData(), dem.width(), dem.height(), (float)dem.noData(), xparam));
+}
+template <class A2, class P3>
+void fm_freeman(const A2 &dem, P3 &props, double xparam) {
+  check(rdb200_fm_freeman_f32(dem.data(), props.getData(), dem.width(), dem.height(), (float)dem.noData(), xparam));
+}
 template <class P3, class C2>
 void flow_accumulation(P3 &props, C2 &accum) {
   check(rdb200_flow_accumulation_props_f64(props.getData(), accum.data(), accum.width(), accum.height()));
@@ -68,6 +84,22 @@ void flow_accumulation(P3 &props, C2 &accum) {
 template <class A2, class C2>
 void fa_d8(const A2 &dem, C2 &accum) {
   check(rdb200_fa_d8_f32_f64(dem.data(), accum.data(), dem.width(), dem.height(), (float)dem.noData(), 0));
+}
+template <class A2, class C2>
+void fa_d4(const A2 &dem, C2 &accum) {
+  check(rdb200_fa_d4_f32_f64(dem.data(), accum.data(), dem.width(), dem.height(), (float)dem.noData()));
+}
+template <class A2, class C2>
+void fa_quinn(const A2 &dem, C2 &accum) {
+  check(rdb200_fa_quinn_f32_f64(dem.data(), accum.data(), dem.width(), dem.height(), (float)dem.noData()));
+}
+template <class A2, class C2>
+void fa_holmgren(const A2 &dem, C2 &accum, double xparam) {
+  check(rdb200_fa_holmgren_f32_f64(dem.data(), accum.data(), dem.width(), dem.height(), (float)dem.noData(), xparam));
+}
+template <class A2, class C2>
+void fa_freeman(const A2 &dem, C2 &accum, double xparam) {
+  check(rdb200_fa_freeman_f32_f64(dem.data(), accum.data(), dem.width(), dem.height(), (float)dem.noData(), xparam));
 }
 template <class A2, class C2>
 void fa_tarboton(const A2 &dem, C2 &accum) {
@@ -96,6 +128,12 @@ namespace richdem {
 // depressions/depressions.hpp:13-21 (D8 -> PriorityFlood_Zhou2016, Zhou2016.hpp:125-191)
 template <>
 inline void FillDepressions<Topology::D8, float>(Array2D<float> &dem) {
+  richdem_b200::fill_depressions_d8(dem);
+}
+// depressions/Zhou2016.hpp:125-191 -- what FillDepressions<D8> dispatches to, and what pyrichdem binds directly as
+// rdFillDepressionsD8 (wrappers/pyrichdem/src/pywrapper.hpp:32)
+template <>
+inline void PriorityFlood_Zhou2016<float>(Array2D<float> &dem) {
   richdem_b200::fill_depressions_d8(dem);
 }
 #endif
@@ -145,6 +183,27 @@ inline void FM_Dinfinity<float>(const Array2D<float> &elevations, Array3D<float>
   props.setNoData(NO_DATA_GEN);
   richdem_b200::fm_tarboton(elevations, props);
 }
+// flowmet/OCallaghan1984.hpp:89-91, Quinn1991.hpp:12-16, Holmgren1994.hpp:13-83, Freeman1991.hpp:13-80
+template <>
+inline void FM_D4<float>(const Array2D<float> &elevations, Array3D<float> &props) {
+  props.setNoData(NO_DATA_GEN);
+  richdem_b200::fm_d4(elevations, props);
+}
+template <>
+inline void FM_Quinn<float>(const Array2D<float> &elevations, Array3D<float> &props) {
+  props.setNoData(NO_DATA_GEN);
+  richdem_b200::fm_quinn(elevations, props);
+}
+template <>
+inline void FM_Holmgren<float>(const Array2D<float> &elevations, Array3D<float> &props, const double xparam) {
+  props.setNoData(NO_DATA_GEN);
+  richdem_b200::fm_holmgren(elevations, props, xparam);
+}
+template <>
+inline void FM_Freeman<float>(const Array2D<float> &elevations, Array3D<float> &props, const double xparam) {
+  props.setNoData(NO_DATA_GEN);
+  richdem_b200::fm_freeman(elevations, props, xparam);
+}
 // methods/flow_accumulation_generic.hpp:33-100
 template <>
 inline void FlowAccumulation<double>(const Array3D<float> &props, Array2D<double> &accum) {
@@ -174,6 +233,35 @@ inline void FA_Dinfinity<float, double>(const Array2D<float> &elevations, Array2
   if (accum.width() != elevations.width() || accum.height() != elevations.height())
     throw std::runtime_error("Accumulation array must have same dimensions as proportions array!");
   richdem_b200::fa_tarboton(elevations, accum);
+}
+// methods/flow_accumulation.hpp:28,19,18,20 -- the 36 B/cell proportions stay in HBM
+template <>
+inline void FA_D4<float, double>(const Array2D<float> &elevations, Array2D<double> &accum) {
+  accum.setNoData(ACCUM_NO_DATA);
+  if (accum.width() != elevations.width() || accum.height() != elevations.height())
+    throw std::runtime_error("Accumulation array must have same dimensions as proportions array!");
+  richdem_b200::fa_d4(elevations, accum);
+}
+template <>
+inline void FA_Quinn<float, double>(const Array2D<float> &elevations, Array2D<double> &accum) {
+  accum.setNoData(ACCUM_NO_DATA);
+  if (accum.width() != elevations.width() || accum.height() != elevations.height())
+    throw std::runtime_error("Accumulation array must have same dimensions as proportions array!");
+  richdem_b200::fa_quinn(elevations, accum);
+}
+template <>
+inline void FA_Holmgren<float, double>(const Array2D<float> &elevations, Array2D<double> &accum, double xparam) {
+  accum.setNoData(ACCUM_NO_DATA);
+  if (accum.width() != elevations.width() || accum.height() != elevations.height())
+    throw std::runtime_error("Accumulation array must have same dimensions as proportions array!");
+  richdem_b200::fa_holmgren(elevations, accum, xparam);
+}
+template <>
+inline void FA_Freeman<float, double>(const Array2D<float> &elevations, Array2D<double> &accum, double xparam) {
+  accum.setNoData(ACCUM_NO_DATA);
+  if (accum.width() != elevations.width() || accum.height() != elevations.height())
+    throw std::runtime_error("Accumulation array must have same dimensions as proportions array!");
+  richdem_b200::fa_freeman(elevations, accum, xparam);
 }
 #endif
 

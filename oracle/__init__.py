@@ -66,6 +66,8 @@ class _Backend:
         self._facc = self._sig(n["facc"], [_f32p, C.c_int, C.c_int, _f64p])
         self._fa_d8 = self._sig(n["fa_d8"], [_f32p, C.c_int, C.c_int, C.c_float, _f64p])
         self._fa_dinf = self._sig(n["fa_dinf"], [_f32p, C.c_int, C.c_int, C.c_float, _f64p])
+        self._fm_method = self._sig(n["fm_method"], [C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_double, _f32p])
+        self._fa_method = self._sig(n["fa_method"], [C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_double, _f64p])
         self._extra = {}
         for k in ("fill_zhou", "fill_barnes", "fill_original"):
             if k in n:
@@ -150,6 +152,25 @@ class _Backend:
         self._fm_dinf(d, w, h, nodata, out.reshape(-1))
         return out
 
+    # -- f1: the remaining flow metrics.  method: "D4", "Quinn", "Holmgren", "Freeman" (also "D8", "Dinf")
+    METHOD_IDS = {"D8": 0, "Dinf": 1, "D4": 2, "Quinn": 3, "Holmgren": 3, "Freeman": 4}
+
+    def fm_method(self, dem, nodata, method, exponent=None):
+        d = self._dem(dem)
+        h, w = d.shape
+        out = np.empty((h, w, 9), np.float32)
+        x = 1.0 if method == "Quinn" else float(exponent or 0.0)
+        self._fm_method(self.METHOD_IDS[method], d, w, h, nodata, x, out.reshape(-1))
+        return out
+
+    def fa_method(self, dem, nodata, method, exponent=None, weights=None):
+        d = self._dem(dem)
+        h, w = d.shape
+        acc = np.ones((h, w), np.float64) if weights is None else np.array(weights, np.float64, order="C")
+        x = 1.0 if method == "Quinn" else float(exponent or 0.0)
+        self._fa_method(self.METHOD_IDS[method], d, w, h, nodata, x, acc)
+        return acc
+
     # -- a11
     def flow_accumulation(self, props, weights=None):
         p = np.ascontiguousarray(props, np.float32)
@@ -181,7 +202,7 @@ _PORT_NAMES = dict(
     dirs="orc_d8_flow_directions_f32", d8acc_u8="orc_d8_flow_accum_u8_i32",
     d8acc_i32="orc_d8_flow_accum_i32", fm_d8="orc_fm_d8_f32", fm_dinf="orc_fm_tarboton_f32",
     facc="orc_flow_accumulation_props_f64", fa_d8="orc_fa_d8_f32_f64",
-    fa_dinf="orc_fa_tarboton_f32_f64",
+    fa_dinf="orc_fa_tarboton_f32_f64", fm_method="orc_fm_method_f32", fa_method="orc_fa_method_f32_f64",
 )
 _REF_NAMES = dict(
     kind="reference",
@@ -190,7 +211,7 @@ _REF_NAMES = dict(
     dirs="ref_d8_flow_directions_f32", d8acc_u8="ref_d8_flow_accum_u8_i32",
     d8acc_i32="ref_d8_flow_accum_i32_i32", fm_d8="ref_fm_d8_f32", fm_dinf="ref_fm_tarboton_f32",
     facc="ref_flow_accumulation_props_f64", fa_d8="ref_fa_d8_f32_f64",
-    fa_dinf="ref_fa_tarboton_f32_f64",
+    fa_dinf="ref_fa_tarboton_f32_f64", fm_method="ref_fm_method_f32", fa_method="ref_fa_method_f32_f64",
     fill_zhou="ref_priority_flood_zhou2016_f32", fill_barnes="ref_priority_flood_barnes2014_f32",
     fill_original="ref_priority_flood_original_f32",
 )
@@ -223,6 +244,19 @@ def ref() -> _Backend:
 def best() -> _Backend:
     """Reference when it was built here, else the port."""
     return ref() if have_ref() else port()
+
+
+def device_fbm(h: int, w: int, seed: int = 42, octaves: int = 12, quantum: float = 0.0, y0: int = 0) -> np.ndarray:
+    """The benchmark raster: bit-identical CPU restatement (oracle.c: orc_generate_fbm_f32) of the device generator
+    rdb200_dev_generate_fbm_f32 (rows y0 .. y0+h of the raster), multi-threaded."""
+    build()
+    lib = C.CDLL(_PORT_PATH)
+    f = lib.orc_generate_fbm_f32
+    f.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_float]
+    f.restype = None
+    out = np.empty((h, w), np.float32)
+    f(out, w, h, y0, seed, octaves, quantum)
+    return out
 
 
 # ---------------------------------------------------------------------------------------

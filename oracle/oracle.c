@@ -595,3 +595,155 @@ void orc_fa_tarboton_f32_f64(const float *dem, int w, int h, float nodata, doubl
   orc_flow_accumulation_props_f64(props, w, h, accum);
   free(props);
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* f1  FM_D4 = FM_OCallaghan<D4> (flowmet/OCallaghan1984.hpp:13-77,89-91): the same scan  */
+/* over the 4 cardinal neighbours (common/constants.hpp:53-54: 1=W 2=N 3=E 4=S); the       */
+/* proportion lands in slot n of THAT numbering, as in the reference.                      */
+static void orc_fm_d4_f32(const float *dem, int w, int h, float nodata, float *props) {
+  static const int D4X[5] = {0, -1, 0, 1, 0};
+  static const int D4Y[5] = {0, 0, -1, 0, 1};
+  const size_t n = (size_t)w * h;
+  for (size_t i = 0; i < 9 * n; i++) props[i] = NO_FLOW_GEN;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const size_t i = (size_t)y * w + x;
+      if (dem[i] == nodata) {
+        props[9 * i] = NO_DATA_GEN;
+        continue;
+      }
+      if (x == 0 || y == 0 || x == w - 1 || y == h - 1) continue;
+      const float e = dem[i];
+      int lowest_n = 0;
+      float lowest = 3.402823466e+38f;
+      for (int k = 1; k <= 4; k++) {
+        const float ne = dem[(size_t)(y + D4Y[k]) * w + (x + D4X[k])];
+        if (ne == nodata) continue;
+        if (ne >= e) continue;
+        if (ne < lowest) {
+          lowest = ne;
+          lowest_n = k;
+        }
+      }
+      if (lowest_n == 0) continue;
+      props[9 * i] = HAS_FLOW_GEN;
+      props[9 * i + lowest_n] = 1.0f;
+    }
+}
+
+/* f1  FM_Holmgren (flowmet/Holmgren1994.hpp:13-83; FM_Quinn = exponent 1, Quinn1991.hpp:15) */
+/* and FM_Freeman (flowmet/Freeman1991.hpp:13-80).  Holmgren sums the float-rounded powers  */
+/* (`C += props(x,y,n)`, :65), Freeman the double ones (`C += cval`, :60).                  */
+static void orc_fm_mfd_f32(const float *dem, int w, int h, float nodata, double xparam, int holmgren, float *props) {
+  const double SQRT2 = 1.414213562373095048801688724209698078569671875376948; /* constants.hpp:34 */
+  const double L1 = 0.5, L2 = 0.354;                                           /* Holmgren1994.hpp:25-26 */
+  const size_t n = (size_t)w * h;
+  for (size_t i = 0; i < 9 * n; i++) props[i] = NO_FLOW_GEN;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const size_t i = (size_t)y * w + x;
+      float *p = props + 9 * i;
+      if (dem[i] == nodata) {
+        p[0] = NO_DATA_GEN;
+        continue;
+      }
+      if (x == 0 || y == 0 || x == w - 1 || y == h - 1) continue;
+      const float e = dem[i];
+      double C = 0;
+      for (int k = 1; k <= 8; k++) {
+        const float ne = dem[(size_t)(y + D8Y[k]) * w + (x + D8X[k])];
+        if (ne == nodata) continue;
+        if (ne < e) {
+          const double rise = e - ne; /* float subtraction, then widened */
+          const double run = (k & 1) ? 1.0 : SQRT2;
+          const double grad = rise / run;
+          if (holmgren) {
+            p[k] = (float)pow(grad * ((k & 1) ? L1 : L2), xparam);
+            C += p[k];
+          } else {
+            const double cval = pow(grad, xparam);
+            p[k] = (float)cval;
+            C += cval;
+          }
+        }
+      }
+      if (C > 0) {
+        p[0] = HAS_FLOW_GEN;
+        C = 1 / C;
+        for (int k = 1; k <= 8; k++) p[k] = p[k] > 0 ? (float)(p[k] * C) : 0.0f;
+      }
+    }
+}
+
+/* method: 2 FM_D4, 3 FM_Holmgren (FM_Quinn: xparam 1), 4 FM_Freeman -- numbering of the C ABI */
+void orc_fm_method_f32(int method, const float *dem, int w, int h, float nodata, double xparam, float *props) {
+  if (method == 0) orc_fm_d8_f32(dem, w, h, nodata, props);
+  else if (method == 1) orc_fm_tarboton_f32(dem, w, h, nodata, props);
+  else if (method == 2) orc_fm_d4_f32(dem, w, h, nodata, props);
+  else orc_fm_mfd_f32(dem, w, h, nodata, xparam, method == 3, props);
+}
+
+/* FA_D4 / FA_Quinn / FA_Holmgren / FA_Freeman (methods/flow_accumulation.hpp:28,19,18,20) */
+void orc_fa_method_f32_f64(int method, const float *dem, int w, int h, float nodata, double xparam, double *accum) {
+  float *props = (float *)malloc(sizeof(float) * 9 * (size_t)w * h);
+  orc_fm_method_f32(method, dem, w, h, nodata, xparam, props);
+  orc_flow_accumulation_props_f64(props, w, h, accum);
+  free(props);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Benchmark input: CPU restatement of the device terrain generator (richdem_b200/csrc/   */
+/* terrain.cu, fbm_kernel -- this repository's own synthetic DEM, not a reference         */
+/* function).  Same integer hash, same single-precision operation order, one rounding per */
+/* operation (build with -ffp-contract=off), so rdb200_dev_generate_fbm_f32 and this      */
+/* function produce identical bits: bench.py --impl reference times the reference on      */
+/* exactly the raster the GPU arm uses without touching the GPU.                           */
+static uint32_t fbm_hash3(uint32_t x, uint32_t y, uint32_t s) {
+  uint32_t h = x * 0x9E3779B1u ^ (y * 0x85EBCA77u + 0x7F4A7C15u) ^ (s * 0xC2B2AE3Du);
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
+}
+static float fbm_lattice(uint32_t ix, uint32_t iy, uint32_t s) {
+  return (float)(fbm_hash3(ix, iy, s) >> 8) * (1.0f / 16777216.0f);
+}
+static float fbm_fade(float t) {
+  const float inner = (t * (t * 6.f - 15.f)) + 10.f;
+  return ((t * t) * t) * inner;
+}
+void orc_generate_fbm_f32(float *dem, int w, int h, int y0, uint32_t seed, int octaves, float quantum) {
+  const int top_log2 = 12;
+  if (octaves <= 0) octaves = 12;
+#pragma omp parallel for schedule(static)
+  for (int yl = 0; yl < h; yl++) {
+    const int y = y0 + yl;
+    for (int x = 0; x < w; x++) {
+      float sum = 0.f, amp = 1.f, norm = 0.f;
+      for (int o = 0; o < octaves; o++) {
+        const int lg = top_log2 - o;
+        if (lg < 1) break;
+        const uint32_t cell = 1u << lg;
+        const uint32_t ix = (uint32_t)x >> lg, iy = (uint32_t)y >> lg;
+        float tx = (float)((uint32_t)x & (cell - 1)) / (float)cell;
+        float ty = (float)((uint32_t)y & (cell - 1)) / (float)cell;
+        tx = fbm_fade(tx);
+        ty = fbm_fade(ty);
+        const uint32_t s = seed * 131u + (uint32_t)o;
+        const float v00 = fbm_lattice(ix, iy, s), v01 = fbm_lattice(ix + 1, iy, s);
+        const float v10 = fbm_lattice(ix, iy + 1, s), v11 = fbm_lattice(ix + 1, iy + 1, s);
+        const float top = v00 * (1.f - tx) + v01 * tx;
+        const float bot = v10 * (1.f - tx) + v11 * tx;
+        const float v = top * (1.f - ty) + bot * ty;
+        sum = sum + amp * v;
+        norm = norm + amp;
+        amp = amp * 0.5946035575f;
+      }
+      float z = (1000.0f * sum) / norm;
+      if (quantum > 0.f) z = rintf(z / quantum) * quantum;
+      dem[(size_t)yl * w + x] = z;
+    }
+  }
+}

@@ -155,4 +155,34 @@ void ref_fa_tarboton_f32_f64(const float *dem, int w, int h, float nodata, doubl
   FA_Tarboton(a, acc);
 }
 
+// method numbering of the C ABI: 0 FM_D8, 1 FM_Tarboton, 2 FM_D4 (flowmet/OCallaghan1984.hpp:89-91),
+// 3 FM_Holmgren (flowmet/Holmgren1994.hpp:13-83; xparam 1 is what FM_Quinn passes, Quinn1991.hpp:15),
+// 4 FM_Freeman (flowmet/Freeman1991.hpp:13-80)
+void ref_fm_method_f32(int method, const float *dem, int w, int h, float nodata, double xparam, float *props) {
+  Array2D<float> a(const_cast<float *>(dem), w, h);
+  a.setNoData(nodata);
+  Array3D<float> p(props, w, h);
+  switch (method) {
+    case 0: FM_D8(a, p); break;
+    case 1: FM_Tarboton(a, p); break;
+    case 2: FM_D4(a, p); break;
+    case 3: if (xparam == 1.0) FM_Quinn(a, p); else FM_Holmgren(a, p, xparam); break;
+    default: FM_Freeman(a, p, xparam); break;
+  }
+}
+
+// methods/flow_accumulation.hpp:28,19,18,20
+void ref_fa_method_f32_f64(int method, const float *dem, int w, int h, float nodata, double xparam, double *accum) {
+  Array2D<float> a(const_cast<float *>(dem), w, h);
+  a.setNoData(nodata);
+  Array2D<double> acc(accum, w, h);
+  switch (method) {
+    case 0: FA_D8(a, acc); break;
+    case 1: FA_Tarboton(a, acc); break;
+    case 2: FA_D4(a, acc); break;
+    case 3: if (xparam == 1.0) FA_Quinn(a, acc); else FA_Holmgren(a, acc, xparam); break;
+    default: FA_Freeman(a, acc, xparam); break;
+  }
+}
+
 }  // extern "C"

@@ -24,8 +24,10 @@ __version__ = "0.1.0"
 
 _D8_METHODS = ("D8", "OCallaghanD8")
 _DINF_METHODS = ("Dinf", "Tarboton")
-_OUT_OF_SCOPE_METHODS = ("Quinn", "Holmgren", "Freeman", "FairfieldLeymarieD8", "FairfieldLeymarieD4",
-                         "Rho8", "Rho4", "OCallaghanD4", "D4")
+_D4_METHODS = ("D4", "OCallaghanD4")
+_EXPONENT_METHODS = ("Freeman", "Holmgren")
+# random-walk metrics (Rho8/Rho4 draw from the reference's global RNG; not reproducible on a GPU) stay on the CPU
+_OUT_OF_SCOPE_METHODS = ("FairfieldLeymarieD8", "FairfieldLeymarieD4", "Rho8", "Rho4")
 
 
 def _version_string() -> str:
@@ -177,7 +179,8 @@ def _accum_array(like, weights, in_place, shape):
 def FlowAccumulation(dem: rdarray, method: Optional[str] = None, exponent: Optional[float] = None,
                      weights: Optional[rdarray] = None, in_place: bool = False) -> rdarray:
     """Flow accumulation (reference FlowAccumulation, :490-596).  Methods on the B200 path:
-    ``D8`` / ``OCallaghanD8`` (FA_D8) and ``Dinf`` / ``Tarboton`` (FA_Tarboton)."""
+    ``D8`` / ``OCallaghanD8`` (FA_D8), ``Dinf`` / ``Tarboton`` (FA_Tarboton), ``D4`` / ``OCallaghanD4`` (FA_D4),
+    ``Quinn``, ``Holmgren`` (exponent), ``Freeman`` (exponent)."""
     if type(dem) is not rdarray:
         raise Exception("A richdem.rdarray or numpy.ndarray is required!")
     accum, ones = _accum_array(dem, weights, in_place, dem.shape)
@@ -190,12 +193,27 @@ def FlowAccumulation(dem: rdarray, method: Optional[str] = None, exponent: Optio
         _lib.check(L.rdb200_fa_d8_f32_f64(_lib.ptr(d), _lib.ptr(accum), w, h, _nodata_f32(dem), int(ones)))
     elif method in _DINF_METHODS:
         _lib.check(L.rdb200_fa_tarboton_f32_f64(_lib.ptr(d), _lib.ptr(accum), w, h, _nodata_f32(dem), int(ones)))
+    elif method in _D4_METHODS or method == "Quinn" or method in _EXPONENT_METHODS:
+        # FM_x into a device-resident proportions array + the generic accumulation (flow_accumulation.hpp:18-20,28)
+        if ones:
+            accum[...] = 1.0
+        nd = _nodata_f32(dem)
+        if method in _D4_METHODS:
+            _lib.check(L.rdb200_fa_d4_f32_f64(_lib.ptr(d), _lib.ptr(accum), w, h, nd))
+        elif method == "Quinn":
+            _lib.check(L.rdb200_fa_quinn_f32_f64(_lib.ptr(d), _lib.ptr(accum), w, h, nd))
+        else:
+            if exponent is None:
+                raise Exception(f'FlowAccumulation method "{method}" requires an exponent!')
+            fn = L.rdb200_fa_freeman_f32_f64 if method == "Freeman" else L.rdb200_fa_holmgren_f32_f64
+            _lib.check(fn(_lib.ptr(d), _lib.ptr(accum), w, h, nd, float(exponent)))
     elif method in _OUT_OF_SCOPE_METHODS:
         raise Exception(f'FlowAccumulation method "{method}" is outside the B200 hot path '
-                        "(available: D8, OCallaghanD8, Dinf, Tarboton)")
+                        "(random-walk metric; use the reference CPU implementation)")
     else:
         raise Exception("Invalid FlowAccumulation method. Valid methods are: " +
-                        ", ".join(_DINF_METHODS + _D8_METHODS + _OUT_OF_SCOPE_METHODS))
+                        ", ".join(_DINF_METHODS + ("Quinn",) + _D8_METHODS + _D4_METHODS + _EXPONENT_METHODS +
+                                  _OUT_OF_SCOPE_METHODS))
     accum.no_data = -1
     return accum
 
@@ -232,12 +250,22 @@ def FlowProportions(dem: rdarray, method: Optional[str] = None, exponent: Option
         _lib.check(L.rdb200_fm_d8_f32(_lib.ptr(d), _lib.ptr(fprops), w, h, _nodata_f32(dem)))
     elif method in _DINF_METHODS:
         _lib.check(L.rdb200_fm_tarboton_f32(_lib.ptr(d), _lib.ptr(fprops), w, h, _nodata_f32(dem)))
+    elif method in _D4_METHODS:
+        _lib.check(L.rdb200_fm_d4_f32(_lib.ptr(d), _lib.ptr(fprops), w, h, _nodata_f32(dem)))
+    elif method == "Quinn":
+        _lib.check(L.rdb200_fm_quinn_f32(_lib.ptr(d), _lib.ptr(fprops), w, h, _nodata_f32(dem)))
+    elif method in _EXPONENT_METHODS:
+        if exponent is None:
+            raise Exception('FlowProportions method "' + method + '" requires an exponent!')
+        fn = L.rdb200_fm_freeman_f32 if method == "Freeman" else L.rdb200_fm_holmgren_f32
+        _lib.check(fn(_lib.ptr(d), _lib.ptr(fprops), w, h, _nodata_f32(dem), float(exponent)))
     elif method in _OUT_OF_SCOPE_METHODS:
         raise Exception(f'FlowProportions method "{method}" is outside the B200 hot path '
-                        "(available: D8, OCallaghanD8, Dinf, Tarboton)")
+                        "(random-walk metric; use the reference CPU implementation)")
     else:
         raise Exception("Invalid FlowProportions method. Valid methods are: " +
-                        ", ".join(_DINF_METHODS + _D8_METHODS + _OUT_OF_SCOPE_METHODS))
+                        ", ".join(_DINF_METHODS + ("Quinn",) + _D8_METHODS + _D4_METHODS + _EXPONENT_METHODS +
+                                  _OUT_OF_SCOPE_METHODS))
     fprops.no_data = -2
     return fprops
 

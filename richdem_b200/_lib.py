@@ -48,6 +48,16 @@ SIGNATURES = {
     "rdb200_d8_flow_accum_u8_i32": [_vp, _vp, _i32, _i32],
     "rdb200_fm_d8_f32": [_vp, _vp, _i32, _i32, _f32],
     "rdb200_fm_tarboton_f32": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_fm_d4_f32": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_fm_quinn_f32": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_fm_holmgren_f32": [_vp, _vp, _i32, _i32, _f32, C.c_double],
+    "rdb200_fm_freeman_f32": [_vp, _vp, _i32, _i32, _f32, C.c_double],
+    "rdb200_fa_d4_f32_f64": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_fa_quinn_f32_f64": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_fa_holmgren_f32_f64": [_vp, _vp, _i32, _i32, _f32, C.c_double],
+    "rdb200_fa_freeman_f32_f64": [_vp, _vp, _i32, _i32, _f32, C.c_double],
+    "rdb200_dev_fm_method_f32": [_i32, _vp, _vp, _i32, _i32, _f32, C.c_double],
+    "rdb200_dev_fa_method_f32_f64": [_i32, _vp, _vp, _i32, _i32, _f32, C.c_double],
     "rdb200_flow_accumulation_props_f64": [_vp, _vp, _i32, _i32],
     "rdb200_fa_d8_f32_f64": [_vp, _vp, _i32, _i32, _f32, _i32],
     "rdb200_fa_tarboton_f32_f64": [_vp, _vp, _i32, _i32, _f32, _i32],
@@ -143,6 +153,11 @@ def stats() -> dict:
 
 def set_param(name: str, value: int) -> None:
     check(lib().rdb200_set_param(name.encode(), int(value)))
+
+
+def reset_params() -> None:
+    """Every rdb200_set_param switch back to its shipped default."""
+    set_param("reset_defaults", 1)
 
 
 def init(device: int = 0) -> None:

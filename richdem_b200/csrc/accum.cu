@@ -490,347 +490,46 @@ __device__ __forceinline__ void levels_follow(const WalkArgs<double> &a, int c, 
 // single-file reaches cost no extra levels, while every other cell it completes -- and its own
 // continuation when the budget runs out -- is appended (coalesced-group atomics) to the next
 // frontier, where other threads pick it up in parallel.  Levels meet at grid.sync().
-// Tail mode (tail_n > 0): once a frontier has at most tail_n cells there is nothing for a whole
-// grid to do, and a grid-wide barrier per level costs far more than the level; block 0 then drains
-// the following levels alone with block barriers (and a larger walking budget) until the frontier
-// is empty or has grown past 4 * tail_n again, while the other blocks wait at the next grid.sync().
 // BAND (row bands, D-infinity): level 0 can be seeded with the cells completed by a neighbour's flow
 // (q0[0..ncells), seeded != 0) and flow into a ghost row is parked there instead of followed.
 template <int MODE, bool BAND = false>
 __global__ void __launch_bounds__(256) accum_levels_kernel(const WalkArgs<double> a, int *q0, int *q1, int *counts,
-                                                            int ncells, int budget, int *levels_out, int seeded,
-                                                            int tail_n, int tail_budget, int agg) {
-  constexpr int kLvCap = 4096;
-  __shared__ int sBuf[kLvCap];
-  __shared__ int sCount, sBase;
+                                                            int ncells, int budget, int *levels_out, int seeded) {
   cg::grid_group grid = cg::this_grid();
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   int level = 0;
   for (;; level++) {
     const int n = level == 0 ? ncells : *reinterpret_cast<volatile int *>(&counts[level % 3]);
     if (n == 0) break;
-    if (tail_n > 0 && level > 0 && n <= tail_n) {
-      grid.sync();  // every block has read `n` and taken this branch before block 0 starts recycling the counters
-      if (blockIdx.x == 0) {
-        int lv = level;
-        for (;;) {
-          const int m = *reinterpret_cast<volatile int *>(&counts[lv % 3]);
-          if (m == 0 || m > 4 * tail_n) break;
-          if (threadIdx.x == 0) counts[(lv + 2) % 3] = 0;
-          const int *qc = (lv & 1) ? q1 : q0;
-          int *qn = (lv & 1) ? q0 : q1;
-          int *cntn = &counts[(lv + 1) % 3];
-          auto push = [&](int r) { qn[atomicAdd(cntn, 1)] = r; };
-          for (int idx = threadIdx.x; idx < m; idx += blockDim.x)
-            levels_follow<MODE, BAND>(a, __ldcg(qc + idx), tail_budget, push);
-          __threadfence();
-          __syncthreads();  // the next frontier and its count are complete and visible to the block
-          lv++;
-        }
-        if (threadIdx.x == 0) *levels_out = lv;  // level to resume at (its frontier is in counts[lv % 3])
-        __threadfence();
-      }
-      grid.sync();
-      level = *reinterpret_cast<volatile int *>(levels_out) - 1;
-      continue;
-    }
     if (gtid == 0) counts[(level + 2) % 3] = 0;
     const int *qc = (level & 1) ? q1 : q0;
     int *qn = (level & 1) ? q0 : q1;
     int *cntn = &counts[(level + 1) % 3];
-    if (agg) {
-      // block-aggregated frontier: cells are collected in shared memory and appended to the global
-      // frontier with ONE atomic per block and level instead of one per converged group of lanes
-      // (the frontier counter is a single address; with ~10^5 pushes per level it serialises at L2)
-      if (threadIdx.x == 0) sCount = 0;
-      __syncthreads();
-      auto push = [&](int r) {
-        const int pos = atomicAdd(&sCount, 1);
-        if (pos < kLvCap) sBuf[pos] = r;
-        else qn[atomicAdd(cntn, 1)] = r;  // buffer full: straight to the global frontier
-      };
-      for (int idx = gtid; idx < n; idx += gsize) {
-        int c;
-        if (level == 0 && !(BAND && seeded)) {
-          c = idx;
-          if (!(a.st[c] & kSrcFlag)) continue;
-        } else {
-          c = __ldcg(qc + idx);
-        }
-        levels_follow<MODE, BAND>(a, c, budget, push);
+    auto push = [&](int r) {
+      cg::coalesced_group g = cg::coalesced_threads();
+      int base = 0;
+      if (g.thread_rank() == 0) base = atomicAdd(cntn, (int)g.size());
+      base = g.shfl(base, 0);
+      qn[base + g.thread_rank()] = r;
+    };
+    for (int idx = gtid; idx < n; idx += gsize) {
+      int c;
+      if (level == 0 && !(BAND && seeded)) {
+        c = idx;
+        if (!(a.st[c] & kSrcFlag)) continue;
+      } else {
+        c = __ldcg(qc + idx);
       }
-      __syncthreads();
-      const int m = sCount < kLvCap ? sCount : kLvCap;
-      if (threadIdx.x == 0) sBase = m ? atomicAdd(cntn, m) : 0;
-      __syncthreads();
-      for (int i = threadIdx.x; i < m; i += blockDim.x) qn[sBase + i] = sBuf[i];
-    } else {
-      auto push = [&](int r) {
-        cg::coalesced_group g = cg::coalesced_threads();
-        int base = 0;
-        if (g.thread_rank() == 0) base = atomicAdd(cntn, (int)g.size());
-        base = g.shfl(base, 0);
-        qn[base + g.thread_rank()] = r;
-      };
-      for (int idx = gtid; idx < n; idx += gsize) {
-        int c;
-        if (level == 0 && !(BAND && seeded)) {
-          c = idx;
-          if (!(a.st[c] & kSrcFlag)) continue;
-        } else {
-          c = __ldcg(qc + idx);
-        }
-        levels_follow<MODE, BAND>(a, c, budget, push);
-      }
+      levels_follow<MODE, BAND>(a, c, budget, push);
     }
     grid.sync();
   }
   if (gtid == 0) *levels_out = level;
 }
 
-// =================================================================================================
-// Asynchronous multi-receiver accumulation (accum_async = 1; prepared for round 2, off by default).
-// No levels and no grid barriers: persistent warps keep all 32 lanes on a ready cell.  A lane pushes
-// its cell's flow downstream and appends the receivers it completes to its warp's FIFO in shared
-// memory; lanes without a cell take from that FIFO, then from the scan of
-// source cells (1024-cell chunks off a global cursor), then from a global ring that warps spill to
-// when their FIFO runs full or when the ring is empty and they hold more than a warp's worth.
-// Termination: a warp that finds no work anywhere counts itself idle; work is only ever created by
-// busy warps, so "every warp idle" is final.  (Cells on a cycle of a user-supplied proportions grid
-// are never ready, exactly as in the level kernel and in the reference's queue.)
-// =================================================================================================
-#ifndef RDB_AS_RING
-#define RDB_AS_RING 256
-#endif
-constexpr int kAsRing = RDB_AS_RING;  // per-warp FIFO of ready cells (shared memory); a power of two >= 128
-static_assert(kAsRing >= 128 && (kAsRing & (kAsRing - 1)) == 0, "ring size");
-struct AccAsyncDev {
-  unsigned int qhead, qtail;  // global ring of spilled ready cells (never wraps: a cell is ready once)
-  int cursor;                 // next chunk of the source scan
-  int idle;                   // warps that found no work anywhere
-  int abort_flag;
-  unsigned long long spilled, steps;
-};
-
-template <int MODE>
-__global__ void __launch_bounds__(256) accum_async_kernel(const WalkArgs<double> a, int ncells, int *gq, AccAsyncDev *dev,
-                                                           long long spin_limit) {
-  // Ready cells wait in FIFO order: a cell on the critical path of the flow graph must not sit under
-  // newer ones (a stack here tripled the number of steps the longest chain took on the CPU model).
-  __shared__ int sRing[8][kAsRing];
-  __shared__ int sHead[8], sTail[8];  // monotonic; count = tail - head
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const unsigned lt = (1u << lane) - 1u;
-  int *ring = sRing[wrp];
-  int *headp = &sHead[wrp], *tailp = &sTail[wrp];
-  const int nwarps = (int)gridDim.x * 8;
-  if (lane == 0) {
-    *headp = 0;
-    *tailp = 0;
-  }
-  __syncwarp();
-  bool have = false;
-  int c = -1;
-  int pos = 0, end = 0;  // warp-uniform: source-scan window
-  bool more = true;      // the cursor may still hold chunks
-  bool counted_idle = false;
-  long long spins = 0;
-  unsigned long long steps = 0;
-  int iter = 0;
-
-  auto global_push = [&](int r) {
-    const unsigned int p = atomicAdd(&dev->qtail, 1u);
-    __threadfence();
-    *reinterpret_cast<volatile int *>(&gq[p]) = r + 1;
-  };
-  auto push = [&](int r) {  // a receiver this lane completed
-    const int p = atomicAdd(tailp, 1);
-    if (p - *reinterpret_cast<volatile int *>(headp) < kAsRing) {
-      ring[p & (kAsRing - 1)] = r;
-    } else {
-      atomicSub(tailp, 1);  // full (any later ticket fails as well, so the surviving ones stay contiguous)
-      global_push(r);
-    }
-  };
-
-  for (;; iter++) {
-    // ---- (1) lanes without a cell take the oldest entries of the warp's FIFO ----
-    unsigned idle = __ballot_sync(full, !have);
-    int head = *reinterpret_cast<volatile int *>(headp);
-    int cnt = *reinterpret_cast<volatile int *>(tailp) - head;
-    if (idle && cnt > 0) {
-      const int nidle = __popc(idle);
-      const int take = nidle < cnt ? nidle : cnt;
-      const int rank = __popc(idle & lt);
-      if (!have && rank < take) {
-        c = ring[(head + rank) & (kAsRing - 1)];
-        have = true;
-      }
-      __syncwarp();
-      if (lane == 0) *headp = head + take;
-      __syncwarp();
-      head += take;
-      cnt -= take;
-      idle = __ballot_sync(full, !have);
-    }
-    // ---- (2) idle lanes left: scan for sources, else pull from the global ring, else rest ----
-    if (idle) {
-      if (cnt <= kAsRing - 32 && (pos < end || more)) {
-        if (pos >= end) {
-          int b = 0;
-          if (lane == 0) b = atomicAdd(&dev->cursor, kLaneChunk);
-          b = __shfl_sync(full, b, 0);
-          if (b >= ncells) {
-            more = false;
-          } else {
-            pos = b;
-            end = b + kLaneChunk < ncells ? b + kLaneChunk : ncells;
-          }
-        }
-        if (pos < end) {
-          const int i = pos + lane;
-          const bool src = i < end && (a.st[i] & kSrcFlag) != 0;
-          const unsigned bal = __ballot_sync(full, src);
-          if (src) ring[(head + cnt + __popc(bal & lt)) & (kAsRing - 1)] = i;
-          __syncwarp();
-          if (lane == 0) *tailp = head + cnt + __popc(bal);
-          __syncwarp();
-          pos += 32;
-        }
-        continue;  // hand the new entries out in (1)
-      }
-      if (!more && pos >= end) {
-        unsigned int h = 0, t = 0;
-        if (lane == 0) {
-          h = *reinterpret_cast<volatile unsigned int *>(&dev->qhead);
-          t = *reinterpret_cast<volatile unsigned int *>(&dev->qtail);
-        }
-        h = __shfl_sync(full, h, 0);
-        t = __shfl_sync(full, t, 0);
-        const int avail = (int)(t - h);
-        if (avail > 0) {
-          if (counted_idle) {  // about to take work: no longer idle
-            if (lane == 0) atomicSub(&dev->idle, 1);
-            counted_idle = false;
-          }
-          const int nidle = __popc(idle);
-          const int want = avail < nidle ? avail : nidle;
-          int got = 0;
-          if (lane == 0) got = atomicCAS(&dev->qhead, h, h + (unsigned)want) == h ? 1 : 0;
-          got = __shfl_sync(full, got, 0);
-          if (got) {
-            const int rank = __popc(idle & lt);
-            if (!have && rank < want) {
-              volatile int *slot = &gq[h + (unsigned)rank];
-              int v;
-              long long w = 0;
-              while ((v = *slot) == 0) {  // the pusher has its ticket but has not written yet
-                __nanosleep(100);
-                if (++w > spin_limit) break;
-              }
-              if (v == 0) {
-                atomicExch(&dev->abort_flag, 1);
-              } else {
-                c = v - 1;
-                have = true;
-              }
-            }
-          }
-          continue;
-        }
-        if (idle == full && cnt == 0) {  // nothing anywhere for this warp
-          int fin = 0;
-          if (lane == 0) {
-            if (!counted_idle) atomicAdd(&dev->idle, 1);
-            fin = *reinterpret_cast<volatile int *>(&dev->idle) >= nwarps || *reinterpret_cast<volatile int *>(&dev->abort_flag);
-          }
-          counted_idle = true;
-          if (__shfl_sync(full, fin, 0)) break;
-          __nanosleep(spins < 4 ? 200u << spins : 3000u);
-          if (++spins > spin_limit) {
-            if (lane == 0) atomicExch(&dev->abort_flag, 1);
-            break;
-          }
-          continue;
-        }
-      }
-    }
-    spins = 0;
-    // ---- (3) one step for every lane that holds a ready cell: its flow goes downstream and every receiver
-    //      it completes joins the FIFO (the same per-cell code as the level kernel, with a budget of one) ----
-    if (have) {
-      levels_follow<MODE, false>(a, c, 1, push);
-      steps++;
-      have = false;
-    }
-    __syncwarp();
-    // ---- (4) share: a FIFO close to full always hands a warp's worth (its oldest entries) to the global
-    //      ring; every 16 steps also when that ring is empty and this warp holds more than it can use ----
-    {
-      const int head2 = *reinterpret_cast<volatile int *>(headp);
-      const int cnt2 = *reinterpret_cast<volatile int *>(tailp) - head2;
-      int spill = cnt2 > kAsRing - 72 ? 1 : 0;  // a step can add up to 32 * 7 entries; the overflow path covers the rest
-      if (!spill && (iter & 15) == 15 && cnt2 > 64) {
-        int empty = 0;
-        if (lane == 0)
-          empty = *reinterpret_cast<volatile unsigned int *>(&dev->qhead) == *reinterpret_cast<volatile unsigned int *>(&dev->qtail);
-        spill = __shfl_sync(full, empty, 0);
-      }
-      if (spill) {
-        const int r = ring[(head2 + lane) & (kAsRing - 1)];  // cnt2 > 32 in both cases
-        __syncwarp();
-        if (lane == 0) *headp = head2 + 32;
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(&dev->qtail, 32u);
-        base = __shfl_sync(full, base, 0);
-        __threadfence();
-        *reinterpret_cast<volatile int *>(&gq[base + (unsigned)lane]) = r + 1;
-        if (lane == 0) atomicAdd(&dev->spilled, 32ull);
-        __syncwarp();
-      }
-    }
-  }
-  if (lane == 0 && steps) atomicAdd(&dev->steps, steps);
-}
-
-template <int MODE>
-void run_accum_async(WalkArgs<double> a, size_t ncells) {
-  Ctx &c = ctx();
-  DevBuf<int> gq(ncells);
-  DevBuf<AccAsyncDev> dev(1);
-  RDB_CK(cudaMemsetAsync(gq.p, 0, ncells * sizeof(int), c.stream));
-  RDB_CK(cudaMemsetAsync(dev.p, 0, sizeof(AccAsyncDev), c.stream));
-  int per_sm = 0;
-  RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_async_kernel<MODE>, 256, 0));
-  if (per_sm < 1) per_sm = 1;
-  long long blocks = (long long)c.num_sms * per_sm;
-  const long long need = ((long long)ncells + kLaneChunk - 1) / kLaneChunk;
-  if (blocks * 8 > need) blocks = (need + 7) / 8;
-  int nc = (int)ncells;
-  int *q = gq.p;
-  AccAsyncDev *d = dev.p;
-  long long spin = 2000000;
-  void *args[] = {(void *)&a, (void *)&nc, (void *)&q, (void *)&d, (void *)&spin};
-  KernelTimer kt;
-  RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_async_kernel<MODE>, dim3((unsigned)blocks), dim3(256), args, 0, c.stream));
-  count_launch();
-  kt.stop_async();
-  AccAsyncDev *h = (AccAsyncDev *)c.pinned;
-  RDB_CK(cudaMemcpyAsync(h, dev.p, sizeof(AccAsyncDev), cudaMemcpyDeviceToHost, c.stream));
-  RDB_CK(cudaStreamSynchronize(c.stream));
-  c.stats.ms_main_kernel += kt.ms();
-  if (h->abort_flag) fail("accumulation (async engine): watchdog expired (qhead=%u qtail=%u idle=%d)", h->qhead, h->qtail, h->idle);
-  c.stats.accum_rounds = 1;
-}
-
 template <int MODE>
 void run_levels(WalkArgs<double> a, size_t ncells) {
   Ctx &c = ctx();
-  if (c.params.accum_async) {
-    run_accum_async<MODE>(a, ncells);
-    return;
-  }
   DevBuf<int> fr0(ncells), fr1(ncells), cnt(4);
   RDB_CK(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(int), c.stream));
   int per_sm = 0;
@@ -840,10 +539,7 @@ void run_levels(WalkArgs<double> a, size_t ncells) {
   int *q0 = fr0.p, *q1 = fr1.p, *counts = cnt.p, *lv = cnt.p + 3;
   int nc = (int)ncells, budget = (int)(c.params.accum_budget > 0 ? c.params.accum_budget : 4);
   int seeded = 0;
-  int tail_n = (int)c.params.accum_tail, tail_budget = (int)(c.params.accum_tail_budget > 0 ? c.params.accum_tail_budget : 32);
-  int agg = (int)c.params.accum_agg;
-  void *args[] = {(void *)&a,      (void *)&q0, (void *)&q1,     (void *)&counts, (void *)&nc,          (void *)&budget,
-                  (void *)&lv,     (void *)&seeded, (void *)&tail_n, (void *)&tail_budget, (void *)&agg};
+  void *args[] = {(void *)&a, (void *)&q0, (void *)&q1, (void *)&counts, (void *)&nc, (void *)&budget, (void *)&lv, (void *)&seeded};
   KernelTimer kt;
   RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_levels_kernel<MODE>, dim3(grid), dim3(256), args, 0, c.stream));
   count_launch();
@@ -1651,11 +1347,8 @@ struct FaccState {
       int *q0 = fr0.p, *q1 = fr1.p, *counts = lc.p, *lv = lc.p + 3;
       int seeded = a.frontier ? 1 : 0;
       int nc = a.nfrontier, budget = (int)(c.params.accum_budget > 0 ? c.params.accum_budget : 4);
-      int tail_n = (int)c.params.accum_tail, tail_budget = (int)(c.params.accum_tail_budget > 0 ? c.params.accum_tail_budget : 32);
       if (nc > 0) {
-        int agg = (int)c.params.accum_agg;
-        void *args[] = {(void *)&a,  (void *)&q0,     (void *)&q1,     (void *)&counts,      (void *)&nc, (void *)&budget,
-                        (void *)&lv, (void *)&seeded, (void *)&tail_n, (void *)&tail_budget, (void *)&agg};
+        void *args[] = {(void *)&a, (void *)&q0, (void *)&q1, (void *)&counts, (void *)&nc, (void *)&budget, (void *)&lv, (void *)&seeded};
         RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_levels_kernel<1, true>, dim3(grid), dim3(256), args, 0,
                                            c.stream));
         count_launch();

@@ -192,7 +192,9 @@ void rdb200_shutdown(void) {
   cudaEventDestroy(c.evk0);
   cudaEventDestroy(c.evk1);
   cudaStreamDestroy(c.own_stream);
+  const Params keep = c.params;  // rdb200_set_param switches are process settings: they survive a re-init
   c = Ctx();
+  c.params = keep;
 }
 
 const char *rdb200_last_error(void) { return g_last_error.c_str(); }
@@ -219,7 +221,8 @@ int rdb200_set_param(const char *name, int64_t value) {
   if (!name) fail("rdb200_set_param: null name");
   Params &p = ctx().params;
   const std::string n(name);
-  if (n == "fill_max_iters") p.fill_max_iters = value;
+  if (n == "reset_defaults") p = Params();
+  else if (n == "fill_max_iters") p.fill_max_iters = value;
   else if (n == "fill_rounds_per_sync") p.fill_rounds_per_sync = value > 0 ? value : 16;
   else if (n == "fill_use_tma") p.fill_use_tma = value;
   else if (n == "fill_profile") p.fill_profile = value;
@@ -228,19 +231,12 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "fill_band_rounds") p.fill_band_rounds = value;
   else if (n == "accum_threads") p.accum_threads = value > 0 ? value : 256;
   else if (n == "accum_budget") p.accum_budget = value;
-  else if (n == "accum_tail") p.accum_tail = value > 0 ? value : 0;
-  else if (n == "accum_tail_budget") p.accum_tail_budget = value;
-  else if (n == "accum_agg") p.accum_agg = value;
   else if (n == "accum_walk_lanes") p.accum_walk_lanes = value;
   else if (n == "accum_fused_prep") p.accum_fused_prep = value;
-  else if (n == "accum_async") p.accum_async = value;
   else if (n == "flats_tiled") p.flats_tiled = value;
-  else if (n == "fill_async") p.fill_async = value;
   else if (n == "fill_multigrid") p.fill_multigrid = value;
   else if (n == "fill_multigrid_min") p.fill_multigrid_min = value;
   else if (n == "fill_vcycle") p.fill_vcycle = value;
-  else if (n == "fill_async_spin") p.fill_async_spin = value;
-  else if (n == "fill_async_thick") p.fill_async_thick = value;
   else if (n == "flats_uf_tiled") p.flats_uf_tiled = value;
   else if (n == "flowdirs_rolling") p.flowdirs_rolling = value;
   else if (n == "accum_packed") p.accum_packed = value;
@@ -325,7 +321,19 @@ int rdb200_d8_flow_accum_u8_i32(const uint8_t *dirs, int32_t *area, int32_t w, i
   CAPI_END
 }
 
-static int fm_host(const float *dem, float *props, int32_t w, int32_t h, float nodata, bool dinf) {
+// method: 0 FM_D8, 1 FM_Tarboton, 2 FM_D4, 3 FM_Holmgren (FM_Quinn = exponent 1), 4 FM_Freeman
+static void fm_dispatch_dev(int method, const float *d_dem, float *d_props, int w, int h, float nodata, double xparam) {
+  switch (method) {
+    case 0: fm_d8_dev(d_dem, d_props, w, h, nodata); break;
+    case 1: fm_tarboton_dev(d_dem, d_props, w, h, nodata); break;
+    case 2: fm_d4_dev(d_dem, d_props, w, h, nodata); break;
+    case 3: fm_holmgren_dev(d_dem, d_props, w, h, nodata, xparam); break;
+    case 4: fm_freeman_dev(d_dem, d_props, w, h, nodata, xparam); break;
+    default: fail("unknown flow metric %d", method);
+  }
+}
+
+static int fm_host(const float *dem, float *props, int32_t w, int32_t h, float nodata, int method, double xparam = 0) {
   CAPI_TRY
   if (!dem || !props) fail("flow metric: null pointer");
   check_dims(w, h);
@@ -333,17 +341,63 @@ static int fm_host(const float *dem, float *props, int32_t w, int32_t h, float n
   const size_t n = (size_t)w * h;
   DevBuf<float> d(n), p(9 * n);
   h2d(d.p, dem, n);
-  if (dinf) fm_tarboton_dev(d.p, p.p, w, h, nodata);
-  else fm_d8_dev(d.p, p.p, w, h, nodata);
+  fm_dispatch_dev(method, d.p, p.p, w, h, nodata, xparam);
   d2h(props, p.p, 9 * n);
   cs.done();
   CAPI_END
 }
 int rdb200_fm_d8_f32(const float *dem, float *props, int32_t w, int32_t h, float nodata) {
-  return fm_host(dem, props, w, h, nodata, false);
+  return fm_host(dem, props, w, h, nodata, 0);
 }
 int rdb200_fm_tarboton_f32(const float *dem, float *props, int32_t w, int32_t h, float nodata) {
-  return fm_host(dem, props, w, h, nodata, true);
+  return fm_host(dem, props, w, h, nodata, 1);
+}
+int rdb200_fm_d4_f32(const float *dem, float *props, int32_t w, int32_t h, float nodata) {
+  return fm_host(dem, props, w, h, nodata, 2);
+}
+int rdb200_fm_quinn_f32(const float *dem, float *props, int32_t w, int32_t h, float nodata) {
+  return fm_host(dem, props, w, h, nodata, 3, 1.0);
+}
+int rdb200_fm_holmgren_f32(const float *dem, float *props, int32_t w, int32_t h, float nodata, double xparam) {
+  return fm_host(dem, props, w, h, nodata, 3, xparam);
+}
+int rdb200_fm_freeman_f32(const float *dem, float *props, int32_t w, int32_t h, float nodata, double xparam) {
+  return fm_host(dem, props, w, h, nodata, 4, xparam);
+}
+
+// FA_<metric> = FM_<metric> into a device-side proportions array + the generic accumulation
+// (reference methods/flow_accumulation.hpp:18-20,28: `Array3D<float> props(elevations); FM_x(...); FlowAccumulation(...)`)
+static void fa_via_props_dev(int method, const float *d_dem, double *d_accum, int w, int h, float nodata, double xparam) {
+  DevBuf<float> p(9 * (size_t)w * h);
+  fm_dispatch_dev(method, d_dem, p.p, w, h, nodata, xparam);
+  flow_accumulation_props_dev(p.p, d_accum, w, h);
+}
+static int fa_via_props_host(int method, const float *dem, double *accum, int32_t w, int32_t h, float nodata, double xparam) {
+  CAPI_TRY
+  if (!dem || !accum) fail("flow accumulation: null pointer");
+  check_dims(w, h);
+  CallScope cs((int64_t)w * h);
+  const size_t n = (size_t)w * h;
+  DevBuf<float> d(n);
+  DevBuf<double> a(n);
+  h2d(d.p, dem, n);
+  h2d(a.p, accum, n);
+  fa_via_props_dev(method, d.p, a.p, w, h, nodata, xparam);
+  d2h(accum, a.p, n);
+  cs.done();
+  CAPI_END
+}
+int rdb200_fa_d4_f32_f64(const float *dem, double *accum, int32_t w, int32_t h, float nodata) {
+  return fa_via_props_host(2, dem, accum, w, h, nodata, 0);
+}
+int rdb200_fa_quinn_f32_f64(const float *dem, double *accum, int32_t w, int32_t h, float nodata) {
+  return fa_via_props_host(3, dem, accum, w, h, nodata, 1.0);
+}
+int rdb200_fa_holmgren_f32_f64(const float *dem, double *accum, int32_t w, int32_t h, float nodata, double xparam) {
+  return fa_via_props_host(3, dem, accum, w, h, nodata, xparam);
+}
+int rdb200_fa_freeman_f32_f64(const float *dem, double *accum, int32_t w, int32_t h, float nodata, double xparam) {
+  return fa_via_props_host(4, dem, accum, w, h, nodata, xparam);
 }
 
 int rdb200_flow_accumulation_props_f64(const float *props, double *accum, int32_t w, int32_t h) {
@@ -412,6 +466,14 @@ int rdb200_dev_fm_d8_f32(const float *d_dem, float *d_props, int32_t w, int32_t 
 }
 int rdb200_dev_fm_tarboton_f32(const float *d_dem, float *d_props, int32_t w, int32_t h, float nodata) {
   DEV_ENTRY((int64_t)w * h, (check_dims(w, h), fm_tarboton_dev(d_dem, d_props, w, h, nodata)))
+}
+int rdb200_dev_fm_method_f32(int32_t method, const float *d_dem, float *d_props, int32_t w, int32_t h, float nodata,
+                             double xparam) {
+  DEV_ENTRY((int64_t)w * h, (check_dims(w, h), fm_dispatch_dev(method, d_dem, d_props, w, h, nodata, xparam)))
+}
+int rdb200_dev_fa_method_f32_f64(int32_t method, const float *d_dem, double *d_accum, int32_t w, int32_t h, float nodata,
+                                 double xparam) {
+  DEV_ENTRY((int64_t)w * h, (check_dims(w, h), fa_via_props_dev(method, d_dem, d_accum, w, h, nodata, xparam)))
 }
 int rdb200_dev_flow_accumulation_props_f64(const float *d_props, double *d_accum, int32_t w, int32_t h) {
   DEV_ENTRY((int64_t)w * h, (check_dims(w, h), flow_accumulation_props_dev(d_props, d_accum, w, h)))

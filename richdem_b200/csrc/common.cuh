@@ -61,24 +61,17 @@ struct Params {
   int64_t fill_order_rounds = 0;  // rounds the level schedule spans (0: 0.8 x tiles across the raster)
   int64_t fill_band_rounds = 0;   // row-band mode: rounds per rdb200_dev_fill_run call (0: to convergence)
   int64_t fill_profile = 0;     // 1: collect + print in-tile work counters (slower)
-  int64_t fill_multigrid = 0;      // k >= 2: start the flood from the lifted fill of the k x k max-pooled raster (recursive)
-  int64_t fill_vcycle = 0;         // with fill_multigrid: coarse-grid correction after every that many fine rounds (0: none)
+  int64_t fill_multigrid = 8;      // k >= 2: start the flood from the lifted fill of the k x k max-pooled raster (recursive)
+  int64_t fill_vcycle = 8;         // with fill_multigrid: coarse-grid correction after every that many fine rounds (0: none)
   int64_t fill_multigrid_min = 0;  // smallest raster side that still gets a coarse level (0: 1024)
-  int64_t fill_async = 0;        // whole-raster fill by one cooperative launch draining per-level tile queues (no rounds)
-  int64_t fill_async_thick = 0;  // queue entries from which a bucket is claimed by fetch-add tickets instead of CAS (0: 256)
-  int64_t fill_async_spin = 0;   // spin budget of an idle CTA before the watchdog aborts the launch (0: 4e6)
-  int64_t flowdirs_rolling = 0;  // d8_flow_directions with a rolling three-row register window (W % 4 == 0)
-  int64_t flats_uf_tiled = 0;  // union-find: unite inside 64x16 tiles in shared memory first, then across tile seams
+  int64_t flowdirs_rolling = 1;  // d8_flow_directions with a rolling three-row register window (W % 4 == 0)
+  int64_t flats_uf_tiled = 1;  // union-find: unite inside 64x16 tiles in shared memory first, then across tile seams
   int64_t flats_tiled = 1;   // flat-resolution gradients by the tile engine (0: one cooperative BFS launch each)
   int64_t accum_packed = 1;  // unit-weight D8: accumulator and donor count share one 64-bit word
-  int64_t accum_async = 0;        // multi-receiver accumulation without levels: persistent warps, per-warp stacks, a spill ring
-  int64_t accum_fused_prep = 0;   // unit-weight D8: flow codes + donor counts + sole-donor bits in one rolling-window pass
-  int64_t accum_walk_lanes = 0;   // unit-weight D8 walk: persistent always-busy lanes fed from per-warp source queues
+  int64_t accum_fused_prep = 1;   // unit-weight D8: flow codes + donor counts + sole-donor bits in one rolling-window pass
+  int64_t accum_walk_lanes = 1;   // unit-weight D8 walk: persistent always-busy lanes fed from per-warp source queues
   int64_t accum_threads = 256;
   int64_t accum_budget = 0;  // cells one thread follows per level in the multi-receiver accumulation (0: 4)
-  int64_t accum_tail = 0;         // multi-receiver accumulation: frontiers up to this size are drained by one block (0: off)
-  int64_t accum_agg = 0;          // multi-receiver accumulation: block-aggregated frontier appends (0: per converged group)
-  int64_t accum_tail_budget = 0;  // walking budget per level in that tail mode (0: 32)
 };
 
 struct WsBlock {
@@ -161,6 +154,9 @@ void d8_flow_directions_dev(const float *d_dem, uint8_t *d_dirs, int w, int h, f
 void d8_flow_accum_dev(const uint8_t *d_dirs, int32_t *d_area, int w, int h);
 void fm_d8_dev(const float *d_dem, float *d_props, int w, int h, float nodata);
 void fm_tarboton_dev(const float *d_dem, float *d_props, int w, int h, float nodata);
+void fm_d4_dev(const float *d_dem, float *d_props, int w, int h, float nodata);
+void fm_holmgren_dev(const float *d_dem, float *d_props, int w, int h, float nodata, double xparam);
+void fm_freeman_dev(const float *d_dem, float *d_props, int w, int h, float nodata, double xparam);
 void flow_accumulation_props_dev(const float *d_props, double *d_accum, int w, int h);
 void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodata, bool ones,
                   bool dinf);

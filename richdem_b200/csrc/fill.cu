@@ -326,319 +326,6 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
   }
 }
 
-// =================================================================================================
-// Asynchronous variant of the sweep (fill_async = 1; prepared for round 2, off by default).
-//
-// The round engine above is as slow as the slowest tile of every round, pays two launches per round
-// and leaves the last wave of CTAs partly idle.  Here ONE cooperative launch of persistent CTAs
-// drains per-level tile queues with no round barrier:
-//   * every tile has a state IDLE / QUEUED / BUSY / BUSY_DIRTY.  Activating a neighbour ORs the
-//     changed apron sides into its mask, then moves IDLE -> QUEUED (and pushes it) or BUSY ->
-//     BUSY_DIRTY; a CTA that finishes a BUSY_DIRTY tile queues it again, so a tile is never relaxed
-//     by two CTAs at once and no activation is lost (the data written before an activation is
-//     fenced before the state change; the relaxing CTA takes the side mask after it set BUSY);
-//   * AQ_BUCKETS ring queues, one per quantile band of the incoming water level (the same sampled
-//     histogram as the level schedule); a CTA always takes from the lowest non-empty bucket, so the
-//     flood still rises roughly in level order but no CTA ever waits for a round to end;
-//   * `pending` counts tiles that are QUEUED or BUSY; CTAs leave when it reaches zero.  A spin
-//     budget turns a protocol bug into an error instead of a hang.
-// The in-tile relaxation is the same code as in fill_sweep_kernel<0>.
-// =================================================================================================
-#ifndef RDB_AQ_BUCKETS
-#define RDB_AQ_BUCKETS 32
-#endif
-constexpr int AQ_BUCKETS = RDB_AQ_BUCKETS;  // <= 32: lane b of the popping warp watches bucket b
-enum : int { TS_IDLE = 0, TS_QUEUED = 1, TS_BUSY = 2, TS_BUSY_DIRTY = 3 };
-
-struct AsyncDev {
-  unsigned int head[AQ_BUCKETS];
-  unsigned int tail[AQ_BUCKETS];
-  float thr[AQ_BUCKETS];  // bucket b takes levels <= thr[b]; the last one is +inf
-  int pending;            // tiles QUEUED or BUSY
-  int abort_flag;         // set by the spin watchdog
-  int edge_changed;       // bit0: raster row 1 changed, bit1: raster row H-2 changed (row-band protocol)
-  unsigned long long visits, iters, requeues, pop_retries;
-};
-
-struct AsyncArgs {
-  const float *Zp;
-  float *Wp;
-  int pitch;
-  int W, H;
-  int tilesX, tilesY;
-  int *state;
-  int *sides;
-  int *keys;
-  int *queue;  // [AQ_BUCKETS][cap]; a slot holds tile + 1, or 0 while empty
-  int cap;     // power of two > number of tiles
-  AsyncDev *dev;
-  int max_iters;
-  int use_tma;
-  int profile;
-  long long spin_limit;
-  int thick;  // entries from which a bucket is claimed by fetch-add tickets
-  unsigned long long visit_stop;  // CTAs stop taking tiles once dev->visits reaches this (leaving the queues as they are)
-};
-
-__device__ __forceinline__ void aq_sleep(unsigned ns = 100) { __nanosleep(ns); }
-// order generic-proxy accesses (other CTAs' stores, made visible by their fences) before this thread's
-// async-proxy (TMA) reads of global memory
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-__device__ __forceinline__ int aq_bucket(const AsyncDev *dev, int key_ord) {
-  const float k = ord2f(key_ord);
-  int b = 0;
-  while (b < AQ_BUCKETS - 1 && k > dev->thr[b]) b++;
-  return b;
-}
-
-// Queue protocol.  A ring slot holds 0 (empty), tile + 1, or -1 (a consumer gave its ticket back).
-// Consumers claim from a well-filled bucket with an unconditional fetch-add on `head` -- a
-// compare-and-swap there succeeds about once per memory round trip however many CTAs try, far
-// below the ~30 pops/us a B200 needs -- so `head` can briefly run ahead of `tail`; a consumer whose
-// slot stays empty for long hands the ticket back by writing -1, and the pusher that later lands
-// on such a slot clears it and draws the next ticket.  Thin buckets are claimed by compare-and-swap.
-__device__ __forceinline__ void aq_push(const AsyncArgs &a, int t, int b) {
-  __threadfence();  // state / sides / keys / tile data are visible before the entry is
-  for (;;) {
-    const unsigned int p = atomicAdd(&a.dev->tail[b], 1u);
-    int *slot = &a.queue[(size_t)b * a.cap + (p & (unsigned)(a.cap - 1))];
-    const int old = atomicCAS(slot, 0, t + 1);
-    if (old == 0) return;
-    // old == -1: that ticket was handed back; recycle the slot and take the next one
-    atomicExch(slot, 0);
-  }
-}
-
-// tell tile `nb` that the apron sides `bits` changed (lowest new level `key_ord`)
-__device__ __forceinline__ void aq_activate(const AsyncArgs &a, int nb, int bits, int key_ord) {
-  atomicOr(&a.sides[nb], bits);
-  atomicMin(&a.keys[nb], key_ord);
-  __threadfence();
-  for (;;) {
-    const int s = atomicCAS(&a.state[nb], TS_IDLE, TS_QUEUED);
-    if (s == TS_IDLE) {
-      atomicAdd(&a.dev->pending, 1);
-      aq_push(a, nb, aq_bucket(a.dev, key_ord));
-      return;
-    }
-    if (s == TS_QUEUED || s == TS_BUSY_DIRTY) return;  // it will (re)read its apron anyway
-    if (atomicCAS(&a.state[nb], TS_BUSY, TS_BUSY_DIRTY) == TS_BUSY) return;
-    // the state moved between the two CAS: look again
-  }
-}
-
-template <int STEP>
-__global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
-    fill_async_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ,
-                      const AsyncArgs a) {
-  __shared__ __align__(128) float sW[SROWS * SP];
-  __shared__ __align__(128) float sZ[TY * TX];
-  __shared__ __align__(8) unsigned long long mbar;
-  __shared__ unsigned char sMark[MKP * (BYN + 2)];
-  __shared__ unsigned char sList[2][NWARP][SEG];
-  __shared__ __align__(16) int sCnt[2][NWARP];
-  __shared__ int sTile;
-  __shared__ int sSides;
-  __shared__ int sFlags;
-  __shared__ int sKey;
-  __shared__ int sProf[2];
-
-  const int tid = threadIdx.x;
-  const unsigned full = 0xffffffffu;
-  AsyncDev *dev = a.dev;
-  if (tid == 0) {
-    mbar_init(&mbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  uint32_t phase = 0;
-  const int max_iters = a.max_iters;
-
-  for (;;) {
-    // ---- take a tile from the lowest non-empty bucket (warp 0; lane b watches bucket b) ----
-    if (tid < 32) {
-      int t = -1;
-      long long spins = 0;
-      for (;;) {
-        {  // a bounded burst (V-cycles): stop taking tiles once the visit budget is spent; queued tiles stay queued
-          int over = 0;
-          if (tid == 0) over = *reinterpret_cast<volatile unsigned long long *>(&dev->visits) >= a.visit_stop;
-          if (__shfl_sync(full, over, 0)) break;
-        }
-        unsigned int h = 0, tl = 0;
-        if (tid < AQ_BUCKETS) {
-          h = *reinterpret_cast<volatile unsigned int *>(&dev->head[tid]);
-          tl = *reinterpret_cast<volatile unsigned int *>(&dev->tail[tid]);
-        }
-        const unsigned ne = __ballot_sync(full, (int)(tl - h) > 0);
-        if (ne) {
-          // Lowest level first.  A bucket holding plenty (>= a.thick entries: more than the CTAs that can
-          // race for them in one memory round trip) is claimed with an unconditional fetch-add ticket;
-          // a thin one with a single compare-and-swap, and whoever loses that moves on to the next bucket
-          // instead of retrying, so a crowd of idle CTAs neither serialises on one counter nor draws
-          // tickets for entries that do not exist.
-          int res = -1;
-          unsigned todo = ne;
-          while (todo && res < 0) {
-            const int b = __ffs((int)todo) - 1;
-            todo &= todo - 1;
-            const unsigned int hb = __shfl_sync(full, h, b);
-            const unsigned int tb = __shfl_sync(full, tl, b);
-            if (tid == 0) {
-              int *slot = nullptr;
-              if ((int)(tb - hb) >= a.thick) {
-                const unsigned int tk = atomicAdd(&dev->head[b], 1u);
-                slot = &a.queue[(size_t)b * a.cap + (tk & (unsigned)(a.cap - 1))];
-              } else if (atomicCAS(&dev->head[b], hb, hb + 1u) == hb) {
-                slot = &a.queue[(size_t)b * a.cap + (hb & (unsigned)(a.cap - 1))];
-              } else if (a.profile) {
-                atomicAdd(&dev->pop_retries, 1ull);
-              }
-              if (slot) {
-                int v = 0;
-                for (long long w = 0; w < a.spin_limit; w++) {  // the pusher has its ticket but may not have written yet
-                  v = *reinterpret_cast<volatile int *>(slot);
-                  if (v > 0) break;
-                  aq_sleep();
-                  if (w >= 512 && (w & 63) == 0) {  // a ticket beyond the tail (over-claimed): hand it back
-                    const int old = atomicCAS(slot, 0, -1);
-                    if (old == 0) break;
-                    v = old;
-                    break;
-                  }
-                }
-                if (v > 0) {
-                  atomicExch(slot, 0);
-                  res = v - 1;
-                  // QUEUED -> BUSY, then take what arrived for this tile (activations after this point find
-                  // BUSY and mark the tile dirty)
-                  atomicExch(&a.state[res], TS_BUSY);
-                  __threadfence();
-                  sSides = atomicExch(&a.sides[res], 0);
-                  atomicExch(&a.keys[res], ORD_POS_INF);
-                }
-              }
-            }
-            res = __shfl_sync(full, res, 0);
-          }
-          if (res >= 0) {
-            t = res;
-            break;
-          }
-          continue;
-        }
-        int stop = 0;  // read once per warp so that all lanes take the same branch
-        if (tid == 0)
-          stop = *reinterpret_cast<volatile int *>(&dev->pending) <= 0 || *reinterpret_cast<volatile int *>(&dev->abort_flag);
-        if (__shfl_sync(full, stop, 0)) break;
-        aq_sleep(spins < 4 ? 100u << spins : 2000u);  // back off: idle CTAs must not hammer the queue counters
-        if (++spins > a.spin_limit) {
-          if (tid == 0) atomicExch(&dev->abort_flag, 1);
-          break;
-        }
-      }
-      if (tid == 0) sTile = t;
-    }
-    for (int k = tid; k < MKP * (BYN + 2); k += FILL_THREADS) sMark[k] = 0;
-    __syncthreads();  // publishes sTile / sSides; all warps are done with smem of the previous tile
-    const int t = sTile;
-    if (t < 0) break;
-    const int tyT = t / a.tilesX, txT = t - tyT * a.tilesX;
-    const int x0 = txT * TX, y0 = tyT * TY;
-
-    // ---- stage W (+apron) and Z ----
-    if (tid == 0) {
-      sFlags = 0;
-      sKey = ORD_POS_INF;
-      sProf[0] = sProf[1] = 0;
-    }
-    if (a.use_tma) {
-      if (tid == 0) {
-        fence_proxy_async_all();
-        mbar_arrive_expect_tx(&mbar, W_TILE_BYTES + Z_TILE_BYTES);
-        tma_load_2d(sW, &mapW, x0, y0, &mbar);
-        tma_load_2d(sZ, &mapZ, x0 + PADL, y0 + 1, &mbar);
-      }
-    } else {
-      for (int k = tid; k < SROWS * (SP / 4); k += FILL_THREADS) {
-        const int rr = k / (SP / 4), cc = k - rr * (SP / 4);
-        reinterpret_cast<float4 *>(sW)[k] =
-            __ldcg(reinterpret_cast<const float4 *>(a.Wp + (size_t)(y0 + rr) * a.pitch + x0) + cc);
-      }
-      for (int k = tid; k < TY * (TX / 4); k += FILL_THREADS) {
-        const int rr = k / (TX / 4), cc = k - rr * (TX / 4);
-        reinterpret_cast<float4 *>(sZ)[k] = __ldg(
-            reinterpret_cast<const float4 *>(a.Zp + (size_t)(y0 + 1 + rr) * a.pitch + x0 + PADL) + cc);
-      }
-    }
-    int sides = sSides;
-#include "fill_relax_body.inc"
-
-    // ---- write back, then activate neighbours ----
-    if (f) {
-      atomicOr(&sFlags, f);
-      if (f & 0xFF) atomicMin(&sKey, f2ord(kmin));
-    }
-    __syncthreads();
-    const int fl = sFlags;
-    const int rowch = (fl >> 12) & 0xFFFF;
-    if (rowch) {
-      for (int k = tid; k < TY * (TX / 4); k += FILL_THREADS) {
-        const int rr = k / (TX / 4), cc = k % (TX / 4);
-        if (rowch & (1 << (rr >> 2))) {
-          const float4 val = *reinterpret_cast<const float4 *>(&sW[(rr + 1) * SP + PADL + 4 * cc]);
-          __stcg(reinterpret_cast<float4 *>(a.Wp + (size_t)(y0 + 1 + rr) * a.pitch + (x0 + PADL)) + cc, val);
-        }
-      }
-      __threadfence();  // my rows are visible device-wide before any neighbour is told about them
-    }
-    __syncthreads();    // ... and every thread's rows are
-    if (rowch && tid < 8) {
-      const bool n_ok = tyT > 0, s_ok = tyT < a.tilesY - 1, w_ok = txT > 0, e_ok = txT < a.tilesX - 1;
-      int nb = -1, bits = 0;
-      switch (tid) {
-        case 0: if ((fl & SIDE_N) && n_ok) { nb = t - a.tilesX; bits = SIDE_S; } break;
-        case 1: if ((fl & SIDE_S) && s_ok) { nb = t + a.tilesX; bits = SIDE_N; } break;
-        case 2: if ((fl & SIDE_W) && w_ok) { nb = t - 1; bits = SIDE_E; } break;
-        case 3: if ((fl & SIDE_E) && e_ok) { nb = t + 1; bits = SIDE_W; } break;
-        case 4: if ((fl & SIDE_NW) && n_ok && w_ok) { nb = t - a.tilesX - 1; bits = SIDE_SE; } break;
-        case 5: if ((fl & SIDE_NE) && n_ok && e_ok) { nb = t - a.tilesX + 1; bits = SIDE_SW; } break;
-        case 6: if ((fl & SIDE_SW) && s_ok && w_ok) { nb = t + a.tilesX - 1; bits = SIDE_NE; } break;
-        default: if ((fl & SIDE_SE) && s_ok && e_ok) { nb = t + a.tilesX + 1; bits = SIDE_NW; } break;
-      }
-      if (nb >= 0) aq_activate(a, nb, bits, sKey);
-      if (tid == 0 && (fl & (3 << 9))) atomicOr(&dev->edge_changed, (fl >> 9) & 3);
-    }
-    __syncthreads();  // all activations of this visit are out before the tile is released
-    if (tid == 0) {
-      atomicAdd(&dev->visits, 1ull);
-      atomicAdd(&dev->iters, (unsigned long long)iters);
-      if (again) {  // iteration cap: not at the local fixed point, relax every block again
-        atomicOr(&a.sides[t], SIDE_FULL);
-        atomicCAS(&a.state[t], TS_BUSY, TS_BUSY_DIRTY);
-      }
-      __threadfence();
-      if (atomicCAS(&a.state[t], TS_BUSY, TS_IDLE) == TS_BUSY) {
-        atomicSub(&dev->pending, 1);
-      } else {
-        // activated while it was being relaxed: straight back into a queue (still counted in `pending`)
-        const int k = *reinterpret_cast<volatile int *>(&a.keys[t]);
-        atomicExch(&a.state[t], TS_QUEUED);
-        aq_push(a, t, aq_bucket(dev, k));
-        if (a.profile) atomicAdd(&dev->requeues, 1ull);
-      }
-    }
-  }
-}
-
-// host-chosen seeds (perimeter tiles at the start, every tile in distance mode, tiles next to a replaced
-// ghost row later): every block dirty, always eligible
-__global__ void __launch_bounds__(256) fill_async_seed_kernel(const AsyncArgs a, const int *__restrict__ tiles, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  aq_activate(a, tiles[i], SIDE_FULL, f2ord(-__int_as_float(0x7f800000)));
-}
-
 // ---- level-ordered mode: split the round's worklist into admitted / postponed tiles ----------
 // Tiles whose lowest incoming water level is above the round's level are carried over to the next
 // round untouched (their side masks and keys move to the other parity); flooding then proceeds
@@ -870,7 +557,15 @@ __global__ void __launch_bounds__(256) fill_prolong_kernel(float *Wp, int pitch,
     float *w = Wp + (size_t)(y + 1) * pitch + x + PADL;
     if (l < *w) {
       *w = l;
-      tile_flag[(y / TY) * tilesX + x / TX] = 1;
+      // a lowered cell on a tile edge is also part of the neighbouring tiles' aprons: wake every tile
+      // that reads it (x, y are interior cells, so x-1, x+1, y-1, y+1 stay inside the raster)
+      const int ty0 = (y - 1) / TY, ty1 = (y + 1) / TY, tx0 = (x - 1) / TX, tx1 = (x + 1) / TX;
+      tile_flag[ty0 * tilesX + tx0] = 1;
+      if (tx1 != tx0) tile_flag[ty0 * tilesX + tx1] = 1;
+      if (ty1 != ty0) {
+        tile_flag[ty1 * tilesX + tx0] = 1;
+        if (tx1 != tx0) tile_flag[ty1 * tilesX + tx1] = 1;
+      }
     }
   }
 }
@@ -1033,7 +728,6 @@ struct FillState {
     if (per_sm < 1) per_sm = 1;
     grid = c.num_sms * per_sm;
     round = 1;  // stamps start at 0, so round numbers (used as stamp values) start at 1
-    use_async = c.params.fill_async != 0;
     // initial worklist: every tile on the perimeter of the tile grid (the only tiles whose
     // cells can see a finite neighbour at the start)
     std::vector<int> init;
@@ -1084,7 +778,6 @@ struct FillState {
     if (per_sm < 1) per_sm = 1;
     grid = c.num_sms * per_sm;
     round = 1;
-    use_async = c.params.fill_async != 0;
     std::vector<int> init((size_t)nt);
     for (size_t t = 0; t < nt; t++) init[t] = (int)t;
     seed_worklist(init);
@@ -1095,10 +788,6 @@ struct FillState {
   void seed_worklist(const std::vector<int> &tiles) {
     Ctx &c = ctx();
     if (tiles.empty()) return;
-    if (use_async) {  // queued by the next run_async()
-      a_seeds.insert(a_seeds.end(), tiles.begin(), tiles.end());
-      return;
-    }
     DevBuf<int> d(tiles.size());
     RDB_CK(cudaMemcpyAsync(d.p, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
     FillArgs a = make_args();
@@ -1138,7 +827,6 @@ struct FillState {
   // result then says so); the caller exchanges halos and calls run again
   int run(int64_t max_rounds = 0) {
     Ctx &c = ctx();
-    if (use_async) return run_async(max_rounds);
     int64_t rounds_this_call = 0;
     FillArgs a = make_args();
     int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 16);
@@ -1190,111 +878,6 @@ struct FillState {
       for (int k = 0; k < 8; k++) fprintf(stderr, "%llu ", hd->iter_hist[k]);
       fprintf(stderr, "\n");
     }
-    return hd->edge_changed | (still_active ? 4 : 0);
-  }
-
-  // fill_async = 1: one cooperative launch of persistent CTAs draining per-level tile queues (see
-  // fill_async_kernel) instead of rounds.  Runs to quiescence; in the row-band protocol every call
-  // between two halo exchanges is one such launch.
-  bool use_async = false;
-  DevBuf<int> a_state, a_queue;
-  DevBuf<AsyncDev> a_dev;
-  int a_cap = 0;
-  std::vector<int> a_seeds;
-  unsigned long long a_visits_done = 0;
-
-  // max_rounds > 0: a bounded burst of about max_rounds / 4 raster-equivalents of tile visits (bit 2 of the result
-  // says whether tiles are still queued)
-  int run_async(int64_t max_rounds = 0) {
-    Ctx &c = ctx();
-    const size_t nt = (size_t)tilesX * tilesY;
-    AsyncDev *hd = (AsyncDev *)c.pinned;
-    if (a_cap == 0) {
-      // ring size per bucket: a power of two above the tile count (a tile is queued at most once) plus
-      // the tickets idle CTAs may hold beyond the tail
-      a_cap = 4096;
-      while ((size_t)a_cap <= nt + 4096) a_cap <<= 1;
-      a_state.alloc(nt);
-      a_queue.alloc((size_t)AQ_BUCKETS * a_cap);
-      a_dev.alloc(1);
-      RDB_CK(cudaMemsetAsync(a_state.p, 0, nt * sizeof(int), c.stream));
-      RDB_CK(cudaMemsetAsync(a_queue.p, 0, (size_t)AQ_BUCKETS * a_cap * sizeof(int), c.stream));
-      memset(hd, 0, sizeof(AsyncDev));
-      for (int b = 0; b < AQ_BUCKETS; b++) {
-        float thr = __builtin_inff();
-        if (!levels.empty() && b < AQ_BUCKETS - 1) {
-          const size_t k = (size_t)((double)(b + 1) / AQ_BUCKETS * (double)levels.size());
-          thr = levels[k < levels.size() ? k : levels.size() - 1];
-        }
-        hd->thr[b] = thr;
-      }
-      RDB_CK(cudaMemcpyAsync(a_dev.p, hd, sizeof(AsyncDev), cudaMemcpyHostToDevice, c.stream));
-      RDB_CK(cudaStreamSynchronize(c.stream));
-    }
-    RDB_CK(cudaMemsetAsync(&a_dev.p->edge_changed, 0, sizeof(int), c.stream));
-    AsyncArgs a;
-    memset(&a, 0, sizeof(a));
-    a.Zp = Zp.p;
-    a.Wp = Wp.p;
-    a.pitch = pitch;
-    a.W = W;
-    a.H = H;
-    a.tilesX = tilesX;
-    a.tilesY = tilesY;
-    a.state = a_state.p;
-    a.sides = sides.p;
-    a.keys = keys.p;
-    a.queue = a_queue.p;
-    a.cap = a_cap;
-    a.dev = a_dev.p;
-    a.max_iters = (int)c.params.fill_max_iters;
-    a.use_tma = (int)c.params.fill_use_tma;
-    a.profile = (int)c.params.fill_profile;
-    a.spin_limit = c.params.fill_async_spin > 0 ? c.params.fill_async_spin : 4000000;
-    a.thick = (int)(c.params.fill_async_thick > 0 ? c.params.fill_async_thick : 256);
-    a.visit_stop = ~0ull;
-    if (max_rounds > 0) a.visit_stop = a_visits_done + (unsigned long long)((double)max_rounds / 4.0 * (double)nt) + 1;
-    int launches = 0;
-    if (!a_seeds.empty()) {
-      DevBuf<int> dseeds(a_seeds.size());
-      RDB_CK(cudaMemcpyAsync(dseeds.p, a_seeds.data(), a_seeds.size() * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-      fill_async_seed_kernel<<<(unsigned)((a_seeds.size() + 255) / 256), 256, 0, c.stream>>>(a, dseeds.p, (int)a_seeds.size());
-      RDB_CK(cudaGetLastError());
-      RDB_CK(cudaStreamSynchronize(c.stream));  // host vector / scratch go out of scope
-      a_seeds.clear();
-      launches++;
-    }
-    int per_sm = 0;
-    if (step_mode) RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_async_kernel<1>, FILL_THREADS, 0));
-    else RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fill_async_kernel<0>, FILL_THREADS, 0));
-    if (per_sm < 1) per_sm = 1;
-    long long blocks = (long long)c.num_sms * per_sm;
-    if (blocks > (long long)nt) blocks = (long long)nt;
-    void *args[] = {(void *)&mapW, (void *)&mapZ, (void *)&a};
-    KernelTimer kt;
-    if (step_mode)
-      RDB_CK(cudaLaunchCooperativeKernel((const void *)fill_async_kernel<1>, dim3((unsigned)blocks), dim3(FILL_THREADS), args, 0, c.stream));
-    else
-      RDB_CK(cudaLaunchCooperativeKernel((const void *)fill_async_kernel<0>, dim3((unsigned)blocks), dim3(FILL_THREADS), args, 0, c.stream));
-    kt.stop_async();
-    count_launch(launches + 1);
-    RDB_CK(cudaMemcpyAsync(hd, a_dev.p, sizeof(AsyncDev), cudaMemcpyDeviceToHost, c.stream));
-    RDB_CK(cudaStreamSynchronize(c.stream));
-    c.stats.ms_main_kernel += kt.ms();
-    a_visits_done = hd->visits;
-    const bool budget_stop = max_rounds > 0 && hd->visits >= a.visit_stop && hd->pending > 0 && !hd->abort_flag;
-    if (!budget_stop && (hd->abort_flag || hd->pending != 0))
-      fail("fill (async engine): the tile queues did not drain (pending=%d, watchdog=%d)", hd->pending, hd->abort_flag);
-    still_active = budget_stop;
-    if (!still_active) first_run = false;
-    rounds_run++;
-    c.stats.fill_rounds = rounds_run;
-    c.stats.fill_tile_visits = (int64_t)hd->visits;
-    c.stats.fill_tile_iters = (int64_t)hd->iters;
-    c.stats.fill_tile_cells = TX * TY;
-    if (c.params.fill_profile)
-      fprintf(stderr, "[fill async] visits=%llu iters=%llu requeues=%llu pop_retries=%llu\n", hd->visits, hd->iters, hd->requeues,
-              hd->pop_retries);
     return hd->edge_changed | (still_active ? 4 : 0);
   }
 

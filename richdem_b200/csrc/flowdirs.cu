@@ -2,6 +2,9 @@
 //   d8_flow_directions  (reference flowmet/d8_flowdirs.hpp:96-123)      4 B in, 1 B out per cell
 //   FM_D8               (reference flowmet/OCallaghan1984.hpp:13-84)    4 B in, 36 B out
 //   FM_Tarboton         (reference flowmet/Tarboton1997.hpp:14-149)     4 B in, 36 B out
+//   FM_D4               (reference flowmet/OCallaghan1984.hpp:13-77,89-91)
+//   FM_Holmgren / FM_Quinn / FM_Freeman (reference flowmet/Holmgren1994.hpp:13-83, Quinn1991.hpp:12-16,
+//                        Freeman1991.hpp:13-80)                         4 B in, 36 B out
 // Neighbour reads go through the read-only path; a warp covers 32 consecutive cells of a row so
 // the three row segments it touches are fetched once from HBM and re-used from L1/L2.
 #include "flowmet.cuh"
@@ -120,9 +123,13 @@ __global__ void __launch_bounds__(256) d8_flowdirs_rolling_kernel(const float *_
 
 // materialised proportions: 256 cells per block staged through shared memory so the 36 B/cell
 // AoS output leaves as coalesced float4 stores
-template <bool DINF>
+// MODE: 0 FM_D8, 1 FM_Tarboton, 2 FM_D4, 3 FM_Holmgren (FM_Quinn = exponent 1), 4 FM_Freeman
+enum : int { FM_MODE_D8 = 0, FM_MODE_DINF = 1, FM_MODE_D4 = 2, FM_MODE_HOLMGREN = 3, FM_MODE_FREEMAN = 4 };
+
+template <int MODE>
 __global__ void __launch_bounds__(256) fm_props_kernel(const float *__restrict__ dem, float *__restrict__ props,
-                                                        int W, int H, float nodata) {
+                                                        int W, int H, float nodata, double xparam) {
+  constexpr bool DINF = MODE == FM_MODE_DINF;
   __shared__ __align__(16) float s[256 * 9];
   const size_t n = (size_t)W * H;
   const size_t base = (size_t)blockIdx.x * 256;
@@ -159,6 +166,18 @@ __global__ void __launch_bounds__(256) fm_props_kernel(const float *__restrict__
           if (k == n2) p[k] = p2;
         }
       }
+    } else if (MODE == FM_MODE_D4) {
+      const int c = fm_d4_cell(dem, x, y, W, H, nodata);
+      if (c == kCodeNoData) {
+        p[0] = kNoDataGen;
+      } else if (c > 0) {
+        p[0] = kHasFlowGen;
+#pragma unroll
+        for (int k = 1; k <= 4; k++)
+          if (k == c) p[k] = 1.0f;
+      }
+    } else if (MODE == FM_MODE_HOLMGREN || MODE == FM_MODE_FREEMAN) {
+      fm_mfd_cell<MODE == FM_MODE_HOLMGREN>(dem, x, y, W, H, nodata, xparam, p);
     } else {
       const int c = fm_d8_cell(dem, x, y, W, H, nodata);
       if (c == kCodeNoData) {
@@ -201,20 +220,29 @@ void d8_flow_directions_dev(const float *d_dem, uint8_t *d_dirs, int w, int h, f
   count_launch();
 }
 
-void fm_d8_dev(const float *d_dem, float *d_props, int w, int h, float nodata) {
+template <int MODE>
+static void fm_launch(const float *d_dem, float *d_props, int w, int h, float nodata, double xparam) {
   Ctx &c = ctx();
   const size_t n = (size_t)w * h;
-  fm_props_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d_dem, d_props, w, h, nodata);
+  fm_props_kernel<MODE><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d_dem, d_props, w, h, nodata, xparam);
   RDB_CK(cudaGetLastError());
   count_launch();
 }
 
+void fm_d8_dev(const float *d_dem, float *d_props, int w, int h, float nodata) {
+  fm_launch<FM_MODE_D8>(d_dem, d_props, w, h, nodata, 0.0);
+}
 void fm_tarboton_dev(const float *d_dem, float *d_props, int w, int h, float nodata) {
-  Ctx &c = ctx();
-  const size_t n = (size_t)w * h;
-  fm_props_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d_dem, d_props, w, h, nodata);
-  RDB_CK(cudaGetLastError());
-  count_launch();
+  fm_launch<FM_MODE_DINF>(d_dem, d_props, w, h, nodata, 0.0);
+}
+void fm_d4_dev(const float *d_dem, float *d_props, int w, int h, float nodata) {
+  fm_launch<FM_MODE_D4>(d_dem, d_props, w, h, nodata, 0.0);
+}
+void fm_holmgren_dev(const float *d_dem, float *d_props, int w, int h, float nodata, double xparam) {
+  fm_launch<FM_MODE_HOLMGREN>(d_dem, d_props, w, h, nodata, xparam);
+}
+void fm_freeman_dev(const float *d_dem, float *d_props, int w, int h, float nodata, double xparam) {
+  fm_launch<FM_MODE_FREEMAN>(d_dem, d_props, w, h, nodata, xparam);
 }
 
 }  // namespace rdb

@@ -43,6 +43,71 @@ __device__ __forceinline__ int fm_d8_cell(const float *__restrict__ dem, int x, 
   return lowest_n;
 }
 
+// FM_OCallaghan<D4> for one cell (reference flowmet/OCallaghan1984.hpp:37-75 with the D4 offset tables
+// common/constants.hpp:53-54: 1 = W, 2 = N, 3 = E, 4 = S).  Returns kCodeNoData, 0 or the D4 index 1..4 --
+// the reference stores the proportion in THAT slot of the 9-slot cell (and its generic accumulation then
+// reads slots as D8 directions, flow_accumulation_generic.hpp:53-56); both are reproduced as they are.
+__device__ __forceinline__ int fm_d4_cell(const float *__restrict__ dem, int x, int y, int W, int H, float nodata) {
+  const size_t i = (size_t)y * W + x;
+  const float e = __ldg(dem + i);
+  if (e == nodata) return kCodeNoData;
+  if (x == 0 || y == 0 || x == W - 1 || y == H - 1) return 0;
+  int lowest_n = 0;
+  float lowest = 3.402823466e+38f;
+#pragma unroll
+  for (int n = 1; n <= 4; n++) {
+    const int dx = n == 1 ? -1 : (n == 3 ? 1 : 0), dy = n == 2 ? -1 : (n == 4 ? 1 : 0);
+    const float ne = __ldg(dem + (size_t)(y + dy) * W + (x + dx));
+    if (ne == nodata) continue;
+    if (ne >= e) continue;
+    if (ne < lowest) {
+      lowest = ne;
+      lowest_n = n;
+    }
+  }
+  return lowest_n;
+}
+
+// FM_Holmgren (HOLMGREN = true; reference flowmet/Holmgren1994.hpp:33-80; FM_Quinn is xparam = 1,
+// Quinn1991.hpp:15) and FM_Freeman (HOLMGREN = false; flowmet/Freeman1991.hpp:28-77) for one cell.
+// p[0..8] arrives filled with NO_FLOW_GEN.  The reference's mixed precision is kept step by step:
+// rise is a float difference widened to double, the gradient and the power are double; Holmgren rounds
+// each power to float BEFORE summing (it sums props(x,y,n)), Freeman sums the unrounded doubles;
+// normalisation multiplies the stored float by the double 1/C and rounds once.  pow(g, 1.0) is g in
+// glibc, so the exponent-1 case takes the value itself instead of the device pow (<= 2 ulp).
+template <bool HOLMGREN>
+__device__ __forceinline__ void fm_mfd_cell(const float *__restrict__ dem, int x, int y, int W, int H, float nodata,
+                                            double xparam, float (&p)[9]) {
+  const size_t i = (size_t)y * W + x;
+  const float e = __ldg(dem + i);
+  if (e == nodata) {
+    p[0] = kNoDataGen;
+    return;
+  }
+  if (x == 0 || y == 0 || x == W - 1 || y == H - 1) return;
+  double C = 0;
+#pragma unroll
+  for (int n = 1; n <= 8; n++) {
+    const float ne = __ldg(dem + (size_t)(y + d8dy(n)) * W + (x + d8dx(n)));
+    if (ne == nodata) continue;
+    if (ne < e) {
+      const double rise = (double)__fsub_rn(e, ne);
+      const double run = (n & 1) ? 1.0 : 1.414213562373095048801688724209698078569671875376948;
+      double g = __ddiv_rn(rise, run);
+      if (HOLMGREN) g = __dmul_rn(g, (n & 1) ? 0.5 : 0.354);
+      const double cval = xparam == 1.0 ? g : pow(g, xparam);
+      p[n] = (float)cval;
+      C = __dadd_rn(C, HOLMGREN ? (double)p[n] : cval);
+    }
+  }
+  if (C > 0) {
+    p[0] = kHasFlowGen;
+    C = __ddiv_rn(1.0, C);
+#pragma unroll
+    for (int n = 1; n <= 8; n++) p[n] = p[n] > 0 ? (float)__dmul_rn((double)p[n], C) : 0.0f;
+  }
+}
+
 // FM_Tarboton for one cell (reference flowmet/Tarboton1997.hpp:62-141).
 // returns kCodeNoData, 0 (no flow) or nmax in 1..8 with *rmax_out = rmax after the facet-parity
 // flip (:121-126).  All double arithmetic uses explicit round-to-nearest intrinsics so that no

@@ -21,6 +21,12 @@ __device__ __forceinline__ float lattice(uint32_t ix, uint32_t iy, uint32_t s) {
   return (float)(hash3(ix, iy, s) >> 8) * (1.0f / 16777216.0f);
 }
 
+// quintic fade t^3 (t (6 t - 15) + 10), one rounding per operation
+__device__ __forceinline__ float fade(float t) {
+  const float inner = __fadd_rn(__fmul_rn(t, __fsub_rn(__fmul_rn(t, 6.f), 15.f)), 10.f);
+  return __fmul_rn(__fmul_rn(__fmul_rn(t, t), t), inner);
+}
+
 __global__ void __launch_bounds__(256) fbm_kernel(float *dem, int W, int H, int y0, uint32_t seed, int octaves,
                                                    int top_log2, float quantum) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -33,20 +39,25 @@ __global__ void __launch_bounds__(256) fbm_kernel(float *dem, int W, int H, int 
       if (lg < 1) break;
       const uint32_t cell = 1u << lg;
       const uint32_t ix = (uint32_t)x >> lg, iy = (uint32_t)y >> lg;
-      float tx = (float)((uint32_t)x & (cell - 1)) / (float)cell;
-      float ty = (float)((uint32_t)y & (cell - 1)) / (float)cell;
-      tx = tx * tx * tx * (tx * (tx * 6.f - 15.f) + 10.f);
-      ty = ty * ty * ty * (ty * (ty * 6.f - 15.f) + 10.f);
+      // every operation is an explicitly rounded IEEE single (no FMA contraction), so that the CPU restatement
+      // of this generator (oracle/oracle.c: orc_generate_fbm_f32, compiled with -ffp-contract=off) produces the
+      // same bits: the reference arm of bench.py runs on exactly the raster the GPU arm runs on
+      float tx = __fdiv_rn((float)((uint32_t)x & (cell - 1)), (float)cell);
+      float ty = __fdiv_rn((float)((uint32_t)y & (cell - 1)), (float)cell);
+      tx = fade(tx);
+      ty = fade(ty);
       const uint32_t s = seed * 131u + (uint32_t)o;
       const float v00 = lattice(ix, iy, s), v01 = lattice(ix + 1, iy, s);
       const float v10 = lattice(ix, iy + 1, s), v11 = lattice(ix + 1, iy + 1, s);
-      const float v = (v00 * (1.f - tx) + v01 * tx) * (1.f - ty) + (v10 * (1.f - tx) + v11 * tx) * ty;
-      sum += amp * v;
-      norm += amp;
-      amp *= 0.5946035575f;  // 2^-0.75
+      const float top = __fadd_rn(__fmul_rn(v00, __fsub_rn(1.f, tx)), __fmul_rn(v01, tx));
+      const float bot = __fadd_rn(__fmul_rn(v10, __fsub_rn(1.f, tx)), __fmul_rn(v11, tx));
+      const float v = __fadd_rn(__fmul_rn(top, __fsub_rn(1.f, ty)), __fmul_rn(bot, ty));
+      sum = __fadd_rn(sum, __fmul_rn(amp, v));
+      norm = __fadd_rn(norm, amp);
+      amp = __fmul_rn(amp, 0.5946035575f);  // 2^-0.75
     }
-    float z = 1000.0f * sum / norm;
-    if (quantum > 0.f) z = rintf(z / quantum) * quantum;
+    float z = __fdiv_rn(__fmul_rn(1000.0f, sum), norm);
+    if (quantum > 0.f) z = __fmul_rn(rintf(__fdiv_rn(z, quantum)), quantum);
     dem[(size_t)yl * W + x] = z;
   }
 }

@@ -221,6 +221,8 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
 
 // ---- atomics (single OS thread: plain read-modify-write) ----
 template <class T> struct rdb_emu_id { typedef T type; };

@@ -105,9 +105,32 @@ def main():
         syn[k + "__fa_d8"] = R.fa_d8(r, -9999.0)
         syn[k + "__fa_dinf"] = R.fa_dinf(r, -9999.0)
     np.savez_compressed(f"{OUT}/synthetic_ref.npz", **syn)
+    metrics()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+METRIC_CASES = [("D4", None), ("Quinn", None), ("Holmgren", 2.5), ("Holmgren", 0.7), ("Freeman", 1.1), ("Freeman", 4.0)]
+
+
+def metrics():
+    """6. the remaining flow metrics: FM_D4 / FM_Quinn / FM_Holmgren / FM_Freeman proportions and the FA_*
+    accumulations of the unmodified reference on the resolved Beauford crop (NoData) and one seeded synthetic DEM."""
+    R = oracle.ref()
+    g = np.load(f"{OUT}/beauford_crop.npz")
+    out = {}
+    syn = R.resolve_flats(R.fill_depressions(oracle.fbm_terrain(150, 210, seed=104, quantum=0.25)), -9999.0)
+    for name, dem in (("beauford", g["resolved"]), ("s104", syn)):
+        for m, e in METRIC_CASES:
+            k = f"{name}__{m}_{e}"
+            out[k + "__fm"] = R.fm_method(dem, -9999.0, m, e).reshape(-1, 9)[::11]  # every 11th cell's 9 slots
+            out[k + "__fa"] = R.fa_method(dem, -9999.0, m, e)[::3, ::3]             # every 3rd row / column
+    out["s104__resolved"] = syn
+    np.savez_compressed(f"{OUT}/flow_metrics_ref.npz", **out)
+
+
 if __name__ == "__main__":
-    main()
+    if "--metrics-only" in sys.argv:
+        metrics()
+    else:
+        main()

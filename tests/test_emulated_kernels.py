@@ -55,12 +55,7 @@ def emulated(emu_lib, monkeypatch):
     _lib.init(0)
     _lib.set_param("fill_use_tma", 0)  # TMA / mbarrier PTX is not emulated
     yield emu_lib
-    for name, value in (("fill_ordered", 1), ("fill_max_iters", 0), ("fill_rounds_per_sync", 16), ("flats_tiled", 1),
-                        ("accum_packed", 1), ("accum_budget", 0), ("fill_order_rounds", 0), ("accum_agg", 0), ("accum_tail", 0),
-                        ("accum_tail_budget", 0), ("accum_walk_lanes", 0), ("accum_fused_prep", 0),
-                        ("flats_uf_tiled", 0), ("fill_async", 0), ("accum_async", 0),
-                        ("fill_async_thick", 0), ("flowdirs_rolling", 0), ("fill_multigrid", 0), ("fill_multigrid_min", 0), ("fill_vcycle", 0)):
-        _lib.set_param(name, value)
+    _lib.reset_params()
 
 
 @pytest.fixture(scope="module")
@@ -111,15 +106,13 @@ def test_in_place_and_copy_semantics(emulated, gp):
 @pytest.mark.parametrize("param,value", [
     ("fill_ordered", 0), ("fill_max_iters", 1), ("fill_max_iters", 2), ("fill_rounds_per_sync", 1), ("fill_order_rounds", 40),
     ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
-    ("accum_agg", 1), ("accum_tail", 5), ("accum_tail", 1 << 20), ("accum_walk_lanes", 1),
-    ("accum_fused_prep", 1), ("flats_uf_tiled", 1), ("fill_async", 1), ("accum_async", 1), ("flowdirs_rolling", 1),
-    ("fill_multigrid", 4),
+    ("accum_walk_lanes", 0), ("accum_fused_prep", 0), ("flats_uf_tiled", 0), ("flowdirs_rolling", 0),
+    ("fill_multigrid", 4), ("fill_multigrid", 0), ("fill_vcycle", 0), ("fill_vcycle", 2),
 ])
 def test_algorithm_variants_agree(emulated, gp, checker, param, value):
     """Every tunable is a schedule / layout choice; none may change a result."""
+    _lib.set_param("fill_multigrid_min", 32)  # so that a 300 x 420 raster gets two coarse levels
     _lib.set_param(param, value)
-    if param == "fill_multigrid":
-        _lib.set_param("fill_multigrid_min", 32)  # so that a 300 x 420 raster gets two coarse levels
     dem = oracle.fbm_terrain(300, 420, seed=17, quantum=0.5)
     dem[40:70, 100:180] = gp.ND
     gp.check_pipeline(dem, gp.ND, checker)
@@ -155,11 +148,8 @@ def band_drivers(emulated, monkeypatch):
     return gs
 
 
-@pytest.mark.parametrize("G", [1, 2, 3, 5, "async"])
+@pytest.mark.parametrize("G", [1, 2, 3, 5])
 def test_band_fill(band_drivers, checker, G):
-    if G == "async":  # the asynchronous engine under the row-band protocol (one launch per halo exchange)
-        _lib.set_param("fill_async", 1)
-        G = 3
     dem = oracle.fbm_terrain(330, 300, seed=31, quantum=0.5)
     got, rounds = band_drivers.emulate_bands(dem, G)
     assert np.array_equal(got, checker.fill_depressions(dem)), f"G={G} after {rounds} exchanges"
@@ -170,17 +160,12 @@ def test_band_fill_ghost_row_on_tile_boundary(band_drivers, checker):
 
 
 @pytest.mark.parametrize("G", [2, 3, 5])
-@pytest.mark.parametrize("dinf", [False, True, "tail", "lanes"])
+@pytest.mark.parametrize("dinf", [False, True, "nolanes"])
 def test_band_accumulation(band_drivers, checker, G, dinf):
     nd = -9999.0
-    if dinf == "lanes":  # unit-weight D8 with the persistent-lane walk
-        _lib.set_param("accum_walk_lanes", 1)
+    if dinf == "nolanes":  # unit-weight D8 with one thread per source instead of the persistent-lane walk
+        _lib.set_param("accum_walk_lanes", 0)
         dinf = False
-    if dinf == "tail":  # D-infinity with the small-frontier tail mode and block-aggregated appends
-        _lib.set_param("accum_tail", 64)
-        _lib.set_param("accum_tail_budget", 3)
-        _lib.set_param("accum_agg", 1)
-        dinf = True
     dem = oracle.fbm_terrain(260, 210, seed=41, quantum=0.25)
     dem[100:140, 60:120] = nd
     resolved = checker.resolve_flats(checker.fill_depressions(dem), nd)
@@ -195,14 +180,11 @@ def test_band_accumulation_with_weights(band_drivers, checker):
     band_drivers.test_band_accumulation_with_weights(checker)
 
 
-@pytest.mark.parametrize("G", [2, 3, 5, "uf_tiled", "async"])
+@pytest.mark.parametrize("G", [2, 3, 5, "uf_global"])
 def test_band_flat_resolution(band_drivers, checker, G):
     nd = -9999.0
-    if G == "uf_tiled":
-        _lib.set_param("flats_uf_tiled", 1)
-        G = 3
-    if G == "async":  # geodesic distances of the flat gradients on the asynchronous engine
-        _lib.set_param("fill_async", 1)
+    if G == "uf_global":  # one-level union-find instead of the tiled one
+        _lib.set_param("flats_uf_tiled", 0)
         G = 3
     dem = oracle.fbm_terrain(300, 260, seed=51, quantum=0.5)
     dem[150:170, 60:120] = nd
@@ -225,40 +207,20 @@ def test_fused_d8_preparation_block_seams(emulated, gp, checker, shape):
     dem[shape[0] // 3: shape[0] // 3 + 5, shape[1] // 2: shape[1] // 2 + 9] = gp.ND
     expected = checker.fa_d8(dem, gp.ND)
     for lanes in (0, 1):
-        _lib.set_param("accum_fused_prep", 1)
         _lib.set_param("accum_walk_lanes", lanes)
         got = np.asarray(rd.FlowAccumulation(gp.R(dem), "D8"))
         assert np.array_equal(got, expected), (shape, lanes)
 
 
-@pytest.mark.parametrize("shape,q", [((150, 200), None), ((300, 420), 0.5), ((64, 64), None), ((65, 129), 1.0), ((3, 3), None),
-                                     ((200, 1500), None), ((640, 700), 2.0)])
-def test_async_fill_engine(emulated, gp, checker, shape, q):
-    """fill_async: persistent CTAs draining per-level tile queues (tile states IDLE / QUEUED / BUSY / BUSY_DIRTY).
-    Also with the in-tile iteration cap, which exercises the re-queue of a tile by the CTA that holds it."""
-    import richdem_b200 as rd
-    dem = oracle.fbm_terrain(*shape, seed=shape[0] + shape[1], quantum=q)
-    expected = checker.fill_depressions(dem)
-    _lib.set_param("fill_async", 1)
-    for cap, thick in ((0, 0), (2, 0), (0, 1), (2, 4)):  # thick: queue length from which tickets replace CAS claims
-        _lib.set_param("fill_max_iters", cap)
-        _lib.set_param("fill_async_thick", thick)
-        got = np.asarray(rd.FillDepressions(gp.R(dem)))
-        assert np.array_equal(got, expected), (shape, cap, thick)
-        assert _lib.stats()["fill_tile_visits"] > 0
-
-
 @pytest.mark.parametrize("k", [2, 3, 4, 8])
-@pytest.mark.parametrize("engine", ["rounds", "async", "vcycle1", "vcycle3", "async_vcycle2"])
+@pytest.mark.parametrize("engine", ["rounds", "vcycle1", "vcycle3"])
 def test_multigrid_seeded_fill(emulated, gp, checker, k, engine):
     """fill_multigrid: the flood starts from the lifted fill of the k x k max-pooled raster (recursively) instead of
-    +inf; ragged block edges, NoData, plateaus, both engines.  Any upper bound must relax to the exact surface."""
+    +inf; ragged block edges, NoData, plateaus.  Any upper bound must relax to the exact surface."""
     import richdem_b200 as rd
     _lib.set_param("fill_multigrid", k)
     _lib.set_param("fill_multigrid_min", 32)
-    _lib.set_param("fill_async", 1 if engine.startswith("async") else 0)
-    if engine == "async_vcycle2":  # the queue engine in bounded bursts (about half a raster-equivalent of visits each)
-        _lib.set_param("fill_vcycle", 2)
+    _lib.set_param("fill_vcycle", 0)
     if engine.startswith("vcycle"):  # coarse-grid corrections (restrict / coarse relax / prolong) every 1 or 3 fine rounds
         _lib.set_param("fill_vcycle", int(engine[-1]))
         _lib.set_param("fill_rounds_per_sync", 2)
@@ -267,6 +229,20 @@ def test_multigrid_seeded_fill(emulated, gp, checker, k, engine):
         dem[shape[0] // 3: shape[0] // 3 + 7, shape[1] // 2: shape[1] // 2 + 9] = gp.ND
         got = np.asarray(rd.FillDepressions(gp.R(dem)))
         assert np.array_equal(got, checker.fill_depressions(dem)), (k, engine, shape)
+
+
+def test_vcycle_prolongation_wakes_neighbouring_tiles(emulated, gp, checker):
+    """ADVICE round 1 regression (walled lake next to a tile seam) on the CPU model of the kernels."""
+    import richdem_b200 as rd
+    dem = gp.walled_lake_case()
+    expected = checker.fill_depressions(dem)
+    for cfg in ({"fill_multigrid": 8, "fill_multigrid_min": 32, "fill_vcycle": 1},
+                {"fill_multigrid": 4, "fill_multigrid_min": 32, "fill_vcycle": 2},
+                {"fill_multigrid": 8, "fill_multigrid_min": 32, "fill_vcycle": 0}):
+        for k, v in cfg.items():
+            _lib.set_param(k, v)
+        assert np.array_equal(np.asarray(rd.FlowDirectionsD8(gp.R(dem))).shape, dem.shape)
+        assert np.array_equal(np.asarray(rd.FillDepressions(gp.R(dem))), expected), cfg
 
 
 def _spread_to_all_lower_neighbours(dem):
@@ -289,16 +265,9 @@ def _spread_to_all_lower_neighbours(dem):
     return p
 
 
-@pytest.mark.parametrize("mode", ["levels", "agg_tail", "async"])
-def test_eight_receiver_proportions(emulated, gp, checker, mode):
-    """FlowAccumulation(props) on graphs with up to 8 receivers per cell (a cone with huge fan-in, and fBm), on the
-    level kernel, its tail / aggregated variants and the asynchronous engine."""
+def test_eight_receiver_proportions(emulated, gp, checker):
+    """FlowAccumulation(props) on graphs with up to 8 receivers per cell (a cone with huge fan-in, and fBm)."""
     import richdem_b200 as rd
-    if mode == "agg_tail":
-        _lib.set_param("accum_agg", 1)
-        _lib.set_param("accum_tail", 100)
-    if mode == "async":
-        _lib.set_param("accum_async", 1)
     yy, xx = np.mgrid[0:201, 0:231]
     cone = np.hypot(yy - 100, xx - 115).astype(np.float32)
     for dem in (cone, checker.resolve_flats(checker.fill_depressions(oracle.fbm_terrain(260, 300, seed=5)), gp.ND)):
@@ -308,15 +277,14 @@ def test_eight_receiver_proportions(emulated, gp, checker, mode):
 
 
 def test_cooperative_kernels_with_several_blocks():
-    """The cooperative kernels (multi-receiver level kernel with its tail mode and block-aggregated appends, the
-    persistent BFS) size their grid from the SM count; re-run their cases with 3 emulated SMs so that they execute as
+    """The cooperative kernels (multi-receiver level kernel, the persistent BFS) size their grid from the SM count; re-run their cases with 3 emulated SMs so that they execute as
     3 blocks side by side, each with its own shared memory and a real grid barrier."""
     import subprocess
     if os.environ.get("RDB_EMU_SMS"):
         pytest.skip("already inside the multi-block run")
     env = dict(os.environ, RDB_EMU_SMS="3", RDB_EMU_CHAOS="7")  # CHAOS: atomics yield at random -> other interleavings
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.abspath(__file__), "-k",
-                        "variants or band_accumulation or special_rasters or degenerate or async or eight_receiver"],
+                        "variants or band_accumulation or special_rasters or degenerate or eight_receiver"],
                        env=env, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
@@ -326,7 +294,6 @@ def test_tiled_union_find_seams(emulated, gp, checker, shape, q):
     """flats_uf_tiled: flats that cross the 64x16 union-find tiles in every direction (coarse quantisation makes
     large plateaus; the last case is one flat covering the raster)."""
     import richdem_b200 as rd
-    _lib.set_param("flats_uf_tiled", 1)
     dem = checker.fill_depressions(oracle.fbm_terrain(*shape, seed=shape[1], quantum=q))
     dem[shape[0] // 2, shape[1] // 3: shape[1] // 3 + 4] = gp.ND
     m, l = rd.FlatMask(gp.R(dem))
@@ -342,7 +309,6 @@ def test_tiled_union_find_seams(emulated, gp, checker, shape, q):
 def test_rolling_flow_directions(emulated, gp, checker, shape):
     """flowdirs_rolling: 4 columns per thread, 64-row chunks, halo columns by shuffle; widths around the block seams."""
     import richdem_b200 as rd
-    _lib.set_param("flowdirs_rolling", 1)
     dem = checker.resolve_flats(checker.fill_depressions(oracle.fbm_terrain(*shape, seed=shape[1], quantum=0.5)), gp.ND)
     dem[shape[0] // 2:, shape[1] // 2: shape[1] // 2 + 3] = gp.ND
     assert np.array_equal(np.asarray(rd.FlowDirectionsD8(gp.R(dem))), checker.d8_flow_directions(dem, gp.ND))

@@ -251,32 +251,144 @@ def test_cxx_dropin_matches_reference_cpu_templates():
 
 
 # ---- alternative code paths must give identical results ------------------------------------------
-def test_algorithm_variants_agree(checker):
-    """Level-ordered vs plain tile admission (fill), tiled vs level-synchronous gradients (flats),
-    packed vs double accumulators (unit-weight D8): same bits, and equal to the checker."""
-    dem = oracle.fbm_terrain(768, 1024, seed=17, quantum=0.25)
+VARIANTS = [  # every switch is a schedule / layout choice (rdb200_set_param); none may change a result
+    {"fill_ordered": 0, "fill_multigrid": 0}, {"fill_multigrid": 0}, {"fill_vcycle": 0}, {"fill_multigrid": 4, "fill_vcycle": 4},
+    {"fill_multigrid": 8, "fill_multigrid_min": 256, "fill_vcycle": 2}, {"fill_multigrid": 3, "fill_multigrid_min": 128, "fill_vcycle": 0},
+    {"flats_tiled": 0}, {"flats_uf_tiled": 0}, {"accum_packed": 0}, {"accum_fused_prep": 0}, {"accum_walk_lanes": 0},
+    {"accum_fused_prep": 0, "accum_walk_lanes": 0}, {"flowdirs_rolling": 0}, {},
+]
+
+
+@pytest.mark.parametrize("cfg", VARIANTS, ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()) or "defaults")
+@pytest.mark.parametrize("shape,q", [((1500, 2040), 0.5), ((777, 1028), 2.0)])
+def test_algorithm_variants_agree(checker, cfg, shape, q):
+    """Round-1 kernels vs the round-2 defaults (multigrid start + V-cycles, fused D8 preparation, persistent-lane
+    walk, tiled union-find, rolling-window direction kernel): same bits, and equal to the checker."""
+    dem = oracle.fbm_terrain(*shape, seed=shape[0], quantum=q)
+    dem[shape[0] // 4: shape[0] // 4 + 40, shape[1] // 3: shape[1] // 3 + 60] = ND
     f_ref = checker.fill_depressions(dem)
     r_ref = checker.resolve_flats(f_ref, ND)
-    a_ref = checker.fa_d8(r_ref, ND)
-    for name, value in (("fill_ordered", 0), ("flats_tiled", 0), ("accum_packed", 0)):
-        default = 1
-        _lib.set_param(name, value)
-        try:
-            f = np.asarray(rd.FillDepressions(R(dem)))
-            r = np.asarray(rd.ResolveFlats(R(f_ref)))
-            a = np.asarray(rd.FlowAccumulation(R(r_ref), "D8"))
-        finally:
-            _lib.set_param(name, default)
-        assert np.array_equal(f, f_ref), name
-        assert np.array_equal(r.view(np.uint32), r_ref.view(np.uint32)), name
-        assert np.array_equal(a, a_ref), name
-    # and the defaults
-    assert np.array_equal(np.asarray(rd.FillDepressions(R(dem))), f_ref)
-    assert np.array_equal(np.asarray(rd.ResolveFlats(R(f_ref))).view(np.uint32), r_ref.view(np.uint32))
-    assert np.array_equal(np.asarray(rd.FlowAccumulation(R(r_ref), "D8")), a_ref)
+    try:
+        for k, v in cfg.items():
+            _lib.set_param(k, v)
+        f = np.asarray(rd.FillDepressions(R(dem)))
+        r = np.asarray(rd.ResolveFlats(R(f_ref)))
+        a = np.asarray(rd.FlowAccumulation(R(r_ref), "D8"))
+        a2 = np.asarray(rd.FlowAccumulation(R(f_ref), "D8"))
+        d = np.asarray(rd.FlowDirectionsD8(R(r_ref)))
+        ai = np.asarray(rd.FlowAccumulation(R(r_ref), "Dinf"))
+    finally:
+        _lib.reset_params()
+    assert np.array_equal(f, f_ref)
+    assert np.array_equal(r.view(np.uint32), r_ref.view(np.uint32))
+    assert np.array_equal(a, checker.fa_d8(r_ref, ND))
+    assert np.array_equal(a2, checker.fa_d8(f_ref, ND))
+    assert np.array_equal(d, checker.d8_flow_directions(r_ref, ND))
+    np.testing.assert_allclose(ai, checker.fa_dinf(r_ref, ND), rtol=ACC_RTOL, atol=0)
+
+
+def walled_lake_case():
+    """a lake whose wall sits inside a coarse block next to a tile seam.  The prolongation of a V-cycle
+    lowers cells on a tile edge; the neighbouring tile (whose own cells lie in blocks with a high maximum) must be
+    woken as well, or 336 cells keep the level 20 instead of 1."""
+    dem = np.full((64, 192), 20.0, np.float32)
+    dem[8:56, 57:191] = 0.0
+    dem[32, 191] = 1.0
+    return dem
+
+
+def test_vcycle_prolongation_wakes_neighbouring_tiles(checker):
+    dem = walled_lake_case()
+    expected = checker.fill_depressions(dem)
+    assert (expected == 1.0).sum() > 6000
+    try:
+        for cfg in ({"fill_multigrid": 8, "fill_multigrid_min": 32, "fill_vcycle": 1},
+                    {"fill_multigrid": 8, "fill_multigrid_min": 32, "fill_vcycle": 1, "fill_use_tma": 0},
+                    {"fill_multigrid": 4, "fill_multigrid_min": 32, "fill_vcycle": 2}):
+            _lib.reset_params()
+            for k, v in cfg.items():
+                _lib.set_param(k, v)
+            assert np.array_equal(np.asarray(rd.FillDepressions(R(dem))), expected), cfg
+    finally:
+        _lib.reset_params()
 
 
 def test_unit_weight_d8_on_width_not_multiple_of_4(checker):
     """W % 4 != 0 takes the scalar (non-vectorised, non-packed) kernels."""
     dem = checker.fill_depressions(oracle.fbm_terrain(301, 403, seed=19, quantum=0.5))
     assert np.array_equal(np.asarray(rd.FlowAccumulation(R(dem), "D8")), checker.fa_d8(dem, ND))
+
+
+# ---- SURVEY 8f-1: FM_D4 / FM_Quinn / FM_Holmgren / FM_Freeman and their FA_* ----------------------------
+METRIC_CASES = [("D4", None), ("Quinn", None), ("Holmgren", 2.5), ("Holmgren", 0.7), ("Freeman", 1.1), ("Freeman", 4.0)]
+MFD_ACC_RTOL = 1e-6  # north_star: 1e-5 relative; proportions may differ by 1 float ulp where pow() is involved
+
+
+def check_metric(dem, nd, m, e, fm_ref, fa_ref, fm_sel=None, fa_sel=None):
+    p = np.asarray(rd.FlowProportions(R(dem, nd), m, exponent=e))
+    p = p if fm_sel is None else fm_sel(p)
+    if m in ("D4", "Quinn"):  # no transcendental involved: bit-identical
+        assert np.array_equal(p, fm_ref), (m, e)
+    else:
+        assert np.array_equal(p > 0, fm_ref > 0), (m, e)
+        assert ulp_diff(p, fm_ref).max() <= 1, (m, e, int(ulp_diff(p, fm_ref).max()))
+    a = rd.FlowAccumulation(R(dem, nd), m, exponent=e)
+    assert a.no_data == -1 and a.dtype == np.float64
+    a = np.asarray(a) if fa_sel is None else fa_sel(np.asarray(a))
+    np.testing.assert_allclose(a, fa_ref, rtol=MFD_ACC_RTOL if m not in ("D4",) else ACC_RTOL, atol=0, err_msg=f"{m} {e}")
+
+
+def test_remaining_flow_metrics_golden(golden):
+    g = golden["flow_metrics_ref"]
+    dems = {"beauford": golden["beauford_crop"]["resolved"], "s104": g["s104__resolved"]}
+    for name, dem in dems.items():
+        for m, e in METRIC_CASES:
+            k = f"{name}__{m}_{e}"
+            check_metric(dem, ND, m, e, g[k + "__fm"], g[k + "__fa"], fm_sel=lambda p: p.reshape(-1, 9)[::11],
+                         fa_sel=lambda a: a[::3, ::3])
+
+
+@pytest.mark.parametrize("method,exponent", METRIC_CASES)
+def test_remaining_flow_metrics_vs_oracle(checker, method, exponent):
+    dem = oracle.fbm_terrain(700, 900, seed=31, quantum=0.25)
+    dem[100:140, 300:420] = ND
+    dem = checker.resolve_flats(checker.fill_depressions(dem), ND)
+    check_metric(dem, ND, method, exponent, checker.fm_method(dem, ND, method, exponent),
+                 checker.fa_method(dem, ND, method, exponent))
+    wts = np.random.default_rng(4).random(dem.shape)
+    a = rd.FlowAccumulation(R(dem), method, exponent=exponent, weights=R(wts, -1))
+    np.testing.assert_allclose(np.asarray(a), checker.fa_method(dem, ND, method, exponent, wts), rtol=MFD_ACC_RTOL, atol=0)
+
+
+def test_exponent_methods_require_an_exponent():
+    dem = R(oracle.fbm_terrain(40, 50, seed=1))
+    for m in ("Holmgren", "Freeman"):
+        with pytest.raises(Exception, match="requires an exponent"):
+            rd.FlowAccumulation(dem, m)
+        with pytest.raises(Exception, match="requires an exponent"):
+            rd.FlowProportions(dem, m)
+    with pytest.raises(Exception, match="outside the B200 hot path"):
+        rd.FlowAccumulation(dem, "Rho8")
+
+
+# ---- the benchmark raster and the benchmark size -----------------------------------------------------------
+def test_device_terrain_generator_equals_its_cpu_restatement():
+    """bench.py --impl reference runs the reference on oracle.device_fbm(...): it must be the raster the GPU arm uses."""
+    import torch
+    L = _lib.lib()
+    for (h, w, y0, seed, q) in ((700, 1000, 0, 42, 0.0), (513, 4100, 12345, 7, 0.0), (300, 260, 70000, 42, 0.5)):
+        d = torch.empty((h, w), dtype=torch.float32, device="cuda")
+        _lib.check(L.rdb200_dev_generate_fbm_f32(d.data_ptr(), w, h, y0, seed, 12, q))
+        assert np.array_equal(d.cpu().numpy().view(np.uint32), oracle.device_fbm(h, w, seed=seed, quantum=q, y0=y0).view(np.uint32))
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="needs the compiled reference (about 20 s of CPU for 8192^2)")
+def test_fill_and_d8_accumulation_vs_reference_at_8192(checker):
+    """The benchmark workload at 8192^2 (67 Mcells) against the compiled reference: fill bit-exact, FA_D8 bit-exact."""
+    N = 8192
+    dem = oracle.device_fbm(N, N, seed=42)
+    f_ref = checker.fill_depressions(dem)
+    filled = np.asarray(rd.FillDepressions(R(dem)))
+    assert np.array_equal(filled, f_ref)
+    a_ref = checker.fa_d8(f_ref, ND)
+    assert np.array_equal(np.asarray(rd.FlowAccumulation(R(filled), "D8")), a_ref)

@@ -69,7 +69,9 @@ def test_argument_validation_matches_reference_behaviour():
     with pytest.raises(Exception, match="Invalid FlowAccumulation method"):
         rd.FlowAccumulation(dem, method="nope")
     with pytest.raises(Exception, match="outside the B200 hot path"):
-        rd.FlowAccumulation(dem, method="Quinn")
+        rd.FlowAccumulation(dem, method="Rho8")
+    with pytest.raises(Exception, match="requires an exponent"):
+        rd.FlowAccumulation(dem, method="Holmgren")
     with pytest.raises(Exception, match="must be of type 'float64'"):
         rd.FlowAccumulation(dem, method="D8", weights=rd.rdarray(np.ones((8, 8), np.float32), no_data=-1))
     with pytest.raises(Exception, match="Invalid FlowProportions method"):

@@ -122,3 +122,30 @@ def test_fill_is_min_over_paths_of_max(port):
             break
         W = new
     assert np.array_equal(W[1:-1, 1:-1], port.fill_depressions(dem))
+
+
+METRIC_CASES = [("D4", None), ("Quinn", None), ("Holmgren", 2.5), ("Holmgren", 0.7), ("Freeman", 1.1), ("Freeman", 4.0)]
+
+
+def test_remaining_flow_metrics_against_reference_outputs(port, golden):
+    """FM_D4 / FM_Quinn / FM_Holmgren / FM_Freeman and their FA_* against stored outputs of the
+    unmodified reference (tests/golden/make_golden.py::metrics)."""
+    g = golden["flow_metrics_ref"]
+    dems = {"beauford": golden["beauford_crop"]["resolved"], "s104": g["s104__resolved"]}
+    for name, dem in dems.items():
+        for m, e in METRIC_CASES:
+            k = f"{name}__{m}_{e}"
+            assert np.array_equal(port.fm_method(dem, ND, m, e).reshape(-1, 9)[::11], g[k + "__fm"]), k
+            assert np.array_equal(port.fa_method(dem, ND, m, e)[::3, ::3], g[k + "__fa"]), k
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no reference tree)")
+@pytest.mark.parametrize("method,exponent", METRIC_CASES)
+def test_remaining_flow_metrics_port_matches_compiled_reference_live(port, method, exponent):
+    R = oracle.ref()
+    dem = oracle.fbm_terrain(140, 190, seed=21, quantum=0.5)
+    dem[20:40, 30:70] = ND
+    assert np.array_equal(port.fm_method(dem, ND, method, exponent), R.fm_method(dem, ND, method, exponent))
+    assert np.array_equal(port.fa_method(dem, ND, method, exponent), R.fa_method(dem, ND, method, exponent))
+    wts = np.random.default_rng(3).random(dem.shape)
+    assert np.array_equal(port.fa_method(dem, ND, method, exponent, wts), R.fa_method(dem, ND, method, exponent, wts))

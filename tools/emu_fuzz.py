@@ -22,7 +22,7 @@ _lib.init(0); _lib.set_param("fill_use_tma", 0); _lib.set_param("fill_multigrid_
 spec = importlib.util.spec_from_file_location("gp", os.path.join(ROOT, "tests", "test_gpu_parity.py")); gp = importlib.util.module_from_spec(spec); spec.loader.exec_module(gp)
 O = oracle.best()
 seed0=int(sys.argv[1]); T=float(sys.argv[2])
-ALLSW=["fill_multigrid","fill_async","accum_async","accum_fused_prep","accum_walk_lanes","accum_agg","accum_tail","flats_uf_tiled","flowdirs_rolling"]
+ALLSW=["fill_multigrid","fill_vcycle","accum_fused_prep","accum_walk_lanes","flats_uf_tiled","flowdirs_rolling"]
 rng=np.random.default_rng(seed0); t0=time.time(); n=0; fails=0
 while time.time()-t0 < T:
     h=int(rng.integers(1,420)); w=int(rng.integers(1,520))

@@ -1,7 +1,7 @@
 """Fill timing / work counters for a list of rdb200_set_param configurations:
 
     python tools/fill_profile.py [N] [cfg ...]        cfg = "k=v,k=v" ("" = defaults)
-    e.g.  timeout 300 python tools/fill_profile.py 32768 "" fill_ordered=0 fill_async=1 fill_async=1,fill_ordered=0
+    e.g.  timeout 300 python tools/fill_profile.py 32768 "" fill_ordered=0 fill_multigrid=0 fill_vcycle=0
 
 Every configuration starts from the defaults, runs twice on the same N x N fBm DEM (seed 42) and reports the
 faster run; `same` compares the result with the first configuration's.  FP_FLAGS=--prof adds the in-tile counters.
@@ -14,8 +14,6 @@ import torch  # noqa: E402
 
 from richdem_b200 import _lib  # noqa: E402
 
-DEFAULTS = {"fill_ordered": 1, "fill_order_rounds": 0, "fill_max_iters": 0, "fill_use_tma": 1, "fill_rounds_per_sync": 16,
-            "fill_async": 0, "fill_async_spin": 0, "fill_async_thick": 0, "fill_multigrid": 0, "fill_multigrid_min": 0, "fill_vcycle": 0, "fill_profile": 0}
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 L = _lib.lib()
 _lib.init(0)
@@ -24,8 +22,7 @@ d = torch.empty((N, N), dtype=torch.float32, device="cuda")
 _lib.check(L.rdb200_dev_generate_fbm_f32(d.data_ptr(), N, N, 0, 42, 12, 0.0))
 ref = None
 for cfg in sys.argv[2:] or [""]:
-    for k, v in DEFAULTS.items():
-        _lib.set_param(k, v)
+    _lib.reset_params()
     for k, v in [a.split("=") for a in cfg.split(",") if a]:
         _lib.set_param(k, int(v))
     if "--prof" in os.environ.get("FP_FLAGS", ""):
@@ -44,5 +41,4 @@ for cfg in sys.argv[2:] or [""]:
           f"sweep_ms={best['ms_main_kernel']:.2f} rounds={best['fill_rounds']} visits={best['fill_tile_visits']} "
           f"({best['fill_tile_visits'] / nt:.2f} raster-eq) passes/visit={best['fill_tile_iters'] / max(1, best['fill_tile_visits']):.2f}",
           flush=True)
-for k, v in DEFAULTS.items():
-    _lib.set_param(k, v)
+_lib.reset_params()
