@@ -27,6 +27,8 @@
 // resolution (csrc/flats.cu), and FillState doubles as the row-band (multi-GPU) solver.
 #include "common.cuh"
 
+#include <chrono>
+
 namespace rdb {
 
 namespace {
@@ -73,6 +75,7 @@ struct FillDev {
   int edge_changed;  // bit0: raster row 1 changed, bit1: raster row H-2 changed
   int zmin_ord, zmax_ord;  // ordered-int min / max of the finite input elevations
   unsigned long long deferred;  // tile visits postponed by the level schedule
+  unsigned long long live_rounds;  // sweep launches that found a non-empty worklist
   // level-ordered admission (device-side feedback loop, see fill_admit_kernel)
   float level, step, step_min, level_max;
   int target, ordered;
@@ -97,6 +100,7 @@ struct FillArgs {
   int max_iters;
   int use_tma;
   int profile;
+  int *dirty;  // per tile: a visit wrote cells back since the flags were last cleared (V-cycle bookkeeping; may be null)
 };
 
 // ---- PTX helpers: mbarrier + TMA ----------------------------------------------------------
@@ -220,7 +224,10 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     RoundCtl *zp = &a.dev->proc[(r + 1) % 3];
     zp->count = 0;
     zp->take = 0;
-    if (n > 0) atomicAdd(&a.dev->visits, (unsigned long long)n);
+    if (n > 0) {
+      atomicAdd(&a.dev->visits, (unsigned long long)n);
+      a.dev->live_rounds++;
+    }
   }
   if (n == 0) return;
 
@@ -310,6 +317,7 @@ __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
         }
         if (nb >= 0) enqueue_tile(a, next, list_next, nb, sv, bits, sKey);
         if (tid == 0 && (fl & (3 << 9))) atomicOr(&a.dev->edge_changed, (fl >> 9) & 3);
+        if (tid == 0 && a.dirty) a.dirty[t] = 1;
       }
     }
     if (tid == 0) {
@@ -369,6 +377,19 @@ __global__ void __launch_bounds__(256) fill_seed_kernel(const FillArgs a, const 
   RoundCtl *cur = &a.dev->ctl[r % 3];
   int *list_cur = (r & 1) ? a.list1 : a.list0;
   enqueue_tile(a, cur, list_cur, tiles[i], r, SIDE_FULL, f2ord(-__int_as_float(0x7f800000)));
+}
+
+// tiles flagged on the device (prolongation, restriction into a coarse level): same as fill_seed_kernel without the
+// trip through the host
+__global__ void __launch_bounds__(256) fill_seed_flags_kernel(const FillArgs a, const int *__restrict__ flag, int ntiles,
+                                                               int *count) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles || !flag[t]) return;
+  const int r = a.round;
+  RoundCtl *cur = &a.dev->ctl[r % 3];
+  int *list_cur = (r & 1) ? a.list1 : a.list0;
+  enqueue_tile(a, cur, list_cur, t, r, SIDE_FULL, f2ord(-__int_as_float(0x7f800000)));
+  if (count) atomicAdd(count, 1);
 }
 
 // ---- layout kernels ----------------------------------------------------------------------
@@ -504,11 +525,18 @@ __global__ void __launch_bounds__(256) fill_maxpool_kernel(const float *__restri
 
 // V-cycle (fill_vcycle): restriction -- the coarse surface drops to the block maximum of the current fine surface
 // wherever that is lower (both are upper bounds of the answer for every cell of the block) ...
+// The coarse surface is the padded water-level array of the coarse level's own solver (pitch `cpitch`, cell (bx, by) at
+// (by + 1) * cpitch + bx + PADL); coarse tiles that hold a lowered cell -- and their neighbours when the cell sits on a
+// tile edge -- are flagged for that solver's next run.  `dirty` (may be null; used when k divides the tile shape): only
+// blocks inside fine tiles that were written since the last restriction are looked at.
 __global__ void __launch_bounds__(256) fill_restrict_kernel(const float *__restrict__ Wp, int pitch, int W, int H,
-                                                             float *Wc, int Wcw, int Hc, int k) {
+                                                             float *Wc, int cpitch, int Wcw, int Hc, int k,
+                                                             const int *__restrict__ dirty, int tilesX, int *ctile_flag,
+                                                             int ctilesX) {
   const int bx = blockIdx.x * blockDim.x + threadIdx.x;
   if (bx >= Wcw) return;
   for (int by = blockIdx.y; by < Hc; by += gridDim.y) {
+    if (dirty && !dirty[((by * k) / TY) * tilesX + (bx * k) / TX]) continue;
     float m = -__int_as_float(0x7f800000);
     for (int j = 0; j < k; j++) {
       const int y = by * k + j;
@@ -518,8 +546,17 @@ __global__ void __launch_bounds__(256) fill_restrict_kernel(const float *__restr
         if (x < W) m = fmaxf(m, __ldcg(Wp + (size_t)(y + 1) * pitch + x + PADL));
       }
     }
-    float *o = Wc + (size_t)by * Wcw + bx;
-    if (m < *o) *o = m;
+    float *o = Wc + (size_t)(by + 1) * cpitch + bx + PADL;
+    if (m < *o && bx > 0 && by > 0 && bx < Wcw - 1 && by < Hc - 1) {  // border blocks stay pinned at their elevation
+      *o = m;
+      const int ty0 = (by - 1) / TY, ty1 = (by + 1) / TY, tx0 = (bx - 1) / TX, tx1 = (bx + 1) / TX;
+      ctile_flag[ty0 * ctilesX + tx0] = 1;
+      if (tx1 != tx0) ctile_flag[ty0 * ctilesX + tx1] = 1;
+      if (ty1 != ty0) {
+        ctile_flag[ty1 * ctilesX + tx0] = 1;
+        if (tx1 != tx0) ctile_flag[ty1 * ctilesX + tx1] = 1;
+      }
+    }
   }
 }
 
@@ -547,26 +584,55 @@ __global__ void __launch_bounds__(256) fill_blockmax_kernel(const float *__restr
 }
 
 // ... and prolongation: every interior fine cell drops to its block's (re-relaxed) coarse level where that is lower;
-// the tiles that hold such a cell are flagged so that the sweep can be told to look at them again.
+// the tiles that hold such a cell -- and the neighbouring tiles whose apron it is part of -- are flagged so that the
+// sweep looks at them again.  The coarse surface is read at Wc[(by + coff_y) * cpitch + bx + coff_x] (a compact array:
+// offsets 0; the coarse solver's padded array: 1 and PADL).  One block per fine tile; `cdirty` (may be null): tiles
+// whose blocks all lie in coarse tiles that the coarse relaxation did not write are skipped.
 __global__ void __launch_bounds__(256) fill_prolong_kernel(float *Wp, int pitch, int W, int H, const float *__restrict__ Wc,
-                                                            int Wcw, int k, int *tile_flag, int tilesX, int yoff) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x < 1 || x >= W - 1) return;
-  for (int y = 1 + blockIdx.y; y < H - 1; y += gridDim.y) {
-    const float l = __ldg(Wc + (size_t)((y + yoff) / k) * Wcw + x / k);
+                                                            int cpitch, int coff_x, int coff_y, int k, int *tile_flag,
+                                                            int tilesX, int yoff, const int *__restrict__ cdirty,
+                                                            int ctilesX) {
+  const int t = blockIdx.x;
+  const int tyT = t / tilesX, txT = t - tyT * tilesX;
+  const int x0 = txT * TX, y0 = tyT * TY;
+  if (cdirty) {
+    // coarse cells of this tile: columns x0/k .. (x0+TX-1)/k, rows (y0+yoff)/k .. ; at most 2 x 2 coarse tiles
+    const int cx0 = (x0 / k) / TX, cx1 = ((x0 + TX - 1) / k) / TX;
+    const int cy0 = ((y0 + yoff) / k) / TY, cy1 = ((y0 + TY - 1 + yoff) / k) / TY;
+    bool any = false;
+    for (int cy = cy0; cy <= cy1; cy++)
+      for (int cx = cx0; cx <= cx1; cx++) any |= cdirty[cy * ctilesX + cx] != 0;
+    if (!any) return;
+  }
+  bool lowered = false, lo_n = false, lo_s = false, lo_w = false, lo_e = false;
+  for (int c = threadIdx.x; c < TX * TY; c += blockDim.x) {
+    const int ly = c / TX, lx = c - ly * TX;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1) continue;
+    const float l = __ldg(Wc + (size_t)((y + yoff) / k + coff_y) * cpitch + x / k + coff_x);
     float *w = Wp + (size_t)(y + 1) * pitch + x + PADL;
     if (l < *w) {
       *w = l;
-      // a lowered cell on a tile edge is also part of the neighbouring tiles' aprons: wake every tile
-      // that reads it (x, y are interior cells, so x-1, x+1, y-1, y+1 stay inside the raster)
-      const int ty0 = (y - 1) / TY, ty1 = (y + 1) / TY, tx0 = (x - 1) / TX, tx1 = (x + 1) / TX;
-      tile_flag[ty0 * tilesX + tx0] = 1;
-      if (tx1 != tx0) tile_flag[ty0 * tilesX + tx1] = 1;
-      if (ty1 != ty0) {
-        tile_flag[ty1 * tilesX + tx0] = 1;
-        if (tx1 != tx0) tile_flag[ty1 * tilesX + tx1] = 1;
-      }
+      lowered = true;
+      lo_n |= ly == 0;
+      lo_s |= ly == TY - 1;
+      lo_w |= lx == 0;
+      lo_e |= lx == TX - 1;
     }
+  }
+  // a lowered cell on a tile edge is also part of the neighbouring tiles' aprons: wake every tile that reads it
+  if (lowered) {
+    const int tilesY = (H + TY - 1) / TY;
+    tile_flag[t] = 1;
+    const bool n_ok = tyT > 0, s_ok = tyT < tilesY - 1, w_ok = txT > 0, e_ok = txT < tilesX - 1;
+    if (lo_n && n_ok) tile_flag[t - tilesX] = 1;
+    if (lo_s && s_ok) tile_flag[t + tilesX] = 1;
+    if (lo_w && w_ok) tile_flag[t - 1] = 1;
+    if (lo_e && e_ok) tile_flag[t + 1] = 1;
+    if (lo_n && lo_w && n_ok && w_ok) tile_flag[t - tilesX - 1] = 1;
+    if (lo_n && lo_e && n_ok && e_ok) tile_flag[t - tilesX + 1] = 1;
+    if (lo_s && lo_w && s_ok && w_ok) tile_flag[t + tilesX - 1] = 1;
+    if (lo_s && lo_e && s_ok && e_ok) tile_flag[t + tilesX + 1] = 1;
   }
 }
 
@@ -625,6 +691,7 @@ struct FillState {
   int W = 0, H = 0, pitch = 0, rows = 0, tilesX = 0, tilesY = 0;
   DevBuf<float> Zp, Wp;
   DevBuf<int> list0, list1, plist, stamp, sides, keys;
+  DevBuf<int> dirty, tflag;  // V-cycle bookkeeping: tiles written since the last look / tiles to wake (both per tile)
   float zmin = 0.f, zmax = 0.f;
   bool first_run = true;
   bool ordered = false;
@@ -634,7 +701,9 @@ struct FillState {
   CUtensorMap mapW, mapZ;
   int round = 0;
   int grid = 0;
-  int64_t rounds_run = 0;
+  int64_t rounds_run = 0;   // sweep launches
+  int64_t live_rounds = 0;  // ... that found a non-empty worklist (the dependent rounds of the flood)
+  int64_t visits_seen = 0;  // tile visits so far (as of the last read-back)
   bool still_active = false;
   int64_t sched_round = 0;
 
@@ -820,6 +889,7 @@ struct FillState {
     a.use_tma = (int)c.params.fill_use_tma;
     a.profile = (int)c.params.fill_profile;
     a.level = __builtin_inff();
+    a.dirty = dirty.p;  // null unless track_dirty() was called
     return a;
   }
 
@@ -867,7 +937,9 @@ struct FillState {
       if (round > (1 << 30)) fail("fill: round counter overflow");
     }
     if (!still_active) first_run = false;
-    c.stats.fill_rounds = rounds_run;
+    live_rounds = (int64_t)hd->live_rounds;
+    visits_seen = (int64_t)hd->visits;
+    c.stats.fill_rounds = live_rounds;
     c.stats.fill_tile_visits = (int64_t)hd->visits;
     c.stats.fill_tile_iters = (int64_t)hd->iters;
     c.stats.fill_tile_cells = TX * TY;
@@ -882,14 +954,44 @@ struct FillState {
   }
 
   // V-cycle plumbing (fill_vcycle): see fill_depressions_level
-  void restrict_to(float *d_wc, int wc, int hc, int k) {
+  void track_dirty() {  // from now on the sweep notes which tiles it wrote
     Ctx &c = ctx();
-    dim3 blk(256), grd((unsigned)((wc + 255) / 256), (unsigned)(hc < 4096 ? hc : 4096));
-    fill_restrict_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, pitch, W, H, d_wc, wc, hc, k);
+    const size_t nt = (size_t)tilesX * tilesY;
+    dirty.alloc(nt);
+    RDB_CK(cudaMemsetAsync(dirty.p, 0, nt * sizeof(int), c.stream));
+  }
+  void clear_dirty() {
+    if (dirty.p) RDB_CK(cudaMemsetAsync(dirty.p, 0, (size_t)tilesX * tilesY * sizeof(int), ctx().stream));
+  }
+  // queue the tiles flagged in tflag for the next run (no host round trip); d_count (optional) receives how many
+  void seed_from_flags(int *d_count = nullptr) {
+    Ctx &c = ctx();
+    const int nt = tilesX * tilesY;
+    FillArgs a = make_args();
+    a.round = round;
+    fill_seed_flags_kernel<<<(nt + 255) / 256, 256, 0, c.stream>>>(a, tflag.p, nt, d_count);
     RDB_CK(cudaGetLastError());
     count_launch();
   }
-  // returns the number of tiles that were lowered (they are queued for the next run)
+  void clear_flags() {
+    const size_t nt = (size_t)tilesX * tilesY;
+    if (!tflag.p) tflag.alloc(nt);
+    RDB_CK(cudaMemsetAsync(tflag.p, 0, nt * sizeof(int), ctx().stream));
+  }
+  // restriction of THIS (fine) level's surface into the coarse level's solver `cs` (its padded water levels drop to the
+  // k x k block maxima where those are lower; the coarse tiles touched are queued for cs's next run)
+  void restrict_into(FillState &cs, int k) {
+    Ctx &c = ctx();
+    cs.clear_flags();
+    const bool selective = dirty.p && TX % k == 0 && TY % k == 0;
+    dim3 blk(256), grd((unsigned)((cs.W + 255) / 256), (unsigned)(cs.H < 4096 ? cs.H : 4096));
+    fill_restrict_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, pitch, W, H, cs.Wp.p, cs.pitch, cs.W, cs.H, k,
+                                                    selective ? dirty.p : nullptr, tilesX, cs.tflag.p, cs.tilesX);
+    RDB_CK(cudaGetLastError());
+    count_launch();
+    cs.seed_from_flags();
+    clear_dirty();
+  }
   void blockmax_into(float *d_out, int wc, int hc, int k, int yoff, int y_lo, int y_hi) {
     Ctx &c = ctx();
     dim3 blk(256), grd((unsigned)((wc + 255) / 256), (unsigned)((y_hi - y_lo) / k + 2 < 4096 ? (y_hi - y_lo) / k + 2 : 4096));
@@ -897,23 +999,23 @@ struct FillState {
     RDB_CK(cudaGetLastError());
     count_launch();
   }
-  size_t prolong_from(const float *d_wc, int wc, int k, int yoff = 0) {
+  // prolongation from a coarse surface stored with row pitch `cpitch` and first cell at (coff_x, coff_y); `cdirty`
+  // (optional, with its tile-grid width): coarse tiles written by the coarse relaxation -- everything else is skipped.
+  // d_count (optional): device counter that receives the number of tiles queued.
+  void prolong_from(const float *d_wc, int cpitch, int coff_x, int coff_y, int k, int yoff = 0, const int *cdirty = nullptr,
+                    int ctilesX = 0, int *d_count = nullptr) {
     Ctx &c = ctx();
-    const size_t nt = (size_t)tilesX * tilesY;
-    DevBuf<int> flag(nt);
-    RDB_CK(cudaMemsetAsync(flag.p, 0, nt * sizeof(int), c.stream));
-    dim3 blk(256), grd((unsigned)((W + 255) / 256), (unsigned)(H < 4096 ? H : 4096));
-    fill_prolong_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, pitch, W, H, d_wc, wc, k, flag.p, tilesX, yoff);
+    clear_flags();
+    const int nt = tilesX * tilesY;
+    fill_prolong_kernel<<<nt, 256, 0, c.stream>>>(Wp.p, pitch, W, H, d_wc, cpitch, coff_x, coff_y, k, tflag.p, tilesX, yoff,
+                                                  cdirty, ctilesX);
     RDB_CK(cudaGetLastError());
     count_launch();
-    std::vector<int> hf(nt);
-    RDB_CK(cudaMemcpyAsync(hf.data(), flag.p, nt * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-    RDB_CK(cudaStreamSynchronize(c.stream));
-    std::vector<int> tiles;
-    for (size_t t = 0; t < nt; t++)
-      if (hf[t]) tiles.push_back((int)t);
-    seed_worklist(tiles);
-    return tiles.size();
+    seed_from_flags(d_count);
+  }
+  void prolong_from_level(FillState &cs, int k) {
+    prolong_from(cs.Wp.p, cs.pitch, PADL, 1, k, 0, cs.dirty.p, cs.tilesX);
+    cs.clear_dirty();
   }
 
   void read_row(int y, float *d_row) {
@@ -1029,29 +1131,57 @@ static void fill_depressions_level(float *d_dem, int w, int h, int depth) {
       // and handed back (prolongation: fine = min(fine, lifted)).  Restriction and coarse relaxation keep every coarse
       // value an upper bound of the answer for all cells of its block, so the fine surface stays an upper bound and
       // still relaxes to exactly W*.
+      // The coarse level keeps ONE solver for all corrections (cst): restriction lowers its padded surface in place
+      // and queues the coarse tiles it touched, its relaxation notes the tiles it writes, and the prolongation only
+      // looks at the fine tiles below those -- a correction costs what it changes, not three passes over the raster.
+      FillState cst;
+      cst.begin(zc.p, wc, hc, coarse.p, wc, 1);  // start: the coarse fill itself (already a fixed point)
+      cst.run();                                  // (drains the initial all-tiles worklist; nothing moves)
+      cst.track_dirty();
+      st.track_dirty();
+      int64_t coarse_visits0 = c.stats.fill_tile_visits, coarse_iters0 = c.stats.fill_tile_iters;
+      const bool trace = c.params.fill_trace != 0;  // per-cycle timeline on stderr (adds stream syncs)
+      auto now_ms = [&]() {
+        RDB_CK(cudaStreamSynchronize(c.stream));
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+      };
       for (int cycle = 0;; cycle++) {
-        if (!(st.run(every) & 4)) break;  // converged
-        if (cycle >= 1000) {              // safety net: plain relaxation to the end
+        const double t0 = trace ? now_ms() : 0;
+        const int64_t v0 = st.visits_seen, r0 = st.live_rounds;
+        const bool active = (st.run(every) & 4) != 0;
+        const double t1 = trace ? now_ms() : 0;
+        if (trace)
+          fprintf(stderr, "[fill trace] depth %d cycle %d: fine run %.3f ms (%lld live rounds, %lld visits)%s\n", depth, cycle,
+                  t1 - t0, (long long)(st.live_rounds - r0), (long long)(st.visits_seen - v0), active ? "" : " -> converged");
+        if (!active) break;
+        if (cycle >= 1000) {  // safety net: plain relaxation to the end
           st.run();
           break;
         }
-        st.restrict_to(coarse.p, wc, hc, k);
-        {
-          FillState cst;  // coarse relaxation from the restricted surface (pool = 1 "lift": start from that array)
-          cst.begin(zc.p, wc, hc, coarse.p, wc, 1);
-          cst.run();
-          cst.finish(coarse.p);
-          RDB_CK(cudaStreamSynchronize(c.stream));
-          extra.fill_rounds += c.stats.fill_rounds;  // cst's own counters (FillState::run reports absolute values)
-          extra.fill_tile_visits += c.stats.fill_tile_visits;
-          extra.fill_tile_iters += c.stats.fill_tile_iters;
+        st.restrict_into(cst, k);
+        const double t2 = trace ? now_ms() : 0;
+        const int64_t cv0 = cst.visits_seen, cr0 = cst.live_rounds;
+        cst.run();
+        const double t3 = trace ? now_ms() : 0;
+        st.prolong_from_level(cst, k);
+        if (trace) {
+          const double t4 = now_ms();
+          fprintf(stderr, "[fill trace] depth %d cycle %d: restrict %.3f ms, coarse run %.3f ms (%lld live rounds, %lld visits), "
+                          "prolong %.3f ms\n", depth, cycle, t2 - t1, t3 - t2, (long long)(cst.live_rounds - cr0),
+                  (long long)(cst.visits_seen - cv0), t4 - t3);
         }
-        st.prolong_from(coarse.p, wc, k);
       }
+      cst.run(1);  // refresh the coarse solver's counters in c.stats (FillState::run reports absolute values)
+      extra.fill_rounds += cst.live_rounds;
+      extra.fill_tile_visits += c.stats.fill_tile_visits;
+      extra.fill_tile_iters += c.stats.fill_tile_iters;
+      (void)coarse_visits0;
+      (void)coarse_iters0;
+      st.run(1);  // and the fine solver's (no tile is active: an empty launch)
     }
     st.finish(d_dem);
     RDB_CK(cudaStreamSynchronize(c.stream));
-    c.stats.fill_rounds = st.rounds_run + extra.fill_rounds;
+    c.stats.fill_rounds = st.live_rounds + extra.fill_rounds;
     c.stats.fill_tile_visits += extra.fill_tile_visits;
     c.stats.fill_tile_iters += extra.fill_tile_iters;
     return;
@@ -1209,8 +1339,14 @@ int rdb200_dev_fill_prolong(rdb200_fill_state *state, const float *d_coarse, int
   RDB_CAPI_TRY
   if (!state) rdb::fail("fill_prolong: null state");
   if (!d_coarse || pool < 2 || row_offset < 0) rdb::fail("fill_prolong: bad arguments");
-  const size_t n = state->st.prolong_from(d_coarse, coarse_width, pool, row_offset);
-  if (tiles_lowered) *tiles_lowered = (int32_t)n;
+  rdb::Ctx &c = rdb::ctx();
+  rdb::DevBuf<int> cnt(1);
+  RDB_CK(cudaMemsetAsync(cnt.p, 0, sizeof(int), c.stream));
+  state->st.prolong_from(d_coarse, coarse_width, 0, 0, pool, row_offset, nullptr, 0, cnt.p);
+  int *h = (int *)c.pinned;
+  RDB_CK(cudaMemcpyAsync(h, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  if (tiles_lowered) *tiles_lowered = *h;
   RDB_CAPI_END
 }
 

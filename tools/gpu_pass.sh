@@ -1,0 +1,37 @@
+#!/bin/bash
+# One gpurun call: GPU parity suite, fill variants with the V-cycle timeline, bench, ncu launch list, reference arm.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_pass.sh 32768 tag'
+# Every step runs under its own `timeout` and writes to gpurun_out/<tag>/.
+N=${1:-32768}
+TAG=${2:-pass}
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+cd "$(dirname "$0")/.."
+
+step() {  # name, seconds, command...
+  local name=$1 secs=$2
+  shift 2
+  echo "=== $name" | tee -a "$OUT/summary.txt"
+  local t0=$(date +%s)
+  timeout "$secs" "$@" >"$OUT/$name.log" 2>&1
+  local rc=$?
+  echo "rc=$rc ($(( $(date +%s) - t0 )) s)" | tee -a "$OUT/summary.txt"
+  tail -n "${TAILN:-12}" "$OUT/$name.log" | cut -c1-1500 | tee -a "$OUT/summary.txt"
+}
+
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv >"$OUT/gpu.txt" 2>&1
+if [ -z "$SKIP_TESTS" ]; then
+  step pytest_gpu 900 python -m pytest tests -m gpu -x -q
+fi
+TAILN=40 step fill_trace 300 env RDB200_PARAMS="fill_trace=1" python tools/fill_profile.py "$N" ""
+step fill_variants 400 python tools/fill_profile.py "$N" "" "fill_vcycle=4" "fill_vcycle=16" "fill_vcycle=0" "fill_multigrid=4" "fill_multigrid=4,fill_vcycle=16" "fill_multigrid=0"
+step flats_profile 240 env RDB200_PROFILE=1 python tools/flats_profile.py "$N"
+TAILN=3 step bench 600 python bench.py --steps 5 --warmup 3
+grep -a '"metric"' "$OUT/bench.log" | tail -1 > "$OUT/bench.json"
+step ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file "$OUT/launches.csv" \
+  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-configs --no-verify
+if [ -n "$REF_SIZE" ]; then
+  TAILN=3 step bench_reference 900 python bench.py --impl reference --steps 1 --warmup 0 --ref-size "$REF_SIZE"
+  grep -a '"impl"' "$OUT/bench_reference.log" | tail -1 > "$OUT/bench_reference.json"
+fi
+echo "done" | tee -a "$OUT/summary.txt"
