@@ -192,6 +192,10 @@ void rdb200_shutdown(void) {
   cudaEventDestroy(c.evk0);
   cudaEventDestroy(c.evk1);
   cudaStreamDestroy(c.own_stream);
+  for (int k = 0; k < 2; k++)
+    if (c.aux_stream[k]) cudaStreamDestroy(c.aux_stream[k]);
+  for (int k = 0; k < 3; k++)
+    if (c.aux_event[k]) cudaEventDestroy(c.aux_event[k]);
   const Params keep = c.params;  // rdb200_set_param switches are process settings: they survive a re-init
   c = Ctx();
   c.params = keep;
@@ -235,6 +239,8 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "accum_walk_lanes") p.accum_walk_lanes = value;
   else if (n == "accum_fused_prep") p.accum_fused_prep = value;
   else if (n == "flats_tiled") p.flats_tiled = value;
+  else if (n == "flats_pair") p.flats_pair = value;
+  else if (n == "flats_fused_classify") p.flats_fused_classify = value;
   else if (n == "fill_multigrid") p.fill_multigrid = value;
   else if (n == "fill_multigrid_min") p.fill_multigrid_min = value;
   else if (n == "fill_vcycle") p.fill_vcycle = value;

@@ -67,6 +67,8 @@ struct Params {
   int64_t fill_multigrid_min = 0;  // smallest raster side that still gets a coarse level (0: 1024)
   int64_t flowdirs_rolling = 1;  // d8_flow_directions with a rolling three-row register window (W % 4 == 0)
   int64_t flats_uf_tiled = 1;  // union-find: unite inside 64x16 tiles in shared memory first, then across tile seams
+  int64_t flats_fused_classify = 1;  // FindFlats + FindFlatEdges in one shared-memory window pass (single-GPU path)
+  int64_t flats_pair = 1;    // the two gradient solves run side by side on two streams
   int64_t flats_tiled = 1;   // flat-resolution gradients by the tile engine (0: one cooperative BFS launch each)
   int64_t accum_packed = 1;  // unit-weight D8: accumulator and donor count share one 64-bit word
   int64_t accum_fused_prep = 1;   // unit-weight D8: flow codes + donor counts + sole-donor bits in one rolling-window pass
@@ -88,6 +90,8 @@ struct Ctx {
   cudaStream_t stream = nullptr;      // stream all work runs on
   cudaStream_t own_stream = nullptr;  // the library's default stream
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};  // side streams for solves that run side by side (flat gradients)
+  cudaEvent_t aux_event[3] = {nullptr, nullptr, nullptr};
   std::vector<WsBlock> ws;
   void *pinned = nullptr;  // small pinned scratch for read-backs
   size_t pinned_bytes = 0;
@@ -146,6 +150,7 @@ struct KernelTimer {
 // ---- stage entry points implemented in the .cu files (device pointers, ctx stream) -------
 void fill_depressions_dev(float *d_dem, int w, int h);
 void geodesic_distance_dev(const uint8_t *d_open, int open_bit, float *d_w_inout, int w, int h);
+void geodesic_distance_pair_dev(const uint8_t *d_open, int open_bit, float *d_wa, float *d_wb, int w, int h);
 rdb200_fill_state *new_band_distance_state(const uint8_t *d_open, int open_bit, const float *d_winit, int w, int h,
                                            int ghost_top, int ghost_bottom);
 void finish_band_distance_state(rdb200_fill_state *s, float *d_out);

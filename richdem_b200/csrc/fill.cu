@@ -893,55 +893,77 @@ struct FillState {
     return a;
   }
 
+  // One batch of `per_sync` sweep rounds plus the read-back of the control block, queued on the context's current
+  // stream / pinned scratch (two solvers can be driven side by side on two streams: see geodesic_distance_pair_dev).
+  bool timed = true;      // false: do not touch the context's timing events (solver driven on a side stream)
+  int batch_edge = 0;     // edge_changed bits read back by the last collect()
+  void launch_batch(int per_sync) {
+    Ctx &c = ctx();
+    FillArgs a = make_args();
+    if (timed) RDB_CK(cudaEventRecord(c.evk0, c.stream));
+    for (int k = 0; k < per_sync; k++) {
+      a.round = round;
+      // level-ordered admission while the schedule lasts; afterwards every active tile is processed
+      if (ordered && sched_round < (int64_t)levels.size()) {
+        a.level = levels[(size_t)sched_round];
+        a.use_proc = 1;
+        fill_admit_kernel<<<c.num_sms * 2, 256, 0, c.stream>>>(a);
+        c.stats.kernel_launches++;
+      } else {
+        a.level = __builtin_inff();
+        a.use_proc = 0;
+      }
+      sched_round++;
+      if (step_mode) fill_sweep_kernel<1><<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
+      else fill_sweep_kernel<0><<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
+      round++;
+    }
+    if (timed) RDB_CK(cudaEventRecord(c.evk1, c.stream));
+    RDB_CK(cudaGetLastError());
+    RDB_CK(cudaMemcpyAsync(c.pinned, dev.p, sizeof(FillDev), cudaMemcpyDeviceToHost, c.stream));
+    c.stats.kernel_launches += per_sync;
+    rounds_run += per_sync;
+    if (round > (1 << 30)) fail("fill: round counter overflow");
+  }
+  // waits for the batch; returns whether tiles are still active
+  bool collect() {
+    Ctx &c = ctx();
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    if (timed) {
+      float t = 0;
+      RDB_CK(cudaEventElapsedTime(&t, c.evk0, c.evk1));
+      c.stats.ms_main_kernel += t;  // device time of the sweep launches only (read-back excluded)
+    }
+    const FillDev *hd = (const FillDev *)c.pinned;
+    still_active = hd->ctl[round % 3].count != 0;
+    if (!still_active) first_run = false;
+    live_rounds = (int64_t)hd->live_rounds;
+    visits_seen = (int64_t)hd->visits;
+    iters_seen = (int64_t)hd->iters;
+    batch_edge = hd->edge_changed;
+    return still_active;
+  }
+  int64_t iters_seen = 0;
+
   // max_rounds > 0: stop after about that many rounds even if tiles are still active (bit 2 of the
   // result then says so); the caller exchanges halos and calls run again
   int run(int64_t max_rounds = 0) {
     Ctx &c = ctx();
     int64_t rounds_this_call = 0;
-    FillArgs a = make_args();
     int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 16);
     if (max_rounds > 0 && max_rounds < per_sync) per_sync = (int)max_rounds;  // a short leash (V-cycles) is honoured exactly
-    FillDev *hd = (FillDev *)c.pinned;
     RDB_CK(cudaMemsetAsync(&dev.p->edge_changed, 0, sizeof(int), c.stream));
     for (;;) {
-      KernelTimer kt;  // device time of the sweep launches only (read-back excluded)
-      for (int k = 0; k < per_sync; k++) {
-        a.round = round;
-        // level-ordered admission while the schedule lasts; afterwards every active tile is processed
-        if (ordered && sched_round < (int64_t)levels.size()) {
-          a.level = levels[(size_t)sched_round];
-          a.use_proc = 1;
-          fill_admit_kernel<<<c.num_sms * 2, 256, 0, c.stream>>>(a);
-          c.stats.kernel_launches++;
-        } else {
-          a.level = __builtin_inff();
-          a.use_proc = 0;
-        }
-        sched_round++;
-        if (step_mode) fill_sweep_kernel<1><<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
-        else fill_sweep_kernel<0><<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
-        round++;
-      }
-      kt.stop_async();
-      RDB_CK(cudaGetLastError());
-      RDB_CK(cudaMemcpyAsync(hd, dev.p, sizeof(FillDev), cudaMemcpyDeviceToHost, c.stream));
-      RDB_CK(cudaStreamSynchronize(c.stream));
-      c.stats.ms_main_kernel += kt.ms();
-      // rounds that found an empty worklist are not counted as launches of interest
-      c.stats.kernel_launches += per_sync;
-      rounds_run += per_sync;
+      launch_batch(per_sync);
+      collect();
       rounds_this_call += per_sync;
-      still_active = hd->ctl[round % 3].count != 0;
       if (!still_active) break;
       if (max_rounds > 0 && rounds_this_call >= max_rounds) break;
-      if (round > (1 << 30)) fail("fill: round counter overflow");
     }
-    if (!still_active) first_run = false;
-    live_rounds = (int64_t)hd->live_rounds;
-    visits_seen = (int64_t)hd->visits;
+    const FillDev *hd = (const FillDev *)c.pinned;
     c.stats.fill_rounds = live_rounds;
-    c.stats.fill_tile_visits = (int64_t)hd->visits;
-    c.stats.fill_tile_iters = (int64_t)hd->iters;
+    c.stats.fill_tile_visits = visits_seen;
+    c.stats.fill_tile_iters = iters_seen;
     c.stats.fill_tile_cells = TX * TY;
     if (c.params.fill_profile) {
       fprintf(stderr, "[fill profile] deferred=%llu visits=%llu iters=%llu block_updates=%llu (%.1f%% of 256/iter) warp_updates=%llu (%.1f%% of 8/iter) idle_visits=%llu hist(1,2,3-4,5-8,9-16,17-32,33-64,65+)=",
@@ -950,7 +972,7 @@ struct FillState {
       for (int k = 0; k < 8; k++) fprintf(stderr, "%llu ", hd->iter_hist[k]);
       fprintf(stderr, "\n");
     }
-    return hd->edge_changed | (still_active ? 4 : 0);
+    return batch_edge | (still_active ? 4 : 0);
   }
 
   // V-cycle plumbing (fill_vcycle): see fill_depressions_level
@@ -1089,6 +1111,73 @@ void geodesic_distance_dev(const uint8_t *d_open, int open_bit, float *d_w_inout
   c.stats = saved;
   c.stats.kernel_launches = launches;
   c.stats.flat_bfs_levels += rounds;
+}
+
+// Two independent distance solves (the away and the towards gradient of the flat resolution) side by side: each is a
+// chain of short dependent rounds with few active tiles, i.e. latency-bound, so their rounds are issued on two streams
+// and the SMs run whatever CTAs of either solve have work.  Results overwrite d_wa / d_wb.
+void geodesic_distance_pair_dev(const uint8_t *d_open, int open_bit, float *d_wa, float *d_wb, int w, int h) {
+  Ctx &c = ctx();
+  if (!c.aux_stream[0]) {
+    RDB_CK(cudaStreamCreateWithFlags(&c.aux_stream[0], cudaStreamNonBlocking));
+    RDB_CK(cudaStreamCreateWithFlags(&c.aux_stream[1], cudaStreamNonBlocking));
+    RDB_CK(cudaEventCreateWithFlags(&c.aux_event[0], cudaEventDisableTiming));
+    RDB_CK(cudaEventCreateWithFlags(&c.aux_event[1], cudaEventDisableTiming));
+    RDB_CK(cudaEventCreateWithFlags(&c.aux_event[2], cudaEventDisableTiming));
+  }
+  const rdb200_stats saved = c.stats;
+  cudaStream_t main_stream = c.stream;
+  void *main_pinned = c.pinned;
+  // the side streams start after everything queued on the main stream so far
+  RDB_CK(cudaEventRecord(c.aux_event[2], main_stream));
+  FillState st[2];
+  float *wbuf[2] = {d_wa, d_wb};
+  auto lane = [&](int k, auto &&fn) {  // run fn with lane k's stream and its own slot of the pinned scratch
+    c.stream = c.aux_stream[k];
+    c.pinned = (char *)main_pinned + 8192 * (k + 1);
+    try {
+      fn(st[k]);
+    } catch (...) {
+      c.stream = main_stream;
+      c.pinned = main_pinned;
+      throw;
+    }
+    c.stream = main_stream;
+    c.pinned = main_pinned;
+  };
+  static_assert(sizeof(FillDev) <= 8192, "pinned slot");
+  try {
+    for (int k = 0; k < 2; k++) {
+      RDB_CK(cudaStreamWaitEvent(c.aux_stream[k], c.aux_event[2], 0));
+      lane(k, [&](FillState &s) {
+        s.timed = false;
+        s.begin_dist(d_open, open_bit, wbuf[k], w, h);
+      });
+    }
+    const int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 16);
+    bool live[2] = {true, true};
+    while (live[0] || live[1]) {
+      for (int k = 0; k < 2; k++)
+        if (live[k]) lane(k, [&](FillState &s) { s.launch_batch(per_sync); });
+      for (int k = 0; k < 2; k++)
+        if (live[k]) lane(k, [&](FillState &s) { live[k] = s.collect(); });
+    }
+    for (int k = 0; k < 2; k++) {
+      lane(k, [&](FillState &s) { s.finish(wbuf[k]); });
+      RDB_CK(cudaEventRecord(c.aux_event[k], c.aux_stream[k]));
+      RDB_CK(cudaStreamWaitEvent(main_stream, c.aux_event[k], 0));
+    }
+  } catch (...) {
+    cudaStreamSynchronize(c.aux_stream[0]);
+    cudaStreamSynchronize(c.aux_stream[1]);
+    throw;
+  }
+  RDB_CK(cudaStreamSynchronize(c.aux_stream[0]));  // the solvers' buffers are released when `st` goes out of scope
+  RDB_CK(cudaStreamSynchronize(c.aux_stream[1]));
+  const int64_t launches = c.stats.kernel_launches;
+  c.stats = saved;
+  c.stats.kernel_launches = launches;
+  c.stats.flat_bfs_levels += st[0].live_rounds + st[1].live_rounds;
 }
 
 // fill_multigrid = k (off by default; prepared for round 2): the flood does not have to start from +inf.  ANY

@@ -39,6 +39,7 @@ struct FlatDev {
   LevelCtl ctl[3];
   int n_low, n_high, n_flat, n_raised;
   int rounds_done;
+  int dist_overflow;  // a geodesic distance reached 2^24, where float steps of 1 stop being exact
 };
 
 // a3: FindFlats
@@ -100,6 +101,97 @@ __global__ void __launch_bounds__(256) flats_edges_kernel(const float *__restric
   if (threadIdx.x == 0) {
     if (nl) atomicAdd(&dev->n_low, nl);
     if (nh) atomicAdd(&dev->n_high, nh);
+  }
+}
+
+// a3 + a4 in one pass (single-GPU path): a block owns a 128 x 32 window, stages the elevations with a two-cell rim in
+// shared memory (every DEM row is fetched once per block instead of ~18 scalar loads per cell through L1/L2), classifies
+// the window plus a one-cell rim (the edge rules look at the neighbours' IS_A_FLAT bit), then derives the edge bits and
+// stores four flag bytes per thread.  Cells outside the raster are staged as NaN / class 0, which every comparison of the
+// two rules treats like "skip" (the reference bounds-checks instead, Barnes2014.hpp:337-341).
+constexpr int CE_TX = 128, CE_TY = 32;
+__global__ void __launch_bounds__(256) flats_classify_edges_kernel(const float *__restrict__ dem, uint8_t *__restrict__ ft,
+                                                                    int W, int H, float nodata, FlatDev *dev) {
+  constexpr int DW = CE_TX + 4, DH = CE_TY + 4;  // staged elevations
+  constexpr int CW = CE_TX + 2, CH = CE_TY + 2;  // classified region
+  __shared__ float sD[DH][DW];
+  __shared__ uint8_t sC[CH][CW + 2];
+  const int x0 = blockIdx.x * CE_TX, y0 = blockIdx.y * CE_TY;
+  const float qnan = __int_as_float(0x7fc00000);
+  for (int k = threadIdx.x; k < DW * DH; k += 256) {
+    const int r = k / DW, cidx = k - r * DW;
+    const int x = x0 - 2 + cidx, y = y0 - 2 + r;
+    sD[r][cidx] = (x >= 0 && y >= 0 && x < W && y < H) ? __ldg(dem + (size_t)y * W + x) : qnan;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < CW * CH; k += 256) {
+    const int r = k / CW, cidx = k - r * CW;
+    const int x = x0 - 1 + cidx, y = y0 - 1 + r;
+    uint8_t f = 0;
+    if (x >= 0 && y >= 0 && x < W && y < H) {
+      const float e = sD[r + 1][cidx + 1];
+      if (e == nodata) {
+        f = FT_NODATA;
+      } else if (!(x == 0 || y == 0 || x == W - 1 || y == H - 1)) {
+        f = FT_FLAT;
+#pragma unroll
+        for (int n = 1; n <= 8; n++) {
+          const float ne = sD[r + 1 + d8dy(n)][cidx + 1 + d8dx(n)];
+          if (ne < e || ne == nodata) f = 0;  // find_flats.hpp:58-61
+        }
+      }
+    }
+    sC[r][cidx] = f;
+  }
+  __syncthreads();
+  int nflat = 0, nlow = 0, nhigh = 0;
+  for (int g = threadIdx.x; g < CE_TX * CE_TY / 4; g += 256) {
+    const int r = g / (CE_TX / 4), c4 = (g - r * (CE_TX / 4)) * 4;
+    const int y = y0 + r;
+    if (y >= H) continue;
+    uint8_t out[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int cidx = c4 + j, x = x0 + cidx;
+      uint8_t f = sC[r + 1][cidx + 1];
+      if (x < W && !(f & FT_NODATA)) {
+        const float e = sD[r + 2][cidx + 2];
+        int low = 0, high = 0;
+#pragma unroll
+        for (int n = 1; n <= 8; n++) {
+          const float ne = sD[r + 2 + d8dy(n)][cidx + 2 + d8dx(n)];
+          if (f == 0) {
+            if ((sC[r + 1 + d8dy(n)][cidx + 1 + d8dx(n)] & FT_FLAT) && ne == e) low = 1;  // Barnes2014.hpp:343-350
+          } else {
+            if (e < ne) high = 1;  // :354-360
+          }
+        }
+        nflat += f == FT_FLAT;
+        f = (uint8_t)(f | (low ? FT_LOW : 0) | (high ? FT_HIGH : 0));
+        nlow += low;
+        nhigh += high;
+      }
+      out[j] = f;
+    }
+    const int x = x0 + c4;
+    uint8_t *o = ft + (size_t)y * W + x;
+    if (x + 3 < W && ((W & 3) == 0)) {
+      *reinterpret_cast<uchar4 *>(o) = make_uchar4(out[0], out[1], out[2], out[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (x + j < W) o[j] = out[j];
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nflat += __shfl_xor_sync(0xffffffffu, nflat, o);
+    nlow += __shfl_xor_sync(0xffffffffu, nlow, o);
+    nhigh += __shfl_xor_sync(0xffffffffu, nhigh, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (nflat) atomicAdd(&dev->n_flat, nflat);
+    if (nlow) atomicAdd(&dev->n_low, nlow);
+    if (nhigh) atomicAdd(&dev->n_high, nhigh);
   }
 }
 
@@ -403,6 +495,43 @@ __global__ void __launch_bounds__(256) flats_apply_kernel(float *dem, const int 
   if (threadIdx.x == 0 && cnt) atomicAdd(&dev->n_raised, cnt);
 }
 
+// 4 cells per thread (W % 4 == 0, no mask / label outputs requested): most quads lie outside every flat and cost one
+// 16-byte label load; the others fetch their distances and elevations with 16-byte accesses as well
+__global__ void __launch_bounds__(256) flats_apply_x4_kernel(float *dem, const int *__restrict__ labels,
+                                                              const int *__restrict__ away, const int *__restrict__ tw,
+                                                              const int *__restrict__ Hh, int W, int H, FlatDev *dev) {
+  const size_t n4 = (size_t)W * H / 4;
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int raised = 0;
+  if (q < n4) {
+    const int4 lab = __ldg(reinterpret_cast<const int4 *>(labels) + q);
+    if (lab.x | lab.y | lab.z | lab.w) {
+      const int4 t4 = __ldg(reinterpret_cast<const int4 *>(tw) + q);
+      const int4 a4 = __ldg(reinterpret_cast<const int4 *>(away) + q);
+      const int l[4] = {lab.x, lab.y, lab.z, lab.w}, t[4] = {t4.x, t4.y, t4.z, t4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w};
+      float4 z4 = reinterpret_cast<float4 *>(dem)[q];
+      float z[4] = {z4.x, z4.y, z4.z, z4.w};
+      const size_t i0 = q * 4;
+      const int y = (int)(i0 / W), x0 = (int)(i0 - (size_t)y * W);
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (l[j] == 0 || t[j] <= 0) continue;
+        const int m = 2 * t[j] + (a[j] > 0 ? __ldg(Hh + l[j] - 1) - a[j] : 0);  // :191-194
+        const int x = x0 + j;
+        if (m > 0 && x > 0 && y > 0 && x < W - 1 && y < H - 1) {  // :511-512 interior only
+          z[j] = advance_ulps(z[j], m);
+          raised++;
+          any = true;
+        }
+      }
+      if (any) reinterpret_cast<float4 *>(dem)[q] = make_float4(z[0], z[1], z[2], z[3]);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) raised += __shfl_xor_sync(0xffffffffu, raised, o);
+  if ((threadIdx.x & 31) == 0 && raised) atomicAdd(&dev->n_raised, raised);
+}
+
 // label = root+1 for data cells of components holding a low edge, else 0 (Barnes2014.hpp:437-441)
 __global__ void __launch_bounds__(256) make_labels_kernel(const uint8_t *__restrict__ rootflag,
                                                            const uint8_t *__restrict__ ft, int *labels, size_t n) {
@@ -448,11 +577,13 @@ __global__ void __launch_bounds__(256) gradient_seed_kernel(const float *__restr
 
 // float distances -> int levels in place (0 = not reached); away also folds the per-flat maximum
 __global__ void __launch_bounds__(256) gradient_convert_kernel(const uint8_t *__restrict__ ft, const int *__restrict__ labels,
-                                                                int *dist_inout, int *Hh, size_t n, int away) {
+                                                                int *dist_inout, int *Hh, size_t n, int away, FlatDev *dev) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = __int_as_float(dist_inout[i]);
   int d = (v < __int_as_float(0x7f800000)) ? (int)v : 0;
+  // float distances are exact below 2^24 only (w + 1 == w from there on); the reference counts in int32
+  if (d >= (1 << 24)) dev->dist_overflow = 1;
   if (!away && (ft[i] & FT_LOW)) d = 1;
   dist_inout[i] = d;
   if (away && d > 0) {
@@ -509,10 +640,16 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   DevBuf<uint8_t> ft(n);
   DevBuf<FlatDev> dev(1);
   RDB_CK(cudaMemsetAsync(dev.p, 0, sizeof(FlatDev), c.stream));
-  flats_classify_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, w, h, nodata, dev.p);
-  flats_edges_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, w, h, dev.p);
+  if (c.params.flats_fused_classify) {
+    dim3 grd((unsigned)((w + CE_TX - 1) / CE_TX), (unsigned)((h + CE_TY - 1) / CE_TY));
+    flats_classify_edges_kernel<<<grd, 256, 0, c.stream>>>(d_dem, ft.p, w, h, nodata, dev.p);
+    count_launch();
+  } else {
+    flats_classify_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, w, h, nodata, dev.p);
+    flats_edges_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, w, h, dev.p);
+    count_launch(2);
+  }
   RDB_CK(cudaGetLastError());
-  count_launch(2);
   FlatDev *hd = (FlatDev *)c.pinned;
   RDB_CK(cudaMemcpyAsync(hd, dev.p, sizeof(FlatDev), cudaMemcpyDeviceToHost, c.stream));
   RDB_CK(cudaStreamSynchronize(c.stream));
@@ -543,7 +680,22 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   DevBuf<int> q0(qcap), q1(qcap);
   RDB_CK(cudaMemsetAsync(Hh.p, 0, n * sizeof(int), c.stream));
   int levels = 0;
-  if (c.params.flats_tiled) {
+  if (c.params.flats_tiled && c.params.flats_pair) {
+    q0.reset();
+    q1.reset();
+    for (int pass = 0; pass < 2; pass++)
+      gradient_seed_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, ft.p, labels.p, reinterpret_cast<float *>(pass == 0 ? away.p : tw.p),
+                                                         w, h, pass == 0);
+    RDB_CK(cudaGetLastError());
+    count_launch(2);
+    geodesic_distance_pair_dev(ft.p, FT_FLAT, reinterpret_cast<float *>(away.p), reinterpret_cast<float *>(tw.p), w, h);
+    for (int pass = 0; pass < 2; pass++)
+      gradient_convert_kernel<<<blocks, 256, 0, c.stream>>>(ft.p, labels.p, pass == 0 ? away.p : tw.p, Hh.p, n, pass == 0, dev.p);
+    RDB_CK(cudaGetLastError());
+    count_launch(2);
+    lap("gradients away + towards (tiled, side by side)");
+    levels = (int)c.stats.flat_bfs_levels;
+  } else if (c.params.flats_tiled) {
     q0.reset();
     q1.reset();
     for (int pass = 0; pass < 2; pass++) {
@@ -553,7 +705,7 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
       RDB_CK(cudaGetLastError());
       count_launch();
       geodesic_distance_dev(ft.p, FT_FLAT, reinterpret_cast<float *>(dist), w, h);
-      gradient_convert_kernel<<<blocks, 256, 0, c.stream>>>(ft.p, labels.p, dist, Hh.p, n, is_away);
+      gradient_convert_kernel<<<blocks, 256, 0, c.stream>>>(ft.p, labels.p, dist, Hh.p, n, is_away, dev.p);
       RDB_CK(cudaGetLastError());
       count_launch();
       lap(is_away ? "gradient away (tiled)" : "gradient towards (tiled)");
@@ -567,13 +719,19 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   }
   c.stats.flat_bfs_levels = levels;
 
-  flats_apply_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, labels.p, away.p, tw.p, Hh.p, d_mask_out, d_labels_out, w, h,
-                                                   apply ? 1 : 0, dev.p);
+  if (apply && !d_mask_out && !d_labels_out && (w & 3) == 0 && ((uintptr_t)d_dem & 15) == 0 && c.params.flats_fused_classify)
+    flats_apply_x4_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, c.stream>>>(d_dem, labels.p, away.p, tw.p, Hh.p, w, h, dev.p);
+  else
+    flats_apply_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, labels.p, away.p, tw.p, Hh.p, d_mask_out, d_labels_out, w, h,
+                                                     apply ? 1 : 0, dev.p);
   RDB_CK(cudaGetLastError());
   count_launch();
   RDB_CK(cudaMemcpyAsync(hd, dev.p, sizeof(FlatDev), cudaMemcpyDeviceToHost, c.stream));
   RDB_CK(cudaStreamSynchronize(c.stream));
   c.stats.flat_cells_raised = hd->n_raised;
+  if (hd->dist_overflow)
+    fail("resolve_flats: a flat is more than 2^24 cells long; the float distance solver is not exact there "
+         "(rdb200_set_param(\"flats_tiled\", 0) selects the int32 level-synchronous solver)");
   lap("apply");
 }
 
@@ -727,7 +885,7 @@ int rdb200_dev_flats_gradient_end(rdb200_flats_state *s, int32_t away, rdb200_fi
   Ctx &c = ctx();
   int *dist = away ? s->away.p : s->tw.p;
   finish_band_distance_state(dist_state, reinterpret_cast<float *>(dist));
-  gradient_convert_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->ft.p, s->labels.p, dist, s->Hh.p, s->n(), away ? 1 : 0);
+  gradient_convert_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->ft.p, s->labels.p, dist, s->Hh.p, s->n(), away ? 1 : 0, s->dev.p);
   RDB_CK(cudaGetLastError());
   RDB_CK(cudaStreamSynchronize(c.stream));
   FLATS_END
@@ -740,7 +898,10 @@ int rdb200_dev_flats_apply(rdb200_flats_state *s) {
   flats_apply_kernel<<<s->blocks(), 256, 0, c.stream>>>(s->dem, s->labels.p, s->away.p, s->tw.p, s->Hh.p, nullptr, nullptr,
                                                         s->W, s->H, 1, s->dev.p);
   RDB_CK(cudaGetLastError());
+  FlatDev *hd = (FlatDev *)c.pinned;
+  RDB_CK(cudaMemcpyAsync(hd, s->dev.p, sizeof(FlatDev), cudaMemcpyDeviceToHost, c.stream));
   RDB_CK(cudaStreamSynchronize(c.stream));
+  if (hd->dist_overflow) fail("resolve_flats (band): a flat is more than 2^24 cells long; float distances are not exact there");
   FLATS_END
 }
 

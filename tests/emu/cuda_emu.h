@@ -49,6 +49,7 @@ struct dim3 {
 };
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(16) double2 { double x, y; };
 struct alignas(16) ulonglong2 { unsigned long long x, y; };
 struct uchar4 { unsigned char x, y, z, w; };
@@ -99,10 +100,14 @@ cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st = nullptr)
 cudaError_t cudaMemset(void *d, int v, size_t n);
 cudaError_t cudaStreamCreate(cudaStream_t *s);
 cudaError_t cudaStreamDestroy(cudaStream_t s);
+enum : unsigned { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { return cudaStreamCreate(s); }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }  // execution is synchronous
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
 cudaError_t cudaDeviceSynchronize();
 cudaError_t cudaEventCreate(cudaEvent_t *e);
 cudaError_t cudaEventDestroy(cudaEvent_t e);
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
 cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s = nullptr);
 cudaError_t cudaEventSynchronize(cudaEvent_t e);
 cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b);
