@@ -44,12 +44,9 @@ SEED = 42
 
 
 def BAND_FILL_KW(row0, height):
-    """Row-band fill start: RDB_BAND_MULTIGRID=k (default 8; 0 = flood from +inf) starts every band from the lifted fill
-    of the k x k max-pooled raster, RDB_BAND_VCYCLE=n adds coarse-grid corrections."""
-    k = int(os.environ.get("RDB_BAND_MULTIGRID", "8"))
-    if k < 2:
-        return {}
-    return {"multigrid": k, "row0": row0, "height": height, "vcycle": int(os.environ.get("RDB_BAND_VCYCLE", "0"))}
+    """The band's place in the raster for sharded.fill_band (the C++ band driver takes the multigrid settings from the
+    library switches fill_multigrid / fill_vcycle; RDB200_PARAMS presets them for experiments)."""
+    return {"row0": row0, "height": height}
 
 
 def measured_hbm_peak():
@@ -284,9 +281,6 @@ def run_b200(args):
            "fill_ms": 0.0, "acc_ms": 0.0, "exchange_rounds": 0}
     last = {}
 
-    def delta(after, before, key):
-        return after[key] - before[key]
-
     def one_step(record: bool):
         work.copy_(dem0)
         if world == 1:
@@ -304,13 +298,11 @@ def run_b200(args):
                 agg["fill_ms"] += s1["ms_total"]
                 agg["acc_ms"] += s2["ms_total"]
         else:
-            # the row-band entry points keep accumulating into the library's counters: take differences
-            b0 = _lib.stats()
+            # rdb200_mgpu_* (the C++ band drivers over NCCL) report per-call counters like the single-GPU entry points
             ta = time.perf_counter()
             filled, rounds, st = sharded.fill_band(work, gt, gb, return_stats=True, **BAND_FILL_KW(r0 - gt, N))
             torch.cuda.synchronize()
             tb = time.perf_counter()
-            b1 = _lib.stats()
             res, rounds2, st2 = sharded.fa_band(filled, gt, gb, ND, dinf=False, rank_rows=(r0, r1, N), return_stats=True)
             torch.cuda.synchronize()
             tc = time.perf_counter()
@@ -320,9 +312,9 @@ def run_b200(args):
                 agg["acc_ms"] += (tc - tb) * 1e3
                 agg["fill_xr"] = agg.get("fill_xr", 0) + rounds
                 agg["acc_xr"] = agg.get("acc_xr", 0) + rounds2
-                agg["launches"] += max(0, delta(st2, b0, "kernel_launches")) + 1
-                agg["sweep_ms"] += max(0.0, delta(b1, b0, "ms_main_kernel"))
-                agg["visits"] += st["fill_tile_visits"]      # absolute per fill state
+                agg["launches"] += st["kernel_launches"] + st2["kernel_launches"] + 1
+                agg["sweep_ms"] += st["ms_main_kernel"]
+                agg["visits"] += st["fill_tile_visits"]
                 agg["rounds"] += st["fill_rounds"]
                 agg["iters"] += st["fill_tile_iters"]
                 agg["exchange_rounds"] += rounds + rounds2

@@ -195,6 +195,46 @@ RDB200_API int rdb200_dev_fa_tarboton_f32_f64(const float *d_dem, double *d_accu
 RDB200_API int rdb200_dev_generate_fbm_f32(float *d_dem, int32_t width, int32_t height, int32_t y0,
                                 uint32_t seed, int32_t octaves, float quantum);
 
+/* ---- multi-GPU: one process per GPU, the raster cut into row bands ----------------------------------------------
+ * (the reference's own distributed path is an MPI tile farm: programs/parallel_priority_flood/main.cpp:394-548.)
+ * Rank r of `world` holds ghost_top + owned + ghost_bottom rows in HBM (ghost_top = r > 0, ghost_bottom = r < world-1;
+ * the ghost rows of the elevation raster hold the neighbouring bands' edge rows).  The rdb200_mgpu_* calls are
+ * collective: every rank calls them in the same order.  A communicator is either NCCL (the product path; libnccl.so.2
+ * is opened at run time) or a pair of caller-supplied callbacks (how the CPU tests run the same C++ drivers over gloo).
+ *
+ *   rank 0:  rdb200_nccl_unique_id(id)   ... ship the 128 bytes to every rank (MPI_Bcast, a file, torch.distributed) ...
+ *   all:     rdb200_init(local_gpu); rdb200_comm_create_nccl(&comm, rank, world, id);
+ *            rdb200_mgpu_fill_depressions_d8_f32(comm, d_band, W, rows, gt, gb, row0, H, NULL);
+ *            rdb200_mgpu_fa_f32_f64(comm, d_band, d_accum, W, rows, nodata, gt, gb, 0, 1, NULL);
+ */
+typedef struct rdb200_comm rdb200_comm;
+enum { RDB200_MAX_F32 = 0, RDB200_MIN_F32 = 1, RDB200_MAX_I32 = 2, RDB200_SUM_I32 = 3 };
+/* exchange `bytes` with rank-1 (send_up / recv_up) and rank+1 (send_dn / recv_dn); a side without a neighbour gets
+ * null pointers.  Pointers are device pointers of the calling rank; the call returns when the data has arrived. */
+typedef int (*rdb200_exchange_fn)(void *user, const void *send_up, void *recv_up, const void *send_dn, void *recv_dn,
+                                  size_t bytes);
+/* in-place all-reduce of `count` elements, op = one of RDB200_MAX_F32 ... */
+typedef int (*rdb200_allreduce_fn)(void *user, void *buf, size_t count, int op);
+RDB200_API int rdb200_nccl_unique_id(uint8_t *out128);
+RDB200_API int rdb200_comm_create_nccl(rdb200_comm **comm, int32_t rank, int32_t world, const uint8_t *id128);
+RDB200_API int rdb200_comm_create_callbacks(rdb200_comm **comm, int32_t rank, int32_t world, void *user,
+                                            rdb200_exchange_fn exchange, rdb200_allreduce_fn allreduce);
+RDB200_API int rdb200_comm_destroy(rdb200_comm *comm);
+
+/* FillDepressions<D8> (include/richdem/depressions/depressions.hpp:13-21) over row bands, in place on `d_band`
+ * (local_rows x width, ghost rows included; their contents are ignored on entry and hold the neighbours' filled edge
+ * rows on return).  row0 = global row of local row 0, height = rows of the whole raster.  Same result as the single-GPU
+ * call, bit for bit.  *exchange_rounds (optional): halo exchanges done. */
+RDB200_API int rdb200_mgpu_fill_depressions_d8_f32(const rdb200_comm *comm, float *d_band, int32_t width, int32_t local_rows,
+                                                   int32_t ghost_top, int32_t ghost_bottom, int32_t row0, int32_t height,
+                                                   int32_t *exchange_rounds);
+/* FA_D8 (dinf = 0) / FA_Tarboton (dinf = 1) (include/richdem/methods/flow_accumulation.hpp:27,16) over row bands.
+ * d_band_dem: elevations incl. ghost rows (neighbours' rows); d_band_accum_inout: weights in / accumulation out on the
+ * owned rows (the ghost rows are scratch); accum_is_ones as in rdb200_fa_d8_f32_f64. */
+RDB200_API int rdb200_mgpu_fa_f32_f64(const rdb200_comm *comm, const float *d_band_dem, double *d_band_accum_inout,
+                                      int32_t width, int32_t local_rows, float nodata, int32_t ghost_top,
+                                      int32_t ghost_bottom, int32_t dinf, int32_t accum_is_ones, int32_t *exchange_rounds);
+
 /* ---- row-band (multi-GPU) fill: one band per GPU, halo rows exchanged by the caller -- */
 /* The band raster handed in is (band_rows + ghost rows) x width.  Its first and last rows are
  * boundary conditions that the solver never changes: a real raster border row, or a ghost

@@ -71,6 +71,12 @@ SIGNATURES = {
     "rdb200_dev_fa_d8_f32_f64": [_vp, _vp, _i32, _i32, _f32, _i32],
     "rdb200_dev_fa_tarboton_f32_f64": [_vp, _vp, _i32, _i32, _f32, _i32],
     "rdb200_dev_generate_fbm_f32": [_vp, _i32, _i32, _i32, C.c_uint32, _i32, _f32],
+    "rdb200_nccl_unique_id": [_vp],
+    "rdb200_comm_create_nccl": [C.POINTER(_vp), _i32, _i32, _vp],
+    "rdb200_comm_create_callbacks": [C.POINTER(_vp), _i32, _i32, _vp, _vp, _vp],
+    "rdb200_comm_destroy": [_vp],
+    "rdb200_mgpu_fill_depressions_d8_f32": [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_i32)],
+    "rdb200_mgpu_fa_f32_f64": [_vp, _vp, _vp, _i32, _i32, _f32, _i32, _i32, _i32, _i32, C.POINTER(_i32)],
     "rdb200_dev_fill_begin": [C.POINTER(_vp), _vp, _i32, _i32],
     "rdb200_dev_fill_begin_lifted": [C.POINTER(_vp), _vp, _i32, _i32, _vp, _i32, _i32, _i32],
     "rdb200_dev_maxpool_rows_f32": [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _i32],

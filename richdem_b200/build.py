@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librichdem_b200.so")
-SOURCES = ["capi.cu", "fill.cu", "flats.cu", "flowdirs.cu", "accum.cu", "terrain.cu"]
+SOURCES = ["capi.cu", "comm.cu", "fill.cu", "flats.cu", "flowdirs.cu", "accum.cu", "terrain.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc compilation failed")
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs,
-            "-Xcompiler", "-fPIC", "-cudart", "shared"]
+            "-Xcompiler", "-fPIC", "-cudart", "shared", "-ldl"]
     subprocess.check_call(link)
     return LIB
 

@@ -692,7 +692,10 @@ constexpr int kPrepRows = 64;
 
 __global__ void __launch_bounds__(256) fa_d8_prep_rolling_kernel(const float *__restrict__ dem, uint8_t *__restrict__ code,
                                                                   unsigned long long *__restrict__ word, int W, int H,
-                                                                  float nodata) {
+                                                                  float nodata, int y_lo, int y_hi) {
+  // Row bands (y_lo > 0 / y_hi < H): rows outside [y_lo, y_hi) are ghost rows.  Their flow codes are NOT computed here
+  // (the row beyond them is unknown): `code` already holds the neighbouring band's codes for them, they are read back
+  // in step A, their words become empty parking slots and they are never a sole-donor target.
   // ring rows carry 4 guard bytes on each side (column c of the block lives at byte c + 4)
   __shared__ __align__(16) uint8_t sCode[5][kPrepCols + 8];
   __shared__ __align__(16) uint8_t sDeps[4][kPrepCols + 8];
@@ -732,7 +735,9 @@ __global__ void __launch_bounds__(256) fa_d8_prep_rolling_kernel(const float *__
         const int x = xc + k;
         const float e = d[1][k + 1];
         int c = 0;
-        if (row_in && col_in) {
+        if (row_in && col_in && (g < y_lo || g >= y_hi)) {
+          c = code[(size_t)g * W + x];  // a neighbouring band's row: its codes were installed by the caller
+        } else if (row_in && col_in) {
           if (e == nodata) {
             c = kCodeNoData;
           } else if (!(x == 0 || g == 0 || x == W - 1 || g == H - 1)) {
@@ -792,8 +797,13 @@ __global__ void __launch_bounds__(256) fa_d8_prep_rolling_kernel(const float *__
       int cc[4] = {c4.x, c4.y, c4.z, c4.w};
       const int dd[4] = {d4.x, d4.y, d4.z, d4.w};
       unsigned long long out[4];
+      const bool ghost = yy < y_lo || yy >= y_hi;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
+        if (ghost) {
+          out[k] = 0;  // an empty parking slot for flow that leaves the band
+          continue;
+        }
         if (cc[k] == kCodeNoData) {
           out[k] = 0xBFF0000000000000ull;  // -1.0 (flow_accumulation_generic.hpp:95-97)
           continue;
@@ -803,15 +813,29 @@ __global__ void __launch_bounds__(256) fa_d8_prep_rolling_kernel(const float *__
         if (dir != 0) {
           const int ry = yy + d8dy(dir), ro = 4 + 4 * t + k + d8dx(dir);
           const int rc = sCode[(ry + 10) % 5][ro];
-          if (rc != kCodeNoData && sDeps[(ry + 8) % 4][ro] == 1) cc[k] |= kCodeSole;  // I am my receiver's only donor
+          // I am my receiver's only donor (a receiver in a ghost row is a parking slot that several bands' worth of
+          // cells may add to: never "sole")
+          if (rc != kCodeNoData && sDeps[(ry + 8) % 4][ro] == 1 && ry >= y_lo && ry < y_hi) cc[k] |= kCodeSole;
         }
       }
       const size_t i0 = (size_t)yy * W + xc;
-      *reinterpret_cast<uchar4 *>(code + i0) = make_uchar4((uint8_t)cc[0], (uint8_t)cc[1], (uint8_t)cc[2], (uint8_t)cc[3]);
+      if (!ghost)
+        *reinterpret_cast<uchar4 *>(code + i0) = make_uchar4((uint8_t)cc[0], (uint8_t)cc[1], (uint8_t)cc[2], (uint8_t)cc[3]);
       reinterpret_cast<ulonglong2 *>(word + i0)[0] = make_ulonglong2(out[0], out[1]);
       reinterpret_cast<ulonglong2 *>(word + i0)[1] = make_ulonglong2(out[2], out[3]);
     }
   }
+}
+
+// flow codes of single rows (the first / last owned row of a row band, which the neighbouring band needs before it
+// can count the donors of its own edge row)
+__global__ void __launch_bounds__(256) flow_code_rows_kernel(const float *__restrict__ dem, uint8_t *__restrict__ code, int W,
+                                                              int H, float nodata, int ya, int yb) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const int y = blockIdx.y == 0 ? ya : yb;
+  if (y < 0) return;
+  code[(size_t)y * W + x] = (uint8_t)fm_d8_cell(dem, x, y, W, H, nodata);
 }
 
 // BAND: cells below ghost_lo_end / from ghost_hi_start on belong to a neighbouring row band; flow
@@ -1056,7 +1080,7 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     if (c.params.accum_fused_prep) {
       dim3 pgrd((unsigned)((w + kPrepOut - 1) / kPrepOut), (unsigned)((h + kPrepRows - 1) / kPrepRows));
       fa_d8_prep_rolling_kernel<<<pgrd, blk, 0, c.stream>>>(d_dem, code.p, reinterpret_cast<unsigned long long *>(d_accum), w, h,
-                                                            nodata);
+                                                            nodata, 0, h);
       count_launch();
     } else {
       flow_code_d8_x4_kernel<<<grd, blk, 0, c.stream>>>(d_dem, code.p, d_accum, w, h, nodata, 2);
@@ -1193,6 +1217,9 @@ struct FaccState {
   DevBuf<int> ghostcnt, fr0, fr1, cnt;
   bool prepared = false;
   bool packed = false;    // unit-weight D8: accumulator words are [donors left | integer sum] until final
+  bool fused = false;     // ... and codes + donor counts come from the fused rolling-window pass at the first run
+  const float *dem = nullptr;
+  float nodata_v = 0.f;
   int n_frontier = 0;     // cells waiting in fr0 (seeded by apply_inflow)
   int rounds = 0;
 
@@ -1219,6 +1246,18 @@ struct FaccState {
     RDB_CK(cudaMemsetAsync(ghostcnt.p, 0, 2 * (size_t)W * sizeof(int), c.stream));
     RDB_CK(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(int), c.stream));
     const unsigned blocks = (unsigned)((n() + 255) / 256);
+    fused = packed && c.params.accum_fused_prep != 0 && ((uintptr_t)d_dem & 15) == 0;
+    dem = d_dem;
+    nodata_v = nodata;
+    if (fused) {
+      // only the rows the neighbours ask for now; everything else in ONE rolling-window pass at the first run, after
+      // the neighbours' edge codes have been installed in the ghost rows
+      dim3 grd((unsigned)((W + 255) / 256), 2);
+      flow_code_rows_kernel<<<grd, 256, 0, c.stream>>>(d_dem, code.p, w, h, nodata, gt ? edge_row(0) : -1, gb ? edge_row(1) : -1);
+      RDB_CK(cudaGetLastError());
+      count_launch();
+      return;
+    }
     // rows 0 / H-1 of the local raster are either true raster edges (no ghost) or ghost rows whose
     // codes are replaced below, so the per-cell functions' own edge test is exactly right here
     if (dinf)
@@ -1280,7 +1319,13 @@ struct FaccState {
     Ctx &c = ctx();
     unsigned long long *word = reinterpret_cast<unsigned long long *>(accum);
     const int lo_end = gt ? W : 0, hi_start = gb ? (H - 1) * W : H * W;
-    if (!prepared) {
+    if (!prepared && fused) {
+      dim3 pgrd((unsigned)((W + kPrepOut - 1) / kPrepOut), (unsigned)((H + kPrepRows - 1) / kPrepRows));
+      fa_d8_prep_rolling_kernel<<<pgrd, 256, 0, c.stream>>>(dem, code.p, word, W, H, nodata_v, gt, H - gb);
+      launch_walk_packed<true>(code.p, word, W, (int)n(), nullptr, lo_end, hi_start);
+      count_launch(2);
+      prepared = true;
+    } else if (!prepared) {
       dim3 blk(256), grd((W / 4 + 255) / 256, H < 8192 ? H : 8192);
       deps_gather_packed_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, W, H, gt, H - gb);
       launch_walk_packed<true>(code.p, word, W, (int)n(), nullptr, lo_end, hi_start);
@@ -1448,6 +1493,63 @@ void FaccState::sum_rows(int *d_sums) {
   Ctx &c = ctx();
   band_sum_counts_kernel<<<64, 256, 0, c.stream>>>(ghostcnt.p, W, d_sums);
   RDB_CK(cudaGetLastError());
+}
+
+// Row-band (multi-GPU) FA_D8 / FA_Tarboton driven from C++ over a rdb200_comm: the protocol of FaccState (edge codes to
+// the neighbours once, then rounds of: walk | parked outflow of the two seams in ONE message per neighbour (sums and
+// parcel counts) | neighbours' inflow releases cells of the edge rows | a 1-int all-reduce says whether anyone shipped).
+void mgpu_fa_band(const rdb200_comm *comm, const float *d_dem, double *d_accum, int w, int hloc, float nodata, int gt, int gb,
+                  bool dinf, bool ones, int *xrounds) {
+  Ctx &c = ctx();
+  const int world = comm_world(comm);
+  FaccState A;
+  A.begin(d_dem, d_accum, w, hloc, nodata, gt, gb, dinf, ones);
+  gt = A.gt;
+  gb = A.gb;
+  // message layout per side: [w doubles: sums | w ints: parcel counts]; codes: [w floats: rmax | w bytes: codes]
+  const size_t msg = (size_t)w * 12;
+  DevBuf<uint8_t> buf(4 * msg);
+  uint8_t *su = buf.p, *sd = buf.p + msg, *ru = buf.p + 2 * msg, *rd = buf.p + 3 * msg;
+  auto rmaxp = [&](uint8_t *m) { return reinterpret_cast<float *>(m); };
+  auto codep = [&](uint8_t *m) { return m + (size_t)w * 4; };
+  auto sump = [&](uint8_t *m) { return reinterpret_cast<double *>(m); };
+  auto cntp = [&](uint8_t *m) { return reinterpret_cast<int *>(m + (size_t)w * 8); };
+  if (world > 1) {
+    RDB_CK(cudaMemsetAsync(buf.p, 0, 4 * msg, c.stream));
+    if (gt) A.get_edge_codes(0, codep(su), rmaxp(su));
+    if (gb) A.get_edge_codes(1, codep(sd), rmaxp(sd));
+    comm_exchange(comm, su, ru, sd, rd, (size_t)w * 5);
+    if (gt) A.set_ghost_codes(0, codep(ru), rmaxp(ru));
+    if (gb) A.set_ghost_codes(1, codep(rd), rmaxp(rd));
+  }
+  DevBuf<int> flag(1);
+  int *hflag = (int *)c.pinned + 1024;
+  int rounds = 0;
+  for (;;) {
+    A.collect_frontier();
+    int a = 0, b = 0;
+    A.run(&a, &b);
+    rounds++;
+    if (world == 1) break;
+    RDB_CK(cudaMemsetAsync(flag.p, 0, sizeof(int), c.stream));
+    if (a + b > 0) count_launch();
+    {
+      const int mine = a + b > 0 ? 1 : 0;
+      RDB_CK(cudaMemcpyAsync(flag.p, &mine, sizeof(int), cudaMemcpyHostToDevice, c.stream));  // (pageable 4 bytes: staged at once)
+    }
+    comm_allreduce(comm, flag.p, 1, RDB200_MAX_I32);
+    RDB_CK(cudaMemcpyAsync(hflag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    if (*hflag == 0) break;
+    if (gt) A.take_outflow(0, sump(su), cntp(su));
+    if (gb) A.take_outflow(1, sump(sd), cntp(sd));
+    comm_exchange(comm, su, ru, sd, rd, msg);
+    if (gt) A.apply_inflow(0, sump(ru), cntp(ru));
+    if (gb) A.apply_inflow(1, sump(rd), cntp(rd));
+    if (rounds > 1000000) fail("mgpu_fa: exchange rounds exceeded");
+  }
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  if (xrounds) *xrounds = rounds;
 }
 
 void capi_set_error(const char *msg);

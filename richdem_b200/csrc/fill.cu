@@ -392,6 +392,36 @@ __global__ void __launch_bounds__(256) fill_seed_flags_kernel(const FillArgs a, 
   if (count) atomicAdd(count, 1);
 }
 
+// row-band fill: ghost row y of the padded arrays takes the neighbouring band's edge row where that is lower (ghost cells
+// are boundary conditions: Z = W), and the tiles whose cells or aprons changed are flagged
+__global__ void __launch_bounds__(256) fill_ghost_update_kernel(float *Wp, float *Zp, int pitch, int W, int H, int y,
+                                                                 const float *__restrict__ row, int *tile_flag, int tilesX,
+                                                                 int *lowered) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const size_t o = (size_t)(y + 1) * pitch + x + PADL;
+  const float v = row[x];
+  if (v < Wp[o]) {
+    Wp[o] = v;
+    Zp[o] = v;
+    *lowered = 1;
+    const int ya = y > 0 ? y - 1 : 0, yb = y < H - 1 ? y + 1 : H - 1, xa = x > 0 ? x - 1 : 0, xb = x < W - 1 ? x + 1 : W - 1;
+    const int ty0 = ya / TY, ty1 = yb / TY, tx0 = xa / TX, tx1 = xb / TX;
+    tile_flag[ty0 * tilesX + tx0] = 1;
+    if (tx1 != tx0) tile_flag[ty0 * tilesX + tx1] = 1;
+    if (ty1 != ty0) {
+      tile_flag[ty1 * tilesX + tx0] = 1;
+      if (tx1 != tx0) tile_flag[ty1 * tilesX + tx1] = 1;
+    }
+  }
+}
+
+// a ghost row of the band's raster starts at its lifted level: the water level of its k x k block in the coarse fill
+__global__ void __launch_bounds__(256) fill_lift_row_kernel(float *row, int W, const float *__restrict__ coarse_row, int k) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x < W) row[x] = coarse_row[x / k];
+}
+
 // ---- layout kernels ----------------------------------------------------------------------
 // compact dem (H x W) -> padded Z and W.  Border cells (all four sides of the raster handed in)
 // are boundary conditions: W = Z = dem there; interior W = +inf; padding Z = W = +inf.
@@ -1035,9 +1065,19 @@ struct FillState {
     count_launch();
     seed_from_flags(d_count);
   }
-  void prolong_from_level(FillState &cs, int k) {
-    prolong_from(cs.Wp.p, cs.pitch, PADL, 1, k, 0, cs.dirty.p, cs.tilesX);
+  void prolong_from_level(FillState &cs, int k, int yoff = 0, int *d_count = nullptr) {
+    prolong_from(cs.Wp.p, cs.pitch, PADL, 1, k, yoff, cs.dirty.p, cs.tilesX, d_count);
     cs.clear_dirty();
+  }
+  // a neighbouring band's edge row arrives: ghost row y (0 or H-1) drops to it where it is lower; the tiles that read
+  // the lowered cells are queued, *d_lowered (device int) is set when anything moved
+  void ghost_update(int y, const float *d_row, int *d_lowered) {
+    Ctx &c = ctx();
+    clear_flags();
+    fill_ghost_update_kernel<<<(W + 255) / 256, 256, 0, c.stream>>>(Wp.p, Zp.p, pitch, W, H, y, d_row, tflag.p, tilesX, d_lowered);
+    RDB_CK(cudaGetLastError());
+    count_launch();
+    seed_from_flags();
   }
 
   void read_row(int y, float *d_row) {
@@ -1302,6 +1342,113 @@ void fill_maxpool_rows(const float *d_src, int w, int h, int yoff, float *d_coar
   fill_maxpool_kernel<<<grd, blk, 0, ctx().stream>>>(d_src, w, h, yoff, d_coarse, wc, hc, k, 1);
   RDB_CK(cudaGetLastError());
   count_launch();
+}
+
+// =================================================================================================
+// Row-band (multi-GPU) fill, driven from C++ over a rdb200_comm (NCCL, or the caller's callbacks in the CPU tests).
+// Every rank holds ghost_top + owned + ghost_bottom rows of the raster in `d_local` (in / out; the ghost rows leave
+// holding the neighbours' filled edge rows).  The multigrid start is what makes the bands nearly independent:
+//   1. every rank max-pools its owned rows; a MAX all-reduce gives every rank the whole k x k pooled raster (1/k^2 of the
+//      cells), which every rank fills itself (redundant but small) -- the coarse surface, lifted, is an upper bound of
+//      the answer for every band and its ghost rows;
+//   2. cycles of: R sweep rounds on the band | edge rows to the neighbours (a ghost row only ever drops) | V-cycle
+//      correction: block maxima of the bands (MAX all-reduce) lower the coarse surface, the coarse relaxation runs on every
+//      rank, the band takes the lowered blocks back | one 4-int MAX all-reduce decides whether anything moved anywhere.
+// The fixed point is the single-GPU one (any admissible schedule ends at W*): when no tile is active, no
+// ghost row dropped and no correction lowered a cell on any rank, every band is at its local fixed point with ghost rows
+// equal to the neighbours' edge rows.
+void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, int gt, int gb, int row0, int H, int *xrounds) {
+  Ctx &c = ctx();
+  const int world = comm_world(comm);
+  gt = gt ? 1 : 0;
+  gb = gb ? 1 : 0;
+  if (w < 3 || hloc - gt - gb < 1 || hloc < 3) fail("mgpu_fill: band too small (%d x %d)", w, hloc);
+  if (row0 < 0 || row0 + hloc > H) fail("mgpu_fill: rows [%d, %d) are outside the raster (%d rows)", row0, row0 + hloc, H);
+  const int k = (int)c.params.fill_multigrid;
+  const int min_side = (int)(c.params.fill_multigrid_min > 0 ? c.params.fill_multigrid_min : 1024);
+  const bool mg = k >= 2 && w >= min_side && H >= min_side && w / k >= 3 && H / k >= 3;
+  const int R = (int)(c.params.fill_vcycle > 0 ? c.params.fill_vcycle : 8);
+  const float inf = __builtin_inff();
+  DevBuf<float> rows(4 * (size_t)w);  // send up, send down, receive up, receive down
+  DevBuf<int> flags(4);               // tiles active | a ghost row dropped | coarse surface lowered | band cells lowered
+  float *send_up = rows.p, *send_dn = rows.p + w, *recv_up = rows.p + 2 * (size_t)w, *recv_dn = rows.p + 3 * (size_t)w;
+  FillState st, cst;
+  DevBuf<float> zc, wcoarse, bm;
+  int wc = 0, hc = 0;
+  auto fill_f32 = [&](float *p, size_t n, float v) {
+    int bits;
+    memcpy(&bits, &v, 4);
+    fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(reinterpret_cast<int *>(p), bits, (int)n);
+    RDB_CK(cudaGetLastError());
+  };
+  if (mg) {
+    wc = (w + k - 1) / k;
+    hc = (H + k - 1) / k;
+    const size_t nc = (size_t)wc * hc;
+    zc.alloc(nc);
+    wcoarse.alloc(nc);
+    bm.alloc(nc);
+    fill_f32(zc.p, nc, -inf);
+    {
+      const int hown = hloc - gt - gb;
+      dim3 blk(256), grd((unsigned)((wc + 255) / 256), (unsigned)(hown / k + 2 < 4096 ? hown / k + 2 : 4096));
+      fill_maxpool_rows(d_local + (size_t)gt * w, w, hown, row0 + gt, zc.p, wc, hc, k, grd, blk);
+    }
+    comm_allreduce(comm, zc.p, nc, RDB200_MAX_F32);
+    RDB_CK(cudaMemcpyAsync(wcoarse.p, zc.p, nc * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
+    fill_depressions_level(wcoarse.p, wc, hc, 1);  // every rank fills the small raster itself
+    for (int side = 0; side < 2; side++) {
+      if (!(side == 0 ? gt : gb)) continue;
+      const int y = side == 0 ? 0 : hloc - 1;
+      fill_lift_row_kernel<<<(w + 255) / 256, 256, 0, c.stream>>>(d_local + (size_t)y * w, w, wcoarse.p + (size_t)((row0 + y) / k) * wc, k);
+    }
+    RDB_CK(cudaGetLastError());
+    st.begin(d_local, w, hloc, wcoarse.p, wc, k, row0);
+    cst.begin(zc.p, wc, hc, wcoarse.p, wc, 1);
+    cst.run();
+    cst.track_dirty();
+    st.track_dirty();
+  } else {
+    if (gt) fill_f32(d_local, (size_t)w, inf);
+    if (gb) fill_f32(d_local + (size_t)(hloc - 1) * w, (size_t)w, inf);
+    st.begin(d_local, w, hloc);
+  }
+  int cycles = 0;
+  int *hflags = (int *)c.pinned + 1024;  // (FillState::run reads its control block back into the front of the scratch)
+  for (;; cycles++) {
+    if (cycles > 100000) fail("mgpu_fill: no convergence");
+    const bool active = (st.run(world > 1 || mg ? R : 0) & 4) != 0;
+    RDB_CK(cudaMemsetAsync(flags.p, 0, 4 * sizeof(int), c.stream));
+    if (world > 1) {
+      if (gt) st.read_row(1, send_up);
+      if (gb) st.read_row(hloc - 2, send_dn);
+      comm_exchange(comm, send_up, recv_up, send_dn, recv_dn, (size_t)w * sizeof(float));
+      if (gt) st.ghost_update(0, recv_up, flags.p + 1);
+      if (gb) st.ghost_update(hloc - 1, recv_dn, flags.p + 1);
+    }
+    if (mg) {
+      fill_f32(bm.p, (size_t)wc * hc, -inf);
+      st.blockmax_into(bm.p, wc, hc, k, row0, gt, hloc - gb);
+      comm_allreduce(comm, bm.p, (size_t)wc * hc, RDB200_MAX_F32);
+      cst.prolong_from(bm.p, wc, 0, 0, 1, 0, nullptr, 0, flags.p + 2);  // the coarse surface drops to the block maxima
+      cst.run();
+      st.prolong_from_level(cst, k, row0, flags.p + 3);
+    }
+    if (active) fill_i32_kernel<<<1, 1, 0, c.stream>>>(flags.p, 1, 1);
+    comm_allreduce(comm, flags.p, 4, RDB200_MAX_I32);
+    RDB_CK(cudaMemcpyAsync(hflags, flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    if (!(hflags[0] | hflags[1] | hflags[2] | hflags[3])) break;
+  }
+  st.run(1);  // refresh the counters (no tile is active: an empty launch)
+  const int64_t visits = st.visits_seen, iters = st.iters_seen, rounds = st.live_rounds;
+  st.finish(d_local);
+  RDB_CK(cudaStreamSynchronize(c.stream));
+  c.stats.fill_rounds = rounds + (mg ? cst.live_rounds : 0);
+  c.stats.fill_tile_visits = visits;
+  c.stats.fill_tile_iters = iters;
+  c.stats.fill_tile_cells = TX * TY;
+  if (xrounds) *xrounds = cycles + 1;
 }
 
 void fill_depressions_dev(float *d_dem, int w, int h) {

@@ -115,6 +115,83 @@ class CudaBandSolver:
         return out
 
 
+# ---- the library's communicator (C++ band drivers: rdb200_mgpu_*) -----------------------------------------------------
+_EXCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+_ALLR_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)
+_COMMS = {}
+
+
+class LibComm:
+    """A rdb200_comm for a torch.distributed process group.  NCCL groups get the library's own NCCL communicator (the
+    128-byte unique id travels over torch.distributed once); any other backend (gloo in the CPU tests, where "device"
+    memory is host memory) gets the callback communicator, whose two callbacks move host buffers with torch.distributed."""
+
+    def __init__(self, group=None):
+        from . import _lib
+        self._lib = _lib
+        L = _lib.lib()
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.group = group
+        self.handle = C.c_void_p()
+        backend = dist.get_backend(group) if dist.is_initialized() else "none"
+        if backend == "nccl":
+            ident = torch.zeros(128, dtype=torch.uint8)
+            if self.rank == 0:
+                _lib.check(L.rdb200_nccl_unique_id(ident.data_ptr()))
+            dev_id = ident.cuda()
+            dist.broadcast(dev_id, 0, group=group)
+            ident = dev_id.cpu()
+            _lib.check(L.rdb200_comm_create_nccl(C.byref(self.handle), self.rank, self.world, ident.data_ptr()))
+            self.kind = "nccl"
+        else:
+            self._exch = _EXCH_FN(self._exchange)
+            self._allr = _ALLR_FN(self._allreduce)
+            _lib.check(L.rdb200_comm_create_callbacks(C.byref(self.handle), self.rank, self.world, None,
+                                                      C.cast(self._exch, C.c_void_p), C.cast(self._allr, C.c_void_p)))
+            self.kind = "callbacks"
+
+    @staticmethod
+    def _host(ptr, nbytes, dtype):
+        buf = (C.c_uint8 * nbytes).from_address(ptr)
+        return torch.frombuffer(buf, dtype=dtype)
+
+    def _exchange(self, user, su, ru, sd, rd, nbytes):
+        try:
+            ops = []
+            for s_, r_, peer in ((su, ru, self.rank - 1), (sd, rd, self.rank + 1)):
+                if s_:
+                    ops += [dist.P2POp(dist.isend, self._host(s_, nbytes, torch.uint8), peer, self.group),
+                            dist.P2POp(dist.irecv, self._host(r_, nbytes, torch.uint8), peer, self.group)]
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            return 0
+        except Exception:  # pragma: no cover
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    def _allreduce(self, user, buf, count, op):
+        try:
+            dtype = torch.float32 if op in (0, 1) else torch.int32
+            t = self._host(buf, count * 4, dtype)
+            dist.all_reduce(t, op={0: dist.ReduceOp.MAX, 1: dist.ReduceOp.MIN, 2: dist.ReduceOp.MAX, 3: dist.ReduceOp.SUM}[op],
+                            group=self.group)
+            return 0
+        except Exception:  # pragma: no cover
+            import traceback
+            traceback.print_exc()
+            return 1
+
+
+def lib_comm(group=None) -> "LibComm":
+    key = id(group)
+    if key not in _COMMS:
+        _COMMS[key] = LibComm(group)
+    return _COMMS[key]
+
+
 def _neighbour_exchange(send_up, send_dn, g_top, g_bot, rank, group):
     """Send a row to each existing neighbour and receive theirs (batched P2P).  Each of
     send_up / send_dn may be a tensor or a list of tensors; returns matching receive buffers."""
@@ -189,6 +266,30 @@ def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None
     across the COARSE raster instead of one tile row / halo exchange at a time."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    import os
+    if solver_cls is None and os.environ.get("RDB_BAND_DRIVER", "cxx") != "python":
+        # the product path: the whole band protocol (multigrid start, halo exchanges, V-cycle corrections, termination)
+        # runs in C++ over the library's communicator (csrc/fill.cu: mgpu_fill_band); in place on local_dem
+        from . import _lib
+        assert _on_device(local_dem) and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
+        _lib.use_torch_stream()
+        h_, w_ = local_dem.shape
+        if height <= 0:
+            hh = torch.tensor([h_ - g_top - g_bot], dtype=torch.int64, device=local_dem.device)
+            if world > 1:
+                allh = [torch.zeros_like(hh) for _ in range(world)]
+                dist.all_gather(allh, hh, group=group)
+                height = int(sum(int(t.item()) for t in allh))
+                row0 = int(sum(int(t.item()) for t in allh[:rank])) - g_top
+            else:
+                height, row0 = h_, 0
+        xr = C.c_int32(0)
+        cm = lib_comm(group)
+        _lib.check(_lib.lib().rdb200_mgpu_fill_depressions_d8_f32(cm.handle, local_dem.data_ptr(), w_, h_, int(g_top), int(g_bot),
+                                                                  int(row0), int(height), C.byref(xr)))
+        if return_stats:
+            return local_dem, int(xr.value), _lib.stats()
+        return local_dem, int(xr.value)
     if solver_cls is None:
         solver_cls = CudaBandSolver
         # halos are exchanged every `band_rounds` sweep rounds instead of after full local convergence,
@@ -300,9 +401,25 @@ def fa_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, nodata: float, di
     its ghost rows must already hold the neighbouring bands' elevations (``fill_band`` leaves them so;
     otherwise call :func:`exchange_rows`).  ``weights`` (float64, same local shape) defaults to ones.
     Returns (local accumulation incl. scratch ghost rows, exchange rounds[, stats])."""
-    accumulator_cls = accumulator_cls or CudaBandAccumulator
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    import os
+    if accumulator_cls is None and os.environ.get("RDB_BAND_DRIVER", "cxx") != "python":
+        from . import _lib
+        ones = weights is None
+        acc = torch.empty(local_dem.shape, dtype=torch.float64, device=local_dem.device) if ones else weights
+        assert _on_device(local_dem) and local_dem.dtype == torch.float32 and local_dem.is_contiguous()
+        assert _on_device(acc) and acc.dtype == torch.float64 and acc.is_contiguous()
+        _lib.use_torch_stream()
+        xr = C.c_int32(0)
+        cm = lib_comm(group)
+        _lib.check(_lib.lib().rdb200_mgpu_fa_f32_f64(cm.handle, local_dem.data_ptr(), acc.data_ptr(), local_dem.shape[1],
+                                                     local_dem.shape[0], float(nodata), int(g_top), int(g_bot), int(dinf),
+                                                     int(ones), C.byref(xr)))
+        if return_stats:
+            return acc, int(xr.value), _lib.stats()
+        return acc, int(xr.value)
+    accumulator_cls = accumulator_cls or CudaBandAccumulator
     ones = weights is None
     acc = torch.empty(local_dem.shape, dtype=torch.float64, device=local_dem.device) if ones else weights
     A = accumulator_cls(local_dem, acc, nodata, g_top, g_bot, dinf, ones)

@@ -62,8 +62,14 @@ def _worker(rank, world, port, lib_path, dem, expected, params, out_q):
         sharded._view = host_view
         _lib.init(0)
         _lib.set_param("fill_use_tma", 0)
-        band_multigrid = params.pop("_band_multigrid", 0)  # fill_band's own arguments, not library switches
+        # the C++ band driver (rdb200_mgpu_*, over the callback communicator here) takes its multigrid settings from the
+        # library switches; the test raster is small, so the coarse levels are allowed down to 16 cells
+        band_multigrid = params.pop("_band_multigrid", 0)
         band_vcycle = params.pop("_band_vcycle", 0)
+        _lib.set_param("fill_multigrid", band_multigrid)
+        _lib.set_param("fill_multigrid_min", 16)
+        if band_vcycle:
+            _lib.set_param("fill_vcycle", band_vcycle)
         for k, v in params.items():
             _lib.set_param(k, v)
 
