@@ -477,6 +477,123 @@ __global__ void fill_init_kernel(const float *__restrict__ dem, float *__restric
   }
 }
 
+// Lifted start with drainage (fill_drain_init, the default with fill_multigrid): one block per tile.  The plain lift
+// gives every cell the water level of its k x k block, so on a slope all cells of a block start at the block's highest
+// elevation and the first sweep has to let them drain cell by cell.  But W*(c) <= max(Z(c), W*(n)) for every neighbour
+// n, so following steepest descent on Z (strictly decreasing, hence acyclic) from c to the cell e where the walk ends --
+// a pit or flat cell, a raster border cell, or the last cell before the walk leaves the tile towards a cell n' --
+// gives the bound  W*(c) <= max(Z(c), B(e))  with B(e) = lift(e) resp. max(Z(e), lift(n')).  The walk is resolved by
+// pointer jumping in shared memory.  Slope cells start at their final value Z(c); only pits and lakes are left to the
+// relaxation.  Writes the tile's cells of the padded Z and W arrays (fill_pad_border_kernel does the rim).
+constexpr int DI_P = TX + 3;  // shared-memory pitch of the (TX + 2)-wide staging arrays
+__global__ void __launch_bounds__(256) fill_init_drain_kernel(const float *__restrict__ dem, float *__restrict__ Zp,
+                                                               float *__restrict__ Wp, int W, int H, int pitch, int tilesX,
+                                                               const float *__restrict__ coarse, int Wc, int pool, int yoff) {
+  __shared__ float sZ[(TY + 2) * DI_P];
+  __shared__ float sL[(TY + 2) * DI_P];
+  __shared__ unsigned short sNext[TX * TY];
+  const float inf = __int_as_float(0x7f800000);
+  const int t = blockIdx.x;
+  const int tyT = t / tilesX, txT = t - tyT * tilesX;
+  const int x0 = txT * TX, y0 = tyT * TY;
+  for (int k = threadIdx.x; k < (TX + 2) * (TY + 2); k += blockDim.x) {
+    const int r = k / (TX + 2), cidx = k - r * (TX + 2);
+    const int x = x0 - 1 + cidx, y = y0 - 1 + r;
+    float z = inf, l = inf;
+    if (x >= 0 && y >= 0 && x < W && y < H) {
+      z = __ldg(dem + (size_t)y * W + x);
+      const bool border = (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
+      l = border ? z : __ldg(coarse + (size_t)((y + yoff) / pool) * Wc + x / pool);
+    }
+    sZ[r * DI_P + cidx] = z;
+    sL[r * DI_P + cidx] = l;
+  }
+  __syncthreads();
+  // steepest-descent successor of every cell of the tile (itself: the walk ends here)
+  for (int c = threadIdx.x; c < TX * TY; c += blockDim.x) {
+    const int ly = c / TX, lx = c - ly * TX;
+    const int x = x0 + lx, y = y0 + ly;
+    const int o = (ly + 1) * DI_P + lx + 1;
+    int nxt = c;
+    if (x > 0 && y > 0 && x < W - 1 && y < H - 1) {
+      const float z = sZ[o];
+      float best = z;
+      int bdx = 0, bdy = 0;
+#pragma unroll
+      for (int n = 1; n <= 8; n++) {
+        const float zn = sZ[o + d8dy(n) * DI_P + d8dx(n)];
+        if (zn < best) {
+          best = zn;
+          bdx = d8dx(n);
+          bdy = d8dy(n);
+        }
+      }
+      if (bdx | bdy) {
+        const int nx = lx + bdx, ny = ly + bdy;
+        if (nx >= 0 && ny >= 0 && nx < TX && ny < TY) {
+          nxt = ny * TX + nx;
+        } else {  // the walk leaves the tile: this cell ends it, bounded through the outside neighbour's lifted level
+          const float b = fmaxf(z, sL[o + bdy * DI_P + bdx]);
+          if (b < sL[o]) sL[o] = b;
+        }
+      }
+    }
+    sNext[c] = (unsigned short)nxt;
+  }
+  __syncthreads();
+  // pointer jumping to the end of every walk
+  for (;;) {
+    int moved = 0;
+    unsigned short nn[(TX * TY + 255) / 256];
+    int q = 0;
+    for (int c = threadIdx.x; c < TX * TY; c += blockDim.x, q++) {
+      const unsigned short a = sNext[c];
+      const unsigned short b = sNext[a];
+      nn[q] = b;
+      moved |= a != b;
+    }
+    __syncthreads();
+    q = 0;
+    for (int c = threadIdx.x; c < TX * TY; c += blockDim.x, q++) sNext[c] = nn[q];
+    if (!__syncthreads_or(moved)) break;
+  }
+  // W0(c) = min(lift(c), max(Z(c), B(end of c's walk)))  and write-back, 4 cells per thread and step
+  for (int g = threadIdx.x; g < TX * TY / 4; g += blockDim.x) {
+    const int ly = g / (TX / 4), lx4 = (g - ly * (TX / 4)) * 4;
+    float zv[4], wv[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int c = ly * TX + lx4 + j;
+      const int o = (ly + 1) * DI_P + lx4 + j + 1;
+      const int e = sNext[c];
+      const int oe = (e / TX + 1) * DI_P + (e % TX) + 1;
+      zv[j] = sZ[o];
+      wv[j] = e == c ? sL[o] : fminf(sL[o], fmaxf(zv[j], sL[oe]));
+    }
+    const size_t po = (size_t)(y0 + ly + 1) * pitch + x0 + lx4 + PADL;
+    *reinterpret_cast<float4 *>(Zp + po) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+    *reinterpret_cast<float4 *>(Wp + po) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+  }
+}
+
+// the rim of the padded arrays that no tile covers: first / last padded row and the PADL columns on either side
+__global__ void __launch_bounds__(256) fill_pad_border_kernel(float *__restrict__ Zp, float *__restrict__ Wp, int pitch, int rows) {
+  const float inf = __int_as_float(0x7f800000);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * pitch) {
+    const size_t o = (size_t)(i < pitch ? 0 : rows - 1) * pitch + (i < pitch ? i : i - pitch);
+    Zp[o] = inf;
+    Wp[o] = inf;
+  }
+  const int j = i - 2 * pitch;
+  if (j >= 0 && j < rows * 2 * PADL) {
+    const int r = j / (2 * PADL), k = j - r * (2 * PADL);
+    const size_t o = (size_t)r * pitch + (k < PADL ? k : pitch - 2 * PADL + k);
+    Zp[o] = inf;
+    Wp[o] = inf;
+  }
+}
+
 // sampled histogram of the input elevations (every `row_stride`-th padded row) for the level schedule
 constexpr int HIST_BINS = 1024;
 __global__ void __launch_bounds__(256) fill_hist_kernel(const float *__restrict__ Zp, int pitch, int rows, int row_stride,
@@ -568,12 +685,22 @@ __global__ void __launch_bounds__(256) fill_restrict_kernel(const float *__restr
   for (int by = blockIdx.y; by < Hc; by += gridDim.y) {
     if (dirty && !dirty[((by * k) / TY) * tilesX + (bx * k) / TX]) continue;
     float m = -__int_as_float(0x7f800000);
-    for (int j = 0; j < k; j++) {
-      const int y = by * k + j;
-      if (y >= H) break;
-      for (int i = 0; i < k; i++) {
-        const int x = bx * k + i;
-        if (x < W) m = fmaxf(m, __ldcg(Wp + (size_t)(y + 1) * pitch + x + PADL));
+    if ((k & 3) == 0 && bx * k + k <= W && by * k + k <= H) {  // whole block inside the raster: 16-byte loads
+      for (int j = 0; j < k; j++) {
+        const float4 *row = reinterpret_cast<const float4 *>(Wp + (size_t)(by * k + j + 1) * pitch + bx * k + PADL);
+        for (int i = 0; i < k / 4; i++) {
+          const float4 q = __ldcg(row + i);
+          m = fmaxf(fmaxf(m, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
+        }
+      }
+    } else {
+      for (int j = 0; j < k; j++) {
+        const int y = by * k + j;
+        if (y >= H) break;
+        for (int i = 0; i < k; i++) {
+          const int x = bx * k + i;
+          if (x < W) m = fmaxf(m, __ldcg(Wp + (size_t)(y + 1) * pitch + x + PADL));
+        }
       }
     }
     float *o = Wc + (size_t)(by + 1) * cpitch + bx + PADL;
@@ -635,19 +762,32 @@ __global__ void __launch_bounds__(256) fill_prolong_kernel(float *Wp, int pitch,
     if (!any) return;
   }
   bool lowered = false, lo_n = false, lo_s = false, lo_w = false, lo_e = false;
-  for (int c = threadIdx.x; c < TX * TY; c += blockDim.x) {
-    const int ly = c / TX, lx = c - ly * TX;
-    const int x = x0 + lx, y = y0 + ly;
-    if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1) continue;
-    const float l = __ldg(Wc + (size_t)((y + yoff) / k + coff_y) * cpitch + x / k + coff_x);
-    float *w = Wp + (size_t)(y + 1) * pitch + x + PADL;
-    if (l < *w) {
-      *w = l;
+  for (int g = threadIdx.x; g < TX * TY / 4; g += blockDim.x) {  // 4 cells per thread and step (16-byte accesses)
+    const int ly = g / (TX / 4), lx4 = (g - ly * (TX / 4)) * 4;
+    const int y = y0 + ly;
+    if (y < 1 || y >= H - 1) continue;
+    float4 *wp4 = reinterpret_cast<float4 *>(Wp + (size_t)(y + 1) * pitch + x0 + lx4 + PADL);
+    const float4 w4 = *wp4;
+    float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+    const float *crow = Wc + (size_t)((y + yoff) / k + coff_y) * cpitch + coff_x;
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int lx = lx4 + j, x = x0 + lx;
+      if (x < 1 || x >= W - 1) continue;
+      const float l = __ldg(crow + x / k);
+      if (l < wv[j]) {
+        wv[j] = l;
+        any = true;
+        lo_w |= lx == 0;
+        lo_e |= lx == TX - 1;
+      }
+    }
+    if (any) {
+      *wp4 = make_float4(wv[0], wv[1], wv[2], wv[3]);
       lowered = true;
       lo_n |= ly == 0;
       lo_s |= ly == TY - 1;
-      lo_w |= lx == 0;
-      lo_e |= lx == TX - 1;
     }
   }
   // a lowered cell on a tile edge is also part of the neighbouring tiles' aprons: wake every tile that reads it
@@ -773,7 +913,12 @@ struct FillState {
       const int n2 = (int)(2 * nt);
       fill_i32_kernel<<<(n2 + 255) / 256, 256, 0, c.stream>>>(keys.p, ORD_POS_INF, n2);
       dim3 blk(128), grd((pitch / 4 + 127) / 128, rows < 2048 ? rows : 2048);
-      if (d_coarse)
+      if (d_coarse && c.params.fill_drain_init) {
+        const int nb = 2 * pitch + rows * 2 * PADL;
+        fill_pad_border_kernel<<<(nb + 255) / 256, 256, 0, c.stream>>>(Zp.p, Wp.p, pitch, rows);
+        fill_init_drain_kernel<<<(unsigned)nt, 256, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, tilesX, d_coarse, coarse_w,
+                                                                  coarse_k, coarse_yoff);
+      } else if (d_coarse)
         fill_init_kernel<true><<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows, dev.p, d_coarse, coarse_w, coarse_k,
                                                          coarse_yoff);
       else
@@ -1381,6 +1526,16 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
     fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(reinterpret_cast<int *>(p), bits, (int)n);
     RDB_CK(cudaGetLastError());
   };
+  const bool trace0 = c.params.fill_trace != 0;
+  double t0_prev = 0;
+  auto lap0 = [&](const char *what) {
+    if (!trace0) return;
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (what) fprintf(stderr, "[mgpu fill trace] rank %d begin: %-32s %8.3f ms\n", comm_rank(comm), what, t - t0_prev);
+    t0_prev = t;
+  };
+  lap0(nullptr);
   if (mg) {
     wc = (w + k - 1) / k;
     hc = (H + k - 1) / k;
@@ -1394,9 +1549,12 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
       dim3 blk(256), grd((unsigned)((wc + 255) / 256), (unsigned)(hown / k + 2 < 4096 ? hown / k + 2 : 4096));
       fill_maxpool_rows(d_local + (size_t)gt * w, w, hown, row0 + gt, zc.p, wc, hc, k, grd, blk);
     }
+    lap0("max-pool own rows");
     comm_allreduce(comm, zc.p, nc, RDB200_MAX_F32);
+    lap0("all-reduce pooled raster");
     RDB_CK(cudaMemcpyAsync(wcoarse.p, zc.p, nc * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
     fill_depressions_level(wcoarse.p, wc, hc, 1);  // every rank fills the small raster itself
+    lap0("coarse fill (replicated)");
     for (int side = 0; side < 2; side++) {
       if (!(side == 0 ? gt : gb)) continue;
       const int y = side == 0 ? 0 : hloc - 1;
@@ -1404,10 +1562,12 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
     }
     RDB_CK(cudaGetLastError());
     st.begin(d_local, w, hloc, wcoarse.p, wc, k, row0);
+    lap0("band start (lifted)");
     cst.begin(zc.p, wc, hc, wcoarse.p, wc, 1);
     cst.run();
     cst.track_dirty();
     st.track_dirty();
+    lap0("coarse solver setup");
   } else {
     if (gt) fill_f32(d_local, (size_t)w, inf);
     if (gb) fill_f32(d_local + (size_t)(hloc - 1) * w, (size_t)w, inf);
@@ -1415,9 +1575,20 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
   }
   int cycles = 0;
   int *hflags = (int *)c.pinned + 1024;  // (FillState::run reads its control block back into the front of the scratch)
+  const bool trace = c.params.fill_trace != 0;  // per-phase timeline on stderr (adds stream syncs)
+  double t_prev = 0;
+  auto lap = [&](const char *what) {
+    if (!trace) return;
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    if (what) fprintf(stderr, "[mgpu fill trace] rank %d cycle %d: %-28s %8.3f ms\n", comm_rank(comm), cycles, what, t - t_prev);
+    t_prev = t;
+  };
+  lap(nullptr);
   for (;; cycles++) {
     if (cycles > 100000) fail("mgpu_fill: no convergence");
     const bool active = (st.run(world > 1 || mg ? R : 0) & 4) != 0;
+    lap("band sweeps");
     RDB_CK(cudaMemsetAsync(flags.p, 0, 4 * sizeof(int), c.stream));
     if (world > 1) {
       if (gt) st.read_row(1, send_up);
@@ -1425,25 +1596,32 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
       comm_exchange(comm, send_up, recv_up, send_dn, recv_dn, (size_t)w * sizeof(float));
       if (gt) st.ghost_update(0, recv_up, flags.p + 1);
       if (gb) st.ghost_update(hloc - 1, recv_dn, flags.p + 1);
+      lap("halo exchange");
     }
     if (mg) {
       fill_f32(bm.p, (size_t)wc * hc, -inf);
       st.blockmax_into(bm.p, wc, hc, k, row0, gt, hloc - gb);
+      lap("block maxima");
       comm_allreduce(comm, bm.p, (size_t)wc * hc, RDB200_MAX_F32);
+      lap("all-reduce coarse");
       cst.prolong_from(bm.p, wc, 0, 0, 1, 0, nullptr, 0, flags.p + 2);  // the coarse surface drops to the block maxima
       cst.run();
+      lap("coarse relaxation");
       st.prolong_from_level(cst, k, row0, flags.p + 3);
+      lap("prolongation");
     }
     if (active) fill_i32_kernel<<<1, 1, 0, c.stream>>>(flags.p, 1, 1);
     comm_allreduce(comm, flags.p, 4, RDB200_MAX_I32);
     RDB_CK(cudaMemcpyAsync(hflags, flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
     RDB_CK(cudaStreamSynchronize(c.stream));
+    lap("termination vote");
     if (!(hflags[0] | hflags[1] | hflags[2] | hflags[3])) break;
   }
   st.run(1);  // refresh the counters (no tile is active: an empty launch)
   const int64_t visits = st.visits_seen, iters = st.iters_seen, rounds = st.live_rounds;
   st.finish(d_local);
   RDB_CK(cudaStreamSynchronize(c.stream));
+  lap("finish");
   c.stats.fill_rounds = rounds + (mg ? cst.live_rounds : 0);
   c.stats.fill_tile_visits = visits;
   c.stats.fill_tile_iters = iters;

@@ -157,6 +157,7 @@ cudaError_t launch_coop(void (*f)(A...), dim3 grid, dim3 block, void **args, siz
 
 static inline void __syncthreads() { rdb_emu::sync_block(); }
 static inline int __syncthreads_count(int pred) { return rdb_emu::sync_block_count(pred); }
+static inline int __syncthreads_or(int pred) { return rdb_emu::sync_block_count(pred) != 0; }
 void rdb_emu_nanosleep();
 static inline void __nanosleep(unsigned) { rdb_emu_nanosleep(); }
 static inline void __threadfence() {}

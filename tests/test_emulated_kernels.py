@@ -107,7 +107,7 @@ def test_in_place_and_copy_semantics(emulated, gp):
     ("fill_ordered", 0), ("fill_max_iters", 1), ("fill_max_iters", 2), ("fill_rounds_per_sync", 1), ("fill_order_rounds", 40),
     ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
     ("accum_walk_lanes", 0), ("accum_fused_prep", 0), ("flats_uf_tiled", 0), ("flats_fused_classify", 0), ("flats_pair", 0), ("flowdirs_rolling", 0),
-    ("fill_multigrid", 4), ("fill_multigrid", 0), ("fill_vcycle", 0), ("fill_vcycle", 2),
+    ("fill_multigrid", 4), ("fill_multigrid", 0), ("fill_vcycle", 0), ("fill_vcycle", 2), ("fill_drain_init", 0),
 ])
 def test_algorithm_variants_agree(emulated, gp, checker, param, value):
     """Every tunable is a schedule / layout choice; none may change a result."""
