@@ -282,6 +282,8 @@ RDB200_API int rdb200_dev_fill_finish(rdb200_fill_state *state, float *d_out);
  * row band.  The local raster (elevations and accumulation) is ghost_top + owned + ghost_bottom
  * rows; ghost elevation rows must hold the neighbouring bands' rows.  The ghost rows of the
  * accumulation array are scratch (parking slots for flow that leaves the band).
+ * d_dem and d_accum_inout must stay valid until finish (the unit-weight D8 path computes the flow codes of the whole
+ * band in its first run, after the neighbours' edge codes have arrived).
  * Protocol per GPU: begin -> exchange edge codes (get_edge_codes / set_ghost_codes) ->
  *   repeat { run ; take_outflow per side ; exchange ; apply_inflow per side } until no rank sent
  *   anything -> finish.  See richdem_b200/sharded.py. */

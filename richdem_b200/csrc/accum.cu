@@ -990,6 +990,227 @@ __global__ void __launch_bounds__(256) accum_walk_packed_lanes_kernel(const uint
   }
 }
 
+// =================================================================================================
+// Unit-weight D-infinity on packed words (accum_dinf_packed, the default for FA_Tarboton without weights).
+// The level-synchronous kernel needs ~7000 grid barriers at 32768^2 and, per cell, two double atomics, a fence and two
+// counter atomics.  With unit weights every accumulation is a sum of products of proportions, so it is carried as a
+// 56-bit fixed-point number (24 fractional bits) next to the 8-bit donor count, exactly like the D8 words:
+//     [ 8 bits donors left | 56 bits sum * 2^24 ]
+// A donor's single atomicAdd(word, share - 2^56) delivers its share AND tells it whether it was the last donor.  The
+// walk has no levels: persistent lanes take sources from a per-warp queue; a lane follows the first receiver it completes
+// and queues the second one.  Rounding every share to 2^-24 keeps the relative error of any cell below 2^-23 (a cell of
+// accumulation A has at most ~2A upstream shares, each off by <= 2^-25), against the 1e-5 the results are specified to;
+// weighted accumulations keep the double-precision path.
+// =================================================================================================
+constexpr unsigned long long kFxOne = 1ull << 24;                    // one unit of flow
+constexpr unsigned long long kFxSource = (1ull << 63) | kFxOne;      // no donors, own unit, not started yet
+constexpr int kLaneQueueD = 256;                                      // per-warp ring (power of two)
+
+__global__ void __launch_bounds__(256) deps_gather_packed_dinf_x4_kernel(const uint8_t *__restrict__ code,
+                                                                          unsigned long long *__restrict__ word, int W, int H) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (x4 >= W) return;
+  for (int y = blockIdx.y; y < H; y += gridDim.y) {
+    const size_t i0 = (size_t)y * W + x4;
+    uint8_t r[3][6];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int yy = y + j - 1;
+      if (yy < 0 || yy >= H) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) r[j][k] = 0;
+      } else {
+        const uint8_t *row = code + (size_t)yy * W + x4;
+        const uchar4 m = *reinterpret_cast<const uchar4 *>(row);
+        r[j][1] = m.x; r[j][2] = m.y; r[j][3] = m.z; r[j][4] = m.w;
+        r[j][0] = x4 > 0 ? row[-1] : (uint8_t)0;
+        r[j][5] = x4 + 4 < W ? row[4] : (uint8_t)0;
+      }
+    }
+    unsigned long long out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int cc = r[1][k + 1];
+      if (cc == kCodeNoData) {
+        out[k] = 0xBFF0000000000000ull;  // -1.0 (flow_accumulation_generic.hpp:95-97)
+        continue;
+      }
+      const int nr[9] = {0, 1, 0, 0, 0, 1, 2, 2, 2};
+      const int nc[9] = {0, k, k, k + 1, k + 2, k + 2, k + 2, k + 1, k};
+      unsigned deps = 0;
+#pragma unroll
+      for (int n = 1; n <= 8; n++) {
+        const int cn = r[nr[n]][nc[n]];
+        if ((cn & 15) == 0 || cn == kCodeNoData) continue;
+        const int inv = d8_inverse(n);
+        const int first = cn & 15;
+        if (first == inv || ((cn & kCodeTwo) && nwrap(first + 1) == inv)) deps++;
+      }
+      out[k] = deps == 0 ? kFxSource : (((unsigned long long)deps << 56) | kFxOne);
+    }
+    reinterpret_cast<ulonglong2 *>(word + i0)[0] = make_ulonglong2(out[0], out[1]);
+    reinterpret_cast<ulonglong2 *>(word + i0)[1] = make_ulonglong2(out[2], out[3]);
+  }
+}
+
+__device__ __forceinline__ double fx_to_double(unsigned long long fx) { return (double)fx * (1.0 / 16777216.0); }
+
+// `frontier` (second and later launches): cells that were completed while their warp's ring was full; their word
+// already holds the final double.
+__global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_t *__restrict__ code,
+                                                                     const float *__restrict__ rmaxArr,
+                                                                     unsigned long long *word, int W, int ncells,
+                                                                     const int *__restrict__ frontier, int *cursor, int *spill,
+                                                                     int *spill_count) {
+  __shared__ int sQ[8][kLaneQueueD];
+  __shared__ unsigned long long sQa[8][kLaneQueueD];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int *q = sQ[threadIdx.x >> 5];
+  unsigned long long *qa = sQa[threadIdx.x >> 5];
+  const unsigned lt = (1u << lane) - 1u;
+  int head = 0, count = 0;  // warp-uniform ring state
+  int pos = 0, end = 0;     // warp-uniform: next candidate, end of the current chunk
+  bool more = true;
+  bool walking = false;
+  int c = 0;
+  unsigned long long acc = 0;
+  for (;;) {
+    // ---- refill from the source scan while the ring has room for a warp of sources plus a warp of hand-overs ----
+    while (count <= kLaneQueueD - 96) {
+      if (pos >= end) {
+        if (!more) break;
+        int b = 0;
+        if (lane == 0) b = atomicAdd(cursor, kLaneChunk);
+        b = __shfl_sync(full, b, 0);
+        if (b >= ncells) {
+          more = false;
+          break;
+        }
+        pos = b;
+        end = b + kLaneChunk < ncells ? b + kLaneChunk : ncells;
+      }
+      const int i = pos + lane;
+      bool src = false;
+      int cell = 0;
+      unsigned long long a0 = kFxOne;
+      if (i < end) {
+        if (frontier) {
+          cell = frontier[i];
+          src = true;
+          a0 = (unsigned long long)(__longlong_as_double((long long)word[cell]) * 16777216.0 + 0.5);
+        } else {
+          cell = i;
+          src = word[i] == kFxSource;
+        }
+      }
+      const unsigned bal = __ballot_sync(full, src);
+      if (src) {
+        const int slot = (head + count + __popc(bal & lt)) & (kLaneQueueD - 1);
+        q[slot] = cell;
+        qa[slot] = a0;
+      }
+      count += __popc(bal);
+      pos += 32;
+    }
+    __syncwarp();
+    // ---- hand queued cells to the lanes that are not walking ----
+    const unsigned idle = __ballot_sync(full, !walking);
+    if (idle == full && count == 0 && !more && pos >= end) break;
+    const int rank = __popc(idle & lt);
+    if (!walking && rank < count) {
+      const int slot = (head + rank) & (kLaneQueueD - 1);
+      c = q[slot];
+      acc = qa[slot];
+      if (!frontier && acc == kFxOne && word[c] == kFxSource) word[c] = (unsigned long long)__double_as_longlong(1.0);
+      walking = true;
+    }
+    {
+      const int nidle = __popc(idle);
+      const int taken = nidle < count ? nidle : count;
+      head = (head + taken) & (kLaneQueueD - 1);
+      count -= taken;
+    }
+    __syncwarp();
+    // ---- one walk step: push this cell's flow to its receiver(s) ----
+    int extra = -1;  // a second receiver completed by this lane in this step
+    unsigned long long extra_acc = 0;
+    if (walking) {
+      const int cd = code[c];
+      const int n1 = cd & 15;
+      if (cd == kCodeNoData || n1 == 0) {
+        walking = false;
+      } else {
+        const int r1 = c + d8dy(n1) * W + d8dx(n1);
+        int next = -1;
+        unsigned long long next_acc = 0;
+        if (cd & kCodeTwo) {
+          const int n2 = nwrap(n1 + 1);
+          const int r2 = c + d8dy(n2) * W + d8dx(n2);
+          float p1, p2;
+          tarboton_props(rmaxArr[c], &p1, &p2);
+          const double ad = (double)acc;
+          const unsigned long long v1 = p1 > 0 ? (unsigned long long)((double)p1 * ad + 0.5) : 0ull;
+          const unsigned long long v2 = p2 > 0 ? (unsigned long long)((double)p2 * ad + 0.5) : 0ull;
+          if (p1 > 0) {
+            const unsigned long long old = atomicAdd(word + r1, v1 - kPkOne);
+            if ((old >> 56) == 1ull) {
+              next = r1;
+              next_acc = (old & kPkVal) + v1;
+            }
+          }
+          if (p2 > 0) {
+            const unsigned long long old = atomicAdd(word + r2, v2 - kPkOne);
+            if ((old >> 56) == 1ull) {
+              const unsigned long long tot = (old & kPkVal) + v2;
+              if (next < 0) {
+                next = r2;
+                next_acc = tot;
+              } else {
+                extra = r2;
+                extra_acc = tot;
+              }
+            }
+          }
+        } else {
+          const unsigned long long old = atomicAdd(word + r1, acc - kPkOne);
+          if ((old >> 56) == 1ull) {
+            next = r1;
+            next_acc = (old & kPkVal) + acc;
+          }
+        }
+        if (next >= 0) {
+          word[next] = (unsigned long long)__double_as_longlong(fx_to_double(next_acc));
+          c = next;
+          acc = next_acc;
+        } else {
+          walking = false;
+        }
+        if (extra >= 0) word[extra] = (unsigned long long)__double_as_longlong(fx_to_double(extra_acc));
+      }
+    }
+    // ---- hand-overs: second completed receivers go to the ring (or, when it is full, to the global spill list) ----
+    {
+      const unsigned pb = __ballot_sync(full, extra >= 0);
+      if (pb) {
+        const int room = kLaneQueueD - count;
+        const int k = __popc(pb & lt);
+        if (extra >= 0) {
+          if (k < room) {
+            const int slot = (head + count + k) & (kLaneQueueD - 1);
+            q[slot] = extra;
+            qa[slot] = extra_acc;
+          } else {
+            spill[atomicAdd(spill_count, 1)] = extra;
+          }
+        }
+        const int np = __popc(pb);
+        count += np < room ? np : room;
+      }
+    }
+  }
+}
+
 template <bool BAND>
 void launch_walk_packed(const uint8_t *code, unsigned long long *word, int W, int ncells, const int *frontier,
                         int ghost_lo_end, int ghost_hi_start) {
@@ -1096,6 +1317,50 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     RDB_CK(cudaStreamSynchronize(c.stream));
     c.stats.ms_main_kernel += kt.ms();
     c.stats.accum_rounds = 1;
+    return;
+  }
+  if (dinf && ones && (w & 3) == 0 && ((uintptr_t)d_accum & 15) == 0 && c.params.accum_dinf_packed) {
+    // unit-weight D-infinity on packed fixed-point words (see accum_walk_dinf_lanes_kernel)
+    DevBuf<uint8_t> code(n);
+    DevBuf<float> rmax(n);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    unsigned long long *word = reinterpret_cast<unsigned long long *>(d_accum);
+    flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, 0);
+    dim3 blk(256), grd((w / 4 + 255) / 256, h < 8192 ? h : 8192);
+    deps_gather_packed_dinf_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, w, h);
+    RDB_CK(cudaGetLastError());
+    count_launch(2);
+    DevBuf<int> spill_a(n), spill_b(n), ctl(4);
+    int per_sm = 0;
+    RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_dinf_lanes_kernel, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    KernelTimer kt;
+    int ncells = (int)n;
+    const int *frontier = nullptr;
+    int *spill = spill_a.p;
+    int rounds = 0;
+    int *hc = (int *)c.pinned;
+    for (;;) {
+      RDB_CK(cudaMemsetAsync(ctl.p, 0, 4 * sizeof(int), c.stream));
+      long long nb = (long long)c.num_sms * per_sm;
+      const long long need = ((long long)ncells + kLaneChunk - 1) / kLaneChunk;
+      if (nb * 8 > need) nb = (need + 7) / 8;
+      accum_walk_dinf_lanes_kernel<<<(unsigned)nb, 256, 0, c.stream>>>(code.p, rmax.p, word, w, ncells, frontier, ctl.p, spill,
+                                                                       ctl.p + 1);
+      RDB_CK(cudaGetLastError());
+      count_launch();
+      rounds++;
+      RDB_CK(cudaMemcpyAsync(hc, ctl.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+      RDB_CK(cudaStreamSynchronize(c.stream));
+      if (hc[1] == 0) break;  // nothing spilled: done
+      ncells = hc[1];
+      frontier = spill;
+      spill = spill == spill_a.p ? spill_b.p : spill_a.p;
+    }
+    kt.stop_async();
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    c.stats.ms_main_kernel += kt.ms();
+    c.stats.accum_rounds = rounds;
     return;
   }
   DevBuf<uint8_t> code(n);

@@ -244,10 +244,10 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "fill_multigrid") p.fill_multigrid = value;
   else if (n == "fill_multigrid_min") p.fill_multigrid_min = value;
   else if (n == "fill_vcycle") p.fill_vcycle = value;
-  else if (n == "fill_drain_init") p.fill_drain_init = value;
   else if (n == "flats_uf_tiled") p.flats_uf_tiled = value;
   else if (n == "flowdirs_rolling") p.flowdirs_rolling = value;
   else if (n == "accum_packed") p.accum_packed = value;
+  else if (n == "accum_dinf_packed") p.accum_dinf_packed = value;
   else fail("rdb200_set_param: unknown parameter '%s'", name);
   CAPI_END
 }

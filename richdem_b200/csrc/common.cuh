@@ -64,13 +64,13 @@ struct Params {
   int64_t fill_trace = 0;       // 1: per-V-cycle timeline of the multigrid fill on stderr (adds stream syncs)
   int64_t fill_multigrid = 8;      // k >= 2: start the flood from the lifted fill of the k x k max-pooled raster (recursive)
   int64_t fill_vcycle = 8;         // with fill_multigrid: coarse-grid correction after every that many fine rounds (0: none)
-  int64_t fill_drain_init = 1;     // with fill_multigrid: the lifted start also follows steepest descent inside every tile
   int64_t fill_multigrid_min = 0;  // smallest raster side that still gets a coarse level (0: 1024)
   int64_t flowdirs_rolling = 1;  // d8_flow_directions with a rolling three-row register window (W % 4 == 0)
   int64_t flats_uf_tiled = 1;  // union-find: unite inside 64x16 tiles in shared memory first, then across tile seams
   int64_t flats_fused_classify = 1;  // FindFlats + FindFlatEdges in one shared-memory window pass (single-GPU path)
   int64_t flats_pair = 1;    // the two gradient solves run side by side on two streams
   int64_t flats_tiled = 1;   // flat-resolution gradients by the tile engine (0: one cooperative BFS launch each)
+  int64_t accum_dinf_packed = 1;  // unit-weight D-infinity: 56-bit fixed-point sums packed with the donor count, no levels
   int64_t accum_packed = 1;  // unit-weight D8: accumulator and donor count share one 64-bit word
   int64_t accum_fused_prep = 1;   // unit-weight D8: flow codes + donor counts + sole-donor bits in one rolling-window pass
   int64_t accum_walk_lanes = 1;   // unit-weight D8 walk: persistent always-busy lanes fed from per-warp source queues

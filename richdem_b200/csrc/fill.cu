@@ -477,123 +477,6 @@ __global__ void fill_init_kernel(const float *__restrict__ dem, float *__restric
   }
 }
 
-// Lifted start with drainage (fill_drain_init, the default with fill_multigrid): one block per tile.  The plain lift
-// gives every cell the water level of its k x k block, so on a slope all cells of a block start at the block's highest
-// elevation and the first sweep has to let them drain cell by cell.  But W*(c) <= max(Z(c), W*(n)) for every neighbour
-// n, so following steepest descent on Z (strictly decreasing, hence acyclic) from c to the cell e where the walk ends --
-// a pit or flat cell, a raster border cell, or the last cell before the walk leaves the tile towards a cell n' --
-// gives the bound  W*(c) <= max(Z(c), B(e))  with B(e) = lift(e) resp. max(Z(e), lift(n')).  The walk is resolved by
-// pointer jumping in shared memory.  Slope cells start at their final value Z(c); only pits and lakes are left to the
-// relaxation.  Writes the tile's cells of the padded Z and W arrays (fill_pad_border_kernel does the rim).
-constexpr int DI_P = TX + 3;  // shared-memory pitch of the (TX + 2)-wide staging arrays
-__global__ void __launch_bounds__(256) fill_init_drain_kernel(const float *__restrict__ dem, float *__restrict__ Zp,
-                                                               float *__restrict__ Wp, int W, int H, int pitch, int tilesX,
-                                                               const float *__restrict__ coarse, int Wc, int pool, int yoff) {
-  __shared__ float sZ[(TY + 2) * DI_P];
-  __shared__ float sL[(TY + 2) * DI_P];
-  __shared__ unsigned short sNext[TX * TY];
-  const float inf = __int_as_float(0x7f800000);
-  const int t = blockIdx.x;
-  const int tyT = t / tilesX, txT = t - tyT * tilesX;
-  const int x0 = txT * TX, y0 = tyT * TY;
-  for (int k = threadIdx.x; k < (TX + 2) * (TY + 2); k += blockDim.x) {
-    const int r = k / (TX + 2), cidx = k - r * (TX + 2);
-    const int x = x0 - 1 + cidx, y = y0 - 1 + r;
-    float z = inf, l = inf;
-    if (x >= 0 && y >= 0 && x < W && y < H) {
-      z = __ldg(dem + (size_t)y * W + x);
-      const bool border = (x == 0) | (y == 0) | (x == W - 1) | (y == H - 1);
-      l = border ? z : __ldg(coarse + (size_t)((y + yoff) / pool) * Wc + x / pool);
-    }
-    sZ[r * DI_P + cidx] = z;
-    sL[r * DI_P + cidx] = l;
-  }
-  __syncthreads();
-  // steepest-descent successor of every cell of the tile (itself: the walk ends here)
-  for (int c = threadIdx.x; c < TX * TY; c += blockDim.x) {
-    const int ly = c / TX, lx = c - ly * TX;
-    const int x = x0 + lx, y = y0 + ly;
-    const int o = (ly + 1) * DI_P + lx + 1;
-    int nxt = c;
-    if (x > 0 && y > 0 && x < W - 1 && y < H - 1) {
-      const float z = sZ[o];
-      float best = z;
-      int bdx = 0, bdy = 0;
-#pragma unroll
-      for (int n = 1; n <= 8; n++) {
-        const float zn = sZ[o + d8dy(n) * DI_P + d8dx(n)];
-        if (zn < best) {
-          best = zn;
-          bdx = d8dx(n);
-          bdy = d8dy(n);
-        }
-      }
-      if (bdx | bdy) {
-        const int nx = lx + bdx, ny = ly + bdy;
-        if (nx >= 0 && ny >= 0 && nx < TX && ny < TY) {
-          nxt = ny * TX + nx;
-        } else {  // the walk leaves the tile: this cell ends it, bounded through the outside neighbour's lifted level
-          const float b = fmaxf(z, sL[o + bdy * DI_P + bdx]);
-          if (b < sL[o]) sL[o] = b;
-        }
-      }
-    }
-    sNext[c] = (unsigned short)nxt;
-  }
-  __syncthreads();
-  // pointer jumping to the end of every walk
-  for (;;) {
-    int moved = 0;
-    unsigned short nn[(TX * TY + 255) / 256];
-    int q = 0;
-    for (int c = threadIdx.x; c < TX * TY; c += blockDim.x, q++) {
-      const unsigned short a = sNext[c];
-      const unsigned short b = sNext[a];
-      nn[q] = b;
-      moved |= a != b;
-    }
-    __syncthreads();
-    q = 0;
-    for (int c = threadIdx.x; c < TX * TY; c += blockDim.x, q++) sNext[c] = nn[q];
-    if (!__syncthreads_or(moved)) break;
-  }
-  // W0(c) = min(lift(c), max(Z(c), B(end of c's walk)))  and write-back, 4 cells per thread and step
-  for (int g = threadIdx.x; g < TX * TY / 4; g += blockDim.x) {
-    const int ly = g / (TX / 4), lx4 = (g - ly * (TX / 4)) * 4;
-    float zv[4], wv[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int c = ly * TX + lx4 + j;
-      const int o = (ly + 1) * DI_P + lx4 + j + 1;
-      const int e = sNext[c];
-      const int oe = (e / TX + 1) * DI_P + (e % TX) + 1;
-      zv[j] = sZ[o];
-      wv[j] = e == c ? sL[o] : fminf(sL[o], fmaxf(zv[j], sL[oe]));
-    }
-    const size_t po = (size_t)(y0 + ly + 1) * pitch + x0 + lx4 + PADL;
-    *reinterpret_cast<float4 *>(Zp + po) = make_float4(zv[0], zv[1], zv[2], zv[3]);
-    *reinterpret_cast<float4 *>(Wp + po) = make_float4(wv[0], wv[1], wv[2], wv[3]);
-  }
-}
-
-// the rim of the padded arrays that no tile covers: first / last padded row and the PADL columns on either side
-__global__ void __launch_bounds__(256) fill_pad_border_kernel(float *__restrict__ Zp, float *__restrict__ Wp, int pitch, int rows) {
-  const float inf = __int_as_float(0x7f800000);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 2 * pitch) {
-    const size_t o = (size_t)(i < pitch ? 0 : rows - 1) * pitch + (i < pitch ? i : i - pitch);
-    Zp[o] = inf;
-    Wp[o] = inf;
-  }
-  const int j = i - 2 * pitch;
-  if (j >= 0 && j < rows * 2 * PADL) {
-    const int r = j / (2 * PADL), k = j - r * (2 * PADL);
-    const size_t o = (size_t)r * pitch + (k < PADL ? k : pitch - 2 * PADL + k);
-    Zp[o] = inf;
-    Wp[o] = inf;
-  }
-}
-
 // sampled histogram of the input elevations (every `row_stride`-th padded row) for the level schedule
 constexpr int HIST_BINS = 1024;
 __global__ void __launch_bounds__(256) fill_hist_kernel(const float *__restrict__ Zp, int pitch, int rows, int row_stride,
@@ -719,12 +602,26 @@ __global__ void __launch_bounds__(256) fill_restrict_kernel(const float *__restr
 
 // band variant of the restriction: block maxima of rows [y_lo, y_hi) of a band whose row 0 is global row `yoff`,
 // max-combined into the full coarse array `out` (pre-filled with -inf; merged across bands by a MAX all-reduce)
+// `dirty` (may be null; used when k divides the tile shape and the band starts on a block boundary): blocks inside fine
+// tiles that no sweep has written since the last call report +inf, i.e. "leave the coarse level as it is".
 __global__ void __launch_bounds__(256) fill_blockmax_kernel(const float *__restrict__ Wp, int pitch, int W, int y_lo, int y_hi,
-                                                             int yoff, float *out, int Wcw, int Hc, int k) {
+                                                             int yoff, float *out, int Wcw, int Hc, int k,
+                                                             const int *__restrict__ dirty, int tilesX) {
   const int bx = blockIdx.x * blockDim.x + threadIdx.x;
   if (bx >= Wcw) return;
   const int by_lo = (yoff + y_lo) / k, by_hi = (yoff + y_hi - 1) / k;
   for (int by = by_lo + blockIdx.y; by <= by_hi && by < Hc; by += gridDim.y) {
+    if (dirty) {
+      // local rows of the block, clipped to the owned rows; with a ghost row on top they can straddle two tile rows
+      int l0 = by * k - yoff, l1 = l0 + k - 1;
+      l0 = l0 < y_lo ? y_lo : l0;
+      l1 = l1 >= y_hi ? y_hi - 1 : l1;
+      const int tx = (bx * k) / TX;
+      if (!dirty[(l0 / TY) * tilesX + tx] && !dirty[(l1 / TY) * tilesX + tx]) {
+        out[(size_t)by * Wcw + bx] = __int_as_float(0x7f800000);
+        continue;
+      }
+    }
     float m = -__int_as_float(0x7f800000);
     for (int j = 0; j < k; j++) {
       const int y = by * k + j - yoff;  // local row
@@ -913,12 +810,7 @@ struct FillState {
       const int n2 = (int)(2 * nt);
       fill_i32_kernel<<<(n2 + 255) / 256, 256, 0, c.stream>>>(keys.p, ORD_POS_INF, n2);
       dim3 blk(128), grd((pitch / 4 + 127) / 128, rows < 2048 ? rows : 2048);
-      if (d_coarse && c.params.fill_drain_init) {
-        const int nb = 2 * pitch + rows * 2 * PADL;
-        fill_pad_border_kernel<<<(nb + 255) / 256, 256, 0, c.stream>>>(Zp.p, Wp.p, pitch, rows);
-        fill_init_drain_kernel<<<(unsigned)nt, 256, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, tilesX, d_coarse, coarse_w,
-                                                                  coarse_k, coarse_yoff);
-      } else if (d_coarse)
+      if (d_coarse)
         fill_init_kernel<true><<<grd, blk, 0, c.stream>>>(d_dem, Zp.p, Wp.p, W, H, pitch, rows, dev.p, d_coarse, coarse_w, coarse_k,
                                                          coarse_yoff);
       else
@@ -1189,12 +1081,16 @@ struct FillState {
     cs.seed_from_flags();
     clear_dirty();
   }
-  void blockmax_into(float *d_out, int wc, int hc, int k, int yoff, int y_lo, int y_hi) {
+  // selective = true: only blocks in tiles written since the last call are evaluated (the others report +inf = "no news")
+  // and the dirty flags are cleared; needs track_dirty()
+  void blockmax_into(float *d_out, int wc, int hc, int k, int yoff, int y_lo, int y_hi, bool selective = false) {
     Ctx &c = ctx();
     dim3 blk(256), grd((unsigned)((wc + 255) / 256), (unsigned)((y_hi - y_lo) / k + 2 < 4096 ? (y_hi - y_lo) / k + 2 : 4096));
-    fill_blockmax_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, pitch, W, y_lo, y_hi, yoff, d_out, wc, hc, k);
+    const bool sel = selective && dirty.p && TX % k == 0;  // (columns of a block then lie in one tile column)
+    fill_blockmax_kernel<<<grd, blk, 0, c.stream>>>(Wp.p, pitch, W, y_lo, y_hi, yoff, d_out, wc, hc, k, sel ? dirty.p : nullptr, tilesX);
     RDB_CK(cudaGetLastError());
     count_launch();
+    if (sel) clear_dirty();
   }
   // prolongation from a coarse surface stored with row pitch `cpitch` and first cell at (coff_x, coff_y); `cdirty`
   // (optional, with its tile-grid width): coarse tiles written by the coarse relaxation -- everything else is skipped.
@@ -1337,6 +1233,8 @@ void geodesic_distance_pair_dev(const uint8_t *d_open, int open_bit, float *d_wa
       lane(k, [&](FillState &s) {
         s.timed = false;
         s.begin_dist(d_open, open_bit, wbuf[k], w, h);
+        // a sweep launch fills every CTA slot of the GPU; two of them only run side by side when each takes half
+        s.grid = s.grid > 1 ? s.grid / 2 : 1;
       });
     }
     const int per_sync = (int)(c.params.fill_rounds_per_sync > 0 ? c.params.fill_rounds_per_sync : 16);
@@ -1574,6 +1472,7 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
     st.begin(d_local, w, hloc);
   }
   int cycles = 0;
+  bool vcycle_on = true;
   int *hflags = (int *)c.pinned + 1024;  // (FillState::run reads its control block back into the front of the scratch)
   const bool trace = c.params.fill_trace != 0;  // per-phase timeline on stderr (adds stream syncs)
   double t_prev = 0;
@@ -1598,9 +1497,12 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
       if (gb) st.ghost_update(hloc - 1, recv_dn, flags.p + 1);
       lap("halo exchange");
     }
-    if (mg) {
+    // the coarse-grid correction is dropped for good once a cycle's correction moved nothing on any rank: what is left
+    // are local repairs next to the seams, and the correction's fixed cost (the all-reduce of the pooled raster and the
+    // coarse relaxation on every rank) would be paid for nothing
+    if (mg && vcycle_on) {
       fill_f32(bm.p, (size_t)wc * hc, -inf);
-      st.blockmax_into(bm.p, wc, hc, k, row0, gt, hloc - gb);
+      st.blockmax_into(bm.p, wc, hc, k, row0, gt, hloc - gb, true);
       lap("block maxima");
       comm_allreduce(comm, bm.p, (size_t)wc * hc, RDB200_MAX_F32);
       lap("all-reduce coarse");
@@ -1616,6 +1518,7 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
     RDB_CK(cudaStreamSynchronize(c.stream));
     lap("termination vote");
     if (!(hflags[0] | hflags[1] | hflags[2] | hflags[3])) break;
+    if (!(hflags[2] | hflags[3])) vcycle_on = false;
   }
   st.run(1);  // refresh the counters (no tile is active: an empty launch)
   const int64_t visits = st.visits_seen, iters = st.iters_seen, rounds = st.live_rounds;

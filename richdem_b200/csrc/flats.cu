@@ -19,6 +19,7 @@
 // frontier length from device memory, so the host only synchronises every few levels.
 #include "common.cuh"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 
@@ -183,15 +184,25 @@ __global__ void __launch_bounds__(256) flats_classify_edges_kernel(const float *
         if (x + j < W) o[j] = out[j];
     }
   }
+  // one atomic per counter and block (a per-warp atomic on three fixed addresses serialises at L2: at 32768^2 that
+  // was most of this kernel's time)
   for (int o = 16; o > 0; o >>= 1) {
     nflat += __shfl_xor_sync(0xffffffffu, nflat, o);
     nlow += __shfl_xor_sync(0xffffffffu, nlow, o);
     nhigh += __shfl_xor_sync(0xffffffffu, nhigh, o);
   }
+  __shared__ int sCnt[3][8];
   if ((threadIdx.x & 31) == 0) {
-    if (nflat) atomicAdd(&dev->n_flat, nflat);
-    if (nlow) atomicAdd(&dev->n_low, nlow);
-    if (nhigh) atomicAdd(&dev->n_high, nhigh);
+    sCnt[0][threadIdx.x >> 5] = nflat;
+    sCnt[1][threadIdx.x >> 5] = nlow;
+    sCnt[2][threadIdx.x >> 5] = nhigh;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) tot += sCnt[threadIdx.x][k];
+    if (tot) atomicAdd(threadIdx.x == 0 ? &dev->n_flat : (threadIdx.x == 1 ? &dev->n_low : &dev->n_high), tot);
   }
 }
 
@@ -501,9 +512,8 @@ __global__ void __launch_bounds__(256) flats_apply_x4_kernel(float *dem, const i
                                                               const int *__restrict__ away, const int *__restrict__ tw,
                                                               const int *__restrict__ Hh, int W, int H, FlatDev *dev) {
   const size_t n4 = (size_t)W * H / 4;
-  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int raised = 0;
-  if (q < n4) {
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
     const int4 lab = __ldg(reinterpret_cast<const int4 *>(labels) + q);
     if (lab.x | lab.y | lab.z | lab.w) {
       const int4 t4 = __ldg(reinterpret_cast<const int4 *>(tw) + q);
@@ -529,7 +539,15 @@ __global__ void __launch_bounds__(256) flats_apply_x4_kernel(float *dem, const i
     }
   }
   for (int o = 16; o > 0; o >>= 1) raised += __shfl_xor_sync(0xffffffffu, raised, o);
-  if ((threadIdx.x & 31) == 0 && raised) atomicAdd(&dev->n_raised, raised);
+  __shared__ int sR[8];
+  if ((threadIdx.x & 31) == 0) sR[threadIdx.x >> 5] = raised;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) tot += sR[k];
+    if (tot) atomicAdd(&dev->n_raised, tot);  // one atomic per (persistent) block
+  }
 }
 
 // label = root+1 for data cells of components holding a low edge, else 0 (Barnes2014.hpp:437-441)
@@ -720,7 +738,8 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   c.stats.flat_bfs_levels = levels;
 
   if (apply && !d_mask_out && !d_labels_out && (w & 3) == 0 && ((uintptr_t)d_dem & 15) == 0 && c.params.flats_fused_classify)
-    flats_apply_x4_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, c.stream>>>(d_dem, labels.p, away.p, tw.p, Hh.p, w, h, dev.p);
+    flats_apply_x4_kernel<<<(unsigned)std::min<size_t>((n / 4 + 255) / 256, (size_t)c.num_sms * 16), 256, 0, c.stream>>>(
+        d_dem, labels.p, away.p, tw.p, Hh.p, w, h, dev.p);
   else
     flats_apply_kernel<<<blocks, 256, 0, c.stream>>>(d_dem, labels.p, away.p, tw.p, Hh.p, d_mask_out, d_labels_out, w, h,
                                                      apply ? 1 : 0, dev.p);

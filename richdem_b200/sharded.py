@@ -361,6 +361,7 @@ class CudaBandAccumulator:
         self.h, self.w = local_dem.shape
         self.dev = local_dem.device
         self.dinf = dinf
+        self._dem, self._accum = local_dem, local_accum  # the library reads the elevations again at the first run
         self._state = C.c_void_p()
         _lib.check(self.L.rdb200_dev_facc_begin(C.byref(self._state), local_dem.data_ptr(), local_accum.data_ptr(),
                                                 self.w, self.h, float(nodata), int(g_top), int(g_bot), int(dinf),

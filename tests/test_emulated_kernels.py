@@ -106,8 +106,8 @@ def test_in_place_and_copy_semantics(emulated, gp):
 @pytest.mark.parametrize("param,value", [
     ("fill_ordered", 0), ("fill_max_iters", 1), ("fill_max_iters", 2), ("fill_rounds_per_sync", 1), ("fill_order_rounds", 40),
     ("flats_tiled", 0), ("accum_packed", 0), ("accum_budget", 1), ("accum_budget", 64),
-    ("accum_walk_lanes", 0), ("accum_fused_prep", 0), ("flats_uf_tiled", 0), ("flats_fused_classify", 0), ("flats_pair", 0), ("flowdirs_rolling", 0),
-    ("fill_multigrid", 4), ("fill_multigrid", 0), ("fill_vcycle", 0), ("fill_vcycle", 2), ("fill_drain_init", 0),
+    ("accum_walk_lanes", 0), ("accum_fused_prep", 0), ("flats_uf_tiled", 0), ("flats_fused_classify", 0), ("flats_pair", 0), ("flowdirs_rolling", 0), ("accum_dinf_packed", 0),
+    ("fill_multigrid", 4), ("fill_multigrid", 0), ("fill_vcycle", 0), ("fill_vcycle", 2),
 ])
 def test_algorithm_variants_agree(emulated, gp, checker, param, value):
     """Every tunable is a schedule / layout choice; none may change a result."""
@@ -166,7 +166,7 @@ def test_band_accumulation(band_drivers, checker, G, dinf):
     if dinf == "nolanes":  # unit-weight D8 with one thread per source instead of the persistent-lane walk
         _lib.set_param("accum_walk_lanes", 0)
         dinf = False
-    dem = oracle.fbm_terrain(260, 210, seed=41, quantum=0.25)
+    dem = oracle.fbm_terrain(260, 212, seed=41, quantum=0.25)  # W % 4 == 0: the packed / fused band path
     dem[100:140, 60:120] = nd
     resolved = checker.resolve_flats(checker.fill_depressions(dem), nd)
     got, _ = band_drivers.emulate_fa_bands(resolved, G, nd, dinf)
