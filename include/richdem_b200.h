@@ -87,6 +87,12 @@ RDB200_API int rdb200_set_param(const char *name, int64_t value);
  *   reference).  Result is bit-identical to the reference. */
 RDB200_API int rdb200_fill_depressions_d8_f32(float *dem, int32_t width, int32_t height);
 
+/* richdem::FillDepressions<Topology::D4>(Array2D<float>&)
+ *   include/richdem/depressions/depressions.hpp:16-17 -> PriorityFlood_Barnes2014<Topology::D4>,
+ *   include/richdem/depressions/Barnes2014.hpp:230-304 (pyrichdem: rdFillDepressionsD4, pywrapper.hpp:33).
+ *   Same engine with the 4-neighbour stencil; bit-identical. */
+RDB200_API int rdb200_fill_depressions_d4_f32(float *dem, int32_t width, int32_t height);
+
 /* richdem::ResolveFlatsEpsilon(Array2D<float>&)
  *   include/richdem/flats/flats.hpp:21-28 (GetFlatMask + ResolveFlatsEpsilon_Barnes2014,
  *   include/richdem/flats/Barnes2014.hpp:398-467, 496-550); pyrichdem rdResolveFlatsEpsilon
@@ -167,6 +173,7 @@ RDB200_API int rdb200_fa_tarboton_f32_f64(const float *dem, double *accum_inout,
 /* ---- device entry points (pointers into HBM of the current device) ----------------- */
 
 RDB200_API int rdb200_dev_fill_depressions_d8_f32(float *d_dem, int32_t width, int32_t height);
+RDB200_API int rdb200_dev_fill_depressions_d4_f32(float *d_dem, int32_t width, int32_t height);
 RDB200_API int rdb200_dev_resolve_flats_epsilon_f32(float *d_dem, int32_t width, int32_t height, float nodata);
 RDB200_API int rdb200_dev_d8_flow_directions_f32(const float *d_dem, uint8_t *d_flowdirs, int32_t width,
                                       int32_t height, float nodata);

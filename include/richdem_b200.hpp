@@ -42,6 +42,10 @@ void fill_depressions_d8(A2 &dem) {
   check(rdb200_fill_depressions_d8_f32(dem.data(), dem.width(), dem.height()));
 }
 template <class A2>
+void fill_depressions_d4(A2 &dem) {
+  check(rdb200_fill_depressions_d4_f32(dem.data(), dem.width(), dem.height()));
+}
+template <class A2>
 void resolve_flats_epsilon(A2 &dem) {
   check(rdb200_resolve_flats_epsilon_f32(dem.data(), dem.width(), dem.height(), (float)dem.noData()));
 }
@@ -129,6 +133,16 @@ namespace richdem {
 template <>
 inline void FillDepressions<Topology::D8, float>(Array2D<float> &dem) {
   richdem_b200::fill_depressions_d8(dem);
+}
+// depressions/depressions.hpp:16-17 (D4 -> PriorityFlood_Barnes2014<D4>, Barnes2014.hpp:230-304; pyrichdem binds the
+// latter as rdFillDepressionsD4, pywrapper.hpp:33)
+template <>
+inline void FillDepressions<Topology::D4, float>(Array2D<float> &dem) {
+  richdem_b200::fill_depressions_d4(dem);
+}
+template <>
+inline void PriorityFlood_Barnes2014<Topology::D4, float>(Array2D<float> &dem) {
+  richdem_b200::fill_depressions_d4(dem);
 }
 // depressions/Zhou2016.hpp:125-191 -- what FillDepressions<D8> dispatches to, and what pyrichdem binds directly as
 // rdFillDepressionsD8 (wrappers/pyrichdem/src/pywrapper.hpp:32)

@@ -69,7 +69,7 @@ class _Backend:
         self._fm_method = self._sig(n["fm_method"], [C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_double, _f32p])
         self._fa_method = self._sig(n["fa_method"], [C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_double, _f64p])
         self._extra = {}
-        for k in ("fill_zhou", "fill_barnes", "fill_original"):
+        for k in ("fill_zhou", "fill_barnes", "fill_original", "fill_d4"):
             if k in n:
                 self._extra[k] = self._sig(n[k], [_f32p, C.c_int, C.c_int])
 
@@ -203,6 +203,7 @@ _PORT_NAMES = dict(
     d8acc_i32="orc_d8_flow_accum_i32", fm_d8="orc_fm_d8_f32", fm_dinf="orc_fm_tarboton_f32",
     facc="orc_flow_accumulation_props_f64", fa_d8="orc_fa_d8_f32_f64",
     fa_dinf="orc_fa_tarboton_f32_f64", fm_method="orc_fm_method_f32", fa_method="orc_fa_method_f32_f64",
+    fill_d4="orc_fill_depressions_d4_f32",
 )
 _REF_NAMES = dict(
     kind="reference",
@@ -213,7 +214,7 @@ _REF_NAMES = dict(
     facc="ref_flow_accumulation_props_f64", fa_d8="ref_fa_d8_f32_f64",
     fa_dinf="ref_fa_tarboton_f32_f64", fm_method="ref_fm_method_f32", fa_method="ref_fa_method_f32_f64",
     fill_zhou="ref_priority_flood_zhou2016_f32", fill_barnes="ref_priority_flood_barnes2014_f32",
-    fill_original="ref_priority_flood_original_f32",
+    fill_original="ref_priority_flood_original_f32", fill_d4="ref_fill_depressions_d4_f32",
 )
 
 _port = None

@@ -109,7 +109,7 @@ static int64_t fifo_pop(Fifo *q) { return q->a[q->head++]; }
 /* same raster (the reference's tests assert that: tests/tests.cpp:238-271); the output is*/
 /* the unique min-over-paths-of-max-elevation surface, so queue order does not matter.    */
 /* NoData is NOT special-cased (neither reference function looks at it).                  */
-void orc_fill_depressions_d8_f32(float *dem, int w, int h) {
+static void orc_fill_topo(float *dem, int w, int h, int d4) {
   const size_t n = (size_t)w * h;
   uint8_t *closed = (uint8_t *)calloc(n, 1);
   Heap open = {0, 0, 0};
@@ -153,6 +153,7 @@ void orc_fill_depressions_d8_f32(float *dem, int w, int h) {
     }
     const int cx = (int)(ci % w), cy = (int)(ci / w);
     for (int k = 1; k <= 8; k++) {
+      if (d4 && !(k & 1)) continue; /* D4 (common/constants.hpp:53-54): the cardinal neighbours are the odd D8 codes */
       const int nx = cx + D8X[k], ny = cy + D8Y[k];
       if (nx < 0 || ny < 0 || nx >= w || ny >= h) continue;
       const size_t ni = (size_t)ny * w + nx;
@@ -174,6 +175,10 @@ void orc_fill_depressions_d8_f32(float *dem, int w, int h) {
   free(pit.a);
   free(pitlev.a);
 }
+
+void orc_fill_depressions_d8_f32(float *dem, int w, int h) { orc_fill_topo(dem, w, h, 0); }
+/* FillDepressions<Topology::D4> = PriorityFlood_Barnes2014<D4> (depressions/depressions.hpp:16-17) */
+void orc_fill_depressions_d4_f32(float *dem, int w, int h) { orc_fill_topo(dem, w, h, 1); }
 
 /* ------------------------------------------------------------------------------------ */
 /* a3  FindFlats  (flats/find_flats.hpp:28-69)                                            */

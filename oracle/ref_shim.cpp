@@ -34,6 +34,12 @@ void ref_fill_depressions_d8_f32(float *dem, int w, int h) {
   FillDepressions<Topology::D8>(a);
 }
 
+// depressions/depressions.hpp:16-17 -> depressions/Barnes2014.hpp:230-304 with the 4-neighbour topology
+void ref_fill_depressions_d4_f32(float *dem, int w, int h) {
+  Array2D<float> a(dem, w, h);
+  FillDepressions<Topology::D4>(a);
+}
+
 // depressions/Zhou2016.hpp:125-191 (the function pyrichdem binds, pywrapper.hpp:32)
 void ref_priority_flood_zhou2016_f32(float *dem, int w, int h) {
   Array2D<float> a(dem, w, h);

@@ -121,22 +121,21 @@ def _nodata_f32(dem) -> float:
 
 def FillDepressions(dem: rdarray, epsilon: bool = False, in_place: bool = False,
                     topology: str = "D8") -> Optional[rdarray]:
-    """Fills all depressions in a DEM (reference FillDepressions, :381-422 ->
-    PriorityFlood_Zhou2016).  Returns the filled DEM unless ``in_place``."""
+    """Fills all depressions in a DEM (reference FillDepressions, :381-422 -> PriorityFlood_Zhou2016 for ``D8``,
+    PriorityFlood_Barnes2014<D4> for ``D4``).  Returns the filled DEM unless ``in_place``."""
     if type(dem) is not rdarray:
         raise Exception("A richdem.rdarray or numpy.ndarray is required!")
     if topology not in ["D8", "D4"]:
         raise Exception("Unknown topology!")
     if epsilon:
         raise Exception("FillDepressions(epsilon=True) is outside the B200 hot path (SURVEY 8f-3)")
-    if topology != "D8":
-        raise Exception("FillDepressions(topology='D4') is outside the B200 hot path")
     if not in_place:
         dem = dem.copy()
     _add_analysis(dem, f"FillDepressions(dem, epsilon={epsilon})")
     d = _dem_f32(dem, "FillDepressions")
     h, w = d.shape
-    _lib.check(_lib.lib().rdb200_fill_depressions_d8_f32(_lib.ptr(d), w, h))
+    fn = _lib.lib().rdb200_fill_depressions_d8_f32 if topology == "D8" else _lib.lib().rdb200_fill_depressions_d4_f32
+    _lib.check(fn(_lib.ptr(d), w, h))
     if not in_place:
         return dem
     return None

@@ -42,6 +42,8 @@ SIGNATURES = {
     "rdb200_get_stats": [C.POINTER(Stats)],
     "rdb200_set_param": [C.c_char_p, C.c_int64],
     "rdb200_fill_depressions_d8_f32": [_vp, _i32, _i32],
+    "rdb200_fill_depressions_d4_f32": [_vp, _i32, _i32],
+    "rdb200_dev_fill_depressions_d4_f32": [_vp, _i32, _i32],
     "rdb200_resolve_flats_epsilon_f32": [_vp, _i32, _i32, _f32],
     "rdb200_get_flat_mask_f32": [_vp, _vp, _vp, _i32, _i32, _f32],
     "rdb200_d8_flow_directions_f32": [_vp, _vp, _i32, _i32, _f32],

@@ -1076,8 +1076,9 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
   int c = 0;
   unsigned long long acc = 0;
   for (;;) {
-    // ---- refill from the source scan while the ring has room for a warp of sources plus a warp of hand-overs ----
-    while (count <= kLaneQueueD - 96) {
+    // ---- refill from the source scan only when the lanes would otherwise starve: the ring's room belongs to the
+    // hand-overs (a ring kept full by the scan overflows into the spill list, which costs a whole extra launch) ----
+    while (count < 32) {
       if (pos >= end) {
         if (!more) break;
         int b = 0;

@@ -268,6 +268,20 @@ int rdb200_fill_depressions_d8_f32(float *dem, int32_t w, int32_t h) {
   CAPI_END
 }
 
+int rdb200_fill_depressions_d4_f32(float *dem, int32_t w, int32_t h) {
+  CAPI_TRY
+  if (!dem) fail("fill_depressions: null dem");
+  check_dims(w, h);
+  CallScope cs((int64_t)w * h);
+  const size_t n = (size_t)w * h;
+  DevBuf<float> d(n);
+  h2d(d.p, dem, n);
+  fill_depressions_dev(d.p, w, h, true);
+  d2h(dem, d.p, n);
+  cs.done();
+  CAPI_END
+}
+
 int rdb200_resolve_flats_epsilon_f32(float *dem, int32_t w, int32_t h, float nodata) {
   CAPI_TRY
   if (!dem) fail("resolve_flats: null dem");
@@ -459,6 +473,9 @@ int rdb200_fa_tarboton_f32_f64(const float *dem, double *accum, int32_t w, int32
 
 int rdb200_dev_fill_depressions_d8_f32(float *d_dem, int32_t w, int32_t h) {
   DEV_ENTRY((int64_t)w * h, (check_dims(w, h), fill_depressions_dev(d_dem, w, h)))
+}
+int rdb200_dev_fill_depressions_d4_f32(float *d_dem, int32_t w, int32_t h) {
+  DEV_ENTRY((int64_t)w * h, (check_dims(w, h), fill_depressions_dev(d_dem, w, h, true)))
 }
 int rdb200_dev_resolve_flats_epsilon_f32(float *d_dem, int32_t w, int32_t h, float nodata) {
   DEV_ENTRY((int64_t)w * h, (check_dims(w, h), resolve_flats_dev(d_dem, w, h, nodata, nullptr, nullptr, true)))

@@ -158,7 +158,7 @@ void mgpu_fa_band(const rdb200_comm *comm, const float *d_dem, double *d_accum, 
                   bool dinf, bool ones, int *xrounds);
 
 // ---- stage entry points implemented in the .cu files (device pointers, ctx stream) -------
-void fill_depressions_dev(float *d_dem, int w, int h);
+void fill_depressions_dev(float *d_dem, int w, int h, bool topo4 = false);
 void geodesic_distance_dev(const uint8_t *d_open, int open_bit, float *d_w_inout, int w, int h);
 void geodesic_distance_pair_dev(const uint8_t *d_open, int open_bit, float *d_wa, float *d_wb, int w, int h);
 rdb200_fill_state *new_band_distance_state(const uint8_t *d_open, int open_bit, const float *d_winit, int w, int h,

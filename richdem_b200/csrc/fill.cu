@@ -187,7 +187,8 @@ __device__ __forceinline__ float min3f(float a, float b, float c) { return fminf
 // STEP = 0: depression filling,     new = min(W, max(Z, min8 W))
 // STEP = 1: geodesic distance,      new = min(W, max(Z, 1 + min8 W))   with Z = 0 on cells the flood
 //           may enter and +inf elsewhere (used for the flat-resolution gradients, csrc/flats.cu)
-template <int STEP>
+// TOPO4: the 4-neighbour (D4) stencil of FillDepressions<Topology::D4>; corner aprons are then never read
+template <int STEP, bool TOPO4 = false>
 __global__ void __launch_bounds__(FILL_THREADS, FILL_MIN_CTAS)
     fill_sweep_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapZ,
                       const FillArgs a) {
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(256) fill_hist_kernel(const float *__restrict_
 __global__ void __launch_bounds__(128) dist_pad_init_kernel(const uint8_t *__restrict__ open, int open_bit,
                                                              const float *__restrict__ winit, float *__restrict__ Zp,
                                                              float *__restrict__ Wp, int W, int H, int pitch, int rows,
-                                                             int ghost_top, int ghost_bottom) {
+                                                             int ghost_top, int ghost_bottom, int *tile_flag, int tilesX) {
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
   if (px >= pitch) return;
   const float inf = __int_as_float(0x7f800000);
@@ -518,6 +519,17 @@ __global__ void __launch_bounds__(128) dist_pad_init_kernel(const uint8_t *__res
       if (!((ghost_top && y == 0) || (ghost_bottom && y == H - 1))) {
         if (open[i] & open_bit) zz = 0.0f;
         ww = winit[i];
+        if (ww < inf) {
+          // only tiles that can see a seed (inside, or in their apron) have anything to do in the first round
+          const int ya = y > 0 ? y - 1 : 0, yb = y < H - 1 ? y + 1 : H - 1, xa = x > 0 ? x - 1 : 0, xb = x < W - 1 ? x + 1 : W - 1;
+          const int ty0 = ya / TY, ty1 = yb / TY, tx0 = xa / TX, tx1 = xb / TX;
+          tile_flag[ty0 * tilesX + tx0] = 1;
+          if (tx1 != tx0) tile_flag[ty0 * tilesX + tx1] = 1;
+          if (ty1 != ty0) {
+            tile_flag[ty1 * tilesX + tx0] = 1;
+            if (tx1 != tx0) tile_flag[ty1 * tilesX + tx1] = 1;
+          }
+        }
       }
     }
     Zp[(size_t)py * pitch + px] = zz;
@@ -763,6 +775,7 @@ struct FillState {
   bool first_run = true;
   bool ordered = false;
   int step_mode = 0;  // 0: fill, 1: geodesic distance
+  bool topo4 = false;  // D4 fill (4-neighbour stencil)
   std::vector<float> levels;
   DevBuf<FillDev> dev;
   CUtensorMap mapW, mapZ;
@@ -874,7 +887,7 @@ struct FillState {
   }
 
   // Geodesic-distance mode: `open` marks the cells the flood may enter (bit `open_bit`), `winit`
-  // holds +inf or the seed distance of every cell.  Every tile is seeded once.
+  // holds +inf or the seed distance of every cell.  The first round visits the tiles that hold or touch a seed.
   void begin_dist(const uint8_t *d_open, int open_bit, const float *d_winit, int w, int h, int ghost_top = 0,
                   int ghost_bottom = 0) {
     Ctx &c = ctx();
@@ -902,8 +915,9 @@ struct FillState {
     const int n2 = (int)(2 * nt);
     fill_i32_kernel<<<(n2 + 255) / 256, 256, 0, c.stream>>>(keys.p, ORD_POS_INF, n2);
     dim3 blk(128), grd((pitch + 127) / 128, rows < 2048 ? rows : 2048);
+    clear_flags();
     dist_pad_init_kernel<<<grd, blk, 0, c.stream>>>(d_open, open_bit, d_winit, Zp.p, Wp.p, W, H, pitch, rows, ghost_top,
-                                                    ghost_bottom);
+                                                    ghost_bottom, tflag.p, tilesX);
     RDB_CK(cudaGetLastError());
     count_launch(2);
     ordered = false;
@@ -914,9 +928,7 @@ struct FillState {
     if (per_sm < 1) per_sm = 1;
     grid = c.num_sms * per_sm;
     round = 1;
-    std::vector<int> init((size_t)nt);
-    for (size_t t = 0; t < nt; t++) init[t] = (int)t;
-    seed_worklist(init);
+    seed_from_flags();  // the tiles that hold or touch a seed
   }
 
   // add `tiles` to the worklist of the next round to be launched (always eligible: key = -inf,
@@ -982,6 +994,7 @@ struct FillState {
       }
       sched_round++;
       if (step_mode) fill_sweep_kernel<1><<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
+      else if (topo4) fill_sweep_kernel<0, true><<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
       else fill_sweep_kernel<0><<<grid, FILL_THREADS, 0, c.stream>>>(mapW, mapZ, a);
       round++;
     }
@@ -1269,11 +1282,12 @@ void geodesic_distance_pair_dev(const uint8_t *d_open, int open_bit, float *d_wa
 // upper bound because the cells of a block are connected below the block's maximum and 8-adjacent blocks contain
 // 8-adjacent cells, so every coarse path lifts to a fine path that is nowhere higher; border blocks contain a border
 // cell.  On the CPU model of the schedule this cuts the dependent rounds 3.5x and the tile visits by 20-40 %.
-static void fill_depressions_level(float *d_dem, int w, int h, int depth) {
+static void fill_depressions_level(float *d_dem, int w, int h, int depth, bool topo4 = false) {
   Ctx &c = ctx();
   const int k = (int)c.params.fill_multigrid;
   const int min_side = (int)(c.params.fill_multigrid_min > 0 ? c.params.fill_multigrid_min : 1024);
   FillState st;
+  st.topo4 = topo4;
   if (k >= 2 && depth < 8 && w >= min_side && h >= min_side && w / k >= 3 && h / k >= 3) {
     const int wc = (w + k - 1) / k, hc = (h + k - 1) / k;
     DevBuf<float> coarse((size_t)wc * hc);
@@ -1288,7 +1302,7 @@ static void fill_depressions_level(float *d_dem, int w, int h, int depth) {
       RDB_CK(cudaMemcpyAsync(zc.p, coarse.p, (size_t)wc * hc * sizeof(float), cudaMemcpyDeviceToDevice, c.stream));
     }
     const rdb200_stats before = c.stats;
-    fill_depressions_level(coarse.p, wc, hc, depth + 1);
+    fill_depressions_level(coarse.p, wc, hc, depth + 1, topo4);
     rdb200_stats extra = c.stats;  // work done on the coarse levels, accounted on top of this level's
     extra.fill_rounds -= before.fill_rounds;
     extra.fill_tile_visits -= before.fill_tile_visits;
@@ -1307,6 +1321,7 @@ static void fill_depressions_level(float *d_dem, int w, int h, int depth) {
       // and queues the coarse tiles it touched, its relaxation notes the tiles it writes, and the prolongation only
       // looks at the fine tiles below those -- a correction costs what it changes, not three passes over the raster.
       FillState cst;
+      cst.topo4 = topo4;
       cst.begin(zc.p, wc, hc, coarse.p, wc, 1);  // start: the coarse fill itself (already a fixed point)
       cst.run();                                  // (drains the initial all-tiles worklist; nothing moves)
       cst.track_dirty();
@@ -1532,11 +1547,11 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
   if (xrounds) *xrounds = cycles + 1;
 }
 
-void fill_depressions_dev(float *d_dem, int w, int h) {
+void fill_depressions_dev(float *d_dem, int w, int h, bool topo4) {
   Ctx &c = ctx();
   c.stats.cells = (int64_t)w * h;
   if (w <= 2 || h <= 2) return;  // every cell is a border cell: nothing can change
-  fill_depressions_level(d_dem, w, h, 0);
+  fill_depressions_level(d_dem, w, h, 0, topo4);
 }
 
 }  // namespace rdb

@@ -245,6 +245,15 @@ def test_vcycle_prolongation_wakes_neighbouring_tiles(emulated, gp, checker):
         assert np.array_equal(np.asarray(rd.FillDepressions(gp.R(dem))), expected), cfg
 
 
+@pytest.mark.parametrize("shape,seed,q", [((150, 220), 1, None), ((400, 500), 3, 2.0), ((64, 64), 5, 10.0), ((3, 3), 9, None)])
+def test_d4_fill(emulated, gp, checker, shape, seed, q):
+    gp.test_d4_fill_vs_oracle(checker, shape, seed, q)
+    _lib.set_param("fill_multigrid", 4)
+    _lib.set_param("fill_multigrid_min", 32)
+    _lib.set_param("fill_vcycle", 2)
+    gp.test_d4_fill_vs_oracle(checker, shape, seed, q)
+
+
 def _spread_to_all_lower_neighbours(dem):
     """An 8-receiver proportions grid (equal shares to every lower neighbour); edge cells carry no flow, as in every
     FM_* output (the reference's accumulation never bounds-checks receivers, flow_accumulation_generic.hpp:84-87)."""

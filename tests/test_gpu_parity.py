@@ -396,3 +396,27 @@ def test_fill_and_d8_accumulation_vs_reference_at_8192(checker):
     assert np.array_equal(filled, f_ref)
     a_ref = checker.fa_d8(f_ref, ND)
     assert np.array_equal(np.asarray(rd.FlowAccumulation(R(filled), "D8")), a_ref)
+
+
+# ---- FillDepressions<Topology::D4> ---------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,seed,q", [((150, 220), 1, None), ((400, 500), 3, 2.0), ((64, 64), 5, 10.0), ((1500, 2040), 7, 0.5),
+                                          ((3, 3), 9, None), ((1, 17), 10, None)])
+def test_d4_fill_vs_oracle(checker, shape, seed, q):
+    dem = oracle.fbm_terrain(*shape, seed=seed, quantum=q)
+    if shape[0] > 100:
+        dem[shape[0] // 4: shape[0] // 4 + 20, shape[1] // 3: shape[1] // 3 + 30] = ND
+    got = np.asarray(rd.FillDepressions(R(dem), topology="D4"))
+    assert np.array_equal(got, checker.fill_depressions(dem, "fill_d4"))
+
+
+def test_d4_fill_variants(checker):
+    dem = oracle.fbm_terrain(1100, 1300, seed=23, quantum=1.0)
+    expected = checker.fill_depressions(dem, "fill_d4")
+    try:
+        for cfg in ({}, {"fill_multigrid": 0}, {"fill_multigrid": 4, "fill_multigrid_min": 128, "fill_vcycle": 2}, {"fill_ordered": 0, "fill_multigrid": 0}):
+            _lib.reset_params()
+            for k, v in cfg.items():
+                _lib.set_param(k, v)
+            assert np.array_equal(np.asarray(rd.FillDepressions(R(dem), topology="D4")), expected), cfg
+    finally:
+        _lib.reset_params()

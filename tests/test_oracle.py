@@ -149,3 +149,14 @@ def test_remaining_flow_metrics_port_matches_compiled_reference_live(port, metho
     assert np.array_equal(port.fa_method(dem, ND, method, exponent), R.fa_method(dem, ND, method, exponent))
     wts = np.random.default_rng(3).random(dem.shape)
     assert np.array_equal(port.fa_method(dem, ND, method, exponent, wts), R.fa_method(dem, ND, method, exponent, wts))
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no reference tree)")
+@pytest.mark.parametrize("seed,shape,q", [(7, (97, 133), None), (8, (160, 120), 0.5), (9, (300, 300), 4.0)])
+def test_d4_fill_port_matches_compiled_reference_live(port, seed, shape, q):
+    """FillDepressions<Topology::D4> (depressions/depressions.hpp:16-17)."""
+    dem = oracle.fbm_terrain(*shape, seed=seed, quantum=q)
+    dem[20:40, 30:60] = ND
+    d4 = port.fill_depressions(dem, "fill_d4")
+    assert np.array_equal(d4, oracle.ref().fill_depressions(dem, "fill_d4"))
+    assert (d4 >= port.fill_depressions(dem)).all() and (d4 > port.fill_depressions(dem)).any(), "D4 fills at least as high as D8"

@@ -23,6 +23,10 @@ run() {  # name, seconds, env string, script + args
 if [ -z "$SKIP_CHECK" ]; then
   run check 400 "RDB_BAND_MULTIGRID=8" tools/mgpu_check.py
 fi
+if [ -z "$SKIP_TRACE" ]; then
+  run band_profile 300 "" tools/band_profile.py 32768
+  grep -a "trace\] rank 0\|^rep" "$OUT/band_profile.log" | tail -n 70 | tee -a "$OUT/summary.txt"
+fi
 i=0
 for e in "$@"; do
   run "bench_$i" 500 "$e" bench.py --gpus "$G" --steps ${STEPS:-4} --warmup 2 ${BENCH_FLAGS:---no-65536}
