@@ -1212,14 +1212,17 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
   }
 }
 
+// `cursor_buf` (optional): a device int the caller owns; the launch is then left in flight (no stream sync)
 template <bool BAND>
 void launch_walk_packed(const uint8_t *code, unsigned long long *word, int W, int ncells, const int *frontier,
-                        int ghost_lo_end, int ghost_hi_start) {
+                        int ghost_lo_end, int ghost_hi_start, int *cursor_buf = nullptr) {
   Ctx &c = ctx();
   if (ncells <= 0) return;
   if (c.params.accum_walk_lanes) {
-    DevBuf<int> cursor(1);
-    RDB_CK(cudaMemsetAsync(cursor.p, 0, sizeof(int), c.stream));
+    DevBuf<int> cursor;
+    if (!cursor_buf) cursor.alloc(1);
+    int *cur = cursor_buf ? cursor_buf : cursor.p;
+    RDB_CK(cudaMemsetAsync(cur, 0, sizeof(int), c.stream));
     int per_sm = 0;
     RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_packed_lanes_kernel<BAND>, 256, 0));
     if (per_sm < 1) per_sm = 1;
@@ -1227,9 +1230,9 @@ void launch_walk_packed(const uint8_t *code, unsigned long long *word, int W, in
     const long long need = ((long long)ncells + kLaneChunk - 1) / kLaneChunk;  // no more warps than chunks
     if (blocks * 8 > need) blocks = (need + 7) / 8;
     accum_walk_packed_lanes_kernel<BAND><<<(unsigned)blocks, 256, 0, c.stream>>>(code, word, W, ncells, frontier, ghost_lo_end,
-                                                                               ghost_hi_start, cursor.p);
+                                                                               ghost_hi_start, cur);
     RDB_CK(cudaGetLastError());
-    RDB_CK(cudaStreamSynchronize(c.stream));  // `cursor` goes out of scope
+    if (!cursor_buf) RDB_CK(cudaStreamSynchronize(c.stream));  // `cursor` goes out of scope
   } else {
     accum_walk_packed_kernel<BAND><<<(unsigned)((ncells + 255) / 256), 256, 0, c.stream>>>(code, word, W, ncells, frontier,
                                                                                         ghost_lo_end, ghost_hi_start);
@@ -1616,6 +1619,32 @@ struct FaccState {
     c.stats.accum_rounds = rounds;
   }
 
+  // packed unit-weight D8, for the C++ band driver: queue the preparation (first call) / the walk from the cells an
+  // inflow completed, without waiting for it
+  void walk_packed_async(int frontier_cells) {
+    Ctx &c = ctx();
+    unsigned long long *word = reinterpret_cast<unsigned long long *>(accum);
+    const int lo_end = gt ? W : 0, hi_start = gb ? (H - 1) * W : H * W;
+    if (!prepared) {
+      if (fused) {
+        dim3 pgrd((unsigned)((W + kPrepOut - 1) / kPrepOut), (unsigned)((H + kPrepRows - 1) / kPrepRows));
+        fa_d8_prep_rolling_kernel<<<pgrd, 256, 0, c.stream>>>(dem, code.p, word, W, H, nodata_v, gt, H - gb);
+      } else {
+        dim3 blk(256), grd((W / 4 + 255) / 256, H < 8192 ? H : 8192);
+        deps_gather_packed_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, W, H, gt, H - gb);
+      }
+      launch_walk_packed<true>(code.p, word, W, (int)n(), nullptr, lo_end, hi_start, cnt.p);
+      count_launch(2);
+      prepared = true;
+    } else if (frontier_cells > 0) {
+      launch_walk_packed<true>(code.p, word, W, frontier_cells, fr0.p, lo_end, hi_start, cnt.p);
+      count_launch();
+    }
+    RDB_CK(cudaGetLastError());
+    rounds++;
+    c.stats.accum_rounds = rounds;
+  }
+
   // returns the number of flow parcels parked in the ghost rows by this run: [top, bottom]
   void run(int *sent_top, int *sent_bottom) {
     if (packed) return run_packed(sent_top, sent_bottom);
@@ -1791,6 +1820,35 @@ void mgpu_fa_band(const rdb200_comm *comm, const float *d_dem, double *d_accum, 
   DevBuf<int> flag(1);
   int *hflag = (int *)c.pinned + 1024;
   int rounds = 0;
+  if (A.packed && world > 1) {
+    // unit-weight D8: one stream synchronisation per exchange round.  Everything of a round is queued back to back --
+    // walk | take the parked outflow (and count the parcels) | exchange | apply the inflow (device-side frontier) | 1-int
+    // all-reduce -- and the host reads {any parcels anywhere, my new frontier length} in one copy.
+    int frontier_cells = 0;
+    for (;;) {
+      A.walk_packed_async(frontier_cells);
+      rounds++;
+      if (getenv("RDB_MGPU_DEBUG")) fprintf(stderr, "[mgpu fa] rank %d round %d frontier %d\n", comm_rank(comm), rounds, frontier_cells);
+      RDB_CK(cudaMemsetAsync(A.cnt.p + 2, 0, 2 * sizeof(int), c.stream));  // [2] frontier length, [3] parcels taken
+      if (gt) A.take_outflow(0, sump(su), cntp(su));
+      if (gb) A.take_outflow(1, sump(sd), cntp(sd));
+      comm_exchange(comm, su, ru, sd, rd, msg);
+      if (gt) A.apply_inflow(0, sump(ru), cntp(ru));
+      if (gb) A.apply_inflow(1, sump(rd), cntp(rd));
+      RDB_CK(cudaMemcpyAsync(flag.p, A.cnt.p + 3, sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+      comm_allreduce(comm, flag.p, 1, RDB200_MAX_I32);
+      RDB_CK(cudaMemcpyAsync(hflag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+      RDB_CK(cudaMemcpyAsync(hflag + 1, A.cnt.p + 2, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+      RDB_CK(cudaStreamSynchronize(c.stream));
+      A.pending_apply = false;
+      if (getenv("RDB_MGPU_DEBUG")) fprintf(stderr, "[mgpu fa] rank %d round %d sent-anywhere %d new frontier %d\n", comm_rank(comm), rounds, hflag[0], hflag[1]);
+      if (hflag[0] == 0) break;
+      frontier_cells = hflag[1];
+      if (rounds > 1000000) fail("mgpu_fa: exchange rounds exceeded");
+    }
+    if (xrounds) *xrounds = rounds;
+    return;
+  }
   for (;;) {
     A.collect_frontier();
     int a = 0, b = 0;

@@ -244,6 +244,7 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "fill_multigrid") p.fill_multigrid = value;
   else if (n == "fill_multigrid_min") p.fill_multigrid_min = value;
   else if (n == "fill_vcycle") p.fill_vcycle = value;
+  else if (n == "fill_band_multigrid") p.fill_band_multigrid = value;
   else if (n == "flats_uf_tiled") p.flats_uf_tiled = value;
   else if (n == "flowdirs_rolling") p.flowdirs_rolling = value;
   else if (n == "accum_packed") p.accum_packed = value;

@@ -64,6 +64,7 @@ struct Params {
   int64_t fill_trace = 0;       // 1: per-V-cycle timeline of the multigrid fill on stderr (adds stream syncs)
   int64_t fill_multigrid = 8;      // k >= 2: start the flood from the lifted fill of the k x k max-pooled raster (recursive)
   int64_t fill_vcycle = 8;         // with fill_multigrid: coarse-grid correction after every that many fine rounds (0: none)
+  int64_t fill_band_multigrid = 0; // row-band driver: pooling factor of the replicated coarse level (0: automatic)
   int64_t fill_multigrid_min = 0;  // smallest raster side that still gets a coarse level (0: 1024)
   int64_t flowdirs_rolling = 1;  // d8_flow_directions with a rolling three-row register window (W % 4 == 0)
   int64_t flats_uf_tiled = 1;  // union-find: unite inside 64x16 tiles in shared memory first, then across tile seams

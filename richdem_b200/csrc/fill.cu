@@ -1422,9 +1422,16 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
   gb = gb ? 1 : 0;
   if (w < 3 || hloc - gt - gb < 1 || hloc < 3) fail("mgpu_fill: band too small (%d x %d)", w, hloc);
   if (row0 < 0 || row0 + hloc > H) fail("mgpu_fill: rows [%d, %d) are outside the raster (%d rows)", row0, row0 + hloc, H);
-  const int k = (int)c.params.fill_multigrid;
+  // pooling factor of the band's coarse level: every rank fills and re-relaxes that raster itself, a cost that does not
+  // shrink with the number of GPUs, so with many bands a coarser one pays (fill_band_multigrid; 0: fill_multigrid for
+  // up to two bands, twice that beyond)
+  int k = (int)c.params.fill_band_multigrid;
+  if (k <= 0) {
+    k = (int)c.params.fill_multigrid;
+    if (k >= 2 && world > 2 && TX % (2 * k) == 0) k *= 2;
+  }
   const int min_side = (int)(c.params.fill_multigrid_min > 0 ? c.params.fill_multigrid_min : 1024);
-  const bool mg = k >= 2 && w >= min_side && H >= min_side && w / k >= 3 && H / k >= 3;
+  const bool mg = k >= 2 && w >= min_side && H >= min_side && w / k >= 3 && H / k >= 3 && c.params.fill_multigrid >= 2;
   const int R = (int)(c.params.fill_vcycle > 0 ? c.params.fill_vcycle : 8);
   const float inf = __builtin_inff();
   DevBuf<float> rows(4 * (size_t)w);  // send up, send down, receive up, receive down
@@ -1512,7 +1519,7 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
       if (gb) st.ghost_update(hloc - 1, recv_dn, flags.p + 1);
       lap("halo exchange");
     }
-    // the coarse-grid correction is dropped for good once a cycle's correction moved nothing on any rank: what is left
+    // the coarse-grid correction is dropped for good once a cycle's correction moved next to nothing on any rank: what is left
     // are local repairs next to the seams, and the correction's fixed cost (the all-reduce of the pooled raster and the
     // coarse relaxation on every rank) would be paid for nothing
     if (mg && vcycle_on) {
@@ -1533,7 +1540,7 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
     RDB_CK(cudaStreamSynchronize(c.stream));
     lap("termination vote");
     if (!(hflags[0] | hflags[1] | hflags[2] | hflags[3])) break;
-    if (!(hflags[2] | hflags[3])) vcycle_on = false;
+    if (hflags[2] + hflags[3] < 32) vcycle_on = false;  // (tiles flagged by the correction on the busiest rank)
   }
   st.run(1);  // refresh the counters (no tile is active: an empty launch)
   const int64_t visits = st.visits_seen, iters = st.iters_seen, rounds = st.live_rounds;

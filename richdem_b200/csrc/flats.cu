@@ -138,7 +138,10 @@ __global__ void __launch_bounds__(256) flats_classify_edges_kernel(const float *
 #pragma unroll
         for (int n = 1; n <= 8; n++) {
           const float ne = sD[r + 1 + d8dy(n)][cidx + 1 + d8dx(n)];
-          if (ne < e || ne == nodata) f = 0;  // find_flats.hpp:58-61
+          if (ne < e || ne == nodata) {  // find_flats.hpp:58-61 (most cells leave at their first lower neighbour)
+            f = 0;
+            break;
+          }
         }
       }
     }
@@ -158,13 +161,21 @@ __global__ void __launch_bounds__(256) flats_classify_edges_kernel(const float *
       if (x < W && !(f & FT_NODATA)) {
         const float e = sD[r + 2][cidx + 2];
         int low = 0, high = 0;
+        if (f == 0) {
 #pragma unroll
-        for (int n = 1; n <= 8; n++) {
-          const float ne = sD[r + 2 + d8dy(n)][cidx + 2 + d8dx(n)];
-          if (f == 0) {
-            if ((sC[r + 1 + d8dy(n)][cidx + 1 + d8dx(n)] & FT_FLAT) && ne == e) low = 1;  // Barnes2014.hpp:343-350
-          } else {
-            if (e < ne) high = 1;  // :354-360
+          for (int n = 1; n <= 8; n++) {
+            if ((sC[r + 1 + d8dy(n)][cidx + 1 + d8dx(n)] & FT_FLAT) && sD[r + 2 + d8dy(n)][cidx + 2 + d8dx(n)] == e) {
+              low = 1;  // Barnes2014.hpp:343-350
+              break;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int n = 1; n <= 8; n++) {
+            if (e < sD[r + 2 + d8dy(n)][cidx + 2 + d8dx(n)]) {
+              high = 1;  // :354-360
+              break;
+            }
           }
         }
         nflat += f == FT_FLAT;

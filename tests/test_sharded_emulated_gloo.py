@@ -100,7 +100,7 @@ def _worker(rank, world, port, lib_path, dem, expected, params, out_q):
 
 @pytest.mark.parametrize("world,params", [(2, {}), (3, {}), (3, {"accum_walk_lanes": 0, "flats_uf_tiled": 0, "accum_fused_prep": 0}),
                                           (3, {"_band_multigrid": 4}), (2, {"_band_multigrid": 8}),
-                                          (4, {"_band_multigrid": 3, "fill_multigrid": 2, "fill_multigrid_min": 16}),
+                                          (4, {"_band_multigrid": 3, "fill_multigrid": 2, "fill_multigrid_min": 16, "fill_band_multigrid": 3}),
                                           (3, {"_band_multigrid": 4, "_band_vcycle": 1, "fill_band_rounds": 2, "fill_rounds_per_sync": 2}),
                                           (2, {"_band_multigrid": 8, "_band_vcycle": 2, "fill_band_rounds": 1, "fill_rounds_per_sync": 1})],
                          ids=["2-ranks", "3-ranks", "3-ranks-round1-kernels", "3-ranks-multigrid", "2-ranks-multigrid8",

@@ -31,6 +31,14 @@ TAILN=3 step bench 600 python bench.py --steps 5 --warmup 3
 grep -a '"metric"' "$OUT/bench.log" | tail -1 > "$OUT/bench.json"
 step ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file "$OUT/launches.csv" \
   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-configs --no-verify
+if [ -n "$NCU_FULL" ]; then
+  # full-set captures of the dominant kernels (one replayed launch each; read here with `ncu -i ... --page raw --csv`):
+  # the heaviest sweep launch is the first round of the 32768^2 level (after the coarse levels' ~80 small launches)
+  step ncu_full_sweep 600 ncu --set full --clock-control none --import-source on -k regex:fill_sweep_kernel --launch-skip 78 --launch-count 8 \
+    -o "$OUT/r2_fill_sweep_full" -f python tools/fill_profile.py "$N" ""
+  step ncu_full_fa 600 ncu --set full --clock-control none --import-source on -k regex:"fa_d8_prep_rolling|accum_walk_packed_lanes" --launch-count 2 \
+    -o "$OUT/r2_fa_d8_full" -f python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-configs --no-verify
+fi
 if [ -n "$REF_SIZE" ]; then
   TAILN=3 step bench_reference 900 python bench.py --impl reference --steps 1 --warmup 0 --ref-size "$REF_SIZE"
   grep -a '"impl"' "$OUT/bench_reference.log" | tail -1 > "$OUT/bench_reference.json"
