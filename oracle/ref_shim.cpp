@@ -15,6 +15,7 @@
 #include <richdem/depressions/Barnes2014.hpp>
 #include <richdem/flats/flats.hpp>
 #include <richdem/flats/find_flats.hpp>
+#include <richdem/flats/flat_resolution.hpp>
 #include <richdem/flowmet/d8_flowdirs.hpp>
 #include <richdem/methods/d8_methods.hpp>
 #include <richdem/methods/flow_accumulation.hpp>
@@ -189,6 +190,23 @@ void ref_fa_method_f32_f64(int method, const float *dem, int w, int h, float nod
     case 3: if (xparam == 1.0) FA_Quinn(a, acc); else FA_Holmgren(a, acc, xparam); break;
     default: FA_Freeman(a, acc, xparam); break;
   }
+}
+
+// flats/flat_resolution.hpp:588-607: barnes_flat_resolution_d8(elevations, flowdirs, alter = false) -- what
+// apps/rd_d8_flowdirs.cpp:18 ships: d8_flow_directions, resolve_flats_barnes (:448-515), d8_flow_flats (:97-116)
+void ref_barnes_flat_resolution_d8_f32(const float *dem, int w, int h, float nodata, uint8_t *dirs, int32_t *mask_out,
+                                       int32_t *labels_out) {
+  Array2D<float> a(w, h);
+  std::memcpy(a.data(), dem, sizeof(float) * (size_t)w * h);
+  a.setNoData(nodata);
+  Array2D<uint8_t> d;
+  d8_flow_directions(a, d);
+  Array2D<int32_t> m, l;
+  resolve_flats_barnes(a, d, m, l);
+  if (mask_out) std::memcpy(mask_out, m.data(), sizeof(int32_t) * (size_t)w * h);
+  if (labels_out) std::memcpy(labels_out, l.data(), sizeof(int32_t) * (size_t)w * h);
+  d8_flow_flats(m, l, d);
+  std::memcpy(dirs, d.data(), (size_t)w * h);
 }
 
 }  // extern "C"

@@ -1356,6 +1356,7 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
       rounds++;
       RDB_CK(cudaMemcpyAsync(hc, ctl.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
       RDB_CK(cudaStreamSynchronize(c.stream));
+      if (getenv("RDB_MGPU_DEBUG")) fprintf(stderr, "[dinf packed] launch %d over %d cells: %d spilled\n", rounds, ncells, hc[1]);
       if (hc[1] == 0) break;  // nothing spilled: done
       ncells = hc[1];
       frontier = spill;
