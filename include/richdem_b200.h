@@ -111,6 +111,15 @@ RDB200_API int rdb200_get_flat_mask_f32(const float *dem, int32_t *flat_mask, in
 RDB200_API int rdb200_d8_flow_directions_f32(const float *dem, uint8_t *flowdirs, int32_t width,
                                   int32_t height, float nodata);
 
+/* richdem::barnes_flat_resolution_d8(Array2D<float>&, Array2D<uint8_t>&, bool alter)
+ *   include/richdem/flats/flat_resolution.hpp:588-607 (apps/rd_d8_flowdirs.cpp:18 ships it with alter = false):
+ *   d8_flow_directions, then the increment mask / labels of the flats the DIRECTION grid shows (resolve_flats_barnes,
+ *   :448-515) and either directions inside the flats from the mask (d8_flow_flats, :97-116; dem untouched) or, with
+ *   alter != 0, the elevations altered by the mask (d8_flats_alter_dem, :540-586; dem updated in place) and the
+ *   directions recomputed.  Bit-identical. */
+RDB200_API int rdb200_d8_flow_directions_flats_f32(float *dem, uint8_t *flowdirs, int32_t width, int32_t height,
+                                                   float nodata, int32_t alter);
+
 /* richdem::d8_flow_accum(const Array2D<uint8_t>&, Array2D<int32_t>&)
  *   include/richdem/methods/d8_methods.hpp:47-139.  NoData direction = 255 -> area -1. */
 RDB200_API int rdb200_d8_flow_accum_u8_i32(const uint8_t *flowdirs, int32_t *area, int32_t width,
@@ -177,6 +186,8 @@ RDB200_API int rdb200_dev_fill_depressions_d4_f32(float *d_dem, int32_t width, i
 RDB200_API int rdb200_dev_resolve_flats_epsilon_f32(float *d_dem, int32_t width, int32_t height, float nodata);
 RDB200_API int rdb200_dev_d8_flow_directions_f32(const float *d_dem, uint8_t *d_flowdirs, int32_t width,
                                       int32_t height, float nodata);
+RDB200_API int rdb200_dev_d8_flow_directions_flats_f32(float *d_dem, uint8_t *d_flowdirs, int32_t width, int32_t height,
+                                                       float nodata, int32_t alter);
 RDB200_API int rdb200_dev_d8_flow_accum_u8_i32(const uint8_t *d_flowdirs, int32_t *d_area, int32_t width,
                                     int32_t height);
 RDB200_API int rdb200_dev_fm_d8_f32(const float *d_dem, float *d_props9, int32_t width, int32_t height,

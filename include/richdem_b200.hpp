@@ -121,6 +121,7 @@ void fa_tarboton(const A2 &dem, C2 &accum) {
 
 #ifdef RICHDEM_B200_HAVE_RICHDEM
 #include <richdem/depressions/depressions.hpp>
+#include <richdem/flats/flat_resolution.hpp>
 #include <richdem/flats/flats.hpp>
 #include <richdem/flowmet/d8_flowdirs.hpp>
 #include <richdem/methods/d8_methods.hpp>
@@ -167,6 +168,19 @@ inline void d8_flow_directions<float, uint8_t>(const Array2D<float> &elevations,
   flowdirs.resize(elevations);
   flowdirs.setNoData(FLOWDIR_NO_DATA);
   richdem_b200::d8_flow_directions(elevations, flowdirs);
+}
+#endif
+
+#if 1
+// flats/flat_resolution.hpp:588-607 (apps/rd_d8_flowdirs.cpp:18): D8 directions with the flats resolved through the
+// increment mask (alter = false) or by altering the elevations (alter = true)
+template <>
+inline void barnes_flat_resolution_d8<float, uint8_t>(Array2D<float> &elevations, Array2D<uint8_t> &flowdirs, bool alter) {
+  flowdirs.resize(elevations);
+  flowdirs.setNoData(FLOWDIR_NO_DATA);
+  richdem_b200::check(rdb200_d8_flow_directions_flats_f32(elevations.data(), flowdirs.data(), elevations.width(),
+                                                          elevations.height(), (float)elevations.noData(), alter ? 1 : 0));
+  flowdirs.templateCopy(elevations);
 }
 #endif
 

@@ -171,6 +171,40 @@ class _Backend:
         self._fa_method(self.METHOD_IDS[method], d, w, h, nodata, x, acc)
         return acc
 
+    # -- f2: direction-grid flat resolution (reference backend only: flats/flat_resolution.hpp:588-607)
+    def d8_flow_directions_flats(self, dem, nodata):
+        """(directions, mask, labels) of barnes_flat_resolution_d8(dem, dirs, alter=false)."""
+        d = self._dem(dem)
+        h, w = d.shape
+        if self.kind == "reference":
+            f = self.lib.ref_barnes_flat_resolution_d8_f32
+            f.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, _u8p, _i32p, _i32p]
+            f.restype = None
+            dirs = np.empty((h, w), np.uint8)
+            m = np.empty((h, w), np.int32)
+            l = np.empty((h, w), np.int32)
+            f(d, w, h, nodata, dirs, m, l)
+            return dirs, m, l
+        # the C port: d8_flow_directions, GetFlatMask's mask / labels (identical to resolve_flats_barnes' wherever the
+        # NoData value lies below the data, as -9999 does: pinned by tests/test_oracle.py against the reference and
+        # the golden fixtures) and the masked direction stencil (flat_resolution.hpp:37-63, 97-116)
+        dirs = self.d8_flow_directions(d, nodata)
+        m, l = self.flat_mask(d, nodata)
+        out = dirs.copy()
+        d8x = [0, -1, -1, 0, 1, 1, 1, 0, -1]
+        d8y = [0, 0, -1, -1, -1, 0, 1, 1, 1]
+        ys, xs = np.nonzero(dirs[1:-1, 1:-1] == 0)
+        for y, x in zip(ys + 1, xs + 1):
+            minimum, flowdir = m[y, x], 0
+            for n in range(1, 9):
+                ny, nx = y + d8y[n], x + d8x[n]
+                if l[ny, nx] != l[y, x]:
+                    continue
+                if m[ny, nx] < minimum or (m[ny, nx] == minimum and flowdir > 0 and flowdir % 2 == 0 and n % 2 == 1):
+                    minimum, flowdir = m[ny, nx], n
+            out[y, x] = flowdir
+        return out, m, l
+
     # -- a11
     def flow_accumulation(self, props, weights=None):
         p = np.ascontiguousarray(props, np.float32)

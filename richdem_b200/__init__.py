@@ -282,6 +282,21 @@ def FlowDirectionsD8(dem: rdarray) -> rdarray:
     return out
 
 
+def FlowDirectionsD8Resolved(dem: rdarray, alter: bool = False) -> rdarray:
+    """richdem::barnes_flat_resolution_d8 (flats/flat_resolution.hpp:588-607; the pipeline of apps/rd_d8_flowdirs.cpp):
+    D8 directions in which drainable flats flow along the Barnes (2014) increment mask.  ``alter=True`` raises the
+    flat cells of ``dem`` in place instead (d8_flats_alter_dem) and recomputes the directions."""
+    if type(dem) is not rdarray:
+        raise Exception("A richdem.rdarray or numpy.ndarray is required!")
+    if dem.dtype != np.float32 or not dem.flags["C_CONTIGUOUS"]:
+        raise Exception("FlowDirectionsD8Resolved needs a C-contiguous float32 rdarray")
+    h, w = dem.shape
+    out = rdarray(np.empty((h, w), np.uint8), meta_obj=dem, no_data=255)
+    _lib.check(_lib.lib().rdb200_d8_flow_directions_flats_f32(_lib.ptr(dem), _lib.ptr(out), w, h, _nodata_f32(dem), int(alter)))
+    out.no_data = 255
+    return out
+
+
 def D8FlowAccum(flowdirs: np.ndarray) -> rdarray:
     """richdem::d8_flow_accum (methods/d8_methods.hpp:47-139) on a uint8 direction grid."""
     f = np.ascontiguousarray(flowdirs, dtype=np.uint8)

@@ -47,6 +47,8 @@ SIGNATURES = {
     "rdb200_resolve_flats_epsilon_f32": [_vp, _i32, _i32, _f32],
     "rdb200_get_flat_mask_f32": [_vp, _vp, _vp, _i32, _i32, _f32],
     "rdb200_d8_flow_directions_f32": [_vp, _vp, _i32, _i32, _f32],
+    "rdb200_d8_flow_directions_flats_f32": [_vp, _vp, _i32, _i32, _f32, _i32],
+    "rdb200_dev_d8_flow_directions_flats_f32": [_vp, _vp, _i32, _i32, _f32, _i32],
     "rdb200_d8_flow_accum_u8_i32": [_vp, _vp, _i32, _i32],
     "rdb200_fm_d8_f32": [_vp, _vp, _i32, _i32, _f32],
     "rdb200_fm_tarboton_f32": [_vp, _vp, _i32, _i32, _f32],

@@ -1075,6 +1075,8 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
   bool walking = false;
   int c = 0;
   unsigned long long acc = 0;
+  int pend = -1;  // a completed receiver this lane keeps for itself (the ring was full when it appeared)
+  unsigned long long pend_acc = 0;
   for (;;) {
     // ---- refill from the source scan only when the lanes would otherwise starve: the ring's room belongs to the
     // hand-overs (a ring kept full by the scan overflows into the spill list, which costs a whole extra launch) ----
@@ -1082,14 +1084,15 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
       if (pos >= end) {
         if (!more) break;
         int b = 0;
-        if (lane == 0) b = atomicAdd(cursor, kLaneChunk);
+        const int chunk = frontier ? 32 : kLaneChunk;  // a spill list is short: spread it over as many warps as possible
+        if (lane == 0) b = atomicAdd(cursor, chunk);
         b = __shfl_sync(full, b, 0);
         if (b >= ncells) {
           more = false;
           break;
         }
         pos = b;
-        end = b + kLaneChunk < ncells ? b + kLaneChunk : ncells;
+        end = b + chunk < ncells ? b + chunk : ncells;
       }
       const int i = pos + lane;
       bool src = false;
@@ -1116,6 +1119,12 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
     }
     __syncwarp();
     // ---- hand queued cells to the lanes that are not walking ----
+    if (!walking && pend >= 0) {  // first what this lane put aside
+      c = pend;
+      acc = pend_acc;
+      pend = -1;
+      walking = true;
+    }
     const unsigned idle = __ballot_sync(full, !walking);
     if (idle == full && count == 0 && !more && pos >= end) break;
     const int rank = __popc(idle & lt);
@@ -1201,8 +1210,11 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
             const int slot = (head + count + k) & (kLaneQueueD - 1);
             q[slot] = extra;
             qa[slot] = extra_acc;
+          } else if (pend < 0) {
+            pend = extra;  // ring full: keep it for myself
+            pend_acc = extra_acc;
           } else {
-            spill[atomicAdd(spill_count, 1)] = extra;
+            spill[atomicAdd(spill_count, 1)] = extra;  // (rare) picked up by the next launch
           }
         }
         const int np = __popc(pb);
@@ -1347,7 +1359,8 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     for (;;) {
       RDB_CK(cudaMemsetAsync(ctl.p, 0, 4 * sizeof(int), c.stream));
       long long nb = (long long)c.num_sms * per_sm;
-      const long long need = ((long long)ncells + kLaneChunk - 1) / kLaneChunk;
+      const int chunk = frontier ? 32 : kLaneChunk;
+      const long long need = ((long long)ncells + chunk - 1) / chunk;
       if (nb * 8 > need) nb = (need + 7) / 8;
       accum_walk_dinf_lanes_kernel<<<(unsigned)nb, 256, 0, c.stream>>>(code.p, rmax.p, word, w, ncells, frontier, ctl.p, spill,
                                                                        ctl.p + 1);

@@ -329,6 +329,22 @@ int rdb200_d8_flow_directions_f32(const float *dem, uint8_t *dirs, int32_t w, in
   CAPI_END
 }
 
+int rdb200_d8_flow_directions_flats_f32(float *dem, uint8_t *dirs, int32_t w, int32_t h, float nodata, int32_t alter) {
+  CAPI_TRY
+  if (!dem || !dirs) fail("d8_flow_directions_flats: null pointer");
+  check_dims(w, h);
+  CallScope cs((int64_t)w * h);
+  const size_t n = (size_t)w * h;
+  DevBuf<float> d(n);
+  DevBuf<uint8_t> o(n);
+  h2d(d.p, dem, n);
+  d8_flow_directions_flats_dev(d.p, o.p, w, h, nodata, alter != 0);
+  d2h(dirs, o.p, n);
+  if (alter) d2h(dem, d.p, n);
+  cs.done();
+  CAPI_END
+}
+
 int rdb200_d8_flow_accum_u8_i32(const uint8_t *dirs, int32_t *area, int32_t w, int32_t h) {
   CAPI_TRY
   if (!dirs || !area) fail("d8_flow_accum: null pointer");
@@ -483,6 +499,9 @@ int rdb200_dev_resolve_flats_epsilon_f32(float *d_dem, int32_t w, int32_t h, flo
 }
 int rdb200_dev_d8_flow_directions_f32(const float *d_dem, uint8_t *d_dirs, int32_t w, int32_t h, float nodata) {
   DEV_ENTRY((int64_t)w * h, (check_dims(w, h), d8_flow_directions_dev(d_dem, d_dirs, w, h, nodata)))
+}
+int rdb200_dev_d8_flow_directions_flats_f32(float *d_dem, uint8_t *d_dirs, int32_t w, int32_t h, float nodata, int32_t alter) {
+  DEV_ENTRY((int64_t)w * h, (check_dims(w, h), d8_flow_directions_flats_dev(d_dem, d_dirs, w, h, nodata, alter != 0)))
 }
 int rdb200_dev_d8_flow_accum_u8_i32(const uint8_t *d_dirs, int32_t *d_area, int32_t w, int32_t h) {
   DEV_ENTRY((int64_t)w * h, (check_dims(w, h), d8_flow_accum_dev(d_dirs, d_area, w, h)))

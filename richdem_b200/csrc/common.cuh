@@ -166,7 +166,8 @@ rdb200_fill_state *new_band_distance_state(const uint8_t *d_open, int open_bit, 
                                            int ghost_top, int ghost_bottom);
 void finish_band_distance_state(rdb200_fill_state *s, float *d_out);
 void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask_out,
-                       int32_t *d_labels_out, bool apply);
+                       int32_t *d_labels_out, bool apply, const uint8_t *d_dirs = nullptr);
+void d8_flow_directions_flats_dev(float *d_dem, uint8_t *d_dirs, int w, int h, float nodata, bool alter);
 void d8_flow_directions_dev(const float *d_dem, uint8_t *d_dirs, int w, int h, float nodata);
 void d8_flow_accum_dev(const uint8_t *d_dirs, int32_t *d_area, int w, int h);
 void fm_d8_dev(const float *d_dem, float *d_props, int w, int h, float nodata);

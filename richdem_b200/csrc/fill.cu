@@ -551,13 +551,22 @@ __global__ void __launch_bounds__(256) fill_maxpool_kernel(const float *__restri
   const int by_lo = yoff / k, by_hi = (yoff + H - 1) / k;
   for (int by = by_lo + blockIdx.y; by <= by_hi && by < Hc; by += gridDim.y) {
     float m = -__int_as_float(0x7f800000);
+    const bool vec = (k & 3) == 0 && (W & 3) == 0 && bx * k + k <= W && ((uintptr_t)src & 15) == 0;
     for (int j = 0; j < k; j++) {
       const int y = by * k + j - yoff;  // local row
       if (y < 0) continue;
       if (y >= H) break;
-      for (int i = 0; i < k; i++) {
-        const int x = bx * k + i;
-        if (x < W) m = fmaxf(m, __ldg(src + (size_t)y * W + x));
+      if (vec) {
+        const float4 *row = reinterpret_cast<const float4 *>(src + (size_t)y * W + bx * k);
+        for (int i = 0; i < k / 4; i++) {
+          const float4 q = __ldg(row + i);
+          m = fmaxf(fmaxf(m, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
+        }
+      } else {
+        for (int i = 0; i < k; i++) {
+          const int x = bx * k + i;
+          if (x < W) m = fmaxf(m, __ldg(src + (size_t)y * W + x));
+        }
       }
     }
     float *o = dst + (size_t)by * Wc + bx;
@@ -1540,7 +1549,11 @@ void mgpu_fill_band(const rdb200_comm *comm, float *d_local, int w, int hloc, in
     RDB_CK(cudaStreamSynchronize(c.stream));
     lap("termination vote");
     if (!(hflags[0] | hflags[1] | hflags[2] | hflags[3])) break;
-    if (hflags[2] + hflags[3] < 32) vcycle_on = false;  // (tiles flagged by the correction on the busiest rank)
+    // (tiles flagged by the correction on the busiest rank; a band has tilesX * tilesY of them)
+    const int few = st.tilesX * st.tilesY / 64 > 32 ? st.tilesX * st.tilesY / 64 : 32;
+    if (trace) fprintf(stderr, "[mgpu fill trace] rank %d cycle %d: flags active=%d ghost=%d coarse=%d fine=%d (cut-off %d)\n",
+                       comm_rank(comm), cycles, hflags[0], hflags[1], hflags[2], hflags[3], few);
+    if (hflags[2] + hflags[3] < few) vcycle_on = false;
   }
   st.run(1);  // refresh the counters (no tile is active: an empty launch)
   const int64_t visits = st.visits_seen, iters = st.iters_seen, rounds = st.live_rounds;

@@ -217,6 +217,77 @@ __global__ void __launch_bounds__(256) flats_classify_edges_kernel(const float *
   }
 }
 
+// Flat / edge flags from a D8 DIRECTION grid instead of from the elevations (flats/flat_resolution.hpp:382-413,
+// find_flat_edges of the direction-grid flat resolution): a flat cell is a cell marked NO_FLOW (0), NoData is the
+// grid's 255; low edge = cell with flow that has an equal-elevation NO_FLOW neighbour, high edge = NO_FLOW cell with a
+// higher neighbour; neighbours outside the grid or NoData in the direction grid are skipped.
+__global__ void __launch_bounds__(256) flats_from_dirs_kernel(const float *__restrict__ dem, const uint8_t *__restrict__ dirs,
+                                                               uint8_t *__restrict__ ft, int W, int H, FlatDev *dev) {
+  const size_t n = (size_t)W * H;
+  int nflat = 0, nlow = 0, nhigh = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+    const uint8_t d = dirs[i];
+    uint8_t f = d == 255 ? FT_NODATA : (d == 0 ? FT_FLAT : 0);
+    if (d != 255) {
+      const float e = __ldg(dem + i);
+      for (int k = 1; k <= 8; k++) {
+        const int nx = x + d8dx(k), ny = y + d8dy(k);
+        if (nx < 0 || ny < 0 || nx >= W || ny >= H) continue;
+        const size_t ni = (size_t)ny * W + nx;
+        const uint8_t dn = dirs[ni];
+        if (dn == 255) continue;
+        const float ne = __ldg(dem + ni);
+        if (d != 0 && dn == 0 && ne == e) {
+          f |= FT_LOW;
+          break;
+        } else if (d == 0 && e < ne) {
+          f |= FT_HIGH;
+          break;
+        }
+      }
+    }
+    ft[i] = f;
+    nflat += (f & FT_FLAT) != 0;
+    nlow += (f & FT_LOW) != 0;
+    nhigh += (f & FT_HIGH) != 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nflat += __shfl_xor_sync(0xffffffffu, nflat, o);
+    nlow += __shfl_xor_sync(0xffffffffu, nlow, o);
+    nhigh += __shfl_xor_sync(0xffffffffu, nhigh, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (nflat) atomicAdd(&dev->n_flat, nflat);
+    if (nlow) atomicAdd(&dev->n_low, nlow);
+    if (nhigh) atomicAdd(&dev->n_high, nhigh);
+  }
+}
+
+// d8_flow_flats (flats/flat_resolution.hpp:97-116) with d8_masked_FlowDir (:37-63): interior cells still marked NO_FLOW
+// take the direction of their lowest same-label neighbour in the increment mask (cardinal neighbours win ties)
+__global__ void __launch_bounds__(256) d8_flow_flats_kernel(const int32_t *__restrict__ mask, const int32_t *__restrict__ labels,
+                                                             uint8_t *dirs, int W, int H) {
+  const size_t n = (size_t)W * H;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+    if (x < 1 || y < 1 || x >= W - 1 || y >= H - 1) continue;
+    if (dirs[i] != 0) continue;
+    const int lab = labels[i];
+    int minimum = mask[i], flowdir = 0;
+    for (int k = 1; k <= 8; k++) {
+      const size_t ni = (size_t)(y + d8dy(k)) * W + (x + d8dx(k));
+      if (labels[ni] != lab) continue;
+      const int m = mask[ni];
+      if (m < minimum || (m == minimum && flowdir > 0 && (flowdir & 1) == 0 && (k & 1) == 1)) {
+        minimum = m;
+        flowdir = k;
+      }
+    }
+    dirs[i] = (uint8_t)flowdir;
+  }
+}
+
 // ---- union-find over exactly-equal elevations --------------------------------------------------
 __device__ __forceinline__ int uf_find(int *parent, int i) {
   int p = parent[i];
@@ -652,7 +723,7 @@ int run_bfs(const uint8_t *ft, const int *labels, int *dist, int *H, int *q0, in
 
 // ResolveFlatsEpsilon (apply=true) / GetFlatMask (apply=false, outputs requested)
 void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask_out, int32_t *d_labels_out,
-                       bool apply) {
+                       bool apply, const uint8_t *d_dirs) {
   Ctx &c = ctx();
   const size_t n = (size_t)w * h;
   c.stats.cells = (int64_t)n;
@@ -669,7 +740,10 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
   DevBuf<uint8_t> ft(n);
   DevBuf<FlatDev> dev(1);
   RDB_CK(cudaMemsetAsync(dev.p, 0, sizeof(FlatDev), c.stream));
-  if (c.params.flats_fused_classify) {
+  if (d_dirs) {  // flats as the direction grid defines them (direction-grid flat resolution)
+    flats_from_dirs_kernel<<<c.num_sms * 16, 256, 0, c.stream>>>(d_dem, d_dirs, ft.p, w, h, dev.p);
+    count_launch();
+  } else if (c.params.flats_fused_classify) {
     dim3 grd((unsigned)((w + CE_TX - 1) / CE_TX), (unsigned)((h + CE_TY - 1) / CE_TY));
     flats_classify_edges_kernel<<<grd, 256, 0, c.stream>>>(d_dem, ft.p, w, h, nodata, dev.p);
     count_launch();
@@ -763,6 +837,27 @@ void resolve_flats_dev(float *d_dem, int w, int h, float nodata, int32_t *d_mask
     fail("resolve_flats: a flat is more than 2^24 cells long; the float distance solver is not exact there "
          "(rdb200_set_param(\"flats_tiled\", 0) selects the int32 level-synchronous solver)");
   lap("apply");
+}
+
+// barnes_flat_resolution_d8(elevations, flowdirs, alter) (flats/flat_resolution.hpp:588-607; what apps/rd_d8_flowdirs.cpp
+// ships with alter = false): D8 directions, the increment mask and labels of the flats the direction grid shows
+// (resolve_flats_barnes, :448-515), then either flow directions inside the flats from the mask (d8_flow_flats, :97-116)
+// or the elevations altered by the mask and the directions recomputed (d8_flats_alter_dem, :540-586).
+void d8_flow_directions_flats_dev(float *d_dem, uint8_t *d_dirs, int w, int h, float nodata, bool alter) {
+  Ctx &c = ctx();
+  const size_t n = (size_t)w * h;
+  d8_flow_directions_dev(d_dem, d_dirs, w, h, nodata);
+  if (alter) {
+    resolve_flats_dev(d_dem, w, h, nodata, nullptr, nullptr, true, d_dirs);
+    d8_flow_directions_dev(d_dem, d_dirs, w, h, nodata);
+    return;
+  }
+  DevBuf<int32_t> mask(n), labels(n);
+  resolve_flats_dev(d_dem, w, h, nodata, mask.p, labels.p, false, d_dirs);
+  d8_flow_flats_kernel<<<c.num_sms * 16, 256, 0, c.stream>>>(mask.p, labels.p, d_dirs, w, h);
+  RDB_CK(cudaGetLastError());
+  count_launch();
+  RDB_CK(cudaStreamSynchronize(c.stream));
 }
 
 }  // namespace rdb

@@ -106,8 +106,22 @@ def main():
         syn[k + "__fa_dinf"] = R.fa_dinf(r, -9999.0)
     np.savez_compressed(f"{OUT}/synthetic_ref.npz", **syn)
     metrics()
+    flowdirs_flats()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def flowdirs_flats():
+    """7. direction-grid flat resolution: barnes_flat_resolution_d8(dem, dirs, alter=false) of the unmodified
+    reference (flats/flat_resolution.hpp:588-607) on the filled Beauford crop and a seeded synthetic DEM."""
+    R = oracle.ref()
+    g = np.load(f"{OUT}/beauford_crop.npz")
+    out = {}
+    for name, dem in (("beauford", g["filled"]), ("s105", R.fill_depressions(oracle.fbm_terrain(160, 230, seed=105, quantum=0.5)))):
+        out[name + "__dirs"] = R.d8_flow_directions_flats(dem, -9999.0)[0]
+        if name != "beauford":
+            out[name + "__dem"] = dem
+    np.savez_compressed(f"{OUT}/flowdirs_flats_ref.npz", **out)
 
 
 METRIC_CASES = [("D4", None), ("Quinn", None), ("Holmgren", 2.5), ("Holmgren", 0.7), ("Freeman", 1.1), ("Freeman", 4.0)]
@@ -132,5 +146,7 @@ def metrics():
 if __name__ == "__main__":
     if "--metrics-only" in sys.argv:
         metrics()
+    elif "--flowdirs-flats-only" in sys.argv:
+        flowdirs_flats()
     else:
         main()

@@ -254,6 +254,12 @@ def test_d4_fill(emulated, gp, checker, shape, seed, q):
     gp.test_d4_fill_vs_oracle(checker, shape, seed, q)
 
 
+def test_direction_grid_flat_resolution(emulated, gp, checker, golden):
+    gp.test_flow_directions_with_resolved_flats_golden(golden)
+    gp.test_flow_directions_with_resolved_flats_vs_oracle(checker, (300, 420), 2, 0.5)
+    gp.test_flow_directions_with_resolved_flats_vs_oracle(checker, (64, 70), 5, 10.0)
+
+
 def _spread_to_all_lower_neighbours(dem):
     """An 8-receiver proportions grid (equal shares to every lower neighbour); edge cells carry no flow, as in every
     FM_* output (the reference's accumulation never bounds-checks receivers, flow_accumulation_generic.hpp:84-87)."""

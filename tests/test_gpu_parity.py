@@ -420,3 +420,27 @@ def test_d4_fill_variants(checker):
             assert np.array_equal(np.asarray(rd.FillDepressions(R(dem), topology="D4")), expected), cfg
     finally:
         _lib.reset_params()
+
+
+# ---- direction-grid flat resolution (barnes_flat_resolution_d8, the pipeline of rd_d8_flowdirs) ----------
+def test_flow_directions_with_resolved_flats_golden(golden):
+    g = golden["flowdirs_flats_ref"]
+    for name, dem in (("beauford", golden["beauford_crop"]["filled"]), ("s105", g["s105__dem"])):
+        d = R(dem.copy())
+        got = np.asarray(rd.FlowDirectionsD8Resolved(d))
+        assert np.array_equal(got, g[name + "__dirs"]), name
+        assert np.array_equal(np.asarray(d), dem), "alter=False leaves the elevations alone"
+
+
+@pytest.mark.parametrize("shape,seed,q", [((300, 420), 2, 0.5), ((777, 1028), 4, 2.0), ((64, 70), 5, 10.0)])
+def test_flow_directions_with_resolved_flats_vs_oracle(checker, shape, seed, q):
+    dem = oracle.fbm_terrain(*shape, seed=seed, quantum=q)
+    dem[shape[0] // 3: shape[0] // 3 + 12, shape[1] // 4: shape[1] // 4 + 25] = ND
+    filled = checker.fill_depressions(dem)
+    expected = checker.d8_flow_directions_flats(filled, ND)[0]
+    assert np.array_equal(np.asarray(rd.FlowDirectionsD8Resolved(R(filled.copy()))), expected)
+    # alter=True: the elevations take the increments and plain D8 directions on them drain every drainable flat
+    d = R(filled.copy())
+    dirs_alt = np.asarray(rd.FlowDirectionsD8Resolved(d, alter=True))
+    assert np.array_equal(np.asarray(d).view(np.uint32), checker.resolve_flats(filled, ND).view(np.uint32))
+    assert np.array_equal(dirs_alt, checker.d8_flow_directions(np.asarray(d), ND))

@@ -160,3 +160,23 @@ def test_d4_fill_port_matches_compiled_reference_live(port, seed, shape, q):
     d4 = port.fill_depressions(dem, "fill_d4")
     assert np.array_equal(d4, oracle.ref().fill_depressions(dem, "fill_d4"))
     assert (d4 >= port.fill_depressions(dem)).all() and (d4 > port.fill_depressions(dem)).any(), "D4 fills at least as high as D8"
+
+
+def test_direction_grid_flat_resolution_against_reference_outputs(port, golden):
+    """barnes_flat_resolution_d8 (flats/flat_resolution.hpp:588-607)."""
+    g = golden["flowdirs_flats_ref"]
+    for name, dem in (("beauford", golden["beauford_crop"]["filled"]), ("s105", g["s105__dem"])):
+        dirs, m, l = port.d8_flow_directions_flats(dem, ND)
+        assert np.array_equal(dirs, g[name + "__dirs"]), name
+        inner = np.zeros(dirs.shape, bool)
+        inner[1:-1, 1:-1] = True
+        assert not ((dirs == 0) & inner & (l != 0)).any(), "every cell of a drainable flat received a direction"
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no reference tree)")
+def test_direction_grid_flat_resolution_port_matches_compiled_reference_live(port):
+    dem = port.fill_depressions(oracle.fbm_terrain(180, 150, seed=33, quantum=1.0))
+    dem[60:80, 40:70] = ND
+    a = port.d8_flow_directions_flats(dem, ND)
+    b = oracle.ref().d8_flow_directions_flats(dem, ND)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2] != 0, b[2] != 0)
