@@ -173,7 +173,7 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print("\n" + json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -490,7 +490,8 @@ def run_b200(args):
         "gpu_launches": launches_all,
         "clocks": clk.summary(),
     }
-    print(json.dumps(line), flush=True)
+    # (the compiled reference writes progress-bar control codes without a newline: keep the JSON on a line of its own)
+    print("\n" + json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -249,6 +249,7 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "flowdirs_rolling") p.flowdirs_rolling = value;
   else if (n == "accum_packed") p.accum_packed = value;
   else if (n == "accum_dinf_packed") p.accum_dinf_packed = value;
+  else if (n == "accum_dinf_share") p.accum_dinf_share = value;
   else fail("rdb200_set_param: unknown parameter '%s'", name);
   CAPI_END
 }

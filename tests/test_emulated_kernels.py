@@ -254,6 +254,19 @@ def test_d4_fill(emulated, gp, checker, shape, seed, q):
     gp.test_d4_fill_vs_oracle(checker, shape, seed, q)
 
 
+@pytest.mark.parametrize("share", [0, 3, -1])
+def test_packed_dinf_work_sharing(emulated, gp, checker, share):
+    """accum_dinf_packed: fixed-point D-infinity walk; share = ring length above which hand-overs go to the global ticket
+    queue (0: every hand-over crosses warps).  Re-run with concurrent blocks by test_cooperative_kernels_with_several_blocks."""
+    import richdem_b200 as rd
+    _lib.set_param("accum_dinf_packed", 1)
+    _lib.set_param("accum_dinf_share", share)
+    dem = checker.resolve_flats(checker.fill_depressions(oracle.fbm_terrain(420, 520, seed=71, quantum=0.5)), gp.ND)
+    dem[200:230, 100:160] = gp.ND
+    got = np.asarray(rd.FlowAccumulation(gp.R(dem), "Dinf"))
+    np.testing.assert_allclose(got, checker.fa_dinf(dem, gp.ND), rtol=gp.DINF_UNIT_RTOL, atol=0)
+
+
 def test_direction_grid_flat_resolution(emulated, gp, checker, golden):
     gp.test_flow_directions_with_resolved_flats_golden(golden)
     gp.test_flow_directions_with_resolved_flats_vs_oracle(checker, (300, 420), 2, 0.5)
@@ -299,7 +312,7 @@ def test_cooperative_kernels_with_several_blocks():
         pytest.skip("already inside the multi-block run")
     env = dict(os.environ, RDB_EMU_SMS="3", RDB_EMU_CHAOS="7")  # CHAOS: atomics yield at random -> other interleavings
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", os.path.abspath(__file__), "-k",
-                        "variants or band_accumulation or special_rasters or degenerate or eight_receiver"],
+                        "variants or band_accumulation or special_rasters or degenerate or eight_receiver or packed_dinf"],
                        env=env, cwd=os.path.dirname(HERE), capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
