@@ -455,6 +455,9 @@ def run_b200(args):
     roofline = {
         "bound": "hbm", "kernel": "fill_sweep_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "peak_source": peak_src, "traffic": args.traffic,
+        "traffic_of": "the dominant launch (first sweep round of the finest level): dram read + write of one ncu --set full "
+                      "capture, profiles/traffic.json; its algorithmic bytes are 12.88 GB",
+        "dominant_launch": args.dominant_launch,
         "algorithmic_bytes_per_launch": sweep_bytes / max(agg["rounds"], 1),
         "avg_launch_ms": agg["sweep_ms"] / max(agg["rounds"], 1),
         "sweep_share_of_step": agg["sweep_ms"] / dev_ms,
@@ -659,11 +662,14 @@ def main():
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per sweep launch from the committed ncu capture (default: profiles/traffic.json)")
     args = ap.parse_args()
-    if args.traffic is None:
-        try:
-            args.traffic = float(json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["dram_bytes_per_launch"])
-        except Exception:
-            args.traffic = None
+    args.dominant_launch = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        args.dominant_launch = tj.get("dominant_launch")
+        if args.traffic is None:
+            args.traffic = float(tj["dram_bytes_per_launch"])
+    except Exception:
+        pass
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -74,7 +74,8 @@ typedef struct rdb200_stats {
 RDB200_API int rdb200_get_stats(rdb200_stats *out);
 
 /* Tunables (algorithm switches and debug aids; see struct Params in csrc/common.cuh for the list and the
- * defaults).  "reset_defaults" restores every one of them.  They are process-wide and survive
+ * defaults).  "reset_defaults" restores every one of them; "trim_workspace" returns the cached device scratch (kept
+ * between calls so that repeated calls do not pay cudaMalloc) to the driver.  They are process-wide and survive
  * rdb200_shutdown / re-init.  The library is single-threaded by contract (see above). */
 RDB200_API int rdb200_set_param(const char *name, int64_t value);
 

@@ -1064,26 +1064,36 @@ __device__ __forceinline__ double fx_to_double(unsigned long long fx) { return (
 // in which case they poll their tickets -- and a slot becomes visible when its cell id (+1) is stored after the cell's
 // final value.  Termination: every data cell is walked exactly once; warps add what they walked to `done` when they run
 // dry and leave when it reaches the number of data cells.  A spin budget turns a protocol error into an error code.
-struct DinfShare {
-  int head, tail;   // tickets claimed / slots taken
+struct alignas(8) DinfShare {
+  int head, tail;   // tickets claimed / slots taken (read together as one 64-bit word)
   int done;         // cells walked, as reported by warps that ran dry
   int n_data;       // cells that have to be walked (every cell that is not NoData)
   int abort_flag;   // the spin budget of a warp expired
   int cursor;       // source scan
+  int n_noflow;     // data cells without a receiver (flat cells of an unresolved DEM, raster edge)
 };
 
 __global__ void __launch_bounds__(256) dinf_count_data_kernel(const uint8_t *__restrict__ code, size_t n, DinfShare *sh) {
-  int k = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    k += code[i] != kCodeNoData;
-  for (int o = 16; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
-  __shared__ int sk[8];
-  if ((threadIdx.x & 31) == 0) sk[threadIdx.x >> 5] = k;
+  int k = 0, z = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int cd = code[i];
+    k += cd != kCodeNoData;
+    z += cd == 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    k += __shfl_xor_sync(0xffffffffu, k, o);
+    z += __shfl_xor_sync(0xffffffffu, z, o);
+  }
+  __shared__ int sk[2][8];
+  if ((threadIdx.x & 31) == 0) {
+    sk[0][threadIdx.x >> 5] = k;
+    sk[1][threadIdx.x >> 5] = z;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 2) {
     int t = 0;
-    for (int w = 0; w < 8; w++) t += sk[w];
-    if (t) atomicAdd(&sh->n_data, t);
+    for (int w = 0; w < 8; w++) t += sk[threadIdx.x][w];
+    if (t) atomicAdd(threadIdx.x == 0 ? &sh->n_data : &sh->n_noflow, t);
   }
 }
 
@@ -1104,6 +1114,8 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
   int claim_pos = 0, claim_end = 0;  // warp-uniform: tickets of the global queue this warp still has to collect
   int walked = 0;                 // warp-uniform: cells walked since the last report
   long long spins = 0;
+  unsigned iter = 0;
+  unsigned backoff = 250u;        // ns a dry warp sleeps between two looks at the global state
   bool walking = false;
   int c = 0;
   unsigned long long acc = 0;
@@ -1136,12 +1148,17 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
       count += __popc(bal);
       pos += 32;
     }
-    // ---- global queue: a warp that is running dry claims tickets and collects whatever has arrived on them ----
-    if (count < 32 && !more && pos >= end) {
+    // ---- global queue: a warp with lanes it cannot feed claims tickets and collects whatever has arrived on them.
+    // Looking at the shared counters costs an L2 round trip on a line every warp reads: a warp that still walks does it
+    // every 16th step only, so that the lanes on a long river are not slowed down by their idle neighbours ----
+    iter++;
+    const int hungry = __popc(__ballot_sync(full, !walking && pend < 0));
+    if (!more && pos >= end && count < hungry && (hungry == 32 || (iter & 15) == 0)) {
       if (claim_pos >= claim_end) {
         int base = -1;
         if (lane == 0) {
-          const int t = *reinterpret_cast<volatile int *>(&sh->tail), h = *reinterpret_cast<volatile int *>(&sh->head);
+          const long long ht = *reinterpret_cast<volatile long long *>(&sh->head);  // {head, tail} in one load
+          const int h = (int)(ht & 0xffffffffll), t = (int)(ht >> 32);
           if (h < t) base = atomicAdd(&sh->head, 32);
         }
         base = __shfl_sync(full, base, 0);
@@ -1199,7 +1216,7 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
       }
       int fin = 0;
       if (lane == 0) {
-        fin = atomicAdd(&sh->done, 0) >= n_data ? 1 : 0;
+        fin = *reinterpret_cast<volatile int *>(&sh->done) >= n_data ? 1 : 0;
         if (!fin && ++spins > spin_limit) {
           atomicExch(&sh->abort_flag, 1);
           fin = 1;
@@ -1208,8 +1225,12 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
       }
       fin = __shfl_sync(full, fin, 0);
       if (fin) break;
+      // back off: thousands of dry warps polling one address would starve the L2 slice the walkers' atomics need
+      __nanosleep(backoff);
+      backoff = backoff < 8000u ? backoff * 2u : 8000u;
       continue;
     }
+    backoff = 250u;
     // ---- one walk step: push this cell's flow to its receiver(s) ----
     int extra = -1;  // a second receiver completed by this lane in this step
     unsigned long long extra_acc = 0;
@@ -1406,22 +1427,36 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     c.stats.accum_rounds = 1;
     return;
   }
+  DevBuf<uint8_t> code(n);
+  DevBuf<float> rmax;
+  bool have_codes = false;
+  // Unit-weight D-infinity has two engines.  The packed fixed-point walk (accum_walk_dinf_lanes_kernel) is throughput
+  // bound: 75 ms against 490 ms at 32768^2 on a filled DEM, whose flats end every flow path early.  After flat
+  // resolution every cell flows on, the longest dependency chains have tens of thousands of cells, and the level kernel's
+  // barriers (540 ms) still beat the walk's long tail (780 ms).  accum_dinf_packed: 0 level kernel, 1 packed walk,
+  // 2 (default) packed walk when more than 5 % of the data cells have no receiver.
   if (dinf && ones && (w & 3) == 0 && ((uintptr_t)d_accum & 15) == 0 && c.params.accum_dinf_packed) {
-    // unit-weight D-infinity on packed fixed-point words (see accum_walk_dinf_lanes_kernel)
-    DevBuf<uint8_t> code(n);
-    DevBuf<float> rmax(n);
+    rmax.alloc(n);
     const unsigned blocks = (unsigned)((n + 255) / 256);
     unsigned long long *word = reinterpret_cast<unsigned long long *>(d_accum);
-    flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, 0);
+    flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, 1);
+    have_codes = true;
+    DevBuf<DinfShare> share(1);
+    RDB_CK(cudaMemsetAsync(share.p, 0, sizeof(DinfShare), c.stream));
+    dinf_count_data_kernel<<<c.num_sms * 8, 256, 0, c.stream>>>(code.p, n, share.p);
+    RDB_CK(cudaGetLastError());
+    count_launch(2);
+    DinfShare *hs0 = reinterpret_cast<DinfShare *>(c.pinned);
+    RDB_CK(cudaMemcpyAsync(hs0, share.p, sizeof(DinfShare), cudaMemcpyDeviceToHost, c.stream));
+    RDB_CK(cudaStreamSynchronize(c.stream));
+    const bool use_packed = c.params.accum_dinf_packed == 1 || (long long)hs0->n_noflow * 20 > (long long)hs0->n_data;
+    if (use_packed) {
     dim3 blk(256), grd((w / 4 + 255) / 256, h < 8192 ? h : 8192);
     deps_gather_packed_dinf_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, w, h);
     RDB_CK(cudaGetLastError());
-    count_launch(2);
+    count_launch();
     DevBuf<int> gq(n);
-    DevBuf<DinfShare> share(1);
     RDB_CK(cudaMemsetAsync(gq.p, 0, n * sizeof(int), c.stream));
-    RDB_CK(cudaMemsetAsync(share.p, 0, sizeof(DinfShare), c.stream));
-    dinf_count_data_kernel<<<c.num_sms * 8, 256, 0, c.stream>>>(code.p, n, share.p);
     int per_sm = 0;
     RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_dinf_lanes_kernel, 256, 0));
     if (per_sm < 1) per_sm = 1;
@@ -1438,7 +1473,7 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
       int a_w = w, a_n = (int)n;
       int *a_gq = gq.p;
       DinfShare *a_sh = share.p;
-      long long a_spin = 20000000;
+      long long a_spin = 4000000;  // ~ 30 s of 8 us naps
       int a_share = (int)(c.params.accum_dinf_share >= 0 ? c.params.accum_dinf_share : 64);
       if (a_share > kLaneQueueD - 96) a_share = kLaneQueueD - 96;
       void *args[] = {(void *)&a_code, (void *)&a_rmax, (void *)&word, (void *)&a_w, (void *)&a_n, (void *)&a_gq, (void *)&a_sh,
@@ -1458,13 +1493,14 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
       fail("D-infinity accumulation (packed walk): the work-sharing protocol did not finish (walked %d of %d cells, watchdog %d)",
            hs->done, hs->n_data, hs->abort_flag);
     return;
+    }
   }
-  DevBuf<uint8_t> code(n);
   DevBuf<uint32_t> st(n);
-  DevBuf<float> rmax;
-  if (dinf) rmax.alloc(n);
+  if (dinf && !have_codes) rmax.alloc(n);
   const unsigned blocks = (unsigned)((n + 255) / 256);
-  if (dinf)
+  if (have_codes) {
+    // flow codes, rmax and the unit weights are in place already
+  } else if (dinf)
     flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, ones ? 1 : 0);
   else if ((w & 3) == 0 && ((uintptr_t)d_dem & 15) == 0 && ((uintptr_t)d_accum & 15) == 0) {
     dim3 blk(256), grd((w / 4 + 255) / 256, h < 8192 ? h : 8192);

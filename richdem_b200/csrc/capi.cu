@@ -99,6 +99,19 @@ void ws_free(void *p) {
     }
 }
 
+// frees every cached block that is not in use (rdb200_set_param("trim_workspace", 1)): the cache only grows otherwise
+void ws_trim() {
+  Ctx &c = ctx();
+  for (auto it = c.ws.begin(); it != c.ws.end();) {
+    if (!it->in_use) {
+      cudaFree(it->ptr);
+      it = c.ws.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
 void ws_release_all() {
   Ctx &c = ctx();
   for (auto &b : c.ws) cudaFree(b.ptr);
@@ -226,6 +239,12 @@ int rdb200_set_param(const char *name, int64_t value) {
   Params &p = ctx().params;
   const std::string n(name);
   if (n == "reset_defaults") p = Params();
+  else if (n == "trim_workspace") {
+    if (ctx().inited) {
+      RDB_CK(cudaStreamSynchronize(ctx().stream));
+      ws_trim();
+    }
+  }
   else if (n == "fill_max_iters") p.fill_max_iters = value;
   else if (n == "fill_rounds_per_sync") p.fill_rounds_per_sync = value > 0 ? value : 16;
   else if (n == "fill_use_tma") p.fill_use_tma = value;

@@ -71,7 +71,7 @@ struct Params {
   int64_t flats_fused_classify = 1;  // FindFlats + FindFlatEdges in one shared-memory window pass (single-GPU path)
   int64_t flats_pair = 1;    // the two gradient solves run side by side on two streams
   int64_t flats_tiled = 1;   // flat-resolution gradients by the tile engine (0: one cooperative BFS launch each)
-  int64_t accum_dinf_packed = 0;  // unit-weight D-infinity on 56-bit fixed-point words, no levels (1: on; measured slower: hand-overs stay in their warp)
+  int64_t accum_dinf_packed = 2;  // unit-weight D-infinity: 0 level kernel, 1 packed fixed-point walk, 2 the walk when > 5 % of the cells have no receiver
   int64_t accum_dinf_share = -1;  // packed D-infinity: ring length above which hand-overs go to the global queue (-1: 64)
   int64_t accum_packed = 1;  // unit-weight D8: accumulator and donor count share one 64-bit word
   int64_t accum_fused_prep = 1;   // unit-weight D8: flow codes + donor counts + sole-donor bits in one rolling-window pass

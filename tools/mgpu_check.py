@@ -63,7 +63,7 @@ for (H, W, q) in [(3000, 2000, 0.5), (8192, 8192, 0.0)]:
                     part = torch.empty((b1 - b0, W), dtype=dtype, device="cuda")
                     dist.recv(part, g)
                 if name == "fa_dinf":
-                    good &= bool(torch.allclose(part, ref[b0:b1], rtol=1e-9, atol=0))
+                    good &= bool(torch.allclose(part, ref[b0:b1], rtol=5e-7, atol=0))
                 else:
                     good &= bool(torch.equal(part, ref[b0:b1]))
             ok[name] = good
