@@ -163,6 +163,29 @@ RDB200_API int rdb200_fa_holmgren_f32_f64(const float *dem, double *accum_inout,
 RDB200_API int rdb200_fa_freeman_f32_f64(const float *dem, double *accum_inout, int32_t width, int32_t height,
                                          float nodata, double xparam);
 
+/* richdem::TA_slope_riserun / TA_slope_percentage / TA_slope_degrees / TA_slope_radians / TA_aspect / TA_curvature /
+ * TA_planform_curvature / TA_profile_curvature(const Array2D<float>&, Array2D<float>&, float zscale)
+ *   include/richdem/methods/terrain_attributes.hpp:370-538 over TerrainProcessor (:336-354) and the per-cell
+ *   formulas (:154-322); pyrichdem TerrainAttribute (wrappers/pyrichdem/richdem/__init__.py:735-794).
+ *   NoData cells of the input (== nodata_in) become nodata_out (the output raster's own NoData, -9999 from
+ *   pyrichdem); neighbours that are NoData or outside the raster take the centre's value.  cell_x / cell_y are
+ *   |geotransform[1]| and |geotransform[5]| (Array2D.hpp:1387-1399).  Double arithmetic in the reference's order
+ *   without fused multiply-adds: slopes (rise/run, percentage) and the three curvatures are bit-identical to a
+ *   stock x86-64 build of the reference; the attributes through atan / atan2 (degrees, radians, aspect) are within
+ *   1 float ulp (device libm differs from glibc by <= 2 ulp of the double). */
+enum {
+  RDB200_TA_SLOPE_RISERUN = 0,
+  RDB200_TA_SLOPE_PERCENTAGE = 1,
+  RDB200_TA_SLOPE_DEGREES = 2,
+  RDB200_TA_SLOPE_RADIANS = 3,
+  RDB200_TA_ASPECT = 4,
+  RDB200_TA_CURVATURE = 5,
+  RDB200_TA_PLANFORM_CURVATURE = 6,
+  RDB200_TA_PROFILE_CURVATURE = 7
+};
+RDB200_API int rdb200_terrain_attribute_f32(int32_t attribute, const float *dem, float *out, int32_t width, int32_t height,
+                                            float nodata_in, float nodata_out, float zscale, double cell_x, double cell_y);
+
 /* richdem::FlowAccumulation(const Array3D<float>&, Array2D<double>&)
  *   include/richdem/methods/flow_accumulation_generic.hpp:33-100 (pyrichdem
  *   "FlowAccumulation", wrappers/pyrichdem/src/pywrapper.cpp:50).  accum arrives holding the
@@ -200,6 +223,9 @@ RDB200_API int rdb200_dev_fm_method_f32(int32_t method, const float *d_dem, floa
                                         int32_t height, float nodata, double xparam);
 RDB200_API int rdb200_dev_fa_method_f32_f64(int32_t method, const float *d_dem, double *d_accum_inout, int32_t width,
                                             int32_t height, float nodata, double xparam);
+RDB200_API int rdb200_dev_terrain_attribute_f32(int32_t attribute, const float *d_dem, float *d_out, int32_t width,
+                                                int32_t height, float nodata_in, float nodata_out, float zscale,
+                                                double cell_x, double cell_y);
 RDB200_API int rdb200_dev_flow_accumulation_props_f64(const float *d_props9, double *d_accum_inout,
                                            int32_t width, int32_t height);
 RDB200_API int rdb200_dev_fa_d8_f32_f64(const float *d_dem, double *d_accum_inout, int32_t width,

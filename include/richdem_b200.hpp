@@ -5,7 +5,7 @@
 //
 //     <richdem/depressions/depressions.hpp>   <richdem/flats/flats.hpp>
 //     <richdem/methods/flow_accumulation.hpp> <richdem/flowmet/d8_flowdirs.hpp>
-//     <richdem/methods/d8_methods.hpp>
+//     <richdem/methods/d8_methods.hpp>         <richdem/methods/terrain_attributes.hpp>
 //
 // itself and then declares the explicit specialisations, so they are seen before any implicit
 // instantiation.  Without RichDEM on the include path only the duck-typed helpers in namespace
@@ -81,6 +81,12 @@ template <class A2, class P3>
 void fm_freeman(const A2 &dem, P3 &props, double xparam) {
   check(rdb200_fm_freeman_f32(dem.data(), props.getData(), dem.width(), dem.height(), (float)dem.noData(), xparam));
 }
+// attribute: RDB200_TA_*; `out` must already have the raster's size (TerrainProcessor resizes it, terrain_attributes.hpp:344)
+template <class A2, class O2>
+void terrain_attribute(int attribute, const A2 &dem, O2 &out, float zscale) {
+  check(rdb200_terrain_attribute_f32(attribute, dem.data(), out.data(), dem.width(), dem.height(), (float)dem.noData(),
+                                     (float)out.noData(), zscale, dem.getCellLengthX(), dem.getCellLengthY()));
+}
 template <class P3, class C2>
 void flow_accumulation(P3 &props, C2 &accum) {
   check(rdb200_flow_accumulation_props_f64(props.getData(), accum.data(), accum.width(), accum.height()));
@@ -126,6 +132,7 @@ void fa_tarboton(const A2 &dem, C2 &accum) {
 #include <richdem/flowmet/d8_flowdirs.hpp>
 #include <richdem/methods/d8_methods.hpp>
 #include <richdem/methods/flow_accumulation.hpp>
+#include <richdem/methods/terrain_attributes.hpp>
 
 namespace richdem {
 
@@ -291,6 +298,23 @@ inline void FA_Freeman<float, double>(const Array2D<float> &elevations, Array2D<
     throw std::runtime_error("Accumulation array must have same dimensions as proportions array!");
   richdem_b200::fa_freeman(elevations, accum, xparam);
 }
+// methods/terrain_attributes.hpp:370-538 (pyrichdem binds &TA_x<float>, pywrapper.hpp:46-53).  As in TerrainProcessor
+// (:336-354) the output is resized to the elevations' shape and keeps its own NoData value.
+#define RICHDEM_B200_TA(NAME, ID)                                                                              \
+  template <>                                                                                                 \
+  inline void NAME<float>(const Array2D<float> &elevations, Array2D<float> &output, float zscale) {           \
+    output.resize(elevations);                                                                                \
+    richdem_b200::terrain_attribute(ID, elevations, output, zscale);                                          \
+  }
+RICHDEM_B200_TA(TA_slope_riserun, RDB200_TA_SLOPE_RISERUN)
+RICHDEM_B200_TA(TA_slope_percentage, RDB200_TA_SLOPE_PERCENTAGE)
+RICHDEM_B200_TA(TA_slope_degrees, RDB200_TA_SLOPE_DEGREES)
+RICHDEM_B200_TA(TA_slope_radians, RDB200_TA_SLOPE_RADIANS)
+RICHDEM_B200_TA(TA_aspect, RDB200_TA_ASPECT)
+RICHDEM_B200_TA(TA_curvature, RDB200_TA_CURVATURE)
+RICHDEM_B200_TA(TA_planform_curvature, RDB200_TA_PLANFORM_CURVATURE)
+RICHDEM_B200_TA(TA_profile_curvature, RDB200_TA_PROFILE_CURVATURE)
+#undef RICHDEM_B200_TA
 #endif
 
 }  // namespace richdem

@@ -68,6 +68,8 @@ class _Backend:
         self._fa_dinf = self._sig(n["fa_dinf"], [_f32p, C.c_int, C.c_int, C.c_float, _f64p])
         self._fm_method = self._sig(n["fm_method"], [C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_double, _f32p])
         self._fa_method = self._sig(n["fa_method"], [C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_double, _f64p])
+        self._ta = self._sig(n["terrain_attribute"], [C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                                      C.c_double, C.c_double, _f32p])
         self._extra = {}
         for k in ("fill_zhou", "fill_barnes", "fill_original", "fill_d4"):
             if k in n:
@@ -171,6 +173,17 @@ class _Backend:
         self._fa_method(self.METHOD_IDS[method], d, w, h, nodata, x, acc)
         return acc
 
+    # -- f4: terrain attributes (methods/terrain_attributes.hpp:370-538)
+    TA_IDS = {"slope_riserun": 0, "slope_percentage": 1, "slope_degrees": 2, "slope_radians": 3, "aspect": 4,
+              "curvature": 5, "planform_curvature": 6, "profile_curvature": 7}
+
+    def terrain_attribute(self, dem, attrib, nodata=-9999.0, zscale=1.0, cell=(1.0, 1.0), nodata_out=-9999.0):
+        d = self._dem(dem)
+        h, w = d.shape
+        out = np.empty((h, w), np.float32)
+        self._ta(self.TA_IDS[attrib], d, w, h, nodata, nodata_out, zscale, float(cell[0]), float(cell[1]), out)
+        return out
+
     # -- f2: direction-grid flat resolution (reference backend only: flats/flat_resolution.hpp:588-607)
     def d8_flow_directions_flats(self, dem, nodata):
         """(directions, mask, labels) of barnes_flat_resolution_d8(dem, dirs, alter=false)."""
@@ -237,6 +250,7 @@ _PORT_NAMES = dict(
     d8acc_i32="orc_d8_flow_accum_i32", fm_d8="orc_fm_d8_f32", fm_dinf="orc_fm_tarboton_f32",
     facc="orc_flow_accumulation_props_f64", fa_d8="orc_fa_d8_f32_f64",
     fa_dinf="orc_fa_tarboton_f32_f64", fm_method="orc_fm_method_f32", fa_method="orc_fa_method_f32_f64",
+    terrain_attribute="orc_terrain_attribute_f32",
     fill_d4="orc_fill_depressions_d4_f32",
 )
 _REF_NAMES = dict(
@@ -247,6 +261,7 @@ _REF_NAMES = dict(
     d8acc_i32="ref_d8_flow_accum_i32_i32", fm_d8="ref_fm_d8_f32", fm_dinf="ref_fm_tarboton_f32",
     facc="ref_flow_accumulation_props_f64", fa_d8="ref_fa_d8_f32_f64",
     fa_dinf="ref_fa_tarboton_f32_f64", fm_method="ref_fm_method_f32", fa_method="ref_fa_method_f32_f64",
+    terrain_attribute="ref_terrain_attribute_f32",
     fill_zhou="ref_priority_flood_zhou2016_f32", fill_barnes="ref_priority_flood_barnes2014_f32",
     fill_original="ref_priority_flood_original_f32", fill_d4="ref_fill_depressions_d4_f32",
 )

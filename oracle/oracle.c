@@ -697,6 +697,61 @@ void orc_fa_method_f32_f64(int method, const float *dem, int w, int h, float nod
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* Terrain attributes (methods/terrain_attributes.hpp).  attribute: 0 slope rise/run (:239-248), 1 percentage   */
+/* (:299-302), 2 degrees (:317-320), 3 radians (:308-311), 4 aspect (:222-236), 5 curvature (:254-258),           */
+/* 6 planform (:264-272), 7 profile (:278-286) -- numbering of the C ABI.  TerrainProcessor (:336-354): NoData    */
+/* cells get the output's NoData; TerrainSetup (:161-194): neighbours outside the raster or NoData take the       */
+/* centre's value, everything scaled by zscale in double.  Built with -ffp-contract=off like the stock reference. */
+static double ta_cell(int attribute, const float *dem, int w, int h, int x, int y, float nodata, float zscale, double lx,
+                      double ly) {
+  double z[9];
+  int k = 0;
+  for (int dy = -1; dy <= 1; dy++)
+    for (int dx = -1; dx <= 1; dx++, k++) {
+      const int nx = x + dx, ny = y + dy;
+      double v = dem[(size_t)y * w + x];
+      if (nx >= 0 && ny >= 0 && nx < w && ny < h && dem[(size_t)ny * w + nx] != nodata) v = dem[(size_t)ny * w + nx];
+      z[k] = v * zscale;
+    }
+  const double a = z[0], b = z[1], c = z[2], d = z[3], e = z[4], f = z[5], g = z[6], hh = z[7], i = z[8];
+  if (attribute <= 4) {
+    const double dzdx = ((c + 2 * f + i) - (a + 2 * d + g)) / 8 / lx;
+    const double dzdy = ((g + 2 * hh + i) - (a + 2 * b + c)) / 8 / ly;
+    if (attribute == 4) {
+      const double asp = 180.0 / M_PI * atan2(dzdy, -dzdx);
+      if (asp < 0) return 90 - asp;
+      if (asp > 90.0) return 360.0 - asp + 90.0;
+      return 90.0 - asp;
+    }
+    const double rr = sqrt(dzdx * dzdx + dzdy * dzdy);
+    if (attribute == 0) return rr;
+    if (attribute == 1) return rr * 100;
+    if (attribute == 2) return atan(rr) * 180 / M_PI;
+    return atan(rr);
+  }
+  const double L = lx;
+  const double D = ((d + f) / 2 - e) / L / L;
+  const double E = ((b + hh) / 2 - e) / L / L;
+  const double F = (-a + c + g - i) / 4 / L / L;
+  const double G = (-d + f) / 2 / L;
+  const double H = (b - hh) / 2 / L;
+  if (attribute == 5) return -2 * (D + E) * 100;
+  if (G == 0 && H == 0) return 0;
+  if (attribute == 6) return -2 * (D * H * H + E * G * G - F * G * H) / (G * G + H * H) * 100;
+  return 2 * (D * G * G + E * H * H + F * G * H) / (G * G + H * H) * 100;
+}
+
+void orc_terrain_attribute_f32(int attribute, const float *dem, int w, int h, float nodata_in, float nodata_out, float zscale,
+                               double cell_x, double cell_y, float *out) {
+#pragma omp parallel for
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const size_t ci = (size_t)y * w + x;
+      out[ci] = dem[ci] == nodata_in ? nodata_out : (float)ta_cell(attribute, dem, w, h, x, y, nodata_in, zscale, cell_x, cell_y);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* Benchmark input: CPU restatement of the device terrain generator (richdem_b200/csrc/   */
 /* terrain.cu, fbm_kernel -- this repository's own synthetic DEM, not a reference         */
 /* function).  Same integer hash, same single-precision operation order, one rounding per */

@@ -19,6 +19,7 @@
 #include <richdem/flowmet/d8_flowdirs.hpp>
 #include <richdem/methods/d8_methods.hpp>
 #include <richdem/methods/flow_accumulation.hpp>
+#include <richdem/methods/terrain_attributes.hpp>
 
 #include <omp.h>
 
@@ -190,6 +191,29 @@ void ref_fa_method_f32_f64(int method, const float *dem, int w, int h, float nod
     case 3: if (xparam == 1.0) FA_Quinn(a, acc); else FA_Holmgren(a, acc, xparam); break;
     default: FA_Freeman(a, acc, xparam); break;
   }
+}
+
+// methods/terrain_attributes.hpp:370-538; attribute numbering of the C ABI (0 slope rise/run, 1 percentage, 2 degrees,
+// 3 radians, 4 aspect, 5 curvature, 6 planform, 7 profile).  The output raster keeps its own NoData (TerrainProcessor
+// :344 resizes without copying it), which is what nodata_out stands for.
+void ref_terrain_attribute_f32(int attribute, const float *dem, int w, int h, float nodata_in, float nodata_out, float zscale,
+                               double cell_x, double cell_y, float *out) {
+  Array2D<float> a(const_cast<float *>(dem), w, h);
+  a.setNoData(nodata_in);
+  a.geotransform = {0.0, cell_x, 0.0, 0.0, 0.0, -cell_y};
+  Array2D<float> o;
+  o.setNoData(nodata_out);
+  switch (attribute) {
+    case 0: TA_slope_riserun(a, o, zscale); break;
+    case 1: TA_slope_percentage(a, o, zscale); break;
+    case 2: TA_slope_degrees(a, o, zscale); break;
+    case 3: TA_slope_radians(a, o, zscale); break;
+    case 4: TA_aspect(a, o, zscale); break;
+    case 5: TA_curvature(a, o, zscale); break;
+    case 6: TA_planform_curvature(a, o, zscale); break;
+    default: TA_profile_curvature(a, o, zscale); break;
+  }
+  std::memcpy(out, o.data(), sizeof(float) * (size_t)w * h);
 }
 
 // flats/flat_resolution.hpp:588-607: barnes_flat_resolution_d8(elevations, flowdirs, alter = false) -- what

@@ -269,6 +269,33 @@ def FlowProportions(dem: rdarray, method: Optional[str] = None, exponent: Option
     return fprops
 
 
+_TERRAIN_ATTRIBS = {"slope_riserun": 0, "slope_percentage": 1, "slope_degrees": 2, "slope_radians": 3, "aspect": 4,
+                    "curvature": 5, "planform_curvature": 6, "profile_curvature": 7}
+
+
+def TerrainAttribute(dem: rdarray, attrib: str, zscale: float = 1.0) -> rdarray:
+    """richdem.TerrainAttribute (wrappers/pyrichdem/richdem/__init__.py:735-794) over TA_* (methods/
+    terrain_attributes.hpp:370-538): Horn (1981) slope / aspect, Zevenbergen & Thorne (1987) curvatures; float32
+    result with no_data -9999.  Cell lengths come from the geotransform (1 x 1 when there is none, as in the
+    reference's wrap())."""
+    if type(dem) is not rdarray:
+        raise Exception("A richdem.rdarray or numpy.ndarray is required!")
+    if attrib not in _TERRAIN_ATTRIBS:
+        raise Exception("Invalid TerrainAttributes attribute. Valid attributes are: " + ", ".join(_TERRAIN_ATTRIBS.keys()))
+    d = _dem_f32(dem, "TerrainAttribute")
+    h, w = d.shape
+    gt = dem.geotransform
+    if gt is None:
+        print("Warning! No geotransform defined. Choosing a standard one! (Top left cell's top let corner at <0,0>; cells are 1x1.)")
+        gt = [0, 1, 0, 0, 0, -1]
+    result = rdarray(np.zeros((h, w), np.float32), meta_obj=dem, no_data=-9999)
+    _add_analysis(result, f"TerrainAttribute(dem, attrib={attrib}, zscale={zscale})")
+    _lib.check(_lib.lib().rdb200_terrain_attribute_f32(_TERRAIN_ATTRIBS[attrib], _lib.ptr(d), _lib.ptr(result), w, h,
+                                                        _nodata_f32(dem), -9999.0, float(zscale), abs(float(gt[1])),
+                                                        abs(float(gt[5]))))
+    return result
+
+
 # ---- C++-only functions of the path, exposed for completeness ---------------------------------
 def FlowDirectionsD8(dem: rdarray) -> rdarray:
     """richdem::d8_flow_directions (flowmet/d8_flowdirs.hpp:96-123): uint8 codes 0..8, 255 NoData."""

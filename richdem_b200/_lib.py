@@ -56,6 +56,8 @@ SIGNATURES = {
     "rdb200_fm_quinn_f32": [_vp, _vp, _i32, _i32, _f32],
     "rdb200_fm_holmgren_f32": [_vp, _vp, _i32, _i32, _f32, C.c_double],
     "rdb200_fm_freeman_f32": [_vp, _vp, _i32, _i32, _f32, C.c_double],
+    "rdb200_terrain_attribute_f32": [_i32, _vp, _vp, _i32, _i32, _f32, _f32, _f32, C.c_double, C.c_double],
+    "rdb200_dev_terrain_attribute_f32": [_i32, _vp, _vp, _i32, _i32, _f32, _f32, _f32, C.c_double, C.c_double],
     "rdb200_fa_d4_f32_f64": [_vp, _vp, _i32, _i32, _f32],
     "rdb200_fa_quinn_f32_f64": [_vp, _vp, _i32, _i32, _f32],
     "rdb200_fa_holmgren_f32_f64": [_vp, _vp, _i32, _i32, _f32, C.c_double],

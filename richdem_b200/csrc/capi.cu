@@ -424,6 +424,22 @@ int rdb200_fm_freeman_f32(const float *dem, float *props, int32_t w, int32_t h, 
   return fm_host(dem, props, w, h, nodata, 4, xparam);
 }
 
+// TA_* (reference methods/terrain_attributes.hpp:370-538): one stencil pass, 4 B in + 4 B out per cell
+int rdb200_terrain_attribute_f32(int32_t attribute, const float *dem, float *out, int32_t w, int32_t h, float nodata_in,
+                                 float nodata_out, float zscale, double cell_x, double cell_y) {
+  CAPI_TRY
+  if (!dem || !out) fail("terrain attribute: null pointer");
+  check_dims(w, h);
+  CallScope cs((int64_t)w * h);
+  const size_t n = (size_t)w * h;
+  DevBuf<float> d(n), o(n);
+  h2d(d.p, dem, n);
+  terrain_attribute_dev(attribute, d.p, o.p, w, h, nodata_in, nodata_out, zscale, cell_x, cell_y);
+  d2h(out, o.p, n);
+  cs.done();
+  CAPI_END
+}
+
 // FA_<metric> = FM_<metric> into a device-side proportions array + the generic accumulation
 // (reference methods/flow_accumulation.hpp:18-20,28: `Array3D<float> props(elevations); FM_x(...); FlowAccumulation(...)`)
 static void fa_via_props_dev(int method, const float *d_dem, double *d_accum, int w, int h, float nodata, double xparam) {
@@ -550,6 +566,11 @@ int rdb200_dev_fa_d8_f32_f64(const float *d_dem, double *d_accum, int32_t w, int
 int rdb200_dev_fa_tarboton_f32_f64(const float *d_dem, double *d_accum, int32_t w, int32_t h, float nodata,
                                    int32_t ones) {
   DEV_ENTRY((int64_t)w * h, (check_dims(w, h), fa_fused_dev(d_dem, d_accum, w, h, nodata, ones != 0, true)))
+}
+int rdb200_dev_terrain_attribute_f32(int32_t attribute, const float *d_dem, float *d_out, int32_t w, int32_t h, float nodata_in,
+                                     float nodata_out, float zscale, double cell_x, double cell_y) {
+  DEV_ENTRY((int64_t)w * h, (check_dims(w, h), terrain_attribute_dev(attribute, d_dem, d_out, w, h, nodata_in, nodata_out, zscale,
+                                                                    cell_x, cell_y)))
 }
 int rdb200_dev_generate_fbm_f32(float *d_dem, int32_t w, int32_t h, int32_t y0, uint32_t seed, int32_t octaves,
                                 float quantum) {

@@ -179,6 +179,8 @@ void fm_freeman_dev(const float *d_dem, float *d_props, int w, int h, float noda
 void flow_accumulation_props_dev(const float *d_props, double *d_accum, int w, int h);
 void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodata, bool ones,
                   bool dinf);
+void terrain_attribute_dev(int attribute_id, const float *d_dem, float *d_out, int w, int h, float nodata_in, float nodata_out,
+                           float zscale, double cell_x, double cell_y);
 void generate_fbm_dev(float *d_dem, int w, int h, int y0, uint32_t seed, int octaves, float quantum);
 
 }  // namespace rdb

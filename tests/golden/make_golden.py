@@ -107,6 +107,7 @@ def main():
     np.savez_compressed(f"{OUT}/synthetic_ref.npz", **syn)
     metrics()
     flowdirs_flats()
+    terrain_attributes()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
@@ -143,10 +144,29 @@ def metrics():
     np.savez_compressed(f"{OUT}/flow_metrics_ref.npz", **out)
 
 
+TA_CASES = [(1.0, (1.0, 1.0)), (2.5, (30.0, 20.0))]
+
+
+def terrain_attributes():
+    """8. terrain attributes: TA_* of the unmodified reference (methods/terrain_attributes.hpp:370-538) on the
+    Beauford crop (NoData) and a seeded synthetic DEM, unit cells / zscale 1 and 30 x 20 cells / zscale 2.5."""
+    R = oracle.ref()
+    g = np.load(f"{OUT}/beauford_crop.npz")
+    syn = oracle.fbm_terrain(140, 190, seed=106, quantum=0.5)  # quantised: exact zero gradients exist
+    out = {"s106__dem": syn}
+    for name, dem in (("beauford", g["dem"]), ("s106", syn)):
+        for attrib in R.TA_IDS:
+            for zs, cell in TA_CASES:
+                out[f"{name}__{attrib}__{zs}"] = R.terrain_attribute(dem, attrib, -9999.0, zs, cell)[::3, ::3]
+    np.savez_compressed(f"{OUT}/terrain_attributes_ref.npz", **out)
+
+
 if __name__ == "__main__":
     if "--metrics-only" in sys.argv:
         metrics()
     elif "--flowdirs-flats-only" in sys.argv:
         flowdirs_flats()
+    elif "--terrain-attributes-only" in sys.argv:
+        terrain_attributes()
     else:
         main()

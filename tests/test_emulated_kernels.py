@@ -340,3 +340,11 @@ def test_rolling_flow_directions(emulated, gp, checker, shape):
     dem = checker.resolve_flats(checker.fill_depressions(oracle.fbm_terrain(*shape, seed=shape[1], quantum=0.5)), gp.ND)
     dem[shape[0] // 2:, shape[1] // 2: shape[1] // 2 + 3] = gp.ND
     assert np.array_equal(np.asarray(rd.FlowDirectionsD8(gp.R(dem))), checker.d8_flow_directions(dem, gp.ND))
+
+
+def test_terrain_attributes(emulated, gp, checker, golden):
+    """the TA_* stencil kernel -- window seams, NoData and raster-edge neighbours, all eight attributes."""
+    gp.test_terrain_attributes_golden(golden)
+    for shape in [(1, 9), (7, 1), (2, 2), (130, 129), (17, 257)]:
+        gp.test_terrain_attributes_vs_oracle(checker, shape)
+    gp.test_terrain_attribute_rejects_unknown_names()

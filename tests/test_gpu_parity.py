@@ -445,3 +445,52 @@ def test_flow_directions_with_resolved_flats_vs_oracle(checker, shape, seed, q):
     dirs_alt = np.asarray(rd.FlowDirectionsD8Resolved(d, alter=True))
     assert np.array_equal(np.asarray(d).view(np.uint32), checker.resolve_flats(filled, ND).view(np.uint32))
     assert np.array_equal(dirs_alt, checker.d8_flow_directions(np.asarray(d), ND))
+
+
+# ---- terrain attributes (TA_*, methods/terrain_attributes.hpp:370-538) ------------------------------------
+TA_EXACT = ("slope_riserun", "slope_percentage", "curvature", "planform_curvature", "profile_curvature")
+TA_LIBM = ("slope_degrees", "slope_radians", "aspect")  # through atan / atan2: <= 1 float ulp
+TA_CASES = [(1.0, (1.0, 1.0)), (2.5, (30.0, 20.0))]
+
+
+def check_terrain_attribute(got, ref, attrib, where):
+    assert got.dtype == np.float32 and got.shape == ref.shape
+    if attrib in TA_EXACT:
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (where, attrib, int((got != ref).sum()))
+    else:
+        d = ulp_diff(got, ref)
+        assert d.max() <= 1, (where, attrib, int(d.max()))
+        assert (d != 0).mean() < 1e-3, (where, attrib, float((d != 0).mean()))  # a rounding-boundary rarity, not a bias
+
+
+def test_terrain_attributes_golden(golden):
+    g = golden["terrain_attributes_ref"]
+    for name, dem in (("beauford", golden["beauford_crop"]["dem"]), ("s106", g["s106__dem"])):
+        for attrib in TA_EXACT + TA_LIBM:
+            for zs, cell in TA_CASES:
+                d = R(dem)
+                d.geotransform = [0.0, cell[0], 0.0, 0.0, 0.0, -cell[1]]
+                out = rd.TerrainAttribute(d, attrib, zscale=zs)
+                assert out.no_data == -9999
+                check_terrain_attribute(np.asarray(out)[::3, ::3], g[f"{name}__{attrib}__{zs}"], attrib, (name, zs))
+
+
+@pytest.mark.parametrize("shape", [(517, 1031), (1, 9), (7, 1), (2, 2), (130, 129), (16, 128), (17, 257)])
+def test_terrain_attributes_vs_oracle(checker, shape):
+    """Shapes around the 128 x 16 window of the kernel, degenerate rasters, NoData patches and NoData on the border."""
+    dem = oracle.fbm_terrain(*shape, seed=shape[0] + shape[1], quantum=0.25)
+    if shape[0] > 40:
+        dem[10:30, 20:90] = ND
+        dem[0, :7] = ND
+        dem[-1, -5:] = ND
+    for attrib in TA_EXACT + TA_LIBM:
+        d = R(dem)
+        d.geotransform = [100.0, 10.0, 0.0, 200.0, 0.0, -10.0]
+        got = np.asarray(rd.TerrainAttribute(d, attrib, zscale=0.3048))
+        ref = checker.terrain_attribute(dem, attrib, ND, 0.3048, (10.0, 10.0))
+        check_terrain_attribute(got, ref, attrib, shape)
+
+
+def test_terrain_attribute_rejects_unknown_names():
+    with pytest.raises(Exception, match="Invalid TerrainAttributes attribute"):
+        rd.TerrainAttribute(R(oracle.fbm_terrain(8, 8, seed=1)), "spi")

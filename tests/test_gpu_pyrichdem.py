@@ -95,3 +95,19 @@ def test_other_dtypes_keep_the_reference_cpu_templates(rdref, golden):
     g = golden["fill_testdem1"]
     f64 = rd.rdarray(g["dem"].astype(np.float64), no_data=float(g["nodata"]))
     assert np.array_equal(np.asarray(rd.FillDepressions(f64)), g["expected"].astype(np.float64))
+
+
+def test_reference_terrain_attribute_runs_on_the_b200(rdref, golden):
+    """richdem.TerrainAttribute (reference __init__.py:735-794) -> TA_x<float> (pywrapper.hpp:46-53) -> the explicit
+    specialisations of include/richdem_b200.hpp -> rdb200_terrain_attribute_f32."""
+    rd = rdref
+    g = golden["terrain_attributes_ref"]
+    dem = rd.rdarray(golden["beauford_crop"]["dem"].copy(), no_data=ND, geotransform=[0, 30.0, 0, 0, 0, -20.0])
+    for attrib in ("slope_riserun", "slope_percentage", "curvature", "planform_curvature", "profile_curvature"):
+        out = rd.TerrainAttribute(dem, attrib, zscale=2.5)
+        assert out.dtype == np.float32 and out.no_data == -9999
+        assert np.array_equal(np.asarray(out)[::3, ::3].view(np.uint32), g[f"beauford__{attrib}__2.5"].view(np.uint32)), attrib
+    for attrib in ("slope_degrees", "slope_radians", "aspect"):
+        got = np.asarray(rd.TerrainAttribute(dem, attrib, zscale=2.5))[::3, ::3]
+        ref = g[f"beauford__{attrib}__2.5"]
+        assert np.abs(got.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64)).max() <= 1, attrib

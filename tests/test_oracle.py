@@ -180,3 +180,32 @@ def test_direction_grid_flat_resolution_port_matches_compiled_reference_live(por
     a = port.d8_flow_directions_flats(dem, ND)
     b = oracle.ref().d8_flow_directions_flats(dem, ND)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2] != 0, b[2] != 0)
+
+
+# ---- terrain attributes --------------------------------------------------------------------------------------
+TA_CASES = [(1.0, (1.0, 1.0)), (2.5, (30.0, 20.0))]
+
+
+def test_terrain_attributes_against_reference_outputs(port, golden):
+    """TA_* (methods/terrain_attributes.hpp:370-538) against stored outputs of the unmodified reference
+    (tests/golden/make_golden.py::terrain_attributes): the restatement is bit-identical, libm calls included."""
+    g = golden["terrain_attributes_ref"]
+    for name, dem in (("beauford", golden["beauford_crop"]["dem"]), ("s106", g["s106__dem"])):
+        for attrib in port.TA_IDS:
+            for zs, cell in TA_CASES:
+                got = port.terrain_attribute(dem, attrib, ND, zs, cell)[::3, ::3]
+                assert np.array_equal(got.view(np.uint32), g[f"{name}__{attrib}__{zs}"].view(np.uint32)), (name, attrib, zs)
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no reference tree)")
+def test_terrain_attributes_port_matches_compiled_reference_live(port):
+    R = oracle.ref()
+    dem = oracle.fbm_terrain(150, 211, seed=23, quantum=0.5)
+    dem[20:40, 30:70] = ND
+    dem[0, :9] = ND
+    for attrib in port.TA_IDS:
+        for zs, cell, nd_out in ((1.0, (1.0, 1.0), -9999.0), (0.3048, (10.0, 10.0), -1.0), (3.0, (5.0, 7.5), -9999.0)):
+            a = port.terrain_attribute(dem, attrib, ND, zs, cell, nd_out)
+            b = R.terrain_attribute(dem, attrib, ND, zs, cell, nd_out)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (attrib, zs)
+            assert np.all(a[dem == ND] == nd_out)
