@@ -711,21 +711,34 @@ __global__ void __launch_bounds__(256) fa_d8_prep_rolling_kernel(const float *__
 #pragma unroll
     for (int r = 0; r < 4; r++) sDeps[r][t] = sDeps[r][kPrepCols + 4 + t] = 0;
   }
-  float d[3][6];  // DEM rows g-1, g, g+1 ; columns xc-1 .. xc+4
-  auto load_row = [&](int gy, float(&o)[6]) {
+  // DEM rows g-1, g, g+1 ; columns xc-1 .. xc+4.  NoData cells are held as NaN -- as a neighbour a NaN fails every
+  // comparison of the steepest-descent scan, which is exactly "skip NoData neighbours" -- and remembered in a bit mask
+  // per row for the cell's own NoData test (a NaN that is data, or a NaN NoData value, keeps the reference's behaviour:
+  // `== nodata` is false for it).
+  float d[3][6];
+  unsigned ndm[3];
+  const float kNaN = __int_as_float(0x7fc00000);
+  auto load_row = [&](int gy, float(&o)[6], unsigned &mask) {
     const bool rin = gy >= 0 && gy < H;
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
     if (rin && col_in) m = __ldg(reinterpret_cast<const float4 *>(dem + (size_t)gy * W + xc));
     float left = __shfl_up_sync(full, m.w, 1), right = __shfl_down_sync(full, m.x, 1);
     if (lane == 0) left = (rin && xc - 1 >= 0 && xc - 1 < W) ? __ldg(dem + (size_t)gy * W + xc - 1) : 0.f;
     if (lane == 31) right = (rin && xc + 4 >= 0 && xc + 4 < W) ? __ldg(dem + (size_t)gy * W + xc + 4) : 0.f;
-    o[0] = left; o[1] = m.x; o[2] = m.y; o[3] = m.z; o[4] = m.w; o[5] = right;
+    const float in[6] = {left, m.x, m.y, m.z, m.w, right};
+    mask = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const bool nd = in[k] == nodata;
+      o[k] = nd ? kNaN : in[k];
+      if (k >= 1 && k <= 4 && nd) mask |= 1u << k;
+    }
   };
-  load_row(y0 - 3, d[0]);
-  load_row(y0 - 2, d[1]);
+  load_row(y0 - 3, d[0], ndm[0]);
+  load_row(y0 - 2, d[1], ndm[1]);
   for (int g = y0 - 2; g <= y0 + kPrepRows + 1; g++) {
     if (g - 2 >= H) break;  // no row left to write (uniform across the block)
-    load_row(g + 1, d[2]);
+    load_row(g + 1, d[2], ndm[2]);
     // ---- A: flow codes of row g (same per-cell rule as flow_code_d8_x4_kernel) ----
     {
       uint8_t cd[4];
@@ -738,17 +751,17 @@ __global__ void __launch_bounds__(256) fa_d8_prep_rolling_kernel(const float *__
         if (row_in && col_in && (g < y_lo || g >= y_hi)) {
           c = code[(size_t)g * W + x];  // a neighbouring band's row: its codes were installed by the caller
         } else if (row_in && col_in) {
-          if (e == nodata) {
+          if (ndm[1] & (1u << (k + 1))) {
             c = kCodeNoData;
           } else if (!(x == 0 || g == 0 || x == W - 1 || g == H - 1)) {
-            // neighbours n = 1..8 : W, NW, N, NE, E, SE, S, SW
+            // neighbours n = 1..8 : W, NW, N, NE, E, SE, S, SW.  The first strictly lowest neighbour below the cell
+            // wins: starting the running minimum at the cell's own value folds the reference's `>= e` skip into it
+            // (capped at FLT_MAX, the reference's starting value, which only matters for an infinite cell)
             const float ne[9] = {0.f, d[1][k], d[0][k], d[0][k + 1], d[0][k + 2], d[1][k + 2], d[2][k + 2], d[2][k + 1], d[2][k]};
-            float lowest = 3.402823466e+38f;
+            float lowest = fminf(e, 3.402823466e+38f);
 #pragma unroll
             for (int n = 1; n <= 8; n++) {
               const float v = ne[n];
-              if (v == nodata) continue;
-              if (v >= e) continue;
               if (v < lowest) {
                 lowest = v;
                 c = n;
@@ -764,29 +777,31 @@ __global__ void __launch_bounds__(256) fa_d8_prep_rolling_kernel(const float *__
         d[0][k] = d[1][k];
         d[1][k] = d[2][k];
       }
+      ndm[0] = ndm[1];
+      ndm[1] = ndm[2];
     }
     __syncthreads();
-    // ---- B: donors of row g-1 from code rows g-2, g-1, g ----
+    // ---- B: donors of row g-1 from code rows g-2, g-1, g, four cells at a time on packed bytes ----
     if (g >= y0) {
-      uint8_t r[3][6];
+      // m[j]: this thread's 4 codes of row g-2+j; wl / wr: the same row seen one column to the left / right
+      uint32_t m[3], wl[3], wr[3];
 #pragma unroll
       for (int j = 0; j < 3; j++) {
         const uint8_t *row = &sCode[(g - 2 + j + 10) % 5][4 + 4 * t];
-        const uchar4 m = *reinterpret_cast<const uchar4 *>(row);
-        r[j][0] = row[-1]; r[j][1] = m.x; r[j][2] = m.y; r[j][3] = m.z; r[j][4] = m.w; r[j][5] = row[4];
+        m[j] = *reinterpret_cast<const uint32_t *>(row);
+        wl[j] = (m[j] << 8) | (uint32_t)row[-1];
+        wr[j] = (m[j] >> 8) | ((uint32_t)row[4] << 24);
       }
-      uint8_t dp[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int nr[9] = {0, 1, 0, 0, 0, 1, 2, 2, 2};
-        const int nc[9] = {0, k, k, k + 1, k + 2, k + 2, k + 2, k + 1, k};
-        int deps = 0;
-#pragma unroll
-        for (int n = 1; n <= 8; n++)  // NoData (255 -> 15) and "no flow" (0) never equal an inverse direction
-          deps += ((r[nr[n]][nc[n]] & 15) == d8_inverse(n)) ? 1 : 0;
-        dp[k] = (uint8_t)deps;
-      }
-      *reinterpret_cast<uchar4 *>(&sDeps[(g - 1 + 8) % 4][4 + 4 * t]) = make_uchar4(dp[0], dp[1], dp[2], dp[3]);
+      // byte k of the result is 1 where the neighbour's direction (low 4 bits; NoData 255 -> 15 and "no flow" 0 never
+      // equal an inverse direction) points back at cell k: x is 0..15 per byte, x + 0x7f sets bit 7 exactly where x != 0
+      auto points_back = [](uint32_t w, uint32_t inv) -> uint32_t {
+        const uint32_t x = (w & 0x0f0f0f0fu) ^ (inv * 0x01010101u);
+        return (~(x + 0x7f7f7f7fu) & 0x80808080u) >> 7;
+      };
+      // neighbours n = 1..8 : W, NW, N, NE, E, SE, S, SW, each against d8_inverse(n) = 5, 6, 7, 8, 1, 2, 3, 4
+      const uint32_t deps4 = points_back(wl[1], 5) + points_back(wl[0], 6) + points_back(m[0], 7) + points_back(wr[0], 8) +
+                             points_back(wr[1], 1) + points_back(wr[2], 2) + points_back(m[2], 3) + points_back(wl[2], 4);
+      *reinterpret_cast<uint32_t *>(&sDeps[(g - 1 + 8) % 4][4 + 4 * t]) = deps4;
     }
     __syncthreads();
     // ---- C: write row g-2 ----
