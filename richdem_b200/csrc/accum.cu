@@ -23,6 +23,7 @@ namespace {
 constexpr uint32_t kDepsMask = 0xFFu;
 constexpr uint32_t kSrcFlag = 0x80000000u;
 constexpr int kCodeSole = 32;  // bit 5 of a code byte: this cell is the only donor of its receiver
+constexpr int kCodeSource = 64;  // bit 6: this cell has no donors (set by the fused D8 preparation for the walk's source scan)
 constexpr int kLaneChunk = 1024;  // cells a persistent warp fetches per cursor atomic (source scans)
 
 // ---- K1: dem -> compact flow code (+ rmax for D-infinity), weights/NoData initialisation ------
@@ -824,6 +825,7 @@ __global__ void __launch_bounds__(256) fa_d8_prep_rolling_kernel(const float *__
           continue;
         }
         out[k] = dd[k] == 0 ? kPkSource : (((unsigned long long)dd[k] << 56) | 1ull);
+        if (dd[k] == 0) cc[k] |= kCodeSource;
         const int dir = cc[k] & 15;
         if (dir != 0) {
           const int ry = yy + d8dy(dir), ro = 4 + 4 * t + k + d8dx(dir);
@@ -902,27 +904,37 @@ __global__ void __launch_bounds__(256) accum_walk_packed_kernel(const uint8_t *_
 // are in flight.  Here a warp pulls chunks of cells from a global cursor, compacts their sources
 // (ballot + popc) into a small queue in shared memory, and every lane whose walk has ended takes
 // the next source from that queue; the loop body is one converged walk step for all 32 lanes.
-constexpr int kLaneQueue = 128;   // per-warp source queue (power of two, >= 64)
+constexpr int kLaneQueue = 256;   // per-warp source queue (power of two, >= 160: a refill adds up to 128 cells)
 
+// `src_in_code`: the preparation marked the cells without donors with kCodeSource in their code byte (the fused
+// preparation does), so the source scan reads 1 B/cell -- four cells per lane and load -- instead of the 8 B words.
+// A walking lane holds the code byte of its cell: the receiver's byte is fetched while the atomic on the receiver's
+// word is in flight (flow codes of this path never point at NoData -- the steepest-descent rule skips NoData
+// neighbours -- so nothing has to be known about the receiver before the add), which takes one of the two dependent
+// memory round trips out of every step.
 template <bool BAND>
 __global__ void __launch_bounds__(256) accum_walk_packed_lanes_kernel(const uint8_t *__restrict__ code,
                                                                        unsigned long long *word, int W, int ncells,
                                                                        const int *__restrict__ frontier, int ghost_lo_end,
-                                                                       int ghost_hi_start, int *cursor) {
+                                                                       int ghost_hi_start, int *cursor, int src_in_code) {
   __shared__ int sQ[8][kLaneQueue];
+  __shared__ uint8_t sQc[8][kLaneQueue];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   int *q = sQ[threadIdx.x >> 5];
+  uint8_t *qc = sQc[threadIdx.x >> 5];
   const unsigned lt = (1u << lane) - 1u;
+  const bool listed = BAND && frontier;
+  const int per_lane = (!listed && src_in_code) ? 4 : 1;  // candidates a lane looks at per refill step
   int head = 0, count = 0;           // warp-uniform queue state
   int pos = 0, end = 0;              // warp-uniform: next candidate, end of the current chunk
   bool more = true;                  // the cursor may still hold chunks
   bool walking = false;
-  int c = 0;
+  int c = 0, cdraw = 0;
   unsigned long long acc = 0;
   for (;;) {
     // ---- refill: keep at least a warp's worth of sources queued while candidates last ----
-    while (count <= kLaneQueue - 32) {
+    while (count <= kLaneQueue - 32 * per_lane) {
       if (pos >= end) {
         if (!more) break;
         int b = 0;
@@ -935,22 +947,38 @@ __global__ void __launch_bounds__(256) accum_walk_packed_lanes_kernel(const uint
         pos = b;
         end = b + kLaneChunk < ncells ? b + kLaneChunk : ncells;
       }
-      const int i = pos + lane;
-      bool src = false;
-      int cell = 0;
+      const int i = pos + per_lane * lane;
+      unsigned flags = 0;            // bit k: candidate i + k is a source
+      uint32_t bytes = 0;            // its code byte(s)
+      int cell = i;
       if (i < end) {
-        if (BAND && frontier) {
+        if (listed) {
           cell = frontier[i];
-          src = true;
-        } else {
-          cell = i;
-          src = word[i] == kPkSource;
+          bytes = code[cell];
+          flags = 1;
+        } else if (per_lane == 4) {  // chunks and ncells are multiples of 4 here (W % 4 == 0)
+          bytes = __ldg(reinterpret_cast<const uint32_t *>(code + i));
+          // a source byte has kCodeSource (bit 6) set and is not NoData (255, the only value with bit 7)
+          const uint32_t sb = (bytes >> 6) & ~(bytes >> 7) & 0x01010101u;
+          flags = (sb & 1u) | ((sb >> 7) & 2u) | ((sb >> 14) & 4u) | ((sb >> 21) & 8u);
+        } else if (word[i] == kPkSource) {
+          bytes = code[i];
+          flags = 1;
         }
       }
-      const unsigned bal = __ballot_sync(full, src);
-      if (src) q[(head + count + __popc(bal & lt)) & (kLaneQueue - 1)] = cell;
-      count += __popc(bal);
-      pos += 32;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (k >= per_lane) break;
+        const bool src = (flags >> k) & 1u;
+        const unsigned bal = __ballot_sync(full, src);
+        if (src) {
+          const int slot = (head + count + __popc(bal & lt)) & (kLaneQueue - 1);
+          q[slot] = cell + k;
+          qc[slot] = (uint8_t)(bytes >> (8 * k));
+        }
+        count += __popc(bal);
+      }
+      pos += 32 * per_lane;
     }
     __syncwarp();  // queue entries written above are read by other lanes below
     // ---- hand queued sources to the lanes that are not walking ----
@@ -958,8 +986,10 @@ __global__ void __launch_bounds__(256) accum_walk_packed_lanes_kernel(const uint
     if (idle == full && count == 0 && !more && pos >= end) break;
     const int rank = __popc(idle & lt);
     if (!walking && rank < count) {
-      c = q[(head + rank) & (kLaneQueue - 1)];
-      if (BAND && frontier) {
+      const int slot = (head + rank) & (kLaneQueue - 1);
+      c = q[slot];
+      cdraw = qc[slot];
+      if (listed) {
         acc = (unsigned long long)__longlong_as_double((long long)word[c]);  // completed by a neighbour's flow
       } else {
         acc = 1;
@@ -976,17 +1006,15 @@ __global__ void __launch_bounds__(256) accum_walk_packed_lanes_kernel(const uint
     __syncwarp();  // everyone has read its queue slot before the next refill overwrites the ring
     // ---- one walk step ----
     if (walking) {
-      const int cdraw = code[c];
       const int cd = cdraw & 15;
       if (cdraw == kCodeNoData || cd == 0) {
         walking = false;
       } else {
         const int r = c + d8dy(cd) * W + d8dx(cd);
+        const int cnext = code[r];  // in flight together with the atomic
         unsigned long long total = 0;
         if (cdraw & kCodeSole) {
           total = acc + 1;  // the receiver holds its own unit and waits for me alone
-        } else if (code[r] == kCodeNoData) {
-          walking = false;  // flow into NoData is dropped
         } else if (BAND && (r < ghost_lo_end || r >= ghost_hi_start)) {
           atomicAdd(word + r, acc + kPkOne);  // park in the ghost row: one more parcel, `acc` more flow
           walking = false;
@@ -999,6 +1027,7 @@ __global__ void __launch_bounds__(256) accum_walk_packed_lanes_kernel(const uint
           word[r] = (unsigned long long)__double_as_longlong((double)total);
           acc = total;
           c = r;
+          cdraw = cnext;
         }
       }
     }
@@ -1334,7 +1363,7 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
 // `cursor_buf` (optional): a device int the caller owns; the launch is then left in flight (no stream sync)
 template <bool BAND>
 void launch_walk_packed(const uint8_t *code, unsigned long long *word, int W, int ncells, const int *frontier,
-                        int ghost_lo_end, int ghost_hi_start, int *cursor_buf = nullptr) {
+                        int ghost_lo_end, int ghost_hi_start, bool src_in_code, int *cursor_buf = nullptr) {
   Ctx &c = ctx();
   if (ncells <= 0) return;
   if (c.params.accum_walk_lanes) {
@@ -1348,8 +1377,9 @@ void launch_walk_packed(const uint8_t *code, unsigned long long *word, int W, in
     long long blocks = (long long)c.num_sms * per_sm;
     const long long need = ((long long)ncells + kLaneChunk - 1) / kLaneChunk;  // no more warps than chunks
     if (blocks * 8 > need) blocks = (need + 7) / 8;
+    const int in_code = src_in_code && (ncells & 3) == 0 && ((uintptr_t)code & 3) == 0 ? 1 : 0;
     accum_walk_packed_lanes_kernel<BAND><<<(unsigned)blocks, 256, 0, c.stream>>>(code, word, W, ncells, frontier, ghost_lo_end,
-                                                                               ghost_hi_start, cur);
+                                                                               ghost_hi_start, cur, in_code);
     RDB_CK(cudaGetLastError());
     if (!cursor_buf) RDB_CK(cudaStreamSynchronize(c.stream));  // `cursor` goes out of scope
   } else {
@@ -1433,7 +1463,8 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     }
     RDB_CK(cudaGetLastError());
     KernelTimer kt;
-    launch_walk_packed<false>(code.p, reinterpret_cast<unsigned long long *>(d_accum), w, (int)n, nullptr, 0, 0);
+    launch_walk_packed<false>(code.p, reinterpret_cast<unsigned long long *>(d_accum), w, (int)n, nullptr, 0, 0,
+                              c.params.accum_fused_prep != 0);
     RDB_CK(cudaGetLastError());
     count_launch();
     kt.stop_async();
@@ -1734,17 +1765,17 @@ struct FaccState {
     if (!prepared && fused) {
       dim3 pgrd((unsigned)((W + kPrepOut - 1) / kPrepOut), (unsigned)((H + kPrepRows - 1) / kPrepRows));
       fa_d8_prep_rolling_kernel<<<pgrd, 256, 0, c.stream>>>(dem, code.p, word, W, H, nodata_v, gt, H - gb);
-      launch_walk_packed<true>(code.p, word, W, (int)n(), nullptr, lo_end, hi_start);
+      launch_walk_packed<true>(code.p, word, W, (int)n(), nullptr, lo_end, hi_start, true);
       count_launch(2);
       prepared = true;
     } else if (!prepared) {
       dim3 blk(256), grd((W / 4 + 255) / 256, H < 8192 ? H : 8192);
       deps_gather_packed_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, W, H, gt, H - gb);
-      launch_walk_packed<true>(code.p, word, W, (int)n(), nullptr, lo_end, hi_start);
+      launch_walk_packed<true>(code.p, word, W, (int)n(), nullptr, lo_end, hi_start, false);
       count_launch(2);
       prepared = true;
     } else if (n_frontier > 0) {
-      launch_walk_packed<true>(code.p, word, W, n_frontier, fr0.p, lo_end, hi_start);
+      launch_walk_packed<true>(code.p, word, W, n_frontier, fr0.p, lo_end, hi_start, false);
       count_launch();
     }
     RDB_CK(cudaGetLastError());
@@ -1776,11 +1807,11 @@ struct FaccState {
         dim3 blk(256), grd((W / 4 + 255) / 256, H < 8192 ? H : 8192);
         deps_gather_packed_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, W, H, gt, H - gb);
       }
-      launch_walk_packed<true>(code.p, word, W, (int)n(), nullptr, lo_end, hi_start, cnt.p);
+      launch_walk_packed<true>(code.p, word, W, (int)n(), nullptr, lo_end, hi_start, fused, cnt.p);
       count_launch(2);
       prepared = true;
     } else if (frontier_cells > 0) {
-      launch_walk_packed<true>(code.p, word, W, frontier_cells, fr0.p, lo_end, hi_start, cnt.p);
+      launch_walk_packed<true>(code.p, word, W, frontier_cells, fr0.p, lo_end, hi_start, false, cnt.p);
       count_launch();
     }
     RDB_CK(cudaGetLastError());
