@@ -1108,6 +1108,12 @@ __device__ __forceinline__ double fx_to_double(unsigned long long fx) { return (
 // in which case they poll their tickets -- and a slot becomes visible when its cell id (+1) is stored after the cell's
 // final value.  Termination: every data cell is walked exactly once; warps add what they walked to `done` when they run
 // dry and leave when it reaches the number of data cells.  A spin budget turns a protocol error into an error code.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct alignas(8) DinfShare {
   int head, tail;   // tickets claimed / slots taken (read together as one 64-bit word)
   int done;         // cells walked, as reported by warps that ran dry
@@ -1144,7 +1150,8 @@ __global__ void __launch_bounds__(256) dinf_count_data_kernel(const uint8_t *__r
 __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_t *__restrict__ code,
                                                                      const float *__restrict__ rmaxArr,
                                                                      unsigned long long *word, int W, int ncells, int *gq,
-                                                                     DinfShare *sh, long long spin_limit, int share_above) {
+                                                                     DinfShare *sh, long long spin_limit, int share_above,
+                                                                     int claim_mode, unsigned long long *stats) {
   __shared__ int sQ[8][kLaneQueueD];
   __shared__ unsigned long long sQa[8][kLaneQueueD];
   const unsigned full = 0xffffffffu;
@@ -1166,7 +1173,15 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
   int pend = -1;                  // a completed receiver this lane keeps for itself (ring full)
   unsigned long long pend_acc = 0;
   const int n_data = *reinterpret_cast<volatile int *>(&sh->n_data);
+  // optional counters (accum_dinf_stats): what the warps spent their loop iterations on
+  unsigned long long st_iters = 0, st_dry = 0, st_steps = 0, st_polls = 0, st_got = 0, st_glob = 0, st_loc = 0;
+  unsigned long long t_start = 0, t_scan_end = 0;
+  if (stats) t_start = global_ns();
   for (;;) {
+    if (stats) {
+      st_iters++;
+      if (!more && pos >= end && t_scan_end == 0) t_scan_end = global_ns();
+    }
     // ---- sources: refill from the scan only when the lanes would otherwise starve ----
     while (count < 32 && (more || pos < end)) {
       if (pos >= end) {
@@ -1199,16 +1214,27 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
     const int hungry = __popc(__ballot_sync(full, !walking && pend < 0));
     if (!more && pos >= end && count < hungry && (hungry == 32 || (iter & 15) == 0)) {
       if (claim_pos >= claim_end) {
-        int base = -1;
+        int base = -1, k = 32;
         if (lane == 0) {
           const long long ht = *reinterpret_cast<volatile long long *>(&sh->head);  // {head, tail} in one load
           const int h = (int)(ht & 0xffffffffll), t = (int)(ht >> 32);
-          if (h < t) base = atomicAdd(&sh->head, 32);
+          if (h < t) {
+            if (claim_mode == 0) {
+              base = atomicAdd(&sh->head, 32);  // possibly tickets nobody has taken a slot for yet
+            } else {
+              // only tickets that exist, and no more than this warp can put to work at once: a hand-over never waits
+              // in the claim of a warp whose lanes are all busy
+              k = hungry - count < t - h ? hungry - count : t - h;
+              if (atomicCAS(&sh->head, h, h + k) == h) base = h;
+            }
+          }
         }
         base = __shfl_sync(full, base, 0);
+        k = __shfl_sync(full, k, 0);
+        if (stats) st_polls++;
         if (base >= 0) {
           claim_pos = base;
-          claim_end = base + 32 < ncells ? base + 32 : ncells;
+          claim_end = base + k < ncells ? base + k : ncells;
         }
       }
       if (claim_pos < claim_end) {
@@ -1225,6 +1251,7 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
         }
         count += nready;
         claim_pos += nready;
+        if (stats) st_got += nready;
       }
     }
     __syncwarp();
@@ -1252,6 +1279,10 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
     __syncwarp();
     const unsigned busy = __ballot_sync(full, walking);
     walked += __popc(busy);
+    if (stats) {
+      st_steps += __popc(busy);
+      if (busy == 0) st_dry++;
+    }
     if (busy == 0) {
       // nothing to do right now: report, and leave when every data cell has been walked
       if (walked) {
@@ -1354,9 +1385,34 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
           }
         }
         count += local;
+        if (stats) {
+          st_glob += np - local;
+          st_loc += local;
+        }
       }
     }
     (void)pend_acc;
+  }
+  if (stats && lane == 0) {
+    const unsigned long long t_end = global_ns();
+    atomicAdd(stats + 0, st_iters);
+    atomicAdd(stats + 1, st_dry);
+    atomicAdd(stats + 2, st_steps);
+    atomicMax(stats + 3, st_iters);
+    atomicAdd(stats + 4, 1ull);
+    atomicAdd(stats + 5, st_polls);
+    atomicAdd(stats + 6, st_got);
+    atomicAdd(stats + 7, st_glob);
+    atomicAdd(stats + 8, st_loc);
+    atomicMax(stats + 9, st_iters - st_dry);
+    // when did this warp finish its source scan / leave?  log2 bins of microseconds since it started
+    auto bin = [](unsigned long long ns) {
+      const unsigned long long us = ns / 1000ull + 1ull;
+      const int b = 63 - __clzll((long long)us);
+      return b > 23 ? 23 : b;
+    };
+    atomicAdd(stats + 16 + bin((t_scan_end ? t_scan_end : t_end) - t_start), 1ull);
+    atomicAdd(stats + 40 + bin(t_end - t_start), 1ull);
   }
 }
 
@@ -1506,6 +1562,7 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     int per_sm = 0;
     RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_dinf_lanes_kernel, 256, 0));
     if (per_sm < 1) per_sm = 1;
+    DevBuf<unsigned long long> dstats;
     KernelTimer kt;
     // every block has to be resident: warps wait for each other's hand-overs
     long long nb = (long long)c.num_sms * per_sm;
@@ -1522,8 +1579,14 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
       long long a_spin = 4000000;  // ~ 30 s of 8 us naps
       int a_share = (int)(c.params.accum_dinf_share >= 0 ? c.params.accum_dinf_share : 64);
       if (a_share > kLaneQueueD - 96) a_share = kLaneQueueD - 96;
+      int a_claim = (int)c.params.accum_dinf_claim;
+      if (c.params.accum_dinf_stats) {
+        dstats.alloc(64);
+        RDB_CK(cudaMemsetAsync(dstats.p, 0, 64 * sizeof(unsigned long long), c.stream));
+      }
+      unsigned long long *a_stats = dstats.p;
       void *args[] = {(void *)&a_code, (void *)&a_rmax, (void *)&word, (void *)&a_w, (void *)&a_n, (void *)&a_gq, (void *)&a_sh,
-                      (void *)&a_spin, (void *)&a_share};
+                      (void *)&a_spin, (void *)&a_share, (void *)&a_claim, (void *)&a_stats};
       RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_walk_dinf_lanes_kernel, dim3((unsigned)nb), dim3(256), args, 0, c.stream));
     }
     RDB_CK(cudaGetLastError());
@@ -1535,6 +1598,20 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     RDB_CK(cudaStreamSynchronize(c.stream));
     c.stats.ms_main_kernel += kt.ms();
     c.stats.accum_rounds = rounds;
+    if (dstats.p) {
+      unsigned long long hsx[64];
+      RDB_CK(cudaMemcpy(hsx, dstats.p, sizeof(hsx), cudaMemcpyDeviceToHost));
+      fprintf(stderr,
+              "[dinf walk] %.2f ms, %llu warps: iterations sum %llu max %llu (busiest warp walked in %llu), dry %llu, lane-steps %llu "
+              "(%.1f %% of the lanes of non-dry iterations), polls %llu, collected %llu, handed over: %llu global %llu local\n",
+              kt.ms(), hsx[4], hsx[0], hsx[3], hsx[9], hsx[1], hsx[2],
+              100.0 * (double)hsx[2] / (32.0 * (double)(hsx[0] - hsx[1] ? hsx[0] - hsx[1] : 1)), hsx[5], hsx[6], hsx[7], hsx[8]);
+      fprintf(stderr, "[dinf walk] warps by log2(us) until their source scan ended:");
+      for (int b = 0; b < 24; b++) fprintf(stderr, " %llu", hsx[16 + b]);
+      fprintf(stderr, "\n[dinf walk] warps by log2(us) until they left:              ");
+      for (int b = 0; b < 24; b++) fprintf(stderr, " %llu", hsx[40 + b]);
+      fprintf(stderr, "\n");
+    }
     if (hs->abort_flag || hs->done != hs->n_data)
       fail("D-infinity accumulation (packed walk): the work-sharing protocol did not finish (walked %d of %d cells, watchdog %d)",
            hs->done, hs->n_data, hs->abort_flag);

@@ -24,10 +24,12 @@ if [ -z "$SKIP_TESTS" ]; then
   step pytest_gpu 900 python -m pytest tests -m gpu -x -q
 fi
 TAILN=40 step fill_trace 300 python tools/fill_profile.py "$N" "fill_trace=1"
-step fill_variants 400 python tools/fill_profile.py "$N" "" "fill_max_iters=2" "fill_max_iters=3" "fill_max_iters=4" "fill_max_iters=6" "fill_vcycle=4" "fill_vcycle=12"
+step fill_variants 400 python tools/fill_profile.py "$N" "" "fill_vcycle=4" "fill_vcycle=12"
 TAILN=60 step band_profile 300 python tools/band_profile.py "$N"
 step flats_profile 240 env RDB200_PROFILE=1 python tools/flats_profile.py "$N"
-step dinf_packed 240 python tools/flats_profile.py "$N" accum_dinf_packed=1
+TAILN=40 step dinf_engines 300 python tools/dinf_profile.py "$N" "accum_dinf_packed=0" "accum_dinf_packed=1 accum_dinf_stats=1" \
+  "accum_dinf_packed=1 accum_dinf_claim=1 accum_dinf_stats=1" "accum_dinf_packed=1 accum_dinf_claim=1 accum_dinf_share=8 accum_dinf_stats=1" \
+  "accum_dinf_packed=1 accum_dinf_claim=1 accum_dinf_share=0" "accum_dinf_packed=1 accum_dinf_claim=1 accum_dinf_share=128"
 TAILN=3 step bench 600 python bench.py --steps 5 --warmup 3
 grep -a '"metric"' "$OUT/bench.log" | tail -1 > "$OUT/bench.json"
 step ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file "$OUT/launches.csv" \
