@@ -558,7 +558,14 @@ def run_configs(args, world, rank, N, W, dem0, work, barrier, gmax):
         dirs = torch.empty((hloc, W), dtype=torch.uint8, device="cuda")
         ms = timed(lambda: _lib.check(L.rdb200_dev_d8_flow_directions_f32(work.data_ptr(), dirs.data_ptr(), W, hloc, ND)))
         out["d8_flow_directions"] = {"workload": f"{N}x{N} d8_flow_directions", "ms": ms, "mcells_per_s": cells / ms / 1e3}
-        del dirs, acc
+        # terrain attributes: one 3x3 stencil pass, 4 B in + 4 B out per cell
+        ta = torch.empty((hloc, W), dtype=torch.float32, device="cuda")
+        for ta_name, ta_id in (("slope_riserun", 0), ("aspect", 4), ("profile_curvature", 7)):
+            ms = timed(lambda: _lib.check(L.rdb200_dev_terrain_attribute_f32(ta_id, work.data_ptr(), ta.data_ptr(), W, hloc, ND, ND,
+                                                                              1.0, 1.0, 1.0)))
+            out["terrain_" + ta_name] = {"workload": f"{N}x{N} TA_{ta_name}", "ms": ms, "mcells_per_s": cells / ms / 1e3,
+                                         "gb_per_s": 8.0 * cells / ms / 1e6}
+        del dirs, acc, ta
 
         # configs 2 and 3 on their own rasters
         for name, n2, with_flats in (("fill4096", 4096, False), ("pipeline16384", 16384, True)):

@@ -904,6 +904,8 @@ __global__ void __launch_bounds__(256) accum_walk_packed_kernel(const uint8_t *_
 // are in flight.  Here a warp pulls chunks of cells from a global cursor, compacts their sources
 // (ballot + popc) into a small queue in shared memory, and every lane whose walk has ended takes
 // the next source from that queue; the loop body is one converged walk step for all 32 lanes.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 constexpr int kLaneQueue = 256;   // per-warp source queue (power of two, >= 160: a refill adds up to 128 cells)
 
 // `src_in_code`: the preparation marked the cells without donors with kCodeSource in their code byte (the fused
@@ -957,6 +959,10 @@ __global__ void __launch_bounds__(256) accum_walk_packed_lanes_kernel(const uint
           bytes = code[cell];
           flags = 1;
         } else if (per_lane == 4) {  // chunks and ncells are multiples of 4 here (W % 4 == 0)
+          // the walks that start here push into words of this and the neighbouring rows: have the 1 KB of words that
+          // belong to these 128 cells on their way into L2 (the 8 B/cell scan used to do that as a side effect; without
+          // it every first atomic on a line waits for DRAM) -- fire and forget, nothing depends on it
+          if (src_in_code == 1 && lane < 8 && pos + 16 * lane < end) prefetch_l2(word + pos + 16 * lane);
           bytes = __ldg(reinterpret_cast<const uint32_t *>(code + i));
           // a source byte has kCodeSource (bit 6) set and is not NoData (255, the only value with bit 7)
           const uint32_t sb = (bytes >> 6) & ~(bytes >> 7) & 0x01010101u;
@@ -1100,27 +1106,36 @@ __global__ void __launch_bounds__(256) deps_gather_packed_dinf_x4_kernel(const u
 __device__ __forceinline__ double fx_to_double(unsigned long long fx) { return (double)fx * (1.0 / 16777216.0); }
 
 // Work sharing.  A lane follows the first receiver it completes; a second one goes to its warp's ring in shared memory,
-// where idle lanes of the warp pick it up -- and, once the ring holds more than `share_above` (64) entries, to a global queue:
-// a river network that one warp happened to walk into is then drained by every warp that has run out of work (without
-// it a few warps inherit whole river systems: 2.4 s instead of 70 ms at 32768^2 after flat resolution).  The global
-// queue is a ticket queue over an array of n slots (a cell is queued at most once, so it never wraps): producers take
-// slots with atomicAdd(tail), starving warps claim 32 tickets with atomicAdd(head) -- possibly ahead of the producers,
-// in which case they poll their tickets -- and a slot becomes visible when its cell id (+1) is stored after the cell's
-// final value.  Termination: every data cell is walked exactly once; warps add what they walked to `done` when they run
-// dry and leave when it reaches the number of data cells.  A spin budget turns a protocol error into an error code.
+// where idle lanes of the warp pick it up.  What a warp completes stays with that warp, so after the source scan the
+// remaining work -- the big rivers and the resolved lakes -- sits with the few warps that happened to complete their
+// upstream ends: measured at 32768^2 after flat resolution, one warp walked 115 000 iterations at 30 busy lanes while
+// 7 000 warps had nothing to do (470 ms), and routing the hand-overs through a global ticket queue that every idle warp
+// polls cost more than it saved (3.8 s with most hand-overs shared).  So the work is rebalanced by stopping the world
+// instead: the kernel runs in PHASES separated by grid barriers.  A warp that has nothing left waits at the barrier; a
+// warp that holds more cells than it has lanes for (`excess_above` queued) while a quarter of the warps wait there asks
+// for the phase to end; every warp then appends what it holds -- ring entries and the cells its lanes stand on -- to a
+// list in global memory, and after the barrier all warps draw from that list in equal portions (a cell's fixed-point
+// sum is recovered from its final double).  The walk is over when a phase ends with an empty list.  No warp polls a
+// shared line while it works except one read every 16 iterations.
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
-struct alignas(8) DinfShare {
-  int head, tail;   // tickets claimed / slots taken (read together as one 64-bit word)
-  int done;         // cells walked, as reported by warps that ran dry
-  int n_data;       // cells that have to be walked (every cell that is not NoData)
-  int abort_flag;   // the spin budget of a warp expired
-  int cursor;       // source scan
-  int n_noflow;     // data cells without a receiver (flat cells of an unresolved DEM, raster edge)
+struct alignas(16) DinfShare {
+  int cursor;          // source scan
+  int n_data;          // cells that have to be walked (every cell that is not NoData)
+  int n_noflow;        // data cells without a receiver (flat cells of an unresolved DEM, raster edge)
+  int done;            // cells walked, reported at the end of every phase (checked by the host)
+  unsigned list_head;  // hand-over list: entries claimed
+  unsigned list_tail;  //                 entries appended
+  unsigned cons_end;   //                 [list_head, cons_end) may be claimed in the current phase
+  int quota;           // entries a warp claims at a time in the current phase
+  int stop;            // a warp asked for phase `stop - 1` to end
+  int n_waiting;       // warps at the barrier
+  int finished;        // the phase ended with an empty list
+  int phases;          // statistics
 };
 
 __global__ void __launch_bounds__(256) dinf_count_data_kernel(const uint8_t *__restrict__ code, size_t n, DinfShare *sh) {
@@ -1149,9 +1164,10 @@ __global__ void __launch_bounds__(256) dinf_count_data_kernel(const uint8_t *__r
 
 __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_t *__restrict__ code,
                                                                      const float *__restrict__ rmaxArr,
-                                                                     unsigned long long *word, int W, int ncells, int *gq,
-                                                                     DinfShare *sh, long long spin_limit, int share_above,
-                                                                     int claim_mode, unsigned long long *stats) {
+                                                                     unsigned long long *word, int W, int ncells, int *list,
+                                                                     unsigned cap, DinfShare *sh, int excess_above,
+                                                                     unsigned long long *stats) {
+  cg::grid_group grid = cg::this_grid();
   __shared__ int sQ[8][kLaneQueueD];
   __shared__ unsigned long long sQa[8][kLaneQueueD];
   const unsigned full = 0xffffffffu;
@@ -1159,260 +1175,246 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
   int *q = sQ[threadIdx.x >> 5];
   unsigned long long *qa = sQa[threadIdx.x >> 5];
   const unsigned lt = (1u << lane) - 1u;
+  const int n_warps = (int)gridDim.x * 8;
   int head = 0, count = 0;        // warp-uniform ring state
   int pos = 0, end = 0;           // warp-uniform: next source candidate, end of the current chunk
   bool more = true;               // the source cursor may still hold chunks
-  int claim_pos = 0, claim_end = 0;  // warp-uniform: tickets of the global queue this warp still has to collect
   int walked = 0;                 // warp-uniform: cells walked since the last report
-  long long spins = 0;
-  unsigned iter = 0;
-  unsigned backoff = 250u;        // ns a dry warp sleeps between two looks at the global state
   bool walking = false;
   int c = 0;
   unsigned long long acc = 0;
-  int pend = -1;                  // a completed receiver this lane keeps for itself (ring full)
-  unsigned long long pend_acc = 0;
-  const int n_data = *reinterpret_cast<volatile int *>(&sh->n_data);
+  int phase = 0, quota = 0;
+  unsigned cons_end = 0;
+  bool list_dry = true;           // nothing to claim from the list in this phase (phase 0: the list is empty)
   // optional counters (accum_dinf_stats): what the warps spent their loop iterations on
-  unsigned long long st_iters = 0, st_dry = 0, st_steps = 0, st_polls = 0, st_got = 0, st_glob = 0, st_loc = 0;
-  unsigned long long t_start = 0, t_scan_end = 0;
-  if (stats) t_start = global_ns();
-  for (;;) {
-    if (stats) {
-      st_iters++;
-      if (!more && pos >= end && t_scan_end == 0) t_scan_end = global_ns();
-    }
-    // ---- sources: refill from the scan only when the lanes would otherwise starve ----
-    while (count < 32 && (more || pos < end)) {
-      if (pos >= end) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(&sh->cursor, kLaneChunk);
-        b = __shfl_sync(full, b, 0);
-        if (b >= ncells) {
-          more = false;
-          break;
+  unsigned long long st_iters = 0, st_steps = 0, st_list = 0, st_loc = 0, st_got = 0;
+  for (;;) {  // phases
+    unsigned iter = 0;
+    for (;;) {  // iterations of this phase
+      iter++;
+      if (stats) st_iters++;
+      // ---- sources: refill from the scan only when the lanes would otherwise starve ----
+      while (count < 32 && (more || pos < end)) {
+        if (pos >= end) {
+          int b = 0;
+          if (lane == 0) b = atomicAdd(&sh->cursor, kLaneChunk);
+          b = __shfl_sync(full, b, 0);
+          if (b >= ncells) {
+            more = false;
+            break;
+          }
+          pos = b;
+          end = b + kLaneChunk < ncells ? b + kLaneChunk : ncells;
         }
-        pos = b;
-        end = b + kLaneChunk < ncells ? b + kLaneChunk : ncells;
+        const int i = pos + lane;
+        const bool src = i < end && word[i] == kFxSource;
+        const unsigned bal = __ballot_sync(full, src);
+        if (src) {
+          const int slot = (head + count + __popc(bal & lt)) & (kLaneQueueD - 1);
+          q[slot] = i;
+          qa[slot] = kFxOne;
+          word[i] = (unsigned long long)__double_as_longlong(1.0);
+        }
+        count += __popc(bal);
+        pos += 32;
       }
-      const int i = pos + lane;
-      const bool src = i < end && word[i] == kFxSource;
-      const unsigned bal = __ballot_sync(full, src);
-      if (src) {
-        const int slot = (head + count + __popc(bal & lt)) & (kLaneQueueD - 1);
-        q[slot] = i;
-        qa[slot] = kFxOne;
-        word[i] = (unsigned long long)__double_as_longlong(1.0);
+      // ---- the hand-over list of this phase: a warp with lanes it cannot feed claims its portion ----
+      const int hungry = __popc(__ballot_sync(full, !walking));
+      if (!list_dry && !more && pos >= end && count < hungry) {
+        unsigned h = 0;
+        if (lane == 0) h = atomicAdd(&sh->list_head, (unsigned)quota);
+        h = __shfl_sync(full, h, 0);
+        const int avail = (int)(cons_end - h);
+        if (avail <= 0) {
+          list_dry = true;
+        } else {
+          const int k = avail < quota ? avail : quota;
+          if (lane < k) {
+            const int cell = __ldcg(list + (h + (unsigned)lane) % cap);
+            const int slot = (head + count + lane) & (kLaneQueueD - 1);
+            q[slot] = cell;
+            qa[slot] = (unsigned long long)(__longlong_as_double((long long)__ldcg(word + cell)) * 16777216.0 + 0.5);
+          }
+          count += k;
+          if (stats) st_got += k;
+        }
       }
-      count += __popc(bal);
-      pos += 32;
-    }
-    // ---- global queue: a warp with lanes it cannot feed claims tickets and collects whatever has arrived on them.
-    // Looking at the shared counters costs an L2 round trip on a line every warp reads: a warp that still walks does it
-    // every 16th step only, so that the lanes on a long river are not slowed down by their idle neighbours ----
-    iter++;
-    const int hungry = __popc(__ballot_sync(full, !walking && pend < 0));
-    if (!more && pos >= end && count < hungry && (hungry == 32 || (iter & 15) == 0)) {
-      if (claim_pos >= claim_end) {
-        int base = -1, k = 32;
+      __syncwarp();
+      // ---- hand queued cells to the lanes that are not walking ----
+      const unsigned idle = __ballot_sync(full, !walking);
+      const int rank = __popc(idle & lt);
+      if (!walking && rank < count) {
+        const int slot = (head + rank) & (kLaneQueueD - 1);
+        c = q[slot];
+        acc = qa[slot];
+        walking = true;
+      }
+      {
+        const int nidle = __popc(idle);
+        const int taken = nidle < count ? nidle : count;
+        head = (head + taken) & (kLaneQueueD - 1);
+        count -= taken;
+      }
+      __syncwarp();
+      const unsigned busy = __ballot_sync(full, walking);
+      if (busy == 0) {
+        if (!more && pos >= end && list_dry) break;  // nothing left for this warp in this phase
+        continue;
+      }
+      // ---- has the end of the phase been asked for?  shall this warp ask? ----
+      if ((iter & 15u) == 0) {
+        int st = 0;
         if (lane == 0) {
-          const long long ht = *reinterpret_cast<volatile long long *>(&sh->head);  // {head, tail} in one load
-          const int h = (int)(ht & 0xffffffffll), t = (int)(ht >> 32);
-          if (h < t) {
-            if (claim_mode == 0) {
-              base = atomicAdd(&sh->head, 32);  // possibly tickets nobody has taken a slot for yet
-            } else {
-              // only tickets that exist, and no more than this warp can put to work at once: a hand-over never waits
-              // in the claim of a warp whose lanes are all busy
-              k = hungry - count < t - h ? hungry - count : t - h;
-              if (atomicCAS(&sh->head, h, h + k) == h) base = h;
-            }
+          st = *reinterpret_cast<volatile int *>(&sh->stop) > phase ? 1 : 0;
+          if (!st && count >= excess_above && (iter >= 64u || count >= kLaneQueueD - 64) &&
+              *reinterpret_cast<volatile int *>(&sh->n_waiting) * 4 >= n_warps) {
+            atomicMax(&sh->stop, phase + 1);
+            st = 1;
           }
         }
-        base = __shfl_sync(full, base, 0);
-        k = __shfl_sync(full, k, 0);
-        if (stats) st_polls++;
-        if (base >= 0) {
-          claim_pos = base;
-          claim_end = base + k < ncells ? base + k : ncells;
-        }
+        st = __shfl_sync(full, st, 0);
+        if (st) break;
       }
-      if (claim_pos < claim_end) {
-        int v = 0;
-        if (claim_pos + lane < claim_end) v = *reinterpret_cast<volatile int *>(gq + claim_pos + lane);
-        const unsigned ready = __ballot_sync(full, v != 0);
-        const int nready = ready == full ? 32 : __ffs(~ready) - 1;  // tickets are collected in order
-        if (lane < nready) {
-          const int cell = v - 1;
-          __threadfence();
-          const int slot = (head + count + lane) & (kLaneQueueD - 1);
-          q[slot] = cell;
-          qa[slot] = (unsigned long long)(__longlong_as_double((long long)__ldcg(word + cell)) * 16777216.0 + 0.5);
-        }
-        count += nready;
-        claim_pos += nready;
-        if (stats) st_got += nready;
-      }
-    }
-    __syncwarp();
-    // ---- hand queued cells to the lanes that are not walking ----
-    if (!walking && pend >= 0) {
-      c = pend;
-      acc = pend_acc;
-      pend = -1;
-      walking = true;
-    }
-    const unsigned idle = __ballot_sync(full, !walking);
-    const int rank = __popc(idle & lt);
-    if (!walking && rank < count) {
-      const int slot = (head + rank) & (kLaneQueueD - 1);
-      c = q[slot];
-      acc = qa[slot];
-      walking = true;
-    }
-    {
-      const int nidle = __popc(idle);
-      const int taken = nidle < count ? nidle : count;
-      head = (head + taken) & (kLaneQueueD - 1);
-      count -= taken;
-    }
-    __syncwarp();
-    const unsigned busy = __ballot_sync(full, walking);
-    walked += __popc(busy);
-    if (stats) {
-      st_steps += __popc(busy);
-      if (busy == 0) st_dry++;
-    }
-    if (busy == 0) {
-      // nothing to do right now: report, and leave when every data cell has been walked
-      if (walked) {
-        if (lane == 0) atomicAdd(&sh->done, walked);
-        walked = 0;
-      }
-      int fin = 0;
-      if (lane == 0) {
-        fin = *reinterpret_cast<volatile int *>(&sh->done) >= n_data ? 1 : 0;
-        if (!fin && ++spins > spin_limit) {
-          atomicExch(&sh->abort_flag, 1);
-          fin = 1;
-        }
-        if (!fin && *reinterpret_cast<volatile int *>(&sh->abort_flag)) fin = 1;
-      }
-      fin = __shfl_sync(full, fin, 0);
-      if (fin) break;
-      // back off: thousands of dry warps polling one address would starve the L2 slice the walkers' atomics need
-      __nanosleep(backoff);
-      backoff = backoff < 8000u ? backoff * 2u : 8000u;
-      continue;
-    }
-    backoff = 250u;
-    // ---- one walk step: push this cell's flow to its receiver(s) ----
-    int extra = -1;  // a second receiver completed by this lane in this step
-    unsigned long long extra_acc = 0;
-    if (walking) {
-      const int cd = code[c];
-      const int n1 = cd & 15;
-      if (cd == kCodeNoData || n1 == 0) {
-        walking = false;
-      } else {
-        const int r1 = c + d8dy(n1) * W + d8dx(n1);
-        int next = -1;
-        unsigned long long next_acc = 0;
-        if (cd & kCodeTwo) {
-          const int n2 = nwrap(n1 + 1);
-          const int r2 = c + d8dy(n2) * W + d8dx(n2);
-          float p1, p2;
-          tarboton_props(rmaxArr[c], &p1, &p2);
-          const double ad = (double)acc;
-          const unsigned long long v1 = p1 > 0 ? (unsigned long long)((double)p1 * ad + 0.5) : 0ull;
-          const unsigned long long v2 = p2 > 0 ? (unsigned long long)((double)p2 * ad + 0.5) : 0ull;
-          if (p1 > 0) {
-            const unsigned long long old = atomicAdd(word + r1, v1 - kPkOne);
-            if ((old >> 56) == 1ull) {
-              next = r1;
-              next_acc = (old & kPkVal) + v1;
-            }
-          }
-          if (p2 > 0) {
-            const unsigned long long old = atomicAdd(word + r2, v2 - kPkOne);
-            if ((old >> 56) == 1ull) {
-              const unsigned long long tot = (old & kPkVal) + v2;
-              if (next < 0) {
-                next = r2;
-                next_acc = tot;
-              } else {
-                extra = r2;
-                extra_acc = tot;
+      // ---- one walk step: push this cell's flow to its receiver(s) ----
+      walked += __popc(busy);
+      if (stats) st_steps += __popc(busy);
+      int extra = -1;  // a second receiver completed by this lane in this step
+      unsigned long long extra_acc = 0;
+      if (walking) {
+        const int cd = code[c];
+        const int n1 = cd & 15;
+        if (cd == kCodeNoData || n1 == 0) {
+          walking = false;
+        } else {
+          const int r1 = c + d8dy(n1) * W + d8dx(n1);
+          int next = -1;
+          unsigned long long next_acc = 0;
+          if (cd & kCodeTwo) {
+            const int n2 = nwrap(n1 + 1);
+            const int r2 = c + d8dy(n2) * W + d8dx(n2);
+            float p1, p2;
+            tarboton_props(rmaxArr[c], &p1, &p2);
+            const double ad = (double)acc;
+            const unsigned long long v1 = p1 > 0 ? (unsigned long long)((double)p1 * ad + 0.5) : 0ull;
+            const unsigned long long v2 = p2 > 0 ? (unsigned long long)((double)p2 * ad + 0.5) : 0ull;
+            if (p1 > 0) {
+              const unsigned long long old = atomicAdd(word + r1, v1 - kPkOne);
+              if ((old >> 56) == 1ull) {
+                next = r1;
+                next_acc = (old & kPkVal) + v1;
               }
             }
-          }
-        } else {
-          const unsigned long long old = atomicAdd(word + r1, acc - kPkOne);
-          if ((old >> 56) == 1ull) {
-            next = r1;
-            next_acc = (old & kPkVal) + acc;
-          }
-        }
-        if (next >= 0) {
-          word[next] = (unsigned long long)__double_as_longlong(fx_to_double(next_acc));
-          c = next;
-          acc = next_acc;
-        } else {
-          walking = false;
-        }
-        if (extra >= 0) word[extra] = (unsigned long long)__double_as_longlong(fx_to_double(extra_acc));
-      }
-    }
-    // ---- hand-overs: to the warp's ring while it is short, to everybody beyond that ----
-    {
-      const unsigned pb = __ballot_sync(full, extra >= 0);
-      if (pb) {
-        const int k = __popc(pb & lt), np = __popc(pb);
-        const int local = count >= share_above ? 0 : (share_above - count < np ? share_above - count : np);
-        int gbase = 0;
-        if (np > local) {
-          if (lane == 0) gbase = atomicAdd(&sh->tail, np - local);
-          gbase = __shfl_sync(full, gbase, 0);
-        }
-        if (extra >= 0) {
-          if (k < local) {
-            const int slot = (head + count + k) & (kLaneQueueD - 1);
-            q[slot] = extra;
-            qa[slot] = extra_acc;
+            if (p2 > 0) {
+              const unsigned long long old = atomicAdd(word + r2, v2 - kPkOne);
+              if ((old >> 56) == 1ull) {
+                const unsigned long long tot = (old & kPkVal) + v2;
+                if (next < 0) {
+                  next = r2;
+                  next_acc = tot;
+                } else {
+                  extra = r2;
+                  extra_acc = tot;
+                }
+              }
+            }
           } else {
-            __threadfence();  // the cell's final value before its ticket
-            *reinterpret_cast<volatile int *>(gq + gbase + (k - local)) = extra + 1;
+            const unsigned long long old = atomicAdd(word + r1, acc - kPkOne);
+            if ((old >> 56) == 1ull) {
+              next = r1;
+              next_acc = (old & kPkVal) + acc;
+            }
           }
+          if (next >= 0) {
+            word[next] = (unsigned long long)__double_as_longlong(fx_to_double(next_acc));
+            c = next;
+            acc = next_acc;
+          } else {
+            walking = false;
+          }
+          if (extra >= 0) word[extra] = (unsigned long long)__double_as_longlong(fx_to_double(extra_acc));
         }
-        count += local;
-        if (stats) {
-          st_glob += np - local;
-          st_loc += local;
+      }
+      // ---- hand-overs: to the warp's ring; what the ring cannot take goes straight to the list of the next phase ----
+      {
+        const unsigned pb = __ballot_sync(full, extra >= 0);
+        if (pb) {
+          const int k = __popc(pb & lt), np = __popc(pb);
+          const int room = kLaneQueueD - 32 - count;
+          const int local = np < room ? np : (room > 0 ? room : 0);
+          unsigned gbase = 0;
+          if (np > local) {
+            if (lane == 0) gbase = atomicAdd(&sh->list_tail, (unsigned)(np - local));
+            gbase = __shfl_sync(full, gbase, 0);
+          }
+          if (extra >= 0) {
+            if (k < local) {
+              const int slot = (head + count + k) & (kLaneQueueD - 1);
+              q[slot] = extra;
+              qa[slot] = extra_acc;
+            } else {
+              list[(gbase + (unsigned)(k - local)) % cap] = extra;
+            }
+          }
+          count += local;
+          if (stats) {
+            st_list += np - local;
+            st_loc += local;
+          }
         }
       }
     }
-    (void)pend_acc;
+    // ---- end of the phase for this warp: everything it holds goes to the list ----
+    {
+      const unsigned wb = __ballot_sync(full, walking);
+      const int total = count + __popc(wb);
+      if (total) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&sh->list_tail, (unsigned)total);
+        base = __shfl_sync(full, base, 0);
+        for (int j = lane; j < count; j += 32) list[(base + (unsigned)j) % cap] = q[(head + j) & (kLaneQueueD - 1)];
+        if (walking) list[(base + (unsigned)(count + __popc(wb & lt))) % cap] = c;
+        if (stats) st_list += total;
+      }
+      if (lane == 0) {
+        if (walked) atomicAdd(&sh->done, walked);
+        atomicAdd(&sh->n_waiting, 1);
+      }
+      walked = 0;
+      count = 0;
+      head = 0;
+      walking = false;
+      __threadfence();
+    }
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned hd = sh->list_head;
+      const unsigned ce = sh->cons_end, tl = sh->list_tail;
+      if ((int)(hd - ce) > 0) hd = ce;  // claims past the end of the last portion
+      const unsigned left = tl - hd;
+      int qv = (int)((left + (unsigned)n_warps - 1u) / (unsigned)n_warps);
+      sh->list_head = hd;
+      sh->cons_end = tl;
+      sh->quota = qv < 1 ? 1 : (qv > 32 ? 32 : qv);
+      sh->n_waiting = 0;
+      sh->finished = left == 0 ? 1 : 0;
+      sh->phases = phase + 1;
+      __threadfence();
+    }
+    grid.sync();
+    phase++;
+    if (*reinterpret_cast<volatile int *>(&sh->finished)) break;
+    quota = *reinterpret_cast<volatile int *>(&sh->quota);
+    cons_end = *reinterpret_cast<volatile unsigned *>(&sh->cons_end);
+    list_dry = false;
   }
   if (stats && lane == 0) {
-    const unsigned long long t_end = global_ns();
     atomicAdd(stats + 0, st_iters);
-    atomicAdd(stats + 1, st_dry);
     atomicAdd(stats + 2, st_steps);
     atomicMax(stats + 3, st_iters);
     atomicAdd(stats + 4, 1ull);
-    atomicAdd(stats + 5, st_polls);
     atomicAdd(stats + 6, st_got);
-    atomicAdd(stats + 7, st_glob);
+    atomicAdd(stats + 7, st_list);
     atomicAdd(stats + 8, st_loc);
-    atomicMax(stats + 9, st_iters - st_dry);
-    // when did this warp finish its source scan / leave?  log2 bins of microseconds since it started
-    auto bin = [](unsigned long long ns) {
-      const unsigned long long us = ns / 1000ull + 1ull;
-      const int b = 63 - __clzll((long long)us);
-      return b > 23 ? 23 : b;
-    };
-    atomicAdd(stats + 16 + bin((t_scan_end ? t_scan_end : t_end) - t_start), 1ull);
-    atomicAdd(stats + 40 + bin(t_end - t_start), 1ull);
   }
 }
 
@@ -1433,7 +1435,8 @@ void launch_walk_packed(const uint8_t *code, unsigned long long *word, int W, in
     long long blocks = (long long)c.num_sms * per_sm;
     const long long need = ((long long)ncells + kLaneChunk - 1) / kLaneChunk;  // no more warps than chunks
     if (blocks * 8 > need) blocks = (need + 7) / 8;
-    const int in_code = src_in_code && (ncells & 3) == 0 && ((uintptr_t)code & 3) == 0 ? 1 : 0;
+    // accum_walk_scan: 0 scan the 8 B words for sources, 1 (default) scan the flagged code bytes and prefetch the words, 2 no prefetch
+    const int in_code = src_in_code && c.params.accum_walk_scan && (ncells & 3) == 0 && ((uintptr_t)code & 3) == 0 ? (int)c.params.accum_walk_scan : 0;
     accum_walk_packed_lanes_kernel<BAND><<<(unsigned)blocks, 256, 0, c.stream>>>(code, word, W, ncells, frontier, ghost_lo_end,
                                                                                ghost_hi_start, cur, in_code);
     RDB_CK(cudaGetLastError());
@@ -1557,64 +1560,53 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     deps_gather_packed_dinf_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, w, h);
     RDB_CK(cudaGetLastError());
     count_launch();
-    DevBuf<int> gq(n);
-    RDB_CK(cudaMemsetAsync(gq.p, 0, n * sizeof(int), c.stream));
+    DevBuf<int> list(n);  // the hand-over list (a ring: at most one entry per ready cell is alive)
     int per_sm = 0;
     RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_dinf_lanes_kernel, 256, 0));
     if (per_sm < 1) per_sm = 1;
     DevBuf<unsigned long long> dstats;
     KernelTimer kt;
-    // every block has to be resident: warps wait for each other's hand-overs
+    // every block has to be resident: the phases meet at grid barriers (a cooperative launch refuses a grid that is not)
     long long nb = (long long)c.num_sms * per_sm;
     const long long need = ((long long)n + kLaneChunk - 1) / kLaneChunk;
     if (nb * 8 > need) nb = (need + 7) / 8;
     {
-      // a cooperative launch: it refuses a grid that cannot be resident at once instead of letting warps wait for blocks
-      // that never start
       const uint8_t *a_code = code.p;
       const float *a_rmax = rmax.p;
       int a_w = w, a_n = (int)n;
-      int *a_gq = gq.p;
+      int *a_list = list.p;
+      unsigned a_cap = (unsigned)n;
       DinfShare *a_sh = share.p;
-      long long a_spin = 4000000;  // ~ 30 s of 8 us naps
-      int a_share = (int)(c.params.accum_dinf_share >= 0 ? c.params.accum_dinf_share : 64);
-      if (a_share > kLaneQueueD - 96) a_share = kLaneQueueD - 96;
-      int a_claim = (int)c.params.accum_dinf_claim;
+      int a_excess = (int)(c.params.accum_dinf_share >= 0 ? c.params.accum_dinf_share : 16);
+      if (a_excess > kLaneQueueD - 96) a_excess = kLaneQueueD - 96;
       if (c.params.accum_dinf_stats) {
-        dstats.alloc(64);
-        RDB_CK(cudaMemsetAsync(dstats.p, 0, 64 * sizeof(unsigned long long), c.stream));
+        dstats.alloc(16);
+        RDB_CK(cudaMemsetAsync(dstats.p, 0, 16 * sizeof(unsigned long long), c.stream));
       }
       unsigned long long *a_stats = dstats.p;
-      void *args[] = {(void *)&a_code, (void *)&a_rmax, (void *)&word, (void *)&a_w, (void *)&a_n, (void *)&a_gq, (void *)&a_sh,
-                      (void *)&a_spin, (void *)&a_share, (void *)&a_claim, (void *)&a_stats};
+      void *args[] = {(void *)&a_code, (void *)&a_rmax, (void *)&word, (void *)&a_w, (void *)&a_n, (void *)&a_list, (void *)&a_cap,
+                      (void *)&a_sh, (void *)&a_excess, (void *)&a_stats};
       RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_walk_dinf_lanes_kernel, dim3((unsigned)nb), dim3(256), args, 0, c.stream));
     }
     RDB_CK(cudaGetLastError());
     count_launch(2);
     DinfShare *hs = reinterpret_cast<DinfShare *>(c.pinned);
     RDB_CK(cudaMemcpyAsync(hs, share.p, sizeof(DinfShare), cudaMemcpyDeviceToHost, c.stream));
-    const int rounds = 1;
     kt.stop_async();
     RDB_CK(cudaStreamSynchronize(c.stream));
     c.stats.ms_main_kernel += kt.ms();
-    c.stats.accum_rounds = rounds;
+    c.stats.accum_rounds = hs->phases;
     if (dstats.p) {
-      unsigned long long hsx[64];
+      unsigned long long hsx[16];
       RDB_CK(cudaMemcpy(hsx, dstats.p, sizeof(hsx), cudaMemcpyDeviceToHost));
       fprintf(stderr,
-              "[dinf walk] %.2f ms, %llu warps: iterations sum %llu max %llu (busiest warp walked in %llu), dry %llu, lane-steps %llu "
-              "(%.1f %% of the lanes of non-dry iterations), polls %llu, collected %llu, handed over: %llu global %llu local\n",
-              kt.ms(), hsx[4], hsx[0], hsx[3], hsx[9], hsx[1], hsx[2],
-              100.0 * (double)hsx[2] / (32.0 * (double)(hsx[0] - hsx[1] ? hsx[0] - hsx[1] : 1)), hsx[5], hsx[6], hsx[7], hsx[8]);
-      fprintf(stderr, "[dinf walk] warps by log2(us) until their source scan ended:");
-      for (int b = 0; b < 24; b++) fprintf(stderr, " %llu", hsx[16 + b]);
-      fprintf(stderr, "\n[dinf walk] warps by log2(us) until they left:              ");
-      for (int b = 0; b < 24; b++) fprintf(stderr, " %llu", hsx[40 + b]);
-      fprintf(stderr, "\n");
+              "[dinf walk] %.2f ms, %llu warps, %d phases: iterations sum %llu max %llu, lane-steps %llu (%.1f %% of the lanes), "
+              "hand-overs %llu in the rings, %llu through the list (%llu claimed back)\n",
+              kt.ms(), hsx[4], hs->phases, hsx[0], hsx[3], hsx[2], 100.0 * (double)hsx[2] / (32.0 * (double)(hsx[0] ? hsx[0] : 1)),
+              hsx[8], hsx[7], hsx[6]);
     }
-    if (hs->abort_flag || hs->done != hs->n_data)
-      fail("D-infinity accumulation (packed walk): the work-sharing protocol did not finish (walked %d of %d cells, watchdog %d)",
-           hs->done, hs->n_data, hs->abort_flag);
+    if (hs->done != hs->n_data)
+      fail("D-infinity accumulation (packed walk): %d of %d cells walked after %d phases", hs->done, hs->n_data, hs->phases);
     return;
     }
   }

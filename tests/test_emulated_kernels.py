@@ -254,15 +254,13 @@ def test_d4_fill(emulated, gp, checker, shape, seed, q):
     gp.test_d4_fill_vs_oracle(checker, shape, seed, q)
 
 
-@pytest.mark.parametrize("claim", [0, 1])
 @pytest.mark.parametrize("share", [0, 3, -1])
-def test_packed_dinf_work_sharing(emulated, gp, checker, share, claim):
-    """accum_dinf_packed: fixed-point D-infinity walk; share = ring length above which hand-overs go to the global ticket
-    queue (0: every hand-over crosses warps).  Re-run with concurrent blocks by test_cooperative_kernels_with_several_blocks."""
+def test_packed_dinf_work_sharing(emulated, gp, checker, share):
+    """accum_dinf_packed: fixed-point D-infinity walk in phases; share = ring entries above which a warp asks for a
+    rebalancing phase once a quarter of the warps wait at the barrier (0: any queued cell does).  Re-run with concurrent blocks by test_cooperative_kernels_with_several_blocks."""
     import richdem_b200 as rd
     _lib.set_param("accum_dinf_packed", 1)
     _lib.set_param("accum_dinf_share", share)
-    _lib.set_param("accum_dinf_claim", claim)  # 1: starving warps claim only tickets that exist (CAS), no more than they can use
     dem = checker.resolve_flats(checker.fill_depressions(oracle.fbm_terrain(420, 520, seed=71, quantum=0.5)), gp.ND)
     dem[200:230, 100:160] = gp.ND
     got = np.asarray(rd.FlowAccumulation(gp.R(dem), "Dinf"))

@@ -38,24 +38,33 @@ def sync():
         torch.cuda.synchronize()
 
 
-for rep in range(3):
-    if rep == 2:
-        _lib.set_param("fill_trace", 1)
-    w = dem.clone()
-    sync()
-    t = time.perf_counter()
-    filled, xr, st = sharded.fill_band(w, gt, gb, row0=r0 - gt, height=N, return_stats=True)
-    sync()
-    tf = time.perf_counter() - t
-    _lib.set_param("fill_trace", 0)
-    t = time.perf_counter()
-    acc, ar, st2 = sharded.fa_band(filled, gt, gb, -9999.0, dinf=False, return_stats=True)
-    sync()
-    ta = time.perf_counter() - t
+# further arguments: configurations of rdb200_set_param switches ("fill_vcycle=16 fill_band_multigrid=32"), each run in turn
+variants = [a for a in sys.argv[2:] if a != "dinf"] or [""]
+for variant in variants:
+    _lib.reset_params()
+    for kv in variant.split():
+        _lib.set_param(kv.split("=")[0], int(kv.split("=")[1]))
     if rank == 0:
-        print(f"rep {rep}: world={world} fill {tf * 1e3:.2f} ms ({xr} cycles, sweep {st['ms_main_kernel']:.2f} ms, "
-              f"{st['fill_rounds']} live rounds, {st['fill_tile_visits']} visits)  fa_d8 {ta * 1e3:.2f} ms ({ar} rounds)", flush=True)
-if len(sys.argv) > 2 and sys.argv[2] == "dinf":
+        print(f"== variant [{variant or 'defaults'}]", flush=True)
+    for rep in range(3):
+        if rep == 2:
+            _lib.set_param("fill_trace", 1)
+        w = dem.clone()
+        sync()
+        t = time.perf_counter()
+        filled, xr, st = sharded.fill_band(w, gt, gb, row0=r0 - gt, height=N, return_stats=True)
+        sync()
+        tf = time.perf_counter() - t
+        _lib.set_param("fill_trace", 0)
+        t = time.perf_counter()
+        acc, ar, st2 = sharded.fa_band(filled, gt, gb, -9999.0, dinf=False, return_stats=True)
+        sync()
+        ta = time.perf_counter() - t
+        if rank == 0:
+            print(f"rep {rep}: world={world} fill {tf * 1e3:.2f} ms ({xr} cycles, sweep {st['ms_main_kernel']:.2f} ms, "
+                  f"{st['fill_rounds']} live rounds, {st['fill_tile_visits']} visits)  fa_d8 {ta * 1e3:.2f} ms ({ar} rounds)", flush=True)
+_lib.reset_params()
+if "dinf" in sys.argv[2:]:
     t = time.perf_counter()
     acc, ar = sharded.fa_band(filled, gt, gb, -9999.0, dinf=True)
     sync()

@@ -28,12 +28,15 @@ step fill_variants 400 python tools/fill_profile.py "$N" "" "fill_vcycle=4" "fil
 TAILN=60 step band_profile 300 python tools/band_profile.py "$N"
 step flats_profile 240 env RDB200_PROFILE=1 python tools/flats_profile.py "$N"
 TAILN=40 step dinf_engines 300 python tools/dinf_profile.py "$N" "accum_dinf_packed=0" "accum_dinf_packed=1 accum_dinf_stats=1" \
-  "accum_dinf_packed=1 accum_dinf_claim=1 accum_dinf_stats=1" "accum_dinf_packed=1 accum_dinf_claim=1 accum_dinf_share=8 accum_dinf_stats=1" \
-  "accum_dinf_packed=1 accum_dinf_claim=1 accum_dinf_share=0" "accum_dinf_packed=1 accum_dinf_claim=1 accum_dinf_share=128"
+  "accum_dinf_packed=1 accum_dinf_share=4 accum_dinf_stats=1" "accum_dinf_packed=1 accum_dinf_share=48 accum_dinf_stats=1"
 TAILN=3 step bench 600 python bench.py --steps 5 --warmup 3
 grep -a '"metric"' "$OUT/bench.log" | tail -1 > "$OUT/bench.json"
 step ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file "$OUT/launches.csv" \
   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-configs --no-verify
+if [ -n "$NCU_DINF" ]; then
+  step ncu_dinf 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_dinf.csv" \
+    python tools/dinf_profile.py "$N" "accum_dinf_packed=1"
+fi
 if [ -n "$NCU_FULL" ]; then
   # full-set captures of the dominant kernels (one replayed launch each; read here with `ncu -i ... --page raw --csv`):
   # the heaviest sweep launch is the first round of the 32768^2 level (after the coarse levels' ~80 small launches)

@@ -24,14 +24,10 @@ if [ -z "$SKIP_CHECK" ]; then
   run check 400 "RDB_BAND_MULTIGRID=8" tools/mgpu_check.py
 fi
 if [ -z "$SKIP_TRACE" ]; then
-  j=0
-  IFS=';' read -ra TV <<< "${TRACE_VARIANTS:-;}"
-  if [ ${#TV[@]} -eq 0 ]; then TV=(""); fi
-  for v in "${TV[@]}"; do
-    run "band_profile_$j" 300 "$v" tools/band_profile.py 32768
-    grep -a "trace\] rank 0\|^rep" "$OUT/band_profile_$j.log" | tail -n ${TRACE_LINES:-70} | tee -a "$OUT/summary.txt"
-    j=$((j + 1))
-  done
+  # TRACE_VARIANTS: ';'-separated configurations of rdb200_set_param switches, all timed inside one torchrun
+  IFS=';' read -ra TV <<< "${TRACE_VARIANTS:-}"
+  run band_profile 400 "" tools/band_profile.py 32768 "${TV[@]}"
+  grep -a "trace\] rank 0\|^rep\|^== variant" "$OUT/band_profile.log" | tail -n ${TRACE_LINES:-70} | tee -a "$OUT/summary.txt"
 fi
 i=0
 for e in "$@"; do
