@@ -12,7 +12,8 @@ L = _lib.lib()
 _lib.init(0)
 _lib.use_torch_stream()
 N = int(sys.argv[1])
-configs = sys.argv[2:] or [""]
+D8 = len(sys.argv) > 2 and sys.argv[2] == "d8"  # time FA_D8 instead (python tools/dinf_profile.py 32768 d8 "accum_walk_scan=0" ...)
+configs = sys.argv[(3 if D8 else 2):] or [""]
 d = torch.empty((N, N), dtype=torch.float32, device="cuda")
 _lib.check(L.rdb200_dev_generate_fbm_f32(d.data_ptr(), N, N, 0, 42, 12, 0.0))
 _lib.check(L.rdb200_dev_fill_depressions_d8_f32(d.data_ptr(), N, N))
@@ -27,13 +28,14 @@ for name, dem in (("filled", d), ("resolved", r)):
             _lib.set_param(kv.split("=")[0], int(kv.split("=")[1]))
         times = []
         for rep in range(2):
-            _lib.check(L.rdb200_dev_fa_tarboton_f32_f64(dem.data_ptr(), acc.data_ptr(), N, N, -9999.0, 1))
+            fa = L.rdb200_dev_fa_d8_f32_f64 if D8 else L.rdb200_dev_fa_tarboton_f32_f64
+            _lib.check(fa(dem.data_ptr(), acc.data_ptr(), N, N, -9999.0, 1))
             times.append(_lib.stats()["ms_total"])
         if ref is None:
             ref = acc.clone()
             err = 0.0
         else:
             err = float(((acc - ref).abs() / ref.abs().clamp(min=1.0)).max())
-        print(f"N={N} {name:8s} [{cfg or 'defaults'}] fa_dinf {min(times):8.1f} ms (runs {', '.join(f'{t:.1f}' for t in times)}) "
+        print(f"N={N} {name:8s} [{cfg or 'defaults'}] {'fa_d8' if D8 else 'fa_dinf'} {min(times):8.1f} ms (runs {', '.join(f'{t:.1f}' for t in times)}) "
               f"rounds={_lib.stats()['accum_rounds']} max rel diff vs first {err:.2e}", flush=True)
 _lib.reset_params()

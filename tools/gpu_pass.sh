@@ -29,6 +29,7 @@ TAILN=60 step band_profile 300 python tools/band_profile.py "$N"
 step flats_profile 240 env RDB200_PROFILE=1 python tools/flats_profile.py "$N"
 TAILN=40 step dinf_engines 300 python tools/dinf_profile.py "$N" "accum_dinf_packed=0" "accum_dinf_packed=1 accum_dinf_stats=1" \
   "accum_dinf_packed=1 accum_dinf_share=4 accum_dinf_stats=1" "accum_dinf_packed=1 accum_dinf_share=48 accum_dinf_stats=1"
+step d8_scan 200 python tools/dinf_profile.py "$N" d8 "accum_walk_scan=1" "accum_walk_scan=0" "accum_walk_scan=2"
 TAILN=3 step bench 600 python bench.py --steps 5 --warmup 3
 grep -a '"metric"' "$OUT/bench.log" | tail -1 > "$OUT/bench.json"
 step ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file "$OUT/launches.csv" \
