@@ -163,13 +163,41 @@ def stats() -> dict:
     return s.as_dict()
 
 
+_param_values: dict = {}  # what this process set through set_param (the C ABI has no getter)
+
+
 def set_param(name: str, value: int) -> None:
     check(lib().rdb200_set_param(name.encode(), int(value)))
+    if name == "reset_defaults":
+        _param_values.clear()
+    elif name != "trim_workspace":
+        _param_values[name] = int(value)
 
 
 def reset_params() -> None:
     """Every rdb200_set_param switch back to its shipped default."""
     set_param("reset_defaults", 1)
+
+
+class scoped_param:
+    """`with scoped_param("fill_band_rounds", 64): ...` -- a switch for the duration of a block, then back to what this
+    process had set before (or to `default`, the library's own default, if it never set it)."""
+
+    def __init__(self, name: str, value: int, default: int = 0):
+        self.name, self.value, self.default = name, int(value), int(default)
+
+    def __enter__(self):
+        self.previous = _param_values.get(self.name)
+        set_param(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        if self.previous is None:
+            set_param(self.name, self.default)
+            _param_values.pop(self.name, None)
+        else:
+            set_param(self.name, self.previous)
+        return False
 
 
 def init(device: int = 0) -> None:

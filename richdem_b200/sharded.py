@@ -299,11 +299,18 @@ def fill_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, solver_cls=None
         from . import _lib
         if band_rounds is None:
             band_rounds = int(os.environ.get("RDB_BAND_ROUNDS", "64")) if world > 1 else 0
-        _lib.set_param("fill_band_rounds", band_rounds)
-        for knob in ("fill_ordered", "fill_rounds_per_sync"):  # experiment hooks
-            v = os.environ.get("RDB_" + knob.upper())
-            if v is not None:
-                _lib.set_param(knob, int(v))
+        # the round leash is a process-wide switch of the library: it is put back when this call is over
+        with _lib.scoped_param("fill_band_rounds", band_rounds):
+            return _fill_band_protocol(local_dem, g_top, g_bot, CudaBandSolver, group, max_rounds, return_stats, multigrid, row0,
+                                       height, vcycle, rank, world)
+    return _fill_band_protocol(local_dem, g_top, g_bot, solver_cls, group, max_rounds, return_stats, multigrid, row0, height, vcycle,
+                               rank, world)
+
+
+def _fill_band_protocol(local_dem, g_top, g_bot, solver_cls, group, max_rounds, return_stats, multigrid, row0, height, vcycle, rank,
+                        world):
+    """The Python band protocol behind :func:`fill_band` (RDB_BAND_DRIVER=python and the CPU tests' solvers).  The ghost rows of
+    ``local_dem`` are overwritten in place (with +inf or their lifted levels)."""
     h, w = local_dem.shape
     if multigrid >= 2:
         assert height > 0, "multigrid start needs the global geometry (row0, height)"
@@ -699,8 +706,8 @@ def resolve_flats_band(local_dem: "torch.Tensor", g_top: int, g_bot: int, nodata
     for away in (True, False):
         solver = F.gradient_begin(away)
         from . import _lib
-        _lib.set_param("fill_band_rounds", 64 if world > 1 else 0)
-        _relax_band(solver, g_top, g_bot, rank, world, group)
+        with _lib.scoped_param("fill_band_rounds", 64 if world > 1 else 0):  # (put back afterwards: a process-wide switch)
+            _relax_band(solver, g_top, g_bot, rank, world, group)
         F.gradient_end(away, solver)
         if away:
             iters += merge_until_stable(F.height_payload, F.merge_heights)
