@@ -918,7 +918,8 @@ template <bool BAND>
 __global__ void __launch_bounds__(256) accum_walk_packed_lanes_kernel(const uint8_t *__restrict__ code,
                                                                        unsigned long long *word, int W, int ncells,
                                                                        const int *__restrict__ frontier, int ghost_lo_end,
-                                                                       int ghost_hi_start, int *cursor, int src_in_code) {
+                                                                       int ghost_hi_start, int *cursor, int src_in_code,
+                                                                       int ahead) {
   __shared__ int sQ[8][kLaneQueue];
   __shared__ uint8_t sQc[8][kLaneQueue];
   const unsigned full = 0xffffffffu;
@@ -935,8 +936,10 @@ __global__ void __launch_bounds__(256) accum_walk_packed_lanes_kernel(const uint
   int c = 0, cdraw = 0;
   unsigned long long acc = 0;
   for (;;) {
-    // ---- refill: keep at least a warp's worth of sources queued while candidates last ----
-    while (count <= kLaneQueue - 32 * per_lane) {
+    // ---- refill: keep `ahead` sources queued while candidates last -- no more: a source waits in the queue while the
+    // words its walk will touch, fetched around the time it was scanned, sit in L2; with every warp a full queue ahead of
+    // its walks those lines are gone again when they are needed ----
+    while (count < ahead) {
       if (pos >= end) {
         if (!more) break;
         int b = 0;
@@ -1162,11 +1165,12 @@ __global__ void __launch_bounds__(256) dinf_count_data_kernel(const uint8_t *__r
   }
 }
 
-__global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_t *__restrict__ code,
+template <bool STATS>
+__global__ void __launch_bounds__(256, 6) accum_walk_dinf_lanes_kernel(const uint8_t *__restrict__ code,
                                                                      const float *__restrict__ rmaxArr,
                                                                      unsigned long long *word, int W, int ncells, int *list,
                                                                      unsigned cap, DinfShare *sh, int excess_above,
-                                                                     unsigned long long *stats) {
+                                                                     int wait_div, unsigned long long *stats) {
   cg::grid_group grid = cg::this_grid();
   __shared__ int sQ[8][kLaneQueueD];
   __shared__ unsigned long long sQa[8][kLaneQueueD];
@@ -1192,7 +1196,7 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
     unsigned iter = 0;
     for (;;) {  // iterations of this phase
       iter++;
-      if (stats) st_iters++;
+      if (STATS) st_iters++;
       // ---- sources: refill from the scan only when the lanes would otherwise starve ----
       while (count < 32 && (more || pos < end)) {
         if (pos >= end) {
@@ -1236,7 +1240,7 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
             qa[slot] = (unsigned long long)(__longlong_as_double((long long)__ldcg(word + cell)) * 16777216.0 + 0.5);
           }
           count += k;
-          if (stats) st_got += k;
+          if (STATS) st_got += k;
         }
       }
       __syncwarp();
@@ -1267,7 +1271,7 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
         if (lane == 0) {
           st = *reinterpret_cast<volatile int *>(&sh->stop) > phase ? 1 : 0;
           if (!st && count >= excess_above && (iter >= 64u || count >= kLaneQueueD - 64) &&
-              *reinterpret_cast<volatile int *>(&sh->n_waiting) * 4 >= n_warps) {
+              *reinterpret_cast<volatile int *>(&sh->n_waiting) * wait_div >= n_warps) {
             atomicMax(&sh->stop, phase + 1);
             st = 1;
           }
@@ -1277,7 +1281,7 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
       }
       // ---- one walk step: push this cell's flow to its receiver(s) ----
       walked += __popc(busy);
-      if (stats) st_steps += __popc(busy);
+      if (STATS) st_steps += __popc(busy);
       int extra = -1;  // a second receiver completed by this lane in this step
       unsigned long long extra_acc = 0;
       if (walking) {
@@ -1356,7 +1360,7 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
             }
           }
           count += local;
-          if (stats) {
+          if (STATS) {
             st_list += np - local;
             st_loc += local;
           }
@@ -1373,7 +1377,7 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
         base = __shfl_sync(full, base, 0);
         for (int j = lane; j < count; j += 32) list[(base + (unsigned)j) % cap] = q[(head + j) & (kLaneQueueD - 1)];
         if (walking) list[(base + (unsigned)(count + __popc(wb & lt))) % cap] = c;
-        if (stats) st_list += total;
+        if (STATS) st_list += total;
       }
       if (lane == 0) {
         if (walked) atomicAdd(&sh->done, walked);
@@ -1407,7 +1411,7 @@ __global__ void __launch_bounds__(256) accum_walk_dinf_lanes_kernel(const uint8_
     cons_end = *reinterpret_cast<volatile unsigned *>(&sh->cons_end);
     list_dry = false;
   }
-  if (stats && lane == 0) {
+  if (STATS && lane == 0) {
     atomicAdd(stats + 0, st_iters);
     atomicAdd(stats + 2, st_steps);
     atomicMax(stats + 3, st_iters);
@@ -1437,8 +1441,11 @@ void launch_walk_packed(const uint8_t *code, unsigned long long *word, int W, in
     if (blocks * 8 > need) blocks = (need + 7) / 8;
     // accum_walk_scan: 0 scan the 8 B words for sources, 1 (default) scan the flagged code bytes and prefetch the words, 2 no prefetch
     const int in_code = src_in_code && c.params.accum_walk_scan && (ncells & 3) == 0 && ((uintptr_t)code & 3) == 0 ? (int)c.params.accum_walk_scan : 0;
+    int ahead = (int)(c.params.accum_walk_ahead > 0 ? c.params.accum_walk_ahead : 64);
+    if (ahead > kLaneQueue - 128) ahead = kLaneQueue - 128;  // one refill step adds up to 128 cells
+    if (ahead < 32) ahead = 32;
     accum_walk_packed_lanes_kernel<BAND><<<(unsigned)blocks, 256, 0, c.stream>>>(code, word, W, ncells, frontier, ghost_lo_end,
-                                                                               ghost_hi_start, cur, in_code);
+                                                                               ghost_hi_start, cur, in_code, ahead);
     RDB_CK(cudaGetLastError());
     if (!cursor_buf) RDB_CK(cudaStreamSynchronize(c.stream));  // `cursor` goes out of scope
   } else {
@@ -1562,7 +1569,9 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     count_launch();
     DevBuf<int> list(n);  // the hand-over list (a ring: at most one entry per ready cell is alive)
     int per_sm = 0;
-    RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_dinf_lanes_kernel, 256, 0));
+    const bool with_stats = c.params.accum_dinf_stats != 0;
+    RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_dinf_lanes_kernel<false>, 256, 0));
+    if (with_stats) RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_dinf_lanes_kernel<true>, 256, 0));
     if (per_sm < 1) per_sm = 1;
     DevBuf<unsigned long long> dstats;
     KernelTimer kt;
@@ -1577,7 +1586,8 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
       int *a_list = list.p;
       unsigned a_cap = (unsigned)n;
       DinfShare *a_sh = share.p;
-      int a_excess = (int)(c.params.accum_dinf_share >= 0 ? c.params.accum_dinf_share : 16);
+      int a_excess = (int)(c.params.accum_dinf_share >= 0 ? c.params.accum_dinf_share : 4);
+      int a_wait = (int)(c.params.accum_dinf_wait > 0 ? c.params.accum_dinf_wait : 4);  // 1 / this share of the warps waiting
       if (a_excess > kLaneQueueD - 96) a_excess = kLaneQueueD - 96;
       if (c.params.accum_dinf_stats) {
         dstats.alloc(16);
@@ -1585,8 +1595,11 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
       }
       unsigned long long *a_stats = dstats.p;
       void *args[] = {(void *)&a_code, (void *)&a_rmax, (void *)&word, (void *)&a_w, (void *)&a_n, (void *)&a_list, (void *)&a_cap,
-                      (void *)&a_sh, (void *)&a_excess, (void *)&a_stats};
-      RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_walk_dinf_lanes_kernel, dim3((unsigned)nb), dim3(256), args, 0, c.stream));
+                      (void *)&a_sh, (void *)&a_excess, (void *)&a_wait, (void *)&a_stats};
+      if (with_stats)
+        RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_walk_dinf_lanes_kernel<true>, dim3((unsigned)nb), dim3(256), args, 0, c.stream));
+      else
+        RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_walk_dinf_lanes_kernel<false>, dim3((unsigned)nb), dim3(256), args, 0, c.stream));
     }
     RDB_CK(cudaGetLastError());
     count_launch(2);

@@ -13,7 +13,7 @@ _lib.init(0)
 _lib.use_torch_stream()
 N = int(sys.argv[1])
 D8 = len(sys.argv) > 2 and sys.argv[2] == "d8"  # time FA_D8 instead (python tools/dinf_profile.py 32768 d8 "accum_walk_scan=0" ...)
-configs = sys.argv[(3 if D8 else 2):] or [""]
+configs = [c.strip() for a in sys.argv[(3 if D8 else 2):] for c in a.split(";")] or [""]  # (";" separates configurations too)
 d = torch.empty((N, N), dtype=torch.float32, device="cuda")
 _lib.check(L.rdb200_dev_generate_fbm_f32(d.data_ptr(), N, N, 0, 42, 12, 0.0))
 _lib.check(L.rdb200_dev_fill_depressions_d8_f32(d.data_ptr(), N, N))

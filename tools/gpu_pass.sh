@@ -23,16 +23,17 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.acti
 if [ -z "$SKIP_TESTS" ]; then
   step pytest_gpu 900 python -m pytest tests -m gpu -x -q
 fi
+if [ -z "$LITE" ]; then
 TAILN=40 step fill_trace 300 python tools/fill_profile.py "$N" "fill_trace=1"
 step fill_variants 400 python tools/fill_profile.py "$N" "" "fill_vcycle=4" "fill_vcycle=12"
 TAILN=60 step band_profile 300 python tools/band_profile.py "$N"
 step flats_profile 240 env RDB200_PROFILE=1 python tools/flats_profile.py "$N"
-TAILN=40 step dinf_engines 300 python tools/dinf_profile.py "$N" "accum_dinf_packed=0" "accum_dinf_packed=1 accum_dinf_stats=1" \
-  "accum_dinf_packed=1 accum_dinf_share=4 accum_dinf_stats=1" "accum_dinf_packed=1 accum_dinf_share=48 accum_dinf_stats=1"
-step d8_scan 200 python tools/dinf_profile.py "$N" d8 "accum_walk_scan=1" "accum_walk_scan=0" "accum_walk_scan=2"
+fi
+TAILN=40 step dinf_engines 300 python tools/dinf_profile.py "$N" "${DINF_CONFIGS:-accum_dinf_packed=0;accum_dinf_packed=1 accum_dinf_stats=1}"
+step d8_scan 200 python tools/dinf_profile.py "$N" d8 "${D8_CONFIGS:-;accum_walk_scan=0}"
 TAILN=3 step bench 600 python bench.py --steps 5 --warmup 3
 grep -a '"metric"' "$OUT/bench.log" | tail -1 > "$OUT/bench.json"
-step ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file "$OUT/launches.csv" \
+[ -z "$LITE" ] && step ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file "$OUT/launches.csv" \
   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-configs --no-verify
 if [ -n "$NCU_DINF" ]; then
   step ncu_dinf 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_dinf.csv" \
