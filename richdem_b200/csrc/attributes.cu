@@ -8,6 +8,8 @@
 // 16 rows, carrying the 3x3 neighbourhood's previous two rows in registers.
 #include "common.cuh"
 
+#include <cmath>
+
 namespace rdb {
 
 namespace {
@@ -18,31 +20,41 @@ struct Nbhd {  // reference naming (terrain_attributes.hpp:163-169):  a b c / d 
   double a, b, c, d, e, f, g, h, i;
 };
 
+// A division by a power of two is the multiplication by its (exact) reciprocal -- same correctly rounded result, a
+// fraction of the double-precision instructions.  The 2, 4 and 8 of the formulas always are; a cell length is checked on
+// the host (1 x 1 cells, the geotransform pyrichdem assumes when there is none, are).
+struct CellLen {
+  double len, inv;  // inv = 1 / len when that is exact, else 0
+};
+__device__ __forceinline__ double over(double x, const CellLen &l) {
+  return l.inv != 0.0 ? __dmul_rn(x, l.inv) : __ddiv_rn(x, l.len);
+}
+
 // Horn (1981) gradients, terrain_attributes.hpp:225-227,244-246
-__device__ __forceinline__ void horn(const Nbhd &t, double lx, double ly, double *dzdx, double *dzdy) {
+__device__ __forceinline__ void horn(const Nbhd &t, const CellLen &lx, const CellLen &ly, double *dzdx, double *dzdy) {
   const double right = __dadd_rn(__dadd_rn(t.c, __dmul_rn(2.0, t.f)), t.i);
   const double left = __dadd_rn(__dadd_rn(t.a, __dmul_rn(2.0, t.d)), t.g);
   const double down = __dadd_rn(__dadd_rn(t.g, __dmul_rn(2.0, t.h)), t.i);
   const double up = __dadd_rn(__dadd_rn(t.a, __dmul_rn(2.0, t.b)), t.c);
-  *dzdx = __ddiv_rn(__ddiv_rn(__dsub_rn(right, left), 8.0), lx);
-  *dzdy = __ddiv_rn(__ddiv_rn(__dsub_rn(down, up), 8.0), ly);
+  *dzdx = over(__dmul_rn(__dsub_rn(right, left), 0.125), lx);
+  *dzdy = over(__dmul_rn(__dsub_rn(down, up), 0.125), ly);
 }
 
 struct Curves {  // Zevenbergen & Thorne (1987) coefficients, terrain_attributes.hpp:198-213
   double D, E, F, G, H;
 };
-__device__ __forceinline__ Curves curves(const Nbhd &t, double L) {
+__device__ __forceinline__ Curves curves(const Nbhd &t, const CellLen &L) {
   Curves p;
-  p.D = __ddiv_rn(__ddiv_rn(__dsub_rn(__ddiv_rn(__dadd_rn(t.d, t.f), 2.0), t.e), L), L);
-  p.E = __ddiv_rn(__ddiv_rn(__dsub_rn(__ddiv_rn(__dadd_rn(t.b, t.h), 2.0), t.e), L), L);
-  p.F = __ddiv_rn(__ddiv_rn(__ddiv_rn(__dsub_rn(__dadd_rn(__dadd_rn(-t.a, t.c), t.g), t.i), 4.0), L), L);
-  p.G = __ddiv_rn(__ddiv_rn(__dadd_rn(-t.d, t.f), 2.0), L);
-  p.H = __ddiv_rn(__ddiv_rn(__dsub_rn(t.b, t.h), 2.0), L);
+  p.D = over(over(__dsub_rn(__dmul_rn(__dadd_rn(t.d, t.f), 0.5), t.e), L), L);
+  p.E = over(over(__dsub_rn(__dmul_rn(__dadd_rn(t.b, t.h), 0.5), t.e), L), L);
+  p.F = over(over(__dmul_rn(__dsub_rn(__dadd_rn(__dadd_rn(-t.a, t.c), t.g), t.i), 0.25), L), L);
+  p.G = over(__dmul_rn(__dadd_rn(-t.d, t.f), 0.5), L);
+  p.H = over(__dmul_rn(__dsub_rn(t.b, t.h), 0.5), L);
   return p;
 }
 
 template <int ATTR>
-__device__ __forceinline__ double attribute(const Nbhd &t, double lx, double ly) {
+__device__ __forceinline__ double attribute(const Nbhd &t, const CellLen &lx, const CellLen &ly) {
   constexpr double kPi = 3.14159265358979323846;
   if (ATTR <= RDB200_TA_SLOPE_RADIANS) {
     double dzdx, dzdy;
@@ -76,8 +88,8 @@ __device__ __forceinline__ double attribute(const Nbhd &t, double lx, double ly)
 
 template <int ATTR>
 __global__ void __launch_bounds__(kTW) terrain_attribute_kernel(const float *__restrict__ dem, float *__restrict__ out, int W, int H,
-                                                                float nodata_in, float nodata_out, float zscale, double lx,
-                                                                double ly) {
+                                                                float nodata_in, float nodata_out, float zscale, CellLen lx,
+                                                                CellLen ly) {
   __shared__ float s[kTH + 2][kTW + 2];
   const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
   // window load: cells outside the raster are marked by a flag row/column test at use, their slot is never read
@@ -130,8 +142,16 @@ __global__ void __launch_bounds__(kTW) terrain_attribute_kernel(const float *__r
 }
 
 template <int ATTR>
-void launch(const float *d_dem, float *d_out, int w, int h, float nodata_in, float nodata_out, float zscale, double lx, double ly) {
+void launch(const float *d_dem, float *d_out, int w, int h, float nodata_in, float nodata_out, float zscale, double cell_x, double cell_y) {
   Ctx &c = ctx();
+  auto cell = [](double len) {
+    int e = 0;
+    CellLen l;
+    l.len = len;
+    l.inv = (std::frexp(len, &e) == 0.5 && e > -1000 && e < 1000) ? 1.0 / len : 0.0;  // a power of two: 1 / len is exact
+    return l;
+  };
+  const CellLen lx = cell(cell_x), ly = cell(cell_y);
   const dim3 grd((w + kTW - 1) / kTW, (h + kTH - 1) / kTH);
   terrain_attribute_kernel<ATTR><<<grd, kTW, 0, c.stream>>>(d_dem, d_out, w, h, nodata_in, nodata_out, zscale, lx, ly);
   RDB_CK(cudaGetLastError());

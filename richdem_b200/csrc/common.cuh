@@ -73,7 +73,7 @@ struct Params {
   int64_t flats_tiled = 1;   // flat-resolution gradients by the tile engine (0: one cooperative BFS launch each)
   int64_t accum_dinf_packed = 1;  // unit-weight D-infinity: 0 level-synchronous kernel, 1 packed fixed-point walk in phases, 2 packed only when > 5 % of the cells have no receiver
   int64_t accum_walk_ahead = 0;   // packed D8 walk: sources a warp keeps queued ahead of its lanes (0: 64; 32..128)
-  int64_t accum_walk_scan = 1;    // packed D8 walk, source scan: 0 over the 8 B words, 1 over the flagged code bytes + L2 prefetch of the words, 2 no prefetch
+  int64_t accum_walk_scan = 0;    // packed D8 walk, source scan: 0 over the 8 B words (measured best: 13.1 vs 16.6 ms FA_D8 at 32768^2), 1 over the flagged code bytes + L2 prefetch of the words, 2 without the prefetch
   int64_t accum_dinf_stats = 0;   // packed D-infinity: print what the warps spent their iterations on (diagnostics)
   int64_t accum_dinf_share = -1;  // packed D-infinity: ring entries above which a warp asks for a rebalancing phase once enough warps wait (-1: 4)
   int64_t accum_dinf_wait = 0;    // packed D-infinity: ... once 1 / this share of the warps wait at the barrier (0: 4)
