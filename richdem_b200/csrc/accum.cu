@@ -1059,8 +1059,10 @@ constexpr unsigned long long kFxOne = 1ull << 24;                    // one unit
 constexpr unsigned long long kFxSource = (1ull << 63) | kFxOne;      // no donors, own unit, not started yet
 constexpr int kLaneQueueD = 256;                                      // per-warp ring (power of two)
 
+// (row bands: rows outside [y_lo, y_hi) are ghost rows -- empty parking slots for the flow that leaves the band)
 __global__ void __launch_bounds__(256) deps_gather_packed_dinf_x4_kernel(const uint8_t *__restrict__ code,
-                                                                          unsigned long long *__restrict__ word, int W, int H) {
+                                                                          unsigned long long *__restrict__ word, int W, int H,
+                                                                          int y_lo, int y_hi) {
   const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (x4 >= W) return;
   for (int y = blockIdx.y; y < H; y += gridDim.y) {
@@ -1084,6 +1086,10 @@ __global__ void __launch_bounds__(256) deps_gather_packed_dinf_x4_kernel(const u
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int cc = r[1][k + 1];
+      if (y < y_lo || y >= y_hi) {
+        out[k] = 0;
+        continue;
+      }
       if (cc == kCodeNoData) {
         out[k] = 0xBFF0000000000000ull;  // -1.0 (flow_accumulation_generic.hpp:95-97)
         continue;
@@ -1170,7 +1176,8 @@ __global__ void __launch_bounds__(256, 6) accum_walk_dinf_lanes_kernel(const uin
                                                                      const float *__restrict__ rmaxArr,
                                                                      unsigned long long *word, int W, int ncells, int *list,
                                                                      unsigned cap, DinfShare *sh, int excess_above,
-                                                                     int wait_div, unsigned long long *stats) {
+                                                                     int wait_div, unsigned long long *stats, int ghost_lo_end,
+                                                                     int ghost_hi_start, int seeded) {
   cg::grid_group grid = cg::this_grid();
   __shared__ int sQ[8][kLaneQueueD];
   __shared__ unsigned long long sQa[8][kLaneQueueD];
@@ -1182,7 +1189,10 @@ __global__ void __launch_bounds__(256, 6) accum_walk_dinf_lanes_kernel(const uin
   const int n_warps = (int)gridDim.x * 8;
   int head = 0, count = 0;        // warp-uniform ring state
   int pos = 0, end = 0;           // warp-uniform: next source candidate, end of the current chunk
-  bool more = true;               // the source cursor may still hold chunks
+  // Row bands: cells below ghost_lo_end / from ghost_hi_start on belong to a neighbouring band; flow into them is parked in
+  // their word as [parcels | sum] for the caller to ship.  `seeded`: no source scan, the list already holds the cells an
+  // inflow completed (the host put their number into list_tail / cons_end and a portion into quota).
+  bool more = seeded == 0;        // the source cursor may still hold chunks
   int walked = 0;                 // warp-uniform: cells walked since the last report
   bool walking = false;
   int c = 0;
@@ -1190,6 +1200,11 @@ __global__ void __launch_bounds__(256, 6) accum_walk_dinf_lanes_kernel(const uin
   int phase = 0, quota = 0;
   unsigned cons_end = 0;
   bool list_dry = true;           // nothing to claim from the list in this phase (phase 0: the list is empty)
+  if (seeded) {
+    quota = *reinterpret_cast<volatile int *>(&sh->quota);
+    cons_end = *reinterpret_cast<volatile unsigned *>(&sh->cons_end);
+    list_dry = false;
+  }
   // optional counters (accum_dinf_stats): what the warps spent their loop iterations on
   unsigned long long st_iters = 0, st_steps = 0, st_list = 0, st_loc = 0, st_got = 0;
   for (;;) {  // phases
@@ -1302,13 +1317,19 @@ __global__ void __launch_bounds__(256, 6) accum_walk_dinf_lanes_kernel(const uin
             const unsigned long long v1 = p1 > 0 ? (unsigned long long)((double)p1 * ad + 0.5) : 0ull;
             const unsigned long long v2 = p2 > 0 ? (unsigned long long)((double)p2 * ad + 0.5) : 0ull;
             if (p1 > 0) {
-              const unsigned long long old = atomicAdd(word + r1, v1 - kPkOne);
-              if ((old >> 56) == 1ull) {
-                next = r1;
-                next_acc = (old & kPkVal) + v1;
+              if (r1 < ghost_lo_end || r1 >= ghost_hi_start) {
+                atomicAdd(word + r1, v1 + kPkOne);  // park: one more parcel, v1 more flow
+              } else {
+                const unsigned long long old = atomicAdd(word + r1, v1 - kPkOne);
+                if ((old >> 56) == 1ull) {
+                  next = r1;
+                  next_acc = (old & kPkVal) + v1;
+                }
               }
             }
-            if (p2 > 0) {
+            if (p2 > 0 && (r2 < ghost_lo_end || r2 >= ghost_hi_start)) {
+              atomicAdd(word + r2, v2 + kPkOne);
+            } else if (p2 > 0) {
               const unsigned long long old = atomicAdd(word + r2, v2 - kPkOne);
               if ((old >> 56) == 1ull) {
                 const unsigned long long tot = (old & kPkVal) + v2;
@@ -1321,6 +1342,8 @@ __global__ void __launch_bounds__(256, 6) accum_walk_dinf_lanes_kernel(const uin
                 }
               }
             }
+          } else if (r1 < ghost_lo_end || r1 >= ghost_hi_start) {
+            atomicAdd(word + r1, acc + kPkOne);
           } else {
             const unsigned long long old = atomicAdd(word + r1, acc - kPkOne);
             if ((old >> 56) == 1ull) {
@@ -1422,6 +1445,61 @@ __global__ void __launch_bounds__(256, 6) accum_walk_dinf_lanes_kernel(const uin
   }
 }
 
+// seeds the shared block for a walk from a list of cells (row bands: the cells an inflow completed)
+__global__ void dinf_share_seed_kernel(DinfShare *sh, int n_list, int n_warps, int ncells) {
+  sh->cursor = ncells;
+  sh->done = 0;
+  sh->list_head = 0;
+  sh->list_tail = (unsigned)n_list;
+  sh->cons_end = (unsigned)n_list;
+  const int q = (n_list + n_warps - 1) / n_warps;
+  sh->quota = q < 1 ? 1 : (q > 32 ? 32 : q);
+  sh->stop = 0;
+  sh->n_waiting = 0;
+  sh->finished = 0;
+  sh->phases = 0;
+}
+
+// Queues the packed D-infinity walk on the library's stream (a cooperative launch: the phases meet at grid barriers, so
+// every block has to be resident).  seeded < 0: sources come from the scan over the words (`share` zeroed by the caller,
+// or holding the cell counts); seeded >= 0: the first `seeded` entries of `list` are the cells to start from.
+void launch_walk_dinf(const uint8_t *code, const float *rmax, unsigned long long *word, int W, int ncells, int *list,
+                      DinfShare *share, unsigned long long *stats, int ghost_lo_end, int ghost_hi_start, int seeded) {
+  Ctx &c = ctx();
+  int per_sm = 0;
+  if (stats) RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_dinf_lanes_kernel<true>, 256, 0));
+  else RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_dinf_lanes_kernel<false>, 256, 0));
+  if (per_sm < 1) per_sm = 1;
+  long long nb = (long long)c.num_sms * per_sm;
+  const long long work = seeded >= 0 ? ((long long)seeded + 31) / 32 : ((long long)ncells + kLaneChunk - 1) / kLaneChunk;
+  if (nb * 8 > work) nb = (work + 7) / 8;  // no more warps than chunks of sources / than warps' worth of listed cells
+  // (a listed cell may be the head of a river through the whole band: keep a block per SM for the phases to spread it over)
+  if (seeded >= 0 && nb < c.num_sms) nb = c.num_sms;
+  if (nb < 1) nb = 1;
+  if (seeded >= 0) {
+    dinf_share_seed_kernel<<<1, 1, 0, c.stream>>>(share, seeded, (int)nb * 8, ncells);
+    RDB_CK(cudaGetLastError());
+  }
+  const uint8_t *a_code = code;
+  const float *a_rmax = rmax;
+  int a_w = W, a_n = ncells;
+  int *a_list = list;
+  unsigned a_cap = (unsigned)ncells;
+  DinfShare *a_sh = share;
+  int a_excess = (int)(c.params.accum_dinf_share >= 0 ? c.params.accum_dinf_share : 4);
+  int a_wait = (int)(c.params.accum_dinf_wait > 0 ? c.params.accum_dinf_wait : 4);  // 1 / this share of the warps waiting
+  if (a_excess > kLaneQueueD - 96) a_excess = kLaneQueueD - 96;
+  unsigned long long *a_stats = stats;
+  int a_lo = ghost_lo_end, a_hi = ghost_hi_start, a_seeded = seeded >= 0 ? 1 : 0;
+  void *args[] = {(void *)&a_code, (void *)&a_rmax, (void *)&word, (void *)&a_w, (void *)&a_n, (void *)&a_list, (void *)&a_cap,
+                  (void *)&a_sh, (void *)&a_excess, (void *)&a_wait, (void *)&a_stats, (void *)&a_lo, (void *)&a_hi, (void *)&a_seeded};
+  if (stats)
+    RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_walk_dinf_lanes_kernel<true>, dim3((unsigned)nb), dim3(256), args, 0, c.stream));
+  else
+    RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_walk_dinf_lanes_kernel<false>, dim3((unsigned)nb), dim3(256), args, 0, c.stream));
+  RDB_CK(cudaGetLastError());
+}
+
 // `cursor_buf` (optional): a device int the caller owns; the launch is then left in flight (no stream sync)
 template <bool BAND>
 void launch_walk_packed(const uint8_t *code, unsigned long long *word, int W, int ncells, const int *frontier,
@@ -1493,7 +1571,7 @@ __global__ void __launch_bounds__(256) band_count_packed_kernel(const unsigned l
 // neighbour's flow arrives at my edge row: fold it into the packed words, release completed cells
 __global__ void __launch_bounds__(256) band_apply_packed_kernel(unsigned long long *row, const double *__restrict__ sum,
                                                                  const int *__restrict__ cnt, int W, int base_index,
-                                                                 int *frontier, int *fcount) {
+                                                                 int *frontier, int *fcount, double scale) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= W) return;
   const int k = cnt[x];
@@ -1502,7 +1580,7 @@ __global__ void __launch_bounds__(256) band_apply_packed_kernel(unsigned long lo
   const unsigned long long val = (wv & kPkVal) + (unsigned long long)sum[x];
   const unsigned long long left = (wv >> 56) - (unsigned long long)k;
   if (left == 0) {
-    row[x] = (unsigned long long)__double_as_longlong((double)val);
+    row[x] = (unsigned long long)__double_as_longlong((double)val * scale);  // (D-infinity sums carry 24 fractional bits)
     frontier[atomicAdd(fcount, 1)] = base_index + x;
   } else {
     row[x] = (left << 56) | val;
@@ -1566,43 +1644,17 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     const bool use_packed = c.params.accum_dinf_packed == 1 || (long long)hs0->n_noflow * 20 > (long long)hs0->n_data;
     if (use_packed) {
     dim3 blk(256), grd((w / 4 + 255) / 256, h < 8192 ? h : 8192);
-    deps_gather_packed_dinf_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, w, h);
+    deps_gather_packed_dinf_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, w, h, 0, h);
     RDB_CK(cudaGetLastError());
     count_launch();
     DevBuf<int> list(n);  // the hand-over list (a ring: at most one entry per ready cell is alive)
-    int per_sm = 0;
-    const bool with_stats = c.params.accum_dinf_stats != 0;
-    RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_dinf_lanes_kernel<false>, 256, 0));
-    if (with_stats) RDB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_walk_dinf_lanes_kernel<true>, 256, 0));
-    if (per_sm < 1) per_sm = 1;
     DevBuf<unsigned long long> dstats;
-    KernelTimer kt;
-    // every block has to be resident: the phases meet at grid barriers (a cooperative launch refuses a grid that is not)
-    long long nb = (long long)c.num_sms * per_sm;
-    const long long need = ((long long)n + kLaneChunk - 1) / kLaneChunk;
-    if (nb * 8 > need) nb = (need + 7) / 8;
-    {
-      const uint8_t *a_code = code.p;
-      const float *a_rmax = rmax.p;
-      int a_w = w, a_n = (int)n;
-      int *a_list = list.p;
-      unsigned a_cap = (unsigned)n;
-      DinfShare *a_sh = share.p;
-      int a_excess = (int)(c.params.accum_dinf_share >= 0 ? c.params.accum_dinf_share : 4);
-      int a_wait = (int)(c.params.accum_dinf_wait > 0 ? c.params.accum_dinf_wait : 4);  // 1 / this share of the warps waiting
-      if (a_excess > kLaneQueueD - 96) a_excess = kLaneQueueD - 96;
-      if (c.params.accum_dinf_stats) {
-        dstats.alloc(16);
-        RDB_CK(cudaMemsetAsync(dstats.p, 0, 16 * sizeof(unsigned long long), c.stream));
-      }
-      unsigned long long *a_stats = dstats.p;
-      void *args[] = {(void *)&a_code, (void *)&a_rmax, (void *)&word, (void *)&a_w, (void *)&a_n, (void *)&a_list, (void *)&a_cap,
-                      (void *)&a_sh, (void *)&a_excess, (void *)&a_wait, (void *)&a_stats};
-      if (with_stats)
-        RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_walk_dinf_lanes_kernel<true>, dim3((unsigned)nb), dim3(256), args, 0, c.stream));
-      else
-        RDB_CK(cudaLaunchCooperativeKernel((const void *)accum_walk_dinf_lanes_kernel<false>, dim3((unsigned)nb), dim3(256), args, 0, c.stream));
+    if (c.params.accum_dinf_stats) {
+      dstats.alloc(16);
+      RDB_CK(cudaMemsetAsync(dstats.p, 0, 16 * sizeof(unsigned long long), c.stream));
     }
+    KernelTimer kt;
+    launch_walk_dinf(code.p, rmax.p, word, w, (int)n, list.p, share.p, dstats.p, 0, (int)n, -1);
     RDB_CK(cudaGetLastError());
     count_launch(2);
     DinfShare *hs = reinterpret_cast<DinfShare *>(c.pinned);
@@ -1744,6 +1796,8 @@ struct FaccState {
   DevBuf<int> ghostcnt, fr0, fr1, cnt;
   bool prepared = false;
   bool packed = false;    // unit-weight D8: accumulator words are [donors left | integer sum] until final
+  bool packed_dinf = false;  // unit-weight D-infinity: the same words with 24 fractional bits (accum_walk_dinf_lanes_kernel)
+  DevBuf<DinfShare> dshare;
   bool fused = false;     // ... and codes + donor counts come from the fused rolling-window pass at the first run
   const float *dem = nullptr;
   float nodata_v = 0.f;
@@ -1763,6 +1817,11 @@ struct FaccState {
     accum = d_accum;
     if (h - gt - gb < 1) fail("facc_begin: band has no owned rows");
     packed = !dinf && ones && (w & 3) == 0 && ((uintptr_t)d_accum & 15) == 0 && c.params.accum_packed != 0;
+    packed_dinf = dinf && ones && (w & 3) == 0 && ((uintptr_t)d_accum & 15) == 0 && c.params.accum_dinf_packed != 0;
+    if (packed_dinf) {
+      packed = true;  // same protocol as packed D8: parked parcels in the ghost words, take / apply on the words
+      dshare.alloc(1);
+    }
     code.alloc(n());
     if (!packed) st.alloc(n());
     if (dinf) rmax.alloc(n());
@@ -1773,7 +1832,7 @@ struct FaccState {
     RDB_CK(cudaMemsetAsync(ghostcnt.p, 0, 2 * (size_t)W * sizeof(int), c.stream));
     RDB_CK(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(int), c.stream));
     const unsigned blocks = (unsigned)((n() + 255) / 256);
-    fused = packed && c.params.accum_fused_prep != 0 && ((uintptr_t)d_dem & 15) == 0;
+    fused = packed && !packed_dinf && c.params.accum_fused_prep != 0 && ((uintptr_t)d_dem & 15) == 0;
     dem = d_dem;
     nodata_v = nodata;
     if (fused) {
@@ -1846,7 +1905,9 @@ struct FaccState {
     Ctx &c = ctx();
     unsigned long long *word = reinterpret_cast<unsigned long long *>(accum);
     const int lo_end = gt ? W : 0, hi_start = gb ? (H - 1) * W : H * W;
-    if (!prepared && fused) {
+    if (packed_dinf) {
+      walk_packed_async(n_frontier);
+    } else if (!prepared && fused) {
       dim3 pgrd((unsigned)((W + kPrepOut - 1) / kPrepOut), (unsigned)((H + kPrepRows - 1) / kPrepRows));
       fa_d8_prep_rolling_kernel<<<pgrd, 256, 0, c.stream>>>(dem, code.p, word, W, H, nodata_v, gt, H - gb);
       launch_walk_packed<true>(code.p, word, W, (int)n(), nullptr, lo_end, hi_start, true);
@@ -1864,7 +1925,7 @@ struct FaccState {
     }
     RDB_CK(cudaGetLastError());
     n_frontier = 0;
-    rounds++;
+    if (!packed_dinf) rounds++;  // (walk_packed_async counted it)
     int *h = (int *)c.pinned;
     DevBuf<int> sums(2);
     RDB_CK(cudaMemsetAsync(sums.p, 0, 2 * sizeof(int), c.stream));
@@ -1883,6 +1944,23 @@ struct FaccState {
     Ctx &c = ctx();
     unsigned long long *word = reinterpret_cast<unsigned long long *>(accum);
     const int lo_end = gt ? W : 0, hi_start = gb ? (H - 1) * W : H * W;
+    if (packed_dinf) {
+      // fr0 is both the list the inflow appended the completed cells to and the walk's hand-over ring
+      if (!prepared) {
+        dim3 blk(256), grd((W / 4 + 255) / 256, H < 8192 ? H : 8192);
+        deps_gather_packed_dinf_x4_kernel<<<grd, blk, 0, c.stream>>>(code.p, word, W, H, gt, H - gb);
+        RDB_CK(cudaMemsetAsync(dshare.p, 0, sizeof(DinfShare), c.stream));
+        launch_walk_dinf(code.p, rmax.p, word, W, (int)n(), fr0.p, dshare.p, nullptr, lo_end, hi_start, -1);
+        count_launch(2);
+        prepared = true;
+      } else if (frontier_cells > 0) {
+        launch_walk_dinf(code.p, rmax.p, word, W, (int)n(), fr0.p, dshare.p, nullptr, lo_end, hi_start, frontier_cells);
+        count_launch(2);
+      }
+      rounds++;
+      c.stats.accum_rounds = rounds;
+      return;
+    }
     if (!prepared) {
       if (fused) {
         dim3 pgrd((unsigned)((W + kPrepOut - 1) / kPrepOut), (unsigned)((H + kPrepRows - 1) / kPrepRows));
@@ -1997,7 +2075,8 @@ struct FaccState {
     const unsigned rb = (unsigned)((W + 255) / 256);
     if (packed) {
       band_apply_packed_kernel<<<rb, 256, 0, c.stream>>>(reinterpret_cast<unsigned long long *>(accum) + (size_t)row * W,
-                                                         d_sum_row, d_cnt_row, W, row * W, fr0.p, cnt.p + 2);
+                                                         d_sum_row, d_cnt_row, W, row * W, fr0.p, cnt.p + 2,
+                                                         packed_dinf ? 1.0 / 16777216.0 : 1.0);
       RDB_CK(cudaGetLastError());
       count_launch();
       pending_apply = true;

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from richdem_b200 import sharded
+from richdem_b200 import _lib, sharded
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"  # tests/test_emulated_kernels.py re-runs these drivers on host memory against the kernel emulation
@@ -124,8 +124,14 @@ def test_band_accumulation_equals_single(checker, G, dinf):
     resolved = checker.resolve_flats(filled, nd)
     expected = checker.fa_dinf(resolved, nd) if dinf else checker.fa_d8(resolved, nd)
     got, rounds = emulate_fa_bands(resolved, G, nd, dinf)
-    if dinf:
-        np.testing.assert_allclose(got, expected, rtol=1e-9, atol=0)
+    if dinf:  # unit weights: the packed fixed-point walk (relative error < 2^-23 by construction)
+        np.testing.assert_allclose(got, expected, rtol=5e-7, atol=0)
+        _lib.set_param("accum_dinf_packed", 0)  # the level kernel's double atomics
+        try:
+            got0, _ = emulate_fa_bands(resolved, G, nd, dinf)
+        finally:
+            _lib.reset_params()
+        np.testing.assert_allclose(got0, expected, rtol=1e-9, atol=0)
     else:
         assert np.array_equal(got, expected), f"G={G}: {(got != expected).sum()} cells differ ({rounds} rounds)"
 

@@ -88,7 +88,7 @@ def _worker(rank, world, port, lib_path, dem, expected, params, out_q):
         res["fa_d8"] = np.array_equal(acc[own].numpy(), expected["fa_d8"][r0:r1])
         acc, _ = sharded.fa_band(filled, gt, gb, ND, dinf=True)
         a, e = acc[own].numpy(), expected["fa_dinf"][r0:r1]
-        res["fa_dinf"] = bool(np.all(np.abs(a - e) <= 1e-9 * np.maximum(1.0, np.abs(e))))
+        res["fa_dinf"] = bool(np.all(np.abs(a - e) <= 5e-7 * np.maximum(1.0, np.abs(e))))  # packed fixed-point sums (< 2^-23)
         out_q.put((rank, res, None))
     except Exception as exc:  # surface the failure in the parent instead of a silent non-zero exit
         import traceback
