@@ -36,8 +36,8 @@ grep -a '"metric"' "$OUT/bench.log" | tail -1 > "$OUT/bench.json"
 [ -z "$LITE" ] && step ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file "$OUT/launches.csv" \
   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-configs --no-verify
 if [ -n "$NCU_DINF" ]; then
-  step ncu_dinf 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_dinf.csv" \
-    python tools/dinf_profile.py "$N" "accum_dinf_packed=1"
+  step ncu_dinf 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"flow_code|dinf|deps_gather" -c 60 --csv \
+    --log-file "$OUT/launches_dinf.csv" python tools/dinf_profile.py "$N" "accum_dinf_packed=1"
 fi
 if [ -n "$NCU_FULL" ]; then
   # full-set captures of the dominant kernels (one replayed launch each; read here with `ncu -i ... --page raw --csv`):
