@@ -30,7 +30,7 @@ constexpr int kLaneChunk = 1024;  // cells a persistent warp fetches per cursor 
 template <bool DINF>
 __global__ void __launch_bounds__(256) flow_code_kernel(const float *__restrict__ dem, uint8_t *__restrict__ code,
                                                          float *__restrict__ rmaxArr, double *__restrict__ accum,
-                                                         int W, int H, float nodata, int ones) {
+                                                         int W, int H, float nodata, int ones, int tfilter) {
   const size_t n = (size_t)W * H;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) flow_code_kernel(const float *__restrict_
   int cd;
   if (DINF) {
     float rmax = 0;
-    const int nm = fm_tarboton_cell(dem, x, y, W, H, nodata, &rmax);
+    const int nm = fm_tarboton_cell(dem, x, y, W, H, nodata, &rmax, tfilter != 0);
     if (nm == kCodeNoData || nm == 0) {
       cd = nm;
     } else if (rmax == 0.0f) {
@@ -1486,7 +1486,7 @@ void launch_walk_dinf(const uint8_t *code, const float *rmax, unsigned long long
   int *a_list = list;
   unsigned a_cap = (unsigned)ncells;
   DinfShare *a_sh = share;
-  int a_excess = (int)(c.params.accum_dinf_share >= 0 ? c.params.accum_dinf_share : 4);
+  int a_excess = (int)(c.params.accum_dinf_share >= 0 ? c.params.accum_dinf_share : 1);  // measured at 32768^2 after flat resolution: 0 / 1 / 2 / 4 / 8 -> 140 / 135 / 141 / 185 / 189 ms
   int a_wait = (int)(c.params.accum_dinf_wait > 0 ? c.params.accum_dinf_wait : 4);  // 1 / this share of the warps waiting
   if (a_excess > kLaneQueueD - 96) a_excess = kLaneQueueD - 96;
   unsigned long long *a_stats = stats;
@@ -1631,7 +1631,7 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
     rmax.alloc(n);
     const unsigned blocks = (unsigned)((n + 255) / 256);
     unsigned long long *word = reinterpret_cast<unsigned long long *>(d_accum);
-    flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, 1);
+    flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, 1, (int)c.params.flowmet_tarboton_filter);
     have_codes = true;
     DevBuf<DinfShare> share(1);
     RDB_CK(cudaMemsetAsync(share.p, 0, sizeof(DinfShare), c.stream));
@@ -1683,12 +1683,12 @@ void fa_fused_dev(const float *d_dem, double *d_accum, int w, int h, float nodat
   if (have_codes) {
     // flow codes, rmax and the unit weights are in place already
   } else if (dinf)
-    flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, ones ? 1 : 0);
+    flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, ones ? 1 : 0, (int)c.params.flowmet_tarboton_filter);
   else if ((w & 3) == 0 && ((uintptr_t)d_dem & 15) == 0 && ((uintptr_t)d_accum & 15) == 0) {
     dim3 blk(256), grd((w / 4 + 255) / 256, h < 8192 ? h : 8192);
     flow_code_d8_x4_kernel<<<grd, blk, 0, c.stream>>>(d_dem, code.p, d_accum, w, h, nodata, ones ? 1 : 0);
   } else
-    flow_code_kernel<false><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, nullptr, d_accum, w, h, nodata, ones ? 1 : 0);
+    flow_code_kernel<false><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, nullptr, d_accum, w, h, nodata, ones ? 1 : 0, (int)c.params.flowmet_tarboton_filter);
   RDB_CK(cudaGetLastError());
   if ((w & 3) == 0) {
     dim3 blk(256), grd((w / 4 + 255) / 256, h < 8192 ? h : 8192);
@@ -1847,9 +1847,9 @@ struct FaccState {
     // rows 0 / H-1 of the local raster are either true raster edges (no ghost) or ghost rows whose
     // codes are replaced below, so the per-cell functions' own edge test is exactly right here
     if (dinf)
-      flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, ones ? 1 : 0);
+      flow_code_kernel<true><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, rmax.p, d_accum, w, h, nodata, ones ? 1 : 0, (int)c.params.flowmet_tarboton_filter);
     else
-      flow_code_kernel<false><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, nullptr, d_accum, w, h, nodata, ones ? 1 : 0);
+      flow_code_kernel<false><<<blocks, 256, 0, c.stream>>>(d_dem, code.p, nullptr, d_accum, w, h, nodata, ones ? 1 : 0, (int)c.params.flowmet_tarboton_filter);
     RDB_CK(cudaGetLastError());
     count_launch();
     if (packed) return;  // the packed gather (first run) initialises every accumulator word

@@ -269,6 +269,7 @@ int rdb200_set_param(const char *name, int64_t value) {
   else if (n == "accum_packed") p.accum_packed = value;
   else if (n == "accum_dinf_packed") p.accum_dinf_packed = value;
   else if (n == "accum_dinf_share") p.accum_dinf_share = value;
+  else if (n == "flowmet_tarboton_filter") p.flowmet_tarboton_filter = value;
   else if (n == "accum_walk_scan") p.accum_walk_scan = value;
   else if (n == "accum_walk_ahead") p.accum_walk_ahead = value;
   else if (n == "accum_dinf_stats") p.accum_dinf_stats = value;

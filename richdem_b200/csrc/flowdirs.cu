@@ -128,7 +128,7 @@ enum : int { FM_MODE_D8 = 0, FM_MODE_DINF = 1, FM_MODE_D4 = 2, FM_MODE_HOLMGREN 
 
 template <int MODE>
 __global__ void __launch_bounds__(256) fm_props_kernel(const float *__restrict__ dem, float *__restrict__ props,
-                                                        int W, int H, float nodata, double xparam) {
+                                                        int W, int H, float nodata, double xparam, int tfilter) {
   constexpr bool DINF = MODE == FM_MODE_DINF;
   __shared__ __align__(16) float s[256 * 9];
   const size_t n = (size_t)W * H;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) fm_props_kernel(const float *__restrict__
     const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
     if (DINF) {
       float rmax = 0;
-      const int nm = fm_tarboton_cell(dem, x, y, W, H, nodata, &rmax);
+      const int nm = fm_tarboton_cell(dem, x, y, W, H, nodata, &rmax, tfilter != 0);
       if (nm == kCodeNoData) {
         p[0] = kNoDataGen;
       } else if (nm > 0) {
@@ -224,7 +224,8 @@ template <int MODE>
 static void fm_launch(const float *d_dem, float *d_props, int w, int h, float nodata, double xparam) {
   Ctx &c = ctx();
   const size_t n = (size_t)w * h;
-  fm_props_kernel<MODE><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d_dem, d_props, w, h, nodata, xparam);
+  fm_props_kernel<MODE><<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d_dem, d_props, w, h, nodata, xparam,
+                                                                           (int)c.params.flowmet_tarboton_filter);
   RDB_CK(cudaGetLastError());
   count_launch();
 }

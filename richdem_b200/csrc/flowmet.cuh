@@ -112,8 +112,39 @@ __device__ __forceinline__ void fm_mfd_cell(const float *__restrict__ dem, int x
 // returns kCodeNoData, 0 (no flow) or nmax in 1..8 with *rmax_out = rmax after the facet-parity
 // flip (:121-126).  All double arithmetic uses explicit round-to-nearest intrinsics so that no
 // FMA contraction happens (the CPU reference is compiled without it).
+
+// which of the reference's three cases a facet falls into (:95-107): 0: r < 1e-7, 1: r > dang - 1e-7, 2: in between.
+// r = atan2(s2, s1) only matters through these two threshold tests and, for the steepest facet, as rmax.  The tests are
+// decided from the signs and the ratio s2 / s1 (atan2 is monotone in it) whenever the ratio is clear of tan(1e-7) and
+// tan(dang - 1e-7) by a relative 1e-9 -- ten million ulps, far beyond any atan2's error -- and by the function itself
+// otherwise; the one atan2 a cell needs is taken at the end.  (8 double atan2 per cell were 77 of the 575 ms of FA_Dinf
+// at 32768^2.)
+__device__ __forceinline__ int tarboton_facet_case(double s1, double s2, double dangd) {
+  if (s2 < 0.0 || (s2 == 0.0 && s1 >= 0.0)) return 0;  // angles in (-pi, 0], and atan2(0, 0) = 0
+  if (s1 <= 0.0) return 1;                              // s2 > 0 (or s2 == 0 with s1 < 0): angles in [pi/2, pi]
+  const double tlo = 1.0000000000000033e-07, thi = 0.9999998437114023;  // tan(1e-7), tan(dang - 1e-7)
+  const double eps = 1e-9;
+  if (s2 < s1 * (tlo * (1.0 - eps))) return 0;
+  if (s2 > s1 * (thi * (1.0 + eps))) return 1;
+  if (s2 > s1 * (tlo * (1.0 + eps)) && s2 < s1 * (thi * (1.0 - eps))) return 2;
+  const double ra = atan2(s2, s1);
+  return ra < 1e-7 ? 0 : (ra > __dsub_rn(dangd, 1e-7) ? 1 : 2);
+}
+// the facet's slope as the reference computes it
+__device__ __forceinline__ double tarboton_facet_slope(int fcase, double s1, double s2, double e0_minus_e2) {
+  if (fcase == 0) return s1;                                               // :99-101
+  if (fcase == 1) return __ddiv_rn(e0_minus_e2, 1.4142135623730951);       // :102-104, sqrt(d1*d1+d2*d2) = sqrt(2.0)
+  return __dsqrt_rn(__dadd_rn(__dmul_rn(s1, s1), __dmul_rn(s2, s2)));      // :106
+}
+
+// `filter`: choose the steepest facet from the SQUARED slopes first (no square root, no division per facet: in a warp
+// whose lanes sit in different cases every facet otherwise costs both) and evaluate the reference's slope for the winner
+// only.  Squaring is monotone, so the facet with the largest square has the largest slope unless another facet's square
+// is within a relative 1e-12 of it (several thousand ulps); an exact tie inside one case means an exactly equal slope and
+// the first facet wins as in the reference; anything else near the maximum sends the cell through the reference's own
+// sequence of comparisons.  Identical result either way (rdb200_set_param("flowmet_tarboton_filter", 0) turns it off).
 __device__ __forceinline__ int fm_tarboton_cell(const float *__restrict__ dem, int x, int y, int W, int H,
-                                                float nodata, float *rmax_out) {
+                                                float nodata, float *rmax_out, bool filter = true) {
   const size_t i = (size_t)y * W + x;
   const float e0f = __ldg(dem + i);
   if (e0f == nodata) return kCodeNoData;
@@ -125,62 +156,76 @@ __device__ __forceinline__ int fm_tarboton_cell(const float *__restrict__ dem, i
   const float dang = 0.78539818525314331f;  // float(atan2(1,1)), :29
   const double dangd = (double)dang;
   const double e0 = (double)e0f;
+  // the eight neighbours once: cardinal W, N, E, S and diagonal NW, NE, SE, SW (interior cell: all in the grid)
+  const float cw = __ldg(dem + i - 1), cn = __ldg(dem + i - W), ce = __ldg(dem + i + 1), cs = __ldg(dem + i + W);
+  const float dnw = __ldg(dem + i - W - 1), dne = __ldg(dem + i - W + 1), dse = __ldg(dem + i + W + 1), dsw = __ldg(dem + i + W - 1);
+  // facet n: e1 = its cardinal neighbour, e2 = its diagonal one
+  const float e1s[9] = {0.f, cw, cn, cn, ce, ce, cs, cs, cw};
+  const float e2s[9] = {0.f, dnw, dnw, dne, dne, dse, dse, dsw, dsw};
   int nmax = -1, bmax = 0;
   double smax = 0, s1max = 0, s2max = 0;
-  float rmax = 0;
+  bool decided = false;
+  if (filter) {
+    double qbest = 0, qsecond = 0;  // largest squared slope and the largest one of any OTHER facet that is not its exact twin
+    int nb = -1, cb = 0;
+    double s1b = 0, s2b = 0, tb = 0;
 #pragma unroll
-  for (int n = 1; n <= 8; n++) {
-    // e1 is the cardinal neighbour of the facet, e2 the diagonal one
-    const int dx1 = (n == 1 || n == 8) ? -1 : ((n == 4 || n == 5) ? 1 : 0);
-    const int dy1 = (n == 2 || n == 3) ? -1 : ((n == 6 || n == 7) ? 1 : 0);
-    const int dx2 = (n == 1 || n == 2 || n == 7 || n == 8) ? -1 : 1;
-    const int dy2 = (n <= 4) ? -1 : 1;
-    // interior cell: both neighbours are in the grid (:76-83 only filter NoData here)
-    const float e1f = __ldg(dem + (size_t)(y + dy1) * W + (x + dx1));
-    const float e2f = __ldg(dem + (size_t)(y + dy2) * W + (x + dx2));
-    if (e1f == nodata || e2f == nodata) continue;
-    const double e1 = (double)e1f, e2 = (double)e2f;
-    const double s1 = __dsub_rn(e0, e1);  // (e0-e1)/d1, d1 = 1
-    const double s2 = __dsub_rn(e1, e2);
-    // r = atan2(s2, s1) only matters through the two threshold tests below and, for the steepest facet, as rmax.
-    // The tests are decided from the signs and the ratio s2 / s1 (atan2 is monotone in it) whenever the ratio is
-    // clear of tan(1e-7) and tan(dang - 1e-7) by a relative 1e-9 -- ten million ulps, far beyond any atan2's error --
-    // and by the function itself otherwise; the one atan2 a cell needs is taken at the end.  (8 double atan2 per cell
-    // were 77 of the 575 ms of FA_Dinf at 32768^2.)
-    int branch;  // 0: r < 1e-7   1: r > dang - 1e-7   2: in between
-    if (s2 < 0.0 || (s2 == 0.0 && s1 >= 0.0)) {
-      branch = 0;  // angles in (-pi, 0], and atan2(0, 0) = 0
-    } else if (s1 <= 0.0) {
-      branch = 1;  // s2 > 0 (or s2 == 0 with s1 < 0): angles in [pi/2, pi]
-    } else {       // first quadrant, both positive
-      const double tlo = 1.0000000000000033e-07, thi = 0.9999998437114023;  // tan(1e-7), tan(dang - 1e-7)
-      const double eps = 1e-9;
-      if (s2 < s1 * (tlo * (1.0 - eps))) branch = 0;
-      else if (s2 > s1 * (thi * (1.0 + eps))) branch = 1;
-      else if (s2 > s1 * (tlo * (1.0 + eps)) && s2 < s1 * (thi * (1.0 - eps))) branch = 2;
-      else {
-        const double ra = atan2(s2, s1);
-        branch = ra < 1e-7 ? 0 : (ra > __dsub_rn(dangd, 1e-7) ? 1 : 2);
+    for (int n = 1; n <= 8; n++) {
+      const float e1f = e1s[n], e2f = e2s[n];
+      if (e1f == nodata || e2f == nodata) continue;  // :76-83
+      const double e1 = (double)e1f, e2 = (double)e2f;
+      const double s1 = __dsub_rn(e0, e1), s2 = __dsub_rn(e1, e2), t = __dsub_rn(e0, e2);  // exact: differences of floats
+      const int fc = tarboton_facet_case(s1, s2, dangd);
+      double q;  // the slope's square; 0 for a slope that is not positive (it can never beat smax = 0)
+      if (fc == 0) q = s1 > 0.0 ? __dmul_rn(s1, s1) : 0.0;
+      else if (fc == 1) q = t > 0.0 ? __dmul_rn(__dmul_rn(t, t), 0.5) : 0.0;
+      else q = __dadd_rn(__dmul_rn(s1, s1), __dmul_rn(s2, s2));
+      if (q > qbest) {
+        if (qbest > qsecond) qsecond = qbest;  // the previous leader becomes a rival
+        qbest = q;
+        nb = n;
+        cb = fc;
+        s1b = s1;
+        s2b = s2;
+        tb = t;
+      } else if (q == qbest && fc == cb) {
+        // an exact twin of the leader in the same case: exactly the same slope, the earlier facet keeps the lead
+      } else if (q > qsecond) {
+        qsecond = q;
       }
     }
-    double s;
-    if (branch == 0) {  // :99-101
-      s = s1;
-    } else if (branch == 1) {  // :102-104
-      s = __ddiv_rn(__dsub_rn(e0, e2), 1.4142135623730951);  // sqrt(d1*d1+d2*d2) = sqrt(2.0)
-    } else {
-      s = __dsqrt_rn(__dadd_rn(__dmul_rn(s1, s1), __dmul_rn(s2, s2)));  // :106
+    if (nb == -1) return 0;  // no facet slopes down (:115-116; every q is 0)
+    if (qsecond < qbest * (1.0 - 1e-12)) {
+      nmax = nb;
+      bmax = cb;
+      s1max = s1b;
+      s2max = s2b;
+      smax = tarboton_facet_slope(cb, s1b, s2b, tb);
+      decided = true;
     }
-    if (s > smax) {  // :109-113
-      smax = s;
-      nmax = n;
-      bmax = branch;
-      s1max = s1;
-      s2max = s2;
+  }
+  if (!decided) {
+    nmax = -1;
+#pragma unroll
+    for (int n = 1; n <= 8; n++) {
+      const float e1f = e1s[n], e2f = e2s[n];
+      if (e1f == nodata || e2f == nodata) continue;
+      const double e1 = (double)e1f, e2 = (double)e2f;
+      const double s1 = __dsub_rn(e0, e1);  // (e0-e1)/d1, d1 = 1
+      const double s2 = __dsub_rn(e1, e2);
+      const int fc = tarboton_facet_case(s1, s2, dangd);
+      const double s = tarboton_facet_slope(fc, s1, s2, __dsub_rn(e0, e2));
+      if (s > smax) {  // :109-113
+        smax = s;
+        nmax = n;
+        bmax = fc;
+        s1max = s1;
+        s2max = s2;
+      }
     }
   }
   if (nmax == -1) return 0;
-  rmax = bmax == 0 ? 0.0f : (bmax == 1 ? (float)dangd : (float)atan2(s2max, s1max));
+  float rmax = bmax == 0 ? 0.0f : (bmax == 1 ? (float)dangd : (float)atan2(s2max, s1max));
   const bool af_pos = (nmax & 1) == 0;  // af[n] == +1 for even n
   if (af_pos && rmax == 0.0f) rmax = dang;
   else if (af_pos && rmax == dang) rmax = 0.0f;

@@ -259,7 +259,7 @@ VARIANTS = [  # every switch is a schedule / layout choice (rdb200_set_param); n
     {"fill_ordered": 0, "fill_multigrid": 0}, {"fill_multigrid": 0}, {"fill_vcycle": 0}, {"fill_multigrid": 4, "fill_vcycle": 4},
     {"fill_multigrid": 8, "fill_multigrid_min": 256, "fill_vcycle": 2}, {"fill_multigrid": 3, "fill_multigrid_min": 128, "fill_vcycle": 0},
     {"flats_tiled": 0}, {"flats_uf_tiled": 0}, {"flats_fused_classify": 0}, {"flats_pair": 0}, {"accum_packed": 0}, {"accum_fused_prep": 0}, {"accum_walk_lanes": 0},
-    {"accum_fused_prep": 0, "accum_walk_lanes": 0}, {"accum_walk_scan": 1}, {"accum_walk_scan": 2}, {"flowdirs_rolling": 0}, {"accum_dinf_packed": 0}, {"accum_dinf_packed": 1}, {"accum_dinf_packed": 1, "accum_dinf_share": 0}, {"accum_dinf_packed": 1, "accum_dinf_share": 64}, {},
+    {"accum_fused_prep": 0, "accum_walk_lanes": 0}, {"accum_walk_scan": 1}, {"accum_walk_scan": 2}, {"flowmet_tarboton_filter": 0}, {"flowdirs_rolling": 0}, {"accum_dinf_packed": 0}, {"accum_dinf_packed": 1}, {"accum_dinf_packed": 1, "accum_dinf_share": 0}, {"accum_dinf_packed": 1, "accum_dinf_share": 64}, {},
 ]
 
 
