@@ -163,3 +163,25 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+def test_scoped_param_restores_what_the_process_had_set():
+    """sharded.py's Python band protocol leashes the fill's rounds per run through a process-wide switch; the switch must be
+    back to what the process had (or to the library's default) when the call is over."""
+    from richdem_b200 import _lib
+    _lib.reset_params()
+    try:
+        with _lib.scoped_param("fill_band_rounds", 64):
+            assert _lib._param_values["fill_band_rounds"] == 64
+        assert "fill_band_rounds" not in _lib._param_values  # never set before: back to the default, not recorded as set
+        _lib.set_param("fill_band_rounds", 7)
+        with _lib.scoped_param("fill_band_rounds", 64):
+            with _lib.scoped_param("fill_band_rounds", 3):
+                assert _lib._param_values["fill_band_rounds"] == 3
+            assert _lib._param_values["fill_band_rounds"] == 64
+        assert _lib._param_values["fill_band_rounds"] == 7
+        with pytest.raises(_lib.RichdemB200Error, match="unknown parameter"):
+            _lib.set_param("no_such_switch", 1)
+    finally:
+        _lib.reset_params()
+    assert _lib._param_values == {}
