@@ -184,6 +184,31 @@ class _Backend:
         self._ta(self.TA_IDS[attrib], d, w, h, nodata, nodata_out, zscale, float(cell[0]), float(cell[1]), out)
         return out
 
+    # -- f4: the native cache format, written / read by the reference itself (common/Array2D.hpp:209-281)
+    def save_native(self, path, dem, nodata, geotransform, projection=""):
+        assert self.kind == "reference"
+        d = self._dem(dem)
+        h, w = d.shape
+        f = self.lib.ref_save_native_f32
+        f.argtypes = [C.c_char_p, _f32p, C.c_int, C.c_int, C.c_float, np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_char_p]
+        f.restype = None
+        f(path.encode(), d, w, h, nodata, np.ascontiguousarray(geotransform, np.float64), projection.encode())
+
+    def load_native(self, path):
+        assert self.kind == "reference"
+        f = self.lib.ref_load_native_f32
+        f.argtypes = [C.c_char_p, C.c_void_p, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS"), C.POINTER(C.c_float),
+                      np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_char_p, C.c_int]
+        f.restype = C.c_int
+        dims = np.zeros(2, np.int32)
+        nd = C.c_float()
+        gt = np.zeros(6, np.float64)
+        proj = C.create_string_buffer(4096)
+        f(path.encode(), None, dims, C.byref(nd), gt, proj, 4096)
+        data = np.empty((int(dims[1]), int(dims[0])), np.float32)
+        f(path.encode(), data.ctypes.data_as(C.c_void_p), dims, C.byref(nd), gt, proj, 4096)
+        return data, float(nd.value), gt, proj.value.decode()
+
     # -- f2: direction-grid flat resolution (reference backend only: flats/flat_resolution.hpp:588-607)
     def d8_flow_directions_flats(self, dem, nodata):
         """(directions, mask, labels) of barnes_flat_resolution_d8(dem, dirs, alter=false)."""

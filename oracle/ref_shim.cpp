@@ -216,6 +216,34 @@ void ref_terrain_attribute_f32(int attribute, const float *dem, int w, int h, fl
   std::memcpy(out, o.data(), sizeof(float) * (size_t)w * h);
 }
 
+// common/Array2D.hpp:209-241 (saveToCache) / :246-281 (loadNative through the `native` constructor, :420-423): the
+// reference's own cache format, written and read by the reference, so that the Python layer's SaveNative / LoadNative can
+// be checked against it in both directions.  geotransform6: the six doubles; projection: a C string.
+void ref_save_native_f32(const char *path, const float *data, int w, int h, float nodata, const double *geotransform6,
+                         const char *projection) {
+  Array2D<float> a(w, h, 0.0f);
+  std::memcpy(a.data(), data, sizeof(float) * (size_t)w * h);
+  a.setNoData(nodata);
+  a.geotransform.assign(geotransform6, geotransform6 + 6);
+  a.projection = projection ? projection : "";
+  a.saveToCache(path);
+}
+// returns 0 and fills the outputs (data may be null to read the header only); dims[0..1] = width, height
+int ref_load_native_f32(const char *path, float *data, int *dims, float *nodata, double *geotransform6, char *projection,
+                        int projection_capacity) {
+  Array2D<float> a(std::string(path), true);
+  dims[0] = a.width();
+  dims[1] = a.height();
+  *nodata = a.noData();
+  for (int k = 0; k < 6; k++) geotransform6[k] = a.geotransform.size() == 6 ? a.geotransform[k] : 0.0;
+  if (projection && projection_capacity > 0) {
+    std::strncpy(projection, a.projection.c_str(), projection_capacity - 1);
+    projection[projection_capacity - 1] = 0;
+  }
+  if (data) std::memcpy(data, a.data(), sizeof(float) * (size_t)a.width() * a.height());
+  return 0;
+}
+
 // flats/flat_resolution.hpp:588-607: barnes_flat_resolution_d8(elevations, flowdirs, alter = false) -- what
 // apps/rd_d8_flowdirs.cpp:18 ships: d8_flow_directions, resolve_flats_barnes (:448-515), d8_flow_flats (:97-116)
 void ref_barnes_flat_resolution_d8_f32(const float *dem, int w, int h, float nodata, uint8_t *dirs, int32_t *mask_out,

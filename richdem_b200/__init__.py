@@ -296,6 +296,56 @@ def TerrainAttribute(dem: rdarray, attrib: str, zscale: float = 1.0) -> rdarray:
     return result
 
 
+# ---- the reference's native cache format (host I/O; nothing runs on the GPU) ---------------------------------------------
+_NATIVE_NO_I = 0xFFFFFFFF  # common/Array2D.hpp:103-115: "number of data cells not counted"
+
+
+def SaveNative(rda: rdarray, filename: str) -> None:
+    """Writes ``rda`` in the uncompressed native cache format of richdem::Array2D (`saveToCache`, common/Array2D.hpp:209-241):
+    int32 height, width, x offset, y offset | uint32 data-cell count | NoData (the raster's dtype) | 6 doubles geotransform |
+    size_t projection length + bytes | the cells, row-major.  The file carries no dtype tag: the reader has to know it
+    (`richdem::Array2D<T>(filename, true)`, :420-423)."""
+    if type(rda) is not rdarray:
+        raise Exception("A richdem.rdarray or numpy.ndarray is required!")
+    if rda.ndim != 2:
+        raise RuntimeError("Array must have two dimensions!")
+    a = np.ascontiguousarray(rda)
+    h, w = a.shape
+    nd = rda.no_data if rda.no_data is not None else -9999
+    gt = rda.geotransform if rda.geotransform is not None else [0, 1, 0, 0, 0, -1]
+    proj = (rda.projection or "").encode()
+    with open(filename, "wb") as f:
+        f.write(np.array([h, w, 0, 0], np.int32).tobytes())
+        f.write(np.array([_NATIVE_NO_I], np.uint32).tobytes())
+        f.write(np.array([nd], a.dtype).tobytes())
+        f.write(np.array(list(gt), np.float64).reshape(6).tobytes())
+        f.write(np.array([len(proj)], np.uint64).tobytes())
+        f.write(proj)
+        f.write(a.tobytes())
+
+
+def LoadNative(filename: str, dtype="float32") -> rdarray:
+    """Reads a raster written by richdem::Array2D<dtype>::saveToCache (or :func:`SaveNative`); see there for the layout."""
+    dt = np.dtype(dtype)
+    with open(filename, "rb") as f:
+        head = f.read(16 + 4 + dt.itemsize + 48 + 8)
+        if len(head) < 16 + 4 + dt.itemsize + 48 + 8:
+            raise RuntimeError(f"Failed to load native file '{filename}'!")
+        h, w, _xoff, _yoff = np.frombuffer(head, np.int32, 4, 0)
+        nd = np.frombuffer(head, dt, 1, 20)[0]
+        gt = np.frombuffer(head, np.float64, 6, 20 + dt.itemsize)
+        plen = int(np.frombuffer(head, np.uint64, 1, 20 + dt.itemsize + 48)[0])
+        if h < 0 or w < 0 or plen > (1 << 20):
+            raise RuntimeError(f"'{filename}' is not a native RichDEM raster of dtype {dt}")
+        proj = f.read(plen).decode(errors="replace")
+        data = np.fromfile(f, dt, int(h) * int(w))
+    if data.size != int(h) * int(w):
+        raise RuntimeError(f"'{filename}' is truncated: {data.size} of {int(h) * int(w)} cells")
+    out = rdarray(data.reshape(int(h), int(w)), no_data=nd.item(), geotransform=[float(g) for g in gt])
+    out.projection = proj
+    return out
+
+
 # ---- C++-only functions of the path, exposed for completeness ---------------------------------
 def FlowDirectionsD8(dem: rdarray) -> rdarray:
     """richdem::d8_flow_directions (flowmet/d8_flowdirs.hpp:96-123): uint8 codes 0..8, 255 NoData."""

@@ -8,6 +8,11 @@ import re
 import numpy as np
 import pytest
 
+
+def oracle_have_ref():
+    import oracle
+    return oracle.have_ref()
+
 import richdem_b200 as rd
 from richdem_b200 import _lib, build
 
@@ -185,3 +190,34 @@ def test_scoped_param_restores_what_the_process_had_set():
     finally:
         _lib.reset_params()
     assert _lib._param_values == {}
+
+
+@pytest.mark.skipif(not oracle_have_ref(), reason="oracle/_ref not built (no reference tree)")
+def test_native_cache_format_round_trips_with_the_reference(tmp_path):
+    """SURVEY 8f-4: SaveNative / LoadNative speak richdem::Array2D's cache format (common/Array2D.hpp:209-281): a file
+    written by the reference is read here and a file written here is read by the reference, bit for bit, metadata included."""
+    import oracle
+    import richdem_b200 as rd
+    R = oracle.ref()
+    dem = oracle.fbm_terrain(37, 53, seed=3)
+    dem[5:9, 7:20] = -9999.0
+    gt = [100.0, 30.0, 0.0, 2000.0, 0.0, -20.0]
+    a = str(tmp_path / "from_reference.rd")
+    R.save_native(a, dem, -9999.0, gt, "EPSG:26915")
+    got = rd.LoadNative(a)
+    assert got.dtype == np.float32 and got.shape == dem.shape and np.array_equal(np.asarray(got).view(np.uint32), dem.view(np.uint32))
+    assert got.no_data == -9999.0 and list(got.geotransform) == gt and got.projection == "EPSG:26915"
+    b = str(tmp_path / "from_python.rd")
+    src = rd.rdarray(dem.copy(), no_data=-9999.0, geotransform=gt)
+    src.projection = "EPSG:26915"
+    rd.SaveNative(src, b)
+    with open(a, "rb") as fa, open(b, "rb") as fb:
+        assert fa.read() == fb.read(), "byte-identical files (the reference has not counted the data cells either)"
+    data, nd, gt2, proj = R.load_native(b)
+    assert np.array_equal(data.view(np.uint32), dem.view(np.uint32)) and nd == -9999.0 and list(gt2) == gt and proj == "EPSG:26915"
+    with pytest.raises(RuntimeError, match="truncated"):
+        with open(b, "rb") as fb:
+            blob = fb.read()
+        with open(b, "wb") as fb:
+            fb.write(blob[:-100])
+        rd.LoadNative(b)
