@@ -42,6 +42,14 @@ void ref_fill_depressions_d4_f32(float *dem, int w, int h) {
   FillDepressions<Topology::D4>(a);
 }
 
+// depressions/Barnes2014.hpp:336-420 (pyrichdem FillDepressions(epsilon=True)); not on the B200 path -- kept in the checker to
+// show what its result depends on (tests/test_oracle.py::test_epsilon_fill_depends_on_the_queue_order)
+void ref_priority_flood_epsilon_f32(float *dem, int w, int h, float nodata) {
+  Array2D<float> a(dem, w, h);
+  a.setNoData(nodata);
+  PriorityFloodEpsilon_Barnes2014<Topology::D8>(a);
+}
+
 // depressions/Zhou2016.hpp:125-191 (the function pyrichdem binds, pywrapper.hpp:32)
 void ref_priority_flood_zhou2016_f32(float *dem, int w, int h) {
   Array2D<float> a(dem, w, h);

@@ -209,3 +209,58 @@ def test_terrain_attributes_port_matches_compiled_reference_live(port):
             b = R.terrain_attribute(dem, attrib, ND, zs, cell, nd_out)
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (attrib, zs)
             assert np.all(a[dem == ND] == nd_out)
+
+
+# ---- why the epsilon fill is not on the B200 path -----------------------------------------------------------
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (no reference tree)")
+def test_epsilon_fill_depends_on_the_queue_order():
+    """PriorityFloodEpsilon_Barnes2014 (depressions/Barnes2014.hpp:336-420) drains its FIFO "pit" queue before it looks at the
+    priority queue again (:377-392), so a pit cell can be closed from a neighbour that is not its cheapest one: the result is
+    NOT the order-free fixed point W = max(Z, min_n nextafter(W_n)) a parallel relaxation converges to -- it lies up to a few
+    float ulps above it in a few cells.  A bit-exact GPU version would have to replay the serial queue order; the row stays
+    on the reference's CPU template."""
+    import ctypes as C
+    import heapq
+    R = oracle.ref()
+    f = R.lib.ref_priority_flood_epsilon_f32
+    f.argtypes = [np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), C.c_int, C.c_int, C.c_float]
+    f.restype = None
+
+    def fixed_point(z):  # Dijkstra on the cost max(Z(c), nextafter(cost of the predecessor))
+        h, w = z.shape
+        W = np.full((h, w), np.inf, np.float32)
+        done = np.zeros((h, w), bool)
+        pq = []
+        for y in range(h):
+            for x in range(w):
+                if y in (0, h - 1) or x in (0, w - 1):
+                    W[y, x] = z[y, x]
+                    heapq.heappush(pq, (float(z[y, x]), y, x))
+        while pq:
+            v, y, x = heapq.heappop(pq)
+            if done[y, x]:
+                continue
+            done[y, x] = True
+            up = np.nextafter(np.float32(v), np.float32(np.inf))
+            for yy in range(max(0, y - 1), min(h, y + 2)):
+                for xx in range(max(0, x - 1), min(w, x + 2)):
+                    if not done[yy, xx]:
+                        c = max(z[yy, xx], up)
+                        if c < W[yy, xx]:
+                            W[yy, xx] = c
+                            heapq.heappush(pq, (float(c), yy, xx))
+        return W
+
+    above, cells = 0, 0
+    for seed in (2, 5, 7):
+        z = oracle.fbm_terrain(60, 80, seed=seed, quantum=0.5)
+        ref = z.copy()
+        f(ref, 80, 60, ND)
+        fp = fixed_point(z)
+        d = ref.view(np.int32).astype(np.int64) - fp.view(np.int32).astype(np.int64)
+        assert d.min() >= 0, "the serial result is never below the order-free fixed point"
+        assert d.max() <= 16
+        above += int((d > 0).sum())
+        cells += z.size
+        assert np.array_equal(ref >= z, np.ones_like(z, bool))
+    assert 0 < above < cells // 100, (above, cells)
