@@ -139,8 +139,10 @@ struct CallScope {  // resets stats, times the whole call
 
 static void check_dims(int w, int h) {
   if (w <= 0 || h <= 0) fail("raster dimensions must be positive (got %d x %d)", w, h);
-  if ((int64_t)w * h > ((int64_t)1 << 31) - 1)
-    fail("rasters above 2^31-1 cells per GPU are not supported yet (got %d x %d); shard by rows", w, h);
+  // cell indices are 32-bit; the source scans of the accumulation walks bump a shared cursor by 1024 cells per warp, which may
+  // run past the last cell by one chunk per resident warp before every warp has seen the end: keep that inside an int
+  if ((int64_t)w * h > ((int64_t)1 << 31) - ((int64_t)1 << 25))
+    fail("rasters above 2^31 - 2^25 cells per GPU are not supported (got %d x %d); shard by rows", w, h);
 }
 
 template <class T>
