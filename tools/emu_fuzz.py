@@ -6,7 +6,7 @@ coarsely quantised / negative terrain, random NoData patches, random weights and
     RDB_EMU_SMS=3 RDB_EMU_CHAOS=5 python tools/emu_fuzz.py <seed> <seconds>
 
 (RDB_EMU_SMS: cooperative kernels as that many concurrent blocks; RDB_EMU_CHAOS: atomics yield at random.)
-Failing inputs are saved as /tmp/fuzz_fail_<seed>_<case>.npy.  Round 1: about 8 500 cases in all (pipeline and row-band protocols), 0 failures; the switch table follows the round-2 kernels.
+Failing inputs are saved as /tmp/fuzz_fail_<seed>_<case>.npy.  Round 1: about 8 500 cases in all (pipeline and row-band protocols), 0 failures; the switch table follows the round-2 kernels (round 2: 8 550 cases over 5 seeds with 1-5 concurrent blocks and random atomic interleavings, 0 failures).
 """
 import sys, os, ctypes as C, importlib.util, time, traceback
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
